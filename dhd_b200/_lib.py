@@ -1,0 +1,82 @@
+"""ctypes binding of libdhd_b200.so (the C-ABI in include/dhd_b200.h).
+
+There is NO fallback: if the shared library is missing or a call fails, a
+RuntimeError is raised.  The library is built in-tree by ``dhd_b200.build``.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libdhd_b200.so')
+
+MAX_PASSES = 4
+MAX_PLANES = 32
+LAYOUT_NHWC, LAYOUT_NCHW_COLLAPSE, LAYOUT_NCDHW = 0, 1, 2
+
+
+class MghsCfg(ctypes.Structure):
+    """struct dhd_mghs_cfg (include/dhd_b200.h)."""
+    _fields_ = [
+        ('B', ctypes.c_int32), ('N', ctypes.c_int32), ('D', ctypes.c_int32),
+        ('fH', ctypes.c_int32), ('fW', ctypes.c_int32), ('C', ctypes.c_int32),
+        ('Dx', ctypes.c_int32), ('Dy', ctypes.c_int32),
+        ('x_lower', ctypes.c_float), ('x_interval', ctypes.c_float), ('x_size', ctypes.c_float),
+        ('y_lower', ctypes.c_float), ('y_interval', ctypes.c_float), ('y_size', ctypes.c_float),
+        ('n_pass', ctypes.c_int32),
+        ('z_lower', ctypes.c_float * MAX_PASSES),
+        ('z_interval', ctypes.c_float * MAX_PASSES),
+        ('z_size', ctypes.c_float * MAX_PASSES),
+        ('dz', ctypes.c_int32 * MAX_PASSES),
+        ('mask_id', ctypes.c_int32 * MAX_PASSES),
+    ]
+
+
+_P = ctypes.c_void_p
+_SIGNATURES = {
+    'dhd_last_error': (ctypes.c_char_p, []),
+    'dhd_abi_version': (ctypes.c_int, []),
+    'dhd_bev_pool_v2_fwd': (ctypes.c_int, [ctypes.c_int, ctypes.c_int] + [_P] * 9),
+    'dhd_bev_pool_v2_bwd': (ctypes.c_int, [ctypes.c_int, ctypes.c_int] + [_P] * 11),
+    'dhd_height_to_mask': (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int, ctypes.c_int, _P, _P,
+                                          ctypes.c_int, _P, _P]),
+    'dhd_mghs_workspace_bytes': (ctypes.c_size_t, [ctypes.POINTER(MghsCfg)]),
+    'dhd_mghs_workspace_count_offset': (ctypes.c_size_t, [ctypes.POINTER(MghsCfg)]),
+    'dhd_mghs_prepare': (ctypes.c_int, [ctypes.POINTER(MghsCfg)] + [_P] * 10 + [ctypes.c_int, _P]),
+    'dhd_mghs_pool_fwd': (ctypes.c_int, [ctypes.POINTER(MghsCfg), _P, _P, _P, _P,
+                                         ctypes.POINTER(_P), ctypes.c_int, _P]),
+    'dhd_mghs_pool_bwd': (ctypes.c_int, [ctypes.POINTER(MghsCfg), _P, _P, _P, _P,
+                                         ctypes.POINTER(_P), ctypes.c_int, _P, _P, _P]),
+    'dhd_mghs_voxel_index': (ctypes.c_int, [ctypes.POINTER(MghsCfg), _P, _P, _P]),
+}
+
+_lib = None
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            'dhd_b200: %s is missing -- run `python -m dhd_b200.build` (or '
+            '__graft_entry__.build()). There is no CPU / PyTorch fallback.' % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)      # AttributeError if the .so is stale
+        fn.restype = res
+        fn.argtypes = args
+    if lib.dhd_abi_version() != 1:
+        raise RuntimeError('dhd_b200: ABI version mismatch, rebuild the library')
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().dhd_last_error().decode('utf-8', 'replace')
+        raise RuntimeError('dhd_b200.%s failed (code %d): %s' % (what, rc, msg))

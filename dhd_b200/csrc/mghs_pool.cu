@@ -1,0 +1,789 @@
+// Fused MGHS view-transform pool for sm_100a.
+//
+// Replaces, for all passes of MGHS.view_transform at once (reference:
+// projects/mmdet3d_plugin/models/necks/lss_heightmap.py:179-231, 261-371, 407-459 and
+// ops/bev_pool_v2/bev_pool.py:17-41,105):
+//   4x get_ego_coor, 4x (quantise + filter + argsort + run-length), 3x masked-feature copies,
+//   4x new_zeros, 4x bev_pool_v2_kernel, 4x permute().contiguous(), 4x collapse-Z cat.
+//
+// Pipeline (all on one stream, no host sync, CUDA-graph capturable):
+//   prepare : geom_count -> scan_local -> scan_blocks -> scatter [-> canonical order]
+//             bins every frustum point that lands in the shared x/y grid by BEV cell;
+//             depends on camera geometry only (cacheable: MGHS `accelerate`).
+//   pool    : cell-owner gather.  One warp owns one BEV cell, keeps the cell's whole
+//             output column (all z-planes of all passes, 64 channels) in registers, walks
+//             the cell's bin, and writes every output byte exactly once with full-line
+//             coalesced streaming stores -- zeros included.  No atomics, no memset,
+//             no layout copy.  HBM-write bound: algorithmic bytes == bytes stored.
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace dhd {
+
+constexpr int kC = 64;            // numC_Trans of every DHD config
+constexpr int kScanChunk = 4096;  // cells per scan block (1024 threads x 4)
+constexpr int kMaxScanBlocks = 1024;
+constexpr int kDetCap = 4096;     // longest bin that is put in canonical order
+
+struct WsLayout {
+  size_t cell_count, cell_start, blk_sum, blk_prefix, total_entries;
+  size_t pt_cell, pt_zb, pt_slot, entries, entries_tmp, bytes;
+  long F;
+  int ncell, ncell_pad, nblk;
+};
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static int ws_layout(const dhd_mghs_cfg* c, WsLayout* w) {
+  DHD_REQUIRE(c != nullptr, "cfg is null");
+  DHD_REQUIRE(c->C == kC, "this build supports C == 64 only");
+  DHD_REQUIRE(c->B > 0 && c->N > 0 && c->D > 0 && c->fH > 0 && c->fW > 0, "bad frustum shape");
+  DHD_REQUIRE(c->Dx > 0 && c->Dy > 0, "bad grid size");
+  DHD_REQUIRE(c->n_pass >= 1 && c->n_pass <= DHD_MAX_PASSES, "n_pass out of range");
+  int planes = 0;
+  for (int p = 0; p < c->n_pass; ++p) {
+    DHD_REQUIRE(c->dz[p] >= 1 && c->dz[p] <= 254, "dz out of range (1..254)");
+    DHD_REQUIRE(c->mask_id[p] >= 0 && c->mask_id[p] <= 127, "mask_id out of range");
+    planes += c->dz[p];
+  }
+  DHD_REQUIRE(planes <= DHD_MAX_PLANES, "sum of dz over passes exceeds DHD_MAX_PLANES");
+  const long F = (long)c->B * c->N * c->D * c->fH * c->fW;
+  const long ncell = (long)c->B * c->Dy * c->Dx;
+  DHD_REQUIRE(F < (1L << 30), "too many frustum points");
+  DHD_REQUIRE(ncell <= (long)kScanChunk * kMaxScanBlocks, "too many BEV cells");
+  w->F = F;
+  w->ncell = (int)ncell;
+  w->nblk = (int)((ncell + kScanChunk - 1) / kScanChunk);
+  w->ncell_pad = w->nblk * kScanChunk;
+  size_t o = 0;
+  w->cell_count = o;  o = align_up(o + (size_t)w->ncell_pad * 4, 256);
+  w->cell_start = o;  o = align_up(o + (size_t)w->ncell_pad * 4, 256);
+  w->blk_sum = o;     o = align_up(o + kMaxScanBlocks * 4, 256);
+  w->blk_prefix = o;  o = align_up(o + kMaxScanBlocks * 4, 256);
+  w->total_entries = o; o = align_up(o + 16, 256);
+  w->pt_cell = o;     o = align_up(o + (size_t)F * 4, 256);
+  w->pt_zb = o;       o = align_up(o + (size_t)F * 4, 256);
+  w->pt_slot = o;     o = align_up(o + (size_t)F * 4, 256);
+  w->entries = o;     o = align_up(o + (size_t)F * 16, 256);
+  w->entries_tmp = o; o = align_up(o + (size_t)F * 16, 256);
+  w->bytes = o;
+  return DHD_OK;
+}
+
+// ------------------------------------------------------------------------ prepare
+struct GeomParams {
+  dhd_mghs_cfg cfg;
+  const float *coor, *fu, *fv, *fd, *ipr, *ptr, *comb, *tr, *bda;
+  int* cell_count;
+  int* pt_cell;
+  uint32_t* pt_zb;
+  int* pt_slot;
+  int F, HW, DyDx;
+};
+
+// trunc-toward-zero voxel index of ((q - lower) / interval), reference .long() semantics
+// (lss_heightmap.py:331-333): subtract THEN divide, both correctly rounded, no reciprocal.
+__device__ __forceinline__ bool quantise(float q, float lower, float interval, float size, int* idx) {
+  const float g = __fdiv_rn(__fsub_rn(q, lower), interval);
+  if (!(fabsf(g) < 1.0e9f)) return false;  // NaN / inf / absurd -> never kept
+  const int i = (int)g;                     // cvt.rzi
+  *idx = i;
+  return i >= 0 && (float)i < size;         // kept test against the fp32 grid_size (340-342)
+}
+
+// 3x3 (row-major) times vector with separately rounded products and left-to-right adds:
+// the operation order torch's CPU batched matmul produces for the reference's get_ego_coor
+// (pinned bitwise by tests/test_oracle_vs_reference.py).
+__device__ __forceinline__ void matvec_rn(const float* __restrict__ m, float x, float y, float z,
+                                          float* ox, float* oy, float* oz) {
+  *ox = __fadd_rn(__fadd_rn(__fmul_rn(m[0], x), __fmul_rn(m[1], y)), __fmul_rn(m[2], z));
+  *oy = __fadd_rn(__fadd_rn(__fmul_rn(m[3], x), __fmul_rn(m[4], y)), __fmul_rn(m[5], z));
+  *oz = __fadd_rn(__fadd_rn(__fmul_rn(m[6], x), __fmul_rn(m[7], y)), __fmul_rn(m[8], z));
+}
+
+__global__ void __launch_bounds__(256) mghs_geom_count_kernel(const GeomParams P) {
+  const int pt = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pt >= P.F) return;
+  const dhd_mghs_cfg& c = P.cfg;
+  const int hw = pt % P.HW;
+  const int t = pt / P.HW;
+  const int d = t % c.D;
+  const int bn = t / c.D;
+  const int b = bn / c.N;
+  float qx, qy, qz;
+  if (P.coor != nullptr) {
+    qx = P.coor[(size_t)pt * 3 + 0];
+    qy = P.coor[(size_t)pt * 3 + 1];
+    qz = P.coor[(size_t)pt * 3 + 2];
+  } else {
+    // get_ego_coor, lss_heightmap.py:206-230
+    const float u = P.fu[hw % c.fW], v = P.fv[hw / c.fW], dd = P.fd[d];
+    const float* pt3 = P.ptr + bn * 3;
+    float x = __fsub_rn(u, pt3[0]), y = __fsub_rn(v, pt3[1]), z = __fsub_rn(dd, pt3[2]);
+    float rx, ry, rz;
+    matvec_rn(P.ipr + bn * 9, x, y, z, &rx, &ry, &rz);
+    x = __fmul_rn(rx, rz);
+    y = __fmul_rn(ry, rz);
+    z = rz;
+    matvec_rn(P.comb + bn * 9, x, y, z, &rx, &ry, &rz);
+    const float* tr = P.tr + bn * 3;
+    rx = __fadd_rn(rx, tr[0]);
+    ry = __fadd_rn(ry, tr[1]);
+    rz = __fadd_rn(rz, tr[2]);
+    matvec_rn(P.bda + b * 9, rx, ry, rz, &qx, &qy, &qz);
+  }
+  int ix = 0, iy = 0;
+  const bool kx = quantise(qx, c.x_lower, c.x_interval, c.x_size, &ix);
+  const bool ky = quantise(qy, c.y_lower, c.y_interval, c.y_size, &iy);
+  uint32_t zb = 0;
+  if (kx && ky) {
+#pragma unroll
+    for (int p = 0; p < DHD_MAX_PASSES; ++p) {
+      if (p < c.n_pass) {
+        int iz = 0;
+        if (quantise(qz, c.z_lower[p], c.z_interval[p], c.z_size[p], &iz))
+          zb |= (uint32_t)(iz + 1) << (8 * p);
+      }
+    }
+  }
+  int cell = -1, slot = 0;
+  if (zb != 0) {
+    cell = b * P.DyDx + iy * c.Dx + ix;
+    slot = atomicAdd(P.cell_count + cell, 1);
+  }
+  P.pt_cell[pt] = cell;
+  P.pt_zb[pt] = zb;
+  P.pt_slot[pt] = slot;
+}
+
+// exclusive scan of cell_count inside chunks of 4096 cells; chunk totals to blk_sum
+__global__ void __launch_bounds__(1024) mghs_scan_local_kernel(const int4* __restrict__ count,
+                                                               int4* __restrict__ start,
+                                                               int* __restrict__ blk_sum) {
+  __shared__ int wsum[32];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int4 v = count[(size_t)blockIdx.x * 1024 + tid];
+  const int tot = v.x + v.y + v.z + v.w;
+  int inc = tot;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int n = __shfl_up_sync(kFull, inc, o);
+    if (lane >= o) inc += n;
+  }
+  if (lane == 31) wsum[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    int w = wsum[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int n = __shfl_up_sync(kFull, w, o);
+      if (lane >= o) w += n;
+    }
+    wsum[lane] = w;
+  }
+  __syncthreads();
+  const int base = (wid > 0 ? wsum[wid - 1] : 0) + inc - tot;
+  int4 o4;
+  o4.x = base;
+  o4.y = base + v.x;
+  o4.z = o4.y + v.y;
+  o4.w = o4.z + v.z;
+  start[(size_t)blockIdx.x * 1024 + tid] = o4;
+  if (tid == 1023) blk_sum[blockIdx.x] = wsum[31];
+}
+
+__global__ void __launch_bounds__(1024) mghs_scan_blocks_kernel(const int* __restrict__ blk_sum,
+                                                                int* __restrict__ blk_prefix,
+                                                                int* __restrict__ total, int nblk) {
+  __shared__ int wsum[32];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int v = tid < nblk ? blk_sum[tid] : 0;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int n = __shfl_up_sync(kFull, inc, o);
+    if (lane >= o) inc += n;
+  }
+  if (lane == 31) wsum[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    int w = wsum[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int n = __shfl_up_sync(kFull, w, o);
+      if (lane >= o) w += n;
+    }
+    wsum[lane] = w;
+  }
+  __syncthreads();
+  const int ex = (wid > 0 ? wsum[wid - 1] : 0) + inc - v;
+  if (tid < nblk) blk_prefix[tid] = ex;
+  if (tid == 0) total[0] = wsum[31];
+}
+
+// entry = {frustum point id, pixel id, z-bytes (z+1 per pass, 0 = not in pass), cell}
+__global__ void __launch_bounds__(256)
+mghs_scatter_kernel(const int* __restrict__ pt_cell, const uint32_t* __restrict__ pt_zb,
+                    const int* __restrict__ pt_slot, const int* __restrict__ cell_start,
+                    const int* __restrict__ blk_prefix, int4* __restrict__ entries, int F, int HW,
+                    int DHW) {
+  const int pt = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pt >= F) return;
+  const int cell = pt_cell[pt];
+  if (cell < 0) return;
+  const int pos = cell_start[cell] + blk_prefix[cell / kScanChunk] + pt_slot[pt];
+  const int pix = (pt / DHW) * HW + pt % HW;
+  entries[pos] = make_int4(pt, pix, (int)pt_zb[pt], cell);
+}
+
+// Put every bin in ascending frustum-point order so the fp32 summation order of the pool
+// (and therefore its result) is reproducible run to run.  Rank by counting: O(n^2/32) per
+// bin, n is ~18 on average; bins longer than kDetCap are copied as they are.
+__global__ void __launch_bounds__(256)
+mghs_canonical_kernel(const int4* __restrict__ src, int4* __restrict__ dst,
+                      const int* __restrict__ cell_start, const int* __restrict__ cell_count,
+                      const int* __restrict__ blk_prefix, int ncell) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int cell = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; cell < ncell; cell += warps) {
+    const int n = cell_count[cell];
+    if (n == 0) continue;
+    const int s = cell_start[cell] + blk_prefix[cell / kScanChunk];
+    if (n <= 32) {
+      int4 e = make_int4(0x7fffffff, 0, 0, 0);
+      if (lane < n) e = src[s + lane];
+      int rank = 0;
+      for (int j = 0; j < n; ++j) rank += (__shfl_sync(kFull, e.x, j) < e.x) ? 1 : 0;
+      if (lane < n) dst[s + rank] = e;
+    } else if (n <= kDetCap) {
+      for (int base = 0; base < n; base += 32) {
+        const int i = base + lane;
+        int4 e = make_int4(0x7fffffff, 0, 0, 0);
+        if (i < n) e = src[s + i];
+        int rank = 0;
+        for (int j = 0; j < n; ++j) rank += (src[s + j].x < e.x) ? 1 : 0;
+        if (i < n) dst[s + rank] = e;
+      }
+    } else {
+      for (int i = lane; i < n; i += 32) dst[s + i] = src[s + i];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------- pool
+struct PoolParams {
+  const int4* entries;
+  const int* cell_start;
+  const int* cell_count;
+  const int* blk_prefix;
+  const float* depth;
+  const float* feat;
+  const int8_t* pixmask;
+  int ncell, nplanes, npass, DyDx;
+  int zoff[DHD_MAX_PASSES];
+  int mask_id[DHD_MAX_PASSES];
+  float* plane_ptr[DHD_MAX_PLANES];     // NHWC: out_p + z*C ; NCHW: out_p + z*zstride
+  int plane_cell_stride[DHD_MAX_PLANES];  // NHWC: floats between consecutive cells (dz_p*C)
+  long plane_b_stride[DHD_MAX_PLANES];    // NCHW: floats between samples
+  int plane_c_stride[DHD_MAX_PLANES];     // NCHW: floats between channels
+};
+
+template <int MAXZ>
+__device__ __forceinline__ void acc_plane(float2 (&acc)[MAXZ], int z, float d, float2 f) {
+  switch (z) {
+#define DHD_CASE(k)                                   \
+  case k:                                             \
+    if (k < MAXZ) {                                   \
+      acc[k < MAXZ ? k : 0].x = fmaf(f.x, d, acc[k < MAXZ ? k : 0].x); \
+      acc[k < MAXZ ? k : 0].y = fmaf(f.y, d, acc[k < MAXZ ? k : 0].y); \
+    }                                                 \
+    break;
+    DHD_CASE(0) DHD_CASE(1) DHD_CASE(2) DHD_CASE(3) DHD_CASE(4) DHD_CASE(5) DHD_CASE(6) DHD_CASE(7)
+    DHD_CASE(8) DHD_CASE(9) DHD_CASE(10) DHD_CASE(11) DHD_CASE(12) DHD_CASE(13) DHD_CASE(14)
+    DHD_CASE(15) DHD_CASE(16) DHD_CASE(17) DHD_CASE(18) DHD_CASE(19) DHD_CASE(20) DHD_CASE(21)
+    DHD_CASE(22) DHD_CASE(23) DHD_CASE(24) DHD_CASE(25) DHD_CASE(26) DHD_CASE(27) DHD_CASE(28)
+    DHD_CASE(29) DHD_CASE(30) DHD_CASE(31)
+#undef DHD_CASE
+    default: break;
+  }
+}
+
+// bitmask of output planes (after mask gating) one binned entry contributes to
+__device__ __forceinline__ uint32_t plane_bits(const PoolParams& P, uint32_t zb, int pm) {
+  uint32_t bits = 0;
+#pragma unroll
+  for (int p = 0; p < DHD_MAX_PASSES; ++p) {
+    if (p < P.npass) {
+      const uint32_t z = (zb >> (8 * p)) & 0xffu;
+      if (z != 0 && (P.mask_id[p] == 0 || P.mask_id[p] == pm)) bits |= 1u << (P.zoff[p] + z - 1);
+    }
+  }
+  return bits;
+}
+
+// Walk one cell's bin and accumulate depth*feat into the per-plane register column.
+// CH_SPLIT=false: lane owns channels (2l, 2l+1) (one 8-byte load, NHWC stores);
+// CH_SPLIT=true : lane owns channels (l, l+32) (two 4-byte loads, NCHW transpose staging).
+// Planes [k0, k0+MAXZ) only.
+template <int MAXZ, bool CH_SPLIT>
+__device__ __forceinline__ void gather_cell(const PoolParams& P, int cell, int lane, int k0,
+                                            float2 (&acc)[MAXZ]) {
+  const int n = P.cell_count[cell];
+  if (n == 0) return;
+  const int s = P.cell_start[cell] + P.blk_prefix[cell / kScanChunk];
+  const uint32_t kmask = (MAXZ >= 32) ? 0xffffffffu : ((1u << MAXZ) - 1u);
+  for (int base = 0; base < n; base += 32) {
+    const int m = min(32, n - base);
+    int pix = 0;
+    float dv = 0.f;
+    uint32_t bits = 0;
+    if (lane < m) {
+      const int4 e = P.entries[s + base + lane];
+      pix = e.y;
+      dv = P.depth[e.x];
+      const int pm = P.pixmask != nullptr ? (int)P.pixmask[pix] : 0;
+      bits = (plane_bits(P, (uint32_t)e.z, pm) >> k0) & kmask;
+    }
+    for (int j = 0; j < m; j += 4) {
+      int px[4];
+      float d[4];
+      uint32_t pb[4];
+      float2 f[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int jj = min(j + u, 31);
+        px[u] = __shfl_sync(kFull, pix, jj);
+        d[u] = __shfl_sync(kFull, dv, jj);
+        pb[u] = __shfl_sync(kFull, bits, jj);
+        if (j + u >= m) pb[u] = 0;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        f[u] = make_float2(0.f, 0.f);
+        if (pb[u] != 0) {
+          const float* row = P.feat + (size_t)px[u] * kC;
+          if (CH_SPLIT) {
+            f[u].x = __ldg(row + lane);
+            f[u].y = __ldg(row + lane + 32);
+          } else {
+            f[u] = __ldg(reinterpret_cast<const float2*>(row) + lane);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        uint32_t b = pb[u];
+        while (b != 0) {
+          const int z = __ffs(b) - 1;
+          b &= b - 1;
+          acc_plane<MAXZ>(acc, z, d[u], f[u]);
+        }
+      }
+    }
+  }
+}
+
+template <int MAXZ, int MINB>
+__global__ void __launch_bounds__(256, MINB) mghs_pool_nhwc_kernel(const PoolParams P) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int cell = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; cell < P.ncell; cell += warps) {
+    float2 acc[MAXZ];
+#pragma unroll
+    for (int k = 0; k < MAXZ; ++k) acc[k] = make_float2(0.f, 0.f);
+    gather_cell<MAXZ, false>(P, cell, lane, 0, acc);
+#pragma unroll
+    for (int k = 0; k < MAXZ; ++k) {
+      if (k < P.nplanes) {
+        float* dst = P.plane_ptr[k] + (size_t)cell * P.plane_cell_stride[k];
+        st_cs(reinterpret_cast<float2*>(dst) + lane, acc[k]);
+      }
+    }
+  }
+}
+
+// NCHW family: a CTA owns 32 consecutive cells of one sample and PZ output planes; each warp
+// gathers 4 cells, the register columns are transposed through a padded smem tile, and every
+// (plane, channel) row leaves as one aligned 128-byte streaming store.
+template <int PZ>
+__global__ void __launch_bounds__(256) mghs_pool_nchw_kernel(const PoolParams P, int tiles_per_b) {
+  extern __shared__ float stage[];  // [PZ*64][33]
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int b = blockIdx.x / tiles_per_b;
+  const int cell0 = (blockIdx.x % tiles_per_b) * 32;
+  const int k0 = blockIdx.y * PZ;
+#pragma unroll 1
+  for (int q = 0; q < 4; ++q) {
+    const int ct = wid * 4 + q;
+    float2 acc[PZ];
+#pragma unroll
+    for (int k = 0; k < PZ; ++k) acc[k] = make_float2(0.f, 0.f);
+    if (cell0 + ct < P.DyDx) gather_cell<PZ, true>(P, b * P.DyDx + cell0 + ct, lane, k0, acc);
+#pragma unroll
+    for (int k = 0; k < PZ; ++k) {
+      stage[(k * kC + lane) * 33 + ct] = acc[k].x;
+      stage[(k * kC + lane + 32) * 33 + ct] = acc[k].y;
+    }
+  }
+  __syncthreads();
+  const bool in = cell0 + lane < P.DyDx;
+  for (int r = wid; r < PZ * kC; r += 8) {
+    const int k = k0 + r / kC, ch = r % kC;
+    if (k < P.nplanes && in) {
+      float* dst = P.plane_ptr[k] + (size_t)b * P.plane_b_stride[k] +
+                   (size_t)ch * P.plane_c_stride[k] + cell0 + lane;
+      st_cs(dst, stage[r * 33 + lane]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------ backward
+struct BwdParams {
+  dhd_mghs_cfg cfg;
+  const int* pt_cell;
+  const uint32_t* pt_zb;
+  const float* depth;
+  const float* feat;
+  const int8_t* pixmask;
+  const float* gout[DHD_MAX_PASSES];  // NHWC (b, y, x, z, c)
+  float* depth_grad;
+  float* feat_grad;
+  int npix, HW;
+};
+
+// One warp per image pixel (= one camera ray of D frustum points).  Gather formulation:
+// depth_grad[pt] = sum_passes <g[voxel(pt)], feat[pix]>, feat_grad[pix] = sum_pt,passes
+// g[voxel(pt)] * depth[pt]; masked passes contribute only where the pixel carries the mask
+// (the product rule of `tran_feat * mask`, lss_heightmap.py:436-442).  No atomics.
+__global__ void __launch_bounds__(256) mghs_pool_bwd_nhwc_kernel(const BwdParams P) {
+  const dhd_mghs_cfg& c = P.cfg;
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int pix = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; pix < P.npix; pix += warps) {
+    const int bn = pix / P.HW, hw = pix % P.HW;
+    const float2 f = __ldg(reinterpret_cast<const float2*>(P.feat + (size_t)pix * kC) + lane);
+    const int pm = P.pixmask != nullptr ? (int)P.pixmask[pix] : 0;
+    uint32_t live = 0;  // passes this pixel feeds
+#pragma unroll
+    for (int p = 0; p < DHD_MAX_PASSES; ++p)
+      if (p < c.n_pass && (c.mask_id[p] == 0 || c.mask_id[p] == pm)) live |= 1u << p;
+    float2 fg = make_float2(0.f, 0.f);
+    for (int d0 = 0; d0 < c.D; d0 += 32) {
+      const int m = min(32, c.D - d0);
+      int cell = -1;
+      uint32_t zb = 0;
+      float dv = 0.f;
+      if (lane < m) {
+        const int pt = (bn * c.D + d0 + lane) * P.HW + hw;
+        cell = P.pt_cell[pt];
+        zb = P.pt_zb[pt];
+        dv = P.depth[pt];
+      }
+      float mine = 0.f;  // lane j keeps depth_grad of point d0+j
+      for (int j = 0; j < m; ++j) {
+        const int cj = __shfl_sync(kFull, cell, j);
+        const uint32_t zj = __shfl_sync(kFull, zb, j);
+        const float dj = __shfl_sync(kFull, dv, j);
+        float dot = 0.f;
+        if (cj >= 0) {
+#pragma unroll
+          for (int p = 0; p < DHD_MAX_PASSES; ++p) {
+            const uint32_t z = (zj >> (8 * p)) & 0xffu;
+            if (p < c.n_pass && z != 0 && ((live >> p) & 1u)) {
+              const float* row = P.gout[p] + ((size_t)cj * c.dz[p] + (z - 1)) * kC;
+              const float2 g = __ldg(reinterpret_cast<const float2*>(row) + lane);
+              dot = fmaf(g.x, f.x, dot);
+              dot = fmaf(g.y, f.y, dot);
+              fg.x = fmaf(g.x, dj, fg.x);
+              fg.y = fmaf(g.y, dj, fg.y);
+            }
+          }
+        }
+        dot = warp_sum(dot);
+        if (lane == j) mine = dot;
+      }
+      if (lane < m) P.depth_grad[(bn * c.D + d0 + lane) * P.HW + hw] = mine;
+    }
+    reinterpret_cast<float2*>(P.feat_grad + (size_t)pix * kC)[lane] = fg;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+mghs_voxel_index_kernel(const dhd_mghs_cfg c, const int* __restrict__ pt_cell,
+                        const uint32_t* __restrict__ pt_zb, int* __restrict__ ranks, int F,
+                        int DyDx) {
+  const int pt = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pt >= F) return;
+  const int cell = pt_cell[pt];
+  const uint32_t zb = pt_zb[pt];
+  for (int p = 0; p < c.n_pass; ++p) {
+    const int z = (int)((zb >> (8 * p)) & 0xffu);
+    int r = -1;
+    if (cell >= 0 && z != 0) {
+      const int b = cell / DyDx, yx = cell % DyDx;
+      r = b * (c.dz[p] * DyDx) + (z - 1) * DyDx + yx;
+    }
+    ranks[(size_t)p * F + pt] = r;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+height_to_mask_kernel(const float* __restrict__ height, int npix, int H, int HW,
+                      const float* __restrict__ height_range, const float* __restrict__ thr,
+                      int n_mask, int8_t* __restrict__ pixmask) {
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= npix) return;
+  const int bn = pix / HW, hw = pix % HW;
+  const float* col = height + (size_t)bn * H * HW + hw;
+  float best = col[0];
+  int arg = 0;
+  for (int k = 1; k < H; ++k) {  // first maximum wins, as torch.argmax
+    const float v = col[(size_t)k * HW];
+    if (v > best) {
+      best = v;
+      arg = k;
+    }
+  }
+  const float h = height_range[arg];
+  int id = 0;
+  for (int k = 0; k < n_mask; ++k)
+    if (h >= thr[k] && h < thr[k + 1]) id = k + 1;  // lss_heightmap.py:561-563, fp32 compares
+  pixmask[pix] = (int8_t)id;
+}
+
+// integer tuning knob read once from the environment (bench / profiling experiments only)
+static int tuning(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v != nullptr && *v != 0 ? atoi(v) : dflt;
+}
+
+static int fill_pool_params(const dhd_mghs_cfg* cfg, const WsLayout& w, const void* workspace,
+                            PoolParams* P) {
+  const char* ws = (const char*)workspace;
+  P->entries = (const int4*)(ws + w.entries);
+  P->cell_start = (const int*)(ws + w.cell_start);
+  P->cell_count = (const int*)(ws + w.cell_count);
+  P->blk_prefix = (const int*)(ws + w.blk_prefix);
+  P->ncell = w.ncell;
+  P->npass = cfg->n_pass;
+  P->DyDx = cfg->Dy * cfg->Dx;
+  int off = 0;
+  for (int p = 0; p < DHD_MAX_PASSES; ++p) {
+    P->zoff[p] = off;
+    P->mask_id[p] = p < cfg->n_pass ? cfg->mask_id[p] : 0;
+    if (p < cfg->n_pass) off += cfg->dz[p];
+  }
+  P->nplanes = off;
+  return DHD_OK;
+}
+
+}  // namespace dhd
+
+using namespace dhd;
+
+extern "C" size_t dhd_mghs_workspace_bytes(const dhd_mghs_cfg* cfg) {
+  WsLayout w;
+  if (ws_layout(cfg, &w) != DHD_OK) return 0;
+  return w.bytes;
+}
+
+extern "C" size_t dhd_mghs_workspace_count_offset(const dhd_mghs_cfg* cfg) {
+  WsLayout w;
+  if (ws_layout(cfg, &w) != DHD_OK) return 0;
+  return w.total_entries;
+}
+
+extern "C" int dhd_mghs_prepare(const dhd_mghs_cfg* cfg, const float* coor, const float* frustum_u,
+                                const float* frustum_v, const float* frustum_d,
+                                const float* inv_post_rot, const float* post_tran,
+                                const float* combine, const float* trans, const float* bda,
+                                void* workspace, int deterministic, void* stream) {
+  WsLayout w;
+  int rc = ws_layout(cfg, &w);
+  if (rc != DHD_OK) return rc;
+  DHD_REQUIRE(workspace != nullptr, "workspace is null");
+  DHD_REQUIRE(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
+  if (coor == nullptr)
+    DHD_REQUIRE(frustum_u && frustum_v && frustum_d && inv_post_rot && post_tran && combine &&
+                    trans && bda, "camera geometry pointers are null and no coor given");
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = (char*)workspace;
+  cudaError_t e = cudaMemsetAsync(ws + w.cell_count, 0, (size_t)w.ncell_pad * 4, st);
+  if (e != cudaSuccess) return fail((int)e, "%s: %ld", "memset(cell_count)", (long)e);
+
+  GeomParams G;
+  G.cfg = *cfg;
+  G.coor = coor; G.fu = frustum_u; G.fv = frustum_v; G.fd = frustum_d;
+  G.ipr = inv_post_rot; G.ptr = post_tran; G.comb = combine; G.tr = trans; G.bda = bda;
+  G.cell_count = (int*)(ws + w.cell_count);
+  G.pt_cell = (int*)(ws + w.pt_cell);
+  G.pt_zb = (uint32_t*)(ws + w.pt_zb);
+  G.pt_slot = (int*)(ws + w.pt_slot);
+  G.F = (int)w.F;
+  G.HW = cfg->fH * cfg->fW;
+  G.DyDx = cfg->Dy * cfg->Dx;
+  const int pblocks = (int)((w.F + 255) / 256);
+  mghs_geom_count_kernel<<<pblocks, 256, 0, st>>>(G);
+  DHD_CUDA_LAUNCH_CHECK("mghs_geom_count");
+  mghs_scan_local_kernel<<<w.nblk, 1024, 0, st>>>((const int4*)(ws + w.cell_count),
+                                                  (int4*)(ws + w.cell_start),
+                                                  (int*)(ws + w.blk_sum));
+  DHD_CUDA_LAUNCH_CHECK("mghs_scan_local");
+  mghs_scan_blocks_kernel<<<1, 1024, 0, st>>>((const int*)(ws + w.blk_sum),
+                                              (int*)(ws + w.blk_prefix),
+                                              (int*)(ws + w.total_entries), w.nblk);
+  DHD_CUDA_LAUNCH_CHECK("mghs_scan_blocks");
+  int4* scatter_dst = (int4*)(ws + (deterministic ? w.entries_tmp : w.entries));
+  mghs_scatter_kernel<<<pblocks, 256, 0, st>>>(G.pt_cell, G.pt_zb, G.pt_slot,
+                                               (const int*)(ws + w.cell_start),
+                                               (const int*)(ws + w.blk_prefix), scatter_dst,
+                                               G.F, G.HW, cfg->D * G.HW);
+  DHD_CUDA_LAUNCH_CHECK("mghs_scatter");
+  if (deterministic) {
+    const int blocks = min((w.ncell + 7) / 8, sm_count() * 8);
+    mghs_canonical_kernel<<<blocks, 256, 0, st>>>((const int4*)(ws + w.entries_tmp),
+                                                  (int4*)(ws + w.entries),
+                                                  (const int*)(ws + w.cell_start),
+                                                  (const int*)(ws + w.cell_count),
+                                                  (const int*)(ws + w.blk_prefix), w.ncell);
+    DHD_CUDA_LAUNCH_CHECK("mghs_canonical");
+  }
+  return DHD_OK;
+}
+
+extern "C" int dhd_mghs_pool_fwd(const dhd_mghs_cfg* cfg, const float* depth, const float* feat,
+                                 const int8_t* pixmask, const void* workspace,
+                                 float* const* out_host, int layout, void* stream) {
+  WsLayout w;
+  int rc = ws_layout(cfg, &w);
+  if (rc != DHD_OK) return rc;
+  DHD_REQUIRE(depth && feat && workspace && out_host, "null pointer");
+  bool masked = false;
+  for (int p = 0; p < cfg->n_pass; ++p) {
+    DHD_REQUIRE(out_host[p] != nullptr, "output pointer is null");
+    masked |= cfg->mask_id[p] != 0;
+  }
+  DHD_REQUIRE(!masked || pixmask != nullptr, "a pass is masked but pixmask is null");
+  PoolParams P;
+  fill_pool_params(cfg, w, workspace, &P);
+  P.depth = depth;
+  P.feat = feat;
+  P.pixmask = pixmask;
+  const long DyDx = (long)cfg->Dy * cfg->Dx;
+  for (int p = 0, k = 0; p < cfg->n_pass; ++p) {
+    for (int z = 0; z < cfg->dz[p]; ++z, ++k) {
+      if (layout == DHD_LAYOUT_NHWC) {
+        P.plane_ptr[k] = out_host[p] + (size_t)z * kC;
+        P.plane_cell_stride[k] = cfg->dz[p] * kC;
+        P.plane_b_stride[k] = 0;
+        P.plane_c_stride[k] = 0;
+      } else if (layout == DHD_LAYOUT_NCHW_COLLAPSE) {
+        P.plane_ptr[k] = out_host[p] + (size_t)z * kC * DyDx;
+        P.plane_cell_stride[k] = 0;
+        P.plane_b_stride[k] = (long)cfg->dz[p] * kC * DyDx;
+        P.plane_c_stride[k] = (int)DyDx;
+      } else if (layout == DHD_LAYOUT_NCDHW) {
+        P.plane_ptr[k] = out_host[p] + (size_t)z * DyDx;
+        P.plane_cell_stride[k] = 0;
+        P.plane_b_stride[k] = (long)cfg->dz[p] * kC * DyDx;
+        P.plane_c_stride[k] = (int)(cfg->dz[p] * DyDx);
+      } else {
+        return fail(DHD_EINVAL, "%s: %ld", "unknown layout", (long)layout);
+      }
+    }
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (layout == DHD_LAYOUT_NHWC) {
+    // grid = one full wave of resident blocks (MINB per SM); warps stride over the cells
+    const int minb = tuning("DHD_POOL_MINB", 3);
+    const int need = (w.ncell + 7) / 8;
+#define DHD_LAUNCH_NHWC(MAXZ, MINB)                                            \
+  mghs_pool_nhwc_kernel<MAXZ, MINB><<<min(need, sm_count() * MINB), 256, 0, st>>>(P)
+    if (P.nplanes <= 8) DHD_LAUNCH_NHWC(8, 4);
+    else if (P.nplanes <= 17) {
+      if (minb >= 4) DHD_LAUNCH_NHWC(17, 4);
+      else if (minb == 3) DHD_LAUNCH_NHWC(17, 3);
+      else DHD_LAUNCH_NHWC(17, 2);
+    } else DHD_LAUNCH_NHWC(32, 2);
+#undef DHD_LAUNCH_NHWC
+    DHD_CUDA_LAUNCH_CHECK("mghs_pool_nhwc");
+  } else {
+    constexpr int PZ = 6;
+    const int tiles_per_b = (int)((DyDx + 31) / 32);
+    const size_t smem = (size_t)PZ * kC * 33 * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(mghs_pool_nchw_kernel<PZ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)smem);
+      attr_set = true;
+    }
+    dim3 grid(cfg->B * tiles_per_b, (P.nplanes + PZ - 1) / PZ);
+    mghs_pool_nchw_kernel<PZ><<<grid, 256, smem, st>>>(P, tiles_per_b);
+    DHD_CUDA_LAUNCH_CHECK("mghs_pool_nchw");
+  }
+  return DHD_OK;
+}
+
+extern "C" int dhd_mghs_pool_bwd(const dhd_mghs_cfg* cfg, const float* depth, const float* feat,
+                                 const int8_t* pixmask, const void* workspace,
+                                 const float* const* gout_host, int layout, float* depth_grad,
+                                 float* feat_grad, void* stream) {
+  WsLayout w;
+  int rc = ws_layout(cfg, &w);
+  if (rc != DHD_OK) return rc;
+  DHD_REQUIRE(depth && feat && workspace && gout_host && depth_grad && feat_grad, "null pointer");
+  if (layout != DHD_LAYOUT_NHWC)
+    return fail(DHD_EUNSUPPORTED, "%s", "pool_bwd: only DHD_LAYOUT_NHWC gradients are supported");
+  BwdParams P;
+  P.cfg = *cfg;
+  const char* ws = (const char*)workspace;
+  P.pt_cell = (const int*)(ws + w.pt_cell);
+  P.pt_zb = (const uint32_t*)(ws + w.pt_zb);
+  P.depth = depth;
+  P.feat = feat;
+  P.pixmask = pixmask;
+  bool masked = false;
+  for (int p = 0; p < DHD_MAX_PASSES; ++p) {
+    P.gout[p] = p < cfg->n_pass ? gout_host[p] : nullptr;
+    if (p < cfg->n_pass) {
+      DHD_REQUIRE(gout_host[p] != nullptr, "gradient pointer is null");
+      masked |= cfg->mask_id[p] != 0;
+    }
+  }
+  DHD_REQUIRE(!masked || pixmask != nullptr, "a pass is masked but pixmask is null");
+  P.depth_grad = depth_grad;
+  P.feat_grad = feat_grad;
+  P.HW = cfg->fH * cfg->fW;
+  P.npix = cfg->B * cfg->N * P.HW;
+  const int blocks = min((P.npix + 7) / 8, sm_count() * 8);
+  mghs_pool_bwd_nhwc_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(P);
+  DHD_CUDA_LAUNCH_CHECK("mghs_pool_bwd_nhwc");
+  return DHD_OK;
+}
+
+extern "C" int dhd_mghs_voxel_index(const dhd_mghs_cfg* cfg, const void* workspace,
+                                    int32_t* ranks_out, void* stream) {
+  WsLayout w;
+  int rc = ws_layout(cfg, &w);
+  if (rc != DHD_OK) return rc;
+  DHD_REQUIRE(workspace && ranks_out, "null pointer");
+  const char* ws = (const char*)workspace;
+  mghs_voxel_index_kernel<<<(int)((w.F + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      *cfg, (const int*)(ws + w.pt_cell), (const uint32_t*)(ws + w.pt_zb), ranks_out, (int)w.F,
+      cfg->Dy * cfg->Dx);
+  DHD_CUDA_LAUNCH_CHECK("mghs_voxel_index");
+  return DHD_OK;
+}
+
+extern "C" int dhd_height_to_mask(const float* height, int BN, int H, int HW,
+                                  const float* height_range, const float* thresholds, int n_mask,
+                                  int8_t* pixmask, void* stream) {
+  DHD_REQUIRE(height && height_range && thresholds && pixmask, "null pointer");
+  DHD_REQUIRE(BN > 0 && H > 0 && HW > 0 && n_mask >= 1 && n_mask <= 127, "bad shape");
+  const int npix = BN * HW;
+  height_to_mask_kernel<<<(npix + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      height, npix, H, HW, height_range, thresholds, n_mask, pixmask);
+  DHD_CUDA_LAUNCH_CHECK("height_to_mask");
+  return DHD_OK;
+}

@@ -1,0 +1,78 @@
+"""CPU tests of the drop-in boundary: the C-ABI library builds, loads and exports every
+symbol include/dhd_b200.h declares; host-only entry points validate their arguments."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='module')
+def lib():
+    from dhd_b200 import build, _lib
+    build.build()
+    return _lib.load()
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, 'include', 'dhd_b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(dhd_[a-z0-9_]+)\s*\(', text)))
+
+
+def test_header_symbols_exported(lib):
+    names = declared_symbols()
+    assert 'dhd_mghs_pool_fwd' in names and 'dhd_bev_pool_v2_fwd' in names
+    for n in names:
+        assert hasattr(lib, n), 'libdhd_b200.so does not export %s' % n
+    from dhd_b200 import _lib
+    assert sorted(_lib.exported_symbols()) == names
+
+
+def test_workspace_size_and_validation(lib):
+    from dhd_b200._lib import MghsCfg
+    cfg = MghsCfg()
+    cfg.B, cfg.N, cfg.D, cfg.fH, cfg.fW, cfg.C = 4, 6, 44, 16, 44, 64
+    cfg.Dx = cfg.Dy = 200
+    cfg.n_pass = 4
+    for p, dz in enumerate((1, 4, 4, 8)):
+        cfg.dz[p] = dz
+        cfg.mask_id[p] = p
+    n = lib.dhd_mghs_workspace_bytes(ctypes.byref(cfg))
+    F = 4 * 6 * 44 * 16 * 44
+    assert n >= F * (12 + 32) and n < F * 64 + (8 << 20)
+    cfg.C = 80                              # unsupported channel count -> 0 + message
+    assert lib.dhd_mghs_workspace_bytes(ctypes.byref(cfg)) == 0
+    assert b'C == 64' in lib.dhd_last_error()
+    cfg.C = 64
+    cfg.dz[3] = 40                          # 1+4+4+40 planes > DHD_MAX_PLANES
+    assert lib.dhd_mghs_workspace_bytes(ctypes.byref(cfg)) == 0
+
+
+def test_null_pointer_is_an_error_not_a_crash(lib):
+    rc = lib.dhd_bev_pool_v2_fwd(64, 5, None, None, None, None, None, None, None, None, None)
+    assert rc != 0 and b'null' in lib.dhd_last_error()
+    assert lib.dhd_bev_pool_v2_fwd(64, 0, None, None, None, None, None, None, None, None, None) == 0
+    assert lib.dhd_bev_pool_v2_fwd(300, 1, None, None, None, None, None, None, None, None, None) != 0
+
+
+def test_no_cpu_fallback():
+    """The product path refuses CPU tensors instead of silently computing elsewhere."""
+    import torch
+    from dhd_b200 import pool
+    z = torch.zeros(1)
+    i = torch.zeros(1, dtype=torch.int32)
+    with pytest.raises(RuntimeError, match='CUDA'):
+        pool.bev_pool_v2(z.view(1, 1, 1, 1, 1), z.view(1, 1, 1, 1, 1), i, i, i, (1, 1, 1, 1, 1), i, i)
+
+
+def test_product_never_imports_oracle():
+    for base in ('dhd_b200', 'projects'):
+        for dp, _, files in os.walk(os.path.join(ROOT, base)):
+            for f in files:
+                if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                    src = open(os.path.join(dp, f)).read()
+                    assert not re.search(r'^\s*(from|import)\s+oracle\b', src, flags=re.M), \
+                        '%s imports the oracle' % os.path.join(dp, f)
