@@ -172,13 +172,28 @@ class MghsPool:
         self.npoints = B * N * D * fH * fW
 
     # -- binning ---------------------------------------------------------------------
+    @staticmethod
+    def camera_matrices(sensor2ego, cam2imgs, post_rots, post_trans, bda):
+        """Per-camera 3x3s with the reference's own torch calls (lss_heightmap.py:207, 217):
+        inv(post_rots), post_trans, sensor2ego[:3,:3] @ inv(K), sensor2ego[:3,3], bda.
+        linalg.inv_ex is torch.inverse without the error-check host sync (same bits)."""
+        B, N = sensor2ego.shape[:2]
+        ipr = torch.linalg.inv_ex(post_rots).inverse.reshape(B * N, 3, 3)
+        comb = sensor2ego[:, :, :3, :3].matmul(torch.linalg.inv_ex(cam2imgs).inverse)
+        return (ipr.contiguous().float(), post_trans.reshape(B * N, 3).contiguous().float(),
+                comb.reshape(B * N, 3, 3).contiguous().float(),
+                sensor2ego[:, :, :3, 3].reshape(B * N, 3).contiguous().float(),
+                bda.contiguous().float())
+
     def prepare(self, frustum=None, sensor2ego=None, cam2imgs=None, post_rots=None,
-                post_trans=None, bda=None, coor=None, deterministic=True, workspace=None):
-        """Bin the frustum by BEV cell.  Either pass `coor` (B,N,D,fH,fW,3) -- the result of
-        the reference's get_ego_coor -- or the camera tensors, in which case the per-camera
-        3x3s are derived with the reference's own torch calls (lss_heightmap.py:207,217) and
-        the per-point transform runs fused in the kernel."""
-        dev = (coor if coor is not None else sensor2ego).device
+                post_trans=None, bda=None, coor=None, cam_mats=None, deterministic=True,
+                workspace=None):
+        """Bin the frustum by BEV cell.  Geometry source, in order of precedence:
+        `coor` (B,N,D,fH,fW,3), the result of the reference's get_ego_coor; `cam_mats`, the
+        tuple camera_matrices() returns; or the raw camera tensors.  With the last two the
+        per-point transform runs fused in the kernel."""
+        src = coor if coor is not None else (cam_mats[0] if cam_mats is not None else sensor2ego)
+        dev = src.device
         if dev.type != 'cuda':
             raise RuntimeError('dhd_b200.mghs: CUDA tensors required (no CPU fallback)')
         ws = workspace
@@ -191,17 +206,16 @@ class MghsPool:
                 raise ValueError('coor has the wrong number of points')
             args[0] = coor
         else:
-            B, N = self.B, self.N
+            if cam_mats is None:
+                cam_mats = self.camera_matrices(sensor2ego, cam2imgs, post_rots, post_trans, bda)
+            ipr, ptn, comb, tr, bda3 = [m.contiguous().float() for m in cam_mats]
+            if ipr.numel() != self.B * self.N * 9 or bda3.numel() != self.B * 9:
+                raise ValueError('camera matrices do not match (B, N)')
             f = frustum.to(device=dev, dtype=torch.float32)
             fu = f[0, 0, :, 0].contiguous()
             fv = f[0, :, 0, 1].contiguous()
             fd = f[:, 0, 0, 2].contiguous()
-            ipr = torch.inverse(post_rots).reshape(B * N, 3, 3).contiguous().float()
-            comb = sensor2ego[:, :, :3, :3].matmul(torch.inverse(cam2imgs))
-            comb = comb.reshape(B * N, 3, 3).contiguous().float()
-            tr = sensor2ego[:, :, :3, 3].reshape(B * N, 3).contiguous().float()
-            ptn = post_trans.reshape(B * N, 3).contiguous().float()
-            args[1:] = [fu, fv, fd, ipr, ptn, comb, tr, bda.contiguous().float()]
+            args[1:] = [fu, fv, fd, ipr, ptn, comb, tr, bda3]
         _lib.check(self._lib.dhd_mghs_prepare(
             ctypes.byref(self.cfg), *[_ptr(a) for a in args], _ptr(ws), int(bool(deterministic)),
             _stream()), 'mghs_prepare')

@@ -30,7 +30,7 @@ def sha(*tensors):
 
 
 def input_sha(inputs, depth, feat, height):
-    ts = list(inputs[1:]) + [depth, feat] + ([height] if height is not None else [])
+    ts = [depth, feat] + ([height] if height is not None else [])
     return sha(*ts)
 
 
@@ -70,6 +70,13 @@ def gen_case(ns, name, cfg, B, seed, full_outputs, flip_bda=False, n_sample=2048
         grids = [cfg['bev_grid']] + list(cfg['mask_grids'])
         data = dict(input_sha=np.array(input_sha(inputs, depth, feat, height)),
                     coor_sha=np.array(sha(coor)))
+        # the camera rig and the per-camera 3x3s the reference derives from it with torch
+        # (host libm / LAPACK results are stored, not regenerated, so they are the same everywhere)
+        for k, v in zip(('sensor2ego', 'ego2global', 'cam2imgs', 'post_rots', 'post_trans', 'bda'), inputs[1:]):
+            data['rig_' + k] = v.numpy()
+        for k, v in zip(('inv_post_rot', 'post_tran', 'combine', 'trans', 'bda'),
+                        O.camera_matrices(inputs[1], inputs[3], inputs[4], inputs[5], inputs[6])):
+            data['mat_' + k] = v.numpy()
         for p, g in enumerate(grids):
             r, n_int, n_kept = ref_ranks(m, coor, g)
             data['n_intervals_%d' % p] = np.array(n_int)

@@ -331,18 +331,25 @@ def synthetic_rig(B, ncams=6, input_size=(256, 704), src_size=(900, 1600), seed=
     return s2e, e2g, K, pr, pt, bda
 
 
-def synthetic_inputs(cfg, B, seed=0, flip_bda=False):
-    """Seeded synthetic tensors for one view-transform call (depth/height already softmaxed)."""
+def synthetic_inputs(cfg, B, seed=0, flip_bda=False, rig=None):
+    """Seeded synthetic tensors for one view-transform call.
+
+    Values are integers scaled by powers of two (exactly representable, no libm / vectorised
+    transcendental in the generator) so they are bit-identical on every host: depth in
+    (0, 1], context in [-4, 4), height scores in [0, 1).  depth / height are "already
+    softmaxed" as far as the view transform is concerned (it never re-normalises them)."""
     g = torch.Generator().manual_seed(seed + 1)
     N = cfg['ncams']
     h_in, w_in = cfg['input_size']
     fH, fW = h_in // cfg['downsample'], w_in // cfg['downsample']
     D = torch.arange(*cfg['depth']).shape[0]
-    rig = synthetic_rig(B, N, cfg['input_size'], seed=seed, flip_bda=flip_bda)
+    if rig is None:
+        rig = synthetic_rig(B, N, cfg['input_size'], seed=seed, flip_bda=flip_bda)
     x = torch.zeros(B, N, 1, fH, fW)        # only its shape is read by view_transform
-    depth = torch.randn(B * N, D, fH, fW, generator=g).softmax(1)
-    feat = torch.randn(B * N, cfg['C'], fH, fW, generator=g)
+    depth = torch.randint(1, 1025, (B * N, D, fH, fW), generator=g).float() * (1.0 / 1024.0)
+    feat = torch.randint(-2048, 2048, (B * N, cfg['C'], fH, fW), generator=g).float() * (1.0 / 512.0)
     height = None
     if cfg['height_range'] is not None:
-        height = torch.randn(B * N, len(cfg['height_range']), fH, fW, generator=g).softmax(1)
-    return (x,) + rig, depth, feat, height
+        height = torch.randint(0, 1 << 20, (B * N, len(cfg['height_range']), fH, fW),
+                               generator=g).float() * (1.0 / (1 << 20))
+    return (x,) + tuple(rig), depth, feat, height

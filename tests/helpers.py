@@ -23,13 +23,25 @@ def sha(*tensors):
     return h.hexdigest()
 
 
+RIG_KEYS = ('sensor2ego', 'ego2global', 'cam2imgs', 'post_rots', 'post_trans', 'bda')
+MAT_KEYS = ('inv_post_rot', 'post_tran', 'combine', 'trans', 'bda')
+
+
 def load_case(name):
+    """Seeded inputs (exact-arithmetic generator, checked by SHA) + the camera rig stored in
+    the fixture + the reference outputs."""
     cfg, B, seed, flip = CASES[name]
-    inputs, depth, feat, height = O.synthetic_inputs(cfg, B, seed=seed, flip_bda=flip)
     gold = np.load(os.path.join(GOLDEN, name + '.npz'))
-    ts = list(inputs[1:]) + [depth, feat] + ([height] if height is not None else [])
+    rig = tuple(torch.from_numpy(gold['rig_' + k]) for k in RIG_KEYS)
+    inputs, depth, feat, height = O.synthetic_inputs(cfg, B, seed=seed, flip_bda=flip, rig=rig)
+    ts = [depth, feat] + ([height] if height is not None else [])
     assert sha(*ts) == str(gold['input_sha']), 'seeded synthetic inputs differ from the ones the fixture was made with'
     return cfg, B, inputs, depth, feat, height, gold
+
+
+def fixture_mats(gold):
+    """Per-camera 3x3s the reference derived from the rig (computed where the fixture was made)."""
+    return [torch.from_numpy(gold['mat_' + k]) for k in MAT_KEYS]
 
 
 def grids_of(cfg):
