@@ -32,6 +32,7 @@ class MghsCfg(ctypes.Structure):
 
 
 _P = ctypes.c_void_p
+_I = ctypes.c_int
 _SIGNATURES = {
     'dhd_last_error': (ctypes.c_char_p, []),
     'dhd_abi_version': (ctypes.c_int, []),
@@ -47,6 +48,13 @@ _SIGNATURES = {
     'dhd_mghs_pool_bwd': (ctypes.c_int, [ctypes.POINTER(MghsCfg), _P, _P, _P, _P,
                                          ctypes.POINTER(_P), ctypes.c_int, _P, _P, _P]),
     'dhd_mghs_voxel_index': (ctypes.c_int, [ctypes.POINTER(MghsCfg), _P, _P, _P]),
+    'dhd_conv2d_fwd': (ctypes.c_int, [_P, _P]),
+    'dhd_pack_nchw_to_nhwc': (ctypes.c_int, [_P] + [_I] * 4 + [_P] + [_I] * 4 + [_P]),
+    'dhd_unpack_nhwc_to_nchw': (ctypes.c_int, [_P] + [_I] * 8 + [_P, _P]),
+    'dhd_mean_hw': (ctypes.c_int, [_P] + [_I] * 7 + [_P, _P]),
+    'dhd_linear_rows': (ctypes.c_int, [_P, _I, _I, _P, _P, _I, _I, _P, _P, _I, _P, _P]),
+    'dhd_sfa_mix': (ctypes.c_int, [_P] + [_I] * 7 + [_P, _P, _P] + [_I] * 4 + [_P]),
+    'dhd_dcn_im2col': (ctypes.c_int, [_P] + [_I] * 8 + [_P] + [_I] * 5 + [_P] + [_I] * 3 + [_P]),
 }
 
 _lib = None

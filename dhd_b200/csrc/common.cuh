@@ -40,6 +40,11 @@ __device__ __forceinline__ float warp_sum(float v) {
 __device__ __forceinline__ void st_cs(float2* p, float2 v) {
   asm volatile("st.global.cs.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
 }
+__device__ __forceinline__ void st_cs(float4* p, float4 v) {
+  asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
 __device__ __forceinline__ void st_cs(float* p, float v) {
   asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }

@@ -1,0 +1,305 @@
+// HBM-bound layout / elementwise kernels around the tensor-core convolutions:
+//   pack   : fp32 NCHW (what the reference modules exchange) -> NHWC split-bf16 activation
+//   mean   : per-image channel means (ASPP global pool depthnet.py:77-82, SFA squeeze mix.py:41)
+//   linear : tiny fp32 row-wise Linear (+act) for the camera-aware MLP / SE / SFA fc chains
+//            (depthnet.py:119-169, mix.py:20-25), M = B*N or B rows -- not tensor-core work
+//   sfa_mix: the two gated blends of channel_spatial_stage.forward (mix.py:44-57)
+//   dcn_im2col: bilinear deformable sampling of mmcv DeformConv2dPack (depthnet.py:466-477)
+//            into a [pixel][group][tap][64] bf16 matrix consumed by the GEMM kernel
+// All are pure streaming kernels: every byte is read once / written once, coalesced.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace dhd {
+
+// split v into `parts` bf16 values, store part p at dst[p * part_stride]
+__device__ __forceinline__ void store_parts(__nv_bfloat16* dst, float v, int parts, int part_stride) {
+  for (int p = 0; p < parts; ++p) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    dst[(size_t)p * part_stride] = h;
+    v -= __bfloat162float(h);
+  }
+}
+__device__ __forceinline__ void store_parts2(__nv_bfloat16* dst, float a, float b, int parts,
+                                             int part_stride) {
+  for (int p = 0; p < parts; ++p) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    *reinterpret_cast<__nv_bfloat162*>(dst + (size_t)p * part_stride) = h;
+    a -= __low2float(h);
+    b -= __high2float(h);
+  }
+}
+__device__ __forceinline__ float load_parts(const __nv_bfloat16* src, int parts, int part_stride) {
+  float v = 0.f;
+  for (int p = parts - 1; p >= 0; --p) v += __bfloat162float(src[(size_t)p * part_stride]);
+  return v;
+}
+
+// ---- pack: one block = 64 channels x 32 pixels of one image -------------------------------
+__global__ void __launch_bounds__(256)
+pack_nchw_to_nhwc_kernel(const float* __restrict__ in, int C, int HW, __nv_bfloat16* __restrict__ out,
+                         int ld, int coff, int part_stride, int parts) {
+  __shared__ float tile[64][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 64, n = blockIdx.z;
+  for (int c = ty; c < 64; c += 8) {
+    float v = 0.f;
+    if (c0 + c < C && p0 + tx < HW) v = in[((size_t)n * C + c0 + c) * HW + p0 + tx];
+    tile[c][tx] = v;
+  }
+  __syncthreads();
+  for (int p = ty; p < 32; p += 8) {
+    if (p0 + p >= HW) continue;
+    const int c = 2 * tx;
+    if (c0 + c >= C) continue;   // C is padded to a multiple of 64 by the caller's zero fill
+    __nv_bfloat16* dst = out + ((size_t)n * HW + p0 + p) * ld + coff + c0 + c;
+    if (c0 + c + 1 < C) store_parts2(dst, tile[c][p], tile[c + 1][p], parts, part_stride);
+    else store_parts(dst, tile[c][p], parts, part_stride);
+  }
+}
+
+// ---- unpack: NHWC split-bf16 -> fp32 NCHW (hand-off to reference-layout consumers) --------
+__global__ void __launch_bounds__(256)
+unpack_nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ in, int ld, int coff, int part_stride,
+                           int parts, int C, int HW, float* __restrict__ out) {
+  __shared__ float tile[64][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 64, n = blockIdx.z;
+  for (int p = ty; p < 32; p += 8) {
+    for (int h = 0; h < 2; ++h) {
+      const int c = tx + 32 * h;
+      float v = 0.f;
+      if (p0 + p < HW && c0 + c < C)
+        v = load_parts(in + ((size_t)n * HW + p0 + p) * ld + coff + c0 + c, parts, part_stride);
+      tile[c][p] = v;
+    }
+  }
+  __syncthreads();
+  for (int c = ty; c < 64; c += 8)
+    if (c0 + c < C && p0 + tx < HW) out[((size_t)n * C + c0 + c) * HW + p0 + tx] = tile[c][tx];
+}
+
+// ---- per-image channel mean of an NHWC split-bf16 activation -> fp32 [N][C] -----------------
+// grid (C/64, N, splits); partial sums are combined with atomicAdd into a pre-zeroed buffer
+// when splits > 1 (then scaled by a second tiny launch), or written directly when splits == 1.
+__global__ void __launch_bounds__(256)
+mean_hw_kernel(const __nv_bfloat16* __restrict__ in, int ld, int coff, int part_stride, int parts,
+               int C, int HW, float* __restrict__ out, float inv, int splits) {
+  __shared__ float red[4][64];
+  const int c = blockIdx.x * 64 + (threadIdx.x & 63), g = threadIdx.x >> 6, n = blockIdx.y;
+  const int per = (HW + splits - 1) / splits;
+  const int lo = blockIdx.z * per, hi = min(HW, lo + per);
+  float s = 0.f;
+  if (c < C)
+    for (int p = lo + g; p < hi; p += 4)
+      s += load_parts(in + ((size_t)n * HW + p) * ld + coff + c, parts, part_stride);
+  red[g][threadIdx.x & 63] = s;
+  __syncthreads();
+  if (g == 0 && c < C) {
+    s = red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x];
+    if (splits == 1) out[(size_t)n * C + c] = s * inv;
+    else atomicAdd(out + (size_t)n * C + c, s * inv);
+  }
+}
+
+// ---- y[r][o] = act(sum_k x[r][k] * w[o][k] + b[o]) (optionally x is first normalised by an
+// eval-mode BatchNorm1d: (x - mean) * rstd * gamma + beta); one warp per output element -------
+__global__ void __launch_bounds__(256)
+linear_rows_kernel(const float* __restrict__ x, int R, int K, const float* __restrict__ w,
+                   const float* __restrict__ b, int O, int act, const float* __restrict__ in_scale,
+                   const float* __restrict__ in_shift, float* __restrict__ y, int one_minus) {
+  const int lane = threadIdx.x & 31;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (gw >= R * O) return;
+  const int r = gw / O, o = gw % O;
+  float s = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    float v = x[(size_t)r * K + k];
+    if (in_scale != nullptr) v = v * in_scale[k] + in_shift[k];
+    s = fmaf(v, w[(size_t)o * K + k], s);
+  }
+  s = warp_sum(s);
+  if (lane == 0) {
+    if (b != nullptr) s += b[o];
+    if (act == DHD_ACT_RELU) s = fmaxf(s, 0.f);
+    else if (act == DHD_ACT_SIGMOID) s = 1.f / (1.f + expf(-s));
+    if (one_minus) s = 1.f - s;
+    y[(size_t)r * O + o] = s;
+  }
+}
+
+// ---- SFA blends (mix.py:44-57), op order and roundings as torch evaluates them -------------
+//   b1 = a1*bev ; v1 = (1-a1)*vox
+//   a2 == null : out = b1 + v1                         (fea_U_1, input of spacial_leanring)
+//   a2 != null : out = a2*b1 + (1-a2)*v1               (x_fuse), a2 = sigmoid already applied
+// x: NHWC split-bf16 with bev channels [0,C) and voxel channels [C,2C); a1: [N][C] fp32.
+__global__ void __launch_bounds__(256)
+sfa_mix_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int x_coff, int x_ps, int x_parts, int C,
+               long npix_total, int HW, const float* __restrict__ a1, const float* __restrict__ a2,
+               __nv_bfloat16* __restrict__ out, int o_ld, int o_coff, int o_ps, int o_parts) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;   // (pixel, channel pair)
+  const int cp = C / 2;
+  if (i >= npix_total * cp) return;
+  const long pix = i / cp;
+  const int c = (int)(i % cp) * 2;
+  const int n = (int)(pix / HW);
+  const __nv_bfloat16* xb = x + (size_t)pix * x_ld + x_coff + c;
+  float r[2];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const float bev = load_parts(xb + j, x_parts, x_ps);
+    const float vox = load_parts(xb + C + j, x_parts, x_ps);
+    const float g1 = a1[(size_t)n * C + c + j];
+    const float b1 = __fmul_rn(g1, bev);
+    const float v1 = __fmul_rn(__fsub_rn(1.f, g1), vox);
+    if (a2 == nullptr) {
+      r[j] = __fadd_rn(b1, v1);
+    } else {
+      const float g2 = a2[(size_t)pix * C + c + j];
+      r[j] = __fadd_rn(__fmul_rn(g2, b1), __fmul_rn(__fsub_rn(1.f, g2), v1));
+    }
+  }
+  store_parts2(out + (size_t)pix * o_ld + o_coff + c, r[0], r[1], o_parts, o_ps);
+}
+
+// ---- deformable im2col (mmcv DeformConv2dPack, deform_groups = 1, stride 1) -----------------
+// x: NHWC split-bf16 (C channels); offset: fp32 NHWC [pix][2*taps] with (dy, dx) interleaved per
+// tap; out: NHWC split-bf16 "image" with taps*C channels ordered [group][tap][C/groups] so that
+// each conv group's K range is contiguous.  One warp per (pixel, tap); lanes own channel pairs.
+__global__ void __launch_bounds__(256)
+dcn_im2col_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int x_coff, int x_ps, int x_parts,
+                  int C, int N, int H, int W, const float* __restrict__ offset, int off_ld, int ksize,
+                  int pad, int dil, int groups, __nv_bfloat16* __restrict__ out, int o_ld, int o_ps,
+                  int o_parts) {
+  const int lane = threadIdx.x & 31;
+  const long gw = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int taps = ksize * ksize;
+  const long total = (long)N * H * W * taps;
+  if (gw >= total) return;
+  const int t = (int)(gw % taps);
+  const long pix = gw / taps;
+  const int wx = (int)(pix % W), hy = (int)((pix / W) % H), n = (int)(pix / ((long)W * H));
+  const float dy = offset[(size_t)pix * off_ld + 2 * t], dx = offset[(size_t)pix * off_ld + 2 * t + 1];
+  const float sy = (float)(hy - pad + (t / ksize) * dil) + dy;
+  const float sx = (float)(wx - pad + (t % ksize) * dil) + dx;
+  const int cg = C / groups;
+  // bilinear weights; a sample is zero when it lies outside (-1, H) x (-1, W), and each corner
+  // outside the image contributes zero (mmcv dmcn_im2col_bilinear / torchvision bilinear_interpolate)
+  float w00 = 0.f, w01 = 0.f, w10 = 0.f, w11 = 0.f;
+  int y0 = 0, x0 = 0, y1 = 0, x1 = 0;
+  const bool inside = sy > -1.f && sx > -1.f && sy < (float)H && sx < (float)W;
+  if (inside) {
+    y0 = (int)floorf(sy);
+    x0 = (int)floorf(sx);
+    y1 = y0 + 1;
+    x1 = x0 + 1;
+    const float ly = sy - (float)y0, lx = sx - (float)x0, hy_ = 1.f - ly, hx_ = 1.f - lx;
+    w00 = hy_ * hx_; w01 = hy_ * lx; w10 = ly * hx_; w11 = ly * lx;
+  }
+  for (int c = 2 * lane; c < C; c += 64) {
+    float v[2] = {0.f, 0.f};
+    if (inside) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const __nv_bfloat16* base = x + (size_t)n * H * W * x_ld + x_coff + c + j;
+        float v00 = 0.f, v01 = 0.f, v10 = 0.f, v11 = 0.f;
+        if (y0 >= 0 && x0 >= 0) v00 = load_parts(base + ((size_t)y0 * W + x0) * x_ld, x_parts, x_ps);
+        if (y0 >= 0 && x1 <= W - 1) v01 = load_parts(base + ((size_t)y0 * W + x1) * x_ld, x_parts, x_ps);
+        if (y1 <= H - 1 && x0 >= 0) v10 = load_parts(base + ((size_t)y1 * W + x0) * x_ld, x_parts, x_ps);
+        if (y1 <= H - 1 && x1 <= W - 1) v11 = load_parts(base + ((size_t)y1 * W + x1) * x_ld, x_parts, x_ps);
+        v[j] = w00 * v00 + w01 * v01 + w10 * v10 + w11 * v11;
+      }
+    }
+    const int g = c / cg, cl = c % cg;
+    store_parts2(out + (size_t)pix * o_ld + (size_t)g * taps * cg + (size_t)t * cg + cl, v[0], v[1],
+                 o_parts, o_ps);
+  }
+}
+
+}  // namespace dhd
+
+using namespace dhd;
+
+extern "C" int dhd_pack_nchw_to_nhwc(const float* in, int N, int C, int H, int W, void* out, int out_ld,
+                                     int out_coff, int part_stride, int parts, void* stream) {
+  DHD_REQUIRE(in && out, "null pointer");
+  DHD_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0 && parts >= 1 && parts <= 3, "bad shape");
+  DHD_REQUIRE(out_ld % 2 == 0 && out_coff % 2 == 0 && part_stride % 2 == 0, "channel offsets must be even");
+  dim3 grid((H * W + 31) / 32, (C + 63) / 64, N);
+  pack_nchw_to_nhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+      in, C, H * W, (__nv_bfloat16*)out, out_ld, out_coff, part_stride, parts);
+  DHD_CUDA_LAUNCH_CHECK("pack_nchw_to_nhwc");
+  return DHD_OK;
+}
+
+extern "C" int dhd_unpack_nhwc_to_nchw(const void* in, int in_ld, int in_coff, int part_stride,
+                                       int parts, int N, int C, int H, int W, float* out, void* stream) {
+  DHD_REQUIRE(in && out, "null pointer");
+  DHD_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0 && parts >= 1 && parts <= 3, "bad shape");
+  dim3 grid((H * W + 31) / 32, (C + 63) / 64, N);
+  unpack_nhwc_to_nchw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)in, in_ld, in_coff, part_stride, parts, C, H * W, out);
+  DHD_CUDA_LAUNCH_CHECK("unpack_nhwc_to_nchw");
+  return DHD_OK;
+}
+
+extern "C" int dhd_mean_hw(const void* in, int in_ld, int in_coff, int part_stride, int parts, int N,
+                           int C, int HW, float* out, void* stream) {
+  DHD_REQUIRE(in && out, "null pointer");
+  DHD_REQUIRE(N > 0 && C > 0 && HW > 0 && parts >= 1 && parts <= 3, "bad shape");
+  const int cblocks = (C + 63) / 64;
+  int splits = 1;
+  if (HW > 4096) splits = min(64, max(1, (sm_count() * 4) / (cblocks * N)));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (splits > 1) {
+    cudaError_t e = cudaMemsetAsync(out, 0, (size_t)N * C * sizeof(float), st);
+    if (e != cudaSuccess) return fail((int)e, "%s: %ld", "memset(mean)", (long)e);
+  }
+  mean_hw_kernel<<<dim3(cblocks, N, splits), 256, 0, st>>>((const __nv_bfloat16*)in, in_ld, in_coff,
+                                                          part_stride, parts, C, HW, out,
+                                                          1.0f / (float)HW, splits);
+  DHD_CUDA_LAUNCH_CHECK("mean_hw");
+  return DHD_OK;
+}
+
+extern "C" int dhd_linear_rows(const float* x, int R, int K, const float* w, const float* b, int O,
+                               int act, const float* in_scale, const float* in_shift, int one_minus,
+                               float* y, void* stream) {
+  DHD_REQUIRE(x && w && y, "null pointer");
+  DHD_REQUIRE(R > 0 && K > 0 && O > 0, "bad shape");
+  DHD_REQUIRE((in_scale == nullptr) == (in_shift == nullptr), "in_scale / in_shift come together");
+  const long warps = (long)R * O;
+  linear_rows_kernel<<<(int)((warps * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      x, R, K, w, b, O, act, in_scale, in_shift, y, one_minus);
+  DHD_CUDA_LAUNCH_CHECK("linear_rows");
+  return DHD_OK;
+}
+
+extern "C" int dhd_sfa_mix(const void* x, int x_ld, int x_coff, int x_part_stride, int x_parts, int C,
+                           int N, int HW, const float* a1, const float* a2, void* out, int o_ld,
+                           int o_coff, int o_part_stride, int o_parts, void* stream) {
+  DHD_REQUIRE(x && a1 && out, "null pointer");
+  DHD_REQUIRE(C > 0 && C % 2 == 0 && N > 0 && HW > 0, "bad shape");
+  const long total = (long)N * HW * (C / 2);
+  sfa_mix_kernel<<<(int)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x, x_ld, x_coff, x_part_stride, x_parts, C, (long)N * HW, HW, a1, a2,
+      (__nv_bfloat16*)out, o_ld, o_coff, o_part_stride, o_parts);
+  DHD_CUDA_LAUNCH_CHECK("sfa_mix");
+  return DHD_OK;
+}
+
+extern "C" int dhd_dcn_im2col(const void* x, int x_ld, int x_coff, int x_part_stride, int x_parts, int C,
+                              int N, int H, int W, const float* offset, int off_ld, int ksize, int pad,
+                              int dilation, int groups, void* out, int o_ld, int o_part_stride,
+                              int o_parts, void* stream) {
+  DHD_REQUIRE(x && offset && out, "null pointer");
+  DHD_REQUIRE(C > 0 && groups > 0 && C % groups == 0 && (C / groups) % 2 == 0, "bad channel grouping");
+  DHD_REQUIRE(N > 0 && H > 0 && W > 0 && ksize >= 1 && ksize <= 3, "bad shape");
+  const long warps = (long)N * H * W * ksize * ksize;
+  dcn_im2col_kernel<<<(int)((warps * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x, x_ld, x_coff, x_part_stride, x_parts, C, N, H, W, offset, off_ld, ksize,
+      pad, dilation, groups, (__nv_bfloat16*)out, o_ld, o_part_stride, o_parts);
+  DHD_CUDA_LAUNCH_CHECK("dcn_im2col");
+  return DHD_OK;
+}

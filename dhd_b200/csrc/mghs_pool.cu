@@ -286,6 +286,8 @@ struct PoolParams {
   float* plane_ptr[DHD_MAX_PLANES];     // NHWC: out_p + z*C ; NCHW: out_p + z*zstride
   int plane_cell_stride[DHD_MAX_PLANES];  // NHWC: floats between consecutive cells (dz_p*C)
   long plane_b_stride[DHD_MAX_PLANES];    // NCHW: floats between samples
+  float* pass_ptr[DHD_MAX_PASSES];        // NHWC: base of pass p's output
+  int pass_q[DHD_MAX_PASSES];             // NHWC: float4 per cell of pass p (dz * C / 4)
   int plane_c_stride[DHD_MAX_PLANES];     // NCHW: floats between channels
 };
 
@@ -400,6 +402,90 @@ __global__ void __launch_bounds__(256, MINB) mghs_pool_nhwc_kernel(const PoolPar
         st_cs(reinterpret_cast<float2*>(dst) + lane, acc[k]);
       }
     }
+  }
+}
+
+// v2 of the NHWC pool: the cell's output column lives in SHARED memory (one private column
+// per warp, planes x 64 floats), so the plane index is a plain address (no register-array
+// switch), registers drop to ~40 and six blocks fit per SM.  Lane l accumulates channels
+// (2l, 2l+1) of every plane into its own smem slots -- no atomics, no barriers -- and the
+// column then leaves as 16-byte streaming stores, one contiguous dz*256-byte run per pass.
+// Empty cells (78 % of a DHD-S grid) skip shared memory and store zeros straight away.
+__global__ void __launch_bounds__(256, 6) mghs_pool_nhwc_smem_kernel(const PoolParams P) {
+  extern __shared__ float4 col_all[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  float4* col4 = col_all + (size_t)wid * P.nplanes * 16;     // [plane][16] float4
+  float2* col2 = reinterpret_cast<float2*>(col4);            // [plane][32] float2
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int nq = P.nplanes * 16;                             // float4 per column
+  int cell = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int n = cell < P.ncell ? __ldg(P.cell_count + cell) : 0;
+  while (cell < P.ncell) {
+    const int next = cell + warps;
+    const int n_next = next < P.ncell ? __ldg(P.cell_count + next) : 0;   // prefetch
+    if (n != 0) {
+      for (int i = lane; i < nq; i += 32) col4[i] = zero4;
+      __syncwarp();
+      const int s = __ldg(P.cell_start + cell) + __ldg(P.blk_prefix + cell / kScanChunk);
+      for (int base = 0; base < n; base += 32) {
+        const int m = min(32, n - base);
+        int pix = 0;
+        float dv = 0.f;
+        uint32_t bits = 0;
+        if (lane < m) {
+          const int4 e = __ldg(P.entries + s + base + lane);
+          pix = e.y;
+          dv = __ldg(P.depth + e.x);
+          const int pm = P.pixmask != nullptr ? (int)__ldg(P.pixmask + pix) : 0;
+          bits = plane_bits(P, (uint32_t)e.z, pm);
+        }
+        for (int j = 0; j < m; j += 4) {
+          int px[4];
+          float d[4];
+          uint32_t pb[4];
+          float2 f[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int jj = min(j + u, 31);
+            px[u] = __shfl_sync(kFull, pix, jj);
+            d[u] = __shfl_sync(kFull, dv, jj);
+            pb[u] = __shfl_sync(kFull, bits, jj);
+            if (j + u >= m) pb[u] = 0;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            f[u] = make_float2(0.f, 0.f);
+            if (pb[u] != 0) f[u] = __ldg(reinterpret_cast<const float2*>(P.feat + (size_t)px[u] * kC) + lane);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            uint32_t b = pb[u];
+            while (b != 0) {
+              const int z = __ffs(b) - 1;
+              b &= b - 1;
+              float2 a = col2[z * 32 + lane];
+              a.x = fmaf(f[u].x, d[u], a.x);
+              a.y = fmaf(f[u].y, d[u], a.y);
+              col2[z * 32 + lane] = a;
+            }
+          }
+        }
+      }
+      __syncwarp();
+    }
+#pragma unroll
+    for (int p = 0; p < DHD_MAX_PASSES; ++p) {
+      if (p < P.npass) {
+        const int q = P.pass_q[p];                                  // dz * 16 float4
+        float4* dst = reinterpret_cast<float4*>(P.pass_ptr[p]) + (size_t)cell * q;
+        const float4* src = col4 + P.zoff[p] * 16;
+        for (int i = lane; i < q; i += 32) st_cs(dst + i, n != 0 ? src[i] : zero4);
+      }
+    }
+    if (n != 0) __syncwarp();
+    cell = next;
+    n = n_next;
   }
 }
 
@@ -693,8 +779,26 @@ extern "C" int dhd_mghs_pool_fwd(const dhd_mghs_cfg* cfg, const float* depth, co
       }
     }
   }
+  for (int p = 0; p < DHD_MAX_PASSES; ++p) {
+    P.pass_ptr[p] = p < cfg->n_pass ? out_host[p] : nullptr;
+    P.pass_q[p] = p < cfg->n_pass ? cfg->dz[p] * kC / 4 : 0;
+  }
   cudaStream_t st = (cudaStream_t)stream;
-  if (layout == DHD_LAYOUT_NHWC) {
+  if (layout == DHD_LAYOUT_NHWC && tuning("DHD_POOL_V", 2) == 2) {
+    for (int p = 0; p < cfg->n_pass; ++p)
+      DHD_REQUIRE(((uintptr_t)out_host[p] & 15) == 0, "NHWC outputs must be 16-byte aligned");
+    const size_t smem = (size_t)8 * P.nplanes * kC * sizeof(float);
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+      cudaFuncSetAttribute(mghs_pool_nhwc_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)smem);
+      smem_set = smem;
+    }
+    const int per_sm = max(1, min(6, (int)((227 * 1024) / (smem + 1024))));
+    const int need = (w.ncell + 7) / 8;
+    mghs_pool_nhwc_smem_kernel<<<min(need, sm_count() * per_sm), 256, smem, st>>>(P);
+    DHD_CUDA_LAUNCH_CHECK("mghs_pool_nhwc_smem");
+  } else if (layout == DHD_LAYOUT_NHWC) {
     // grid = one full wave of resident blocks (MINB per SM); warps stride over the cells
     const int minb = tuning("DHD_POOL_MINB", 3);
     const int need = (w.ncell + 7) / 8;

@@ -1,0 +1,213 @@
+"""Host side of the dense layers of the hot path (ctypes over the C-ABI; torch only owns the
+device memory and the stream).
+
+Activations travel between layers as ``Act``: NHWC bf16 with up to three "parts" stacked on
+the channel axis (x = x0 + x1 + x2, each part bf16) -- 1 part is plain bf16, 3 parts carry a
+full fp32 value.  ``conv2d`` runs one implicit-GEMM convolution on the tcgen05 tensor cores
+(csrc/conv_igemm.cu) with the BatchNorm / bias / residual / activation / gate epilogue fused.
+
+Precision modes (``PRECISIONS``): the number of bf16 x bf16 MMAs issued per product term
+  'bf16'   1 part,  1 term   -- speed mode
+  'bf16x3' 2 parts, 3 terms  -- ~2^-16 relative
+  'fp32'   3 parts, 6 terms  -- fp32-grade; the mode the 1e-4 logits parity is checked in
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+ACT = {None: 0, 'none': 0, 'relu': 1, 'sigmoid': 2, 'softplus': 3, 'softmax': 4}
+PRECISIONS = {
+    'bf16': (1, [(0, 0)]),
+    'bf16x3': (2, [(0, 0), (0, 1), (1, 0)]),
+    'fp32': (3, [(0, 0), (0, 1), (1, 0), (0, 2), (1, 1), (2, 0)]),
+}
+MAX_TAPS, MAX_TERMS, MAX_SEGS = 9, 6, 2
+
+
+class ConvSeg(ctypes.Structure):
+    _fields_ = [
+        ('c_lo', ctypes.c_int32), ('c_hi', ctypes.c_int32), ('act', ctypes.c_int32),
+        ('out_f32', ctypes.c_void_p),
+        ('f32_sN', ctypes.c_int64), ('f32_sY', ctypes.c_int64), ('f32_sX', ctypes.c_int64),
+        ('f32_sC', ctypes.c_int64),
+        ('out_b16', ctypes.c_void_p),
+        ('b16_ld', ctypes.c_int32), ('b16_coff', ctypes.c_int32), ('b16_parts', ctypes.c_int32),
+        ('b16_part_stride', ctypes.c_int32),
+    ]
+
+
+class ConvDesc(ctypes.Structure):
+    _fields_ = [
+        ('N', ctypes.c_int32), ('H', ctypes.c_int32), ('W', ctypes.c_int32),
+        ('Cin', ctypes.c_int32), ('Cout', ctypes.c_int32), ('taps', ctypes.c_int32),
+        ('tap_dy', ctypes.c_int32 * MAX_TAPS), ('tap_dx', ctypes.c_int32 * MAX_TAPS),
+        ('bw', ctypes.c_int32), ('bh', ctypes.c_int32),
+        ('in_', ctypes.c_void_p),
+        ('in_ld', ctypes.c_int32), ('in_coff', ctypes.c_int32), ('in_part_stride', ctypes.c_int32),
+        ('weight', ctypes.c_void_p), ('w_parts', ctypes.c_int32), ('n_terms', ctypes.c_int32),
+        ('term_a', ctypes.c_int32 * MAX_TERMS), ('term_b', ctypes.c_int32 * MAX_TERMS),
+        ('scale', ctypes.c_void_p), ('bias', ctypes.c_void_p), ('img_bias', ctypes.c_void_p),
+        ('img_gate', ctypes.c_void_p), ('residual', ctypes.c_void_p),
+        ('res_sN', ctypes.c_int64), ('res_sY', ctypes.c_int64), ('res_sX', ctypes.c_int64),
+        ('n_seg', ctypes.c_int32), ('seg', ConvSeg * MAX_SEGS),
+    ]
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return t.data_ptr() if t is not None else None
+
+
+class Act:
+    """NHWC bf16 activation with `parts` split-bf16 parts: tensor (N, H, W, parts*C)."""
+
+    def __init__(self, data, C, parts):
+        self.data, self.C, self.parts = data, C, parts
+        self.N, self.H, self.W = data.shape[:3]
+        self.ld = data.shape[3]
+        self.coff = 0
+        self.part_stride = C
+
+    @staticmethod
+    def empty(N, H, W, C, parts, device):
+        return Act(torch.empty(N, H, W, parts * C, dtype=torch.bfloat16, device=device), C, parts)
+
+    def slice(self, c_lo, c_hi):
+        """A channel sub-range view (same storage), e.g. one branch of a concatenation."""
+        a = Act.__new__(Act)
+        a.data, a.C, a.parts = self.data, c_hi - c_lo, self.parts
+        a.N, a.H, a.W, a.ld = self.N, self.H, self.W, self.ld
+        a.coff, a.part_stride = self.coff + c_lo, self.part_stride
+        return a
+
+    def float(self):
+        """fp32 NCHW value (sum of the parts) -- for tests / hand-off to torch code."""
+        x = self.data.float().view(self.N, self.H, self.W, -1)
+        v = 0
+        for p in range(self.parts):
+            lo = self.coff + p * self.part_stride
+            v = v + x[..., lo:lo + self.C]
+        return v.permute(0, 3, 1, 2).contiguous()
+
+
+def split_bf16(x, parts):
+    """fp32 tensor -> list of `parts` bf16 tensors whose sum reproduces x to ~2^(-8*parts)."""
+    out, r = [], x.float()
+    for _ in range(parts):
+        h = r.to(torch.bfloat16)
+        out.append(h)
+        r = r - h.float()
+    return out
+
+
+def pack_weight(w, parts):
+    """(Cout, Cin, kh, kw) or (Cout, Cin) fp32 -> bf16 [Cout][taps][parts][Cin] contiguous
+    (done once when a module is built, not on the hot path)."""
+    if w.dim() == 2:
+        w = w[:, :, None, None]
+    Cout, Cin, kh, kw = w.shape
+    w = w.detach().float().permute(0, 2, 3, 1).reshape(Cout, kh * kw, Cin)       # [Cout][tap][Cin]
+    ps = split_bf16(w, parts)
+    return torch.stack(ps, dim=2).contiguous()                                     # [Cout][tap][part][Cin]
+
+
+def pack_input(x, parts):
+    """(N, C, H, W) fp32 -> Act (C padded to a multiple of 64 with zeros).  Uses the library's
+    pack kernel when present (csrc/layout.cu), torch otherwise is NOT a fallback: raises."""
+    lib = _lib.load()
+    N, C, H, W = x.shape
+    Cp = (C + 63) // 64 * 64
+    x = x.contiguous().float()
+    out = Act.empty(N, H, W, Cp, parts, x.device)
+    if Cp != C:
+        out.data.zero_()
+    _lib.check(lib.dhd_pack_nchw_to_nhwc(ctypes.c_void_p(x.data_ptr()), N, C, H, W,
+                                         ctypes.c_void_p(out.data.data_ptr()), out.ld, 0, Cp, parts,
+                                         _stream()), 'pack_nchw_to_nhwc')
+    return out
+
+
+def tile_box(H, W):
+    """(bw, bh) with bw*bh == 128 minimising the padded area of an H x W image."""
+    best = None
+    for bw in (4, 8, 16, 32, 64, 128):
+        bh = 128 // bw
+        area = ((W + bw - 1) // bw * bw) * ((H + bh - 1) // bh * bh)
+        if best is None or area < best[0]:
+            best = (area, bw, bh)
+    return best[1], best[2]
+
+
+def conv2d(x, weight, Cout, ksize=1, dilation=1, precision='fp32', scale=None, bias=None,
+           img_bias=None, img_gate=None, residual=None, segs=None):
+    """One fused convolution.  x: Act; weight: pack_weight() result with PRECISIONS[precision]
+    parts; segs: list of dicts {c_lo, c_hi, act, out_f32 (tensor, strides (sN,sY,sX,sC)),
+    out_act (Act or Act.slice)}.  Returns nothing: outputs are written in place."""
+    parts, terms = PRECISIONS[precision]
+    if x.parts < parts or weight.shape[2] != parts:
+        raise ValueError('activation has %d parts, weight %d, precision %s needs %d' %
+                         (x.parts, weight.shape[2], precision, parts))
+    d = ConvDesc()
+    d.N, d.H, d.W = x.N, x.H, x.W
+    d.Cin, d.Cout = x.C, Cout
+    taps = ksize * ksize
+    if weight.shape[0] != Cout or weight.shape[1] != taps or weight.shape[3] != x.C:
+        raise ValueError('weight shape %s does not match Cout=%d taps=%d Cin=%d' %
+                         (tuple(weight.shape), Cout, taps, x.C))
+    d.taps = taps
+    r = ksize // 2
+    for t in range(taps):
+        d.tap_dy[t] = (t // ksize - r) * dilation
+        d.tap_dx[t] = (t % ksize - r) * dilation
+    d.bw, d.bh = tile_box(x.H, x.W)
+    d.in_ = x.data.data_ptr()
+    d.in_ld, d.in_coff, d.in_part_stride = x.ld, x.coff, x.part_stride
+    d.weight = weight.data_ptr()
+    d.w_parts = parts
+    d.n_terms = len(terms)
+    for i, (a, b) in enumerate(terms):
+        d.term_a[i], d.term_b[i] = a, b
+    keep = [x.data, weight]
+    for name, t in (('scale', scale), ('bias', bias), ('img_bias', img_bias), ('img_gate', img_gate)):
+        if t is not None:
+            if t.dtype != torch.float32 or not t.is_contiguous() or not t.is_cuda:
+                raise ValueError(name + ' must be a contiguous fp32 CUDA tensor')
+            setattr(d, name, t.data_ptr())
+            keep.append(t)
+    if residual is not None:
+        rt, (sN, sY, sX) = residual
+        d.residual = rt.data_ptr()
+        d.res_sN, d.res_sY, d.res_sX = sN, sY, sX
+        keep.append(rt)
+    d.n_seg = len(segs)
+    for i, s in enumerate(segs):
+        g = d.seg[i]
+        g.c_lo, g.c_hi = s.get('c_lo', 0), s.get('c_hi', Cout)
+        g.act = ACT[s.get('act')]
+        if s.get('out_f32') is not None:
+            t, st = s['out_f32']
+            g.out_f32 = t.data_ptr()
+            g.f32_sN, g.f32_sY, g.f32_sX, g.f32_sC = st
+            keep.append(t)
+        if s.get('out_act') is not None:
+            a = s['out_act']
+            if (a.N, a.H, a.W) != (x.N, x.H, x.W) or a.C < g.c_hi - g.c_lo:
+                raise ValueError('output activation does not match the layer')
+            g.out_b16 = a.data.data_ptr()
+            g.b16_ld, g.b16_coff, g.b16_parts, g.b16_part_stride = a.ld, a.coff, a.parts, a.part_stride
+            keep.append(a.data)
+    _lib.check(_lib.load().dhd_conv2d_fwd(ctypes.byref(d), _stream()), 'conv2d_fwd')
+    return keep
+
+
+def nchw_strides(C, H, W):
+    return (C * H * W, W, 1, H * W)
+
+
+def nhwc_strides(C, H, W):
+    return (H * W * C, W * C, C, 1)

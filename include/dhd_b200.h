@@ -20,6 +20,8 @@
  *                            models/necks/lss_heightmap.py:261-300, 407-459; bev_pool.py:17-41,105
  *   dhd_mghs_pool_bwd     <- QuickCumsumCuda.backward x4 + mask product backward
  *                            ops/bev_pool_v2/bev_pool.py:44-83
+ *   dhd_conv2d_fwd        <- nn.Conv2d / nn.Linear of depth_net, HeightNet, SFA, predictor
+ *                            (see the dense-layer section below)
  *   dhd_mghs_voxel_index  <- the (kept, ranks_bev) part of voxel_pooling_prepare_v2
  *                            models/necks/lss_heightmap.py:331-354 (bit-exact parity hook)
  */
@@ -128,6 +130,91 @@ int dhd_mghs_voxel_index(const dhd_mghs_cfg* cfg, const void* workspace, int32_t
 /* number of binned entries after prepare (device int32[1] copied by caller) lives at this
  * byte offset of the workspace */
 size_t dhd_mghs_workspace_count_offset(const dhd_mghs_cfg* cfg);
+
+/* ---- dense layers: implicit-GEMM convolution on tcgen05 tensor cores ------------------
+ * Replaces the cuDNN / cuBLAS calls behind nn.Conv2d / nn.Linear in
+ *   MGHS.depth_net                     models/necks/lss_heightmap.py:62, 482-485
+ *   HeightNet / DepthNet / ASPP / SE   models/model_utils/depthnet.py:10-116, 150-243, 418-487
+ *   SFA                                models/necks/mix.py:28-33, 74-85
+ *   predictor.final_conv / predicter   models/dense_heads/occ_head.py:52-67
+ * Input: NHWC bf16, `in_ld` channels per pixel; the layer reads Cin channels starting at
+ * in_coff (+ part * in_part_stride for split-bf16 part `part`).  Weight: bf16
+ * [Cout][taps][w_parts][Cin].  out = act(scale[c]*acc + bias[c] + img_bias[n,c] + residual)
+ * * img_gate[n,c], written per output segment (a channel range of this layer). */
+#define DHD_CONV_MAX_TAPS 9
+#define DHD_CONV_MAX_TERMS 6
+#define DHD_CONV_MAX_SEGS 2
+
+enum {
+  DHD_ACT_NONE = 0,
+  DHD_ACT_RELU = 1,
+  DHD_ACT_SIGMOID = 2,
+  DHD_ACT_SOFTPLUS = 3, /* torch.nn.Softplus(beta=1, threshold=20) */
+  DHD_ACT_SOFTMAX = 4   /* over the channels of the segment (must sit in one 128-channel tile) */
+};
+
+typedef struct dhd_conv_seg {
+  int32_t c_lo, c_hi;          /* output channels [c_lo, c_hi) of this layer */
+  int32_t act;                 /* DHD_ACT_* */
+  float* out_f32;              /* or NULL; element (n, y, x, c) at n*sN + y*sY + x*sX + (c-c_lo)*sC */
+  int64_t f32_sN, f32_sY, f32_sX, f32_sC;
+  void* out_b16;               /* or NULL; NHWC bf16, b16_ld channels per pixel, channel c-c_lo at
+                                  b16_coff + part*b16_part_stride + (c-c_lo) */
+  int32_t b16_ld, b16_coff, b16_parts, b16_part_stride;
+} dhd_conv_seg;
+
+typedef struct dhd_conv_desc {
+  int32_t N, H, W;             /* images and spatial size (stride-1 convolution, same size out) */
+  int32_t Cin, Cout;           /* Cin % 64 == 0 */
+  int32_t taps;                /* 1 (1x1 / linear) .. 9 */
+  int32_t tap_dy[DHD_CONV_MAX_TAPS], tap_dx[DHD_CONV_MAX_TAPS]; /* input offset of tap t: (k-1)*dilation */
+  int32_t bw, bh;              /* output tile box, bw*bh == 128 */
+  const void* in;              /* bf16 NHWC */
+  int32_t in_ld, in_coff, in_part_stride;
+  const void* weight;          /* bf16 [Cout][taps][w_parts][Cin] */
+  int32_t w_parts;
+  int32_t n_terms;             /* MMAs per (tap, 64-channel chunk): 1 = bf16, 3 / 6 = split-bf16 */
+  int32_t term_a[DHD_CONV_MAX_TERMS], term_b[DHD_CONV_MAX_TERMS];
+  const float* scale;          /* [Cout] or NULL (folded BatchNorm scale) */
+  const float* bias;           /* [Cout] or NULL */
+  const float* img_bias;       /* [N][Cout] or NULL */
+  const float* img_gate;       /* [N][Cout] or NULL, applied after the activation */
+  const float* residual;       /* fp32 (n,y,x,c) at n*res_sN + y*res_sY + x*res_sX + c, or NULL */
+  int64_t res_sN, res_sY, res_sX;
+  int32_t n_seg;
+  dhd_conv_seg seg[DHD_CONV_MAX_SEGS];
+} dhd_conv_desc;
+
+int dhd_conv2d_fwd(const dhd_conv_desc* desc, void* stream);
+
+/* ---- streaming layout / elementwise helpers of the dense path (csrc/layout.cu) -----------
+ * "split-bf16 NHWC": bf16, `ld` channels per pixel, logical channel c of part p at
+ * coff + p*part_stride + c; the fp32 value is the sum of the parts. */
+/* fp32 NCHW -> split-bf16 NHWC (reference modules exchange fp32 NCHW tensors) */
+int dhd_pack_nchw_to_nhwc(const float* in, int N, int C, int H, int W, void* out, int out_ld,
+                          int out_coff, int part_stride, int parts, void* stream);
+int dhd_unpack_nhwc_to_nchw(const void* in, int in_ld, int in_coff, int part_stride, int parts,
+                            int N, int C, int H, int W, float* out, void* stream);
+/* out[n][c] = mean over the HW pixels (AdaptiveAvgPool2d(1): depthnet.py:77-82; mix.py:41) */
+int dhd_mean_hw(const void* in, int in_ld, int in_coff, int part_stride, int parts, int N, int C,
+                int HW, float* out, void* stream);
+/* y[r][o] = act(sum_k (x[r][k]*in_scale[k]+in_shift[k]) * w[o][k] + b[o]); one_minus: y = 1 - y.
+ * fp32 CUDA-core path for the M = B*N row MLP / SE / fc chains (depthnet.py:119-169, mix.py:20-25) */
+int dhd_linear_rows(const float* x, int R, int K, const float* w, const float* b, int O, int act,
+                    const float* in_scale, const float* in_shift, int one_minus, float* y,
+                    void* stream);
+/* channel_spatial_stage blends (mix.py:44-57): x holds bev channels [0,C) and voxel channels
+ * [C,2C); a1 [N][C]; a2 NULL -> a1*bev + (1-a1)*vox, else a2*(a1*bev) + (1-a2)*((1-a1)*vox) with
+ * a2 fp32 NHWC [pix][C] (already sigmoid-ed) */
+int dhd_sfa_mix(const void* x, int x_ld, int x_coff, int x_part_stride, int x_parts, int C, int N,
+                int HW, const float* a1, const float* a2, void* out, int o_ld, int o_coff,
+                int o_part_stride, int o_parts, void* stream);
+/* deformable bilinear im2col of mmcv DeformConv2dPack (depthnet.py:225-236, 466-477), stride 1,
+ * deform_groups 1; offset fp32 [pix][off_ld] with (dy, dx) per tap; out channels ordered
+ * [group][tap][C/groups] */
+int dhd_dcn_im2col(const void* x, int x_ld, int x_coff, int x_part_stride, int x_parts, int C, int N,
+                   int H, int W, const float* offset, int off_ld, int ksize, int pad, int dilation,
+                   int groups, void* out, int o_ld, int o_part_stride, int o_parts, void* stream);
 
 #ifdef __cplusplus
 }
