@@ -59,6 +59,19 @@ pack_nchw_to_nhwc_kernel(const float* __restrict__ in, int C, int HW, __nv_bfloa
   }
 }
 
+// ---- split: fp32 rows [R][C] (an NHWC tensor) -> split-bf16 rows, channel pairs per thread ----
+__global__ void __launch_bounds__(256)
+split_nhwc_kernel(const float* __restrict__ in, long R, int C, __nv_bfloat16* __restrict__ out, int ld,
+                  int coff, int part_stride, int parts) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int cp = C / 2;
+  if (i >= R * cp) return;
+  const long r = i / cp;
+  const int c = (int)(i % cp) * 2;
+  const float2 v = *reinterpret_cast<const float2*>(in + r * C + c);
+  store_parts2(out + r * ld + coff + c, v.x, v.y, parts, part_stride);
+}
+
 // ---- unpack: NHWC split-bf16 -> fp32 NCHW (hand-off to reference-layout consumers) --------
 __global__ void __launch_bounds__(256)
 unpack_nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ in, int ld, int coff, int part_stride,
@@ -230,6 +243,19 @@ extern "C" int dhd_pack_nchw_to_nhwc(const float* in, int N, int C, int H, int W
   pack_nchw_to_nhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
       in, C, H * W, (__nv_bfloat16*)out, out_ld, out_coff, part_stride, parts);
   DHD_CUDA_LAUNCH_CHECK("pack_nchw_to_nhwc");
+  return DHD_OK;
+}
+
+extern "C" int dhd_split_nhwc(const float* in, long rows, int C, void* out, int out_ld, int out_coff,
+                              int part_stride, int parts, void* stream) {
+  DHD_REQUIRE(in && out, "null pointer");
+  DHD_REQUIRE(rows > 0 && C > 0 && C % 2 == 0 && parts >= 1 && parts <= 3, "bad shape (C must be even)");
+  DHD_REQUIRE(out_ld % 2 == 0 && out_coff % 2 == 0 && part_stride % 2 == 0, "channel offsets must be even");
+  DHD_REQUIRE(((uintptr_t)in & 7) == 0, "input must be 8-byte aligned");
+  const long total = rows * (C / 2);
+  split_nhwc_kernel<<<(int)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      in, rows, C, (__nv_bfloat16*)out, out_ld, out_coff, part_stride, parts);
+  DHD_CUDA_LAUNCH_CHECK("split_nhwc");
   return DHD_OK;
 }
 

@@ -277,6 +277,7 @@ struct PoolParams {
   const int* cell_start;
   const int* cell_count;
   const int* blk_prefix;
+  const int* total_entries;
   const float* depth;
   const float* feat;
   const int8_t* pixmask;
@@ -411,23 +412,50 @@ __global__ void __launch_bounds__(256, MINB) mghs_pool_nhwc_kernel(const PoolPar
 // (2l, 2l+1) of every plane into its own smem slots -- no atomics, no barriers -- and the
 // column then leaves as 16-byte streaming stores, one contiguous dz*256-byte run per pass.
 // Empty cells (78 % of a DHD-S grid) skip shared memory and store zeros straight away.
+//
+// Work split: a warp owns a CONTIGUOUS run of cells chosen so that every warp gets the same
+// cost, cost(cell) = kCellCost + entries(cell).  The bins of a DHD-S frame are heavy-tailed
+// (median 16, max 256 entries; a strided split leaves the slowest warp with 4x the mean), and
+// the exclusive scan made by prepare already is the cumulative cost, so each warp finds its run
+// with one binary search over it -- deterministic, no atomics, contiguous output per warp.
+constexpr int kCellCost = 2;
+
+__device__ __forceinline__ int bin_start(const PoolParams& P, int cell) {
+  return __ldg(P.cell_start + cell) + __ldg(P.blk_prefix + cell / kScanChunk);
+}
+// smallest cell in [0, ncell] whose cumulative cost reaches `target`
+__device__ __forceinline__ int find_cell(const PoolParams& P, long target, int total) {
+  int lo = 0, hi = P.ncell;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    const long cum = (long)kCellCost * mid + (mid < P.ncell ? bin_start(P, mid) : total);
+    if (cum >= target) hi = mid;
+    else lo = mid + 1;
+  }
+  return lo;
+}
+
 __global__ void __launch_bounds__(256, 6) mghs_pool_nhwc_smem_kernel(const PoolParams P) {
   extern __shared__ float4 col_all[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   float4* col4 = col_all + (size_t)wid * P.nplanes * 16;     // [plane][16] float4
   float2* col2 = reinterpret_cast<float2*>(col4);            // [plane][32] float2
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   const int nq = P.nplanes * 16;                             // float4 per column
-  int cell = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  int n = cell < P.ncell ? __ldg(P.cell_count + cell) : 0;
-  while (cell < P.ncell) {
-    const int next = cell + warps;
-    const int n_next = next < P.ncell ? __ldg(P.cell_count + next) : 0;   // prefetch
+  const int total = __ldg(P.total_entries);
+  const long cost = (long)kCellCost * P.ncell + total;
+  int cell = find_cell(P, cost * gw / warps, total);
+  const int cell_end = gw + 1 == warps ? P.ncell : find_cell(P, cost * (gw + 1) / warps, total);
+  int n = cell < cell_end ? __ldg(P.cell_count + cell) : 0;
+  while (cell < cell_end) {
+    const int next = cell + 1;
+    const int n_next = next < cell_end ? __ldg(P.cell_count + next) : 0;   // prefetch
     if (n != 0) {
       for (int i = lane; i < nq; i += 32) col4[i] = zero4;
       __syncwarp();
-      const int s = __ldg(P.cell_start + cell) + __ldg(P.blk_prefix + cell / kScanChunk);
+      const int s = bin_start(P, cell);
       for (int base = 0; base < n; base += 32) {
         const int m = min(32, n - base);
         int pix = 0;
@@ -651,6 +679,7 @@ static int fill_pool_params(const dhd_mghs_cfg* cfg, const WsLayout& w, const vo
   P->cell_start = (const int*)(ws + w.cell_start);
   P->cell_count = (const int*)(ws + w.cell_count);
   P->blk_prefix = (const int*)(ws + w.blk_prefix);
+  P->total_entries = (const int*)(ws + w.total_entries);
   P->ncell = w.ncell;
   P->npass = cfg->n_pass;
   P->DyDx = cfg->Dy * cfg->Dx;

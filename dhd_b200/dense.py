@@ -132,6 +132,30 @@ def pack_input(x, parts):
     return out
 
 
+def pack_any(x, parts):
+    """Logical (N, C, H, W) fp32 tensor in either memory format -> Act."""
+    if x.dim() != 4:
+        raise ValueError('expected a (N, C, H, W) tensor')
+    if not x.is_contiguous() and x.permute(0, 2, 3, 1).is_contiguous():
+        return pack_nhwc(x.permute(0, 2, 3, 1), parts)
+    return pack_input(x, parts)
+
+
+def pack_nhwc(x, parts):
+    """(N, H, W, C) contiguous fp32 -> Act: the pack kernel run on an (N*H*W, C, 1, 1) view."""
+    lib = _lib.load()
+    N, H, W, C = x.shape
+    Cp = (C + 63) // 64 * 64
+    x = x.contiguous().float()
+    out = Act.empty(N, H, W, Cp, parts, x.device)
+    if Cp != C:
+        out.data.zero_()
+    _lib.check(lib.dhd_split_nhwc(ctypes.c_void_p(x.data_ptr()), N * H * W, C,
+                                  ctypes.c_void_p(out.data.data_ptr()), out.ld, 0, Cp, parts,
+                                  _stream()), 'split_nhwc')
+    return out
+
+
 def tile_box(H, W):
     """(bw, bh) with bw*bh == 128 minimising the padded area of an H x W image."""
     best = None

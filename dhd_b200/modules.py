@@ -1,0 +1,304 @@
+"""Compiled (inference) forms of the dense hot-path modules.
+
+Each ``*Engine`` takes the torch module that owns the parameters (same parameter names as the
+reference), folds eval-mode BatchNorm into per-channel scale / bias
+vectors, packs the weights to split-bf16 once, and runs the forward pass entirely through the
+C-ABI library: tcgen05 implicit-GEMM convolutions with fused epilogues plus a handful of
+streaming kernels.  No torch.nn.functional call is on the forward path.
+
+Reference forward passes restated here:
+  HeightNet.forward     models/model_utils/depthnet.py:605-652 (trunk 430-484; ASPP 42-108;
+                        Mlp 119-147; SELayer 150-169; mmdet BasicBlock; mmcv DeformConv2dPack)
+  MGHS.depth_net        models/necks/lss_heightmap.py:62, 482-485
+  SFA.forward           models/necks/mix.py:37-59, 87-90
+  predictor.forward     models/dense_heads/occ_head.py:84-100
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from . import dense as D
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def fold_bn(bn, conv_bias=None):
+    """Eval-mode BatchNorm2d/1d after a conv: y = conv*scale + bias."""
+    scale = (bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps))
+    bias = bn.bias.detach().float() - bn.running_mean.detach().float() * scale
+    if conv_bias is not None:
+        bias = bias + conv_bias.detach().float() * scale
+    return scale.contiguous(), bias.contiguous()
+
+
+def linear_rows(x, w, b=None, act=None, in_scale=None, in_shift=None, one_minus=False):
+    """y = act(x' @ w.T + b) on fp32 rows through dhd_linear_rows (M = B*N rows: CUDA cores)."""
+    R, K = x.shape
+    O = w.shape[0]
+    y = torch.empty(R, O, device=x.device)
+    _lib.check(_lib.load().dhd_linear_rows(_p(x), R, K, _p(w), _p(b), O, D.ACT[act], _p(in_scale),
+                                           _p(in_shift), int(one_minus), _p(y), _stream()), 'linear_rows')
+    return y
+
+
+def mean_hw(a):
+    out = torch.empty(a.N, a.C, device=a.data.device)
+    _lib.check(_lib.load().dhd_mean_hw(_p(a.data), a.ld, a.coff, a.part_stride, a.parts, a.N, a.C,
+                                       a.H * a.W, _p(out), _stream()), 'mean_hw')
+    return out
+
+
+def unpack(a):
+    """Act -> fp32 NCHW torch tensor (reference layout hand-off)."""
+    out = torch.empty(a.N, a.C, a.H, a.W, device=a.data.device)
+    _lib.check(_lib.load().dhd_unpack_nhwc_to_nchw(_p(a.data), a.ld, a.coff, a.part_stride, a.parts,
+                                                   a.N, a.C, a.H, a.W, _p(out), _stream()), 'unpack')
+    return out
+
+
+class _Conv:
+    """One packed convolution: weight parts + folded scale / bias."""
+
+    def __init__(self, conv, bn, precision, device, weight=None, bias=None):
+        parts = D.PRECISIONS[precision][0]
+        w = conv.weight if weight is None else weight
+        self.w = D.pack_weight(w.detach().to(device), parts)
+        self.Cout = w.shape[0]
+        self.ksize = w.shape[2] if w.dim() == 4 else 1
+        self.dilation = conv.dilation[0] if hasattr(conv, 'dilation') and not isinstance(conv.dilation, int) \
+            else getattr(conv, 'dilation', 1)
+        cb = (conv.bias if bias is None else bias) if hasattr(conv, 'bias') else None
+        if bn is not None:
+            s, b = fold_bn(bn, cb)
+            self.scale, self.bias = s.to(device), b.to(device)
+        else:
+            self.scale = None
+            self.bias = cb.detach().float().contiguous().to(device) if cb is not None else None
+        self.precision = precision
+
+    def __call__(self, x, segs, **kw):
+        return D.conv2d(x, self.w, self.Cout, ksize=self.ksize, dilation=self.dilation,
+                        precision=self.precision, scale=self.scale, bias=self.bias, segs=segs, **kw)
+
+
+class HeightNetEngine:
+    """depthnet.py:418-487, 605-652 (non-stereo path), eval mode."""
+
+    def __init__(self, net, precision='fp32', device='cuda'):
+        self.precision, self.device = precision, device
+        self.parts = D.PRECISIONS[precision][0]
+        dev = device
+        f = lambda t: t.detach().float().contiguous().to(dev)
+        self.C = net.reduce_conv[0].out_channels
+        self.reduce = _Conv(net.reduce_conv[0], net.reduce_conv[1], precision, dev)
+        # BatchNorm1d(27) folded into the first Linear's input transform
+        self.bn_scale, self.bn_shift = [t.to(dev) for t in fold_bn(net.bn)]
+        m = net.depth_mlp
+        self.fc1_w, self.fc1_b, self.fc2_w, self.fc2_b = f(m.fc1.weight), f(m.fc1.bias), f(m.fc2.weight), f(m.fc2.bias)
+        se = net.depth_se
+        self.se_r_w, self.se_r_b = f(se.conv_reduce.weight.flatten(1)), f(se.conv_reduce.bias)
+        self.se_e_w, self.se_e_b = f(se.conv_expand.weight.flatten(1)), f(se.conv_expand.bias)
+        layers = list(net.depth_conv)
+        self.blocks = []
+        i = 0
+        while i < len(layers) and type(layers[i]).__name__ == 'BasicBlock':
+            blk = layers[i]
+            if blk.downsample is not None:
+                raise NotImplementedError('HeightNet stereo downsample branch is not on this path yet')
+            self.blocks.append((_Conv(blk.conv1, blk.bn1, precision, dev), _Conv(blk.conv2, blk.bn2, precision, dev)))
+            i += 1
+        self.aspp = None
+        if i < len(layers) and type(layers[i]).__name__ == 'ASPP':
+            a = layers[i]
+            mid = a.aspp1.atrous_conv.out_channels
+            self.aspp_mid = mid
+            self.aspp_branches = [_Conv(b.atrous_conv, b.bn, precision, dev) for b in (a.aspp1, a.aspp2, a.aspp3, a.aspp4)]
+            # global-pool branch: mean -> 1x1 -> BN -> ReLU is a per-image vector; its share of
+            # conv1 (columns [4*mid, 5*mid)) becomes a per-image bias of conv1's epilogue
+            s5, b5 = fold_bn(a.global_avg_pool[2])
+            self.gap_w = f(a.global_avg_pool[1].weight.flatten(1) * s5[:, None].to(a.global_avg_pool[1].weight.device))
+            self.gap_b = b5.to(dev)
+            s1, _ = fold_bn(a.bn1)
+            w1 = a.conv1.weight.detach().float()
+            self.aspp_out = _Conv(a.conv1, a.bn1, precision, dev, weight=w1[:, :4 * mid])
+            self.aspp_w5 = f(w1[:, 4 * mid:].flatten(1) * s1[:, None].to(w1.device))
+            self.aspp = a
+            i += 1
+        self.dcn = None
+        if i < len(layers) and hasattr(layers[i], 'conv_offset'):
+            dc = layers[i]
+            self.dcn = dc
+            self.dcn_groups = dc.groups
+            self.dcn_offset = _Conv(dc.conv_offset, None, precision, dev)
+            cg = self.C // dc.groups
+            k = dc.weight.shape[2]
+            self.dcn_k = k
+            self.dcn_pad = dc.padding if isinstance(dc.padding, int) else dc.padding[0]
+            self.dcn_dil = dc.dilation if isinstance(dc.dilation, int) else dc.dilation[0]
+            # per group: [Cout/g][1 tap][parts][k*k*cg] with K ordered (tap, channel)
+            self.dcn_w = []
+            for g in range(dc.groups):
+                wg = dc.weight.detach().float()[g * cg:(g + 1) * cg]                # (cg_out, cg, k, k)
+                wg = wg.permute(0, 2, 3, 1).reshape(wg.shape[0], k * k * cg)        # K = (tap, c)
+                self.dcn_w.append(D.pack_weight(wg.to(dev), self.parts))
+            i += 1
+        self.head = _Conv(layers[i], None, precision, dev)
+        self.H_bins = self.head.Cout
+
+    def gate(self, mlp_input):
+        x = mlp_input.reshape(-1, mlp_input.shape[-1]).contiguous().float()
+        h = linear_rows(x, self.fc1_w, self.fc1_b, 'relu', self.bn_scale, self.bn_shift)
+        h = linear_rows(h, self.fc2_w, self.fc2_b)
+        h = linear_rows(h, self.se_r_w, self.se_r_b, 'relu')
+        return linear_rows(h, self.se_e_w, self.se_e_b, 'sigmoid')
+
+    def __call__(self, x, mlp_input, softmax=True):
+        """x: Act (B*N, 256, fH, fW); returns height (B*N, H, fH, fW) fp32 NCHW (softmax-ed
+        unless softmax=False, which gives the raw HeightNet output the reference returns)."""
+        N, H, W, C, P, dev = x.N, x.H, x.W, self.C, self.parts, x.data.device
+        new = lambda c: D.Act.empty(N, H, W, c, P, dev)
+        nhwc = D.nhwc_strides(C, H, W)
+        gate = self.gate(mlp_input)
+        h = new(C)
+        h32 = torch.empty(N, H, W, C, device=dev)
+        self.reduce(x, [dict(act='relu', out_act=h, out_f32=(h32, nhwc))], img_gate=gate)
+        for c1, c2 in self.blocks:
+            t = new(C)
+            c1(h, [dict(act='relu', out_act=t)])
+            h2, h2_32 = new(C), torch.empty(N, H, W, C, device=dev)
+            c2(t, [dict(act='relu', out_act=h2, out_f32=(h2_32, nhwc))], residual=(h32, nhwc[:3]))
+            h, h32 = h2, h2_32
+        if self.aspp is not None:
+            mid = self.aspp_mid
+            cat = new(4 * mid)
+            for b, conv in enumerate(self.aspp_branches):
+                conv(h, [dict(act='relu', out_act=cat.slice(b * mid, (b + 1) * mid))])
+            x5 = linear_rows(mean_hw(h), self.gap_w, self.gap_b, 'relu')
+            ib = linear_rows(x5, self.aspp_w5)
+            h = new(C)
+            self.aspp_out(cat, [dict(act='relu', out_act=h)], img_bias=ib)
+        if self.dcn is not None:
+            k, g = self.dcn_k, self.dcn_groups
+            off = torch.empty(N, H, W, 2 * k * k, device=dev)
+            self.dcn_offset(h, [dict(out_f32=(off, D.nhwc_strides(2 * k * k, H, W)))])
+            col = new(k * k * C)
+            _lib.check(_lib.load().dhd_dcn_im2col(
+                _p(h.data), h.ld, h.coff, h.part_stride, h.parts, C, N, H, W, _p(off), 2 * k * k, k,
+                self.dcn_pad, self.dcn_dil, g, _p(col.data), col.ld, col.part_stride, col.parts,
+                _stream()), 'dcn_im2col')
+            out = new(C)
+            cg = C // g
+            for gi in range(g):
+                D.conv2d(col.slice(gi * k * k * cg, (gi + 1) * k * k * cg), self.dcn_w[gi], cg,
+                         precision=self.precision,
+                         segs=[dict(out_act=out.slice(gi * cg, (gi + 1) * cg))])
+            h = out
+        height = torch.empty(N, self.H_bins, H, W, device=dev)
+        self.head(h, [dict(act='softmax' if softmax else None,
+                           out_f32=(height, D.nchw_strides(self.H_bins, H, W)))])
+        return height
+
+
+class DepthHeadEngine:
+    """MGHS.depth_net: one 1x1 conv -> softmax(depth) NCHW + context NHWC (the pool's layouts)."""
+
+    def __init__(self, conv, n_depth, precision='fp32', device='cuda'):
+        self.conv = _Conv(conv, None, precision, device)
+        self.D = n_depth
+        self.C = self.conv.Cout - n_depth
+
+    def __call__(self, x):
+        N, H, W, dev = x.N, x.H, x.W, x.data.device
+        depth = torch.empty(N, self.D, H, W, device=dev)
+        feat = torch.empty(N, H, W, self.C, device=dev)
+        self.conv(x, [dict(c_lo=0, c_hi=self.D, act='softmax', out_f32=(depth, D.nchw_strides(self.D, H, W))),
+                      dict(c_lo=self.D, c_hi=self.D + self.C, out_f32=(feat, D.nhwc_strides(self.C, H, W)))])
+        return depth, feat
+
+
+class SFAEngine:
+    """mix.py:8-90 in eval mode."""
+
+    def __init__(self, sfa, precision='fp32', device='cuda'):
+        self.precision, self.parts = precision, D.PRECISIONS[precision][0]
+        f = lambda t: t.detach().float().contiguous().to(device)
+        st = sfa.mysk_7
+        self.C = st.channels
+        self.fc0_w, self.fc0_b = f(st.fc[0].weight), f(st.fc[0].bias)
+        self.fc2_w, self.fc2_b = f(st.fc[2].weight), f(st.fc[2].bias)
+        sl = st.spacial_leanring
+        self.sp1 = _Conv(sl[0], sl[1], precision, device)
+        self.sp2 = _Conv(sl[3], sl[4], precision, device)
+        mr = sfa.mix_residual
+        self.res1 = _Conv(mr[0], mr[1], precision, device)
+        self.res2 = _Conv(mr[3], mr[4], precision, device)
+        self.short = _Conv(sfa.mix_shortcut[0], sfa.mix_shortcut[1], precision, device)
+        self.Cout = self.res2.Cout
+
+    def _mix(self, x, a1, a2, out):
+        _lib.check(_lib.load().dhd_sfa_mix(
+            _p(x.data), x.ld, x.coff, x.part_stride, x.parts, self.C, x.N, x.H * x.W, _p(a1), _p(a2),
+            _p(out.data), out.ld, out.coff, out.part_stride, out.parts, _stream()), 'sfa_mix')
+
+    def __call__(self, x, out_f32=None):
+        """x: Act (B, 2C, Dy, Dx) = cat(bev feature, voxel feature).  Returns Act (B, Cout, Dy, Dx)."""
+        N, H, W, C, P, dev = x.N, x.H, x.W, self.C, self.parts, x.data.device
+        new = lambda c: D.Act.empty(N, H, W, c, P, dev)
+        s = mean_hw(x)
+        a1 = linear_rows(linear_rows(s, self.fc0_w, self.fc0_b, 'relu'), self.fc2_w, self.fc2_b, 'sigmoid')
+        u = new(C)
+        self._mix(x, a1, None, u)
+        t = new(C)
+        self.sp1(u, [dict(act='relu', out_act=t)])
+        a2 = torch.empty(N, H, W, C, device=dev)
+        self.sp2(t, [dict(act='sigmoid', out_f32=(a2, D.nhwc_strides(C, H, W)))])
+        fuse = u                                   # reuse the buffer
+        self._mix(x, a1, a2, fuse)
+        sc = a2                                    # reuse: shortcut branch, fp32 NHWC
+        self.short(x, [dict(out_f32=(sc, D.nhwc_strides(self.Cout, H, W)))])
+        self.res1(fuse, [dict(act='relu', out_act=t)])
+        out = new(self.Cout)
+        seg = dict(act='relu', out_act=out)
+        if out_f32 is not None:
+            seg['out_f32'] = out_f32
+        self.res2(t, [seg], residual=(sc, D.nhwc_strides(self.Cout, H, W)[:3]))
+        return out
+
+
+class PredictorEngine:
+    """occ_head.py:52-67, 84-100: 3x3 conv (+ mmcv ConvModule's default ReLU) -> permute ->
+    Linear -> Softplus -> Linear -> (B, Dx, Dy, Dz, n_cls)."""
+
+    def __init__(self, head, precision='fp32', device='cuda'):
+        self.conv = _Conv(head.final_conv.conv, None, precision, device)
+        self.relu = getattr(head.final_conv, 'with_activation', True)
+        self.use_predicter = head.use_predicter
+        if head.use_predicter:
+            self.fc0 = _Conv(head.predicter[0], None, precision, device, weight=head.predicter[0].weight[:, :, None, None])
+            self.fc2 = _Conv(head.predicter[2], None, precision, device, weight=head.predicter[2].weight[:, :, None, None])
+        self.Dz, self.ncls = head.Dz, head.num_classes
+        self.parts = D.PRECISIONS[precision][0]
+
+    def __call__(self, x):
+        """x: Act (B, C, Dy, Dx) -> occ_pred (B, Dx, Dy, Dz, n_cls) fp32."""
+        N, H, W, P, dev = x.N, x.H, x.W, self.parts, x.data.device
+        if not self.use_predicter:
+            Co = self.conv.Cout
+            out = torch.empty(N, W, H, Co, device=dev)
+            self.conv(x, [dict(act='relu' if self.relu else None, out_f32=(out, (W * H * Co, Co, H * Co, 1)))])
+            return out
+        t = D.Act.empty(N, H, W, self.conv.Cout, P, dev)
+        self.conv(x, [dict(act='relu' if self.relu else None, out_act=t)])
+        u = D.Act.empty(N, H, W, self.fc0.Cout, P, dev)
+        self.fc0(t, [dict(act='softplus', out_act=u)])
+        Co = self.fc2.Cout
+        out = torch.empty(N, W, H, Co, device=dev)          # (B, Dx, Dy, C): permute(0, 3, 2, 1)
+        self.fc2(u, [dict(out_f32=(out, (W * H * Co, Co, H * Co, 1)))])
+        return out.view(N, W, H, self.Dz, self.ncls)

@@ -193,6 +193,9 @@ int dhd_conv2d_fwd(const dhd_conv_desc* desc, void* stream);
 /* fp32 NCHW -> split-bf16 NHWC (reference modules exchange fp32 NCHW tensors) */
 int dhd_pack_nchw_to_nhwc(const float* in, int N, int C, int H, int W, void* out, int out_ld,
                           int out_coff, int part_stride, int parts, void* stream);
+/* fp32 rows [rows][C] (NHWC) -> split-bf16 rows */
+int dhd_split_nhwc(const float* in, long rows, int C, void* out, int out_ld, int out_coff,
+                   int part_stride, int parts, void* stream);
 int dhd_unpack_nhwc_to_nchw(const void* in, int in_ld, int in_coff, int part_stride, int parts,
                             int N, int C, int H, int W, float* out, void* stream);
 /* out[n][c] = mean over the HW pixels (AdaptiveAvgPool2d(1): depthnet.py:77-82; mix.py:41) */

@@ -1,21 +1,32 @@
-"""TEST INFRASTRUCTURE -- torch fp32 restatements of the third-party layers the
-reference's dense hot-path modules pull from un-vendored packages:
+"""TEST INFRASTRUCTURE -- CPU (torch) restatement of the reference's dense hot-path modules,
+written as pure functions of a state_dict so the same seeded weights can be pushed through the
+reference classes (in the build container), this oracle (anywhere) and the CUDA engines.
 
-  mmcv-full 1.5.3  DCN == DeformConv2dPack (depthnet.py:225-236, 466-477)
-  mmdet 2.25.1     BasicBlock               (depthnet.py:4, 217-220, 458-461)
-  mmcv-full 1.5.3  ConvModule               (occ_head.py:52-60)
+  heightnet_forward   models/model_utils/depthnet.py:605-652 (trunk 418-487, ASPP 88-108,
+                      Mlp 136-147, SELayer 158-169)
+  depth_head_forward  models/necks/lss_heightmap.py:482-485
+  sfa_forward         models/necks/mix.py:37-59, 87-90
+  predictor_forward   models/dense_heads/occ_head.py:84-100
 
-PARITY UNPINNED for these three: the reference ships no test vector at these
-boundaries and the packages are not installable here; the restatements follow the
-published layer definitions (DeformConv2dPack: zero-initialised 3x3 offset conv
-producing deform_groups*2*kh*kw channels in (dy, dx) interleaved order, then
-deformable conv without bias).
+Third-party layers not under /root/reference, restated from their published
+definitions -- PARITY UNPINNED at these three boundaries (no reference test vector exists and
+the packages cannot be installed here):
+  mmcv-full 1.5.3  DCN == DeformConv2dPack (depthnet.py:225-236, 466-477): 3x3 offset conv ->
+                   deform_groups*2*kh*kw channels in (dy, dx) order per tap -> deformable conv, no bias
+                   (restated with torchvision.ops.deform_conv2d, same offset layout)
+  mmdet 2.25.1     BasicBlock: conv3x3-BN-ReLU-conv3x3-BN + identity -> ReLU
+  mmcv-full 1.5.3  ConvModule: conv -> [norm] -> ReLU by default (occ_head.py:52-60)
+Everything that IS under /root/reference is pinned against the real classes by
+tests/test_dense_oracle.py.
 """
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 
 class DeformConv2dPack(nn.Module):
+    """Stand-in handed to the reference's build_conv_layer(type='DCN') by oracle/ref_loader.py."""
+
     def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0,
                  dilation=1, groups=1, deform_groups=1, bias=False, **kw):
         super().__init__()
@@ -34,3 +45,125 @@ class DeformConv2dPack(nn.Module):
         off = self.conv_offset(x)
         return deform_conv2d(x, off, self.weight, None, stride=self.stride, padding=self.padding,
                              dilation=self.dilation)
+
+
+# ------------------------------------------------------------------ seeded, exactly representable weights
+def seeded_state_dict(module, seed):
+    """Fill every parameter / buffer with values that are integers scaled by powers of two
+    (bit-identical on every host; no libm in the generator), at magnitudes that keep activations
+    O(1): weights ~ U(-a, a), a = 2^round(log2(sqrt(3 / fan_in))); BN gamma in [0.75, 1.25],
+    beta / running_mean in [-0.25, 0.25], running_var in [0.5, 1.5]."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    import math
+    for name, t in module.state_dict().items():
+        if name.endswith('num_batches_tracked'):
+            sd[name] = torch.zeros_like(t)
+            continue
+        r = torch.randint(-2048, 2048, t.shape, generator=g).double() / 2048.0      # U(-1, 1), 12 bits
+        if name.endswith('running_var'):
+            v = 1.0 + 0.5 * r
+        elif name.endswith('running_mean') or (name.endswith('.bias') and t.dim() == 1):
+            v = 0.25 * r
+        elif t.dim() == 1:                                                           # BN weight
+            v = 1.0 + 0.25 * r
+        else:
+            fan_in = t[0].numel()
+            a = 2.0 ** round(math.log2(math.sqrt(3.0 / fan_in)))
+            if 'conv_offset' in name:
+                a *= 0.5                                                             # offsets of ~1 px
+            v = a * r
+        sd[name] = v.to(t.dtype)
+    return sd
+
+
+def seeded_tensor(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randint(-2048, 2048, shape, generator=g).float() * (scale / 1024.0)
+
+
+# ------------------------------------------------------------------ functional restatements
+def _bn(sd, p, x, eps=1e-5):
+    return F.batch_norm(x, sd[p + '.running_mean'], sd[p + '.running_var'], sd[p + '.weight'],
+                        sd[p + '.bias'], False, 0.0, eps)
+
+
+def _basic_block(sd, p, x):
+    out = F.relu(_bn(sd, p + '.bn1', F.conv2d(x, sd[p + '.conv1.weight'], padding=1)))
+    out = _bn(sd, p + '.bn2', F.conv2d(out, sd[p + '.conv2.weight'], padding=1))
+    return F.relu(out + x)
+
+
+def _aspp(sd, p, x):
+    outs = [F.relu(_bn(sd, p + '.aspp1.bn', F.conv2d(x, sd[p + '.aspp1.atrous_conv.weight'])))]
+    for k, d in (('aspp2', 6), ('aspp3', 12), ('aspp4', 18)):
+        outs.append(F.relu(_bn(sd, '%s.%s.bn' % (p, k),
+                               F.conv2d(x, sd['%s.%s.atrous_conv.weight' % (p, k)], padding=d, dilation=d))))
+    g = F.adaptive_avg_pool2d(x, 1)
+    g = F.relu(_bn(sd, p + '.global_avg_pool.2', F.conv2d(g, sd[p + '.global_avg_pool.1.weight'])))
+    outs.append(F.interpolate(g, size=x.shape[2:], mode='bilinear', align_corners=True))
+    y = F.conv2d(torch.cat(outs, 1), sd[p + '.conv1.weight'])
+    return F.relu(_bn(sd, p + '.bn1', y))          # Dropout(0.5) is the identity in eval
+
+
+def _dcn(sd, p, x, groups=4):
+    from torchvision.ops import deform_conv2d
+    off = F.conv2d(x, sd[p + '.conv_offset.weight'], sd[p + '.conv_offset.bias'], padding=1)
+    return deform_conv2d(x, off, sd[p + '.weight'], None, stride=1, padding=1, dilation=1)
+
+
+def heightnet_forward(sd, x, mlp_input, prefix=''):
+    """Eval-mode HeightNet (non-stereo).  sd: state_dict with the reference's names."""
+    p = prefix
+    m = F.batch_norm(mlp_input.reshape(-1, mlp_input.shape[-1]), sd[p + 'bn.running_mean'],
+                     sd[p + 'bn.running_var'], sd[p + 'bn.weight'], sd[p + 'bn.bias'], False, 0.0, 1e-5)
+    x = F.conv2d(x, sd[p + 'reduce_conv.0.weight'], sd[p + 'reduce_conv.0.bias'], padding=1)
+    x = F.relu(_bn(sd, p + 'reduce_conv.1', x))
+    se = F.linear(F.relu(F.linear(m, sd[p + 'depth_mlp.fc1.weight'], sd[p + 'depth_mlp.fc1.bias'])),
+                  sd[p + 'depth_mlp.fc2.weight'], sd[p + 'depth_mlp.fc2.bias'])[..., None, None]
+    se = F.relu(F.conv2d(se, sd[p + 'depth_se.conv_reduce.weight'], sd[p + 'depth_se.conv_reduce.bias']))
+    se = F.conv2d(se, sd[p + 'depth_se.conv_expand.weight'], sd[p + 'depth_se.conv_expand.bias'])
+    x = x * torch.sigmoid(se)
+    i = 0
+    while (p + 'depth_conv.%d.bn2.weight' % i) in sd:      # BasicBlocks (ASPP has conv1 + bn1 but no bn2)
+        x = _basic_block(sd, p + 'depth_conv.%d' % i, x)
+        i += 1
+    if (p + 'depth_conv.%d.aspp1.atrous_conv.weight' % i) in sd:
+        x = _aspp(sd, p + 'depth_conv.%d' % i, x)
+        i += 1
+    if (p + 'depth_conv.%d.conv_offset.weight' % i) in sd:
+        x = _dcn(sd, p + 'depth_conv.%d' % i, x)
+        i += 1
+    return F.conv2d(x, sd[p + 'depth_conv.%d.weight' % i], sd[p + 'depth_conv.%d.bias' % i])
+
+
+def depth_head_forward(sd, x, n_depth, prefix='depth_net.'):
+    y = F.conv2d(x, sd[prefix + 'weight'], sd[prefix + 'bias'])
+    return y[:, :n_depth].softmax(dim=1), y[:, n_depth:]
+
+
+def sfa_forward(sd, x, prefix=''):
+    p = prefix
+    C = x.shape[1] // 2
+    bev, vox = x[:, :C], x[:, C:]
+    s = x.mean(-1).mean(-1)
+    a1 = torch.sigmoid(F.linear(F.relu(F.linear(s, sd[p + 'mysk_7.fc.0.weight'], sd[p + 'mysk_7.fc.0.bias'])),
+                                sd[p + 'mysk_7.fc.2.weight'], sd[p + 'mysk_7.fc.2.bias']))[..., None, None]
+    b1, v1 = a1 * bev, (1 - a1) * vox
+    q = p + 'mysk_7.spacial_leanring'
+    t = F.relu(_bn(sd, q + '.1', F.conv2d(b1 + v1, sd[q + '.0.weight'], sd[q + '.0.bias'])))
+    a2 = torch.sigmoid(_bn(sd, q + '.4', F.conv2d(t, sd[q + '.3.weight'], sd[q + '.3.bias'])))
+    fuse = a2 * b1 + (1 - a2) * v1
+    r = F.relu(_bn(sd, p + 'mix_residual.1', F.conv2d(fuse, sd[p + 'mix_residual.0.weight'], padding=1)))
+    r = _bn(sd, p + 'mix_residual.4', F.conv2d(r, sd[p + 'mix_residual.3.weight'], padding=1))
+    sc = _bn(sd, p + 'mix_shortcut.1', F.conv2d(x, sd[p + 'mix_shortcut.0.weight']))
+    return F.relu(r + sc)
+
+
+def predictor_forward(sd, x, Dz=16, num_classes=18, prefix=''):
+    p = prefix
+    y = F.relu(F.conv2d(x, sd[p + 'final_conv.conv.weight'], sd[p + 'final_conv.conv.bias'], padding=1))
+    y = y.permute(0, 3, 2, 1)
+    y = F.linear(F.softplus(F.linear(y, sd[p + 'predicter.0.weight'], sd[p + 'predicter.0.bias'])),
+                 sd[p + 'predicter.2.weight'], sd[p + 'predicter.2.bias'])
+    return y.view(y.shape[0], y.shape[1], y.shape[2], Dz, num_classes)

@@ -1,0 +1,4 @@
+from .dense_heads import *  # noqa: F401,F403
+from .detectors import *  # noqa: F401,F403
+from .model_utils import *  # noqa: F401,F403
+from .necks import *  # noqa: F401,F403

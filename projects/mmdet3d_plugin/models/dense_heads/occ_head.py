@@ -1,0 +1,61 @@
+"""Occupancy head `predictor` (reference: projects/mmdet3d_plugin/models/dense_heads/occ_head.py:32-153):
+3x3 ConvModule (+ mmcv's default ReLU) -> permute to (B, Dx, Dy, C) -> Linear, Softplus, Linear ->
+(B, Dx, Dy, Dz, n_cls).  Parameter names final_conv.conv.* / predicter.{0,2}.* as in the
+reference; forward on tcgen05 GEMMs, the permute folded into the last layer's output strides."""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from dhd_b200.compat import HEADS, BaseModule, ConvModule, build_loss
+
+# class frequencies of Occ3D-nuScenes used for the class-balanced CE weights (occ_head.py:10-29)
+nusc_class_frequencies = np.array([
+    944004, 1897170, 152386, 2391677, 16957802, 724139, 189027, 2074468, 413451, 2384460,
+    5916653, 175883646, 4275424, 51393615, 61411620, 105975596, 116424404, 1892500630])
+
+
+@HEADS.register_module(force=True)
+class predictor(BaseModule):
+    def __init__(self, in_dim=256, out_dim=256, Dz=16, use_mask=True, weight_ce=1, weight_geo=1,
+                 weight_sem=1, num_classes=18, use_predicter=True, class_balance=False, loss_occ=None,
+                 precision='fp32'):
+        super().__init__()
+        self.in_dim, self.out_dim, self.Dz = in_dim, out_dim, Dz
+        out_channels = out_dim if use_predicter else num_classes * Dz
+        self.final_conv = ConvModule(in_dim, out_channels, kernel_size=3, stride=1, padding=1, bias=True,
+                                     conv_cfg=dict(type='Conv2d'))
+        self.use_predicter = use_predicter
+        if use_predicter:
+            self.predicter = nn.Sequential(nn.Linear(out_dim, out_dim * 2), nn.Softplus(),
+                                           nn.Linear(out_dim * 2, num_classes * Dz))
+        self.use_mask, self.num_classes, self.class_balance = use_mask, num_classes, class_balance
+        if class_balance:
+            self.cls_weights = torch.from_numpy(1 / np.log(nusc_class_frequencies[:num_classes] + 0.001))
+            if loss_occ is not None:
+                loss_occ = dict(loss_occ, class_weight=self.cls_weights)
+        self.loss_occ = build_loss(loss_occ) if loss_occ is not None else None
+        self.weight_ce, self.weight_geo, self.weight_sem = weight_ce, weight_geo, weight_sem
+        self.precision = precision
+        self._engine = None
+
+    def _load_from_state_dict(self, *a, **k):
+        self._engine = None
+        return super()._load_from_state_dict(*a, **k)
+
+    def forward(self, img_feats):
+        """img_feats: (B, C, Dy, Dx) fp32 CUDA tensor or a dhd_b200.dense.Act -> (B, Dx, Dy, Dz, n_cls)."""
+        from dhd_b200 import dense as D
+        from dhd_b200.modules import PredictorEngine
+        with torch.no_grad():
+            if not isinstance(img_feats, D.Act):
+                if not img_feats.is_cuda:
+                    raise RuntimeError('dhd_b200: expected CUDA tensors (the hot path has no CPU fallback)')
+                img_feats = D.pack_any(img_feats, D.PRECISIONS[self.precision][0])
+            if self._engine is None:
+                self._engine = PredictorEngine(self, self.precision, img_feats.data.device)
+            return self._engine(img_feats)
+
+    def get_occ(self, occ_pred, img_metas=None):
+        """(B, Dx, Dy, Dz, C) -> list of (Dx, Dy, Dz) uint8 class maps (occ_head.py:141-153)."""
+        res = occ_pred.softmax(-1).argmax(-1)
+        return list(res.cpu().numpy().astype(np.uint8))

@@ -1,9 +1,17 @@
 set -x
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv
-python -m pytest tests -m gpu -x -q 2>&1 | tail -5 > gpurun_out/r01_pytest.log
-python bench.py --steps 30 --warmup 5 > gpurun_out/r01_bench.json 2> gpurun_out/r01_bench.err
-python bench.py --steps 30 --warmup 5 --layout nchw --no-cpu-baseline > gpurun_out/r01_bench_nchw.json 2>> gpurun_out/r01_bench.err
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r01_launches.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/r01_ncu_bench.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:mghs_pool_nhwc -s 3 -c 2 -o gpurun_out/r01_pool_fwd python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/r01_ncu_full.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:mghs_pool_bwd -s 3 -c 1 -o gpurun_out/r01_pool_bwd python bench.py --steps 2 --warmup 3 --no-cpu-baseline >> gpurun_out/r01_ncu_full.log 2>&1
-cat gpurun_out/r01_pytest.log gpurun_out/r01_bench.json
+python -m pytest tests/test_dense_gpu.py -x -q 2>&1 | tail -30
+python -m pytest tests -m gpu -x -q --deselect tests/test_dense_gpu.py 2>&1 | tail -5
+python bench.py --steps 50 --warmup 5 --no-cpu-baseline > gpurun_out/r01_bench_poolv3.json; cat gpurun_out/r01_bench_poolv3.json
+python - <<'P'
+import torch
+x = torch.empty(704*1024*1024//4, device='cuda')
+for f in (lambda: x.zero_(), lambda: x.fill_(1.0)):
+    for _ in range(3): f()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10): f()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)/10
+    print('memset-like write of %.0f MB: %.1f us = %.0f GB/s' % (x.numel()*4/1e6, ms*1e3, x.numel()*4/ms/1e6))
+P

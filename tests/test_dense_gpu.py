@@ -1,0 +1,152 @@
+"""GPU parity tests of the dense hot-path modules (plugin API -> engines -> C-ABI -> tcgen05)
+against (a) the fixture generated from the REAL reference modules and (b) the CPU oracle, on the
+same seeded weights and inputs.
+
+Tolerance: north_star asks occupancy logits within 1e-4 in fp32.  In the 'fp32' precision mode
+(6-term split-bf16 MMAs, fp32 accumulation) every module output must be within
+atol 1e-4 + rtol 1e-4 of the reference; the 'bf16' speed mode is checked against its own, looser
+bound (2e-2 of the output scale) and reported separately."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import dense_oracle as DO
+from oracle import make_golden_dense as MG
+from oracle import mghs_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'dense_modules.npz')
+ATOL, RTOL = 1e-4, 1e-4
+
+
+def build(precision):
+    import projects.mmdet3d_plugin  # noqa: F401
+    from projects.mmdet3d_plugin.models.dense_heads.occ_head import predictor
+    from projects.mmdet3d_plugin.models.model_utils.depthnet import HeightNet
+    from projects.mmdet3d_plugin.models.necks.mix import SFA
+    hn = HeightNet(256, 256, 65, precision=precision).eval()
+    sfa = SFA(512, 256, precision=precision).eval()
+    head = predictor(in_dim=256, out_dim=256, Dz=16, num_classes=18, use_predicter=True,
+                     class_balance=False, loss_occ=None, precision=precision).eval()
+    dn = torch.nn.Conv2d(256, 108, 1)
+    for m, s in zip((hn, sfa, head, dn), (21, 22, 23, 24)):
+        m.load_state_dict(DO.seeded_state_dict(m, s))
+    return hn.cuda(), sfa.cuda(), head.cuda(), dn.cuda()
+
+
+def close(got, ref, what, atol=ATOL, rtol=RTOL):
+    got, ref = got.detach().float().cpu(), ref.detach().float().cpu()
+    assert got.shape == ref.shape, '%s: shape %s vs %s' % (what, tuple(got.shape), tuple(ref.shape))
+    err = (got - ref).abs()
+    bad = err > atol + rtol * ref.abs()
+    assert not bad.any(), '%s: %d / %d elements off, max abs err %.3g (ref scale %.3g)' % (
+        what, int(bad.sum()), bad.numel(), err.max(), ref.abs().max())
+
+
+def test_heightnet_matches_reference_fixture(cuda_lib):
+    gold = np.load(GOLD)
+    hn, _, _, _ = build('fp32')
+    x, mlp, _ = MG.inputs()
+    height = hn(x.cuda(), mlp.cuda())
+    close(height, torch.from_numpy(gold['height']), 'HeightNet logits')
+    sm = hn(x.cuda(), mlp.cuda(), softmax=True)
+    close(sm, torch.from_numpy(gold['height']).softmax(1), 'HeightNet softmax', atol=1e-5)
+
+
+def test_heightnet_without_dcn_matches_oracle(cuda_lib):
+    """DHD-L switches the deformable conv off (use_dcn=False, DHD-L.py:118-119)."""
+    from projects.mmdet3d_plugin.models.model_utils.depthnet import HeightNet
+    hn = HeightNet(256, 256, 65, use_dcn=False).eval()
+    hn.load_state_dict(DO.seeded_state_dict(hn, 31))
+    x, mlp, _ = MG.inputs()
+    with torch.no_grad():
+        ref = DO.heightnet_forward(hn.state_dict(), x, mlp)
+    close(hn.cuda()(x.cuda(), mlp.cuda()), ref, 'HeightNet(use_dcn=False)')
+
+
+def test_depth_head_matches_reference_fixture(cuda_lib):
+    from dhd_b200 import dense as D
+    from dhd_b200.modules import DepthHeadEngine
+    gold = np.load(GOLD)
+    _, _, _, dn = build('fp32')
+    x, _, _ = MG.inputs()
+    depth, feat = DepthHeadEngine(dn, 44, 'fp32', 'cuda')(D.pack_input(x.cuda(), 3))
+    y = torch.from_numpy(gold['depth_net'])
+    close(depth, y[:, :44].softmax(1), 'depth softmax', atol=1e-5)
+    close(feat.permute(0, 3, 1, 2), y[:, 44:], 'context feature')
+
+
+def test_sfa_and_predictor_match_reference_fixture(cuda_lib):
+    gold = np.load(GOLD)
+    _, sfa, head, _ = build('fp32')
+    _, _, bev = MG.inputs()
+    fused = sfa(bev.cuda())
+    close(fused, torch.from_numpy(gold['sfa']), 'SFA output')
+    occ = head(sfa(bev.cuda(), return_act=True))
+    close(occ, torch.from_numpy(gold['occ']), 'occupancy logits')
+    # channels_last input and the tensor (non-Act) path of the head
+    fused_cl = sfa(bev.cuda().contiguous(memory_format=torch.channels_last))
+    assert torch.equal(fused_cl, fused)
+    close(head(fused), torch.from_numpy(gold['occ']), 'occupancy logits (tensor path)')
+
+
+def test_bf16_speed_mode_is_close(cuda_lib):
+    gold = np.load(GOLD)
+    hn, sfa, head, _ = build('bf16')
+    x, mlp, bev = MG.inputs()
+    occ = head(sfa(bev.cuda(), return_act=True)).cpu()
+    ref = torch.from_numpy(gold['occ'])
+    assert (occ - ref).abs().max() <= 2e-2 * ref.abs().max()
+    h = hn(x.cuda(), mlp.cuda()).cpu()
+    ref = torch.from_numpy(gold['height'])
+    assert (h - ref).abs().max() <= 3e-2 * ref.abs().max()
+
+
+def test_mghs_forward_end_to_end(cuda_lib):
+    """Plugin MGHS.forward (dense front + fused pool) on the MINI rig: dense outputs against the
+    oracle, pooled BEV tensors against the oracle's view_transform fed with the SAME depth /
+    context / height (so an argmax tie in the height head cannot flip a mask between the two)."""
+    from projects.mmdet3d_plugin.models.necks.lss_heightmap import MGHS
+    cfg, B = O.MINI, 2
+    grids = cfg['mask_grids']
+    vt = MGHS(grid_config=dict(cfg['bev_grid'], depth=cfg['depth']), input_size=cfg['input_size'],
+              in_channels=256, out_channels=64, height_range=cfg['height_range'], height_interval=0.1,
+              mask_range=cfg['mask_range'], mask_1_grid=dict(grids[0], depth=cfg['depth']),
+              mask_2_grid=dict(grids[1], depth=cfg['depth']), mask_3_grid=dict(grids[2], depth=cfg['depth']),
+              downsample=16).eval()
+    # MINI uses coarse slabs on the x/y grid of the BEV pass for the fused path
+    for g in (vt.mask_1_grid, vt.mask_2_grid, vt.mask_3_grid):
+        g['x'], g['y'] = [-40, 40, 0.4], [-40, 40, 0.4]
+    vt.load_state_dict(DO.seeded_state_dict(vt, 41))
+    rig = O.synthetic_rig(B, cfg['ncams'], cfg['input_size'], seed=3)
+    s2e, e2g, K, pr, pt, bda = rig
+    N, fH, fW = cfg['ncams'], 4, 11
+    x = DO.seeded_tensor((B, N, 256, fH, fW), 42)
+    mlp = vt.get_mlp_input(s2e, e2g, K, pr, pt, bda)
+    sd = vt.state_dict()
+    with torch.no_grad():
+        d_ref, f_ref = DO.depth_head_forward(sd, x.view(B * N, 256, fH, fW), vt.D)
+        h_ref = DO.heightnet_forward(sd, x.view(B * N, 256, fH, fW), mlp, prefix='height_net.').softmax(1)
+    vt = vt.cuda()
+    args = [t.cuda() for t in (x, s2e, e2g, K, pr, pt, bda, mlp)]
+    bev, depth, height, lo, mid, hi = vt(args)
+    close(depth, d_ref, 'depth', atol=1e-5)
+    close(height, h_ref, 'height', atol=1e-5)
+    assert bev.shape == (B, 64, 200, 200) and lo.shape == (B, 256, 200, 200) and hi.shape == (B, 512, 200, 200)
+    # pool against the oracle on the module's own dense outputs
+    fr = O.frustum(cfg['depth'], cfg['input_size'], cfg['downsample'])
+    feat_nchw = vt._last_feat.permute(0, 3, 1, 2).contiguous().cpu() if hasattr(vt, '_last_feat') else None
+    if feat_nchw is None:
+        from dhd_b200 import dense as D
+        from dhd_b200.modules import DepthHeadEngine
+        _, f = DepthHeadEngine(vt.depth_net, vt.D, 'fp32', 'cuda')(D.pack_input(args[0].view(B * N, 256, fH, fW), 3))
+        feat_nchw = f.permute(0, 3, 1, 2).contiguous().cpu()
+    close(feat_nchw, f_ref, 'context')
+    big = [dict(g) for g in (vt.mask_1_grid, vt.mask_2_grid, vt.mask_3_grid)]
+    ref = O.view_transform((x,) + tuple(rig), depth.cpu(), feat_nchw, height.cpu(), fr, cfg['height_range'],
+                           cfg['mask_range'], big)
+    for got, want, name in zip((bev, lo, mid, hi), ref, ('bev', 'low', 'mid', 'high')):
+        close(got, want, 'pooled ' + name, atol=2e-6, rtol=1e-5)
+    assert vt.grid_config is vt.mask_3_grid        # the reference's leftover grid (LH:455)

@@ -1,0 +1,136 @@
+"""CPU tests of the dense-path oracle and of the plugin boundary:
+(a) oracle/dense_oracle.py reproduces the fixture made from the REAL reference modules;
+(b) where /root/reference exists, it also matches those modules directly;
+(c) the plugin's modules expose the reference's parameter names and shapes;
+(d) the reference's DHD-*.py configs load unchanged and build the hot-path modules."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import dense_oracle as DO
+from oracle import make_golden_dense as MG
+from oracle import ref_loader
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'dense_modules.npz')
+
+
+def plugin_modules():
+    import projects.mmdet3d_plugin  # noqa: F401  (registers)
+    from projects.mmdet3d_plugin.models.dense_heads.occ_head import predictor
+    from projects.mmdet3d_plugin.models.model_utils.depthnet import HeightNet
+    from projects.mmdet3d_plugin.models.necks.mix import SFA
+    hn = HeightNet(256, 256, 65).eval()
+    sfa = SFA(512, 256).eval()
+    head = predictor(in_dim=256, out_dim=256, Dz=16, num_classes=18, use_predicter=True,
+                     class_balance=False, loss_occ=None).eval()
+    return hn, sfa, head, torch.nn.Conv2d(256, 108, 1)
+
+
+def seeded(mods):
+    return [DO.seeded_state_dict(m, s) for m, s in zip(mods, (21, 22, 23, 24))]
+
+
+def test_seeded_weights_reproduce_the_fixture_hashes():
+    gold = np.load(GOLD)
+    sds = seeded(plugin_modules())
+    for name, sd in zip(('heightnet', 'sfa', 'predictor', 'depth_net'), sds):
+        assert MG.sha_sd(sd) == str(gold['sha_' + name]), name
+    x, mlp, bev = MG.inputs()
+    assert hashlib.sha256(b''.join(t.numpy().tobytes() for t in (x, mlp, bev))).hexdigest() == str(gold['input_sha'])
+
+
+def test_oracle_matches_reference_fixture():
+    gold = np.load(GOLD)
+    hn_sd, sfa_sd, head_sd, dn_sd = seeded(plugin_modules())
+    x, mlp, bev = MG.inputs()
+    with torch.no_grad():
+        height = DO.heightnet_forward(hn_sd, x, mlp)
+        y = torch.nn.functional.conv2d(x, dn_sd['weight'], dn_sd['bias'])
+        fused = DO.sfa_forward(sfa_sd, bev)
+        occ = DO.predictor_forward(head_sd, fused)
+    for got, key in ((height, 'height'), (y, 'depth_net'), (fused, 'sfa'), (occ, 'occ')):
+        ref = torch.from_numpy(gold[key])
+        assert got.shape == ref.shape
+        assert torch.allclose(got, ref, rtol=1e-5, atol=2e-5), \
+            '%s: max abs diff %.3g' % (key, (got - ref).abs().max())
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason='reference tree not present')
+def test_oracle_matches_real_reference_modules():
+    hn, sfa, head, dn = MG.build_reference_modules()
+    x, mlp, bev = MG.inputs()
+    for m, s in zip((hn, sfa, head, dn), (21, 22, 23, 24)):
+        m.load_state_dict(DO.seeded_state_dict(m, s))
+    with torch.no_grad():
+        assert torch.allclose(DO.heightnet_forward(hn.state_dict(), x, mlp), hn(x, mlp), rtol=1e-5, atol=2e-5)
+        fused = sfa(bev)
+        assert torch.allclose(DO.sfa_forward(sfa.state_dict(), bev), fused, rtol=1e-5, atol=2e-5)
+        assert torch.allclose(DO.predictor_forward(head.state_dict(), fused), head(fused), rtol=1e-5, atol=2e-5)
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason='reference tree not present')
+def test_plugin_state_dict_names_match_reference():
+    ref = MG.build_reference_modules()
+    ours = plugin_modules()
+    for r, o in zip(ref, ours):
+        rs, os_ = r.state_dict(), o.state_dict()
+        assert list(rs.keys()) == list(os_.keys())
+        for k in rs:
+            assert rs[k].shape == os_[k].shape, k
+    ns = ref_loader.load_reference()
+    from dhd_b200.compat import Config
+    cfg = Config.fromfile(os.path.join(ref_loader.load_reference_configs(), 'DHD-S.py'))
+    vt = dict(cfg.model.img_view_transformer)
+    vt.pop('type')
+    import projects.mmdet3d_plugin.models.necks.lss_heightmap as LH
+    ours_vt, ref_vt = LH.MGHS(**vt), ns.MGHS(**vt)
+    assert list(ours_vt.state_dict().keys()) == list(ref_vt.state_dict().keys())
+    assert torch.equal(ours_vt.frustum, ref_vt.frustum)
+    for a in ('grid_lower_bound', 'grid_interval', 'grid_size'):
+        assert torch.equal(getattr(ours_vt, a), getattr(ref_vt, a))
+    assert ours_vt.D == ref_vt.D and ours_vt.H == ref_vt.H
+    g = torch.Generator().manual_seed(0)
+    args = [torch.randn(2, 6, 4, 4, generator=g), torch.randn(2, 6, 4, 4, generator=g), torch.randn(2, 6, 3, 3, generator=g),
+            torch.randn(2, 6, 3, 3, generator=g), torch.randn(2, 6, 3, generator=g), torch.randn(2, 3, 3, generator=g)]
+    assert torch.equal(ours_vt.get_mlp_input(*args), ref_vt.get_mlp_input(*args))
+    # height-loss path (GT min-pool, binning, BCE) against the reference's own code
+    gt_d = torch.where(torch.rand(1, 6, 256, 704, generator=g) < 0.02, 1 + 50 * torch.rand(1, 6, 256, 704, generator=g), torch.zeros(1))
+    gt_h = torch.where(gt_d > 0, -1.2 + 7 * torch.rand(1, 6, 256, 704, generator=g), torch.zeros(1))
+    h = torch.rand(6, 65, 16, 44, generator=g).softmax(1)
+    for m in (ours_vt, ref_vt):       # the reference computes the loss after view_transform left mask_3_grid behind
+        m.grid_config = m.mask_3_grid
+    assert torch.equal(ours_vt.get_downsampled_gt_depth(gt_d), ref_vt.get_downsampled_gt_depth(gt_d))
+    assert torch.equal(ours_vt.get_downsampled_gt_height(gt_h), ref_vt.get_downsampled_gt_height(gt_h))
+    assert torch.allclose(ours_vt.get_height_loss(gt_d, gt_h, h), ref_vt.get_height_loss(gt_d, gt_h, h), rtol=1e-6)
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason='reference tree not present')
+@pytest.mark.parametrize('name', ['DHD-S.py', 'DHD-M.py', 'DHD-L.py'])
+def test_reference_configs_load_unchanged(name):
+    import projects.mmdet3d_plugin  # noqa: F401
+    from dhd_b200 import compat as C
+    cfg = C.Config.fromfile(os.path.join(ref_loader.load_reference_configs(), name))
+    assert cfg.plugin and cfg.plugin_dir == 'projects/mmdet3d_plugin/'
+    assert cfg.dist_params.backend == 'nccl'            # from the un-vendored _base_ fallback
+    assert cfg.model.type in ('DHD', 'DHD_stereo')
+    if name == 'DHD-S.py':
+        model = C.build_model(cfg.model)
+        vt = model.img_view_transformer
+        assert (vt.D, vt.H, vt.out_channels) == (44, 65, 64)
+        assert type(model.mix).__name__ == 'SFA' and type(model.occ_head).__name__ == 'predictor'
+        assert model.occ_head.cls_weights.shape == (18,)
+    cfg.merge_from_dict({'model.img_view_transformer.accelerate': True})
+    assert cfg.model.img_view_transformer.accelerate is True
+
+
+def test_dense_modules_refuse_cpu_tensors():
+    hn, sfa, head, _ = plugin_modules()
+    with pytest.raises(RuntimeError, match='CUDA'):
+        sfa(torch.zeros(1, 512, 8, 16))
+    with pytest.raises(RuntimeError, match='CUDA'):
+        head(torch.zeros(1, 256, 8, 16))
+    with pytest.raises(RuntimeError, match='CUDA'):
+        hn(torch.zeros(1, 256, 8, 16), torch.zeros(1, 1, 27))
