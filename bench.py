@@ -28,7 +28,7 @@ if ROOT not in sys.path:
 
 import torch  # noqa: E402
 
-METRIC = 'samples/s DHD-S 6-cam 256x704 hot path (view transform + voxel pool)'
+METRIC = 'samples/s DHD-S 6-cam 256x704 hot path (DepthNet/HeightNet, MGHS view transform + voxel pool, SFA, occupancy head)'
 UNIT = 'samples/s'
 B_PER_GPU = 4
 
@@ -39,7 +39,8 @@ def parse():
     ap.add_argument('--steps', type=int, default=30)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--layout', default='nhwc', choices=['nhwc', 'nchw'])
+    ap.add_argument('--precision', default='bf16', choices=['bf16', 'bf16x3', 'fp32'])
+    ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     return ap.parse_args()
 
@@ -98,8 +99,9 @@ class ClockSampler:
 # --------------------------------------------------------------------------- our arm
 def run_ours(args):
     import torch.distributed as dist
-    from dhd_b200.pipeline import HotPathStep, algorithmic_bytes
-    from oracle import mghs_oracle as O   # synthetic input generator + cpu_baseline leg only
+    from dhd_b200 import _lib
+    from dhd_b200.pipeline import HotPathStep, algorithmic_bytes, dense_flops
+    from oracle import mghs_oracle as O   # synthetic camera rig + the cpu_baseline leg only
 
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
@@ -109,10 +111,12 @@ def run_ours(args):
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     cfg = O.DHD_S
     B = B_PER_GPU
-    inputs, depth, feat, height = O.synthetic_inputs(cfg, B, seed=100 + rank)
-    step = HotPathStep(cfg, B, layout=args.layout)
-    host = step.pin_host_inputs(inputs, depth, feat, height)      # pinned host copies
-    dev = step.to_device(host)                                    # resident copies
+    step = HotPathStep(cfg, B, precision=args.precision, use_graph=not args.no_graph)
+    rig = O.synthetic_rig(B, cfg['ncams'], cfg['input_size'], seed=100 + rank)
+    host = step.make_host_inputs(rig, seed=100 + rank)          # pinned host copies
+    step.alloc_static(host)
+    step.upload(host)                                           # resident copies
+    graphed = step.capture()
     st = torch.cuda.current_stream()
 
     def barrier():
@@ -121,10 +125,10 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     for _ in range(max(args.warmup, 3)):
-        step.run(dev)
+        step.run()
     barrier()
 
-    # ---- device-resident timing (value) + per-launch timing of the dominant kernel
+    # ---- device-resident timing (value) + in-place timing of the dominant HBM kernel
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -134,14 +138,14 @@ def run_ours(args):
     barrier()
     ev0.record(st)
     for i in range(args.steps):
-        step.run(dev, pool_events=kev[i])
+        step.run(pool_events=kev[i])
     ev1.record(st)
     barrier()
     ms_total = ev0.elapsed_time(ev1)
     pool_ms = sorted(a.elapsed_time(b) for a, b in kev)
     pool_ms_avg = sum(pool_ms) / len(pool_ms)
 
-    # ---- end to end: pinned host inputs -> H2D -> step -> D2H of the step result
+    # ---- end to end: pinned host inputs -> H2D -> step -> D2H of the occupancy class map
     for _ in range(3):
         step.run_e2e(host)
     barrier()
@@ -154,6 +158,30 @@ def run_ours(args):
     ms_e2e = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---- extras: pool backward (a10) and per-stage times, outside the timed regions
+    b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(3):
+        step.run_pool_bwd()
+    b0.record(st)
+    for _ in range(10):
+        step.run_pool_bwd()
+    b1.record(st)
+    torch.cuda.synchronize()
+    bwd_ms = b0.elapsed_time(b1) / 10
+    stage_ms = {}
+    for name, fn in (('front(pack+depth_net+HeightNet+mask+prepare)', step._front), ('pool_fwd', step._pool),
+                     ('back(split+SFA+predictor+argmax)', step._back)):
+        if step.graph is not None and name != 'pool_fwd':
+            fn = step.graph[0].replay if name.startswith('front') else step.graph[1].replay
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        fn()
+        s0.record(st)
+        for _ in range(5):
+            fn()
+        s1.record(st)
+        torch.cuda.synchronize()
+        stage_ms[name] = s0.elapsed_time(s1) / 5
+
     t = torch.tensor([ms_total, ms_e2e, pool_ms_avg], device='cuda', dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -162,26 +190,31 @@ def run_ours(args):
     if rank == 0:
         peak, peak_src = peaks()
         alg = algorithmic_bytes(cfg, B)
+        fl = dense_flops(cfg, B)
         achieved = alg['pool_fwd_bytes'] / (pool_ms_avg * 1e-3) / 1e9
         line = {
             'metric': METRIC, 'value': world * B * args.steps / (ms_total * 1e-3), 'unit': UNIT,
             'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
             'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'vs_baseline': None, 'dtype': {'bf16': 'bf16', 'bf16x3': 'bf16x3 (split-bf16)',
+                                           'fp32': 'f32 (6-term split-bf16)'}[args.precision],
+            'data': 'synthetic',
             'config': {
-                'workload': 'BASELINE configs[1]: DHD-S, 6-cam 256x704 -> 16x44 feats, D=44, C=64, '
-                            'grids 200x200x{1,4,4,8}, batch=%d per GPU' % B,
-                'stages': step.stage_names(), 'layout': args.layout, 'samples_per_gpu': B,
-                'l2': 'pool output working set %.0f MB per step > 126 MB L2 (no explicit flush)'
-                      % (alg['pool_fwd_bytes'] / 1e6),
+                'workload': 'BASELINE configs[1]: DHD-S hot path inference, 6-cam 256x704 -> 16x44x256 image '
+                            'features, D=44, C=64, grids 200x200x{1,4,4,8}, SFA 512->256 + predictor @200x200, '
+                            'batch=%d per GPU; random-init weights' % B,
+                'stages': step.stage_names(), 'samples_per_gpu': B, 'precision': args.precision,
+                'pool_arithmetic': 'f32', 'cuda_graph': bool(graphed),
+                'encoders': 'BEV/voxel encoders are outside the path: resident synthetic (B,512,200,200) features',
+                'l2': 'per-step working set > 1 GB (pool outputs 696 MB, BEV activations) > 126 MB L2, no explicit flush',
                 'sharding': 'batch axis, one process per GPU, no data-path collective',
             },
             'clocks': clocks,
             'e2e': {'value': world * B * args.steps / (ms_e2e * 1e-3), 'unit': UNIT,
                     'h2d_bytes_per_step': step.h2d_bytes, 'd2h_bytes_per_step': step.d2h_bytes},
-            'gpu_launches': step.launches_per_step * args.steps,
+            'gpu_launches': step.launches_per_step * args.steps * 2,
             'roofline': {
-                'kernel': 'mghs_pool_%s_kernel (fused 4-pass voxel pool forward)' % args.layout,
+                'kernel': 'mghs_pool_nhwc_smem_kernel (fused 4-pass voxel pool forward)',
                 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                 'frac': achieved / peak, 'frac_of_nominal_8TBs': achieved / 8000.0,
                 'peak_source': peak_src, 'traffic': step.ncu_traffic_bytes(),
@@ -189,28 +222,62 @@ def run_ours(args):
                 'kernel_ms_avg': pool_ms_avg, 'kernel_ms_min': pool_ms[0],
                 'kernel_share_of_step': pool_ms_avg / (ms_total / args.steps),
             },
+            'extras': {
+                'stage_ms': stage_ms, 'pool_bwd_ms': bwd_ms,
+                'dense_tflops_algorithmic': {k: v / 1e12 for k, v in fl.items()},
+                'dense_tflop_per_s': sum(fl.values()) / 1e12 /
+                (1e-3 * max(1e-9, stage_ms['front(pack+depth_net+HeightNet+mask+prepare)'] +
+                            stage_ms['back(split+SFA+predictor+argmax)'])),
+                'launches_per_step': step.launches_per_step,
+                'graph_error': getattr(step, 'graph_error', None),
+            },
         }
         if world == 1 and not args.no_cpu_baseline:
-            line['cpu_baseline'] = cpu_reference_leg(cfg, seconds=15.0)
+            line['cpu_baseline'] = cpu_reference_leg(cfg, seconds=20.0)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
 # ----------------------------------------------------------------------- CPU oracle leg
+_CPU_STATE = {}
+
+
 def cpu_step(cfg, B, seed, threads):
-    """One pass of the reference algorithm on the host: the oracle port of MGHS.view_transform
-    (4x get_ego_coor-equivalent geometry, prepare, pool) + the pool backward."""
+    """One pass of the reference algorithm on the host for B samples: dense front (depth_net,
+    HeightNet), the oracle port of MGHS.view_transform (4x geometry, prepare, pool), SFA and
+    predictor on synthetic encoder features, class argmax -- the same stages as the GPU step."""
+    from oracle import dense_oracle as DO
     from oracle import mghs_oracle as O
     O._PoolFn.threads = threads
-    inputs, depth, feat, height = O.synthetic_inputs(cfg, B, seed=seed)
+    if 'sd' not in _CPU_STATE:
+        import projects.mmdet3d_plugin  # noqa: F401  (parameter containers only; forward is the oracle's)
+        from projects.mmdet3d_plugin.models.dense_heads.occ_head import predictor
+        from projects.mmdet3d_plugin.models.model_utils.depthnet import HeightNet
+        from projects.mmdet3d_plugin.models.necks.mix import SFA
+        torch.manual_seed(0)
+        _CPU_STATE['sd'] = (HeightNet(256, 256, 65).eval().state_dict(), torch.nn.Conv2d(256, 108, 1).state_dict(),
+                            SFA(512, 256).eval().state_dict(),
+                            predictor(256, 256, 16, num_classes=18, loss_occ=None).eval().state_dict())
+    hn_sd, dn_sd, sfa_sd, head_sd = _CPU_STATE['sd']
+    N = cfg['ncams']
+    fH, fW = cfg['input_size'][0] // cfg['downsample'], cfg['input_size'][1] // cfg['downsample']
+    rig = O.synthetic_rig(B, N, cfg['input_size'], seed=seed)
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B * N, 256, fH, fW, generator=g)
+    enc = torch.randn(B, 512, 200, 200, generator=g)
     fr = O.frustum(cfg['depth'], cfg['input_size'], cfg['downsample'])
-    depth = depth.requires_grad_()
-    feat = feat.requires_grad_()
     t0 = time.perf_counter()
-    outs = O.view_transform(inputs, depth, feat, height, fr, cfg['height_range'], cfg['mask_range'],
-                            cfg['mask_grids'])
-    sum(o.sum() for o in outs).backward()
+    with torch.no_grad():
+        y = torch.nn.functional.conv2d(x, dn_sd['weight'], dn_sd['bias'])
+        depth, feat = y[:, :44].softmax(1), y[:, 44:].contiguous()
+        s2e, e2g, K, pr, pt, bda = rig
+        mlp = torch.zeros(B, N, 27)
+        height = DO.heightnet_forward(hn_sd, x, mlp).softmax(1)
+        inputs = (torch.zeros(B, N, 1, fH, fW),) + tuple(rig)
+        O.view_transform(inputs, depth, feat, height, fr, cfg['height_range'], cfg['mask_range'], cfg['mask_grids'])
+        occ = DO.predictor_forward(head_sd, DO.sfa_forward(sfa_sd, enc))
+        occ.argmax(-1).to(torch.uint8)
     return time.perf_counter() - t0
 
 
@@ -223,8 +290,9 @@ def cpu_reference_leg(cfg, seconds):
         t += cpu_step(cfg, 1, n + 1, cores)
         n += 1
     return {'value': n / t, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-            'sample': '%d steps of B=1 DHD-S samples (view_transform fwd + pool bwd), oracle port '
-                      'of the reference Python + C restatement of its CUDA kernels, %.1f s' % (n, t)}
+            'sample': '%d steps of B=1 DHD-S samples (same stages as the GPU step: dense front, 4-pass view '
+                      'transform, SFA, predictor, argmax); oracle port = reference Python + torch CPU convs + '
+                      'C restatement of the bev_pool_v2 kernels, %.1f s' % (n, t)}
 
 
 def run_reference(args):
@@ -235,20 +303,25 @@ def run_reference(args):
     cfg = O.DHD_S
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    for i in range(max(1, min(args.warmup, 2))):
+    warm = max(1, min(args.warmup, 2))
+    for i in range(warm):
         cpu_step(cfg, 1, i, cores)
     steps = min(args.steps, 20)
     t = 0.0
     for i in range(steps):
         t += cpu_step(cfg, 1, 10 + i, cores)
+        if t > 120 and i >= 2:
+            steps = i + 1
+            break
     v = steps / t
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus,
-        'steps': steps, 'warmup': max(1, min(args.warmup, 2)), 'ms_per_step': 1e3 * t / steps,
+        'steps': steps, 'warmup': warm, 'ms_per_step': 1e3 * t / steps,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
         'data': 'synthetic',
-        'config': {'workload': 'BASELINE configs[1] DHD-S hot path on the host cores; each step a '
-                               'bounded sample of B=1 (one 6-camera frame set)'},
+        'config': {'workload': 'BASELINE configs[1] DHD-S hot path inference on the host cores (reference '
+                               'algorithm: oracle port, the reference ships no CPU kernel for bev_pool_v2); '
+                               'each step a bounded sample of B=1 (one 6-camera frame set)'},
         'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                          'sample': '%d steps of B=1' % steps},
         'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},

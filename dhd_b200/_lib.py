@@ -50,6 +50,8 @@ _SIGNATURES = {
     'dhd_mghs_voxel_index': (ctypes.c_int, [ctypes.POINTER(MghsCfg), _P, _P, _P]),
     'dhd_conv2d_fwd': (ctypes.c_int, [_P, _P]),
     'dhd_pack_nchw_to_nhwc': (ctypes.c_int, [_P] + [_I] * 4 + [_P] + [_I] * 4 + [_P]),
+    'dhd_occ_argmax': (ctypes.c_int, [_P, ctypes.c_long, _I, _P, _P]),
+    'dhd_launch_count': (ctypes.c_long, []),
     'dhd_split_nhwc': (ctypes.c_int, [_P, ctypes.c_long, _I, _P] + [_I] * 4 + [_P]),
     'dhd_unpack_nhwc_to_nchw': (ctypes.c_int, [_P] + [_I] * 8 + [_P, _P]),
     'dhd_mean_hw': (ctypes.c_int, [_P] + [_I] * 7 + [_P, _P]),

@@ -20,8 +20,11 @@ inline int fail(int code, const char* fmt, const char* a = "", long b = 0, long 
     if (!(cond)) return ::dhd::fail(DHD_EINVAL, "%s (" #cond ")", msg);            \
   } while (0)
 
+extern long g_launches;  // kernels enqueued by this library since load (bench bookkeeping)
+
 #define DHD_CUDA_LAUNCH_CHECK(name)                                               \
   do {                                                                            \
+    ++::dhd::g_launches;                                                          \
     cudaError_t e__ = cudaGetLastError();                                         \
     if (e__ != cudaSuccess)                                                       \
       return ::dhd::fail((int)e__, "%s launch failed: %ld", name, (long)e__);      \

@@ -230,9 +230,39 @@ dcn_im2col_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int x_coff, int
   }
 }
 
+// ---- occupancy class map: argmax over the class logits (softmax is monotone, so
+// predictor.get_occ's softmax -> argmax -> uint8, occ_head.py:141-153, is the argmax of the logits;
+// first maximum wins as in torch.argmax).  One thread per voxel, logits [voxel][ncls] fp32.
+__global__ void __launch_bounds__(256)
+occ_argmax_kernel(const float* __restrict__ logits, long nvox, int ncls, uint8_t* __restrict__ out) {
+  const long v = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= nvox) return;
+  const float* row = logits + v * ncls;
+  float best = row[0];
+  int arg = 0;
+  for (int k = 1; k < ncls; ++k) {
+    const float x = row[k];
+    if (x > best) {
+      best = x;
+      arg = k;
+    }
+  }
+  out[v] = (uint8_t)arg;
+}
+
 }  // namespace dhd
 
 using namespace dhd;
+
+extern "C" long dhd_launch_count(void) { return g_launches; }
+
+extern "C" int dhd_occ_argmax(const float* logits, long nvox, int ncls, uint8_t* out, void* stream) {
+  DHD_REQUIRE(logits && out, "null pointer");
+  DHD_REQUIRE(nvox > 0 && ncls > 0 && ncls <= 256, "bad shape");
+  occ_argmax_kernel<<<(int)((nvox + 255) / 256), 256, 0, (cudaStream_t)stream>>>(logits, nvox, ncls, out);
+  DHD_CUDA_LAUNCH_CHECK("occ_argmax");
+  return DHD_OK;
+}
 
 extern "C" int dhd_pack_nchw_to_nhwc(const float* in, int N, int C, int H, int W, void* out, int out_ld,
                                      int out_coff, int part_stride, int parts, void* stream) {

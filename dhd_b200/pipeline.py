@@ -1,20 +1,31 @@
-"""The hot path as one re-runnable step (used by bench.py and the multi-GPU harness).
+"""The hot path as one re-runnable inference step (bench.py and the multi-GPU harness).
 
-Stages implemented here run only through the C-ABI library; torch provides device
-memory, pinned host buffers, streams and events.  Per step and per GPU (DHD-S, B samples):
+Per step and per GPU (DHD-S, B samples = 6B camera images), everything through the C-ABI library:
 
-  height_to_mask   argmax over the height distribution -> per-pixel mask id      (a5)
-  mghs_prepare     fused get_ego_coor + quantise + bin by BEV cell, once for all
-                   four passes (geom_count, scan_local, scan_blocks, scatter,
-                   canonical)                                                     (a7, a8)
-  mghs_pool_fwd    masked lift (x) splat, four grids, single write              (a6, a9, a11)
-  mghs_pool_bwd    depth / context gradients of the four passes                   (a10)
+  front   pack (fp32 NCHW image features -> NHWC split-bf16)            dhd_pack_nchw_to_nhwc
+          depth_net 1x1 + softmax / context split                       dhd_conv2d_fwd        (a3)
+          HeightNet (19 tcgen05 convs, SE gate, ASPP, DCN) + softmax    dhd_conv2d_fwd, ...   (a4)
+  pool    height -> mask id                                             dhd_height_to_mask    (a5)
+          geometry + binning of the four grids                          dhd_mghs_prepare      (a7, a8)
+          fused masked lift-splat, four BEV tensors, single write       dhd_mghs_pool_fwd     (a6, a9, a11)
+  back    [BEV / voxel encoders: outside the path -> resident synthetic (B,512,Dy,Dx) features]
+          split to bf16, SFA (5 convs + gates), predictor (3 GEMMs)     dhd_conv2d_fwd, ...   (a14, a15)
+          class map (argmax over 18 classes) uint8                      dhd_occ_argmax
+
+The front and the back of the step are captured into two CUDA graphs (launch-bound otherwise:
+~75 kernels); the pool kernel between them is an eager launch so it can be timed in place.
+The pool backward (a10) is timed separately by bench.py (`extras`), the dense layers being
+inference-only in this build.
 """
+import ctypes
 import json
 import os
 
 import torch
 
+from . import _lib
+from . import dense as D
+from .modules import DepthHeadEngine, HeightNetEngine, PredictorEngine, SFAEngine
 from .pool import MghsPool, height_to_mask
 
 _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -26,7 +37,7 @@ def algorithmic_bytes(cfg, B):
     N = cfg['ncams']
     h, w = cfg['input_size']
     fH, fW = h // cfg['downsample'], w // cfg['downsample']
-    D = len(range(int(cfg['depth'][0]), int(cfg['depth'][1]), int(cfg['depth'][2])))
+    D_ = len(range(int(cfg['depth'][0]), int(cfg['depth'][1]), int(cfg['depth'][2])))
     C = cfg['C']
     P = B * N * fH * fW
     grids = [cfg['bev_grid']] + list(cfg['mask_grids'])
@@ -36,122 +47,204 @@ def algorithmic_bytes(cfg, B):
         dy = int(round((g['y'][1] - g['y'][0]) / g['y'][2]))
         dz = int(round((g['z'][1] - g['z'][0]) / g['z'][2]))
         out_elems += B * dz * dy * dx * C
-    reads = P * D * 4 + P * C * 4 + P
+    reads = P * D_ * 4 + P * C * 4 + P
     return {'pool_fwd_bytes': reads + out_elems * 4,
-            'pool_bwd_bytes': out_elems * 4 + reads + P * D * 4 + P * C * 4,
+            'pool_bwd_bytes': out_elems * 4 + reads + P * D_ * 4 + P * C * 4,
             'pool_out_bytes': out_elems * 4}
 
 
+def dense_flops(cfg, B, Dy=200, Dx=200):
+    """Algorithmic forward FLOPs (2*M*N*K per conv) of the dense stages, for the report."""
+    N = cfg['ncams']
+    h, w = cfg['input_size']
+    M = B * N * (h // cfg['downsample']) * (w // cfg['downsample'])
+    c = 256
+    hn = M * c * c * 2 * (9 + 6 * 9 + 1 + 3 * 9 + 4 + 9 / 4) + M * c * 2 * (18 * 9 + 65)
+    dn = M * c * 108 * 2
+    Mb = B * Dy * Dx
+    sfa = Mb * 2 * (256 * 256 * 2 + 512 * 256 + 2 * 9 * 256 * 256)
+    head = Mb * 2 * (9 * 256 * 256 + 256 * 512 + 512 * 288)
+    return {'heightnet': hn, 'depth_net': dn, 'sfa': sfa, 'predictor': head}
+
+
 class HotPathStep:
-    def __init__(self, cfg, B, layout='nhwc', deterministic=True, device='cuda'):
-        self.cfg, self.B, self.layout, self.deterministic = cfg, B, layout, deterministic
+    def __init__(self, cfg, B, precision='bf16', deterministic=True, device='cuda', seed=0,
+                 use_graph=True):
+        from projects.mmdet3d_plugin.models.dense_heads.occ_head import predictor
+        from projects.mmdet3d_plugin.models.necks.lss_heightmap import MGHS
+        from projects.mmdet3d_plugin.models.necks.mix import SFA
+        self.cfg, self.B, self.precision, self.deterministic = cfg, B, precision, deterministic
+        self.parts = D.PRECISIONS[precision][0]
         self.N = cfg['ncams']
         h, w = cfg['input_size']
         self.fH, self.fW = h // cfg['downsample'], w // cfg['downsample']
-        self.D = torch.arange(*cfg['depth']).numel()
-        self.C = cfg['C']
-        grids = [cfg['bev_grid']] + list(cfg['mask_grids'])
-        self.plan = MghsPool(B, self.N, self.D, self.fH, self.fW, self.C, grids[0]['x'], grids[0]['y'],
-                             [(g['z'], m) for m, g in enumerate(grids)])
+        self.C, self.Cin = cfg['C'], cfg['C_in']
         self.device = torch.device(device)
+        g = cfg['mask_grids']
+        torch.manual_seed(seed)               # random-init weights of the DHD-S architecture
+        self.vt = MGHS(grid_config=dict(cfg['bev_grid'], depth=cfg['depth']), input_size=cfg['input_size'],
+                       in_channels=self.Cin, out_channels=self.C, height_range=cfg['height_range'],
+                       height_interval=0.1, mask_range=cfg['mask_range'],
+                       mask_1_grid=dict(g[0], depth=cfg['depth']), mask_2_grid=dict(g[1], depth=cfg['depth']),
+                       mask_3_grid=dict(g[2], depth=cfg['depth']), downsample=cfg['downsample'],
+                       precision=precision).eval().to(self.device)
+        self.sfa = SFA(512, 256, precision=precision).eval().to(self.device)
+        self.head = predictor(in_dim=256, out_dim=256, Dz=16, num_classes=18, use_predicter=True,
+                              class_balance=False, loss_occ=None, precision=precision).eval().to(self.device)
+        self.D = self.vt.D
+        self.depth_engine = DepthHeadEngine(self.vt.depth_net, self.D, precision, self.device)
+        self.height_engine = HeightNetEngine(self.vt.height_net, precision, self.device)
+        self.sfa_engine = SFAEngine(self.sfa, precision, self.device)
+        self.head_engine = PredictorEngine(self.head, precision, self.device)
+        grids = [cfg['bev_grid']] + list(g)
+        self.plan = MghsPool(B, self.N, self.D, self.fH, self.fW, self.C, grids[0]['x'], grids[0]['y'],
+                             [(gr['z'], m) for m, gr in enumerate(grids)])
+        self.Dy, self.Dx = self.plan.Dy, self.plan.Dx
         self.workspace = torch.empty(self.plan.ws_bytes, dtype=torch.uint8, device=self.device)
-        self.outs = self.plan.alloc_outputs(layout, self.device)
-        g = torch.Generator(device=self.device).manual_seed(7)
-        # upstream gradients of the four BEV tensors (what the encoders hand back), resident
-        self.gouts = [torch.randn(o.shape if layout == 'nhwc' else
-                                  (B, self.plan.Dy, self.plan.Dx, dz * self.C),
-                                  device=self.device, generator=g)
-                      for o, dz in zip(self.outs, self.plan.dz)]
+        self.outs = self.plan.alloc_outputs('nhwc', self.device)
+        self.frustum = self.vt.frustum.to(self.device)
+        gen = torch.Generator(device=self.device).manual_seed(7)
+        # stand-in for the (out-of-scope) BEV / voxel encoders' output: channels-last fp32
+        self.encoded = torch.randn(B, self.Dy, self.Dx, 512, device=self.device, generator=gen)
+        self.occ = torch.empty(B, self.Dx, self.Dy, 16, dtype=torch.uint8, device=self.device)
+        self.host_occ = torch.empty(self.occ.shape, dtype=torch.uint8, pin_memory=True)
+        # pool backward leg (timed separately)
+        self.gouts = [torch.randn(o.shape, device=self.device, generator=gen) for o in self.outs]
         self.depth_grad = torch.empty(B * self.N, self.D, self.fH, self.fW, device=self.device)
         self.feat_grad = torch.empty(B, self.N, self.fH, self.fW, self.C, device=self.device)
-        self.host_dgrad = torch.empty(self.depth_grad.shape, pin_memory=True)
-        self.host_fgrad = torch.empty(self.feat_grad.shape, pin_memory=True)
-        self.height_range = cfg['height_range']
-        self.mask_range = cfg['mask_range']
         self.h2d_bytes = 0
-        self.d2h_bytes = self.host_dgrad.numel() * 4 + self.host_fgrad.numel() * 4
-        self.launches_per_step = 1 + (5 if deterministic else 4) + 1 + 1
-        self._dev_e2e = None
+        self.d2h_bytes = self.host_occ.numel()
+        self.use_graph = use_graph
+        self.graph = None
+        self.static = None
+        self.launches_per_step = None
+        self._last = {}
 
     def stage_names(self):
-        return ['height_to_mask', 'mghs_prepare(geometry+binning, all 4 passes)',
-                'mghs_pool_fwd(%s)' % self.layout, 'mghs_pool_bwd(nhwc grads)']
+        return ['pack', 'depth_net(1x1+softmax)', 'HeightNet(+softmax)', 'height_to_mask',
+                'mghs_prepare(geometry+binning, 4 grids)', 'mghs_pool_fwd(nhwc, fused 4-pass)',
+                'split(encoder stand-in -> bf16)', 'SFA', 'predictor', 'occ_argmax']
 
-    # ---- inputs ---------------------------------------------------------------------
-    def pin_host_inputs(self, inputs, depth, feat, height):
-        """Host-side (pinned) step inputs in the layouts the plugin call takes."""
-        from .pool import grid_infos  # noqa: F401  (kept for symmetry with MGHS)
-        x, s2e, e2g, K, pr, pt, bda = inputs
-        B, N, C = self.B, self.N, self.C
-        h = {
-            'depth': depth.contiguous(),
-            'feat': feat.view(B, N, C, self.fH, self.fW).permute(0, 1, 3, 4, 2).contiguous(),
-            'height': height.contiguous(),
-            'sensor2ego': s2e.contiguous(), 'cam2imgs': K.contiguous(), 'post_rots': pr.contiguous(),
-            'post_trans': pt.contiguous(), 'bda': bda.contiguous(),
-        }
+    # ---- inputs -----------------------------------------------------------------------------
+    def make_host_inputs(self, rig, seed):
+        """Pinned host buffers of one step: image features + camera geometry."""
+        s2e, e2g, K, pr, pt, bda = rig
+        g = torch.Generator().manual_seed(seed)
+        x = torch.randn(self.B, self.N, self.Cin, self.fH, self.fW, generator=g)
+        h = {'x': x, 'sensor2ego': s2e.contiguous(), 'ego2global': e2g.contiguous(), 'cam2imgs': K.contiguous(),
+             'post_rots': pr.contiguous(), 'post_trans': pt.contiguous(), 'bda': bda.contiguous()}
         h = {k: v.pin_memory() for k, v in h.items()}
         self.h2d_bytes = sum(v.numel() * v.element_size() for v in h.values())
         return h
 
-    def frustum(self):
-        """create_frustum (lss_heightmap.py:105-134), sid=False."""
-        cfg = self.cfg
-        h_in, w_in = cfg['input_size']
-        d = torch.arange(*cfg['depth'], dtype=torch.float).view(-1, 1, 1).expand(-1, self.fH, self.fW)
-        xs = torch.linspace(0, w_in - 1, self.fW, dtype=torch.float).view(1, 1, self.fW).expand(self.D, self.fH, self.fW)
-        ys = torch.linspace(0, h_in - 1, self.fH, dtype=torch.float).view(1, self.fH, 1).expand(self.D, self.fH, self.fW)
-        return torch.stack((xs, ys, d), -1)
+    def alloc_static(self, host):
+        self.static = {k: torch.empty(v.shape, dtype=v.dtype, device=self.device) for k, v in host.items()}
+        return self.static
 
-    def to_device(self, host):
-        dev = {k: v.to(self.device, non_blocking=True) for k, v in host.items()}
-        dev['frustum'] = self.frustum().to(self.device)
-        return dev
+    def upload(self, host):
+        for k, v in host.items():
+            self.static[k].copy_(v, non_blocking=True)
 
-    # ---- one step ----------------------------------------------------------------------
-    def run(self, dev, pool_events=None):
-        pixmask = height_to_mask(dev['height'], self.height_range, self.mask_range)
-        self.plan.prepare(frustum=dev['frustum'], sensor2ego=dev['sensor2ego'],
-                          cam2imgs=dev['cam2imgs'], post_rots=dev['post_rots'],
-                          post_trans=dev['post_trans'], bda=dev['bda'],
+    # ---- one step ---------------------------------------------------------------------------
+    def _front(self):
+        s = self.static
+        B, N = self.B, self.N
+        xa = D.pack_input(s['x'].view(B * N, self.Cin, self.fH, self.fW), self.parts)
+        depth, feat = self.depth_engine(xa)
+        mlp = self.vt.get_mlp_input(s['sensor2ego'], s['ego2global'], s['cam2imgs'], s['post_rots'],
+                                    s['post_trans'], s['bda'])
+        height = self.height_engine(xa, mlp, softmax=True)
+        pixmask = height_to_mask(height, self.cfg['height_range'], self.cfg['mask_range'])
+        self.plan.prepare(frustum=self.frustum, sensor2ego=s['sensor2ego'], cam2imgs=s['cam2imgs'],
+                          post_rots=s['post_rots'], post_trans=s['post_trans'], bda=s['bda'],
                           deterministic=self.deterministic, workspace=self.workspace)
+        self._last = {'depth': depth, 'feat': feat, 'height': height, 'pixmask': pixmask}
+
+    def _pool(self):
+        L = self._last
+        self.plan.raw_forward(L['depth'], L['feat'], L['pixmask'], self.outs, 'nhwc', workspace=self.workspace)
+
+    def _back(self):
+        enc = D.pack_nhwc(self.encoded, self.parts)
+        fused = self.sfa_engine(enc)
+        logits = self.head_engine(fused)
+        _lib.check(_lib.load().dhd_occ_argmax(ctypes.c_void_p(logits.data_ptr()), self.occ.numel(), 18,
+                                              ctypes.c_void_p(self.occ.data_ptr()),
+                                              ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                   'occ_argmax')
+        self._logits = logits
+
+    def capture(self):
+        """Warm up eagerly, count this library's launches for one step, then capture the front and
+        the back of the step into two CUDA graphs; the pool kernel between them stays an eager
+        launch so bench.py can bracket it with CUDA events inside the timed region."""
+        lib = _lib.load()
+        for _ in range(2):
+            n0 = lib.dhd_launch_count()
+            self._front(); self._pool(); self._back()
+            torch.cuda.synchronize()
+            self.launches_per_step = lib.dhd_launch_count() - n0
+        if not self.use_graph:
+            return False
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self._front(); self._pool(); self._back()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g1):
+                self._front()
+            with torch.cuda.graph(g2):
+                self._back()
+            self.graph = (g1, g2)
+            return True
+        except Exception as e:  # noqa: BLE001  (capture unsupported by some torch op: run eagerly)
+            self.graph = None
+            self.graph_error = repr(e)[:300]
+            torch.cuda.synchronize()
+            return False
+
+    def run(self, pool_events=None):
         st = torch.cuda.current_stream()
+        if self.graph is not None:
+            self.graph[0].replay()
+        else:
+            self._front()
         if pool_events is not None:
             pool_events[0].record(st)
-        self.plan.raw_forward(dev['depth'], dev['feat'], pixmask, self.outs, self.layout)
+        self._pool()
         if pool_events is not None:
             pool_events[1].record(st)
-        import ctypes
-        from . import _lib
+        if self.graph is not None:
+            self.graph[1].replay()
+        else:
+            self._back()
+
+    def run_e2e(self, host):
+        """Host buffers in, host buffer out: H2D of the step inputs, the step, D2H of the class map."""
+        self.upload(host)
+        self.run()
+        self.host_occ.copy_(self.occ, non_blocking=True)
+
+    def run_pool_bwd(self):
+        st = torch.cuda.current_stream()
         arr = (ctypes.c_void_p * len(self.gouts))(*[g.data_ptr() for g in self.gouts])
+        L = self._last
         _lib.check(self.plan._lib.dhd_mghs_pool_bwd(
-            ctypes.byref(self.plan.cfg), ctypes.c_void_p(dev['depth'].data_ptr()),
-            ctypes.c_void_p(dev['feat'].data_ptr()), ctypes.c_void_p(pixmask.data_ptr()),
+            ctypes.byref(self.plan.cfg), ctypes.c_void_p(L['depth'].data_ptr()),
+            ctypes.c_void_p(L['feat'].data_ptr()), ctypes.c_void_p(L['pixmask'].data_ptr()),
             ctypes.c_void_p(self.workspace.data_ptr()), arr, 0,
             ctypes.c_void_p(self.depth_grad.data_ptr()), ctypes.c_void_p(self.feat_grad.data_ptr()),
             ctypes.c_void_p(st.cuda_stream)), 'mghs_pool_bwd')
-        self._keep = pixmask
-
-    def run_e2e(self, host):
-        """Host buffers in, host buffers out: H2D of every step input, the step, D2H of the
-        step result (depth / context gradients)."""
-        if self._dev_e2e is None:
-            self._dev_e2e = {'frustum': self.frustum().to(self.device)}
-        d = self._dev_e2e
-        for k, v in host.items():
-            if k not in d:
-                d[k] = torch.empty(v.shape, dtype=v.dtype, device=self.device)
-            d[k].copy_(v, non_blocking=True)
-        self.run(d)
-        self.host_dgrad.copy_(self.depth_grad, non_blocking=True)
-        self.host_fgrad.copy_(self.feat_grad, non_blocking=True)
 
     def ncu_traffic_bytes(self):
         """dram read+write bytes per launch of the pool kernel from the committed ncu capture."""
-        p = os.path.join(_ROOT, 'profiles', 'pool_fwd_%s_traffic.json' % self.layout)
+        p = os.path.join(_ROOT, 'profiles', 'pool_fwd_traffic.json')
         if os.path.exists(p):
             try:
                 return json.load(open(p)).get('dram_bytes_per_launch')
-            except Exception:
+            except Exception:  # noqa: BLE001
                 return None
         return None

@@ -91,6 +91,9 @@ def bev_pool_v2(depth, feat, ranks_depth, ranks_feat, ranks_bev, bev_feat_shape,
 
 
 # ------------------------------------------------------------------ height -> mask id
+_TABLES = {}
+
+
 def height_to_mask(height, height_range, thresholds):
     """(BN, H, fH, fW) height distribution -> int8 (BN, fH, fW) mask id: k (1-based) iff
     thresholds[k-1] <= height_range[argmax] < thresholds[k], else 0
@@ -98,8 +101,11 @@ def height_to_mask(height, height_range, thresholds):
     _need_cuda(height)
     height = height.contiguous().float()
     BN, H, fH, fW = height.shape
-    hr = torch.tensor(height_range, dtype=torch.float32, device=height.device)
-    th = torch.tensor(thresholds, dtype=torch.float32, device=height.device)
+    key = (tuple(height_range), tuple(thresholds), height.device)
+    if key not in _TABLES:       # cached: no pageable H2D copy per call (CUDA-graph capturable)
+        _TABLES[key] = (torch.tensor(height_range, dtype=torch.float32, device=height.device),
+                        torch.tensor(thresholds, dtype=torch.float32, device=height.device))
+    hr, th = _TABLES[key]
     if hr.numel() != H:
         raise ValueError('height_range has %d entries, height has %d channels' % (hr.numel(), H))
     out = torch.empty(BN, fH, fW, dtype=torch.int8, device=height.device)

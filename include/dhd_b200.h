@@ -193,6 +193,10 @@ int dhd_conv2d_fwd(const dhd_conv_desc* desc, void* stream);
 /* fp32 NCHW -> split-bf16 NHWC (reference modules exchange fp32 NCHW tensors) */
 int dhd_pack_nchw_to_nhwc(const float* in, int N, int C, int H, int W, void* out, int out_ld,
                           int out_coff, int part_stride, int parts, void* stream);
+/* class map of predictor.get_occ (occ_head.py:141-153): out[v] = argmax_k logits[v][k] (uint8) */
+int dhd_occ_argmax(const float* logits, long nvox, int ncls, uint8_t* out, void* stream);
+/* number of kernels this library has enqueued since it was loaded (bench bookkeeping) */
+long dhd_launch_count(void);
 /* fp32 rows [rows][C] (NHWC) -> split-bf16 rows */
 int dhd_split_nhwc(const float* in, long rows, int C, void* out, int out_ld, int out_coff,
                    int part_stride, int parts, void* stream);

@@ -1,17 +1,7 @@
 set -x
-python -m pytest tests/test_dense_gpu.py -x -q 2>&1 | tail -30
-python -m pytest tests -m gpu -x -q --deselect tests/test_dense_gpu.py 2>&1 | tail -5
-python bench.py --steps 50 --warmup 5 --no-cpu-baseline > gpurun_out/r01_bench_poolv3.json; cat gpurun_out/r01_bench_poolv3.json
-python - <<'P'
-import torch
-x = torch.empty(704*1024*1024//4, device='cuda')
-for f in (lambda: x.zero_(), lambda: x.fill_(1.0)):
-    for _ in range(3): f()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(10): f()
-    e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)/10
-    print('memset-like write of %.0f MB: %.1f us = %.0f GB/s' % (x.numel()*4/1e6, ms*1e3, x.numel()*4/ms/1e6))
-P
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
+python -m pytest tests -m gpu -x -q 2>&1 | tail -5
+python bench.py --steps 20 --warmup 3 > gpurun_out/r01_bench_full_bf16.json 2> gpurun_out/r01_bench_full.err; tail -3 gpurun_out/r01_bench_full.err; cat gpurun_out/r01_bench_full_bf16.json
+python bench.py --steps 10 --warmup 3 --precision fp32 --no-cpu-baseline > gpurun_out/r01_bench_full_fp32.json 2>> gpurun_out/r01_bench_full.err; cat gpurun_out/r01_bench_full_fp32.json
+python bench.py --steps 10 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/r01_bench_full_nograph.json 2>> gpurun_out/r01_bench_full.err; cat gpurun_out/r01_bench_full_nograph.json
+ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r01_launches_full.csv python bench.py --steps 2 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/r01_ncu_bench.log 2>&1
