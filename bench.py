@@ -182,10 +182,8 @@ def run_ours(args):
         torch.cuda.synchronize()
         stage_ms[name] = s0.elapsed_time(s1) / 5
 
-    t = torch.tensor([ms_total, ms_e2e, pool_ms_avg], device='cuda', dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e, pool_ms_avg = t.tolist()
+    from dhd_b200 import shard
+    ms_total, ms_e2e, pool_ms_avg = shard.max_over_ranks([ms_total, ms_e2e, pool_ms_avg], device='cuda')
 
     if rank == 0:
         peak, peak_src = peaks()

@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, 'libdhd_b200.so')
 
 MAX_PASSES = 4
 MAX_PLANES = 32
-LAYOUT_NHWC, LAYOUT_NCHW_COLLAPSE, LAYOUT_NCDHW = 0, 1, 2
+LAYOUT_NHWC, LAYOUT_NCHW_COLLAPSE, LAYOUT_NCDHW, LAYOUT_NCDHW_CAT = 0, 1, 2, 3
 
 
 class MghsCfg(ctypes.Structure):
@@ -53,9 +53,11 @@ _SIGNATURES = {
     'dhd_occ_argmax': (ctypes.c_int, [_P, ctypes.c_long, _I, _P, _P]),
     'dhd_launch_count': (ctypes.c_long, []),
     'dhd_split_nhwc': (ctypes.c_int, [_P, ctypes.c_long, _I, _P] + [_I] * 4 + [_P]),
+    'dhd_split_nhwc_mean': (ctypes.c_int, [_P, _I, _I, _I, _P] + [_I] * 4 + [_P, _P]),
     'dhd_unpack_nhwc_to_nchw': (ctypes.c_int, [_P] + [_I] * 8 + [_P, _P]),
     'dhd_mean_hw': (ctypes.c_int, [_P] + [_I] * 7 + [_P, _P]),
     'dhd_linear_rows': (ctypes.c_int, [_P, _I, _I, _P, _P, _I, _I, _P, _P, _I, _P, _P]),
+    'dhd_gate_channels': (ctypes.c_int, [_P, _I, _I, _I, _P, _P] + [_I] * 4 + [_P, _P]),
     'dhd_sfa_mix': (ctypes.c_int, [_P] + [_I] * 7 + [_P, _P, _P] + [_I] * 4 + [_P]),
     'dhd_dcn_im2col': (ctypes.c_int, [_P] + [_I] * 8 + [_P] + [_I] * 5 + [_P] + [_I] * 3 + [_P]),
 }

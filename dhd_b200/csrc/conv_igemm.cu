@@ -26,10 +26,10 @@
 // Warp roles (192 threads): warps 0-3 epilogue (TMEM lanes 32w..32w+31), warp 4 TMA producer,
 // warp 5 TMEM allocator + single-thread MMA issuer.  3-stage smem ring (A 16 KB + B 16 KB per
 // stage) -> 2 CTAs per SM, so one CTA's epilogue overlaps the other's main loop.
-#include <cuda.h>
-#include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace dhd {
 
@@ -37,7 +37,6 @@ constexpr int kBlockM = 128;
 constexpr int kBlockN = 128;
 constexpr int kBlockK = 64;  // bf16 elements = one 128-byte swizzle row
 constexpr int kStages = 3;
-constexpr int kUmmaK = 16;
 constexpr int kConvThreads = 192;
 constexpr uint32_t kABytes = kBlockM * kBlockK * 2;
 constexpr uint32_t kBBytes = kBlockN * kBlockK * 2;
@@ -50,102 +49,7 @@ struct ConvKernelParams {
   int tiles_w, tiles_h;
 };
 
-// ------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra WAIT_DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(bar),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
-                                            int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
-      "[%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
-      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
-                                            int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
-      "[%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-      "l"(map), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() {
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tc_fence_after() {
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]^T, 128 x 128 x 16, bf16 in / fp32 accumulate
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
-                                          uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// mbarrier arrive once every previously issued tcgen05.mma of this thread has completed
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
-      "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
-        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
-        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
-        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart.
-// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48),
-//  layout SWIZZLE_128B=2 [61,64))
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-// cute::UMMA::InstrDescriptor: c=F32 [4,6)=1, a=BF16 [7,10)=1, b=BF16 [10,13)=1, K-major A and B,
-// N>>3 [17,23), M>>4 [24,29)
-constexpr uint32_t kInstrDesc =
-    (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kBlockN >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+constexpr uint32_t kInstrDesc = umma_instr_desc_bf16(kBlockM, kBlockN);
 
 __device__ __forceinline__ float act_apply(float v, int act) {
   switch (act) {
@@ -404,6 +308,13 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
+int conv2_launch(const dhd_conv_desc* d, void* encode, void* stream);   // conv_igemm2.cu
+
+static int conv_version() {
+  const char* v = getenv("DHD_CONV_V");
+  return v != nullptr && *v != 0 ? atoi(v) : 2;
+}
+
 }  // namespace dhd
 
 using namespace dhd;
@@ -437,6 +348,15 @@ extern "C" int dhd_conv2d_fwd(const dhd_conv_desc* d, void* stream) {
   }
   EncodeTiledFn enc = encode_fn();
   if (enc == nullptr) return fail(DHD_EUNSUPPORTED, "%s", "cuTensorMapEncodeTiled is unavailable");
+
+  bool centre = false;
+  for (int t = 0; t < d->taps; ++t) centre |= d->tap_dx[t] == 0 && d->tap_dy[t] == 0;
+  DHD_REQUIRE(centre, "the filter must contain the (0, 0) tap");
+  if (d->residual != nullptr)
+    DHD_REQUIRE(d->Cout % 32 == 0 && ((uintptr_t)d->residual & 15) == 0 && d->res_sN % 4 == 0 &&
+                    d->res_sY % 4 == 0 && d->res_sX % 4 == 0,
+                "residual needs Cout % 32 == 0 and 16-byte aligned rows");
+  if (conv_version() != 1) return conv2_launch(d, (void*)enc, stream);
 
   CUtensorMap map_a, map_b;
   {

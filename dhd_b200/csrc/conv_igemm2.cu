@@ -1,0 +1,485 @@
+// Persistent implicit-GEMM convolution, second generation (same dhd_conv_desc contract as
+// conv_igemm.cu, selected by dhd_conv2d_fwd unless DHD_CONV_V=1).
+//
+// What changed against the first kernel and why (B200 measurements in profiles/):
+//  * the first kernel was bound by L2 -> shared-memory traffic (128x128x64 steps move 32 KB per
+//    2.1 MFLOP = 64 FLOP/B; the chip delivers ~6.5 TB/s from L2, so ~400 TFLOP/s): the N tile is
+//    now 256 wide for layers with Cout > 128 (85 FLOP/B) -- A is fetched once for 256 channels;
+//  * it is persistent (one CTA per SM walks the tile list) with the accumulator double-buffered
+//    in TMEM (2 x NT columns), so tile i's epilogue overlaps tile i+1's main loop and the
+//    TMEM allocation / barrier set-up is paid once per SM instead of once per tile;
+//  * the epilogue reads scale / bias / per-image vectors from shared memory (staged once per
+//    tile) instead of issuing two global loads per element, and channel-contiguous outputs
+//    (every bf16 activation and every NHWC fp32 tensor) leave through 128B-swizzled shared
+//    memory and TMA box stores: full-line coalesced writes, image borders clipped by the TMA
+//    unit; strided outputs (NCHW heads) keep the direct path.
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace dhd {
+
+constexpr int kM2 = 128;          // pixels per tile (TMEM lanes)
+constexpr int kK2 = 64;           // bf16 per smem row (128 B swizzle span)
+constexpr int kThreads2 = 192;
+constexpr uint32_t kA2Bytes = kM2 * kK2 * 2;
+constexpr uint32_t kStageBufBytes = 16384;   // one TMA-store staging tile: 128 rows x 128 B
+
+template <int NT>
+struct Cfg2 {
+  static constexpr int kStages = NT == 256 ? 3 : 5;
+  static constexpr uint32_t kBBytes = NT * kK2 * 2;
+  static constexpr uint32_t kStageBytes = kA2Bytes + kBBytes;
+  static constexpr uint32_t kVecBytes = 3 * NT * 4;            // scale, bias(+img_bias), gate
+  static constexpr uint32_t kSmem = kStages * kStageBytes + 2 * kStageBufBytes + kVecBytes + 256 + 1024;
+  static constexpr int kTmemCols = 2 * NT;
+};
+
+struct Conv2Params {
+  dhd_conv_desc d;
+  int tiles_w, tiles_h, n_tiles, total_tiles;
+  int seg_b16_tma[DHD_CONV_MAX_SEGS], seg_f32_tma[DHD_CONV_MAX_SEGS];
+};
+
+struct Conv2Maps {
+  CUtensorMap a, b;
+  CUtensorMap o16[DHD_CONV_MAX_SEGS][3];
+  CUtensorMap o32[DHD_CONV_MAX_SEGS];
+};
+
+__device__ __forceinline__ float act2(float v, int act) {
+  switch (act) {
+    case DHD_ACT_RELU: return fmaxf(v, 0.f);
+    case DHD_ACT_SIGMOID: return 1.f / (1.f + expf(-v));
+    case DHD_ACT_SOFTPLUS: return v > 20.f ? v : log1pf(expf(v));
+    default: return v;
+  }
+}
+
+__device__ __forceinline__ bool tap_dead2(const dhd_conv_desc& d, int t, int x0, int y0) {
+  const int xs = x0 + d.tap_dx[t], ys = y0 + d.tap_dy[t];
+  return xs >= d.W || xs + d.bw <= 0 || ys >= d.H || ys + d.bh <= 0;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(kThreads2, 1)
+conv_igemm2_kernel(const __grid_constant__ Conv2Maps M, const __grid_constant__ Conv2Params P) {
+  using C = Cfg2<NT>;
+  extern __shared__ uint8_t smem_raw[];
+  const dhd_conv_desc& d = P.d;
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t stagebuf = base + C::kStages * C::kStageBytes;            // 2 x 16 KB, 1024-aligned
+  const uint32_t vec_base = stagebuf + 2 * kStageBufBytes;
+  const uint32_t bar_base = vec_base + C::kVecBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (C::kStages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * C::kStages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * C::kStages + 2 + s); };
+  uint8_t* gen = smem_raw + (base - raw);                                   // generic view of `base`
+  float* s_scale = reinterpret_cast<float*>(gen + (vec_base - base));
+  float* s_bias = s_scale + NT;
+  float* s_gate = s_bias + NT;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + (bar_base - base) + 8u * (2 * C::kStages + 4));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kchunks = d.Cin / kK2;
+  constexpr uint32_t kIdesc = umma_instr_desc_bf16(kM2, NT);
+
+  if (warp == 4 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&M.a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&M.b) : "memory");
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(C::kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto decode = [&](int tile, int& img, int& x0, int& y0, int& n0) {
+    const int nt = tile % P.n_tiles;
+    int mt = tile / P.n_tiles;
+    const int tx = mt % P.tiles_w;
+    mt /= P.tiles_w;
+    const int ty = mt % P.tiles_h;
+    img = mt / P.tiles_h;
+    x0 = tx * d.bw;
+    y0 = ty * d.bh;
+    n0 = nt * NT;
+  };
+
+  if (warp == 4) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+        int img, x0, y0, n0;
+        decode(tile, img, x0, y0, n0);
+        for (int t = 0; t < d.taps; ++t) {
+          if (tap_dead2(d, t, x0, y0)) continue;
+          for (int kc = 0; kc < kchunks; ++kc) {
+            for (int e = 0; e < d.n_terms; ++e, ++it) {
+              const int s = it % C::kStages;
+              const uint32_t ph = (it / C::kStages) & 1;
+              mbar_wait(empty_bar(s), ph ^ 1);
+              const uint32_t sa = base + s * C::kStageBytes, sb = sa + kA2Bytes;
+              mbar_expect_tx(full_bar(s), C::kStageBytes);
+              tma_load_4d(sa, &M.a, full_bar(s), d.in_coff + d.term_a[e] * d.in_part_stride + kc * kK2,
+                          x0 + d.tap_dx[t], y0 + d.tap_dy[t], img);
+              tma_load_2d(sb, &M.b, full_bar(s), (t * d.w_parts + d.term_b[e]) * d.Cin + kc * kK2, n0);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ===================================================== MMA issuer
+    if (lane == 0) {
+      int it = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++lt) {
+        int img, x0, y0, n0;
+        decode(tile, img, x0, y0, n0);
+        const int as = lt & 1;
+        mbar_wait(tempty_bar(as), ((lt >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + (uint32_t)(as * NT);
+        int first = 1;
+        for (int t = 0; t < d.taps; ++t) {
+          if (tap_dead2(d, t, x0, y0)) continue;
+          for (int kc = 0; kc < kchunks; ++kc) {
+            for (int e = 0; e < d.n_terms; ++e, ++it) {
+              const int s = it % C::kStages;
+              const uint32_t ph = (it / C::kStages) & 1;
+              mbar_wait(full_bar(s), ph);
+              tc_fence_after();
+              const uint32_t sa = base + s * C::kStageBytes, sb = sa + kA2Bytes;
+              const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sb);
+#pragma unroll
+              for (int k = 0; k < kK2 / kUmmaK; ++k)
+                umma_bf16(tacc, da + 2u * k, db + 2u * k, kIdesc, (first && k == 0) ? 0u : 1u);
+              first = 0;
+              umma_commit(empty_bar(s));
+            }
+          }
+        }
+        umma_commit(tfull_bar(as));
+      }
+    }
+  } else {
+    // ===================================================== epilogue (warps 0..3 = TMEM lanes 32w..)
+    // Kept deliberately COMPACT (32-column chunks in a rolled loop, one activation switch per
+    // chunk): the first version unrolled 64 columns x every activation and its 220 KB of SASS
+    // made the four epilogue warps stall on instruction fetch (ncu: stall_no_inst 34 %).
+    const int tid = threadIdx.x;            // 0..127
+    const int row = tid;
+    int lt = 0;
+    uint32_t nstore = 0;                    // TMA stores issued so far (selects the staging buffer)
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++lt) {
+      int img, x0, y0, n0;
+      decode(tile, img, x0, y0, n0);
+      const int as = lt & 1;
+      named_bar_sync(1, 128);               // everyone is done with the previous tile's vectors
+      for (int c = tid; c < NT; c += 128) {
+        const int ch = n0 + c;
+        float sc = 1.f, bi = 0.f, ga = 1.f;
+        if (ch < d.Cout) {
+          if (d.scale != nullptr) sc = __ldg(d.scale + ch);
+          if (d.bias != nullptr) bi = __ldg(d.bias + ch);
+          if (d.img_bias != nullptr) bi += __ldg(d.img_bias + (size_t)img * d.Cout + ch);
+          if (d.img_gate != nullptr) ga = __ldg(d.img_gate + (size_t)img * d.Cout + ch);
+        }
+        s_scale[c] = sc;
+        s_bias[c] = bi;
+        s_gate[c] = ga;
+      }
+      named_bar_sync(1, 128);
+      mbar_wait(tfull_bar(as), (lt >> 1) & 1);
+      tc_fence_after();
+      const int px = x0 + row % d.bw, py = y0 + row / d.bw;
+      const bool valid = px < d.W && py < d.H;
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(as * NT);
+      const float* res = nullptr;
+      if (d.residual != nullptr && valid)
+        res = d.residual + (size_t)img * d.res_sN + (size_t)py * d.res_sY + (size_t)px * d.res_sX + n0;
+      const bool has_gate = d.img_gate != nullptr;
+
+#pragma unroll 1
+      for (int sgi = 0; sgi < d.n_seg; ++sgi) {
+        const dhd_conv_seg& sg = d.seg[sgi];
+        const int c_lo = max(sg.c_lo, n0), c_hi = min(sg.c_hi, min(d.Cout, n0 + NT));
+        if (c_lo >= c_hi) continue;
+        const bool tma16 = P.seg_b16_tma[sgi] != 0, tma32 = P.seg_f32_tma[sgi] != 0;
+        const int act = sg.act;
+        const int cb_lo = (c_lo - n0) / 32, cb_hi = (c_hi - n0 + 31) / 32;
+        // y = acc*scale + bias (+ residual) for one 32-column chunk, out-of-segment columns -> -inf / 0
+        auto affine = [&](int cb, float (&v)[32], float fill) {
+          tmem_ld32(taddr + cb * 32, v);
+          const float4* sc4 = reinterpret_cast<const float4*>(s_scale + cb * 32);
+          const float4* bi4 = reinterpret_cast<const float4*>(s_bias + cb * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 s = sc4[j], b = bi4[j];
+            v[4 * j] = fmaf(v[4 * j], s.x, b.x);
+            v[4 * j + 1] = fmaf(v[4 * j + 1], s.y, b.y);
+            v[4 * j + 2] = fmaf(v[4 * j + 2], s.z, b.z);
+            v[4 * j + 3] = fmaf(v[4 * j + 3], s.w, b.w);
+          }
+          if (res != nullptr) {
+            const float* rp = res + cb * 32;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {     // host guarantees 16-byte alignment and Cout % 32 == 0
+              const float4 q = __ldg(reinterpret_cast<const float4*>(rp) + j);
+              v[4 * j] += q.x; v[4 * j + 1] += q.y; v[4 * j + 2] += q.z; v[4 * j + 3] += q.w;
+            }
+          }
+          if (n0 + cb * 32 < c_lo || n0 + cb * 32 + 32 > c_hi) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int c = n0 + cb * 32 + j;
+              if (c < c_lo || c >= c_hi) v[j] = fill;
+            }
+          }
+        };
+        // one rolled loop nest: softmax makes three passes over the chunks (max, sum, write), every
+        // other activation one; a single inlined copy of `affine` keeps the code small
+        float mx = -INFINITY, sum = 0.f, inv = 1.f;
+        const int npass = act == DHD_ACT_SOFTMAX ? 3 : 1;
+#pragma unroll 1
+        for (int pass = 0; pass < npass; ++pass) {
+        if (pass == 2) inv = 1.f / sum;
+#pragma unroll 1
+        for (int cb = cb_lo; cb < cb_hi; ++cb) {
+          float v[32];
+          affine(cb, v, act == DHD_ACT_SOFTMAX ? -INFINITY : 0.f);
+          if (npass == 3 && pass == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, v[j]);
+            continue;
+          }
+          if (npass == 3 && pass == 1) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sum += __expf(v[j] - mx);    // exp(-inf) = 0 outside the segment
+            continue;
+          }
+          switch (act) {
+            case DHD_ACT_RELU:
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+              break;
+            case DHD_ACT_SIGMOID:
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = __frcp_rn(1.f + __expf(-v[j]));
+              break;
+            case DHD_ACT_SOFTPLUS:   // torch Softplus(beta=1, threshold=20)
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = v[j] > 20.f ? v[j] : __logf(1.f + __expf(v[j]));
+              break;
+            case DHD_ACT_SOFTMAX:
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = __expf(v[j] - mx) * inv;
+              break;
+            default: break;
+          }
+          if (has_gate) {
+            const float4* g4 = reinterpret_cast<const float4*>(s_gate + cb * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 g = g4[j];
+              v[4 * j] *= g.x; v[4 * j + 1] *= g.y; v[4 * j + 2] *= g.z; v[4 * j + 3] *= g.w;
+            }
+          }
+          const int cfirst = n0 + cb * 32;
+          // ---------------- fp32 output
+          if (sg.out_f32 != nullptr) {
+            if (tma32) {
+              const uint32_t buf = stagebuf + (nstore & 1u) * kStageBufBytes;
+              if (tid == 0) tma_store_wait_read<1>();      // the store that last used this buffer has read it
+              named_bar_sync(1, 128);
+              float4* dst = reinterpret_cast<float4*>(gen + (buf - base) + row * 128);
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                dst[j ^ (row & 7)] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              fence_proxy_async_smem();
+              named_bar_sync(1, 128);
+              if (tid == 0) {
+                tma_store_4d(&M.o32[sgi], buf, cfirst - sg.c_lo, x0, y0, img);
+                tma_store_commit();
+              }
+              ++nstore;
+            } else if (valid) {
+              float* o = sg.out_f32 + (size_t)img * sg.f32_sN + (size_t)py * sg.f32_sY + (size_t)px * sg.f32_sX;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const int c = cfirst + j;
+                if (c >= c_lo && c < c_hi) o[(size_t)(c - sg.c_lo) * sg.f32_sC] = v[j];
+              }
+            }
+          }
+          // ---------------- bf16 (split) output: part p = bf16 of what parts < p left over
+          if (sg.out_b16 != nullptr) {
+#pragma unroll 1
+            for (int p = 0; p < sg.b16_parts; ++p) {
+              uint4 q[4];
+              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(q);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                h[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                v[2 * j] -= __low2float(h[j]);
+                v[2 * j + 1] -= __high2float(h[j]);
+              }
+              if (tma16) {
+                // 32 channels = 64-byte rows, SWIZZLE_64B: 16-byte chunk j of row r sits at j ^ ((r >> 1) & 3)
+                const uint32_t buf = stagebuf + (nstore & 1u) * kStageBufBytes;
+                if (tid == 0) tma_store_wait_read<1>();
+                named_bar_sync(1, 128);
+                uint4* dst = reinterpret_cast<uint4*>(gen + (buf - base) + row * 64);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dst[j ^ ((row >> 1) & 3)] = q[j];
+                fence_proxy_async_smem();
+                named_bar_sync(1, 128);
+                if (tid == 0) {
+                  tma_store_4d(&M.o16[sgi][p], buf, cfirst - sg.c_lo, x0, y0, img);
+                  tma_store_commit();
+                }
+                ++nstore;
+              } else if (valid) {
+                __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(sg.out_b16) +
+                                    ((size_t)img * d.H * d.W + (size_t)py * d.W + px) * sg.b16_ld + sg.b16_coff +
+                                    (size_t)p * sg.b16_part_stride;
+                const __nv_bfloat16* hs = reinterpret_cast<const __nv_bfloat16*>(q);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  const int c = cfirst + j;
+                  if (c >= c_lo && c < c_hi) op[c - sg.c_lo] = hs[j];
+                }
+              }
+            }
+          }
+        }
+        }
+      }
+      // accumulator drained: hand it back to the MMA warp
+      tc_fence_before();
+      named_bar_sync(1, 128);
+      if (tid == 0) {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty_bar(as)) : "memory");
+      }
+    }
+    if (tid == 0) tma_store_wait<0>();      // all bulk stores complete before the CTA exits
+  }
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::kTmemCols)
+                 : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                   CUtensorMapFloatOOBfill);
+
+template <int NT>
+static int launch2(const Conv2Maps& maps, const Conv2Params& P, cudaStream_t st) {
+  using C = Cfg2<NT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_igemm2_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)C::kSmem);
+    if (e != cudaSuccess) return fail((int)e, "%s: %ld", "cudaFuncSetAttribute(conv_igemm2)", (long)e);
+    attr_set = true;
+  }
+  const int grid = min(P.total_tiles, sm_count());
+  conv_igemm2_kernel<NT><<<grid, kThreads2, C::kSmem, st>>>(maps, P);
+  DHD_CUDA_LAUNCH_CHECK("conv_igemm2");
+  return DHD_OK;
+}
+
+// called by dhd_conv2d_fwd (conv_igemm.cu) after argument validation
+int conv2_launch(const dhd_conv_desc* d, void* encode, void* stream) {
+  EncodeTiledFn2 enc = (EncodeTiledFn2)encode;
+  Conv2Maps maps;
+  Conv2Params P;
+  P.d = *d;
+  const int NT = d->Cout > 128 ? 256 : 128;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)d->in_ld, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
+    cuuint64_t strides[3] = {(cuuint64_t)d->in_ld * 2, (cuuint64_t)d->W * d->in_ld * 2,
+                             (cuuint64_t)d->H * d->W * d->in_ld * 2};
+    cuuint32_t box[4] = {(cuuint32_t)kK2, (cuuint32_t)d->bw, (cuuint32_t)d->bh, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(&maps.a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)d->in, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(DHD_EINVAL, "%s: %ld", "cuTensorMapEncodeTiled(A) failed", (long)r);
+  }
+  {
+    const cuuint64_t ktot = (cuuint64_t)d->taps * d->w_parts * d->Cin;
+    cuuint64_t dims[2] = {ktot, (cuuint64_t)d->Cout};
+    cuuint64_t strides[1] = {ktot * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kK2, (cuuint32_t)NT};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(&maps.b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)d->weight, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(DHD_EINVAL, "%s: %ld", "cuTensorMapEncodeTiled(B) failed", (long)r);
+  }
+  for (int s = 0; s < DHD_CONV_MAX_SEGS; ++s) {
+    P.seg_b16_tma[s] = 0;
+    P.seg_f32_tma[s] = 0;
+    if (s >= d->n_seg) continue;
+    const dhd_conv_seg& sg = d->seg[s];
+    const cuuint64_t nch = (cuuint64_t)(sg.c_hi - sg.c_lo);
+    // a TMA store may hang over the far edges of the tensor but its start coordinate must not be
+    // negative: 32-channel boxes start at multiples of 32, so the segment has to as well
+    if (sg.c_lo % 32 != 0) continue;
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    if (sg.out_b16 != nullptr && sg.b16_ld % 8 == 0 && sg.b16_coff % 8 == 0 && sg.b16_part_stride % 8 == 0 &&
+        ((uintptr_t)sg.out_b16 & 15) == 0) {
+      bool ok = true;
+      for (int p = 0; p < sg.b16_parts && ok; ++p) {
+        cuuint64_t dims[4] = {nch, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
+        cuuint64_t strides[3] = {(cuuint64_t)sg.b16_ld * 2, (cuuint64_t)d->W * sg.b16_ld * 2,
+                                 (cuuint64_t)d->H * d->W * sg.b16_ld * 2};
+        cuuint32_t box[4] = {32, (cuuint32_t)d->bw, (cuuint32_t)d->bh, 1};   // 64-byte rows
+        void* basep = (char*)sg.out_b16 + ((size_t)sg.b16_coff + (size_t)p * sg.b16_part_stride) * 2;
+        ok = enc(&maps.o16[s][p], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, basep, dims, strides, box, es,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+      }
+      P.seg_b16_tma[s] = ok ? 1 : 0;
+    }
+    if (sg.out_f32 != nullptr && sg.f32_sC == 1 && sg.f32_sX % 4 == 0 && sg.f32_sY % 4 == 0 &&
+        sg.f32_sN % 4 == 0 && ((uintptr_t)sg.out_f32 & 15) == 0 && sg.act != DHD_ACT_SOFTMAX) {
+      cuuint64_t dims[4] = {nch, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
+      cuuint64_t strides[3] = {(cuuint64_t)sg.f32_sX * 4, (cuuint64_t)sg.f32_sY * 4, (cuuint64_t)sg.f32_sN * 4};
+      cuuint32_t box[4] = {32, (cuuint32_t)d->bw, (cuuint32_t)d->bh, 1};
+      P.seg_f32_tma[s] = enc(&maps.o32[s], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)sg.out_f32, dims, strides,
+                             box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                             CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS
+                             ? 1 : 0;
+    }
+  }
+  P.tiles_w = (d->W + d->bw - 1) / d->bw;
+  P.tiles_h = (d->H + d->bh - 1) / d->bh;
+  P.n_tiles = (d->Cout + NT - 1) / NT;
+  P.total_tiles = P.tiles_w * P.tiles_h * d->N * P.n_tiles;
+  if (NT == 256) return launch2<256>(maps, P, (cudaStream_t)stream);
+  return launch2<128>(maps, P, (cudaStream_t)stream);
+}
+
+}  // namespace dhd

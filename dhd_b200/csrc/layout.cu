@@ -36,6 +36,34 @@ __device__ __forceinline__ float load_parts(const __nv_bfloat16* src, int parts,
   return v;
 }
 
+// 8-channel (16-byte) variants: v[8] <-> `parts` uint4 of bf16
+__device__ __forceinline__ void load_parts8(const __nv_bfloat16* src, int parts, int part_stride, float (&v)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = 0.f;
+  for (int p = parts - 1; p >= 0; --p) {
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(src + (size_t)p * part_stride));
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[2 * j] += __low2float(h[j]);
+      v[2 * j + 1] += __high2float(h[j]);
+    }
+  }
+}
+__device__ __forceinline__ void store_parts8(__nv_bfloat16* dst, float (&v)[8], int parts, int part_stride) {
+  for (int p = 0; p < parts; ++p) {
+    uint4 q;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&q);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      h[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+      v[2 * j] -= __low2float(h[j]);
+      v[2 * j + 1] -= __high2float(h[j]);
+    }
+    *reinterpret_cast<uint4*>(dst + (size_t)p * part_stride) = q;
+  }
+}
+
 // ---- pack: one block = 64 channels x 32 pixels of one image -------------------------------
 __global__ void __launch_bounds__(256)
 pack_nchw_to_nhwc_kernel(const float* __restrict__ in, int C, int HW, __nv_bfloat16* __restrict__ out,
@@ -70,6 +98,191 @@ split_nhwc_kernel(const float* __restrict__ in, long R, int C, __nv_bfloat16* __
   const int c = (int)(i % cp) * 2;
   const float2 v = *reinterpret_cast<const float2*>(in + r * C + c);
   store_parts2(out + r * ld + coff + c, v.x, v.y, parts, part_stride);
+}
+
+// 8 channels per thread; block = (C/8 channel groups) x (256/(C/8) pixel rows), `pb` pixels of ONE image
+// per block; optionally accumulates the per-image channel mean of the rows it touches (SFA squeeze,
+// mix.py:41) so the tensor is read once.
+__global__ void __launch_bounds__(256)
+split_nhwc8_kernel(const float* __restrict__ in, int HW, int C, int pb, __nv_bfloat16* __restrict__ out, int ld,
+                   int coff, int part_stride, int parts, float* __restrict__ mean_out, float inv) {
+  __shared__ float red[256][9];
+  const int cg = C / 8, rows = 256 / cg;
+  const int gi = threadIdx.x % cg, ri = threadIdx.x / cg;
+  const int n = blockIdx.y, p0 = blockIdx.x * pb, p1 = min(HW, p0 + pb);
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (ri < rows) {
+    for (int p = p0 + ri; p < p1; p += rows) {
+      const size_t r = (size_t)n * HW + p;
+      const float4* src = reinterpret_cast<const float4*>(in + r * C + gi * 8);
+      const float4 a = __ldg(src), b = __ldg(src + 1);
+      float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += v[j];
+      store_parts8(out + r * ld + coff + gi * 8, v, parts, part_stride);
+    }
+  }
+  if (mean_out == nullptr) return;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[threadIdx.x][j] = acc[j];
+  __syncthreads();
+  if (ri == 0) {
+    for (int k = 1; k < rows; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += red[threadIdx.x + k * cg][j];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(mean_out + (size_t)n * C + gi * 8 + j, acc[j] * inv);
+  }
+}
+
+// per-image channel mean of an Act, 8 channels per thread, partial sums by atomicAdd (out pre-zeroed)
+__global__ void __launch_bounds__(256)
+mean_hw8_kernel(const __nv_bfloat16* __restrict__ in, int ld, int coff, int part_stride, int parts, int C,
+                int HW, int pb, float* __restrict__ out, float inv) {
+  __shared__ float red[256][9];
+  const int cg = C / 8, rows = 256 / cg;
+  const int gi = threadIdx.x % cg, ri = threadIdx.x / cg;
+  const int n = blockIdx.y, p0 = blockIdx.x * pb, p1 = min(HW, p0 + pb);
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (ri < rows) {
+    for (int p = p0 + ri; p < p1; p += rows) {
+      float v[8];
+      load_parts8(in + ((size_t)n * HW + p) * ld + coff + gi * 8, parts, part_stride, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += v[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[threadIdx.x][j] = acc[j];
+  __syncthreads();
+  if (ri == 0) {
+    for (int k = 1; k < rows; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += red[threadIdx.x + k * cg][j];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(out + (size_t)n * C + gi * 8 + j, acc[j] * inv);
+  }
+}
+
+// out = x * gate[n][c] (SELayer's multiply, depthnet.py:169, when one feature map feeds two
+// differently gated branches as in DepthNet.forward :388-396): fp32 NHWC in, split-bf16 (+ fp32) out
+__global__ void __launch_bounds__(256)
+gate_channels_kernel(const float* __restrict__ x, int C, long npix_total, int HW, const float* __restrict__ gate,
+                     __nv_bfloat16* __restrict__ out, int o_ld, int o_coff, int o_ps, int o_parts,
+                     float* __restrict__ out32) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int cg = C / 8;
+  if (i >= npix_total * cg) return;
+  const long pix = i / cg;
+  const int c = (int)(i % cg) * 8;
+  const int n = (int)(pix / HW);
+  const float4* xp = reinterpret_cast<const float4*>(x + (size_t)pix * C + c);
+  const float4* gp = reinterpret_cast<const float4*>(gate + (size_t)n * C + c);
+  const float4 a = __ldg(xp), b = __ldg(xp + 1), ga = __ldg(gp), gb = __ldg(gp + 1);
+  float v[8] = {a.x * ga.x, a.y * ga.y, a.z * ga.z, a.w * ga.w, b.x * gb.x, b.y * gb.y, b.z * gb.z, b.w * gb.w};
+  if (out32 != nullptr) {
+    float4* o = reinterpret_cast<float4*>(out32 + (size_t)pix * C + c);
+    o[0] = make_float4(v[0], v[1], v[2], v[3]);
+    o[1] = make_float4(v[4], v[5], v[6], v[7]);
+  }
+  store_parts8(out + (size_t)pix * o_ld + o_coff + c, v, o_parts, o_ps);
+}
+
+// SFA blends, 8 channels per thread (same arithmetic as sfa_mix_kernel)
+__global__ void __launch_bounds__(256)
+sfa_mix8_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int x_coff, int x_ps, int x_parts, int C,
+                long npix_total, int HW, const float* __restrict__ a1, const float* __restrict__ a2,
+                __nv_bfloat16* __restrict__ out, int o_ld, int o_coff, int o_ps, int o_parts) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int cg = C / 8;
+  if (i >= npix_total * cg) return;
+  const long pix = i / cg;
+  const int c = (int)(i % cg) * 8;
+  const int n = (int)(pix / HW);
+  float bev[8], vox[8], r[8];
+  load_parts8(x + (size_t)pix * x_ld + x_coff + c, x_parts, x_ps, bev);
+  load_parts8(x + (size_t)pix * x_ld + x_coff + C + c, x_parts, x_ps, vox);
+  const float4* g1p = reinterpret_cast<const float4*>(a1 + (size_t)n * C + c);
+  const float4 ga = __ldg(g1p), gb = __ldg(g1p + 1);
+  const float g1[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+  float g2[8];
+  if (a2 != nullptr) {
+    const float4* g2p = reinterpret_cast<const float4*>(a2 + (size_t)pix * C + c);
+    const float4 qa = __ldg(g2p), qb = __ldg(g2p + 1);
+    g2[0] = qa.x; g2[1] = qa.y; g2[2] = qa.z; g2[3] = qa.w; g2[4] = qb.x; g2[5] = qb.y; g2[6] = qb.z; g2[7] = qb.w;
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float b1 = __fmul_rn(g1[j], bev[j]);
+    const float v1 = __fmul_rn(__fsub_rn(1.f, g1[j]), vox[j]);
+    r[j] = a2 == nullptr ? __fadd_rn(b1, v1)
+                         : __fadd_rn(__fmul_rn(g2[j], b1), __fmul_rn(__fsub_rn(1.f, g2[j]), v1));
+  }
+  store_parts8(out + (size_t)pix * o_ld + o_coff + c, r, o_parts, o_ps);
+}
+
+// deformable im2col, one warp per (pixel, tap), 8 channels per lane (C multiple of 256 per pass)
+__global__ void __launch_bounds__(256)
+dcn_im2col8_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int x_coff, int x_ps, int x_parts, int C,
+                   int N, int H, int W, const float* __restrict__ offset, int off_ld, int ksize, int pad,
+                   int dil, int groups, __nv_bfloat16* __restrict__ out, int o_ld, int o_ps, int o_parts) {
+  const int lane = threadIdx.x & 31;
+  const long gw = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int taps = ksize * ksize;
+  if (gw >= (long)N * H * W * taps) return;
+  const int t = (int)(gw % taps);
+  const long pix = gw / taps;
+  const int wx = (int)(pix % W), hy = (int)((pix / W) % H), n = (int)(pix / ((long)W * H));
+  const float dy = __ldg(offset + (size_t)pix * off_ld + 2 * t), dx = __ldg(offset + (size_t)pix * off_ld + 2 * t + 1);
+  const float sy = (float)(hy - pad + (t / ksize) * dil) + dy;
+  const float sx = (float)(wx - pad + (t % ksize) * dil) + dx;
+  const int cg = C / groups;
+  float w00 = 0.f, w01 = 0.f, w10 = 0.f, w11 = 0.f;
+  int y0 = 0, x0 = 0, y1 = 0, x1 = 0;
+  const bool inside = sy > -1.f && sx > -1.f && sy < (float)H && sx < (float)W;
+  if (inside) {
+    y0 = (int)floorf(sy);
+    x0 = (int)floorf(sx);
+    y1 = y0 + 1;
+    x1 = x0 + 1;
+    const float ly = sy - (float)y0, lx = sx - (float)x0, hy_ = 1.f - ly, hx_ = 1.f - lx;
+    w00 = hy_ * hx_; w01 = hy_ * lx; w10 = ly * hx_; w11 = ly * lx;
+  }
+  for (int c = 8 * lane; c < C; c += 256) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    if (inside) {
+      const __nv_bfloat16* base = x + (size_t)n * H * W * x_ld + x_coff + c;
+      float q[8];
+      if (y0 >= 0 && x0 >= 0) {
+        load_parts8(base + ((size_t)y0 * W + x0) * x_ld, x_parts, x_ps, q);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = w00 * q[j];
+      }
+      if (y0 >= 0 && x1 <= W - 1) {
+        load_parts8(base + ((size_t)y0 * W + x1) * x_ld, x_parts, x_ps, q);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += w01 * q[j];
+      }
+      if (y1 <= H - 1 && x0 >= 0) {
+        load_parts8(base + ((size_t)y1 * W + x0) * x_ld, x_parts, x_ps, q);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += w10 * q[j];
+      }
+      if (y1 <= H - 1 && x1 <= W - 1) {
+        load_parts8(base + ((size_t)y1 * W + x1) * x_ld, x_parts, x_ps, q);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += w11 * q[j];
+      }
+    }
+    const int g = c / cg, cl = c % cg;
+    store_parts8(out + (size_t)pix * o_ld + (size_t)g * taps * cg + (size_t)t * cg + cl, v, o_parts, o_ps);
+  }
 }
 
 // ---- unpack: NHWC split-bf16 -> fp32 NCHW (hand-off to reference-layout consumers) --------
@@ -276,12 +489,43 @@ extern "C" int dhd_pack_nchw_to_nhwc(const float* in, int N, int C, int H, int W
   return DHD_OK;
 }
 
+static bool vec8_ok(int C, int ld, int coff, int ps, const void* a, const void* b) {
+  return C % 8 == 0 && C / 8 <= 256 && 256 % (C / 8) == 0 && ld % 8 == 0 && coff % 8 == 0 && ps % 8 == 0 &&
+         ((uintptr_t)a & 15) == 0 && ((uintptr_t)b & 15) == 0;
+}
+
+// blocks per image so that the grid is a few waves of the SM count
+static int pixels_per_block(int N, int HW) {
+  const int want = max(1, (sm_count() * 8) / max(1, N));
+  return max(16, (HW + want - 1) / want);
+}
+
+extern "C" int dhd_split_nhwc_mean(const float* in, int N, int HW, int C, void* out, int out_ld, int out_coff,
+                                   int part_stride, int parts, float* mean_out, void* stream) {
+  DHD_REQUIRE(in && out, "null pointer");
+  DHD_REQUIRE(N > 0 && HW > 0 && C > 0 && parts >= 1 && parts <= 3, "bad shape");
+  DHD_REQUIRE(vec8_ok(C, out_ld, out_coff, part_stride, in, out), "split_nhwc_mean needs C % 8 == 0 and 16-byte alignment");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (mean_out != nullptr) {
+    cudaError_t e = cudaMemsetAsync(mean_out, 0, (size_t)N * C * sizeof(float), st);
+    if (e != cudaSuccess) return fail((int)e, "%s: %ld", "memset(mean)", (long)e);
+  }
+  const int pb = pixels_per_block(N, HW);
+  split_nhwc8_kernel<<<dim3((HW + pb - 1) / pb, N), 256, 0, st>>>(in, HW, C, pb, (__nv_bfloat16*)out, out_ld,
+                                                                 out_coff, part_stride, parts, mean_out,
+                                                                 1.0f / (float)HW);
+  DHD_CUDA_LAUNCH_CHECK("split_nhwc8");
+  return DHD_OK;
+}
+
 extern "C" int dhd_split_nhwc(const float* in, long rows, int C, void* out, int out_ld, int out_coff,
                               int part_stride, int parts, void* stream) {
   DHD_REQUIRE(in && out, "null pointer");
   DHD_REQUIRE(rows > 0 && C > 0 && C % 2 == 0 && parts >= 1 && parts <= 3, "bad shape (C must be even)");
   DHD_REQUIRE(out_ld % 2 == 0 && out_coff % 2 == 0 && part_stride % 2 == 0, "channel offsets must be even");
   DHD_REQUIRE(((uintptr_t)in & 7) == 0, "input must be 8-byte aligned");
+  if (vec8_ok(C, out_ld, out_coff, part_stride, in, out) && rows < (1L << 31))
+    return dhd_split_nhwc_mean(in, 1, (int)rows, C, out, out_ld, out_coff, part_stride, parts, nullptr, stream);
   const long total = rows * (C / 2);
   split_nhwc_kernel<<<(int)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       in, rows, C, (__nv_bfloat16*)out, out_ld, out_coff, part_stride, parts);
@@ -304,6 +548,17 @@ extern "C" int dhd_mean_hw(const void* in, int in_ld, int in_coff, int part_stri
                            int C, int HW, float* out, void* stream) {
   DHD_REQUIRE(in && out, "null pointer");
   DHD_REQUIRE(N > 0 && C > 0 && HW > 0 && parts >= 1 && parts <= 3, "bad shape");
+  cudaStream_t st8 = (cudaStream_t)stream;
+  if (vec8_ok(C, in_ld, in_coff, part_stride, in, out)) {
+    cudaError_t e = cudaMemsetAsync(out, 0, (size_t)N * C * sizeof(float), st8);
+    if (e != cudaSuccess) return fail((int)e, "%s: %ld", "memset(mean)", (long)e);
+    const int pb = pixels_per_block(N, HW);
+    mean_hw8_kernel<<<dim3((HW + pb - 1) / pb, N), 256, 0, st8>>>((const __nv_bfloat16*)in, in_ld, in_coff,
+                                                                 part_stride, parts, C, HW, pb, out,
+                                                                 1.0f / (float)HW);
+    DHD_CUDA_LAUNCH_CHECK("mean_hw8");
+    return DHD_OK;
+  }
   const int cblocks = (C + 63) / 64;
   int splits = 1;
   if (HW > 4096) splits = min(64, max(1, (sm_count() * 4) / (cblocks * N)));
@@ -332,11 +587,34 @@ extern "C" int dhd_linear_rows(const float* x, int R, int K, const float* w, con
   return DHD_OK;
 }
 
+extern "C" int dhd_gate_channels(const float* x, int N, int HW, int C, const float* gate, void* out, int o_ld,
+                                 int o_coff, int o_part_stride, int o_parts, float* out32, void* stream) {
+  DHD_REQUIRE(x && gate && out, "null pointer");
+  DHD_REQUIRE(N > 0 && HW > 0 && C > 0 && C % 8 == 0 && o_parts >= 1 && o_parts <= 3, "bad shape (C % 8)");
+  DHD_REQUIRE(o_ld % 8 == 0 && o_coff % 8 == 0 && o_part_stride % 8 == 0, "channel offsets must be multiples of 8");
+  DHD_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)gate & 15) == 0 && ((uintptr_t)out & 15) == 0 &&
+                  ((uintptr_t)out32 & 15) == 0, "pointers must be 16-byte aligned");
+  const long total = (long)N * HW * (C / 8);
+  gate_channels_kernel<<<(int)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      x, C, (long)N * HW, HW, gate, (__nv_bfloat16*)out, o_ld, o_coff, o_part_stride, o_parts, out32);
+  DHD_CUDA_LAUNCH_CHECK("gate_channels");
+  return DHD_OK;
+}
+
 extern "C" int dhd_sfa_mix(const void* x, int x_ld, int x_coff, int x_part_stride, int x_parts, int C,
                            int N, int HW, const float* a1, const float* a2, void* out, int o_ld,
                            int o_coff, int o_part_stride, int o_parts, void* stream) {
   DHD_REQUIRE(x && a1 && out, "null pointer");
   DHD_REQUIRE(C > 0 && C % 2 == 0 && N > 0 && HW > 0, "bad shape");
+  if (vec8_ok(C, x_ld, x_coff, x_part_stride, x, out) && o_ld % 8 == 0 && o_coff % 8 == 0 &&
+      o_part_stride % 8 == 0 && ((uintptr_t)a1 & 15) == 0 && ((uintptr_t)a2 & 15) == 0) {
+    const long total8 = (long)N * HW * (C / 8);
+    sfa_mix8_kernel<<<(int)((total8 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x, x_ld, x_coff, x_part_stride, x_parts, C, (long)N * HW, HW, a1, a2,
+        (__nv_bfloat16*)out, o_ld, o_coff, o_part_stride, o_parts);
+    DHD_CUDA_LAUNCH_CHECK("sfa_mix8");
+    return DHD_OK;
+  }
   const long total = (long)N * HW * (C / 2);
   sfa_mix_kernel<<<(int)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)x, x_ld, x_coff, x_part_stride, x_parts, C, (long)N * HW, HW, a1, a2,
@@ -353,6 +631,14 @@ extern "C" int dhd_dcn_im2col(const void* x, int x_ld, int x_coff, int x_part_st
   DHD_REQUIRE(C > 0 && groups > 0 && C % groups == 0 && (C / groups) % 2 == 0, "bad channel grouping");
   DHD_REQUIRE(N > 0 && H > 0 && W > 0 && ksize >= 1 && ksize <= 3, "bad shape");
   const long warps = (long)N * H * W * ksize * ksize;
+  if ((C / groups) % 8 == 0 && x_ld % 8 == 0 && x_coff % 8 == 0 && x_part_stride % 8 == 0 && o_ld % 8 == 0 &&
+      o_part_stride % 8 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)out & 15) == 0) {
+    dcn_im2col8_kernel<<<(int)((warps * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x, x_ld, x_coff, x_part_stride, x_parts, C, N, H, W, offset, off_ld, ksize, pad,
+        dilation, groups, (__nv_bfloat16*)out, o_ld, o_part_stride, o_parts);
+    DHD_CUDA_LAUNCH_CHECK("dcn_im2col8");
+    return DHD_OK;
+  }
   dcn_im2col_kernel<<<(int)((warps * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)x, x_ld, x_coff, x_part_stride, x_parts, C, N, H, W, offset, off_ld, ksize,
       pad, dilation, groups, (__nv_bfloat16*)out, o_ld, o_part_stride, o_parts);

@@ -776,7 +776,7 @@ extern "C" int dhd_mghs_pool_fwd(const dhd_mghs_cfg* cfg, const float* depth, co
   DHD_REQUIRE(depth && feat && workspace && out_host, "null pointer");
   bool masked = false;
   for (int p = 0; p < cfg->n_pass; ++p) {
-    DHD_REQUIRE(out_host[p] != nullptr, "output pointer is null");
+    if (layout != DHD_LAYOUT_NCDHW_CAT || p < 2) DHD_REQUIRE(out_host[p] != nullptr, "output pointer is null");
     masked |= cfg->mask_id[p] != 0;
   }
   DHD_REQUIRE(!masked || pixmask != nullptr, "a pass is masked but pixmask is null");
@@ -803,6 +803,22 @@ extern "C" int dhd_mghs_pool_fwd(const dhd_mghs_cfg* cfg, const float* depth, co
         P.plane_cell_stride[k] = 0;
         P.plane_b_stride[k] = (long)cfg->dz[p] * kC * DyDx;
         P.plane_c_stride[k] = (int)(cfg->dz[p] * DyDx);
+      } else if (layout == DHD_LAYOUT_NCDHW_CAT) {
+        int zc = 0, zo = 0;                    // planes of the stacked tensor, offset of this pass
+        for (int q = 1; q < cfg->n_pass; ++q) {
+          if (q < p) zo += cfg->dz[q];
+          zc += cfg->dz[q];
+        }
+        if (p == 0) {
+          P.plane_ptr[k] = out_host[0] + (size_t)z * DyDx;
+          P.plane_b_stride[k] = (long)cfg->dz[0] * kC * DyDx;
+          P.plane_c_stride[k] = (int)(cfg->dz[0] * DyDx);
+        } else {
+          P.plane_ptr[k] = out_host[1] + (size_t)(zo + z) * DyDx;
+          P.plane_b_stride[k] = (long)zc * kC * DyDx;
+          P.plane_c_stride[k] = (int)(zc * DyDx);
+        }
+        P.plane_cell_stride[k] = 0;
       } else {
         return fail(DHD_EINVAL, "%s: %ld", "unknown layout", (long)layout);
       }

@@ -72,6 +72,7 @@ class Act:
         self.ld = data.shape[3]
         self.coff = 0
         self.part_stride = C
+        self.mean = None          # optional (N, C) fp32 per-image channel means made by the producer
 
     @staticmethod
     def empty(N, H, W, C, parts, device):
@@ -83,6 +84,7 @@ class Act:
         a.data, a.C, a.parts = self.data, c_hi - c_lo, self.parts
         a.N, a.H, a.W, a.ld = self.N, self.H, self.W, self.ld
         a.coff, a.part_stride = self.coff + c_lo, self.part_stride
+        a.mean = None
         return a
 
     def float(self):
@@ -132,17 +134,18 @@ def pack_input(x, parts):
     return out
 
 
-def pack_any(x, parts):
+def pack_any(x, parts, want_mean=False):
     """Logical (N, C, H, W) fp32 tensor in either memory format -> Act."""
     if x.dim() != 4:
         raise ValueError('expected a (N, C, H, W) tensor')
     if not x.is_contiguous() and x.permute(0, 2, 3, 1).is_contiguous():
-        return pack_nhwc(x.permute(0, 2, 3, 1), parts)
+        return pack_nhwc(x.permute(0, 2, 3, 1), parts, want_mean=want_mean)
     return pack_input(x, parts)
 
 
-def pack_nhwc(x, parts):
-    """(N, H, W, C) contiguous fp32 -> Act: the pack kernel run on an (N*H*W, C, 1, 1) view."""
+def pack_nhwc(x, parts, want_mean=False):
+    """(N, H, W, C) contiguous fp32 -> Act.  want_mean=True also produces the per-image channel
+    means in the same pass (attached as `act.mean`, consumed by the SFA squeeze)."""
     lib = _lib.load()
     N, H, W, C = x.shape
     Cp = (C + 63) // 64 * 64
@@ -150,6 +153,13 @@ def pack_nhwc(x, parts):
     out = Act.empty(N, H, W, Cp, parts, x.device)
     if Cp != C:
         out.data.zero_()
+    if want_mean and C % 8 == 0 and 256 % (C // 8) == 0:
+        mean = torch.empty(N, C, device=x.device)
+        _lib.check(lib.dhd_split_nhwc_mean(ctypes.c_void_p(x.data_ptr()), N, H * W, C,
+                                           ctypes.c_void_p(out.data.data_ptr()), out.ld, 0, Cp, parts,
+                                           ctypes.c_void_p(mean.data_ptr()), _stream()), 'split_nhwc_mean')
+        out.mean = mean
+        return out
     _lib.check(lib.dhd_split_nhwc(ctypes.c_void_p(x.data_ptr()), N * H * W, C,
                                   ctypes.c_void_p(out.data.data_ptr()), out.ld, 0, Cp, parts,
                                   _stream()), 'split_nhwc')

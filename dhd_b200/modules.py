@@ -169,6 +169,13 @@ class HeightNetEngine:
         h = new(C)
         h32 = torch.empty(N, H, W, C, device=dev)
         self.reduce(x, [dict(act='relu', out_act=h, out_f32=(h32, nhwc))], img_gate=gate)
+        return self.trunk(h, h32, softmax)
+
+    def trunk(self, h, h32, softmax=True):
+        """BasicBlocks -> ASPP -> DCN -> 1x1 head on the gated feature map (Act + its fp32 copy)."""
+        N, H, W, C, P, dev = h.N, h.H, h.W, self.C, self.parts, h.data.device
+        new = lambda c: D.Act.empty(N, H, W, c, P, dev)
+        nhwc = D.nhwc_strides(C, H, W)
         for c1, c2 in self.blocks:
             t = new(C)
             c1(h, [dict(act='relu', out_act=t)])
@@ -204,6 +211,48 @@ class HeightNetEngine:
         self.head(h, [dict(act='softmax' if softmax else None,
                            out_f32=(height, D.nchw_strides(self.H_bins, H, W)))])
         return height
+
+
+class DepthNetEngine(HeightNetEngine):
+    """DepthNet of MGHS_Depth / MGHS_Stereo (depthnet.py:172-243, 362-415), non-stereo path:
+    the reduce_conv output feeds a camera-gated context branch (1x1 conv) and a camera-gated
+    depth trunk (the same trunk as HeightNet).  Returns (depth (B*N, D, fH, fW) NCHW, softmax-ed
+    or raw, context (B*N, fH, fW, C) NHWC) -- the pool's input layouts."""
+
+    def __init__(self, net, precision='fp32', device='cuda'):
+        super().__init__(net, precision, device)
+        f = lambda t: t.detach().float().contiguous().to(device)
+        m, se = net.context_mlp, net.context_se
+        self.cfc1_w, self.cfc1_b, self.cfc2_w, self.cfc2_b = f(m.fc1.weight), f(m.fc1.bias), f(m.fc2.weight), f(m.fc2.bias)
+        self.cse_r_w, self.cse_r_b = f(se.conv_reduce.weight.flatten(1)), f(se.conv_reduce.bias)
+        self.cse_e_w, self.cse_e_b = f(se.conv_expand.weight.flatten(1)), f(se.conv_expand.bias)
+        self.context = _Conv(net.context_conv, None, precision, device)
+        self.Cctx = self.context.Cout
+
+    def context_gate(self, mlp_input):
+        x = mlp_input.reshape(-1, mlp_input.shape[-1]).contiguous().float()
+        h = linear_rows(x, self.cfc1_w, self.cfc1_b, 'relu', self.bn_scale, self.bn_shift)
+        h = linear_rows(h, self.cfc2_w, self.cfc2_b)
+        h = linear_rows(h, self.cse_r_w, self.cse_r_b, 'relu')
+        return linear_rows(h, self.cse_e_w, self.cse_e_b, 'sigmoid')
+
+    def _gated(self, x32, gate, want32):
+        N, H, W, C = x32.shape
+        out = D.Act.empty(N, H, W, C, self.parts, x32.device)
+        o32 = torch.empty_like(x32) if want32 else None
+        _lib.check(_lib.load().dhd_gate_channels(_p(x32), N, H * W, C, _p(gate), _p(out.data), out.ld, out.coff,
+                                                 out.part_stride, out.parts, _p(o32), _stream()), 'gate_channels')
+        return out, o32
+
+    def __call__(self, x, mlp_input, softmax=True):
+        N, H, W, C, dev = x.N, x.H, x.W, self.C, x.data.device
+        x32 = torch.empty(N, H, W, C, device=dev)
+        self.reduce(x, [dict(act='relu', out_f32=(x32, D.nhwc_strides(C, H, W)))])
+        ctx, _ = self._gated(x32, self.context_gate(mlp_input), False)
+        feat = torch.empty(N, H, W, self.Cctx, device=dev)
+        self.context(ctx, [dict(out_f32=(feat, D.nhwc_strides(self.Cctx, H, W)))])
+        h, h32 = self._gated(x32, self.gate(mlp_input), True)
+        return self.trunk(h, h32, softmax), feat
 
 
 class DepthHeadEngine:
@@ -251,7 +300,7 @@ class SFAEngine:
         """x: Act (B, 2C, Dy, Dx) = cat(bev feature, voxel feature).  Returns Act (B, Cout, Dy, Dx)."""
         N, H, W, C, P, dev = x.N, x.H, x.W, self.C, self.parts, x.data.device
         new = lambda c: D.Act.empty(N, H, W, c, P, dev)
-        s = mean_hw(x)
+        s = x.mean if getattr(x, 'mean', None) is not None else mean_hw(x)
         a1 = linear_rows(linear_rows(s, self.fc0_w, self.fc0_b, 'relu'), self.fc2_w, self.fc2_b, 'sigmoid')
         u = new(C)
         self._mix(x, a1, None, u)

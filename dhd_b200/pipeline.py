@@ -165,7 +165,7 @@ class HotPathStep:
         self.plan.raw_forward(L['depth'], L['feat'], L['pixmask'], self.outs, 'nhwc', workspace=self.workspace)
 
     def _back(self):
-        enc = D.pack_nhwc(self.encoded, self.parts)
+        enc = D.pack_nhwc(self.encoded, self.parts, want_mean=True)
         fused = self.sfa_engine(enc)
         logits = self.head_engine(fused)
         _lib.check(_lib.load().dhd_occ_argmax(ctypes.c_void_p(logits.data_ptr()), self.occ.numel(), 18,

@@ -11,9 +11,9 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import LAYOUT_NCDHW, LAYOUT_NCHW_COLLAPSE, LAYOUT_NHWC, MghsCfg
+from ._lib import LAYOUT_NCDHW, LAYOUT_NCDHW_CAT, LAYOUT_NCHW_COLLAPSE, LAYOUT_NHWC, MghsCfg
 
-_LAYOUTS = {'nhwc': LAYOUT_NHWC, 'nchw': LAYOUT_NCHW_COLLAPSE, 'ncdhw': LAYOUT_NCDHW}
+_LAYOUTS = {'nhwc': LAYOUT_NHWC, 'nchw': LAYOUT_NCHW_COLLAPSE, 'ncdhw': LAYOUT_NCDHW, 'ncdhw_cat': LAYOUT_NCDHW_CAT}
 
 
 def _stream():
@@ -243,6 +243,9 @@ class MghsPool:
 
     # -- pooling -----------------------------------------------------------------------
     def alloc_outputs(self, layout, device):
+        if layout == 'ncdhw_cat':     # pass 0 alone, passes 1.. stacked on z (MGHS_Depth, LH:845)
+            return [torch.empty(self.B, self.C, self.dz[0], self.Dy, self.Dx, device=device),
+                    torch.empty(self.B, self.C, sum(self.dz[1:]), self.Dy, self.Dx, device=device)]
         outs = []
         for dz in self.dz:
             if layout == 'nhwc':
@@ -271,7 +274,9 @@ class MghsPool:
 
     def raw_forward(self, depth, feat, pixmask, outs, layout='nhwc', workspace=None):
         """Enqueue the pool kernel into preallocated outputs (no autograd, no allocation)."""
-        arr = (ctypes.c_void_p * len(outs))(*[o.data_ptr() for o in outs])
+        ptrs = [o.data_ptr() for o in outs]
+        ptrs += [0] * (len(self.passes) - len(ptrs))          # 'ncdhw_cat' hands over two tensors
+        arr = (ctypes.c_void_p * len(ptrs))(*ptrs)
         _lib.check(self._lib.dhd_mghs_pool_fwd(
             ctypes.byref(self.cfg), _ptr(depth), _ptr(feat), _ptr(pixmask),
             _ptr(workspace if workspace is not None else self.workspace), arr, _LAYOUTS[layout],
@@ -288,6 +293,13 @@ class MghsPool:
         return outs
 
     def _backward(self, depth, feat, pixmask, gouts, layout, workspace):
+        if layout == 'ncdhw_cat':     # split the stacked gradient back into per-pass (B, C, dz, Dy, Dx) views
+            g0, gc = gouts
+            parts, z = [], 0
+            for dz in self.dz[1:]:
+                parts.append(None if gc is None else gc[:, :, z:z + dz])
+                z += dz
+            gouts, layout = [g0] + parts, 'ncdhw'
         gs = []
         for g, dz in zip(gouts, self.dz):
             if g is None:
@@ -312,6 +324,7 @@ class MghsPool:
     def __call__(self, depth, feat, pixmask=None, layout='nhwc'):
         """depth (B,N,D,fH,fW) or (B*N,D,fH,fW); feat (B,N,fH,fW,C) channels-last context;
         pixmask int8 (B*N,fH,fW).  Returns one tensor per pass in the memory `layout`:
-        'nhwc' (B,Dy,Dx,dz*C) | 'nchw' (B,dz*C,Dy,Dx) | 'ncdhw' (B,C,dz,Dy,Dx).
+        'nhwc' (B,Dy,Dx,dz*C) | 'nchw' (B,dz*C,Dy,Dx) | 'ncdhw' (B,C,dz,Dy,Dx) | 'ncdhw_cat' (two
+        tensors: pass 0 as ncdhw, passes 1.. stacked on z).
         Differentiable w.r.t. depth and feat."""
         return _MghsPoolFn.apply(depth, feat, self, pixmask, layout)

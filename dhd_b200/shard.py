@@ -1,0 +1,45 @@
+"""Multi-GPU plumbing of the hot path: the batch-sample axis is the only shard axis (a sample's
+voxel reduction sums over its 6 cameras); one process per GPU, no data-path
+collective.  The only collectives are bookkeeping: the max-over-ranks of the timed regions and
+(optionally) gathering the per-rank class maps on rank 0, like mmdet's multi_gpu_test
+(tools/test.py:267)."""
+import torch
+import torch.distributed as dist
+
+
+def shard_samples(global_batch, world, rank):
+    """Contiguous, balanced split of sample indices [0, global_batch) over `world` ranks."""
+    if not 0 <= rank < world:
+        raise ValueError('rank %d outside world %d' % (rank, world))
+    base, extra = divmod(global_batch, world)
+    lo = rank * base + min(rank, extra)
+    return list(range(lo, lo + base + (1 if rank < extra else 0)))
+
+
+def max_over_ranks(values, device='cpu'):
+    """Element-wise MAX of a list of floats over all ranks (timing aggregation)."""
+    t = torch.tensor(list(values), dtype=torch.float64, device=device)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.tolist()
+
+
+def samples_per_second(samples_all_ranks, ms):
+    return samples_all_ranks / (ms * 1e-3)
+
+
+def gather_on_rank0(t):
+    """Concatenate per-rank results along dim 0 on rank 0 (None elsewhere)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return t
+    world, rank = dist.get_world_size(), dist.get_rank()
+    sizes = [torch.zeros(1, dtype=torch.int64, device=t.device) for _ in range(world)]
+    dist.all_gather(sizes, torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device))
+    mx = int(max(s.item() for s in sizes))
+    pad = torch.zeros((mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    pad[:t.shape[0]] = t
+    bufs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(bufs, pad)
+    if rank != 0:
+        return None
+    return torch.cat([b[:int(s.item())] for b, s in zip(bufs, sizes)], dim=0)

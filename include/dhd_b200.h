@@ -51,7 +51,9 @@ enum {
 enum {
   DHD_LAYOUT_NHWC = 0,          /* (b, y, x, z, c): channels_last of the collapsed tensor; fastest */
   DHD_LAYOUT_NCHW_COLLAPSE = 1, /* (b, z, c, y, x): contiguous (B, dz*C, Dy, Dx), the reference layout */
-  DHD_LAYOUT_NCDHW = 2          /* (b, c, z, y, x): contiguous (B, C, dz, Dy, Dx), collapse_z=False */
+  DHD_LAYOUT_NCDHW = 2,         /* (b, c, z, y, x): contiguous (B, C, dz, Dy, Dx), collapse_z=False */
+  DHD_LAYOUT_NCDHW_CAT = 3      /* pass 0 as NCDHW into out[0]; passes 1.. stacked on z in ONE tensor out[1] of
+                                   shape (B, C, sum dz[1..], Dy, Dx): MGHS_Depth's torch.cat(dim=2), lss_heightmap.py:845 */
 };
 
 /* One fused view-transform problem: a frustum of B*N*D*fH*fW points pooled into
@@ -200,6 +202,10 @@ long dhd_launch_count(void);
 /* fp32 rows [rows][C] (NHWC) -> split-bf16 rows */
 int dhd_split_nhwc(const float* in, long rows, int C, void* out, int out_ld, int out_coff,
                    int part_stride, int parts, void* stream);
+/* same for an (N, HW, C) tensor, optionally also writing the per-image channel means
+ * (mean_out [N][C] or NULL): the SFA squeeze (mix.py:41) fused into the one read of the tensor */
+int dhd_split_nhwc_mean(const float* in, int N, int HW, int C, void* out, int out_ld, int out_coff,
+                        int part_stride, int parts, float* mean_out, void* stream);
 int dhd_unpack_nhwc_to_nchw(const void* in, int in_ld, int in_coff, int part_stride, int parts,
                             int N, int C, int H, int W, float* out, void* stream);
 /* out[n][c] = mean over the HW pixels (AdaptiveAvgPool2d(1): depthnet.py:77-82; mix.py:41) */
@@ -210,6 +216,11 @@ int dhd_mean_hw(const void* in, int in_ld, int in_coff, int part_stride, int par
 int dhd_linear_rows(const float* x, int R, int K, const float* w, const float* b, int O, int act,
                     const float* in_scale, const float* in_shift, int one_minus, float* y,
                     void* stream);
+/* out = x * gate[n][c]: SELayer's multiply (depthnet.py:169) for a feature map that feeds two
+ * differently gated branches (DepthNet.forward, depthnet.py:388-396); x fp32 NHWC [N][HW][C];
+ * out split-bf16 NHWC, out32 optional fp32 NHWC copy (residual input of the next block) */
+int dhd_gate_channels(const float* x, int N, int HW, int C, const float* gate, void* out, int o_ld,
+                      int o_coff, int o_part_stride, int o_parts, float* out32, void* stream);
 /* channel_spatial_stage blends (mix.py:44-57): x holds bev channels [0,C) and voxel channels
  * [C,2C); a1 [N][C]; a2 NULL -> a1*bev + (1-a1)*vox, else a2*(a1*bev) + (1-a2)*((1-a1)*vox) with
  * a2 fp32 NHWC [pix][C] (already sigmoid-ed) */

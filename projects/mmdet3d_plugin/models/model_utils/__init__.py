@@ -1,3 +1,3 @@
-from .depthnet import ASPP, HeightNet, Mlp, SELayer
+from .depthnet import ASPP, DepthNet, HeightNet, Mlp, SELayer
 
-__all__ = ['HeightNet', 'ASPP', 'Mlp', 'SELayer']
+__all__ = ['DepthNet', 'HeightNet', 'ASPP', 'Mlp', 'SELayer']

@@ -65,29 +65,103 @@ class SELayer(nn.Module):
         self.gate = gate_layer()
 
 
+def _trunk_layers(mid_channels, depth_channels, use_dcn, use_aspp, aspp_mid_channels, stereo):
+    """depth_conv of DepthNet / HeightNet: 3 BasicBlocks [+ ASPP] [+ DCN] + 1x1 (depthnet.py:203-243, 448-484)."""
+    first_in, downsample = mid_channels, None
+    if stereo:
+        first_in = mid_channels + depth_channels
+        downsample = nn.Conv2d(first_in, mid_channels, 1, 1, 0)
+    layers = [BasicBlock(first_in, mid_channels, downsample=downsample),
+              BasicBlock(mid_channels, mid_channels), BasicBlock(mid_channels, mid_channels)]
+    if use_aspp:
+        layers.append(ASPP(mid_channels, mid_channels if aspp_mid_channels < 0 else aspp_mid_channels))
+    if use_dcn:
+        layers.append(build_conv_layer(cfg=dict(type='DCN', in_channels=mid_channels, out_channels=mid_channels,
+                                                kernel_size=3, padding=1, groups=4, im2col_step=128)))
+    layers.append(nn.Conv2d(mid_channels, depth_channels, kernel_size=1, stride=1, padding=0))
+    return nn.Sequential(*layers)
+
+
+def _cost_volumn_net(depth_channels):
+    layers = []
+    for _ in range(2):
+        layers += [nn.Conv2d(depth_channels, depth_channels, kernel_size=3, stride=2, padding=1),
+                   nn.BatchNorm2d(depth_channels)]
+    return nn.Sequential(*layers)
+
+
+class DepthNet(nn.Module):
+    """Depth + context head of MGHS_Depth / MGHS_Stereo (reference depthnet.py:172-415).
+    stereo=True builds the reference's extra parameters (cost_volumn_net, first-block downsample)
+    so checkpoints load, but the plane-sweep cost volume itself is SURVEY 8(f) rank 3: forward raises."""
+
+    def __init__(self, in_channels, mid_channels, context_channels, depth_channels, use_dcn=True,
+                 use_aspp=True, with_cp=False, stereo=False, bias=0.0, aspp_mid_channels=-1, precision='fp32'):
+        super().__init__()
+        self.reduce_conv = nn.Sequential(
+            nn.Conv2d(in_channels, mid_channels, kernel_size=3, stride=1, padding=1),
+            nn.BatchNorm2d(mid_channels), nn.ReLU(inplace=True))
+        self.context_conv = nn.Conv2d(mid_channels, context_channels, kernel_size=1, stride=1, padding=0)
+        self.bn = nn.BatchNorm1d(27)
+        self.depth_mlp = Mlp(27, mid_channels, mid_channels)
+        self.depth_se = SELayer(mid_channels)
+        self.context_mlp = Mlp(27, mid_channels, mid_channels)
+        self.context_se = SELayer(mid_channels)
+        if stereo:
+            self.cost_volumn_net = _cost_volumn_net(depth_channels)
+            self.bias = bias
+        self.depth_conv = _trunk_layers(mid_channels, depth_channels, use_dcn, use_aspp, aspp_mid_channels, stereo)
+        self.with_cp, self.depth_channels, self.stereo = with_cp, depth_channels, stereo
+        self.precision = precision
+        self._engine = None
+
+    def _load_from_state_dict(self, *a, **k):
+        self._engine = None
+        return super()._load_from_state_dict(*a, **k)
+
+    def forward_split(self, x, mlp_input, softmax=True):
+        """-> (depth (B*N, D, fH, fW) NCHW [softmax-ed], context (B*N, fH, fW, C) NHWC): the layouts the
+        fused pool consumes, written directly by the layer epilogues."""
+        from dhd_b200 import dense as D
+        from dhd_b200.modules import DepthNetEngine
+        if self.training:
+            raise NotImplementedError('dhd_b200 DepthNet: inference (eval-mode BatchNorm) only in this build')
+        if self.stereo:
+            raise NotImplementedError('DepthNet(stereo=True): the cost-volume branch is SURVEY 8(f) rank 3')
+        if not isinstance(x, D.Act):
+            if not x.is_cuda:
+                raise RuntimeError('dhd_b200: expected CUDA tensors (the hot path has no CPU fallback)')
+            x = D.pack_input(x, D.PRECISIONS[self.precision][0])
+        with torch.no_grad():
+            if self._engine is None:
+                self._engine = DepthNetEngine(self, self.precision, x.data.device)
+            return self._engine(x, mlp_input, softmax=softmax)
+
+    def forward(self, x, mlp_input, stereo_metas=None):
+        """Reference signature: (B*N, D + C_context, fH, fW) logits, depthnet.py:362-415."""
+        if stereo_metas is not None:
+            raise NotImplementedError('stereo_metas: SURVEY 8(f) rank 3')
+        depth, ctx = self.forward_split(x, mlp_input, softmax=False)
+        return torch.cat([depth, ctx.permute(0, 3, 1, 2)], dim=1)
+
+
 class HeightNet(nn.Module):
     """Per-pixel height distribution head (reference depthnet.py:418-652)."""
 
     def __init__(self, in_channels, mid_channels, depth_channels, use_dcn=True, use_aspp=True,
                  with_cp=False, stereo=False, bias=0.0, aspp_mid_channels=-1, precision='fp32'):
         super().__init__()
-        if stereo:
-            raise NotImplementedError('HeightNet(stereo=True) cost-volume branch: SURVEY 8(f) rank 3')
+        self.stereo = stereo
         self.reduce_conv = nn.Sequential(
             nn.Conv2d(in_channels, mid_channels, kernel_size=3, stride=1, padding=1),
             nn.BatchNorm2d(mid_channels), nn.ReLU(inplace=True))
         self.bn = nn.BatchNorm1d(27)
         self.depth_mlp = Mlp(27, mid_channels, mid_channels)
         self.depth_se = SELayer(mid_channels)
-        layers = [BasicBlock(mid_channels, mid_channels) for _ in range(3)]
-        if use_aspp:
-            layers.append(ASPP(mid_channels, mid_channels if aspp_mid_channels < 0 else aspp_mid_channels))
-        if use_dcn:
-            layers.append(build_conv_layer(cfg=dict(type='DCN', in_channels=mid_channels,
-                                                    out_channels=mid_channels, kernel_size=3, padding=1,
-                                                    groups=4, im2col_step=128)))
-        layers.append(nn.Conv2d(mid_channels, depth_channels, kernel_size=1, stride=1, padding=0))
-        self.depth_conv = nn.Sequential(*layers)
+        if stereo:
+            self.cost_volumn_net = _cost_volumn_net(depth_channels)
+            self.bias = bias
+        self.depth_conv = _trunk_layers(mid_channels, depth_channels, use_dcn, use_aspp, aspp_mid_channels, stereo)
         self.with_cp = with_cp
         self.depth_channels = depth_channels
         self.precision = precision
@@ -118,8 +192,8 @@ class HeightNet(nn.Module):
         from dhd_b200 import dense as D
         if self.training:
             raise NotImplementedError('dhd_b200 HeightNet: inference (eval-mode BatchNorm) only in this build')
-        if stereo_metas is not None:
-            raise NotImplementedError('stereo_metas: SURVEY 8(f) rank 3')
+        if stereo_metas is not None or self.stereo:
+            raise NotImplementedError('HeightNet stereo / cost-volume branch: SURVEY 8(f) rank 3')
         if not isinstance(x, D.Act):
             if not x.is_cuda:
                 raise RuntimeError('dhd_b200: expected CUDA tensors (the hot path has no CPU fallback)')

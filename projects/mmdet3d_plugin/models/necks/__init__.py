@@ -1,5 +1,5 @@
 from .identity import Identity
-from .lss_heightmap import MGHS
+from .lss_heightmap import MGHS, MGHS_Depth, MGHS_Stereo
 from .mix import SFA
 
-__all__ = ['SFA', 'Identity', 'MGHS']
+__all__ = ['SFA', 'Identity', 'MGHS', 'MGHS_Depth', 'MGHS_Stereo']

@@ -22,7 +22,7 @@ from dhd_b200.compat import NECKS, BaseModule, force_fp32
 from dhd_b200.pool import MghsPool, height_to_mask
 
 from ...ops import bev_pool_v2
-from ..model_utils import HeightNet
+from ..model_utils import DepthNet, HeightNet
 
 _BEV_PASS_GRID = {'x': [-40, 40, 0.4], 'y': [-40, 40, 0.4], 'z': [-1, 5.4, 6.4],
                   'depth': [1.0, 45.0, 0.5]}      # hard-coded by the reference, LH:425-431
@@ -282,3 +282,78 @@ class MGHS(BaseModule):
         preds = height.permute(0, 2, 3, 1).contiguous().view(-1, self.H)
         loss = torch.nn.functional.binary_cross_entropy(preds[fg].float(), labels[fg], reduction='none').sum()
         return self.loss_height_weight * loss / max(1.0, float(fg.sum()))
+
+
+@NECKS.register_module(force=True)
+class MGHS_Depth(MGHS):
+    """MGHS with the camera-aware DepthNet (DHD-M / DHD-L), reference LH:704-897.  Returns
+    (bev, bev_w_z, depth, height); with collapse_z=False bev is (B, C, 1, Dy, Dx) and bev_w_z the
+    low / mid / high slabs stacked on z, (B, C, 16, Dy, Dx) -- written in place by the pool kernel
+    (DHD_LAYOUT_NCDHW_CAT) instead of three tensors + torch.cat."""
+
+    def __init__(self, loss_depth_weight=3.0, depthnet_cfg=dict(), **kwargs):
+        super().__init__(**kwargs)
+        self.loss_depth_weight = loss_depth_weight
+        self.depth_net = DepthNet(in_channels=self.in_channels, mid_channels=self.in_channels,
+                                  context_channels=self.out_channels, depth_channels=self.D,
+                                  precision=self.precision, **depthnet_cfg)
+
+    def forward(self, input, stereo_metas=None):
+        from dhd_b200 import dense as D
+        x, mlp_input = input[0], input[7]
+        B, N, C, H, W = x.shape
+        if self.training:
+            raise NotImplementedError('dhd_b200 MGHS_Depth: the dense layers are inference-only in this build')
+        if stereo_metas is not None:
+            raise NotImplementedError('stereo_metas (plane-sweep cost volume): SURVEY 8(f) rank 3')
+        if not x.is_cuda:
+            raise RuntimeError('dhd_b200: expected CUDA tensors (the hot path has no CPU fallback)')
+        with torch.no_grad():
+            xa = D.pack_input(x.reshape(B * N, C, H, W), D.PRECISIONS[self.precision][0])
+            depth, feat = self.depth_net.forward_split(xa, mlp_input, softmax=True)
+            height = self.height_net(xa, mlp_input, None, softmax=True)
+            return self.view_transform(input, depth, None, height, feat_nhwc=feat)
+
+    def view_transform(self, input, depth, tran_feat, height, feat_nhwc=None):
+        B, N, _, H, W = input[0].shape
+        if not depth.is_cuda:
+            raise RuntimeError('dhd_b200: expected CUDA tensors (the hot path has no CPU fallback)')
+        if self.accelerate and not self.initial_flag and self._plan is not None:
+            plan = self._plan[1]
+        else:
+            plan = self._prepare(input)
+            self.initial_flag = not self.accelerate
+        if feat_nhwc is None:
+            feat_nhwc = tran_feat.view(B, N, self.out_channels, H, W).permute(0, 1, 3, 4, 2).contiguous()
+        feat_nhwc = feat_nhwc.view(B, N, H, W, self.out_channels)
+        pixmask = height_to_mask(height, self.height_range, self.mask_range)
+        if self.collapse_z:       # not used by any config; same concatenation on dim 2 as the reference
+            outs = plan(depth, feat_nhwc, pixmask, layout='nchw')
+            bev, bev_w_z = outs[0], torch.cat(outs[1:], dim=2)
+        else:
+            bev, bev_w_z = plan(depth, feat_nhwc, pixmask, layout='ncdhw_cat')
+        self.grid_config = dict(_BEV_PASS_GRID)        # "reset grid_config!", LH:848-854
+        self.create_grid_infos(**self.grid_config)
+        return bev, bev_w_z, depth, height
+
+    @force_fp32()
+    def get_depth_and_height_loss(self, gt_depth, gt_height, depth, height):
+        """LH:859-897: BCE of the depth and height distributions on foreground pixels."""
+        hl = self.get_downsampled_gt_height(gt_height)
+        dl = self.get_downsampled_gt_depth(gt_depth)
+        fg = dl.max(dim=1).values > 0.0
+        hp = height.permute(0, 2, 3, 1).contiguous().view(-1, self.H)[fg]
+        dp = depth.permute(0, 2, 3, 1).contiguous().view(-1, self.D)[fg]
+        bce = torch.nn.functional.binary_cross_entropy
+        norm = max(1.0, float(fg.sum()))
+        return (self.loss_depth_weight * bce(dp.float(), dl[fg], reduction='none').sum() / norm,
+                self.loss_height_weight * bce(hp.float(), hl[fg], reduction='none').sum() / norm)
+
+
+@NECKS.register_module(force=True)
+class MGHS_Stereo(MGHS_Depth):
+    """LH:900-907: MGHS_Depth + the 1/4-resolution frustum template the stereo cost volume uses."""
+
+    def __init__(self, **kwargs):
+        super().__init__(**kwargs)
+        self.cv_frustum = self.create_frustum(kwargs['grid_config']['depth'], kwargs['input_size'], downsample=4)

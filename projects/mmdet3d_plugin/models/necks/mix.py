@@ -60,7 +60,7 @@ class SFA(BaseModule):
             if not isinstance(inputs, D.Act):
                 if not inputs.is_cuda:
                     raise RuntimeError('dhd_b200: expected CUDA tensors (the hot path has no CPU fallback)')
-                inputs = D.pack_any(inputs, D.PRECISIONS[self.precision][0])
+                inputs = D.pack_any(inputs, D.PRECISIONS[self.precision][0], want_mean=True)
             if self._engine is None:
                 self._engine = SFAEngine(self, self.precision, inputs.data.device)
             if return_act:

@@ -88,7 +88,7 @@ def test_sfa_and_predictor_match_reference_fixture(cuda_lib):
     close(occ, torch.from_numpy(gold['occ']), 'occupancy logits')
     # channels_last input and the tensor (non-Act) path of the head
     fused_cl = sfa(bev.cuda().contiguous(memory_format=torch.channels_last))
-    assert torch.equal(fused_cl, fused)
+    close(fused_cl, fused, "SFA channels_last vs NCHW input", atol=1e-5, rtol=1e-5)   # squeeze mean uses fp32 atomics
     close(head(fused), torch.from_numpy(gold['occ']), 'occupancy logits (tensor path)')
 
 

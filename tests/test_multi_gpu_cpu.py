@@ -1,0 +1,59 @@
+"""world_size-2 gloo tests (CPU) of the N>1 plumbing: batch-axis sharding, max-over-ranks timing
+aggregation, result gathering -- the host logic bench.py and the plugin use under torchrun."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from dhd_b200 import shard
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        mine = shard.shard_samples(7, world, rank)
+        # each rank "processes" its samples: result row = sample id
+        res = torch.tensor(mine, dtype=torch.int64).view(-1, 1)
+        got = shard.gather_on_rank0(res)
+        times = shard.max_over_ranks([10.0 + rank, 5.0 - rank])
+        dist.barrier()
+        q.put((rank, mine, None if got is None else got.flatten().tolist(), times))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shard_is_a_partition():
+    for world in (1, 2, 4, 8):
+        for gb in (1, 7, 32):
+            parts = [shard.shard_samples(gb, world, r) for r in range(world)]
+            assert sorted(sum(parts, [])) == list(range(gb))
+            assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+
+
+def test_two_rank_gloo_aggregation():
+    world, port = 2, _free_port()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (r0, m0, g0, t0), (r1, m1, g1, t1) = out
+    assert m0 == [0, 1, 2, 3] and m1 == [4, 5, 6]
+    assert g0 == list(range(7)) and g1 is None
+    assert t0 == t1 == [11.0, 5.0]          # element-wise max over the two ranks
+    assert shard.samples_per_second(8, 2.0) == 4000.0
