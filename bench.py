@@ -212,7 +212,7 @@ def run_ours(args):
                     'h2d_bytes_per_step': step.h2d_bytes, 'd2h_bytes_per_step': step.d2h_bytes},
             'gpu_launches': step.launches_per_step * args.steps * 2,
             'roofline': {
-                'kernel': 'mghs_pool_nhwc_smem_kernel (fused 4-pass voxel pool forward)',
+                'kernel': 'mghs_pool_stream_kernel (fused 4-pass voxel pool forward, TMA bulk stores)',
                 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                 'frac': achieved / peak, 'frac_of_nominal_8TBs': achieved / 8000.0,
                 'peak_source': peak_src, 'traffic': step.ncu_traffic_bytes(),

@@ -25,10 +25,11 @@ constexpr int kC = 64;            // numC_Trans of every DHD config
 constexpr int kScanChunk = 4096;  // cells per scan block (1024 threads x 4)
 constexpr int kMaxScanBlocks = 1024;
 constexpr int kDetCap = 4096;     // longest bin that is put in canonical order
+constexpr int kMaxChunks = 65536; // work chunks of the streaming pool kernel
 
 struct WsLayout {
   size_t cell_count, cell_start, blk_sum, blk_prefix, total_entries;
-  size_t pt_cell, pt_zb, pt_slot, entries, entries_tmp, bytes;
+  size_t pt_cell, pt_zb, pt_slot, entries, entries_tmp, chunks, bytes;
   long F;
   int ncell, ncell_pad, nblk;
 };
@@ -61,12 +62,13 @@ static int ws_layout(const dhd_mghs_cfg* c, WsLayout* w) {
   w->cell_start = o;  o = align_up(o + (size_t)w->ncell_pad * 4, 256);
   w->blk_sum = o;     o = align_up(o + kMaxScanBlocks * 4, 256);
   w->blk_prefix = o;  o = align_up(o + kMaxScanBlocks * 4, 256);
-  w->total_entries = o; o = align_up(o + 16, 256);
+  w->total_entries = o; o = align_up(o + 256, 256);   // total, and at +64 the pool scheduler counters
   w->pt_cell = o;     o = align_up(o + (size_t)F * 4, 256);
   w->pt_zb = o;       o = align_up(o + (size_t)F * 4, 256);
   w->pt_slot = o;     o = align_up(o + (size_t)F * 4, 256);
   w->entries = o;     o = align_up(o + (size_t)F * 16, 256);
   w->entries_tmp = o; o = align_up(o + (size_t)F * 16, 256);
+  w->chunks = o;      o = align_up(o + (size_t)(kMaxChunks + 1) * 8, 256);
   w->bytes = o;
   return DHD_OK;
 }
@@ -271,6 +273,32 @@ mghs_canonical_kernel(const int4* __restrict__ src, int4* __restrict__ dst,
   }
 }
 
+// Work chunks of the streaming pool kernel: chunk k = cells [tab[k].x, tab[k+1].x) and binned
+// entries [tab[k].y, tab[k+1].y); boundaries are placed so that every chunk carries the same cost,
+// cost(cell) = cell_cost + entries(cell).  tab[k].x is the smallest cell c whose cost-before-c
+// reaches k*unit; the thread of cell c writes every k it is the boundary of (c == ncell closes
+// the table), so no search and no atomics.
+__global__ void __launch_bounds__(256)
+mghs_chunks_kernel(const int* __restrict__ cell_start, const int* __restrict__ blk_prefix,
+                   const int* __restrict__ total, int ncell, int nch, int cell_cost, int2* __restrict__ tab) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c > ncell) return;
+  const int tot = total[0];
+  const long cost = (long)cell_cost * ncell + tot;
+  const long unit = (cost + nch - 1) / nch > 0 ? (cost + nch - 1) / nch : 1;
+  auto before = [&](int cell) -> long {     // cost of all cells < cell
+    const int e = cell < ncell ? cell_start[cell] + blk_prefix[cell / kScanChunk] : tot;
+    return (long)cell_cost * cell + e;
+  };
+  const int e_c = c < ncell ? cell_start[c] + blk_prefix[c / kScanChunk] : tot;
+  const long hi = (long)cell_cost * c + e_c;
+  const long lo = c == 0 ? -1 : before(c - 1);
+  long k0 = lo < 0 ? 0 : lo / unit + 1;
+  long k1 = c == ncell ? nch : hi / unit;
+  if (k1 > nch) k1 = nch;
+  for (long k = k0; k <= k1; ++k) tab[k] = make_int2(c, e_c);
+}
+
 // ---------------------------------------------------------------------------- pool
 struct PoolParams {
   const int4* entries;
@@ -290,6 +318,10 @@ struct PoolParams {
   float* pass_ptr[DHD_MAX_PASSES];        // NHWC: base of pass p's output
   int pass_q[DHD_MAX_PASSES];             // NHWC: float4 per cell of pass p (dz * C / 4)
   int plane_c_stride[DHD_MAX_PLANES];     // NCHW: floats between channels
+  const int2* chunks;                     // work chunks of the streaming kernel (mghs_chunks_kernel)
+  int nch;
+  int* sched;                             // {next chunk, finished warps}: dynamic scheduler of the v3 kernel, self-resetting
+  int probe;                              // bandwidth probe (DHD_POOL_PROBE=1): treat every cell as empty
 };
 
 template <int MAXZ>
@@ -448,10 +480,10 @@ __global__ void __launch_bounds__(256, 6) mghs_pool_nhwc_smem_kernel(const PoolP
   const long cost = (long)kCellCost * P.ncell + total;
   int cell = find_cell(P, cost * gw / warps, total);
   const int cell_end = gw + 1 == warps ? P.ncell : find_cell(P, cost * (gw + 1) / warps, total);
-  int n = cell < cell_end ? __ldg(P.cell_count + cell) : 0;
+  int n = cell < cell_end && !P.probe ? __ldg(P.cell_count + cell) : 0;
   while (cell < cell_end) {
     const int next = cell + 1;
-    const int n_next = next < cell_end ? __ldg(P.cell_count + next) : 0;   // prefetch
+    const int n_next = next < cell_end && !P.probe ? __ldg(P.cell_count + next) : 0;   // prefetch
     if (n != 0) {
       for (int i = lane; i < nq; i += 32) col4[i] = zero4;
       __syncwarp();
@@ -515,6 +547,546 @@ __global__ void __launch_bounds__(256, 6) mghs_pool_nhwc_smem_kernel(const PoolP
     cell = next;
     n = n_next;
   }
+}
+
+// v3 of the NHWC pool: the same cell-owner gather, but every output byte leaves the SM through
+// the TMA unit (cp.async.bulk shared -> global) instead of the LSU:
+//   * a run of empty cells is ONE bulk copy per pass out of a zero tile in shared memory that is
+//     never written after set-up (lanes 0..npass-1 issue one pass each, nothing to wait for);
+//   * a non-empty cell accumulates into the warp's private shared-memory column exactly as in v2
+//     and the column then leaves as one bulk copy per pass (dz*256 contiguous bytes).  Columns are
+//     double-buffered per warp, so the gather of the next cell overlaps the TMA read of this one;
+//     only the planes a cell touched are re-zeroed when its buffer comes round again.
+// The warps therefore issue almost no store instructions (v2 spent 41 % of its issue slots in
+// the store loop, profiles/r01_pool_fwd_v3.txt) and never stall on store back-pressure: the SM's
+// instruction stream is the gather alone while the TMA engine keeps HBM writes saturated.
+__device__ __forceinline__ void bulk_store(void* gdst, uint32_t ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_store_hint(void* gdst, uint32_t ssrc, uint32_t bytes, uint64_t pol) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst),
+               "r"(ssrc), "r"(bytes), "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t smem_addr(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ int find_cell_c(const PoolParams& P, long target, int total, int cell_cost) {
+  int lo = 0, hi = P.ncell;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    const long cum = (long)cell_cost * mid + (mid < P.ncell ? bin_start(P, mid) : total);
+    if (cum >= target) hi = mid;
+    else lo = mid + 1;
+  }
+  return lo;
+}
+
+
+// Gather of one cell's bin into the warp's shared-memory column (lane l owns channels 2l, 2l+1
+// of every plane).  Entries are consumed in ascending order, 8 at a time:
+//   * the 8 context rows of group g+1 are requested before group g is accumulated (register
+//     double buffer), and the next 32 binned entries before the current 32 are consumed, so the
+//     L2 latency of one request overlaps the arithmetic of the previous one;
+//   * accumulation is plane-major: for every plane touched by the group the column slot is read
+//     once, receives the (up to 8) products in entry order, and is written once -- the slot of a
+//     plane no longer makes a shared-memory read-after-write round trip per entry (every entry
+//     hits the BEV plane).
+// The summation order per output element is ascending frustum-point order, as in v2.
+// Returns the planes written.
+constexpr int kG = 8;
+struct Batch { int pix; float dv; uint32_t bits; };
+__device__ __forceinline__ Batch load_batch(const PoolParams& P, int s, int n, int base, int lane) {
+  Batch b = {0, 0.f, 0u};
+  if (base + lane < n) {
+    const int4 e = __ldg(P.entries + s + base + lane);
+    b.pix = e.y;
+    b.dv = __ldg(P.depth + e.x);
+    const int pm = P.pixmask != nullptr ? (int)__ldg(P.pixmask + b.pix) : 0;
+    b.bits = plane_bits(P, (uint32_t)e.z, pm);
+    if (P.probe == 3) b.bits = b.dv == 123.456f ? 1u : 0u;
+  }
+  return b;
+}
+__device__ __forceinline__ void load_group(const PoolParams& P, const Batch& b, int j, int lane, float2 (&f)[kG]) {
+#pragma unroll
+  for (int u = 0; u < kG; ++u) {
+    const int px = __shfl_sync(kFull, b.pix, (j + u) & 31);
+    const uint32_t pb = __shfl_sync(kFull, b.bits, (j + u) & 31);
+    f[u] = make_float2(0.f, 0.f);
+    if (j + u < 32 && pb != 0) f[u] = __ldg(reinterpret_cast<const float2*>(P.feat + (size_t)px * kC) + lane);
+  }
+}
+__device__ __forceinline__ uint32_t gather_cell_smem(const PoolParams& P, int s, int n, float2* col2, int lane) {
+  uint32_t touched = 0;
+  Batch cur = load_batch(P, s, n, 0, lane);
+  float2 f[kG], fn[kG];
+  load_group(P, cur, 0, lane, f);
+  for (int base = 0; base < n; base += 32) {
+    const int m = min(32, n - base);
+    const bool more = base + 32 < n;
+    Batch nxt = {0, 0.f, 0u};
+    if (more) nxt = load_batch(P, s, n, base + 32, lane);
+    touched |= __reduce_or_sync(kFull, cur.bits);
+    for (int j = 0; j < m; j += kG) {
+      // request the next group's rows (of this batch, or the first group of the next batch)
+      if (j + kG < m) load_group(P, cur, j + kG, lane, fn);
+      else if (more) load_group(P, nxt, 0, lane, fn);
+      float d[kG];
+      uint32_t pb[kG];
+      uint32_t uni = 0;
+#pragma unroll
+      for (int u = 0; u < kG; ++u) {
+        d[u] = __shfl_sync(kFull, cur.dv, (j + u) & 31);
+        pb[u] = __shfl_sync(kFull, cur.bits, (j + u) & 31);
+        if (j + u >= 32) pb[u] = 0;            // lanes >= m carry bits == 0 already
+        uni |= pb[u];
+      }
+      while (uni != 0) {
+        const int z = __ffs(uni) - 1;
+        uni &= uni - 1;
+        float2 a = col2[z * 32 + lane];
+#pragma unroll
+        for (int u = 0; u < kG; ++u) {
+          if ((pb[u] >> z) & 1u) {
+            a.x = fmaf(f[u].x, d[u], a.x);
+            a.y = fmaf(f[u].y, d[u], a.y);
+          }
+        }
+        col2[z * 32 + lane] = a;
+      }
+#pragma unroll
+      for (int u = 0; u < kG; ++u) f[u] = fn[u];
+    }
+    cur = nxt;
+  }
+  return touched;
+}
+
+template <bool HINT>
+__global__ void __launch_bounds__(256, 2) mghs_pool_nhwc_tma_kernel(const PoolParams P, int cell_cost,
+                                                                 int zero_bytes, int chunk_cells, int windows) {
+  extern __shared__ __align__(128) uint8_t smem_pool[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int wpb = blockDim.x >> 5;
+  const uint32_t col_bytes = (uint32_t)P.nplanes * 256u;
+  {
+    float4* z = reinterpret_cast<float4*>(smem_pool);
+    const int n16 = (zero_bytes + wpb * 2 * (int)col_bytes) / 16;
+    for (int i = threadIdx.x; i < n16; i += blockDim.x) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  uint64_t pol = 0;
+  if (HINT) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  const uint32_t zero_s = smem_addr(smem_pool);
+  uint8_t* col_g = smem_pool + zero_bytes + (size_t)wid * 2 * col_bytes;
+  const uint32_t col_s = smem_addr(col_g);
+
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int total = __ldg(P.total_entries);
+  const long cost = (long)cell_cost * P.ncell + total;
+  // Work distribution.  chunk_cells > 0 (default): warps take chunks of consecutive cells from a
+  // global counter, so at any moment the whole GPU writes inside one sliding window of each
+  // output tensor -- the address pattern of a plain fill (measured: a fill with one private
+  // contiguous run per warp reaches 4.9 TB/s, a sliding window 5.9 TB/s, scripts/bench_pool.py
+  // probes) -- and heavy bins cannot leave a tail.  chunk_cells == 0: the static cost-balanced
+  // split of v2 (one contiguous run per warp).
+  int cell = 0, cell_end = 0;
+  if (chunk_cells == 0) {
+    cell = find_cell_c(P, cost * gw / warps, total, cell_cost);
+    cell_end = gw + 1 == warps ? P.ncell : find_cell_c(P, cost * (gw + 1) / warps, total, cell_cost);
+  }
+  // this lane's pass when it issues the zero-run copies
+  int my_q = 0;
+  char* my_out = nullptr;
+#pragma unroll
+  for (int p = 0; p < DHD_MAX_PASSES; ++p) {
+    if (p < P.npass && lane == p) {
+      my_q = P.pass_q[p];
+      my_out = reinterpret_cast<char*>(P.pass_ptr[p]);
+    }
+  }
+  int buf = 0;
+  uint32_t touched0 = 0, touched1 = 0;     // planes written in column buffer 0 / 1 by its last cell
+
+  for (;;) {
+  if (chunk_cells != 0) {
+    int ch = 0;
+    if (lane == 0) ch = atomicAdd(P.sched, 1);
+    ch = __shfl_sync(kFull, ch, 0);
+    // `windows` sliding windows evenly spaced over the cell range advance together, so dense
+    // (gather-heavy) and empty (write-only) regions of the grid are in flight at the same time
+    const int nchunks = (P.ncell + chunk_cells - 1) / chunk_cells;
+    const int per_win = (nchunks + windows - 1) / windows;
+    if (ch >= per_win * windows) break;
+    const int cidx = (ch % windows) * per_win + ch / windows;
+    if (cidx >= nchunks) continue;
+    cell = cidx * chunk_cells;
+    cell_end = min(cell + chunk_cells, P.ncell);
+  }
+  while (cell < cell_end) {
+    const int nb = min(32, cell_end - cell);
+    const int cnt = lane < nb && P.probe != 1 ? __ldg(P.cell_count + cell + lane) : 0;
+    const int s_mine = (lane < nb && cnt != 0) ? bin_start(P, cell + lane) : 0;
+    const uint32_t nz = __ballot_sync(kFull, cnt != 0);
+    int pos = 0;
+    while (pos < nb) {
+      const uint32_t rest = nz >> pos;
+      const int run = rest != 0 ? __ffs(rest) - 1 : nb - pos;
+      if (run > 0) {
+        if (my_out != nullptr) {
+          size_t bytes = (size_t)run * my_q * 16;
+          char* dst = my_out + (size_t)(cell + pos) * my_q * 16;
+          while (bytes != 0) {
+            const uint32_t b = bytes < (size_t)zero_bytes ? (uint32_t)bytes : (uint32_t)zero_bytes;
+            if (HINT) bulk_store_hint(dst, zero_s, b, pol);
+            else bulk_store(dst, zero_s, b);
+            dst += b;
+            bytes -= b;
+          }
+        }
+        pos += run;
+      }
+      if (pos >= nb) break;
+      // ---------------------------------------------------------------- non-empty cell
+      const int c = cell + pos;
+      const int n = __shfl_sync(kFull, cnt, pos);
+      const int s = __shfl_sync(kFull, s_mine, pos);
+      float2* col2 = reinterpret_cast<float2*>(col_g + (size_t)buf * col_bytes);
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");       // the copy that last read this buffer is done with it
+      __syncwarp();
+      uint32_t t = buf ? touched1 : touched0;
+      while (t != 0) {
+        const int z = __ffs(t) - 1;
+        t &= t - 1;
+        col2[z * 32 + lane] = make_float2(0.f, 0.f);
+      }
+      const uint32_t touched = P.probe == 2 ? 0u : gather_cell_smem(P, s, n, col2, lane);
+      if (buf) touched1 = touched; else touched0 = touched;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) {
+        const uint32_t src = col_s + (uint32_t)buf * col_bytes;
+#pragma unroll
+        for (int p = 0; p < DHD_MAX_PASSES; ++p) {
+          if (p < P.npass) {
+            const uint32_t bytes = (uint32_t)P.pass_q[p] * 16u;
+            char* dst = reinterpret_cast<char*>(P.pass_ptr[p]) + (size_t)c * bytes;
+            if (HINT) bulk_store_hint(dst, src + (uint32_t)P.zoff[p] * 256u, bytes, pol);
+            else bulk_store(dst, src + (uint32_t)P.zoff[p] * 256u, bytes);
+          }
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      buf ^= 1;
+      ++pos;
+    }
+    cell += nb;
+  }
+  if (chunk_cells == 0) break;
+  }
+  if (chunk_cells != 0 && lane == 0) {
+    // the last warp to run dry re-arms the scheduler for the next launch on this workspace
+    if (atomicAdd(P.sched + 1, 1) == warps - 1) {
+      P.sched[0] = 0;
+      P.sched[1] = 0;
+    }
+  }
+  // shared memory must outlive every bulk copy that reads it
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+
+// v4 of the NHWC pool ("stream"): same single-write output path as v3 (TMA bulk copies of zero
+// runs and of finished columns), but the gather no longer walks one cell at a time.  Under a
+// saturated write stream a dependent global load takes ~2 us (measured: the entries -> depth
+// -> context chain of v3 cost 8 us per non-empty cell per warp), so the per-warp dependent chain
+// has to go.  The bins of consecutive cells are contiguous in the entry list and every entry
+// carries its cell id, hence a work chunk is ONE contiguous stream of entries:
+//   stage A  entries of batch k+2 (32 per warp, coalesced)
+//   stage B  depth / mask id of batch k+1
+//   stage C  context rows of batch k, 8 entries per request with the next 8 requested before the
+//            current 8 are accumulated (across batch boundaries too)
+// all three in flight at once; a change of cell id inside the stream flushes the column (bulk
+// copy), zero-fills the empty cells that were skipped (bulk copy from the zero tile) and flips to
+// the warp's other column buffer.  Chunks carry equal cost (mghs_chunks_kernel) and are handed
+// out by a global counter through `windows` sliding windows, the next chunk id being requested
+// one chunk ahead.  Summation order per output element: ascending frustum-point order (as v2/v3).
+
+// loads that keep their line in L2 (evict_last): the pool's inputs (~18 MB) are re-read across the
+// kernel while 700 MB of write-once output stream through the same L2
+__device__ __forceinline__ uint64_t policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ int4 ld_keep(const int4* p, uint64_t pol) {
+  int4 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.s32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ float2 ld_keep(const float2* p, uint64_t pol) {
+  float2 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ float ld_keep(const float* p, uint64_t pol) {
+  float v;
+  asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ int ld_keep(const int8_t* p, uint64_t pol) {
+  int v;
+  asm volatile("ld.global.nc.L2::cache_hint.s8 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+}
+
+struct PoolLane {          // per-lane issue state for the zero-run copies
+  int q;
+  char* out;
+};
+
+template <bool HINT, int MINB>
+__global__ void __launch_bounds__(128, MINB) mghs_pool_stream_kernel(const PoolParams P, int zero_bytes, int windows) {
+  extern __shared__ __align__(128) uint8_t smem_pool[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int wpb = blockDim.x >> 5;
+  const uint32_t col_bytes = (uint32_t)P.nplanes * 256u;
+  {
+    float4* z = reinterpret_cast<float4*>(smem_pool);
+    const int n16 = (zero_bytes + wpb * 2 * (int)col_bytes) / 16;
+    for (int i = threadIdx.x; i < n16; i += blockDim.x) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  const uint64_t keep = policy_evict_last();
+  uint64_t pol = 0;
+  if (HINT) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  const uint32_t zero_s = smem_addr(smem_pool);
+  uint8_t* col_g = smem_pool + zero_bytes + (size_t)wid * 2 * col_bytes;
+  const uint32_t col_s = smem_addr(col_g);
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  int my_q = 0;
+  char* my_out = nullptr;
+#pragma unroll
+  for (int p = 0; p < DHD_MAX_PASSES; ++p) {
+    if (p < P.npass && lane == p) {
+      my_q = P.pass_q[p];
+      my_out = reinterpret_cast<char*>(P.pass_ptr[p]);
+    }
+  }
+  // zero-fill cells [c0, c1) of every pass: one bulk copy per pass and zero-tile-full
+  auto zero_run = [&](int c0, int c1) {
+    if (c1 > c0 && my_out != nullptr) {
+      size_t bytes = (size_t)(c1 - c0) * my_q * 16;
+      char* dst = my_out + (size_t)c0 * my_q * 16;
+      while (bytes != 0) {
+        const uint32_t b = bytes < (size_t)zero_bytes ? (uint32_t)bytes : (uint32_t)zero_bytes;
+        if (HINT) bulk_store_hint(dst, zero_s, b, pol);
+        else bulk_store(dst, zero_s, b);
+        dst += b;
+        bytes -= b;
+      }
+    }
+  };
+  const int per_win = (P.nch + windows - 1) / windows;
+  const int n_iter = per_win * windows;
+  auto fetch = [&]() {
+    int ch = 0;
+    if (lane == 0) ch = atomicAdd(P.sched, 1);
+    return ch;                               // valid in lane 0; broadcast when consumed
+  };
+  int buf = 0;
+  uint32_t touched0 = 0, touched1 = 0;
+  int next_raw = fetch();
+  for (;;) {
+    const int ch = __shfl_sync(kFull, next_raw, 0);
+    if (ch >= n_iter) break;
+    next_raw = fetch();
+    const int cidx = (ch % windows) * per_win + ch / windows;
+    if (cidx >= P.nch) continue;
+    const int2 t0 = __ldg(P.chunks + cidx), t1 = __ldg(P.chunks + cidx + 1);
+    const int cell_lo = t0.x, cell_hi = t1.x, e_lo = t0.y, e_hi = P.probe == 1 ? t0.y : t1.y;
+    int pos = cell_lo;                       // every cell < pos of this chunk has been written
+    int cur_cell = -1;
+    uint32_t touched = 0;
+    float2* col2 = reinterpret_cast<float2*>(col_g + (size_t)buf * col_bytes);
+    const int nE = e_hi - e_lo;
+    if (nE > 0) {
+      // ---- software pipeline registers
+      int a_pt = 0, a_pix = 0, a_cell = -1;
+      uint32_t a_zb = 0;
+      int b_pix = 0, b_cell = -1, b_pm = 0;
+      uint32_t b_zb = 0;
+      float b_dv = 0.f;
+      int c_pix = 0, c_cell = -1;
+      float c_dv = 0.f;
+      uint32_t c_bits = 0;
+      auto loadA = [&](int idx) {
+        a_pt = 0; a_pix = 0; a_cell = -1; a_zb = 0;
+        if (idx < e_hi) {
+          const int4 e = ld_keep(P.entries + idx, keep);
+          a_pt = e.x; a_pix = e.y; a_zb = (uint32_t)e.z; a_cell = e.w;
+        }
+      };
+      auto AtoB = [&]() {
+        b_pix = a_pix; b_cell = a_cell; b_zb = a_zb; b_dv = 0.f; b_pm = 0;
+        if (a_cell >= 0) {
+          b_dv = ld_keep(P.depth + a_pt, keep);
+          if (P.pixmask != nullptr) b_pm = ld_keep(P.pixmask + a_pix, keep);
+        }
+      };
+      auto BtoC = [&]() {
+        c_pix = b_pix; c_cell = b_cell; c_dv = b_dv;
+        c_bits = b_cell >= 0 ? plane_bits(P, b_zb, b_pm) : 0u;
+      };
+      auto load_group8 = [&](int pix, uint32_t bits, int j, float2 (&f)[kG]) {
+#pragma unroll
+        for (int u = 0; u < kG; ++u) {
+          const int px = __shfl_sync(kFull, pix, (j + u) & 31);
+          const uint32_t pb = __shfl_sync(kFull, bits, (j + u) & 31);
+          f[u] = make_float2(0.f, 0.f);
+          if (pb != 0) f[u] = ld_keep(reinterpret_cast<const float2*>(P.feat + (size_t)px * kC) + lane, keep);
+        }
+      };
+      loadA(e_lo + lane);
+      AtoB();
+      loadA(e_lo + 32 + lane);
+      BtoC();
+      AtoB();
+      loadA(e_lo + 64 + lane);
+      float2 f[kG], fn[kG];
+      load_group8(c_pix, c_bits, 0, f);
+      for (int base = 0; base < nE; base += 32) {
+        const int m = min(32, nE - base);
+        for (int j = 0; j < m; j += kG) {
+          if (j + kG < m) {
+            load_group8(c_pix, c_bits, j + kG, fn);
+          } else if (base + 32 < nE) {
+            const uint32_t nbits = b_cell >= 0 ? plane_bits(P, b_zb, b_pm) : 0u;
+            load_group8(b_pix, nbits, 0, fn);
+          }
+          float d[kG];
+          uint32_t pb[kG];
+          int cl[kG];
+          uint32_t rem = 0;
+#pragma unroll
+          for (int u = 0; u < kG; ++u) {
+            d[u] = __shfl_sync(kFull, c_dv, (j + u) & 31);
+            pb[u] = __shfl_sync(kFull, c_bits, (j + u) & 31);
+            cl[u] = __shfl_sync(kFull, c_cell, (j + u) & 31);
+            if (j + u < m) rem |= 1u << u;
+          }
+          while (rem != 0) {
+            const int c = __shfl_sync(kFull, c_cell, (j + __ffs(rem) - 1) & 31);
+            if (c != cur_cell) {
+              if (cur_cell >= 0) {
+                // ---- flush the finished column: one bulk copy per pass
+                if (buf) touched1 = touched; else touched0 = touched;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                  const uint32_t src = col_s + (uint32_t)buf * col_bytes;
+#pragma unroll
+                  for (int p = 0; p < DHD_MAX_PASSES; ++p) {
+                    if (p < P.npass) {
+                      const uint32_t bytes = (uint32_t)P.pass_q[p] * 16u;
+                      char* dst = reinterpret_cast<char*>(P.pass_ptr[p]) + (size_t)cur_cell * bytes;
+                      if (HINT) bulk_store_hint(dst, src + (uint32_t)P.zoff[p] * 256u, bytes, pol);
+                      else bulk_store(dst, src + (uint32_t)P.zoff[p] * 256u, bytes);
+                    }
+                  }
+                  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                buf ^= 1;
+                pos = cur_cell + 1;
+              }
+              zero_run(pos, c);
+              pos = c;
+              // ---- claim the other column buffer: its last copy must have read it; re-zero what that cell touched
+              col2 = reinterpret_cast<float2*>(col_g + (size_t)buf * col_bytes);
+              if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+              __syncwarp();
+              uint32_t t = buf ? touched1 : touched0;
+              while (t != 0) {
+                const int z = __ffs(t) - 1;
+                t &= t - 1;
+                col2[z * 32 + lane] = make_float2(0.f, 0.f);
+              }
+              touched = 0;
+              cur_cell = c;
+            }
+            uint32_t run = 0, uni = 0;
+#pragma unroll
+            for (int u = 0; u < kG; ++u) {
+              if (cl[u] == c && ((rem >> u) & 1u)) {
+                run |= 1u << u;
+                uni |= pb[u];
+              }
+            }
+            rem &= ~run;
+            touched |= uni;
+            while (uni != 0) {
+              const int z = __ffs(uni) - 1;
+              uni &= uni - 1;
+              float2 a = col2[z * 32 + lane];
+#pragma unroll
+              for (int u = 0; u < kG; ++u) {
+                if (((run >> u) & 1u) && ((pb[u] >> z) & 1u)) {
+                  a.x = fmaf(f[u].x, d[u], a.x);
+                  a.y = fmaf(f[u].y, d[u], a.y);
+                }
+              }
+              col2[z * 32 + lane] = a;
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < kG; ++u) f[u] = fn[u];
+        }
+        BtoC();
+        AtoB();
+        loadA(e_lo + base + 96 + lane);
+      }
+      // ---- last column of the chunk
+      if (cur_cell >= 0) {
+        if (buf) touched1 = touched; else touched0 = touched;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          const uint32_t src = col_s + (uint32_t)buf * col_bytes;
+#pragma unroll
+          for (int p = 0; p < DHD_MAX_PASSES; ++p) {
+            if (p < P.npass) {
+              const uint32_t bytes = (uint32_t)P.pass_q[p] * 16u;
+              char* dst = reinterpret_cast<char*>(P.pass_ptr[p]) + (size_t)cur_cell * bytes;
+              if (HINT) bulk_store_hint(dst, src + (uint32_t)P.zoff[p] * 256u, bytes, pol);
+              else bulk_store(dst, src + (uint32_t)P.zoff[p] * 256u, bytes);
+            }
+          }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        buf ^= 1;
+        pos = cur_cell + 1;
+      }
+    }
+    zero_run(pos, cell_hi);
+  }
+  if (lane == 0) {
+    // the last warp to run dry re-arms the scheduler for the next launch on this workspace
+    if (atomicAdd(P.sched + 1, 1) == warps - 1) {
+      P.sched[0] = 0;
+      P.sched[1] = 0;
+    }
+  }
+  // shared memory must outlive every bulk copy that reads it
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // NCHW family: a CTA owns 32 consecutive cells of one sample and PZ output planes; each warp
@@ -672,6 +1244,14 @@ static int tuning(const char* name, int dflt) {
   return v != nullptr && *v != 0 ? atoi(v) : dflt;
 }
 
+// number of equal-cost work chunks (same value in prepare and in the pool launch)
+static int pool_nch(int ncell) {
+  int n = tuning("DHD_POOL_NCH", 16384);
+  if (n > kMaxChunks) n = kMaxChunks;
+  if (n > ncell) n = ncell;
+  return n < 1 ? 1 : n;
+}
+
 static int fill_pool_params(const dhd_mghs_cfg* cfg, const WsLayout& w, const void* workspace,
                             PoolParams* P) {
   const char* ws = (const char*)workspace;
@@ -680,6 +1260,9 @@ static int fill_pool_params(const dhd_mghs_cfg* cfg, const WsLayout& w, const vo
   P->cell_count = (const int*)(ws + w.cell_count);
   P->blk_prefix = (const int*)(ws + w.blk_prefix);
   P->total_entries = (const int*)(ws + w.total_entries);
+  P->sched = (int*)(ws + w.total_entries + 64);
+  P->chunks = (const int2*)(ws + w.chunks);
+  P->nch = pool_nch(w.ncell);
   P->ncell = w.ncell;
   P->npass = cfg->n_pass;
   P->DyDx = cfg->Dy * cfg->Dx;
@@ -690,6 +1273,7 @@ static int fill_pool_params(const dhd_mghs_cfg* cfg, const WsLayout& w, const vo
     if (p < cfg->n_pass) off += cfg->dz[p];
   }
   P->nplanes = off;
+  P->probe = tuning("DHD_POOL_PROBE", 0);
   return DHD_OK;
 }
 
@@ -726,6 +1310,8 @@ extern "C" int dhd_mghs_prepare(const dhd_mghs_cfg* cfg, const float* coor, cons
   char* ws = (char*)workspace;
   cudaError_t e = cudaMemsetAsync(ws + w.cell_count, 0, (size_t)w.ncell_pad * 4, st);
   if (e != cudaSuccess) return fail((int)e, "%s: %ld", "memset(cell_count)", (long)e);
+  e = cudaMemsetAsync(ws + w.total_entries, 0, 256, st);      // total + the pool's scheduler counters
+  if (e != cudaSuccess) return fail((int)e, "%s: %ld", "memset(sched)", (long)e);
 
   GeomParams G;
   G.cfg = *cfg;
@@ -763,6 +1349,13 @@ extern "C" int dhd_mghs_prepare(const dhd_mghs_cfg* cfg, const float* coor, cons
                                                   (const int*)(ws + w.cell_count),
                                                   (const int*)(ws + w.blk_prefix), w.ncell);
     DHD_CUDA_LAUNCH_CHECK("mghs_canonical");
+  }
+  {
+    const int nch = pool_nch(w.ncell);
+    mghs_chunks_kernel<<<(w.ncell + 1 + 255) / 256, 256, 0, st>>>(
+        (const int*)(ws + w.cell_start), (const int*)(ws + w.blk_prefix), (const int*)(ws + w.total_entries),
+        w.ncell, nch, max(1, tuning("DHD_POOL_CELLCOST", 8)), (int2*)(ws + w.chunks));
+    DHD_CUDA_LAUNCH_CHECK("mghs_chunks");
   }
   return DHD_OK;
 }
@@ -829,7 +1422,55 @@ extern "C" int dhd_mghs_pool_fwd(const dhd_mghs_cfg* cfg, const float* depth, co
     P.pass_q[p] = p < cfg->n_pass ? cfg->dz[p] * kC / 4 : 0;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  if (layout == DHD_LAYOUT_NHWC && tuning("DHD_POOL_V", 2) == 2) {
+  if (layout == DHD_LAYOUT_NHWC && tuning("DHD_POOL_V", 4) == 4) {
+    for (int p = 0; p < cfg->n_pass; ++p)
+      DHD_REQUIRE(((uintptr_t)out_host[p] & 15) == 0, "NHWC outputs must be 16-byte aligned");
+    const int threads = tuning("DHD_POOL_THREADS", 128);
+    DHD_REQUIRE(threads == 32 || threads == 64 || threads == 128, "stream pool: 32, 64 or 128 threads per block");
+    const int zero_bytes = tuning("DHD_POOL_ZT", 4096) / 256 * 256;
+    const int hint = tuning("DHD_POOL_HINT", 1);
+    const int cap = tuning("DHD_POOL_PERSM", 16);
+    const int windows = max(1, tuning("DHD_POOL_WINDOWS", 1));
+    const int wpb = threads / 32;
+    const size_t smem = (size_t)zero_bytes + (size_t)wpb * 2 * P.nplanes * 256;
+    DHD_REQUIRE(smem <= 227 * 1024, "pool column buffers do not fit in shared memory");
+    const int minb = tuning("DHD_POOL_MINB", 4) >= 5 ? 5 : 4;
+    void (*kern)(const PoolParams, int, int) =
+        hint ? (minb == 5 ? mghs_pool_stream_kernel<true, 5> : mghs_pool_stream_kernel<true, 4>)
+             : (minb == 5 ? mghs_pool_stream_kernel<false, 5> : mghs_pool_stream_kernel<false, 4>);
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem);
+    const int per_sm = max(1, min(cap, occ));
+    const int grid = min((P.nch + wpb - 1) / wpb, sm_count() * per_sm);
+    kern<<<grid, threads, smem, st>>>(P, zero_bytes, windows);
+    DHD_CUDA_LAUNCH_CHECK("mghs_pool_stream");
+  } else if (layout == DHD_LAYOUT_NHWC && tuning("DHD_POOL_V", 4) == 3) {
+    for (int p = 0; p < cfg->n_pass; ++p)
+      DHD_REQUIRE(((uintptr_t)out_host[p] & 15) == 0, "NHWC outputs must be 16-byte aligned");
+    const int threads = tuning("DHD_POOL_THREADS", 256);
+    const int zero_bytes = tuning("DHD_POOL_ZT", 4096) / 256 * 256;
+    const int cell_cost = tuning("DHD_POOL_CELLCOST", 2);
+    const int hint = tuning("DHD_POOL_HINT", 0);
+    const int cap = tuning("DHD_POOL_PERSM", 8);
+    const int chunk_cells = tuning("DHD_POOL_CHUNK", 8);
+    const int windows = max(1, tuning("DHD_POOL_WINDOWS", 8));
+    const int wpb = threads / 32;
+    const size_t smem = (size_t)zero_bytes + (size_t)wpb * 2 * P.nplanes * 256;
+    DHD_REQUIRE(smem <= 227 * 1024, "pool column buffers do not fit in shared memory");
+    static size_t smem_set[2] = {0, 0};
+    if (smem > smem_set[hint != 0]) {
+      if (hint) cudaFuncSetAttribute(mghs_pool_nhwc_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      else cudaFuncSetAttribute(mghs_pool_nhwc_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      smem_set[hint != 0] = smem;
+    }
+    const int per_sm = max(1, min(min(cap, 2048 / threads), (int)((227 * 1024) / (smem + 1024))));
+    const int need = (w.ncell + wpb - 1) / wpb;
+    const int grid = min(need, sm_count() * per_sm);
+    if (hint) mghs_pool_nhwc_tma_kernel<true><<<grid, threads, smem, st>>>(P, cell_cost, zero_bytes, chunk_cells, windows);
+    else mghs_pool_nhwc_tma_kernel<false><<<grid, threads, smem, st>>>(P, cell_cost, zero_bytes, chunk_cells, windows);
+    DHD_CUDA_LAUNCH_CHECK("mghs_pool_nhwc_tma");
+  } else if (layout == DHD_LAYOUT_NHWC && tuning("DHD_POOL_V", 4) == 2) {
     for (int p = 0; p < cfg->n_pass; ++p)
       DHD_REQUIRE(((uintptr_t)out_host[p] & 15) == 0, "NHWC outputs must be 16-byte aligned");
     const size_t smem = (size_t)8 * P.nplanes * kC * sizeof(float);

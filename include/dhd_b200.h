@@ -197,6 +197,10 @@ int dhd_pack_nchw_to_nhwc(const float* in, int N, int C, int H, int W, void* out
                           int out_coff, int part_stride, int parts, void* stream);
 /* class map of predictor.get_occ (occ_head.py:141-153): out[v] = argmax_k logits[v][k] (uint8) */
 int dhd_occ_argmax(const float* logits, long nvox, int ncls, uint8_t* out, void* stream);
+/* write-bandwidth probe (measurement only): zero-fills `bytes` at dst with mode 0 = grid-stride
+ * st.global.cs.v4, 1 = grid-stride st.global.v4, 2 = one contiguous run per warp (st.cs),
+ * 3 = cp.async.bulk from a shared-memory zero tile, one run per CTA, 4 = same, one run per warp */
+int dhd_probe_write_bw(void* dst, size_t bytes, int mode, int chunk_bytes, int blocks_per_sm, void* stream);
 /* number of kernels this library has enqueued since it was loaded (bench bookkeeping) */
 long dhd_launch_count(void);
 /* fp32 rows [rows][C] (NHWC) -> split-bf16 rows */
