@@ -343,3 +343,36 @@ def test_reference_cuda_kernel_agrees(cuda_lib):
     torch.cuda.synchronize()
     ours = bev_pool_v2(d5, f5, rd, rf, rb, shape, st, ln)
     assert torch.equal(ours, out_ref.permute(0, 4, 1, 2, 3).contiguous())   # same order -> bitwise
+
+
+def test_fused_matches_reference_cuda_path_full_size(cuda_lib):
+    """DHD-S at BASELINE's full size (B=4, 6 cameras, 200x200x{1,4,4,8}): the fused pool against the
+    reference's own CUDA path (oracle/ref_cuda_path.py: the reference op sequence in torch CUDA ops +
+    its unmodified kernel from oracle/_ref) -- voxel indices from identical coordinates, so the
+    four outputs must agree to summation-order tolerance everywhere."""
+    from oracle import ref_cuda_path as R
+    if not R.available():
+        pytest.skip('oracle/_ref not built')
+    from dhd_b200.pool import MghsPool, height_to_mask
+    cfg, B = O.DHD_S, 4
+    inputs, depth, feat, height = O.synthetic_inputs(cfg, B, seed=11, flip_bda=True)
+    inputs = tuple(t.cuda() for t in inputs)
+    depth, feat, height = depth.cuda(), feat.cuda(), height.cuda()
+    N, D = cfg['ncams'], depth.shape[1]
+    fH, fW = depth.shape[-2:]
+    C = cfg['C']
+    fr = O.frustum(cfg['depth'], cfg['input_size'], cfg['downsample']).cuda()
+    want = R.view_transform_cuda(inputs, depth, feat, height, fr, cfg['height_range'], cfg['mask_range'],
+                                 cfg['mask_grids'])
+    grids = [cfg['bev_grid']] + list(cfg['mask_grids'])
+    plan = MghsPool(B, N, D, fH, fW, C, grids[0]['x'], grids[0]['y'], [(g['z'], m) for m, g in enumerate(grids)])
+    coor = O.ego_coor(fr, inputs[1], inputs[3], inputs[4], inputs[5], inputs[6])
+    plan.prepare(coor=coor)
+    pm = height_to_mask(height, cfg['height_range'], cfg['mask_range'])
+    f_nhwc = feat.view(B, N, C, fH, fW).permute(0, 1, 3, 4, 2).contiguous()
+    outs = plan(depth, f_nhwc, pm, layout='nhwc')
+    for o, w in zip(outs, want):
+        got = o.permute(0, 3, 1, 2)
+        assert got.shape == w.shape
+        assert torch.allclose(got, w, rtol=1e-5, atol=2e-6)
+        assert int((got != 0).sum()) == int((w != 0).sum())       # identical support (bit-exact voxel indices)
