@@ -20,17 +20,18 @@ namespace dhd {
 
 constexpr int kM2 = 128;          // pixels per tile (TMEM lanes)
 constexpr int kK2 = 64;           // bf16 per smem row (128 B swizzle span)
-constexpr int kThreads2 = 192;
+constexpr int kEpiWarps = 8;         // two groups of four: group g owns the odd/even 32-column chunks
+constexpr int kThreads2 = (kEpiWarps + 2) * 32;
 constexpr uint32_t kA2Bytes = kM2 * kK2 * 2;
 constexpr uint32_t kStageBufBytes = 16384;   // one TMA-store staging tile: 128 rows x 128 B
 
 template <int NT>
 struct Cfg2 {
-  static constexpr int kStages = NT == 256 ? 3 : 5;
+  static constexpr int kStages = NT == 256 ? 3 : 4;
   static constexpr uint32_t kBBytes = NT * kK2 * 2;
   static constexpr uint32_t kStageBytes = kA2Bytes + kBBytes;
   static constexpr uint32_t kVecBytes = 3 * NT * 4;            // scale, bias(+img_bias), gate
-  static constexpr uint32_t kSmem = kStages * kStageBytes + 2 * kStageBufBytes + kVecBytes + 256 + 1024;
+  static constexpr uint32_t kSmem = kStages * kStageBytes + 4 * kStageBufBytes + kVecBytes + 256 + 1024;
   static constexpr int kTmemCols = 2 * NT;
 };
 
@@ -68,8 +69,8 @@ conv_igemm2_kernel(const __grid_constant__ Conv2Maps M, const __grid_constant__ 
   const dhd_conv_desc& d = P.d;
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
-  const uint32_t stagebuf = base + C::kStages * C::kStageBytes;            // 2 x 16 KB, 1024-aligned
-  const uint32_t vec_base = stagebuf + 2 * kStageBufBytes;
+  const uint32_t stagebuf = base + C::kStages * C::kStageBytes;            // 2 groups x 2 x 16 KB, 1024-aligned
+  const uint32_t vec_base = stagebuf + 4 * kStageBufBytes;
   const uint32_t bar_base = vec_base + C::kVecBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (C::kStages + s); };
@@ -85,7 +86,7 @@ conv_igemm2_kernel(const __grid_constant__ Conv2Maps M, const __grid_constant__ 
   const int kchunks = d.Cin / kK2;
   constexpr uint32_t kIdesc = umma_instr_desc_bf16(kM2, NT);
 
-  if (warp == 4 && lane == 0) {
+  if (warp == kEpiWarps && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&M.a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&M.b) : "memory");
     for (int s = 0; s < C::kStages; ++s) {
@@ -94,11 +95,11 @@ conv_igemm2_kernel(const __grid_constant__ Conv2Maps M, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 1);
+      mbar_init(tempty_bar(s), 2);          // one arrival per epilogue group
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 5) {
+  if (warp == kEpiWarps + 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "n"(C::kTmemCols)
                  : "memory");
@@ -121,7 +122,7 @@ conv_igemm2_kernel(const __grid_constant__ Conv2Maps M, const __grid_constant__ 
     n0 = nt * NT;
   };
 
-  if (warp == 4) {
+  if (warp == kEpiWarps) {
     // ===================================================== TMA producer
     if (lane == 0) {
       int it = 0;
@@ -145,7 +146,7 @@ conv_igemm2_kernel(const __grid_constant__ Conv2Maps M, const __grid_constant__ 
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == kEpiWarps + 1) {
     // ===================================================== MMA issuer
     if (lane == 0) {
       int it = 0, lt = 0;
@@ -183,16 +184,23 @@ conv_igemm2_kernel(const __grid_constant__ Conv2Maps M, const __grid_constant__ 
     // Kept deliberately COMPACT (32-column chunks in a rolled loop, one activation switch per
     // chunk): the first version unrolled 64 columns x every activation and its 220 KB of SASS
     // made the four epilogue warps stall on instruction fetch (ncu: stall_no_inst 34 %).
-    const int tid = threadIdx.x;            // 0..127
+    // Two groups of four warps: warp w reads TMEM lanes 32*(w%4).. (the hardware's lane window of a
+    // warp), group g = w/4 takes the 32-column chunks with (chunk & 1) == g.  1x1 layers are bound
+    // by this epilogue (4 k-steps per 256 columns), so the second group doubles their throughput;
+    // each group has its own pair of staging tiles and its own named barrier.
+    const int grp = warp >> 2;              // 0 / 1
+    const int tid = threadIdx.x & 127;      // 0..127 inside the group
+    const int gbar = 1 + grp;               // named barrier of this group
+    const uint32_t gstage = stagebuf + (uint32_t)grp * 2u * kStageBufBytes;
     const int row = tid;
     int lt = 0;
-    uint32_t nstore = 0;                    // TMA stores issued so far (selects the staging buffer)
+    uint32_t nstore = 0;                    // TMA stores issued so far by this group (selects the staging buffer)
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++lt) {
       int img, x0, y0, n0;
       decode(tile, img, x0, y0, n0);
       const int as = lt & 1;
-      named_bar_sync(1, 128);               // everyone is done with the previous tile's vectors
-      for (int c = tid; c < NT; c += 128) {
+      named_bar_sync(3, 256);               // everyone is done with the previous tile's vectors
+      for (int c = threadIdx.x; c < NT; c += 256) {
         const int ch = n0 + c;
         float sc = 1.f, bi = 0.f, ga = 1.f;
         if (ch < d.Cout) {
@@ -205,12 +213,12 @@ conv_igemm2_kernel(const __grid_constant__ Conv2Maps M, const __grid_constant__ 
         s_bias[c] = bi;
         s_gate[c] = ga;
       }
-      named_bar_sync(1, 128);
+      named_bar_sync(3, 256);
       mbar_wait(tfull_bar(as), (lt >> 1) & 1);
       tc_fence_after();
       const int px = x0 + row % d.bw, py = y0 + row / d.bw;
       const bool valid = px < d.W && py < d.H;
-      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(as * NT);
+      const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(as * NT);
       const float* res = nullptr;
       if (d.residual != nullptr && valid)
         res = d.residual + (size_t)img * d.res_sN + (size_t)py * d.res_sY + (size_t)px * d.res_sX + n0;
@@ -262,6 +270,7 @@ conv_igemm2_kernel(const __grid_constant__ Conv2Maps M, const __grid_constant__ 
         if (pass == 2) inv = 1.f / sum;
 #pragma unroll 1
         for (int cb = cb_lo; cb < cb_hi; ++cb) {
+          if ((npass == 1 || pass == 2) && (cb & 1) != grp) continue;     // row statistics need every chunk
           float v[32];
           affine(cb, v, act == DHD_ACT_SOFTMAX ? -INFINITY : 0.f);
           if (npass == 3 && pass == 0) {
@@ -281,7 +290,7 @@ conv_igemm2_kernel(const __grid_constant__ Conv2Maps M, const __grid_constant__ 
               break;
             case DHD_ACT_SIGMOID:
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = __frcp_rn(1.f + __expf(-v[j]));
+              for (int j = 0; j < 32; ++j) v[j] = __fdividef(1.f, 1.f + __expf(-v[j]));
               break;
             case DHD_ACT_SOFTPLUS:   // torch Softplus(beta=1, threshold=20)
 #pragma unroll
@@ -305,15 +314,15 @@ conv_igemm2_kernel(const __grid_constant__ Conv2Maps M, const __grid_constant__ 
           // ---------------- fp32 output
           if (sg.out_f32 != nullptr) {
             if (tma32) {
-              const uint32_t buf = stagebuf + (nstore & 1u) * kStageBufBytes;
+              const uint32_t buf = gstage + (nstore & 1u) * kStageBufBytes;
               if (tid == 0) tma_store_wait_read<1>();      // the store that last used this buffer has read it
-              named_bar_sync(1, 128);
+              named_bar_sync(gbar, 128);
               float4* dst = reinterpret_cast<float4*>(gen + (buf - base) + row * 128);
 #pragma unroll
               for (int j = 0; j < 8; ++j)
                 dst[j ^ (row & 7)] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
               fence_proxy_async_smem();
-              named_bar_sync(1, 128);
+              named_bar_sync(gbar, 128);
               if (tid == 0) {
                 tma_store_4d(&M.o32[sgi], buf, cfirst - sg.c_lo, x0, y0, img);
                 tma_store_commit();
@@ -342,14 +351,14 @@ conv_igemm2_kernel(const __grid_constant__ Conv2Maps M, const __grid_constant__ 
               }
               if (tma16) {
                 // 32 channels = 64-byte rows, SWIZZLE_64B: 16-byte chunk j of row r sits at j ^ ((r >> 1) & 3)
-                const uint32_t buf = stagebuf + (nstore & 1u) * kStageBufBytes;
+                const uint32_t buf = gstage + (nstore & 1u) * kStageBufBytes;
                 if (tid == 0) tma_store_wait_read<1>();
-                named_bar_sync(1, 128);
+                named_bar_sync(gbar, 128);
                 uint4* dst = reinterpret_cast<uint4*>(gen + (buf - base) + row * 64);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) dst[j ^ ((row >> 1) & 3)] = q[j];
                 fence_proxy_async_smem();
-                named_bar_sync(1, 128);
+                named_bar_sync(gbar, 128);
                 if (tid == 0) {
                   tma_store_4d(&M.o16[sgi][p], buf, cfirst - sg.c_lo, x0, y0, img);
                   tma_store_commit();
@@ -373,7 +382,7 @@ conv_igemm2_kernel(const __grid_constant__ Conv2Maps M, const __grid_constant__ 
       }
       // accumulator drained: hand it back to the MMA warp
       tc_fence_before();
-      named_bar_sync(1, 128);
+      named_bar_sync(gbar, 128);
       if (tid == 0) {
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty_bar(as)) : "memory");
       }
@@ -381,7 +390,7 @@ conv_igemm2_kernel(const __grid_constant__ Conv2Maps M, const __grid_constant__ 
     if (tid == 0) tma_store_wait<0>();      // all bulk stores complete before the CTA exits
   }
   __syncthreads();
-  if (warp == 5) {
+  if (warp == kEpiWarps + 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::kTmemCols)
                  : "memory");
