@@ -223,10 +223,60 @@ class HotPathStep:
             self._back()
 
     def run_e2e(self, host):
-        """Host buffers in, host buffer out: H2D of the step inputs, the step, D2H of the class map."""
+        """Host buffers in, host buffer out: H2D of the step inputs, the step, D2H of the class map
+        (all on the compute stream, nothing overlapped)."""
         self.upload(host)
         self.run()
         self.host_occ.copy_(self.occ, non_blocking=True)
+
+    # ---- streamed end-to-end: the copies of neighbouring steps overlap the compute of this one ----
+    def e2e_open(self, host):
+        """Start a stream of steps: queue the H2D copy of the first step's inputs."""
+        if not hasattr(self, '_h2d'):
+            self._h2d, self._d2h = torch.cuda.Stream(), torch.cuda.Stream()
+            self._stage = [{k: torch.empty_like(v) for k, v in self.static.items()} for _ in range(2)]
+            self._h2d_done = [torch.cuda.Event(), torch.cuda.Event()]
+            self._stage_free = [torch.cuda.Event(), torch.cuda.Event()]
+            self._d2h_done, self._step_done = torch.cuda.Event(), torch.cuda.Event()
+        main = torch.cuda.current_stream()
+        self._i = 0
+        for e in self._stage_free:
+            e.record(main)
+        self._d2h_done.record(main)
+        self._queue_h2d(host, 0)
+
+    def _queue_h2d(self, host, slot):
+        self._h2d.wait_event(self._stage_free[slot])
+        with torch.cuda.stream(self._h2d):
+            for k, v in host.items():
+                self._stage[slot][k].copy_(v, non_blocking=True)
+            self._h2d_done[slot].record(self._h2d)
+
+    def run_e2e_streamed(self, host, next_host=None):
+        """One step of the stream: inputs arrive from pinned host memory (copied on a side stream
+        while the previous step computed), the class map leaves to pinned host memory on another;
+        `next_host` = the following step's inputs (None for the last step).  Every step still
+        moves h2d_bytes in and d2h_bytes out."""
+        main = torch.cuda.current_stream()
+        slot = self._i & 1
+        main.wait_event(self._h2d_done[slot])
+        for k, v in self._stage[slot].items():          # device-to-device into the graph's input buffers
+            self.static[k].copy_(v, non_blocking=True)
+        self._stage_free[slot].record(main)
+        if next_host is not None:
+            self._queue_h2d(next_host, slot ^ 1)
+        main.wait_event(self._d2h_done)                 # the previous class map has left `occ`
+        self.run()
+        self._step_done.record(main)
+        self._d2h.wait_event(self._step_done)
+        with torch.cuda.stream(self._d2h):
+            self.host_occ.copy_(self.occ, non_blocking=True)
+            self._d2h_done.record(self._d2h)
+        self._i += 1
+
+    def e2e_close(self):
+        """Join the side streams into the compute stream (before the caller's closing event)."""
+        torch.cuda.current_stream().wait_event(self._d2h_done)
 
     def run_pool_bwd(self):
         st = torch.cuda.current_stream()
