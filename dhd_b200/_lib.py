@@ -49,6 +49,8 @@ _SIGNATURES = {
                                          ctypes.POINTER(_P), ctypes.c_int, _P, _P, _P]),
     'dhd_mghs_voxel_index': (ctypes.c_int, [ctypes.POINTER(MghsCfg), _P, _P, _P]),
     'dhd_conv2d_fwd': (ctypes.c_int, [_P, _P]),
+    'dhd_conv2d_wgrad_workspace_bytes': (ctypes.c_size_t, [_P]),
+    'dhd_conv2d_wgrad': (ctypes.c_int, [_P, _P]),
     'dhd_pack_nchw_to_nhwc': (ctypes.c_int, [_P] + [_I] * 4 + [_P] + [_I] * 4 + [_P]),
     'dhd_occ_argmax': (ctypes.c_int, [_P, ctypes.c_long, _I, _P, _P]),
     'dhd_launch_count': (ctypes.c_long, []),

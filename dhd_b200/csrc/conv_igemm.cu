@@ -309,6 +309,7 @@ static EncodeTiledFn encode_fn() {
 }
 
 int conv2_launch(const dhd_conv_desc* d, void* encode, void* stream);   // conv_igemm2.cu
+void* conv_encode_fn() { return (void*)encode_fn(); }                  // used by conv_wgrad.cu
 
 static int conv_version() {
   const char* v = getenv("DHD_CONV_V");

@@ -245,3 +245,71 @@ def nchw_strides(C, H, W):
 
 def nhwc_strides(C, H, W):
     return (H * W * C, W * C, C, 1)
+
+
+# ------------------------------------------------------------------------------ backward
+class WgradDesc(ctypes.Structure):
+    """struct dhd_wgrad_desc (include/dhd_b200.h)."""
+    _fields_ = [
+        ('N', ctypes.c_int32), ('H', ctypes.c_int32), ('W', ctypes.c_int32),
+        ('Cin', ctypes.c_int32), ('Cout', ctypes.c_int32), ('taps', ctypes.c_int32),
+        ('tap_dy', ctypes.c_int32 * MAX_TAPS), ('tap_dx', ctypes.c_int32 * MAX_TAPS),
+        ('bw', ctypes.c_int32), ('bh', ctypes.c_int32),
+        ('x', ctypes.c_void_p), ('x_ld', ctypes.c_int32), ('x_coff', ctypes.c_int32),
+        ('dy', ctypes.c_void_p), ('dy_ld', ctypes.c_int32), ('dy_coff', ctypes.c_int32),
+        ('scale', ctypes.c_void_p), ('dw', ctypes.c_void_p), ('partial', ctypes.c_void_p),
+        ('accumulate', ctypes.c_int32),
+    ]
+
+
+_WGRAD_WS = {}
+
+
+def conv2d_wgrad(x, dy, Cout, ksize=1, dilation=1, scale=None, out=None, accumulate=False):
+    """Weight gradient of a stride-1 'same' convolution: x, dy are Acts (part 0 is used: bf16
+    operands, fp32 accumulation).  Returns dw fp32 (Cout, ksize*ksize, Cin) -- the tap-major layout
+    of pack_weight(); `weight_grad_to_torch` turns it into (Cout, Cin, kh, kw)."""
+    if (x.N, x.H, x.W) != (dy.N, dy.H, dy.W) or dy.C < Cout:
+        raise ValueError('x / dy shapes do not match')
+    d = WgradDesc()
+    d.N, d.H, d.W, d.Cin, d.Cout = x.N, x.H, x.W, x.C, Cout
+    taps = ksize * ksize
+    d.taps = taps
+    r = ksize // 2
+    for t in range(taps):
+        d.tap_dy[t] = (t // ksize - r) * dilation
+        d.tap_dx[t] = (t % ksize - r) * dilation
+    d.bw, d.bh = tile_box(x.H, x.W)
+    d.x, d.x_ld, d.x_coff = x.data.data_ptr(), x.ld, x.coff
+    d.dy, d.dy_ld, d.dy_coff = dy.data.data_ptr(), dy.ld, dy.coff
+    if scale is not None:
+        d.scale = scale.data_ptr()
+    if out is None:
+        out = torch.empty(Cout, taps, x.C, device=x.data.device)
+        accumulate = False
+    d.dw = out.data_ptr()
+    d.accumulate = int(accumulate)
+    lib = _lib.load()
+    need = lib.dhd_conv2d_wgrad_workspace_bytes(ctypes.byref(d))
+    key = (x.data.device, torch.cuda.current_stream().cuda_stream)
+    ws = _WGRAD_WS.get(key)
+    if ws is None or ws.numel() < need:         # one scratch buffer per (device, stream), grown on demand
+        ws = torch.empty(max(need, 1 << 20), dtype=torch.uint8, device=x.data.device)
+        _WGRAD_WS[key] = ws
+    d.partial = ws.data_ptr()
+    _lib.check(lib.dhd_conv2d_wgrad(ctypes.byref(d), _stream()), 'conv2d_wgrad')
+    return out
+
+
+def weight_grad_to_torch(dw, ksize):
+    """(Cout, taps, Cin) -> (Cout, Cin, kh, kw), the shape of nn.Conv2d.weight.grad."""
+    Cout, taps, Cin = dw.shape
+    return dw.view(Cout, ksize, ksize, Cin).permute(0, 3, 1, 2).contiguous()
+
+
+def pack_weight_dgrad(w, parts=1):
+    """Forward weight (Cout, Cin, kh, kw) -> the packed weight of the data-gradient convolution:
+    dx = conv(dy, w'), w'[ci][tap'][co] = w[co][tap][ci] with the taps mirrored."""
+    if w.dim() == 2:
+        w = w[:, :, None, None]
+    return pack_weight(w.detach().transpose(0, 1).flip(2, 3), parts)

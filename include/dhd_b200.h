@@ -189,6 +189,34 @@ typedef struct dhd_conv_desc {
 
 int dhd_conv2d_fwd(const dhd_conv_desc* desc, void* stream);
 
+/* ---- backward of the dense layers ------------------------------------------------------
+ * (torch autograd of nn.Conv2d / nn.Linear in the modules listed above; the reference trains them
+ * through cuDNN's backward-data / backward-filter.)
+ * Data gradient: dx = conv(dy, w') with w'[ci][flipped tap][co] = w[co][tap][ci] -- the same
+ * dhd_conv2d_fwd kernel on a weight tensor repacked once per step by the host.
+ * Weight gradient: dw[co][tap][ci] = scale[co] * sum_pixels dy[p][co] * x[p + tap][ci], bf16
+ * operands, fp32 accumulation in TMEM.  `partial` is a caller-owned workspace of
+ * dhd_conv2d_wgrad_workspace_bytes() bytes; dw is fp32 [Cout][taps][Cin] (the layout of the packed
+ * forward weight), written completely, or added to when accumulate != 0. */
+typedef struct dhd_wgrad_desc {
+  int32_t N, H, W;
+  int32_t Cin, Cout;           /* Cin % 64 == 0 */
+  int32_t taps;
+  int32_t tap_dy[DHD_CONV_MAX_TAPS], tap_dx[DHD_CONV_MAX_TAPS];
+  int32_t bw, bh;              /* pixel box, bw*bh == 128 */
+  const void* x;               /* layer input, bf16 NHWC: channel c at x_coff + c of x_ld */
+  int32_t x_ld, x_coff;
+  const void* dy;              /* gradient w.r.t. the convolution output, bf16 NHWC */
+  int32_t dy_ld, dy_coff;
+  const float* scale;          /* [Cout] or NULL (folded BatchNorm scale of the forward epilogue) */
+  float* dw;
+  float* partial;
+  int32_t accumulate;
+} dhd_wgrad_desc;
+
+size_t dhd_conv2d_wgrad_workspace_bytes(const dhd_wgrad_desc* desc);
+int dhd_conv2d_wgrad(const dhd_wgrad_desc* desc, void* stream);
+
 /* ---- streaming layout / elementwise helpers of the dense path (csrc/layout.cu) -----------
  * "split-bf16 NHWC": bf16, `ld` channels per pixel, logical channel c of part p at
  * coff + p*part_stride + c; the fp32 value is the sum of the parts. */
