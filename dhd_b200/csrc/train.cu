@@ -1,0 +1,257 @@
+// Streaming kernels of the training path of the dense hot-path layers (everything between the
+// tensor-core GEMMs of the backward pass): activation derivatives with the per-channel bias /
+// BatchNorm reductions fused, the class-weighted masked cross-entropy of the occupancy head
+// (reference: models/dense_heads/occ_head.py:102-139 with mmdet's CrossEntropyLoss,
+// models/losses/cross_entropy_loss.py:11-62), and the softmax backward of MGHS.depth_net
+// (models/necks/lss_heightmap.py:482-489).  All HBM-bound: every tensor is read once and
+// written once, 16 bytes per thread.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace dhd {
+
+constexpr int kMaxSumBlocks = 1024;
+
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&v)[8]) {
+  const uint4 q = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    v[2 * j] = __low2float(h[j]);
+    v[2 * j + 1] = __high2float(h[j]);
+  }
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&v)[8]) {
+  uint4 q;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&q);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+  *reinterpret_cast<uint4*>(p) = q;
+}
+
+// dz = dy * act'(y) on bf16 NHWC rows; per-block partial column sums of dz and dz*y.
+// act: 0 none, 1 relu (y > 0), 2 sigmoid (y (1 - y)), 3 softplus (1 - exp(-y)).
+// gate (optional, [N][C], rows_per_img rows per image): dz *= gate (a per-image channel gate that was
+// applied AFTER the activation in the forward epilogue, e.g. the SE gate).
+__global__ void __launch_bounds__(256)
+act_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int dy_ld, int dy_coff, const __nv_bfloat16* __restrict__ y,
+               int y_ld, int y_coff, long rows, int C, int act, __nv_bfloat16* __restrict__ out, int out_ld,
+               int out_coff, float* __restrict__ partial, long rows_per_block) {
+  __shared__ float red[256][17];
+  const int cg = C / 8, rpb = 256 / cg;
+  const int gi = threadIdx.x % cg, ri = threadIdx.x / cg;
+  const long r0 = (long)blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  float s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+  if (ri < rpb) {
+    for (long r = r0 + ri; r < r1; r += rpb) {
+      float g[8], v[8];
+      load8(dy + r * dy_ld + dy_coff + gi * 8, g);
+      if (act != 0 || partial != nullptr) load8(y + r * y_ld + y_coff + gi * 8, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float d = 1.f;
+        if (act == 1) d = v[j] > 0.f ? 1.f : 0.f;
+        else if (act == 2) d = v[j] * (1.f - v[j]);
+        else if (act == 3) d = 1.f - __expf(-v[j]);
+        g[j] *= d;
+        s1[j] += g[j];
+        s2[j] += g[j] * v[j];
+      }
+      if (out != nullptr) store8(out + r * out_ld + out_coff + gi * 8, g);
+    }
+  }
+  if (partial == nullptr) return;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    red[threadIdx.x][j] = s1[j];
+    red[threadIdx.x][8 + j] = s2[j];
+  }
+  __syncthreads();
+  if (ri == 0) {
+    for (int k = 1; k < rpb; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s1[j] += red[threadIdx.x + k * cg][j];
+        s2[j] += red[threadIdx.x + k * cg][8 + j];
+      }
+    float* p = partial + (size_t)blockIdx.x * 2 * C;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      p[gi * 8 + j] = s1[j];
+      p[C + gi * 8 + j] = s2[j];
+    }
+  }
+}
+
+// sums[i] = sum over blocks (ascending) of partial[b][i]
+__global__ void __launch_bounds__(256)
+colsum_reduce_kernel(const float* __restrict__ partial, int nblocks, int n, float* __restrict__ sums) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float a = 0.f;
+  for (int b = 0; b < nblocks; ++b) a += partial[(size_t)b * n + i];
+  sums[i] = a;
+}
+
+// ---- occupancy cross-entropy ---------------------------------------------------------------
+// norm[0] = sum over voxels of mask * class_weight[label]   (the reference's num_total_samples)
+__global__ void __launch_bounds__(256)
+ce_norm_kernel(const uint8_t* __restrict__ labels, const uint8_t* __restrict__ mask, const float* __restrict__ cw,
+               int ncls, int ignore, long nvox, float* __restrict__ norm) {
+  float a = 0.f;
+  for (long v = (long)blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += (long)gridDim.x * blockDim.x) {
+    const int l = labels[v];
+    if (l == ignore || l >= ncls) continue;
+    if (mask != nullptr && mask[v] == 0) continue;
+    a += cw != nullptr ? cw[l] : 1.f;
+  }
+  a = warp_sum(a);
+  __shared__ float ws[8];
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = a;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += ws[i];
+    atomicAdd(norm, t);
+  }
+}
+
+// logits (B, Dx, Dy, Dz, ncls) fp32 (the predictor's output layout); labels / mask (B, Dx, Dy, Dz);
+// dlogits bf16 NHWC rows [(b*Dy + y)*Dx + x][ld], channel z*ncls + k (the layout the last Linear's
+// backward GEMMs read); loss[0] += sum of weighted voxel losses * loss_weight / norm.
+__global__ void __launch_bounds__(256)
+ce_loss_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ labels, const uint8_t* __restrict__ mask,
+               const float* __restrict__ cw, int ncls, int ignore, int B, int Dx, int Dy, int Dz, float loss_weight,
+               const float* __restrict__ norm, float* __restrict__ loss, __nv_bfloat16* __restrict__ dlogits, int ld) {
+  const long nvox = (long)B * Dx * Dy * Dz;
+  const float inv = loss_weight / (norm[0] + 1.1920929e-07f);
+  float acc = 0.f;
+  for (long v = (long)blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += (long)gridDim.x * blockDim.x) {
+    const int z = (int)(v % Dz);
+    long t = v / Dz;
+    const int y = (int)(t % Dy);
+    t /= Dy;
+    const int x = (int)(t % Dx);
+    const int b = (int)(t / Dx);
+    const float* lg = logits + v * ncls;
+    const int l = labels[v];
+    float w = 0.f;
+    if (l != ignore && l < ncls && (mask == nullptr || mask[v] != 0)) w = cw != nullptr ? cw[l] : 1.f;
+    __nv_bfloat16* g = dlogits + (((size_t)b * Dy + y) * Dx + x) * ld + z * ncls;
+    if (w == 0.f) {
+      for (int k = 0; k < ncls; ++k) g[k] = __float2bfloat16(0.f);
+      continue;
+    }
+    float mx = -INFINITY;
+    for (int k = 0; k < ncls; ++k) mx = fmaxf(mx, lg[k]);
+    float s = 0.f;
+    for (int k = 0; k < ncls; ++k) s += __expf(lg[k] - mx);
+    const float lse = mx + __logf(s);
+    acc += w * (lse - lg[l]);
+    const float wi = w * inv, is = 1.f / s;
+    for (int k = 0; k < ncls; ++k) {
+      const float p = __expf(lg[k] - mx) * is;
+      g[k] = __float2bfloat16(wi * (p - (k == l ? 1.f : 0.f)));
+    }
+  }
+  acc = warp_sum(acc);
+  __shared__ float ws[8];
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += ws[i];
+    atomicAdd(loss, t * inv);
+  }
+}
+
+// ---- MGHS.depth_net backward head ---------------------------------------------------------
+// depth = softmax(logits) over D (NCHW, (BN, D, HW)); g = dL/d depth from the pool backward;
+// feat_grad (BN*HW, C) = dL/d context.  Writes the gradient w.r.t. the 1x1 convolution's output as
+// one bf16 NHWC row per pixel: [0, D) = depth * (g - <g, depth>), [D, D + C) = feat_grad, rest 0.
+__global__ void __launch_bounds__(128)
+depth_head_bwd_kernel(const float* __restrict__ depth, const float* __restrict__ g, const float* __restrict__ fg,
+                      int BN, int D, int HW, int C, __nv_bfloat16* __restrict__ out, int ld) {
+  const long pix = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= (long)BN * HW) return;
+  const int bn = (int)(pix / HW), hw = (int)(pix % HW);
+  const float* dp = depth + (size_t)bn * D * HW + hw;
+  const float* gp = g + (size_t)bn * D * HW + hw;
+  float dot = 0.f;
+  for (int d = 0; d < D; ++d) dot += dp[(size_t)d * HW] * gp[(size_t)d * HW];
+  __nv_bfloat16* o = out + (size_t)pix * ld;
+  for (int d = 0; d < D; ++d) o[d] = __float2bfloat16(dp[(size_t)d * HW] * (gp[(size_t)d * HW] - dot));
+  const float* f = fg + (size_t)pix * C;
+  for (int c = 0; c < C; ++c) o[D + c] = __float2bfloat16(f[c]);
+  for (int c = D + C; c < ld; ++c) o[c] = __float2bfloat16(0.f);
+}
+
+}  // namespace dhd
+
+using namespace dhd;
+
+static inline bool ok8(int C, int ld, int coff, const void* p) {
+  return C % 8 == 0 && ld % 8 == 0 && coff % 8 == 0 && ((uintptr_t)p & 15) == 0;
+}
+
+extern "C" size_t dhd_act_bwd_workspace_bytes(int C) { return (size_t)kMaxSumBlocks * 2 * C * sizeof(float); }
+
+extern "C" int dhd_act_bwd(const void* dy, int dy_ld, int dy_coff, const void* y, int y_ld, int y_coff, long rows,
+                           int C, int act, void* out, int out_ld, int out_coff, float* colsum, float* workspace,
+                           void* stream) {
+  DHD_REQUIRE(dy != nullptr && rows > 0 && C > 0, "bad arguments");
+  DHD_REQUIRE(act >= 0 && act <= 3, "act must be none / relu / sigmoid / softplus");
+  DHD_REQUIRE(act == 0 || y != nullptr, "the activation derivative needs the saved output");
+  DHD_REQUIRE(out != nullptr || colsum != nullptr, "nothing to compute");
+  DHD_REQUIRE(colsum == nullptr || (workspace != nullptr && y != nullptr), "column sums need the workspace and y");
+  DHD_REQUIRE(C <= 2048 && ok8(C, dy_ld, dy_coff, dy), "dy: C % 8, 16-byte aligned rows");
+  if (y != nullptr) DHD_REQUIRE(ok8(C, y_ld, y_coff, y), "y: 16-byte aligned rows");
+  if (out != nullptr) DHD_REQUIRE(ok8(C, out_ld, out_coff, out), "out: 16-byte aligned rows");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int rpb = 256 / (C / 8);
+  long rows_per_block = (rows + kMaxSumBlocks - 1) / kMaxSumBlocks;
+  if (rows_per_block < 4L * rpb) rows_per_block = 4L * rpb;
+  const int nblocks = (int)((rows + rows_per_block - 1) / rows_per_block);
+  act_bwd_kernel<<<nblocks, 256, 0, st>>>((const __nv_bfloat16*)dy, dy_ld, dy_coff, (const __nv_bfloat16*)y, y_ld,
+                                          y_coff, rows, C, act, (__nv_bfloat16*)out, out_ld, out_coff,
+                                          colsum != nullptr ? workspace : nullptr, rows_per_block);
+  DHD_CUDA_LAUNCH_CHECK("act_bwd");
+  if (colsum != nullptr) {
+    colsum_reduce_kernel<<<(2 * C + 255) / 256, 256, 0, st>>>(workspace, nblocks, 2 * C, colsum);
+    DHD_CUDA_LAUNCH_CHECK("colsum_reduce");
+  }
+  return DHD_OK;
+}
+
+extern "C" int dhd_occ_ce_loss(const float* logits, const uint8_t* labels, const uint8_t* mask,
+                               const float* class_weight, int ncls, int ignore_index, int B, int Dx, int Dy, int Dz,
+                               float loss_weight, float* loss_and_norm, void* dlogits, int dl_ld, void* stream) {
+  DHD_REQUIRE(logits && labels && loss_and_norm && dlogits, "null pointer");
+  DHD_REQUIRE(B > 0 && Dx > 0 && Dy > 0 && Dz > 0 && ncls > 0 && ncls <= 64, "bad shape");
+  DHD_REQUIRE(dl_ld >= Dz * ncls, "dlogits rows are too short");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(loss_and_norm, 0, 2 * sizeof(float), st);
+  if (e != cudaSuccess) return fail((int)e, "%s: %ld", "memset(loss)", (long)e);
+  const long nvox = (long)B * Dx * Dy * Dz;
+  const int blocks = (int)min((nvox + 255) / 256, (long)sm_count() * 16);
+  ce_norm_kernel<<<blocks, 256, 0, st>>>(labels, mask, class_weight, ncls, ignore_index, nvox, loss_and_norm + 1);
+  DHD_CUDA_LAUNCH_CHECK("ce_norm");
+  ce_loss_kernel<<<blocks, 256, 0, st>>>(logits, labels, mask, class_weight, ncls, ignore_index, B, Dx, Dy, Dz,
+                                         loss_weight, loss_and_norm + 1, loss_and_norm, (__nv_bfloat16*)dlogits, dl_ld);
+  DHD_CUDA_LAUNCH_CHECK("ce_loss");
+  return DHD_OK;
+}
+
+extern "C" int dhd_depth_head_bwd(const float* depth, const float* depth_grad, const float* feat_grad, int BN, int D,
+                                  int HW, int C, void* out, int out_ld, void* stream) {
+  DHD_REQUIRE(depth && depth_grad && feat_grad && out, "null pointer");
+  DHD_REQUIRE(BN > 0 && D > 0 && HW > 0 && C > 0 && out_ld >= D + C, "bad shape");
+  const long npix = (long)BN * HW;
+  depth_head_bwd_kernel<<<(int)((npix + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      depth, depth_grad, feat_grad, BN, D, HW, C, (__nv_bfloat16*)out, out_ld);
+  DHD_CUDA_LAUNCH_CHECK("depth_head_bwd");
+  return DHD_OK;
+}

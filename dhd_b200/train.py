@@ -1,0 +1,226 @@
+"""Training path of the dense hot-path layers: forward with saved activations, backward through
+the C-ABI kernels (tcgen05 data / weight gradient GEMMs + the streaming kernels of csrc/train.cu),
+gradients accumulated into the `.grad` of the torch parameters that own the weights -- so the
+optimizer and the data-parallel gradient all-reduce (dhd_b200/shard.py) see ordinary parameters.
+
+What the reference does here is torch autograd over cuDNN / cuBLAS (tools/train.py -> mmdet3d
+train_model); the layers are the ones listed in dhd_b200/modules.py.  Arithmetic: bf16 operands,
+fp32 accumulation (mixed-precision training), fp32 master weights and fp32 weight gradients.
+BatchNorm layers run with frozen statistics and frozen affine parameters in this build
+(FrozenBN fine-tuning): batch-statistics BatchNorm is the next step.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from . import dense as D
+from .modules import _p, _stream, fold_bn
+
+ACT_ID = {None: 0, 'none': 0, 'relu': 1, 'sigmoid': 2, 'softplus': 3}
+_WS = {}
+
+
+def _workspace(dev, nbytes):
+    key = (dev, torch.cuda.current_stream().cuda_stream, 'act')
+    ws = _WS.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        _WS[key] = ws
+    return ws
+
+
+def act_bwd(dy, y, act, out=None, want_sums=False):
+    """dz = dy * act'(y) (Acts, part 0).  out=None -> in place on dy.  Returns (dz Act, sums) with
+    sums (2, C) fp32 = [sum_rows dz, sum_rows dz*y] when want_sums."""
+    lib = _lib.load()
+    C = dy.C
+    out = dy if out is None else out
+    sums = ws = None
+    if want_sums:
+        sums = torch.empty(2, C, device=dy.data.device)
+        ws = _workspace(dy.data.device, lib.dhd_act_bwd_workspace_bytes(C))
+    yy = y if y is not None else dy
+    _lib.check(lib.dhd_act_bwd(_p(dy.data), dy.ld, dy.coff, _p(yy.data), yy.ld, yy.coff, dy.N * dy.H * dy.W, C,
+                               ACT_ID[act], _p(out.data), out.ld, out.coff, _p(sums), _p(ws), _stream()), 'act_bwd')
+    return out, sums
+
+
+def _acc(param, g):
+    """param.grad += g (fp32), allocating on first use."""
+    g = g.reshape(param.shape).to(param.dtype)
+    if param.grad is None:
+        param.grad = g.clone()
+    else:
+        param.grad.add_(g)
+
+
+class _TrainConv:
+    """One convolution of a trainable module: fp32 master weight lives in the torch parameter;
+    `refresh()` re-packs the bf16 forward and data-gradient weights after an optimizer step."""
+
+    def __init__(self, weight, bias, bn, ksize, dilation=1, cin_pad=None, cout_pad=None):
+        self.weight, self.bias_p, self.bn = weight, bias, bn
+        self.ksize, self.dilation = ksize, dilation
+        self.Cout, self.Cin = weight.shape[0], weight.shape[1]
+        self.cin_pad = cin_pad or self.Cin          # forward input channels (zero padded to % 64)
+        self.cout_pad = cout_pad or self.Cout       # backward input channels (dy padded to % 64)
+        self.refresh()
+
+    def refresh(self):
+        w = self.weight.detach().float()
+        if w.dim() == 2:
+            w = w[:, :, None, None]
+        dev = w.device
+        if self.bn is not None:
+            s, b = fold_bn(self.bn, self.bias_p)
+            self.scale, self.bias = s.to(dev), b.to(dev)
+        else:
+            self.scale = None
+            self.bias = self.bias_p.detach().float().contiguous() if self.bias_p is not None else None
+        wf = w
+        if self.cin_pad != self.Cin:
+            wf = torch.nn.functional.pad(w, (0, 0, 0, 0, 0, self.cin_pad - self.Cin))
+        self.w_fwd = D.pack_weight(wf, 1)
+        wb = w if self.scale is None else w * self.scale.view(-1, 1, 1, 1)     # d(scale*conv)/dx
+        if self.cout_pad != self.Cout:
+            wb = torch.nn.functional.pad(wb, (0, 0, 0, 0, 0, 0, 0, self.cout_pad - self.Cout))
+        self.w_bwd = D.pack_weight_dgrad(wb, 1)
+
+    def forward(self, x, segs, **kw):
+        return D.conv2d(x, self.w_fwd, self.Cout, ksize=self.ksize, dilation=self.dilation, precision='bf16',
+                        scale=self.scale, bias=self.bias, segs=segs, **kw)
+
+    def backward(self, x, dy, dx_segs=None, bias_sums=None):
+        """dy: Act = gradient w.r.t. this layer's pre-activation output (channels >= Cout zero).
+        Accumulates weight / bias gradients; writes dx through `dx_segs` (conv2d segs) if given."""
+        dw = D.conv2d_wgrad(x, dy, self.Cout, ksize=self.ksize, dilation=self.dilation, scale=self.scale)
+        if x.C != self.Cin:
+            dw = dw[:, :, :self.Cin]
+        g = D.weight_grad_to_torch(dw.contiguous(), self.ksize)
+        _acc(self.weight, g if self.weight.dim() == 4 else g[:, :, 0, 0])
+        if self.bias_p is not None and self.bn is None and bias_sums is not None:
+            _acc(self.bias_p, bias_sums[:self.Cout])
+        if dx_segs is not None:
+            D.conv2d(dy, self.w_bwd, self.cin_pad, ksize=self.ksize, dilation=self.dilation, precision='bf16',
+                     segs=dx_segs)
+
+
+class PredictorTrainer:
+    """predictor (occ_head.py:52-67, 84-131): forward, class-weighted masked cross-entropy, backward."""
+
+    def __init__(self, head, device='cuda'):
+        if not head.use_predicter:
+            raise NotImplementedError('use_predicter=False head')
+        self.head, self.device = head, device
+        self.Dz, self.ncls = head.Dz, head.num_classes
+        self.conv = _TrainConv(head.final_conv.conv.weight, head.final_conv.conv.bias, None, 3)
+        self.relu = getattr(head.final_conv, 'with_activation', True)
+        nout = self.Dz * self.ncls
+        self.nout, self.nout_pad = nout, (nout + 63) // 64 * 64
+        self.fc0 = _TrainConv(head.predicter[0].weight, head.predicter[0].bias, None, 1)
+        self.fc2 = _TrainConv(head.predicter[2].weight, head.predicter[2].bias, None, 1, cout_pad=self.nout_pad)
+        cw = getattr(head, 'cls_weights', None) if head.class_balance else None
+        self.class_weight = cw.float().to(device).contiguous() if cw is not None else None
+        self.loss_weight = float(getattr(head.loss_occ, 'loss_weight', 1.0)) * float(head.weight_ce) \
+            if head.loss_occ is not None else float(head.weight_ce)
+        self.ignore_index = int(getattr(head.loss_occ, 'ignore_index', 255) or 255) if head.loss_occ is not None else 255
+        self._buf = {}
+
+    def refresh(self):
+        for c in (self.conv, self.fc0, self.fc2):
+            c.refresh()
+
+    def _act(self, name, N, H, W, C, zero=False):
+        key = (name, N, H, W, C)
+        a = self._buf.get(key)
+        if a is None:
+            a = D.Act.empty(N, H, W, C, 1, self.device)
+            if zero:
+                a.data.zero_()
+            self._buf[key] = a
+        return a
+
+    def forward(self, x):
+        """x: Act (B, C, Dy, Dx) -> occ_pred (B, Dx, Dy, Dz, n_cls) fp32; activations saved."""
+        N, H, W = x.N, x.H, x.W
+        t = self._act('t', N, H, W, self.conv.Cout)
+        self.conv.forward(x, [dict(act='relu' if self.relu else None, out_act=t)])
+        u = self._act('u', N, H, W, self.fc0.Cout)
+        self.fc0.forward(t, [dict(act='softplus', out_act=u)])
+        Co = self.nout
+        out = torch.empty(N, W, H, Co, device=self.device)
+        self.fc2.forward(u, [dict(out_f32=(out, (W * H * Co, Co, H * Co, 1)))])
+        self.saved = (x, t, u, out)
+        return out.view(N, W, H, self.Dz, self.ncls)
+
+    def loss(self, voxel_semantics, mask_camera=None):
+        """Cross-entropy term of predictor.loss on the logits of the last forward.  Returns a 2-element
+        device tensor [loss, avg_factor]; the gradient w.r.t. the logits is kept for backward()."""
+        x, t, u, out = self.saved
+        N, H, W = x.N, x.H, x.W
+        labels = voxel_semantics.to(torch.uint8).contiguous()
+        mask = mask_camera.to(torch.uint8).contiguous() if mask_camera is not None else None
+        dlog = self._act('dlog', N, H, W, self.nout_pad, zero=True)
+        res = torch.empty(2, device=self.device)
+        _lib.check(_lib.load().dhd_occ_ce_loss(_p(out), _p(labels), _p(mask), _p(self.class_weight), self.ncls,
+                                               self.ignore_index, N, W, H, self.Dz, self.loss_weight, _p(res),
+                                               _p(dlog.data), dlog.ld, _stream()), 'occ_ce_loss')
+        self.dlog = dlog
+        return res
+
+    def backward(self, want_dx=True):
+        """Backward of loss() through the head.  Returns dL/dx as an Act (bf16) or None."""
+        x, t, u, out = self.saved
+        N, H, W = x.N, x.H, x.W
+        dlog = self.dlog
+        _, sums = act_bwd(dlog, None, None, want_sums=True)                   # bias gradient of predicter[2]
+        du = self._act('du', N, H, W, self.fc0.Cout)
+        self.fc2.backward(u, dlog, [dict(out_act=du)], bias_sums=sums[0])
+        _, sums = act_bwd(du, u, 'softplus', want_sums=True)
+        dt = self._act('dt', N, H, W, self.conv.Cout)
+        self.fc0.backward(t, du, [dict(out_act=dt)], bias_sums=sums[0])
+        _, sums = act_bwd(dt, t, 'relu' if self.relu else None, want_sums=True)
+        dx = self._act('dx', N, H, W, x.C) if want_dx else None
+        self.conv.backward(x, dt, [dict(out_act=dx)] if want_dx else None, bias_sums=sums[0])
+        return dx
+
+
+class DepthHeadTrainer:
+    """MGHS.depth_net (lss_heightmap.py:62, 482-489): 1x1 conv -> softmax(depth) | context, and its
+    backward from the pool's depth / context gradients."""
+
+    def __init__(self, conv, n_depth, device='cuda'):
+        self.D = n_depth
+        self.C = conv.weight.shape[0] - n_depth
+        self.device = device
+        self.cout_pad = (conv.weight.shape[0] + 63) // 64 * 64
+        self.conv = _TrainConv(conv.weight, conv.bias, None, 1, cout_pad=self.cout_pad)
+        self._dy = None
+
+    def refresh(self):
+        self.conv.refresh()
+
+    def forward(self, x):
+        N, H, W = x.N, x.H, x.W
+        depth = torch.empty(N, self.D, H, W, device=self.device)
+        feat = torch.empty(N, H, W, self.C, device=self.device)
+        self.conv.forward(x, [dict(c_lo=0, c_hi=self.D, act='softmax', out_f32=(depth, D.nchw_strides(self.D, H, W))),
+                              dict(c_lo=self.D, c_hi=self.D + self.C, out_f32=(feat, D.nhwc_strides(self.C, H, W)))])
+        self.saved = (x, depth)
+        return depth, feat
+
+    def backward(self, depth_grad, feat_grad, want_dx=True):
+        """depth_grad (BN, D, fH, fW), feat_grad (.., fH, fW, C) fp32 from dhd_mghs_pool_bwd."""
+        x, depth = self.saved
+        N, H, W = x.N, x.H, x.W
+        if self._dy is None or (self._dy.N, self._dy.H, self._dy.W) != (N, H, W):
+            self._dy = D.Act.empty(N, H, W, self.cout_pad, 1, self.device)
+        dy = self._dy
+        _lib.check(_lib.load().dhd_depth_head_bwd(_p(depth), _p(depth_grad.contiguous()), _p(feat_grad.contiguous()),
+                                                  N, self.D, H * W, self.C, _p(dy.data), dy.ld, _stream()),
+                   'depth_head_bwd')
+        _, sums = act_bwd(dy, None, None, want_sums=True)
+        dx = D.Act.empty(N, H, W, x.C, 1, self.device) if want_dx else None
+        self.conv.backward(x, dy, [dict(out_act=dx)] if want_dx else None, bias_sums=sums[0])
+        return dx

@@ -217,6 +217,29 @@ typedef struct dhd_wgrad_desc {
 size_t dhd_conv2d_wgrad_workspace_bytes(const dhd_wgrad_desc* desc);
 int dhd_conv2d_wgrad(const dhd_wgrad_desc* desc, void* stream);
 
+/* ---- streaming kernels of the training path (csrc/train.cu) ----------------------------------
+ * dz = dy * act'(y) on bf16 NHWC rows (y = the layer's saved OUTPUT: relu y>0, sigmoid y(1-y),
+ * softplus 1-exp(-y)); out may alias dy or be NULL.  colsum (2*C floats, or NULL): [0,C) = sum_rows dz
+ * (bias / BatchNorm beta gradient), [C,2C) = sum_rows dz*y (BatchNorm gamma gradient after the
+ * affine fix-up); needs workspace of dhd_act_bwd_workspace_bytes(C); sums are deterministic. */
+size_t dhd_act_bwd_workspace_bytes(int C);
+int dhd_act_bwd(const void* dy, int dy_ld, int dy_coff, const void* y, int y_ld, int y_coff, long rows,
+                int C, int act, void* out, int out_ld, int out_coff, float* colsum, float* workspace,
+                void* stream);
+/* predictor.loss, cross-entropy term (occ_head.py:102-131; mmdet CrossEntropyLoss with class_weight,
+ * weight = mask_camera, avg_factor = sum mask*class_weight[label]): logits (B,Dx,Dy,Dz,ncls) fp32,
+ * labels / mask (B,Dx,Dy,Dz) uint8 (mask or class_weight may be NULL).  loss_and_norm[0] = loss,
+ * [1] = avg_factor; dlogits = d loss / d logits as bf16 NHWC rows [(b*Dy+y)*Dx+x][dl_ld], channel
+ * z*ncls+k -- the input layout of the last Linear's backward GEMMs. */
+int dhd_occ_ce_loss(const float* logits, const uint8_t* labels, const uint8_t* mask,
+                    const float* class_weight, int ncls, int ignore_index, int B, int Dx, int Dy, int Dz,
+                    float loss_weight, float* loss_and_norm, void* dlogits, int dl_ld, void* stream);
+/* backward of MGHS.depth_net's output head (lss_heightmap.py:482-489): depth = softmax over D (NCHW),
+ * depth_grad / feat_grad from dhd_mghs_pool_bwd -> gradient w.r.t. the 1x1 convolution output, one bf16
+ * NHWC row per pixel: [0,D) softmax backward, [D,D+C) feat_grad, [D+C,out_ld) zeros. */
+int dhd_depth_head_bwd(const float* depth, const float* depth_grad, const float* feat_grad, int BN, int D,
+                       int HW, int C, void* out, int out_ld, void* stream);
+
 /* ---- streaming layout / elementwise helpers of the dense path (csrc/layout.cu) -----------
  * "split-bf16 NHWC": bf16, `ld` channels per pixel, logical channel c of part p at
  * coff + p*part_stride + c; the fp32 value is the sum of the parts. */
