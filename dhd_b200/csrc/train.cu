@@ -189,6 +189,118 @@ depth_head_bwd_kernel(const float* __restrict__ depth, const float* __restrict__
   for (int c = D + C; c < ld; ++c) o[c] = __float2bfloat16(0.f);
 }
 
+
+// ---- SFA gates backward (mix.py:37-59) -----------------------------------------------------
+// forward:  u = a1*bev + (1-a1)*vox ;  fuse = a2*a1*bev + (1-a2)*(1-a1)*vox
+//           (a1 [N][C] per-image channel gate, a2 [pix][C] spatial gate, x = [bev | vox] bf16 NHWC)
+// mode 0 (fuse):  g = d fuse
+//    dpre2        = g * (a1*bev - (1-a1)*vox) * a2*(1-a2)          (bf16, gradient at the sigmoid input)
+//    dx[bev]      = g * a2*a1          dx[vox] = g * (1-a2)*(1-a1)  (fp32, written)
+//    s[n][c]     += g * (a2*bev - (1-a2)*vox)                       (d a1, per-image partial sums)
+// mode 1 (u):     g = d u
+//    dx[bev]     += g * a1             dx[vox] += g * (1-a1)        (fp32, accumulated)
+//    s[n][c]     += g * (bev - vox)
+// Blocks cover `pb` pixels of one image; their partial sums go to partial[(n*gridDim.x + bx)][C].
+__global__ void __launch_bounds__(256)
+sfa_gate_bwd_kernel(int mode, const __nv_bfloat16* __restrict__ g, int g_ld, int g_coff, const __nv_bfloat16* __restrict__ x,
+                    int x_ld, int x_coff, int C, int HW, int pb, const float* __restrict__ a1,
+                    const float* __restrict__ a2, __nv_bfloat16* __restrict__ dpre2, int d_ld, int d_coff,
+                    float* __restrict__ dx, float* __restrict__ partial) {
+  __shared__ float red[256][9];
+  const int cg = C / 8, rows = 256 / cg;
+  const int gi = threadIdx.x % cg, ri = threadIdx.x / cg;
+  const int n = blockIdx.y, p0 = blockIdx.x * pb, p1 = min(HW, p0 + pb);
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (ri < rows) {
+    const float4* g1p = reinterpret_cast<const float4*>(a1 + (size_t)n * C + gi * 8);
+    const float4 ga = __ldg(g1p), gb = __ldg(g1p + 1);
+    const float g1[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+    for (int p = p0 + ri; p < p1; p += rows) {
+      const size_t r = (size_t)n * HW + p;
+      float gv[8], bev[8], vox[8];
+      load8(g + r * g_ld + g_coff + gi * 8, gv);
+      load8(x + r * x_ld + x_coff + gi * 8, bev);
+      load8(x + r * x_ld + x_coff + C + gi * 8, vox);
+      float* db = dx + r * (size_t)(2 * C) + gi * 8;
+      float* dv = db + C;
+      float ob[8], ov[8];
+      if (mode == 0) {
+        const float4* g2p = reinterpret_cast<const float4*>(a2 + r * C + gi * 8);
+        const float4 qa = __ldg(g2p), qb = __ldg(g2p + 1);
+        const float g2[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+        float dp[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float b1 = g1[j] * bev[j], v1 = (1.f - g1[j]) * vox[j];
+          dp[j] = gv[j] * (b1 - v1) * g2[j] * (1.f - g2[j]);
+          ob[j] = gv[j] * g2[j] * g1[j];
+          ov[j] = gv[j] * (1.f - g2[j]) * (1.f - g1[j]);
+          acc[j] += gv[j] * (g2[j] * bev[j] - (1.f - g2[j]) * vox[j]);
+        }
+        store8(dpre2 + r * d_ld + d_coff + gi * 8, dp);
+      } else {
+        const float4 b0 = *reinterpret_cast<const float4*>(db), b1 = *reinterpret_cast<const float4*>(db + 4);
+        const float4 v0 = *reinterpret_cast<const float4*>(dv), v1 = *reinterpret_cast<const float4*>(dv + 4);
+        const float pbv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        const float pvv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          ob[j] = pbv[j] + gv[j] * g1[j];
+          ov[j] = pvv[j] + gv[j] * (1.f - g1[j]);
+          acc[j] += gv[j] * (bev[j] - vox[j]);
+        }
+      }
+      *reinterpret_cast<float4*>(db) = make_float4(ob[0], ob[1], ob[2], ob[3]);
+      *reinterpret_cast<float4*>(db + 4) = make_float4(ob[4], ob[5], ob[6], ob[7]);
+      *reinterpret_cast<float4*>(dv) = make_float4(ov[0], ov[1], ov[2], ov[3]);
+      *reinterpret_cast<float4*>(dv + 4) = make_float4(ov[4], ov[5], ov[6], ov[7]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[threadIdx.x][j] = acc[j];
+  __syncthreads();
+  if (ri == 0) {
+    for (int k = 1; k < rows; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += red[threadIdx.x + k * cg][j];
+    float* pp = partial + ((size_t)n * gridDim.x + blockIdx.x) * C + gi * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) pp[j] = acc[j];
+  }
+}
+
+// sums[n][c] (+)= sum over the image's blocks (ascending)
+__global__ void __launch_bounds__(256)
+image_sum_reduce_kernel(const float* __restrict__ partial, int nb, int N, int C, float* __restrict__ sums, int accumulate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * C) return;
+  const int n = i / C, c = i % C;
+  float a = 0.f;
+  for (int b = 0; b < nb; ++b) a += partial[((size_t)n * nb + b) * C + c];
+  sums[i] = accumulate ? sums[i] + a : a;
+}
+
+// out[pix][c] (bf16) = in[pix][c] (fp32) + v[n][c]
+__global__ void __launch_bounds__(256)
+add_rowvec_kernel(const float* __restrict__ in, const float* __restrict__ v, long npix, int HW, int C,
+                  __nv_bfloat16* __restrict__ out, int o_ld, int o_coff) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int cg = C / 8;
+  if (i >= npix * cg) return;
+  const long pix = i / cg;
+  const int c = (int)(i % cg) * 8;
+  const int n = (int)(pix / HW);
+  const float4 a = *reinterpret_cast<const float4*>(in + pix * C + c), b = *reinterpret_cast<const float4*>(in + pix * C + c + 4);
+  float r[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  if (v != nullptr) {
+    const float4 p = __ldg(reinterpret_cast<const float4*>(v + (size_t)n * C + c)), q = __ldg(reinterpret_cast<const float4*>(v + (size_t)n * C + c) + 1);
+    r[0] += p.x; r[1] += p.y; r[2] += p.z; r[3] += p.w; r[4] += q.x; r[5] += q.y; r[6] += q.z; r[7] += q.w;
+  }
+  store8(out + pix * o_ld + o_coff + c, r);
+}
+
 }  // namespace dhd
 
 using namespace dhd;
@@ -253,5 +365,48 @@ extern "C" int dhd_depth_head_bwd(const float* depth, const float* depth_grad, c
   depth_head_bwd_kernel<<<(int)((npix + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
       depth, depth_grad, feat_grad, BN, D, HW, C, (__nv_bfloat16*)out, out_ld);
   DHD_CUDA_LAUNCH_CHECK("depth_head_bwd");
+  return DHD_OK;
+}
+
+static int sfa_pb(int N, int HW) {
+  const int want = max(1, (sm_count() * 8) / max(1, N));
+  return max(16, (HW + want - 1) / want);
+}
+
+extern "C" size_t dhd_sfa_gate_bwd_workspace_bytes(int N, int HW, int C) {
+  const int pb = sfa_pb(N, HW);
+  return (size_t)N * ((HW + pb - 1) / pb) * C * sizeof(float);
+}
+
+extern "C" int dhd_sfa_gate_bwd(int mode, const void* g, int g_ld, int g_coff, const void* x, int x_ld, int x_coff,
+                                int C, int N, int HW, const float* a1, const float* a2, void* dpre2, int d_ld,
+                                int d_coff, float* dx, float* a1_sums, int accumulate_sums, float* workspace,
+                                void* stream) {
+  DHD_REQUIRE(g && x && a1 && dx && a1_sums && workspace, "null pointer");
+  DHD_REQUIRE(mode == 0 || mode == 1, "mode must be 0 (fuse) or 1 (u)");
+  DHD_REQUIRE(mode == 1 || (a2 != nullptr && dpre2 != nullptr), "mode 0 needs a2 and dpre2");
+  DHD_REQUIRE(N > 0 && HW > 0 && C > 0 && C <= 2048, "bad shape");
+  DHD_REQUIRE(ok8(C, g_ld, g_coff, g) && ok8(C, x_ld, x_coff, x) && ((uintptr_t)dx & 15) == 0 &&
+                  ((uintptr_t)a1 & 15) == 0, "needs C % 8 == 0 and 16-byte aligned rows");
+  if (mode == 0) DHD_REQUIRE(ok8(C, d_ld, d_coff, dpre2) && ((uintptr_t)a2 & 15) == 0, "dpre2 / a2 alignment");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int pb = sfa_pb(N, HW), nb = (HW + pb - 1) / pb;
+  sfa_gate_bwd_kernel<<<dim3(nb, N), 256, 0, st>>>(mode, (const __nv_bfloat16*)g, g_ld, g_coff, (const __nv_bfloat16*)x,
+                                                   x_ld, x_coff, C, HW, pb, a1, a2, (__nv_bfloat16*)dpre2, d_ld, d_coff,
+                                                   dx, workspace);
+  DHD_CUDA_LAUNCH_CHECK("sfa_gate_bwd");
+  image_sum_reduce_kernel<<<(N * C + 255) / 256, 256, 0, st>>>(workspace, nb, N, C, a1_sums, accumulate_sums);
+  DHD_CUDA_LAUNCH_CHECK("image_sum_reduce");
+  return DHD_OK;
+}
+
+extern "C" int dhd_add_rowvec(const float* in, const float* v, int N, int HW, int C, void* out, int out_ld,
+                              int out_coff, void* stream) {
+  DHD_REQUIRE(in && out, "null pointer");
+  DHD_REQUIRE(N > 0 && HW > 0 && ok8(C, out_ld, out_coff, out) && ((uintptr_t)in & 15) == 0, "bad shape / alignment");
+  const long total = (long)N * HW * (C / 8);
+  add_rowvec_kernel<<<(int)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(in, v, (long)N * HW, HW, C,
+                                                                                 (__nv_bfloat16*)out, out_ld, out_coff);
+  DHD_CUDA_LAUNCH_CHECK("add_rowvec");
   return DHD_OK;
 }

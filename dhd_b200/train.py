@@ -91,7 +91,7 @@ class _TrainConv:
         return D.conv2d(x, self.w_fwd, self.Cout, ksize=self.ksize, dilation=self.dilation, precision='bf16',
                         scale=self.scale, bias=self.bias, segs=segs, **kw)
 
-    def backward(self, x, dy, dx_segs=None, bias_sums=None):
+    def backward(self, x, dy, dx_segs=None, bias_sums=None, **kw):
         """dy: Act = gradient w.r.t. this layer's pre-activation output (channels >= Cout zero).
         Accumulates weight / bias gradients; writes dx through `dx_segs` (conv2d segs) if given."""
         dw = D.conv2d_wgrad(x, dy, self.Cout, ksize=self.ksize, dilation=self.dilation, scale=self.scale)
@@ -99,11 +99,11 @@ class _TrainConv:
             dw = dw[:, :, :self.Cin]
         g = D.weight_grad_to_torch(dw.contiguous(), self.ksize)
         _acc(self.weight, g if self.weight.dim() == 4 else g[:, :, 0, 0])
-        if self.bias_p is not None and self.bn is None and bias_sums is not None:
-            _acc(self.bias_p, bias_sums[:self.Cout])
+        if self.bias_p is not None and bias_sums is not None:      # a conv bias under a frozen BN sees the BN scale
+            _acc(self.bias_p, bias_sums[:self.Cout] if self.bn is None else bias_sums[:self.Cout] * self.scale)
         if dx_segs is not None:
             D.conv2d(dy, self.w_bwd, self.cin_pad, ksize=self.ksize, dilation=self.dilation, precision='bf16',
-                     segs=dx_segs)
+                     segs=dx_segs, **kw)
 
 
 class PredictorTrainer:
@@ -223,4 +223,118 @@ class DepthHeadTrainer:
         _, sums = act_bwd(dy, None, None, want_sums=True)
         dx = D.Act.empty(N, H, W, x.C, 1, self.device) if want_dx else None
         self.conv.backward(x, dy, [dict(out_act=dx)] if want_dx else None, bias_sums=sums[0])
+        return dx
+
+
+class SFATrainer:
+    """SFA (mix.py:8-90) with frozen BatchNorm: forward with saved activations and the backward of
+    every convolution, both gated blends and the squeeze MLP."""
+
+    def __init__(self, sfa, device='cuda'):
+        from .modules import linear_rows, mean_hw
+        self._linear, self._mean = linear_rows, mean_hw
+        self.sfa, self.device = sfa, device
+        st = sfa.mysk_7
+        self.C = st.channels
+        self.fc0, self.fc2 = st.fc[0], st.fc[2]
+        sl, mr, ms = st.spacial_leanring, sfa.mix_residual, sfa.mix_shortcut
+        self.sp1 = _TrainConv(sl[0].weight, sl[0].bias, sl[1], 1)
+        self.sp2 = _TrainConv(sl[3].weight, sl[3].bias, sl[4], 1)
+        self.res1 = _TrainConv(mr[0].weight, None, mr[1], 3)
+        self.res2 = _TrainConv(mr[3].weight, None, mr[4], 3)
+        self.short = _TrainConv(ms[0].weight, None, ms[1], 1)
+        self.Cout = self.res2.Cout
+        self._buf = {}
+
+    def refresh(self):
+        for c in (self.sp1, self.sp2, self.res1, self.res2, self.short):
+            c.refresh()
+
+    def _act(self, name, N, H, W, C):
+        key = (name, N, H, W, C)
+        if key not in self._buf:
+            self._buf[key] = D.Act.empty(N, H, W, C, 1, self.device)
+        return self._buf[key]
+
+    def _f32(self, name, *shape):
+        key = (name,) + shape
+        if key not in self._buf:
+            self._buf[key] = torch.empty(*shape, device=self.device)
+        return self._buf[key]
+
+    def _mix(self, x, a1, a2, out):
+        _lib.check(_lib.load().dhd_sfa_mix(_p(x.data), x.ld, x.coff, x.part_stride, x.parts, self.C, x.N, x.H * x.W,
+                                           _p(a1), _p(a2), _p(out.data), out.ld, out.coff, out.part_stride, out.parts,
+                                           _stream()), 'sfa_mix')
+
+    def forward(self, x):
+        """x: Act (B, 2C, Dy, Dx) = cat(bev feature, voxel feature) -> Act (B, Cout, Dy, Dx)."""
+        N, H, W, C = x.N, x.H, x.W, self.C
+        f = lambda t: t.detach().float().contiguous()
+        s = x.mean if getattr(x, 'mean', None) is not None else self._mean(x)
+        h = self._linear(s, f(self.fc0.weight), f(self.fc0.bias), 'relu')
+        a1 = self._linear(h, f(self.fc2.weight), f(self.fc2.bias), 'sigmoid')
+        u = self._act('u', N, H, W, C)
+        self._mix(x, a1, None, u)
+        t = self._act('t', N, H, W, C)
+        self.sp1.forward(u, [dict(act='relu', out_act=t)])
+        a2 = self._f32('a2', N, H, W, C)
+        self.sp2.forward(t, [dict(act='sigmoid', out_f32=(a2, D.nhwc_strides(C, H, W)))])
+        fuse = self._act('fuse', N, H, W, C)
+        self._mix(x, a1, a2, fuse)
+        sc = self._f32('sc', N, H, W, self.Cout)
+        self.short.forward(x, [dict(out_f32=(sc, D.nhwc_strides(self.Cout, H, W)))])
+        r = self._act('r', N, H, W, self.Cout)
+        self.res1.forward(fuse, [dict(act='relu', out_act=r)])
+        out = self._act('out', N, H, W, self.Cout)
+        self.res2.forward(r, [dict(act='relu', out_act=out)], residual=(sc, D.nhwc_strides(self.Cout, H, W)[:3]))
+        self.saved = (x, s, h, a1, u, t, a2, fuse, r, out)
+        return out
+
+    def backward(self, dout, want_dx=True):
+        """dout: Act = dL/d(SFA output) (modified in place).  Returns dL/dx as an Act (bf16)."""
+        x, s, h, a1, u, t, a2, fuse, r, out = self.saved
+        N, H, W, C = x.N, x.H, x.W, self.C
+        lib = _lib.load()
+        act_bwd(dout, out, 'relu')
+        dr = self._act('dr', N, H, W, self.Cout)
+        self.res2.backward(r, dout, [dict(out_act=dr)])
+        act_bwd(dr, r, 'relu')
+        dfuse = self._act('dfuse', N, H, W, C)
+        self.res1.backward(fuse, dr, [dict(out_act=dfuse)])
+        dxa = self._f32('dxa', N, H, W, 2 * C)
+        dxb = self._f32('dxb', N, H, W, 2 * C)
+        dpre2 = self._act('dpre2', N, H, W, C)
+        S = self._f32('S', N, C)
+        ws = _workspace(self.device, lib.dhd_sfa_gate_bwd_workspace_bytes(N, H * W, C))
+        _lib.check(lib.dhd_sfa_gate_bwd(0, _p(dfuse.data), dfuse.ld, dfuse.coff, _p(x.data), x.ld, x.coff, C, N, H * W,
+                                        _p(a1), _p(a2), _p(dpre2.data), dpre2.ld, dpre2.coff, _p(dxa), _p(S), 0,
+                                        _p(ws), _stream()), 'sfa_gate_bwd(fuse)')
+        # shortcut: weight gradient, and dxb = dxa + dgrad(dout) through the residual input of the epilogue
+        st2 = D.nhwc_strides(2 * C, H, W)
+        self.short.backward(x, dout, [dict(out_f32=(dxb, st2))], residual=(dxa, st2[:3]))
+        dt = self._act('dt', N, H, W, C)
+        _, sums = act_bwd(dpre2, None, None, want_sums=True)
+        self.sp2.backward(t, dpre2, [dict(out_act=dt)], bias_sums=sums[0])
+        _, sums = act_bwd(dt, t, 'relu', want_sums=True)
+        du = self._act('du', N, H, W, C)
+        self.sp1.backward(u, dt, [dict(out_act=du)], bias_sums=sums[0])
+        _lib.check(lib.dhd_sfa_gate_bwd(1, _p(du.data), du.ld, du.coff, _p(x.data), x.ld, x.coff, C, N, H * W,
+                                        _p(a1), None, None, 0, 0, _p(dxb), _p(S), 1, _p(ws), _stream()),
+                   'sfa_gate_bwd(u)')
+        # squeeze MLP (B rows): CUDA-core products through dhd_linear_rows
+        lin = self._linear
+        dz2 = (S * a1 * (1.0 - a1)).contiguous()
+        _acc(self.fc2.weight, lin(dz2.t().contiguous(), h.t().contiguous()))
+        _acc(self.fc2.bias, dz2.sum(0))
+        dh = lin(dz2, self.fc2.weight.detach().float().t().contiguous())
+        dz0 = (dh * (h > 0).float()).contiguous()
+        _acc(self.fc0.weight, lin(dz0.t().contiguous(), s.t().contiguous()))
+        _acc(self.fc0.bias, dz0.sum(0))
+        if not want_dx:
+            return None
+        ds = lin(dz0, self.fc0.weight.detach().float().t().contiguous()) * (1.0 / (H * W))
+        dx = self._act('dx', N, H, W, 2 * C)
+        _lib.check(lib.dhd_add_rowvec(_p(dxb), _p(ds.contiguous()), N, H * W, 2 * C, _p(dx.data), dx.ld, dx.coff,
+                                      _stream()), 'add_rowvec')
         return dx

@@ -240,6 +240,19 @@ int dhd_occ_ce_loss(const float* logits, const uint8_t* labels, const uint8_t* m
 int dhd_depth_head_bwd(const float* depth, const float* depth_grad, const float* feat_grad, int BN, int D,
                        int HW, int C, void* out, int out_ld, void* stream);
 
+/* backward of the SFA gates (mix.py:37-59; formulas at sfa_gate_bwd_kernel in csrc/train.cu).
+ * mode 0: g = d fuse -> dpre2 (bf16 NHWC, gradient at the spatial gate's sigmoid input), dx (fp32
+ * [pix][2C], written), a1_sums [N][C] (d a1 from this blend); mode 1: g = d u -> dx accumulated,
+ * a1_sums (accumulated when accumulate_sums != 0).  x = [bev | vox] bf16 NHWC (2C channels at x_coff). */
+size_t dhd_sfa_gate_bwd_workspace_bytes(int N, int HW, int C);
+int dhd_sfa_gate_bwd(int mode, const void* g, int g_ld, int g_coff, const void* x, int x_ld, int x_coff,
+                     int C, int N, int HW, const float* a1, const float* a2, void* dpre2, int d_ld,
+                     int d_coff, float* dx, float* a1_sums, int accumulate_sums, float* workspace,
+                     void* stream);
+/* out (bf16 NHWC) = in (fp32 [N*HW][C]) + v[n][c] (v may be NULL) */
+int dhd_add_rowvec(const float* in, const float* v, int N, int HW, int C, void* out, int out_ld,
+                   int out_coff, void* stream);
+
 /* ---- streaming layout / elementwise helpers of the dense path (csrc/layout.cu) -----------
  * "split-bf16 NHWC": bf16, `ld` channels per pixel, logical channel c of part p at
  * coff + p*part_stride + c; the fp32 value is the sum of the parts. */

@@ -95,3 +95,71 @@ def test_depth_head_backward(cuda_lib):
     assert rel(conv.weight.grad, want_w) < 2e-2
     assert rel(conv.bias.grad, want_b) < 2e-2
     assert rel(dx.float(), want_x) < 2e-2
+
+
+def _q(t):
+    """bf16 rounding with a straight-through gradient: the CUDA path stores these activations in bf16."""
+    return t + (t.bfloat16().float() - t).detach()
+
+
+def _sfa_forward_q(sd, x, q):
+    """oracle.dense_oracle.sfa_forward (mix.py:37-59, 87-90) with `q` applied where the CUDA path rounds an
+    activation to bf16 (u, t, fuse, r, out), so ReLU masks and saved values agree between the two sides and
+    the comparison measures the backward arithmetic."""
+    import torch.nn.functional as F
+    from oracle.dense_oracle import _bn
+    C = x.shape[1] // 2
+    bev, vox = x[:, :C], x[:, C:]
+    s = x.mean(-1).mean(-1)
+    a1 = torch.sigmoid(F.linear(F.relu(F.linear(s, sd['mysk_7.fc.0.weight'], sd['mysk_7.fc.0.bias'])),
+                                sd['mysk_7.fc.2.weight'], sd['mysk_7.fc.2.bias']))[..., None, None]
+    b1, v1 = a1 * bev, (1 - a1) * vox
+    k = 'mysk_7.spacial_leanring'
+    t = q(F.relu(_bn(sd, k + '.1', F.conv2d(q(b1 + v1), sd[k + '.0.weight'], sd[k + '.0.bias']))))
+    a2 = torch.sigmoid(_bn(sd, k + '.4', F.conv2d(t, sd[k + '.3.weight'], sd[k + '.3.bias'])))
+    fuse = q(a2 * b1 + (1 - a2) * v1)
+    r = q(F.relu(_bn(sd, 'mix_residual.1', F.conv2d(fuse, sd['mix_residual.0.weight'], padding=1))))
+    r = _bn(sd, 'mix_residual.4', F.conv2d(r, sd['mix_residual.3.weight'], padding=1))
+    sc = _bn(sd, 'mix_shortcut.1', F.conv2d(x, sd['mix_shortcut.0.weight']))
+    return q(F.relu(r + sc))
+
+
+def test_sfa_backward(cuda_lib):
+    """SFA with frozen BatchNorm: every convolution / squeeze-MLP gradient and dL/dx against autograd."""
+    import projects.mmdet3d_plugin  # noqa: F401
+    from dhd_b200 import dense as D
+    from dhd_b200.train import SFATrainer
+    from oracle import dense_oracle as DO
+    from projects.mmdet3d_plugin.models.necks.mix import SFA
+    sfa = SFA(512, 256).eval()
+    sfa.load_state_dict({k: v.bfloat16().float() if v.dtype.is_floating_point and 'running' not in k and
+                         not k.endswith(('bn.weight', 'bn.bias')) else v
+                         for k, v in DO.seeded_state_dict(sfa, 1).items()})
+    B, H, W = 2, 24, 40
+    x = DO.seeded_tensor((B, 512, H, W), 3).bfloat16().float()
+    gout = (DO.seeded_tensor((B, 256, H, W), 4) * 0.01).bfloat16().float()
+    sd = {k: v.clone().requires_grad_(v.dtype.is_floating_point and 'running' not in k)
+          for k, v in sfa.state_dict().items()}
+    xr = x.clone().requires_grad_()
+    with torch.no_grad():
+        assert torch.equal(_sfa_forward_q(sd, x, lambda t: t), DO.sfa_forward(sd, x))   # same restatement
+    y = _sfa_forward_q(sd, xr, _q)
+    (y * gout).sum().backward()
+    sfa = sfa.cuda()
+    for p in sfa.parameters():
+        p.grad = None
+    tr = SFATrainer(sfa)
+    out = tr.forward(D.pack_input(x.cuda(), 1))
+    assert rel(out.float(), y.detach()) < 1e-2
+    dx = tr.backward(D.pack_input(gout.cuda(), 1))
+    torch.cuda.synchronize()
+    errs = {}
+    for name, p in sfa.named_parameters():
+        bn = isinstance(dict(sfa.named_modules())[name.rsplit('.', 1)[0]], torch.nn.BatchNorm2d)
+        if bn:
+            assert p.grad is None          # frozen BatchNorm in this build
+            continue
+        errs[name] = rel(p.grad, sd[name].grad)
+    errs['x'] = rel(dx.float(), xr.grad)
+    print('relative L2 gradient errors:', {k: round(v, 4) for k, v in errs.items()})
+    assert max(errs.values()) < 2e-2, errs
