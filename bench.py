@@ -42,6 +42,7 @@ def parse():
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'bf16x3', 'fp32'])
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-train', action='store_true', help='skip the training-step extra')
     return ap.parse_args()
 
 
@@ -196,8 +197,42 @@ def run_ours(args):
         torch.cuda.synchronize()
         stage_ms[name] = s0.elapsed_time(s1) / 5
 
+    # ---- extras: the data-parallel TRAINING step of the path (forward, loss, backward, one gradient
+    # all-reduce over NCCL, AdamW, weight re-pack), see dhd_b200.pipeline.TrainStep for what is trainable
+    train = None
+    if not args.no_train:
+        from dhd_b200.pipeline import TrainStep
+        del step.graph
+        step.graph = None
+        ts = TrainStep(cfg, B)
+        ts.alloc_static(host)
+        ts.upload(host)
+        lib = _lib.load()
+        for _ in range(3):
+            ts.train_step()
+        barrier()
+        n0 = lib.dhd_launch_count()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        nt = max(3, min(args.steps, 10))
+        t0.record(st)
+        for _ in range(nt):
+            ts.train_step()
+        t1.record(st)
+        barrier()
+        ms_train = t0.elapsed_time(t1) / nt
+        train = {'ms_per_step': ms_train, 'launches_per_step': (lib.dhd_launch_count() - n0) / nt,
+                 'loss': float(ts.loss[0]), 'trainable_params': ts.n_params,
+                 'gradient_all_reduce_bytes': ts.n_params * 4,
+                 'what': 'forward + CE loss + backward of depth_net, SFA (frozen BN) and predictor, fused pool fwd+bwd, '
+                         'one NCCL all-reduce of the fp32 gradient bucket, AdamW, bf16 weight re-pack; HeightNet runs '
+                         'forward only (mask), encoders stand in as resident tensors (see TrainStep)'}
+        del ts
+
     from dhd_b200 import shard
     ms_total, ms_e2e, pool_ms_avg = shard.max_over_ranks([ms_total, ms_e2e, pool_ms_avg], device='cuda')
+    if train is not None:
+        train['ms_per_step'] = shard.max_over_ranks([train['ms_per_step']], device='cuda')[0]
+        train['samples_per_s'] = world * B / (train['ms_per_step'] * 1e-3)
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -237,7 +272,7 @@ def run_ours(args):
                 'kernel_share_of_step': pool_ms_avg / (ms_total / args.steps),
             },
             'extras': {
-                'stage_ms': stage_ms, 'pool_bwd_ms': bwd_ms,
+                'stage_ms': stage_ms, 'pool_bwd_ms': bwd_ms, 'train_step': train,
                 'e2e_serialised_ms_per_step (H2D, kernels, D2H on one stream)': ms_e2e_serial,
                 'dense_tflops_algorithmic': {k: v / 1e12 for k, v in fl.items()},
                 'dense_tflop_per_s': sum(fl.values()) / 1e12 /

@@ -298,3 +298,81 @@ class HotPathStep:
             except Exception:  # noqa: BLE001
                 return None
         return None
+
+
+class TrainStep(HotPathStep):
+    """One data-parallel TRAINING step of the hot path on this rank's B samples (bf16 operands, fp32
+    accumulation / master weights / gradients):
+
+      forward   pack -> depth_net (trainable) -> HeightNet (mask only: argmax is not differentiable, its
+                own gradient comes from the height loss, not built yet) -> prepare -> fused pool forward
+                [BEV / voxel encoders: outside the path -> resident synthetic features]
+                SFA (frozen BN) -> predictor -> class-weighted masked cross-entropy (occ_head.py:102-131)
+      backward  predictor -> SFA (gradient w.r.t. the encoder features is produced and dropped at the
+                boundary) ; [encoders' backward: outside the path -> resident synthetic gradients of the
+                four pool outputs] -> fused pool backward -> depth_net backward (dL/d image features)
+      exchange  ONE all-reduce of the flat fp32 gradient bucket (NCCL; launched asynchronously as soon
+                as the last gradient is written, joined before the optimizer)
+      update    AdamW (DHD-S.py:262: lr 2e-4, weight decay 1e-2) on the fp32 master weights, then the
+                bf16 forward / data-gradient weights are re-packed.
+    """
+
+    def __init__(self, cfg, B, device='cuda', seed=0):
+        super().__init__(cfg, B, precision='bf16', device=device, seed=seed, use_graph=False)
+        from projects.mmdet3d_plugin.models.dense_heads.occ_head import predictor
+        from . import shard
+        from .train import DepthHeadTrainer, PredictorTrainer, SFATrainer
+        torch.manual_seed(seed + 1)
+        self.head = predictor(in_dim=256, out_dim=256, Dz=16, num_classes=18, use_predicter=True, class_balance=True,
+                              loss_occ=dict(type='CrossEntropyLoss', use_sigmoid=False, ignore_index=255,
+                                            loss_weight=1.0)).to(self.device)
+        for m in self.sfa.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                for p in m.parameters():
+                    p.requires_grad_(False)
+        self.t_depth = DepthHeadTrainer(self.vt.depth_net, self.D, self.device)
+        self.t_sfa = SFATrainer(self.sfa, self.device)
+        self.t_head = PredictorTrainer(self.head, self.device)
+        params = list(self.vt.depth_net.parameters()) + [p for p in self.sfa.parameters() if p.requires_grad] + \
+            list(self.head.parameters())
+        self.bucket = shard.GradBucket(params)
+        self.opt = torch.optim.AdamW(self.bucket.params, lr=2e-4, weight_decay=1e-2, fused=True)
+        gen = torch.Generator(device=self.device).manual_seed(11)
+        self.labels = torch.randint(0, 18, (B, self.Dx, self.Dy, 16), device=self.device, generator=gen).to(torch.uint8)
+        self.mask_camera = (torch.rand(B, self.Dx, self.Dy, 16, device=self.device, generator=gen) < 0.5).to(torch.uint8)
+        for g in self.gouts:
+            g.mul_(1e-3)
+        self.n_params = self.bucket.flat.numel()
+        self.loss = None
+
+    def train_step(self):
+        s = self.static
+        B, N = self.B, self.N
+        self.bucket.zero()
+        # ---- forward
+        xa = D.pack_input(s['x'].view(B * N, self.Cin, self.fH, self.fW), 1)
+        depth, feat = self.t_depth.forward(xa)
+        mlp = self.vt.get_mlp_input(s['sensor2ego'], s['ego2global'], s['cam2imgs'], s['post_rots'],
+                                    s['post_trans'], s['bda'])
+        height = self.height_engine(xa, mlp, softmax=True)
+        pixmask = height_to_mask(height, self.cfg['height_range'], self.cfg['mask_range'])
+        self.plan.prepare(frustum=self.frustum, sensor2ego=s['sensor2ego'], cam2imgs=s['cam2imgs'],
+                          post_rots=s['post_rots'], post_trans=s['post_trans'], bda=s['bda'],
+                          deterministic=self.deterministic, workspace=self.workspace)
+        self._last = {'depth': depth, 'feat': feat, 'height': height, 'pixmask': pixmask}
+        self._pool()
+        enc = D.pack_nhwc(self.encoded, 1, want_mean=True)
+        fused = self.t_sfa.forward(enc)
+        self.t_head.forward(fused)
+        self.loss = self.t_head.loss(self.labels, self.mask_camera)
+        # ---- backward
+        dfused = self.t_head.backward()
+        self.t_sfa.backward(dfused)
+        self.run_pool_bwd()
+        self.t_depth.backward(self.depth_grad, self.feat_grad)
+        # ---- exchange + update
+        self.bucket.all_reduce_async()
+        self.bucket.wait()
+        self.opt.step()
+        for t in (self.t_depth, self.t_sfa, self.t_head):
+            t.refresh()

@@ -43,3 +43,37 @@ def gather_on_rank0(t):
     if rank != 0:
         return None
     return torch.cat([b[:int(s.item())] for b, s in zip(bufs, sizes)], dim=0)
+
+
+class GradBucket:
+    """Flat fp32 gradient buffer of a parameter list: every `param.grad` is a view into it, so the
+    backward kernels accumulate straight into the bucket and the data-parallel reduction is ONE
+    all-reduce of one contiguous tensor (the reference: torch DDP's bucketed all-reduce over NCCL,
+    tools/train.py:195 -> mmdet3d train_model -> MMDistributedDataParallel).  `all_reduce_async`
+    launches it on the process group's stream (NCCL: overlaps whatever is enqueued afterwards) and
+    `wait` joins it and divides by the world size."""
+
+    def __init__(self, params):
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError('no trainable parameters')
+        dev, n = self.params[0].device, sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        o = 0
+        for p in self.params:
+            p.grad = self.flat[o:o + p.numel()].view(p.shape)
+            o += p.numel()
+        self._work = None
+
+    def zero(self):
+        self.flat.zero_()
+
+    def all_reduce_async(self):
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            self._work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, async_op=True)
+
+    def wait(self):
+        if self._work is not None:
+            self._work.wait()
+            self._work = None
+            self.flat.mul_(1.0 / dist.get_world_size())

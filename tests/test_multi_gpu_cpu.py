@@ -57,3 +57,39 @@ def test_two_rank_gloo_aggregation():
     assert g0 == list(range(7)) and g1 is None
     assert t0 == t1 == [11.0, 5.0]          # element-wise max over the two ranks
     assert shard.samples_per_second(8, 2.0) == 4000.0
+
+
+def _grad_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        lin = torch.nn.Linear(5, 3)
+        frozen = torch.nn.Parameter(torch.zeros(2), requires_grad=False)
+        b = shard.GradBucket(list(lin.parameters()) + [frozen])
+        b.zero()
+        lin.weight.grad.add_(float(rank + 1))          # what a backward kernel does: accumulate in place
+        lin.bias.grad.add_(10.0 * (rank + 1))
+        b.all_reduce_async()
+        b.wait()
+        q.put((rank, lin.weight.grad.flatten().tolist(), lin.bias.grad.tolist(), b.flat.numel(),
+               lin.weight.grad.data_ptr() == b.flat.data_ptr()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gradient_bucket_single_all_reduce():
+    """The data-parallel exchange of the training step: one flat bucket, one SUM all-reduce, mean."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_grad_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, w, bias, n, aliased in out:
+        assert w == [1.5] * 15 and bias == [15.0] * 3      # mean of (1, 2) and of (10, 20)
+        assert n == 18 and aliased
