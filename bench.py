@@ -28,6 +28,8 @@ if ROOT not in sys.path:
 
 import torch  # noqa: E402
 
+_OUT = sys.stdout
+
 METRIC = 'samples/s DHD-S 6-cam 256x704 hot path (DepthNet/HeightNet, MGHS view transform + voxel pool, SFA, occupancy head)'
 UNIT = 'samples/s'
 B_PER_GPU = 4
@@ -284,7 +286,7 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             line['cpu_baseline'] = cpu_reference_leg(cfg, seconds=20.0)
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -376,10 +378,14 @@ def run_reference(args):
                          'sample': '%d steps of B=1' % steps},
         'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_OUT, flush=True)
 
 
 if __name__ == '__main__':
+    # stdout carries exactly ONE line (the JSON): libraries that write to fd 1 themselves (NCCL's version
+    # banner) are sent to stderr for the duration of the run
+    _OUT = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
     a = parse()
     if a.impl == 'reference':
         run_reference(a)
