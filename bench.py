@@ -225,9 +225,10 @@ def run_ours(args):
         train = {'ms_per_step': ms_train, 'launches_per_step': (lib.dhd_launch_count() - n0) / nt,
                  'loss': float(ts.loss[0]), 'trainable_params': ts.n_params,
                  'gradient_all_reduce_bytes': ts.n_params * 4,
-                 'what': 'forward + CE loss + backward of depth_net, SFA (frozen BN) and predictor, fused pool fwd+bwd, '
-                         'one NCCL all-reduce of the fp32 gradient bucket, AdamW, bf16 weight re-pack; HeightNet runs '
-                         'forward only (mask), encoders stand in as resident tensors (see TrainStep)'}
+                 'loss_height': float(ts.loss_height[0]),
+                 'what': 'forward + losses (occupancy CE, height BCE) + backward of depth_net, HeightNet, SFA and predictor '
+                         '(BatchNorm frozen), fused pool fwd+bwd, one NCCL all-reduce of the fp32 gradient bucket, AdamW, '
+                         'bf16 weight re-pack; encoders stand in as resident tensors (see TrainStep)'}
         del ts
 
     from dhd_b200 import shard

@@ -37,7 +37,8 @@ __device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&v)[8]) {
 __global__ void __launch_bounds__(256)
 act_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int dy_ld, int dy_coff, const __nv_bfloat16* __restrict__ y,
                int y_ld, int y_coff, long rows, int C, int act, __nv_bfloat16* __restrict__ out, int out_ld,
-               int out_coff, float* __restrict__ partial, long rows_per_block) {
+               int out_coff, float* __restrict__ partial, long rows_per_block,
+               const __nv_bfloat16* __restrict__ add, int add_ld, int add_coff) {
   __shared__ float red[256][17];
   const int cg = C / 8, rpb = 256 / cg;
   const int gi = threadIdx.x % cg, ri = threadIdx.x / cg;
@@ -49,6 +50,12 @@ act_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int dy_ld, int dy_coff, con
     for (long r = r0 + ri; r < r1; r += rpb) {
       float g[8], v[8];
       load8(dy + r * dy_ld + dy_coff + gi * 8, g);
+      if (add != nullptr) {            // a second gradient path into the same tensor (residual connection)
+        float a[8];
+        load8(add + r * add_ld + add_coff + gi * 8, a);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] += a[j];
+      }
       if (act != 0 || partial != nullptr) load8(y + r * y_ld + y_coff + gi * 8, v);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -301,6 +308,162 @@ add_rowvec_kernel(const float* __restrict__ in, const float* __restrict__ v, lon
   store8(out + pix * o_ld + o_coff + c, r);
 }
 
+
+// ---- SE gate backward (depthnet.py:150-169, 624-629): h = relu(bn(conv x)) * gate[n][c] ----------
+// dpre = dh * gate * (h > 0) (bf16);  partial per-image sums of dh * h / gate = d gate.
+__global__ void __launch_bounds__(256)
+se_gate_bwd_kernel(const __nv_bfloat16* __restrict__ dh, int g_ld, int g_coff, const __nv_bfloat16* __restrict__ h,
+                   int h_ld, int h_coff, int C, int HW, int pb, const float* __restrict__ gate,
+                   __nv_bfloat16* __restrict__ dpre, int d_ld, int d_coff, float* __restrict__ partial) {
+  __shared__ float red[256][9];
+  const int cg = C / 8, rows = 256 / cg;
+  const int gi = threadIdx.x % cg, ri = threadIdx.x / cg;
+  const int n = blockIdx.y, p0 = blockIdx.x * pb, p1 = min(HW, p0 + pb);
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (ri < rows) {
+    const float4* gp = reinterpret_cast<const float4*>(gate + (size_t)n * C + gi * 8);
+    const float4 ga = __ldg(gp), gb = __ldg(gp + 1);
+    const float g1[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+    for (int p = p0 + ri; p < p1; p += rows) {
+      const size_t r = (size_t)n * HW + p;
+      float gv[8], hv[8], o[8];
+      load8(dh + r * g_ld + g_coff + gi * 8, gv);
+      load8(h + r * h_ld + h_coff + gi * 8, hv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        o[j] = hv[j] > 0.f ? gv[j] * g1[j] : 0.f;
+        acc[j] += g1[j] != 0.f ? gv[j] * hv[j] / g1[j] : 0.f;
+      }
+      store8(dpre + r * d_ld + d_coff + gi * 8, o);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[threadIdx.x][j] = acc[j];
+  __syncthreads();
+  if (ri == 0) {
+    for (int k = 1; k < rows; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += red[threadIdx.x + k * cg][j];
+    float* pp = partial + ((size_t)n * gridDim.x + blockIdx.x) * C + gi * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) pp[j] = acc[j];
+  }
+}
+
+// ---- height loss (lss_heightmap.py:595-622) ------------------------------------------------------
+// height = softmax over H bins (NCHW (BN, H, HW)); label[pix] = GT bin (or -1: all-zero one-hot row);
+// fg[pix] = pixel has a valid GT depth.  loss = weight * sum_fg BCE(height, onehot) / max(1, #fg);
+// dz (bf16 NHWC, ld channels) = d loss / d logits through the softmax; zero rows for background pixels.
+__global__ void __launch_bounds__(128)
+height_loss_kernel(const float* __restrict__ height, const int* __restrict__ label, const uint8_t* __restrict__ fg,
+                   int BN, int H, int HW, float weight, const float* __restrict__ nfg, float* __restrict__ loss,
+                   __nv_bfloat16* __restrict__ dz, int ld) {
+  const long pix = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  float acc = 0.f;
+  if (pix < (long)BN * HW) {
+    const int bn = (int)(pix / HW), hw = (int)(pix % HW);
+    __nv_bfloat16* o = dz + (size_t)pix * ld;
+    if (fg[pix] == 0) {
+      for (int k = 0; k < ld; ++k) o[k] = __float2bfloat16(0.f);
+    } else {
+      const float scale = weight / fmaxf(1.f, nfg[0]);
+      const float* hp = height + (size_t)bn * H * HW + hw;
+      const int l = label[pix];
+      float dot = 0.f;
+      for (int k = 0; k < H; ++k) {
+        const float p = hp[(size_t)k * HW], t = k == l ? 1.f : 0.f;
+        acc -= t * fmaxf(__logf(p), -100.f) + (1.f - t) * fmaxf(__logf(1.f - p), -100.f);
+        const float g = (p - t) / fmaxf(p * (1.f - p), 1e-12f);
+        dot += g * p;
+      }
+      for (int k = 0; k < H; ++k) {
+        const float p = hp[(size_t)k * HW], t = k == l ? 1.f : 0.f;
+        const float g = (p - t) / fmaxf(p * (1.f - p), 1e-12f);
+        o[k] = __float2bfloat16(scale * p * (g - dot));
+      }
+      for (int k = H; k < ld; ++k) o[k] = __float2bfloat16(0.f);
+      acc *= scale;
+    }
+  }
+  acc = warp_sum(acc);
+  __shared__ float ws[4];
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) atomicAdd(loss, ws[0] + ws[1] + ws[2] + ws[3]);
+}
+
+// ---- deformable convolution backward, sampling part (mmcv DeformConv2dPack / modulated-free DCNv1) ----
+// forward: col[pix][g][tap][c] = bilinear(x, (y + tap_y + off_y, x + tap_x + off_x)) (dcn_im2col in layout.cu)
+// backward, one warp per (pixel, tap):  dx[corner][c] += w_corner * dcol[c]  (fp32 atomics),
+//   doff[pix][2 tap + 0/1] = sum_c dcol[c] * d sample / d (sy, sx).
+__global__ void __launch_bounds__(256)
+dcn_col2im_bwd_kernel(const __nv_bfloat16* __restrict__ dcol, int c_ld, const __nv_bfloat16* __restrict__ x, int x_ld,
+                      int x_coff, int C, int N, int H, int W, const float* __restrict__ offset, int off_ld, int ksize,
+                      int pad, int dil, int groups, float* __restrict__ dx, float* __restrict__ doff) {
+  const int lane = threadIdx.x & 31;
+  const long gw = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int taps = ksize * ksize;
+  if (gw >= (long)N * H * W * taps) return;
+  const int t = (int)(gw % taps);
+  const long pix = gw / taps;
+  const int wx = (int)(pix % W), hy = (int)((pix / W) % H), n = (int)(pix / ((long)W * H));
+  const float oy = __ldg(offset + (size_t)pix * off_ld + 2 * t), ox = __ldg(offset + (size_t)pix * off_ld + 2 * t + 1);
+  const float sy = (float)(hy - pad + (t / ksize) * dil) + oy;
+  const float sx = (float)(wx - pad + (t % ksize) * dil) + ox;
+  const int cg = C / groups;
+  const bool inside = sy > -1.f && sx > -1.f && sy < (float)H && sx < (float)W;
+  float gy = 0.f, gx = 0.f;
+  if (inside) {
+    const int y0 = (int)floorf(sy), x0 = (int)floorf(sx), y1 = y0 + 1, x1 = x0 + 1;
+    const float ly = sy - (float)y0, lx = sx - (float)x0, hy_ = 1.f - ly, hx_ = 1.f - lx;
+    const bool v00 = y0 >= 0 && x0 >= 0, v01 = y0 >= 0 && x1 <= W - 1, v10 = y1 <= H - 1 && x0 >= 0,
+               v11 = y1 <= H - 1 && x1 <= W - 1;
+    const size_t img = (size_t)n * H * W;
+    for (int c = 8 * lane; c < C; c += 256) {
+      const int g = c / cg, cl = c % cg;
+      float d[8], q00[8], q01[8], q10[8], q11[8];
+      load8(dcol + (size_t)pix * c_ld + (size_t)g * taps * cg + (size_t)t * cg + cl, d);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) q00[j] = q01[j] = q10[j] = q11[j] = 0.f;
+      const __nv_bfloat16* xb = x + img * x_ld + x_coff + c;
+      float* db = dx + img * C + c;
+      if (v00) {
+        load8(xb + ((size_t)y0 * W + x0) * x_ld, q00);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(db + ((size_t)y0 * W + x0) * C + j, hy_ * hx_ * d[j]);
+      }
+      if (v01) {
+        load8(xb + ((size_t)y0 * W + x1) * x_ld, q01);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(db + ((size_t)y0 * W + x1) * C + j, hy_ * lx * d[j]);
+      }
+      if (v10) {
+        load8(xb + ((size_t)y1 * W + x0) * x_ld, q10);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(db + ((size_t)y1 * W + x0) * C + j, ly * hx_ * d[j]);
+      }
+      if (v11) {
+        load8(xb + ((size_t)y1 * W + x1) * x_ld, q11);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(db + ((size_t)y1 * W + x1) * C + j, ly * lx * d[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        gy += d[j] * ((q10[j] - q00[j]) * hx_ + (q11[j] - q01[j]) * lx);
+        gx += d[j] * ((q01[j] - q00[j]) * hy_ + (q11[j] - q10[j]) * ly);
+      }
+    }
+  }
+  gy = warp_sum(gy);
+  gx = warp_sum(gx);
+  if (lane == 0) {
+    doff[(size_t)pix * off_ld + 2 * t] = gy;
+    doff[(size_t)pix * off_ld + 2 * t + 1] = gx;
+  }
+}
+
 }  // namespace dhd
 
 using namespace dhd;
@@ -313,7 +476,7 @@ extern "C" size_t dhd_act_bwd_workspace_bytes(int C) { return (size_t)kMaxSumBlo
 
 extern "C" int dhd_act_bwd(const void* dy, int dy_ld, int dy_coff, const void* y, int y_ld, int y_coff, long rows,
                            int C, int act, void* out, int out_ld, int out_coff, float* colsum, float* workspace,
-                           void* stream) {
+                           const void* add, int add_ld, int add_coff, void* stream) {
   DHD_REQUIRE(dy != nullptr && rows > 0 && C > 0, "bad arguments");
   DHD_REQUIRE(act >= 0 && act <= 3, "act must be none / relu / sigmoid / softplus");
   DHD_REQUIRE(act == 0 || y != nullptr, "the activation derivative needs the saved output");
@@ -322,6 +485,7 @@ extern "C" int dhd_act_bwd(const void* dy, int dy_ld, int dy_coff, const void* y
   DHD_REQUIRE(C <= 2048 && ok8(C, dy_ld, dy_coff, dy), "dy: C % 8, 16-byte aligned rows");
   if (y != nullptr) DHD_REQUIRE(ok8(C, y_ld, y_coff, y), "y: 16-byte aligned rows");
   if (out != nullptr) DHD_REQUIRE(ok8(C, out_ld, out_coff, out), "out: 16-byte aligned rows");
+  if (add != nullptr) DHD_REQUIRE(ok8(C, add_ld, add_coff, add), "add: 16-byte aligned rows");
   cudaStream_t st = (cudaStream_t)stream;
   const int rpb = 256 / (C / 8);
   long rows_per_block = (rows + kMaxSumBlocks - 1) / kMaxSumBlocks;
@@ -329,7 +493,8 @@ extern "C" int dhd_act_bwd(const void* dy, int dy_ld, int dy_coff, const void* y
   const int nblocks = (int)((rows + rows_per_block - 1) / rows_per_block);
   act_bwd_kernel<<<nblocks, 256, 0, st>>>((const __nv_bfloat16*)dy, dy_ld, dy_coff, (const __nv_bfloat16*)y, y_ld,
                                           y_coff, rows, C, act, (__nv_bfloat16*)out, out_ld, out_coff,
-                                          colsum != nullptr ? workspace : nullptr, rows_per_block);
+                                          colsum != nullptr ? workspace : nullptr, rows_per_block,
+                                          (const __nv_bfloat16*)add, add_ld, add_coff);
   DHD_CUDA_LAUNCH_CHECK("act_bwd");
   if (colsum != nullptr) {
     colsum_reduce_kernel<<<(2 * C + 255) / 256, 256, 0, st>>>(workspace, nblocks, 2 * C, colsum);
@@ -408,5 +573,55 @@ extern "C" int dhd_add_rowvec(const float* in, const float* v, int N, int HW, in
   add_rowvec_kernel<<<(int)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(in, v, (long)N * HW, HW, C,
                                                                                  (__nv_bfloat16*)out, out_ld, out_coff);
   DHD_CUDA_LAUNCH_CHECK("add_rowvec");
+  return DHD_OK;
+}
+
+extern "C" int dhd_se_gate_bwd(const void* dh, int g_ld, int g_coff, const void* h, int h_ld, int h_coff, int C, int N,
+                               int HW, const float* gate, void* dpre, int d_ld, int d_coff, float* gate_sums,
+                               float* workspace, void* stream) {
+  DHD_REQUIRE(dh && h && gate && dpre && gate_sums && workspace, "null pointer");
+  DHD_REQUIRE(N > 0 && HW > 0 && C > 0 && C <= 2048, "bad shape");
+  DHD_REQUIRE(ok8(C, g_ld, g_coff, dh) && ok8(C, h_ld, h_coff, h) && ok8(C, d_ld, d_coff, dpre) &&
+                  ((uintptr_t)gate & 15) == 0, "needs C % 8 == 0 and 16-byte aligned rows");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int pb = sfa_pb(N, HW), nb = (HW + pb - 1) / pb;
+  se_gate_bwd_kernel<<<dim3(nb, N), 256, 0, st>>>((const __nv_bfloat16*)dh, g_ld, g_coff, (const __nv_bfloat16*)h, h_ld,
+                                                  h_coff, C, HW, pb, gate, (__nv_bfloat16*)dpre, d_ld, d_coff, workspace);
+  DHD_CUDA_LAUNCH_CHECK("se_gate_bwd");
+  image_sum_reduce_kernel<<<(N * C + 255) / 256, 256, 0, st>>>(workspace, nb, N, C, gate_sums, 0);
+  DHD_CUDA_LAUNCH_CHECK("image_sum_reduce");
+  return DHD_OK;
+}
+
+extern "C" int dhd_height_loss(const float* height, const int32_t* label, const uint8_t* fg, int BN, int H, int HW,
+                               float weight, const float* n_fg, float* loss, void* dz, int dz_ld, void* stream) {
+  DHD_REQUIRE(height && label && fg && n_fg && loss && dz, "null pointer");
+  DHD_REQUIRE(BN > 0 && H > 0 && HW > 0 && dz_ld >= H, "bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(loss, 0, sizeof(float), st);
+  if (e != cudaSuccess) return fail((int)e, "%s: %ld", "memset(loss)", (long)e);
+  const long npix = (long)BN * HW;
+  height_loss_kernel<<<(int)((npix + 127) / 128), 128, 0, st>>>(height, label, fg, BN, H, HW, weight, n_fg, loss,
+                                                               (__nv_bfloat16*)dz, dz_ld);
+  DHD_CUDA_LAUNCH_CHECK("height_loss");
+  return DHD_OK;
+}
+
+extern "C" int dhd_dcn_col2im_bwd(const void* dcol, int col_ld, const void* x, int x_ld, int x_coff, int C, int N, int H,
+                                  int W, const float* offset, int off_ld, int ksize, int pad, int dilation, int groups,
+                                  float* dx, float* doff, void* stream) {
+  DHD_REQUIRE(dcol && x && offset && dx && doff, "null pointer");
+  DHD_REQUIRE(C > 0 && groups > 0 && C % groups == 0 && (C / groups) % 8 == 0, "bad channel grouping");
+  DHD_REQUIRE(N > 0 && H > 0 && W > 0 && ksize >= 1 && ksize <= 3, "bad shape");
+  DHD_REQUIRE(col_ld % 8 == 0 && x_ld % 8 == 0 && x_coff % 8 == 0 && ((uintptr_t)dcol & 15) == 0 &&
+                  ((uintptr_t)x & 15) == 0, "16-byte aligned rows");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(dx, 0, (size_t)N * H * W * C * sizeof(float), st);
+  if (e != cudaSuccess) return fail((int)e, "%s: %ld", "memset(dx)", (long)e);
+  const long warps = (long)N * H * W * ksize * ksize;
+  dcn_col2im_bwd_kernel<<<(int)((warps * 32 + 255) / 256), 256, 0, st>>>(
+      (const __nv_bfloat16*)dcol, col_ld, (const __nv_bfloat16*)x, x_ld, x_coff, C, N, H, W, offset, off_ld, ksize, pad,
+      dilation, groups, dx, doff);
+  DHD_CUDA_LAUNCH_CHECK("dcn_col2im_bwd");
   return DHD_OK;
 }

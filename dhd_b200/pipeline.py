@@ -304,13 +304,14 @@ class TrainStep(HotPathStep):
     """One data-parallel TRAINING step of the hot path on this rank's B samples (bf16 operands, fp32
     accumulation / master weights / gradients):
 
-      forward   pack -> depth_net (trainable) -> HeightNet (mask only: argmax is not differentiable, its
-                own gradient comes from the height loss, not built yet) -> prepare -> fused pool forward
+      forward   pack -> depth_net -> HeightNet (its mask gates the pool; argmax is not differentiable, so its
+                gradient comes from the height loss, lss_heightmap.py:595-622) -> prepare -> fused pool forward
                 [BEV / voxel encoders: outside the path -> resident synthetic features]
                 SFA (frozen BN) -> predictor -> class-weighted masked cross-entropy (occ_head.py:102-131)
       backward  predictor -> SFA (gradient w.r.t. the encoder features is produced and dropped at the
                 boundary) ; [encoders' backward: outside the path -> resident synthetic gradients of the
                 four pool outputs] -> fused pool backward -> depth_net backward (dL/d image features)
+                height loss -> HeightNet backward (DCN, ASPP, BasicBlocks, SE gate, reduce conv)
       exchange  ONE all-reduce of the flat fp32 gradient bucket (NCCL; launched asynchronously as soon
                 as the last gradient is written, joined before the optimizer)
       update    AdamW (DHD-S.py:262: lr 2e-4, weight decay 1e-2) on the fp32 master weights, then the
@@ -321,20 +322,21 @@ class TrainStep(HotPathStep):
         super().__init__(cfg, B, precision='bf16', device=device, seed=seed, use_graph=False)
         from projects.mmdet3d_plugin.models.dense_heads.occ_head import predictor
         from . import shard
-        from .train import DepthHeadTrainer, PredictorTrainer, SFATrainer
+        from .train import DepthHeadTrainer, HeightNetTrainer, PredictorTrainer, SFATrainer
         torch.manual_seed(seed + 1)
         self.head = predictor(in_dim=256, out_dim=256, Dz=16, num_classes=18, use_predicter=True, class_balance=True,
                               loss_occ=dict(type='CrossEntropyLoss', use_sigmoid=False, ignore_index=255,
                                             loss_weight=1.0)).to(self.device)
-        for m in self.sfa.modules():
-            if isinstance(m, torch.nn.BatchNorm2d):
+        for m in list(self.sfa.modules()) + list(self.vt.height_net.modules()):
+            if isinstance(m, (torch.nn.BatchNorm2d, torch.nn.BatchNorm1d)):
                 for p in m.parameters():
                     p.requires_grad_(False)
         self.t_depth = DepthHeadTrainer(self.vt.depth_net, self.D, self.device)
         self.t_sfa = SFATrainer(self.sfa, self.device)
         self.t_head = PredictorTrainer(self.head, self.device)
-        params = list(self.vt.depth_net.parameters()) + [p for p in self.sfa.parameters() if p.requires_grad] + \
-            list(self.head.parameters())
+        self.t_height = HeightNetTrainer(self.vt.height_net, self.device, loss_weight=0.1)
+        params = list(self.vt.depth_net.parameters()) + [p for p in self.vt.height_net.parameters() if p.requires_grad] + \
+            [p for p in self.sfa.parameters() if p.requires_grad] + list(self.head.parameters())
         self.bucket = shard.GradBucket(params)
         self.opt = torch.optim.AdamW(self.bucket.params, lr=2e-4, weight_decay=1e-2, fused=True)
         gen = torch.Generator(device=self.device).manual_seed(11)
@@ -342,6 +344,9 @@ class TrainStep(HotPathStep):
         self.mask_camera = (torch.rand(B, self.Dx, self.Dy, 16, device=self.device, generator=gen) < 0.5).to(torch.uint8)
         for g in self.gouts:
             g.mul_(1e-3)
+        npix = B * self.N * self.fH * self.fW             # binned LiDAR supervision (synthetic): height bin, fg flag
+        self.height_label = torch.randint(-1, 65, (npix,), device=self.device, generator=gen).int()
+        self.height_fg = (torch.rand(npix, device=self.device, generator=gen) < 0.3).to(torch.uint8)
         self.n_params = self.bucket.flat.numel()
         self.loss = None
 
@@ -354,13 +359,14 @@ class TrainStep(HotPathStep):
         depth, feat = self.t_depth.forward(xa)
         mlp = self.vt.get_mlp_input(s['sensor2ego'], s['ego2global'], s['cam2imgs'], s['post_rots'],
                                     s['post_trans'], s['bda'])
-        height = self.height_engine(xa, mlp, softmax=True)
+        height = self.t_height.forward(xa, mlp)
         pixmask = height_to_mask(height, self.cfg['height_range'], self.cfg['mask_range'])
         self.plan.prepare(frustum=self.frustum, sensor2ego=s['sensor2ego'], cam2imgs=s['cam2imgs'],
                           post_rots=s['post_rots'], post_trans=s['post_trans'], bda=s['bda'],
                           deterministic=self.deterministic, workspace=self.workspace)
         self._last = {'depth': depth, 'feat': feat, 'height': height, 'pixmask': pixmask}
         self._pool()
+        self.loss_height = self.t_height.loss(self.height_label, self.height_fg)
         enc = D.pack_nhwc(self.encoded, 1, want_mean=True)
         fused = self.t_sfa.forward(enc)
         self.t_head.forward(fused)
@@ -370,9 +376,10 @@ class TrainStep(HotPathStep):
         self.t_sfa.backward(dfused)
         self.run_pool_bwd()
         self.t_depth.backward(self.depth_grad, self.feat_grad)
+        self.t_height.backward(want_dx=True)
         # ---- exchange + update
         self.bucket.all_reduce_async()
         self.bucket.wait()
         self.opt.step()
-        for t in (self.t_depth, self.t_sfa, self.t_head):
+        for t in (self.t_depth, self.t_height, self.t_sfa, self.t_head):
             t.refresh()

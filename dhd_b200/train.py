@@ -30,9 +30,9 @@ def _workspace(dev, nbytes):
     return ws
 
 
-def act_bwd(dy, y, act, out=None, want_sums=False):
-    """dz = dy * act'(y) (Acts, part 0).  out=None -> in place on dy.  Returns (dz Act, sums) with
-    sums (2, C) fp32 = [sum_rows dz, sum_rows dz*y] when want_sums."""
+def act_bwd(dy, y, act, out=None, want_sums=False, add=None):
+    """dz = (dy [+ add]) * act'(y) (Acts, part 0).  out=None -> in place on dy.  Returns (dz Act, sums)
+    with sums (2, C) fp32 = [sum_rows dz, sum_rows dz*y] when want_sums."""
     lib = _lib.load()
     C = dy.C
     out = dy if out is None else out
@@ -42,7 +42,9 @@ def act_bwd(dy, y, act, out=None, want_sums=False):
         ws = _workspace(dy.data.device, lib.dhd_act_bwd_workspace_bytes(C))
     yy = y if y is not None else dy
     _lib.check(lib.dhd_act_bwd(_p(dy.data), dy.ld, dy.coff, _p(yy.data), yy.ld, yy.coff, dy.N * dy.H * dy.W, C,
-                               ACT_ID[act], _p(out.data), out.ld, out.coff, _p(sums), _p(ws), _stream()), 'act_bwd')
+                               ACT_ID[act], _p(out.data), out.ld, out.coff, _p(sums), _p(ws),
+                               _p(add.data) if add is not None else None, add.ld if add is not None else 0,
+                               add.coff if add is not None else 0, _stream()), 'act_bwd')
     return out, sums
 
 
@@ -59,10 +61,13 @@ class _TrainConv:
     """One convolution of a trainable module: fp32 master weight lives in the torch parameter;
     `refresh()` re-packs the bf16 forward and data-gradient weights after an optimizer step."""
 
-    def __init__(self, weight, bias, bn, ksize, dilation=1, cin_pad=None, cout_pad=None):
+    def __init__(self, weight, bias, bn, ksize, dilation=1, cin_pad=None, cout_pad=None, cols=None):
+        """cols=(lo, hi): the layer uses input-channel columns [lo, hi) of `weight` only (a branch of a
+        concatenation whose other columns are handled elsewhere)."""
         self.weight, self.bias_p, self.bn = weight, bias, bn
-        self.ksize, self.dilation = ksize, dilation
-        self.Cout, self.Cin = weight.shape[0], weight.shape[1]
+        self.ksize, self.dilation, self.cols = ksize, dilation, cols
+        self.Cout = weight.shape[0]
+        self.Cin = weight.shape[1] if cols is None else cols[1] - cols[0]
         self.cin_pad = cin_pad or self.Cin          # forward input channels (zero padded to % 64)
         self.cout_pad = cout_pad or self.Cout       # backward input channels (dy padded to % 64)
         self.refresh()
@@ -71,6 +76,8 @@ class _TrainConv:
         w = self.weight.detach().float()
         if w.dim() == 2:
             w = w[:, :, None, None]
+        if self.cols is not None:
+            w = w[:, self.cols[0]:self.cols[1]]
         dev = w.device
         if self.bn is not None:
             s, b = fold_bn(self.bn, self.bias_p)
@@ -98,7 +105,10 @@ class _TrainConv:
         if x.C != self.Cin:
             dw = dw[:, :, :self.Cin]
         g = D.weight_grad_to_torch(dw.contiguous(), self.ksize)
-        _acc(self.weight, g if self.weight.dim() == 4 else g[:, :, 0, 0])
+        if self.cols is not None:
+            _ensure_grad(self.weight)[:, self.cols[0]:self.cols[1]].add_(g)
+        else:
+            _acc(self.weight, g if self.weight.dim() == 4 else g[:, :, 0, 0])
         if self.bias_p is not None and bias_sums is not None:      # a conv bias under a frozen BN sees the BN scale
             _acc(self.bias_p, bias_sums[:self.Cout] if self.bn is None else bias_sums[:self.Cout] * self.scale)
         if dx_segs is not None:
@@ -337,4 +347,257 @@ class SFATrainer:
         dx = self._act('dx', N, H, W, 2 * C)
         _lib.check(lib.dhd_add_rowvec(_p(dxb), _p(ds.contiguous()), N, H * W, 2 * C, _p(dx.data), dx.ld, dx.coff,
                                       _stream()), 'add_rowvec')
+        return dx
+
+
+def _ensure_grad(p):
+    if p.grad is None:
+        p.grad = torch.zeros_like(p)
+    return p.grad
+
+
+class HeightNetTrainer:
+    """HeightNet (depthnet.py:418-487, 605-652, non-stereo) with frozen BatchNorm and Dropout off:
+    reduce conv + camera-aware SE gate, BasicBlocks, ASPP (global branch as a per-image bias), DCN
+    (deformable im2col + grouped GEMM), 1x1 head + softmax; backward of all of it, fed by the height loss
+    (lss_heightmap.py:595-622)."""
+
+    def __init__(self, net, device='cuda', loss_weight=0.1):
+        from .modules import linear_rows, mean_hw
+        self._linear, self._mean = linear_rows, mean_hw
+        self.net, self.device, self.loss_weight = net, device, float(loss_weight)
+        self.C = net.reduce_conv[0].out_channels
+        self.reduce = _TrainConv(net.reduce_conv[0].weight, net.reduce_conv[0].bias, net.reduce_conv[1], 3)
+        layers = list(net.depth_conv)
+        self.blocks, i = [], 0
+        while i < len(layers) and type(layers[i]).__name__ == 'BasicBlock':
+            b = layers[i]
+            if b.downsample is not None:
+                raise NotImplementedError('stereo downsample branch')
+            self.blocks.append((_TrainConv(b.conv1.weight, None, b.bn1, 3), _TrainConv(b.conv2.weight, None, b.bn2, 3)))
+            i += 1
+        a = layers[i]
+        if type(a).__name__ != 'ASPP':
+            raise NotImplementedError('HeightNet without ASPP')
+        self.aspp = a
+        self.mid = mid = a.aspp1.atrous_conv.out_channels
+        self.branches = [_TrainConv(b.atrous_conv.weight, None, b.bn, b.atrous_conv.kernel_size[0], b.atrous_conv.dilation[0])
+                         for b in (a.aspp1, a.aspp2, a.aspp3, a.aspp4)]
+        self.aspp_out = _TrainConv(a.conv1.weight, None, a.bn1, 1, cols=(0, 4 * mid))
+        i += 1
+        self.dcn = layers[i] if hasattr(layers[i], 'conv_offset') else None
+        if self.dcn is None:
+            raise NotImplementedError('HeightNet without DCN (DHD-L): use_dcn=False trunk')
+        dc = self.dcn
+        self.k, self.groups = dc.weight.shape[2], dc.groups
+        self.pad = dc.padding if isinstance(dc.padding, int) else dc.padding[0]
+        self.dil = dc.dilation if isinstance(dc.dilation, int) else dc.dilation[0]
+        self.noff = 2 * self.k * self.k
+        self.dcn_offset = _TrainConv(dc.conv_offset.weight, dc.conv_offset.bias, None, self.k, cout_pad=64)
+        i += 1
+        head = layers[i]
+        self.H_bins = head.weight.shape[0]
+        self.head = _TrainConv(head.weight, head.bias, None, 1, cout_pad=(self.H_bins + 63) // 64 * 64)
+        self._buf = {}
+        self.refresh()
+
+    # ---- weights -------------------------------------------------------------------------------
+    def refresh(self):
+        for c in [self.reduce, self.aspp_out, self.dcn_offset, self.head] + self.branches + \
+                [c for pair in self.blocks for c in pair]:
+            c.refresh()
+        f = lambda t: t.detach().float().contiguous()
+        net, a, dc = self.net, self.aspp, self.dcn
+        self.bn_scale, self.bn_shift = fold_bn(net.bn)
+        s5, b5 = fold_bn(a.global_avg_pool[2])
+        self.s5, self.b5 = s5, b5
+        self.gap_ws = f(a.global_avg_pool[1].weight.flatten(1) * s5[:, None])
+        s1, _ = fold_bn(a.bn1)
+        self.s1 = s1
+        self.w5s = f(a.conv1.weight.detach()[:, 4 * self.mid:].flatten(1) * s1[:, None])
+        cg, k = self.C // self.groups, self.k
+        self.dcn_wf, self.dcn_wb = [], []
+        for g in range(self.groups):
+            wg = dc.weight.detach().float()[g * cg:(g + 1) * cg].permute(0, 2, 3, 1).reshape(cg, k * k * cg)
+            self.dcn_wf.append(D.pack_weight(wg, 1))
+            self.dcn_wb.append(D.pack_weight_dgrad(wg, 1))
+
+    def _act(self, name, N, H, W, C):
+        key = (name, N, H, W, C)
+        if key not in self._buf:
+            self._buf[key] = D.Act.empty(N, H, W, C, 1, self.device)
+        return self._buf[key]
+
+    def _f32(self, name, *shape):
+        key = (name,) + shape
+        if key not in self._buf:
+            self._buf[key] = torch.empty(*shape, device=self.device)
+        return self._buf[key]
+
+    # ---- forward -------------------------------------------------------------------------------
+    def forward(self, x, mlp_input):
+        """x: Act (B*N, C_in, fH, fW); mlp_input (B, N, 27).  Returns softmax height (B*N, H, fH, fW) fp32."""
+        net, lin = self.net, self._linear
+        N, H, W, C = x.N, x.H, x.W, self.C
+        f = lambda t: t.detach().float().contiguous()
+        m_in = mlp_input.reshape(-1, mlp_input.shape[-1]).contiguous().float()
+        mlp, se = net.depth_mlp, net.depth_se
+        h1 = lin(m_in, f(mlp.fc1.weight), f(mlp.fc1.bias), 'relu', self.bn_scale, self.bn_shift)
+        h2 = lin(h1, f(mlp.fc2.weight), f(mlp.fc2.bias))
+        h3 = lin(h2, f(se.conv_reduce.weight.flatten(1)), f(se.conv_reduce.bias), 'relu')
+        gate = lin(h3, f(se.conv_expand.weight.flatten(1)), f(se.conv_expand.bias), 'sigmoid')
+        nhwc = D.nhwc_strides(C, H, W)
+        h = self._act('h0', N, H, W, C)
+        h32 = self._f32('h0_32', N, H, W, C)
+        self.reduce.forward(x, [dict(act='relu', out_act=h, out_f32=(h32, nhwc))], img_gate=gate)
+        hs, ts = [h], []
+        for bi, (c1, c2) in enumerate(self.blocks):
+            t = self._act('t%d' % bi, N, H, W, C)
+            c1.forward(h, [dict(act='relu', out_act=t)])
+            hn, hn32 = self._act('h%d' % (bi + 1), N, H, W, C), self._f32('h%d_32' % (bi + 1), N, H, W, C)
+            c2.forward(t, [dict(act='relu', out_act=hn, out_f32=(hn32, nhwc))], residual=(h32, nhwc[:3]))
+            h, h32 = hn, hn32
+            hs.append(h)
+            ts.append(t)
+        mid = self.mid
+        cat = self._act('cat', N, H, W, 4 * mid)
+        for b, conv in enumerate(self.branches):
+            conv.forward(h, [dict(act='relu', out_act=cat.slice(b * mid, (b + 1) * mid))])
+        meanh = self._mean(h)
+        x5 = lin(meanh, self.gap_ws, self.b5.to(self.device), 'relu')
+        ib = lin(x5, self.w5s)
+        ha = self._act('ha', N, H, W, C)
+        self.aspp_out.forward(cat, [dict(act='relu', out_act=ha)], img_bias=ib)
+        k, g, cg = self.k, self.groups, C // self.groups
+        off = self._f32('off', N, H, W, self.noff)
+        self.dcn_offset.forward(ha, [dict(out_f32=(off, D.nhwc_strides(self.noff, H, W)))])
+        col = self._act('col', N, H, W, k * k * C)
+        _lib.check(_lib.load().dhd_dcn_im2col(_p(ha.data), ha.ld, ha.coff, ha.part_stride, ha.parts, C, N, H, W,
+                                              _p(off), self.noff, k, self.pad, self.dil, g, _p(col.data), col.ld,
+                                              col.part_stride, col.parts, _stream()), 'dcn_im2col')
+        out = self._act('dcn_out', N, H, W, C)
+        for gi in range(g):
+            D.conv2d(col.slice(gi * k * k * cg, (gi + 1) * k * k * cg), self.dcn_wf[gi], cg, precision='bf16',
+                     segs=[dict(out_act=out.slice(gi * cg, (gi + 1) * cg))])
+        height = torch.empty(N, self.H_bins, H, W, device=self.device)
+        self.head.forward(out, [dict(act='softmax', out_f32=(height, D.nchw_strides(self.H_bins, H, W)))])
+        self.saved = dict(x=x, m_in=m_in, h1=h1, h2=h2, h3=h3, gate=gate, hs=hs, ts=ts, cat=cat, meanh=meanh, x5=x5,
+                          ha=ha, off=off, col=col, out=out, height=height)
+        return height
+
+    # ---- loss ----------------------------------------------------------------------------------
+    def loss(self, label, fg):
+        """label (npix,) int32 GT height bin (-1: none), fg (npix,) uint8/bool: MGHS.get_height_loss on
+        binned labels.  Returns a 1-element device tensor; keeps d loss / d logits for backward()."""
+        sv = self.saved
+        h = sv['height']
+        N, Hb, H, W = h.shape
+        fg = fg.to(torch.uint8).contiguous()
+        nfg = fg.sum().float().reshape(1)
+        dz = self._act('dz', N, H, W, self.head.cout_pad)
+        res = torch.empty(1, device=self.device)
+        _lib.check(_lib.load().dhd_height_loss(_p(h), _p(label.int().contiguous()), _p(fg), N, Hb, H * W,
+                                               self.loss_weight, _p(nfg), _p(res), _p(dz.data), dz.ld, _stream()),
+                   'height_loss')
+        self.dz = dz
+        return res
+
+    # ---- backward ------------------------------------------------------------------------------
+    def backward(self, want_dx=False):
+        sv, lin, lib = self.saved, self._linear, _lib.load()
+        x, hs, ts, cat, ha, off, col, out = sv['x'], sv['hs'], sv['ts'], sv['cat'], sv['ha'], sv['off'], sv['col'], sv['out']
+        N, H, W, C = x.N, x.H, x.W, self.C
+        HW = H * W
+        k, g, cg, mid = self.k, self.groups, C // self.groups, self.mid
+        nhwc = D.nhwc_strides(C, H, W)
+        dz = self.dz
+        _, sums = act_bwd(dz, None, None, want_sums=True)
+        dout = self._act('d_out', N, H, W, C)
+        self.head.backward(out, dz, [dict(out_act=dout)], bias_sums=sums[0])
+        # ---- DCN: grouped GEMM backward, then the sampling backward
+        dcol = self._act('d_col', N, H, W, k * k * C)
+        wgrad = _ensure_grad(self.dcn.weight)
+        for gi in range(g):
+            cs, ds = col.slice(gi * k * k * cg, (gi + 1) * k * k * cg), dout.slice(gi * cg, (gi + 1) * cg)
+            dw = D.conv2d_wgrad(cs, ds, cg)                                   # (cg, 1, k*k*cg), K = (tap, c)
+            wgrad[gi * cg:(gi + 1) * cg].add_(dw.view(cg, k, k, cg).permute(0, 3, 1, 2))
+            D.conv2d(ds, self.dcn_wb[gi], k * k * cg, precision='bf16',
+                     segs=[dict(out_act=dcol.slice(gi * k * k * cg, (gi + 1) * k * k * cg))])
+        dxs = self._f32('d_sample', N, H, W, C)
+        doff = self._f32('d_off', N, H, W, self.noff)
+        _lib.check(lib.dhd_dcn_col2im_bwd(_p(dcol.data), dcol.ld, _p(ha.data), ha.ld, ha.coff, C, N, H, W, _p(off),
+                                          self.noff, k, self.pad, self.dil, g, _p(dxs), _p(doff), _stream()),
+                   'dcn_col2im_bwd')
+        doff_a = self._act('d_off_a', N, H, W, self.dcn_offset.cout_pad)
+        doff_a.data.zero_()
+        doff_a.data[..., :self.noff] = doff.to(torch.bfloat16)
+        _, sums = act_bwd(doff_a, None, None, want_sums=True)
+        dha = self._act('d_ha', N, H, W, C)
+        self.dcn_offset.backward(ha, doff_a, [dict(out_act=dha)], bias_sums=sums[0], residual=(dxs, nhwc[:3]))
+        # ---- ASPP
+        act_bwd(dha, ha, 'relu')
+        dib = self._mean(dha) * float(HW)                                       # (N, C): sum over pixels
+        dcat = self._act('d_cat', N, H, W, 4 * mid)
+        self.aspp_out.backward(cat, dha, [dict(out_act=dcat)])
+        x5, meanh = sv['x5'], sv['meanh']
+        s1, s5 = self.s1.to(self.device), self.s5.to(self.device)
+        a = self.aspp
+        _ensure_grad(a.conv1.weight)[:, 4 * mid:].add_((lin(dib.t().contiguous(), x5.t().contiguous()) *
+                                                        s1[:, None]).view(C, mid, 1, 1))
+        dg = (lin(dib, self.w5s.t().contiguous()) * (x5 > 0).float()).contiguous()
+        _acc(a.global_avg_pool[1].weight, lin(dg.t().contiguous(), meanh.t().contiguous()) * s5[:, None])
+        dmean = lin(dg, self.gap_ws.t().contiguous()) * (1.0 / HW)
+        act_bwd(dcat, cat, 'relu')
+        hl = hs[-1]
+        A, B = self._f32('acc_a', N, H, W, C), self._f32('acc_b', N, H, W, C)
+        src = None
+        for b, conv in enumerate(self.branches):
+            dst = A if b % 2 == 0 else B
+            kw = {} if src is None else dict(residual=(src, nhwc[:3]))
+            conv.backward(hl, dcat.slice(b * mid, (b + 1) * mid), [dict(out_f32=(dst, nhwc))], **kw)
+            src = dst
+        dh = self._act('d_h', N, H, W, C)
+        _lib.check(lib.dhd_add_rowvec(_p(src), _p(dmean.contiguous()), N, HW, C, _p(dh.data), dh.ld, dh.coff,
+                                      _stream()), 'add_rowvec')
+        act_bwd(dh, hl, 'relu')
+        # ---- BasicBlocks, last to first
+        for bi in range(len(self.blocks) - 1, -1, -1):
+            c1, c2 = self.blocks[bi]
+            t, hin = ts[bi], hs[bi]
+            dt = self._act('d_t', N, H, W, C)
+            c2.backward(t, dh, [dict(out_act=dt)])
+            act_bwd(dt, t, 'relu')
+            dhin = self._act('d_hin%d' % (bi & 1), N, H, W, C)
+            c1.backward(hin, dt, [dict(out_act=dhin)])
+            act_bwd(dhin, hin if bi > 0 else None, 'relu' if bi > 0 else None, add=dh)     # + identity path
+            dh = dhin
+        # ---- reduce conv + SE gate
+        gate = sv['gate']
+        dpre = self._act('d_pre', N, H, W, C)
+        gsum = self._f32('gsum', N, C)
+        ws = _workspace(self.device, lib.dhd_sfa_gate_bwd_workspace_bytes(N, HW, C))
+        _lib.check(lib.dhd_se_gate_bwd(_p(dh.data), dh.ld, dh.coff, _p(hs[0].data), hs[0].ld, hs[0].coff, C, N, HW,
+                                       _p(gate), _p(dpre.data), dpre.ld, dpre.coff, _p(gsum), _p(ws), _stream()),
+                   'se_gate_bwd')
+        _, sums = act_bwd(dpre, None, None, want_sums=True)
+        dx = self._act('d_x', N, H, W, x.C) if want_dx else None
+        self.reduce.backward(x, dpre, [dict(out_act=dx)] if want_dx else None, bias_sums=sums[0])
+        # ---- camera-aware gate MLP (B*N rows)
+        net = self.net
+        mlp, se = net.depth_mlp, net.depth_se
+        f = lambda t: t.detach().float().contiguous()
+        h1, h2, h3, m_in = sv['h1'], sv['h2'], sv['h3'], sv['m_in']
+        m_bn = m_in * self.bn_scale.to(self.device) + self.bn_shift.to(self.device)
+        dze = (gsum * gate * (1.0 - gate)).contiguous()
+        _acc(se.conv_expand.weight, lin(dze.t().contiguous(), h3.t().contiguous()))
+        _acc(se.conv_expand.bias, dze.sum(0))
+        dzr = (lin(dze, f(se.conv_expand.weight.flatten(1)).t().contiguous()) * (h3 > 0).float()).contiguous()
+        _acc(se.conv_reduce.weight, lin(dzr.t().contiguous(), h2.t().contiguous()))
+        _acc(se.conv_reduce.bias, dzr.sum(0))
+        dh2 = lin(dzr, f(se.conv_reduce.weight.flatten(1)).t().contiguous())
+        _acc(mlp.fc2.weight, lin(dh2.t().contiguous(), h1.t().contiguous()))
+        _acc(mlp.fc2.bias, dh2.sum(0))
+        dz1 = (lin(dh2, f(mlp.fc2.weight).t().contiguous()) * (h1 > 0).float()).contiguous()
+        _acc(mlp.fc1.weight, lin(dz1.t().contiguous(), m_bn.t().contiguous()))
+        _acc(mlp.fc1.bias, dz1.sum(0))
         return dx

@@ -225,7 +225,8 @@ int dhd_conv2d_wgrad(const dhd_wgrad_desc* desc, void* stream);
 size_t dhd_act_bwd_workspace_bytes(int C);
 int dhd_act_bwd(const void* dy, int dy_ld, int dy_coff, const void* y, int y_ld, int y_coff, long rows,
                 int C, int act, void* out, int out_ld, int out_coff, float* colsum, float* workspace,
-                void* stream);
+                const void* add, int add_ld, int add_coff, void* stream);
+/* (add, optional: a second bf16 gradient summed into dy first -- the identity path of a residual block) */
 /* predictor.loss, cross-entropy term (occ_head.py:102-131; mmdet CrossEntropyLoss with class_weight,
  * weight = mask_camera, avg_factor = sum mask*class_weight[label]): logits (B,Dx,Dy,Dz,ncls) fp32,
  * labels / mask (B,Dx,Dy,Dz) uint8 (mask or class_weight may be NULL).  loss_and_norm[0] = loss,
@@ -252,6 +253,25 @@ int dhd_sfa_gate_bwd(int mode, const void* g, int g_ld, int g_coff, const void* 
 /* out (bf16 NHWC) = in (fp32 [N*HW][C]) + v[n][c] (v may be NULL) */
 int dhd_add_rowvec(const float* in, const float* v, int N, int HW, int C, void* out, int out_ld,
                    int out_coff, void* stream);
+
+/* SE gate backward (depthnet.py:150-169, 624-629): h = relu(bn(conv x)) * gate[n][c] saved as bf16;
+ * dpre = dh * gate * (h > 0); gate_sums [N][C] = sum_pixels dh * h / gate (= d gate); workspace as
+ * dhd_sfa_gate_bwd_workspace_bytes(N, HW, C). */
+int dhd_se_gate_bwd(const void* dh, int g_ld, int g_coff, const void* h, int h_ld, int h_coff, int C, int N,
+                    int HW, const float* gate, void* dpre, int d_ld, int d_coff, float* gate_sums,
+                    float* workspace, void* stream);
+/* MGHS.get_height_loss (lss_heightmap.py:595-622) on already binned labels: height (BN,H,HW) softmax
+ * probabilities, label[pix] = GT height bin or -1 (all-zero one-hot row), fg[pix] = valid GT depth,
+ * n_fg device scalar.  loss[0] = weight * sum_fg BCE / max(1, n_fg); dz = d loss / d logits (through
+ * the softmax) as bf16 NHWC rows of dz_ld channels (zero beyond H and for background pixels). */
+int dhd_height_loss(const float* height, const int32_t* label, const uint8_t* fg, int BN, int H, int HW,
+                    float weight, const float* n_fg, float* loss, void* dz, int dz_ld, void* stream);
+/* sampling part of the deformable convolution backward (mmcv DeformConv2dPack, depthnet.py:466-477):
+ * dcol in the layout dhd_dcn_im2col writes; dx fp32 [N*H*W][C] (zeroed here, accumulated with atomics),
+ * doff fp32 [N*H*W][off_ld] gradient of the offsets. */
+int dhd_dcn_col2im_bwd(const void* dcol, int col_ld, const void* x, int x_ld, int x_coff, int C, int N, int H,
+                       int W, const float* offset, int off_ld, int ksize, int pad, int dilation, int groups,
+                       float* dx, float* doff, void* stream);
 
 /* ---- streaming layout / elementwise helpers of the dense path (csrc/layout.cu) -----------
  * "split-bf16 NHWC": bf16, `ld` channels per pixel, logical channel c of part p at
