@@ -350,7 +350,52 @@ class TrainStep(HotPathStep):
         self.n_params = self.bucket.flat.numel()
         self.loss = None
 
+    def capture_train(self):
+        """Capture forward + losses + backward (graph 1) and the weight re-pack (graph 2) into CUDA graphs:
+        the step is ~190 library launches plus the small torch ops of the gate MLPs, i.e. launch-bound
+        when issued one by one.  The all-reduce and the optimizer stay eager."""
+        for _ in range(2):
+            self.train_step()
+        torch.cuda.synchronize()
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self._fwd_bwd()
+                self._refresh()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g1):
+                self._fwd_bwd()
+            with torch.cuda.graph(g2):
+                self._refresh()
+            self.train_graph = (g1, g2)
+        except Exception as e:  # noqa: BLE001
+            self.train_graph = None
+            self.train_graph_error = repr(e)[:300]
+            torch.cuda.synchronize()
+        return self.train_graph is not None
+
+    def _refresh(self):
+        for t in (self.t_depth, self.t_height, self.t_sfa, self.t_head):
+            t.refresh()
+
     def train_step(self):
+        g = getattr(self, 'train_graph', None)
+        if g is not None:
+            g[0].replay()
+        else:
+            self._fwd_bwd()
+        self.bucket.all_reduce_async()
+        self.bucket.wait()
+        self.opt.step()
+        if g is not None:
+            g[1].replay()
+        else:
+            self._refresh()
+
+    def _fwd_bwd(self):
         s = self.static
         B, N = self.B, self.N
         self.bucket.zero()
@@ -377,9 +422,3 @@ class TrainStep(HotPathStep):
         self.run_pool_bwd()
         self.t_depth.backward(self.depth_grad, self.feat_grad)
         self.t_height.backward(want_dx=True)
-        # ---- exchange + update
-        self.bucket.all_reduce_async()
-        self.bucket.wait()
-        self.opt.step()
-        for t in (self.t_depth, self.t_height, self.t_sfa, self.t_head):
-            t.refresh()
