@@ -93,14 +93,16 @@ act_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int dy_ld, int dy_coff, con
   }
 }
 
-// sums[i] = sum over blocks (ascending) of partial[b][i]
+// sums[i] = sum over blocks of partial[b][i]: one warp per column, lanes stride over the blocks, fixed
+// shuffle tree (deterministic)
 __global__ void __launch_bounds__(256)
 colsum_reduce_kernel(const float* __restrict__ partial, int nblocks, int n, float* __restrict__ sums) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (i >= n) return;
   float a = 0.f;
-  for (int b = 0; b < nblocks; ++b) a += partial[(size_t)b * n + i];
-  sums[i] = a;
+  for (int b = lane; b < nblocks; b += 32) a += partial[(size_t)b * n + i];
+  a = warp_sum(a);
+  if (lane == 0) sums[i] = a;
 }
 
 // ---- occupancy cross-entropy ---------------------------------------------------------------
@@ -148,20 +150,45 @@ ce_loss_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ lab
     float w = 0.f;
     if (l != ignore && l < ncls && (mask == nullptr || mask[v] != 0)) w = cw != nullptr ? cw[l] : 1.f;
     __nv_bfloat16* g = dlogits + (((size_t)b * Dy + y) * Dx + x) * ld + z * ncls;
+    const bool word_ok = ((z * ncls) & 1) == 0 && (ld & 1) == 0;        // 4-byte aligned pair stores
     if (w == 0.f) {
-      for (int k = 0; k < ncls; ++k) g[k] = __float2bfloat16(0.f);
+      if (word_ok) {
+        uint32_t* g2 = reinterpret_cast<uint32_t*>(g);
+        for (int k = 0; k < ncls / 2; ++k) g2[k] = 0u;
+        if (ncls & 1) g[ncls - 1] = __float2bfloat16(0.f);
+      } else {
+        for (int k = 0; k < ncls; ++k) g[k] = __float2bfloat16(0.f);
+      }
       continue;
     }
+    float e[32];                     // ncls <= 32 on this path (host checks); logits stay in registers
     float mx = -INFINITY;
-    for (int k = 0; k < ncls; ++k) mx = fmaxf(mx, lg[k]);
-    float s = 0.f;
-    for (int k = 0; k < ncls; ++k) s += __expf(lg[k] - mx);
-    const float lse = mx + __logf(s);
-    acc += w * (lse - lg[l]);
-    const float wi = w * inv, is = 1.f / s;
-    for (int k = 0; k < ncls; ++k) {
-      const float p = __expf(lg[k] - mx) * is;
-      g[k] = __float2bfloat16(wi * (p - (k == l ? 1.f : 0.f)));
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      e[k] = k < ncls ? __ldg(lg + k) : -INFINITY;
+      mx = fmaxf(mx, e[k]);
+    }
+    float s = 0.f, ll = 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      if (k == l) ll = e[k];
+      e[k] = __expf(e[k] - mx);      // exp(-inf) = 0 beyond ncls
+      s += e[k];
+    }
+    acc += w * (mx + __logf(s) - ll);
+    const float wi = w * inv / s;
+#pragma unroll
+    for (int k = 0; k < 32; k += 2) {
+      if (k < ncls) {
+        const float a0 = wi * e[k] - (k == l ? w * inv : 0.f);
+        const float a1 = wi * e[k + 1] - (k + 1 == l ? w * inv : 0.f);
+        if (word_ok && k + 1 < ncls) {
+          *reinterpret_cast<__nv_bfloat162*>(g + k) = __floats2bfloat162_rn(a0, a1);
+        } else {
+          g[k] = __float2bfloat16(a0);
+          if (k + 1 < ncls) g[k + 1] = __float2bfloat16(a1);
+        }
+      }
     }
   }
   acc = warp_sum(acc);
@@ -431,23 +458,39 @@ dcn_col2im_bwd_kernel(const __nv_bfloat16* __restrict__ dcol, int c_ld, const __
       float* db = dx + img * C + c;
       if (v00) {
         load8(xb + ((size_t)y0 * W + x0) * x_ld, q00);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) atomicAdd(db + ((size_t)y0 * W + x0) * C + j, hy_ * hx_ * d[j]);
+        {
+          float4* q4 = reinterpret_cast<float4*>(db + ((size_t)y0 * W + x0) * C);
+          const float ww = hy_ * hx_;
+          atomicAdd(q4, make_float4(ww * d[0], ww * d[1], ww * d[2], ww * d[3]));
+          atomicAdd(q4 + 1, make_float4(ww * d[4], ww * d[5], ww * d[6], ww * d[7]));
+        }
       }
       if (v01) {
         load8(xb + ((size_t)y0 * W + x1) * x_ld, q01);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) atomicAdd(db + ((size_t)y0 * W + x1) * C + j, hy_ * lx * d[j]);
+        {
+          float4* q4 = reinterpret_cast<float4*>(db + ((size_t)y0 * W + x1) * C);
+          const float ww = hy_ * lx;
+          atomicAdd(q4, make_float4(ww * d[0], ww * d[1], ww * d[2], ww * d[3]));
+          atomicAdd(q4 + 1, make_float4(ww * d[4], ww * d[5], ww * d[6], ww * d[7]));
+        }
       }
       if (v10) {
         load8(xb + ((size_t)y1 * W + x0) * x_ld, q10);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) atomicAdd(db + ((size_t)y1 * W + x0) * C + j, ly * hx_ * d[j]);
+        {
+          float4* q4 = reinterpret_cast<float4*>(db + ((size_t)y1 * W + x0) * C);
+          const float ww = ly * hx_;
+          atomicAdd(q4, make_float4(ww * d[0], ww * d[1], ww * d[2], ww * d[3]));
+          atomicAdd(q4 + 1, make_float4(ww * d[4], ww * d[5], ww * d[6], ww * d[7]));
+        }
       }
       if (v11) {
         load8(xb + ((size_t)y1 * W + x1) * x_ld, q11);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) atomicAdd(db + ((size_t)y1 * W + x1) * C + j, ly * lx * d[j]);
+        {
+          float4* q4 = reinterpret_cast<float4*>(db + ((size_t)y1 * W + x1) * C);
+          const float ww = ly * lx;
+          atomicAdd(q4, make_float4(ww * d[0], ww * d[1], ww * d[2], ww * d[3]));
+          atomicAdd(q4 + 1, make_float4(ww * d[4], ww * d[5], ww * d[6], ww * d[7]));
+        }
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -461,6 +504,48 @@ dcn_col2im_bwd_kernel(const __nv_bfloat16* __restrict__ dcol, int c_ld, const __
   if (lane == 0) {
     doff[(size_t)pix * off_ld + 2 * t] = gy;
     doff[(size_t)pix * off_ld + 2 * t + 1] = gx;
+  }
+}
+
+
+// ---- weight re-pack after an optimizer step ------------------------------------------------------
+// fp32 master weight w[co][ci_total][tap] (nn.Conv2d / nn.Linear layout) ->
+//   fwd  bf16 [Cout][taps][cin_pad]            : w[co][col_lo + ci][t]                 (forward GEMM operand)
+//   bwd  bf16 [Cin][taps][cout_pad]  (mode 0)  : scale[co] * w[co][col_lo + ci][taps-1-t]  (data-gradient operand)
+//        bf16 [taps][Cin][cout_pad]  (mode 1)  : scale[co] * w[co][col_lo + ci][t]      (grouped 1x1 view, K = (tap, ci))
+// zero padded; one launch per layer instead of a dozen small tensor ops.
+__global__ void __launch_bounds__(256)
+pack_conv_weights_kernel(const float* __restrict__ w, int Cout, int cin_total, int taps, int col_lo, int Cin,
+                         const float* __restrict__ scale, __nv_bfloat16* __restrict__ fwd, int cin_pad,
+                         __nv_bfloat16* __restrict__ bwd, int cout_pad, int bwd_mode) {
+  const long nf = fwd != nullptr ? (long)Cout * taps * cin_pad : 0;
+  const long nb = bwd != nullptr ? (long)Cin * taps * cout_pad : 0;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nf + nb; i += (long)gridDim.x * blockDim.x) {
+    if (i < nf) {
+      const int ci = (int)(i % cin_pad);
+      const int t = (int)((i / cin_pad) % taps);
+      const int co = (int)(i / ((long)cin_pad * taps));
+      const float v = ci < Cin ? w[((size_t)co * cin_total + col_lo + ci) * taps + t] : 0.f;
+      fwd[i] = __float2bfloat16(v);
+    } else {
+      const long j = i - nf;
+      const int co = (int)(j % cout_pad);
+      int ci, t;
+      if (bwd_mode == 0) {
+        t = (int)((j / cout_pad) % taps);
+        ci = (int)(j / ((long)cout_pad * taps));
+      } else {
+        ci = (int)((j / cout_pad) % Cin);
+        t = (int)(j / ((long)cout_pad * Cin));
+      }
+      float v = 0.f;
+      if (co < Cout) {
+        const int ts = bwd_mode == 0 ? taps - 1 - t : t;
+        v = w[((size_t)co * cin_total + col_lo + ci) * taps + ts];
+        if (scale != nullptr) v *= scale[co];
+      }
+      bwd[j] = __float2bfloat16(v);
+    }
   }
 }
 
@@ -497,7 +582,7 @@ extern "C" int dhd_act_bwd(const void* dy, int dy_ld, int dy_coff, const void* y
                                           (const __nv_bfloat16*)add, add_ld, add_coff);
   DHD_CUDA_LAUNCH_CHECK("act_bwd");
   if (colsum != nullptr) {
-    colsum_reduce_kernel<<<(2 * C + 255) / 256, 256, 0, st>>>(workspace, nblocks, 2 * C, colsum);
+    colsum_reduce_kernel<<<(2 * C * 32 + 255) / 256, 256, 0, st>>>(workspace, nblocks, 2 * C, colsum);
     DHD_CUDA_LAUNCH_CHECK("colsum_reduce");
   }
   return DHD_OK;
@@ -507,7 +592,7 @@ extern "C" int dhd_occ_ce_loss(const float* logits, const uint8_t* labels, const
                                const float* class_weight, int ncls, int ignore_index, int B, int Dx, int Dy, int Dz,
                                float loss_weight, float* loss_and_norm, void* dlogits, int dl_ld, void* stream) {
   DHD_REQUIRE(logits && labels && loss_and_norm && dlogits, "null pointer");
-  DHD_REQUIRE(B > 0 && Dx > 0 && Dy > 0 && Dz > 0 && ncls > 0 && ncls <= 64, "bad shape");
+  DHD_REQUIRE(B > 0 && Dx > 0 && Dy > 0 && Dz > 0 && ncls > 0 && ncls <= 32, "bad shape (ncls <= 32)");
   DHD_REQUIRE(dl_ld >= Dz * ncls, "dlogits rows are too short");
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = cudaMemsetAsync(loss_and_norm, 0, 2 * sizeof(float), st);
@@ -623,5 +708,20 @@ extern "C" int dhd_dcn_col2im_bwd(const void* dcol, int col_ld, const void* x, i
       (const __nv_bfloat16*)dcol, col_ld, (const __nv_bfloat16*)x, x_ld, x_coff, C, N, H, W, offset, off_ld, ksize, pad,
       dilation, groups, dx, doff);
   DHD_CUDA_LAUNCH_CHECK("dcn_col2im_bwd");
+  return DHD_OK;
+}
+
+extern "C" int dhd_pack_conv_weights(const float* w, int Cout, int cin_total, int taps, int col_lo, int Cin,
+                                     const float* scale, void* fwd, int cin_pad, void* bwd, int cout_pad, int bwd_mode,
+                                     void* stream) {
+  DHD_REQUIRE(w != nullptr && (fwd != nullptr || bwd != nullptr), "null pointer");
+  DHD_REQUIRE(Cout > 0 && Cin > 0 && taps >= 1 && col_lo >= 0 && col_lo + Cin <= cin_total, "bad shape");
+  DHD_REQUIRE(cin_pad >= Cin && cout_pad >= Cout && (bwd_mode == 0 || bwd_mode == 1), "bad padding / mode");
+  const long n = (fwd ? (long)Cout * taps * cin_pad : 0) + (bwd ? (long)Cin * taps * cout_pad : 0);
+  const int blocks = (int)min((n + 255) / 256, (long)sm_count() * 8);
+  pack_conv_weights_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, Cout, cin_total, taps, col_lo, Cin, scale,
+                                                                    (__nv_bfloat16*)fwd, cin_pad, (__nv_bfloat16*)bwd,
+                                                                    cout_pad, bwd_mode);
+  DHD_CUDA_LAUNCH_CHECK("pack_conv_weights");
   return DHD_OK;
 }

@@ -73,26 +73,29 @@ class _TrainConv:
         self.refresh()
 
     def refresh(self):
-        w = self.weight.detach().float()
-        if w.dim() == 2:
-            w = w[:, :, None, None]
-        if self.cols is not None:
-            w = w[:, self.cols[0]:self.cols[1]]
+        """Re-pack the bf16 GEMM operands from the fp32 master weight: ONE dhd_pack_conv_weights launch.
+        BatchNorm is frozen, so its folded scale is computed once; the folded bias is refreshed only where
+        a trainable conv bias sits under the BatchNorm."""
+        w = self.weight
         dev = w.device
-        if self.bn is not None:
-            s, b = fold_bn(self.bn, self.bias_p)
-            self.scale, self.bias = s.to(dev), b.to(dev)
+        taps = self.ksize * self.ksize
+        cin_total = w.shape[1]
+        if not hasattr(self, 'w_fwd'):
+            if self.bn is not None:
+                s, b = fold_bn(self.bn, None)
+                self.scale, self._bn_bias = s.to(dev), b.to(dev)
+            else:
+                self.scale = None
+            self.w_fwd = torch.empty(self.Cout, taps, 1, self.cin_pad, dtype=torch.bfloat16, device=dev)
+            self.w_bwd = torch.empty(self.Cin, taps, 1, self.cout_pad, dtype=torch.bfloat16, device=dev)
+        if self.bn is None:
+            self.bias = self.bias_p.detach() if self.bias_p is not None else None     # shares the parameter's storage
         else:
-            self.scale = None
-            self.bias = self.bias_p.detach().float().contiguous() if self.bias_p is not None else None
-        wf = w
-        if self.cin_pad != self.Cin:
-            wf = torch.nn.functional.pad(w, (0, 0, 0, 0, 0, self.cin_pad - self.Cin))
-        self.w_fwd = D.pack_weight(wf, 1)
-        wb = w if self.scale is None else w * self.scale.view(-1, 1, 1, 1)     # d(scale*conv)/dx
-        if self.cout_pad != self.Cout:
-            wb = torch.nn.functional.pad(wb, (0, 0, 0, 0, 0, 0, 0, self.cout_pad - self.Cout))
-        self.w_bwd = D.pack_weight_dgrad(wb, 1)
+            self.bias = self._bn_bias if self.bias_p is None else self._bn_bias + self.bias_p.detach() * self.scale
+        col_lo = 0 if self.cols is None else self.cols[0]
+        _lib.check(_lib.load().dhd_pack_conv_weights(_p(w.detach()), self.Cout, cin_total, taps, col_lo, self.Cin,
+                                                     _p(self.scale), _p(self.w_fwd), self.cin_pad, _p(self.w_bwd),
+                                                     self.cout_pad, 0, _stream()), 'pack_conv_weights')
 
     def forward(self, x, segs, **kw):
         return D.conv2d(x, self.w_fwd, self.Cout, ksize=self.ksize, dilation=self.dilation, precision='bf16',
@@ -408,19 +411,24 @@ class HeightNetTrainer:
             c.refresh()
         f = lambda t: t.detach().float().contiguous()
         net, a, dc = self.net, self.aspp, self.dcn
-        self.bn_scale, self.bn_shift = fold_bn(net.bn)
-        s5, b5 = fold_bn(a.global_avg_pool[2])
-        self.s5, self.b5 = s5, b5
-        self.gap_ws = f(a.global_avg_pool[1].weight.flatten(1) * s5[:, None])
-        s1, _ = fold_bn(a.bn1)
-        self.s1 = s1
-        self.w5s = f(a.conv1.weight.detach()[:, 4 * self.mid:].flatten(1) * s1[:, None])
+        if not hasattr(self, 's5'):                          # frozen BatchNorm folds: once
+            self.bn_scale, self.bn_shift = fold_bn(net.bn)
+            self.s5, self.b5 = fold_bn(a.global_avg_pool[2])
+            self.s1, _ = fold_bn(a.bn1)
+            cg, k = self.C // self.groups, self.k
+            self.dcn_wf = [torch.empty(cg, k * k * cg, 1, 1, dtype=torch.bfloat16, device=self.device).view(cg, 1, 1, k * k * cg)
+                           for _ in range(self.groups)]
+            self.dcn_wb = [torch.empty(k * k * cg, 1, 1, cg, dtype=torch.bfloat16, device=self.device)
+                           for _ in range(self.groups)]
+        self.gap_ws = f(a.global_avg_pool[1].weight.flatten(1) * self.s5[:, None])
+        self.w5s = f(a.conv1.weight.detach()[:, 4 * self.mid:].flatten(1) * self.s1[:, None])
         cg, k = self.C // self.groups, self.k
-        self.dcn_wf, self.dcn_wb = [], []
+        lib, wd = _lib.load(), dc.weight.detach()
         for g in range(self.groups):
-            wg = dc.weight.detach().float()[g * cg:(g + 1) * cg].permute(0, 2, 3, 1).reshape(cg, k * k * cg)
-            self.dcn_wf.append(D.pack_weight(wg, 1))
-            self.dcn_wb.append(D.pack_weight_dgrad(wg, 1))
+            # group g as a 1x1 layer over K = (tap, channel): [co][tap][ci] forward, [tap][ci][co] data gradient
+            _lib.check(lib.dhd_pack_conv_weights(ctypes.c_void_p(wd.data_ptr() + g * cg * cg * k * k * 4), cg, cg, k * k,
+                                                 0, cg, None, _p(self.dcn_wf[g]), cg, _p(self.dcn_wb[g]), cg, 1,
+                                                 _stream()), 'pack_conv_weights(dcn)')
 
     def _act(self, name, N, H, W, C):
         key = (name, N, H, W, C)

@@ -273,6 +273,14 @@ int dhd_dcn_col2im_bwd(const void* dcol, int col_ld, const void* x, int x_ld, in
                        int W, const float* offset, int off_ld, int ksize, int pad, int dilation, int groups,
                        float* dx, float* doff, void* stream);
 
+/* re-pack one layer's fp32 master weight w[Cout][cin_total][taps] (input columns [col_lo, col_lo+Cin)) after
+ * an optimizer step: fwd = bf16 [Cout][taps][cin_pad] (dhd_conv2d_fwd operand), bwd = the data-gradient operand
+ * with scale[co] folded in: mode 0 [Cin][mirrored tap][cout_pad], mode 1 [tap][Cin][cout_pad] (grouped 1x1 view
+ * of the DCN weight).  Either output may be NULL. */
+int dhd_pack_conv_weights(const float* w, int Cout, int cin_total, int taps, int col_lo, int Cin,
+                          const float* scale, void* fwd, int cin_pad, void* bwd, int cout_pad, int bwd_mode,
+                          void* stream);
+
 /* ---- streaming layout / elementwise helpers of the dense path (csrc/layout.cu) -----------
  * "split-bf16 NHWC": bf16, `ld` channels per pixel, logical channel c of part p at
  * coff + p*part_stride + c; the fp32 value is the sum of the parts. */
