@@ -12,20 +12,22 @@
 // borders are the TMA box coordinates / OOB zero fill, as in the forward kernel.
 //
 // One CTA owns (128 output channels) x (<=256 input channels) x (one tap) x (a slice of the pixel
-// tiles); the fp32 accumulator lives in TMEM for the whole slice, is written once to a partial
+// tiles, streamed 64 pixels per stage through a 4-stage TMA ring); the fp32 accumulator lives in TMEM for the whole slice, is written once to a partial
 // buffer, and a second small kernel sums the slices in a fixed order (deterministic, no atomics).
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
 namespace dhd {
 
-constexpr int kWgBoxBytes = 128 * 128;            // one {64 ch x 128 px} bf16 box
-constexpr int kWgStages = 2;
+constexpr int kWgPix = 64;                        // pixels (= GEMM K) per pipeline stage: half of a 128-pixel tile box
+constexpr int kWgBoxBytes = kWgPix * 128;         // one {64 ch x 64 px} bf16 box
+constexpr int kWgStages = 4;
 constexpr int kWgThreads = 128;
 
 struct WgradParams {
   dhd_wgrad_desc d;
-  int tiles_w, tiles_h, tiles;      // pixel tiles (128-px boxes) per image row / column / total
+  int sbw, sbh;                     // stage box = half of the (bw x bh) tile box: sbw * sbh == 64 pixels
+  int tiles_w, tiles_h, tiles;      // stage boxes per image row / column / total
   int co_blocks, ci_blocks, ncols;  // ncols = input channels per CTA (<= 256, multiple of 64)
   int splits;
 };
@@ -96,8 +98,8 @@ conv_wgrad_kernel(const __grid_constant__ WgradMaps M, const __grid_constant__ W
     t /= P.tiles_w;
     const int ty = t % P.tiles_h;
     img = t / P.tiles_h;
-    x0 = tx * d.bw;
-    y0 = ty * d.bh;
+    x0 = tx * P.sbw;
+    y0 = ty * P.sbh;
   };
 
   if (warp == 0) {
@@ -130,7 +132,7 @@ conv_wgrad_kernel(const __grid_constant__ WgradMaps M, const __grid_constant__ W
         tc_fence_after();
         const uint32_t sa = base + s * stage_bytes, sb = sa + 2 * kWgBoxBytes;
 #pragma unroll
-        for (int k = 0; k < 128 / kUmmaK; ++k) {
+        for (int k = 0; k < kWgPix / kUmmaK; ++k) {
           const uint64_t da = umma_desc_mn_sw128(sa + k * 2048, kWgBoxBytes, 1024);
           const uint64_t db = umma_desc_mn_sw128(sb + k * 2048, kWgBoxBytes, 1024);
           umma_bf16(tmem_base, da, db, idesc, (it == 0 && k == 0) ? 0u : 1u);
@@ -190,17 +192,20 @@ void* conv_encode_fn();   // conv_igemm.cu
 
 static void wgrad_plan(const dhd_wgrad_desc* d, WgradParams* P) {
   P->d = *d;
-  P->tiles_w = (d->W + d->bw - 1) / d->bw;
-  P->tiles_h = (d->H + d->bh - 1) / d->bh;
+  P->sbw = d->bh >= 2 ? d->bw : d->bw / 2;
+  P->sbh = d->bh >= 2 ? d->bh / 2 : 1;
+  P->tiles_w = (d->W + P->sbw - 1) / P->sbw;
+  P->tiles_h = (d->H + P->sbh - 1) / P->sbh;
   P->tiles = P->tiles_w * P->tiles_h * d->N;
   P->co_blocks = (d->Cout + 127) / 128;
   P->ncols = d->Cin % 256 == 0 ? 256 : (d->Cin % 128 == 0 ? 128 : 64);
   if (P->ncols > d->Cin) P->ncols = d->Cin;
   P->ci_blocks = d->Cin / P->ncols;
   const int items = P->co_blocks * d->taps * P->ci_blocks;
-  int splits = (2 * sm_count() + items - 1) / items;
+  // one CTA per SM (192 KB of shared memory each): as many slices as fill ONE wave, never a partial second one
+  int splits = sm_count() / items;
   if (splits > P->tiles) splits = P->tiles;
-  if (splits > 64) splits = 64;
+  if (splits > 128) splits = 128;
   if (splits < 1) splits = 1;
   P->splits = splits;
 }
@@ -235,7 +240,7 @@ extern "C" int dhd_conv2d_wgrad(const dhd_wgrad_desc* d, void* stream) {
   WgradParams P;
   wgrad_plan(d, &P);
   WgradMaps maps;
-  cuuint32_t box[4] = {64, (cuuint32_t)d->bw, (cuuint32_t)d->bh, 1};
+  cuuint32_t box[4] = {64, (cuuint32_t)P.sbw, (cuuint32_t)P.sbh, 1};
   cuuint32_t es[4] = {1, 1, 1, 1};
   {
     // the channel extent stops at the layer's last channel: a 64-channel box past it reads zeros

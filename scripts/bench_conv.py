@@ -19,7 +19,33 @@ SHAPES = [  # name, N, Cin, Cout, H, W, ksize, dilation
 ]
 
 
+def wgrad():
+    """weight-gradient kernel (dhd_conv2d_wgrad) on the same shapes"""
+    for name, N, Cin, Cout, H, W, k, dil in SHAPES:
+        x = D.Act.empty(N, H, W, Cin, 1, 'cuda')
+        x.data.normal_()
+        dy = D.Act.empty(N, H, W, (Cout + 63) // 64 * 64, 1, 'cuda')
+        dy.data.normal_()
+        out = torch.empty(Cout, k * k, Cin, device='cuda')
+        run = lambda: D.conv2d_wgrad(x, dy, Cout, ksize=k, dilation=dil, out=out)
+        for _ in range(3):
+            run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        it = 20
+        e0.record()
+        for _ in range(it):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / it
+        flops = 2.0 * N * H * W * Cout * Cin * k * k
+        print('%-40s %-7s %8.1f us  %7.1f TFLOP/s algorithmic' % (name, 'wgrad', ms * 1e3, flops / ms / 1e9), flush=True)
+
+
 def main():
+    if sys.argv[1:] == ['wgrad']:
+        return wgrad()
     precs = sys.argv[1:] or ['bf16', 'bf16x3', 'fp32']
     for name, N, Cin, Cout, H, W, k, dil in SHAPES:
         for prec in precs:
