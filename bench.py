@@ -104,7 +104,7 @@ def run_ours(args):
     import torch.distributed as dist
     from dhd_b200 import _lib
     from dhd_b200.pipeline import HotPathStep, algorithmic_bytes, dense_flops
-    from oracle import mghs_oracle as O   # synthetic camera rig + the cpu_baseline leg only
+    from dhd_b200 import synth as O        # the product arm never touches oracle/
 
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))

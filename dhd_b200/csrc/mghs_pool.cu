@@ -853,7 +853,7 @@ struct PoolLane {          // per-lane issue state for the zero-run copies
 };
 
 template <bool HINT, int MINB>
-__global__ void __launch_bounds__(128, MINB) mghs_pool_stream_kernel(const PoolParams P, int zero_bytes, int windows) {
+__global__ void __launch_bounds__(128, MINB) mghs_pool_stream_kernel(const PoolParams P, int zero_bytes, int windows, int prefetch) {
   extern __shared__ __align__(128) uint8_t smem_pool[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int wpb = blockDim.x >> 5;
@@ -904,14 +904,30 @@ __global__ void __launch_bounds__(128, MINB) mghs_pool_stream_kernel(const PoolP
   };
   int buf = 0;
   uint32_t touched0 = 0, touched1 = 0;
+  // chunk ids are requested two chunks ahead and the chunk table entry one chunk ahead, so neither the
+  // atomic nor the table load sits on the critical path of a chunk
+  int2 pt0 = make_int2(0, 0), pt1 = make_int2(0, 0);
+  auto load_table = [&](int ch) -> bool {
+    if (ch >= n_iter) return false;
+    const int cidx = (ch % windows) * per_win + ch / windows;
+    if (cidx >= P.nch) return false;
+    pt0 = __ldg(P.chunks + cidx);
+    pt1 = __ldg(P.chunks + cidx + 1);
+    return true;
+  };
+  int cur = __shfl_sync(kFull, fetch(), 0);
+  bool pvalid = load_table(cur);
   int next_raw = fetch();
   for (;;) {
-    const int ch = __shfl_sync(kFull, next_raw, 0);
-    if (ch >= n_iter) break;
+    if (cur >= n_iter) break;
+    if (!prefetch) pvalid = load_table(cur);      // A/B switch (DHD_POOL_PREFETCH=0): table on the critical path
+    const int2 t0 = pt0, t1 = pt1;
+    const bool valid = pvalid;
+    const int nxt = __shfl_sync(kFull, next_raw, 0);
+    if (prefetch) pvalid = load_table(nxt);
     next_raw = fetch();
-    const int cidx = (ch % windows) * per_win + ch / windows;
-    if (cidx >= P.nch) continue;
-    const int2 t0 = __ldg(P.chunks + cidx), t1 = __ldg(P.chunks + cidx + 1);
+    cur = nxt;
+    if (!valid) continue;
     const int cell_lo = t0.x, cell_hi = t1.x, e_lo = t0.y, e_hi = P.probe == 1 ? t0.y : t1.y;
     int pos = cell_lo;                       // every cell < pos of this chunk has been written
     int cur_cell = -1;
@@ -1435,7 +1451,8 @@ extern "C" int dhd_mghs_pool_fwd(const dhd_mghs_cfg* cfg, const float* depth, co
     const size_t smem = (size_t)zero_bytes + (size_t)wpb * 2 * P.nplanes * 256;
     DHD_REQUIRE(smem <= 227 * 1024, "pool column buffers do not fit in shared memory");
     const int minb = tuning("DHD_POOL_MINB", 4) >= 5 ? 5 : 4;
-    void (*kern)(const PoolParams, int, int) =
+    const int prefetch = tuning("DHD_POOL_PREFETCH", 1);
+    void (*kern)(const PoolParams, int, int, int) =
         hint ? (minb == 5 ? mghs_pool_stream_kernel<true, 5> : mghs_pool_stream_kernel<true, 4>)
              : (minb == 5 ? mghs_pool_stream_kernel<false, 5> : mghs_pool_stream_kernel<false, 4>);
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1443,7 +1460,7 @@ extern "C" int dhd_mghs_pool_fwd(const dhd_mghs_cfg* cfg, const float* depth, co
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem);
     const int per_sm = max(1, min(cap, occ));
     const int grid = min((P.nch + wpb - 1) / wpb, sm_count() * per_sm);
-    kern<<<grid, threads, smem, st>>>(P, zero_bytes, windows);
+    kern<<<grid, threads, smem, st>>>(P, zero_bytes, windows, prefetch);
     DHD_CUDA_LAUNCH_CHECK("mghs_pool_stream");
   } else if (layout == DHD_LAYOUT_NHWC && tuning("DHD_POOL_V", 4) == 3) {
     for (int p = 0; p < cfg->n_pass; ++p)

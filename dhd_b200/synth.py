@@ -1,0 +1,51 @@
+"""Synthetic workload of the benchmark: the DHD-S shapes of
+projects/configs/DHD/DHD-S.py:20-105 and a seeded 6-camera surround rig with nuScenes-like intrinsics and
+the resize + crop augmentation of the reference's data pipeline (datasets/pipelines/loading.py:55-94).
+Product-side generator: bench.py's own arm and the pipeline use this one (the CPU oracle keeps an
+independent copy; tests/test_oracle.py checks the two agree)."""
+import math
+
+import torch
+
+BEV_GRID = {'x': [-40, 40, 0.4], 'y': [-40, 40, 0.4], 'z': [-1, 5.4, 6.4]}     # lss_heightmap.py:425-431
+
+DHD_S = dict(
+    input_size=(256, 704), downsample=16, depth=[1.0, 45.0, 1.0], C=64, C_in=256,
+    height_range=[round(-1.0 + 0.1 * i, 1) for i in range(65)],
+    mask_range=[-1.0, 0.6, 2.2, 5.4],
+    mask_grids=[
+        {'x': [-40, 40, 0.4], 'y': [-40, 40, 0.4], 'z': [-1, 0.6, 0.4]},
+        {'x': [-40, 40, 0.4], 'y': [-40, 40, 0.4], 'z': [0.6, 2.2, 0.4]},
+        {'x': [-40, 40, 0.4], 'y': [-40, 40, 0.4], 'z': [2.2, 5.4, 0.4]},
+    ],
+    bev_grid=BEV_GRID, ncams=6,
+)
+
+
+def synthetic_rig(B, ncams=6, input_size=(256, 704), src_size=(900, 1600), seed=0, flip_bda=False):
+    """(sensor2ego (B,N,4,4), ego2global, cam2img (B,N,3,3), post_rot, post_tran (B,N,3), bda (B,3,3))."""
+    g = torch.Generator().manual_seed(seed)
+    yaws = [55.0, 0.0, -55.0, 110.0, 180.0, -110.0][:ncams]
+    base = torch.tensor([[0.0, 0.0, 1.0], [-1.0, 0.0, 0.0], [0.0, -1.0, 0.0]])
+    s2e = torch.zeros(B, ncams, 4, 4)
+    for n, yaw in enumerate(yaws):
+        a = math.radians(yaw)
+        rz = torch.tensor([[math.cos(a), -math.sin(a), 0.0], [math.sin(a), math.cos(a), 0.0], [0.0, 0.0, 1.0]])
+        s2e[:, n, :3, :3] = rz @ base
+        s2e[:, n, :3, 3] = torch.tensor([1.5 * math.cos(a), 1.5 * math.sin(a), 1.5])
+        s2e[:, n, 3, 3] = 1.0
+    K = torch.tensor([[1266.0, 0.0, 816.0], [0.0, 1266.0, 491.0], [0.0, 0.0, 1.0]]).expand(B, ncams, 3, 3).clone()
+    scale = input_size[1] / src_size[1]
+    s = scale + 0.01 * torch.rand(B, ncams, generator=g)
+    pr = torch.zeros(B, ncams, 3, 3)
+    pr[..., 0, 0] = s
+    pr[..., 1, 1] = s
+    pr[..., 2, 2] = 1.0
+    pt = torch.zeros(B, ncams, 3)
+    pt[..., 1] = -(src_size[0] * scale - input_size[0])
+    bda = torch.eye(3).expand(B, 3, 3).clone()
+    if flip_bda:
+        bda[1::2, 0, 0] = -1.0
+        bda[1::2, 1, 1] = -1.0
+    e2g = torch.eye(4).expand(B, ncams, 4, 4).clone()
+    return s2e, e2g, K, pr, pt, bda

@@ -8,7 +8,7 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 from dhd_b200.pipeline import TrainStep  # noqa: E402
-from oracle import mghs_oracle as O  # noqa: E402
+from dhd_b200 import synth as O  # noqa: E402
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 cfg, B = O.DHD_S, 4

@@ -115,3 +115,15 @@ def test_oracle_vs_live_reference_view_transform():
     key_r = r[0].long() * (1 << 32) + r[1].long()
     key_o = o[0].long() * (1 << 32) + o[1].long()
     assert torch.equal(key_r.sort().values, key_o.sort().values)
+
+
+def test_product_synthetic_workload_matches_the_oracle_copy():
+    """bench.py's own arm builds its inputs with dhd_b200.synth (it must not import oracle/); the oracle
+    keeps an independent copy of the same rig -- they have to describe the same workload."""
+    from dhd_b200 import synth
+    assert synth.DHD_S == O.DHD_S
+    for seed, flip in ((0, False), (103, True)):
+        a = synth.synthetic_rig(3, 6, (256, 704), seed=seed, flip_bda=flip)
+        b = O.synthetic_rig(3, 6, (256, 704), seed=seed, flip_bda=flip)
+        for x, y in zip(a, b):
+            assert torch.equal(x, y)
