@@ -1,5 +1,6 @@
 set -x
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q 2>&1 | tail -15 | tee gpurun_out/r01_pytest_gpu.log
-python scripts/bench_conv.py bf16 fp32 2>&1 | tee gpurun_out/r01_bench_conv_v3.txt
-python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/r01_bench_full.json 2> gpurun_out/r01_bench_full.err; tail -3 gpurun_out/r01_bench_full.err; cat gpurun_out/r01_bench_full.json
+ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/r01_launches_infer.csv python bench.py --steps 2 --warmup 3 --no-graph --no-cpu-baseline --no-train > gpurun_out/r01_ncu_bench.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:conv_wgrad -s 4 -c 1 -o gpurun_out/r01_wgrad python scripts/bench_conv.py wgrad > gpurun_out/r01_ncu_wgrad.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:conv_igemm2 -s 16 -c 1 -o gpurun_out/r01_conv3x3 python scripts/bench_conv.py bf16 > gpurun_out/r01_ncu_conv.log 2>&1
+ls -la gpurun_out | tail -8
