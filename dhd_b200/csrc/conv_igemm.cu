@@ -357,7 +357,16 @@ extern "C" int dhd_conv2d_fwd(const dhd_conv_desc* d, void* stream) {
     DHD_REQUIRE(d->Cout % 32 == 0 && ((uintptr_t)d->residual & 15) == 0 && d->res_sN % 4 == 0 &&
                     d->res_sY % 4 == 0 && d->res_sX % 4 == 0,
                 "residual needs Cout % 32 == 0 and 16-byte aligned rows");
+  DHD_REQUIRE(d->stride == 0 || d->stride == 1 || d->stride == 2, "stride must be 1 or 2");
+  if (d->stride == 2) {
+    DHD_REQUIRE(d->in_H > 0 && d->in_W > 0 && d->H == (d->in_H + 1) / 2 && d->W == (d->in_W + 1) / 2,
+                "stride 2: output size must be ceil(input / 2) (3x3, pad 1)");
+    DHD_REQUIRE(d->bw * 2 <= 256 && d->bh * 2 <= 256, "stride 2: tile box too large for the strided TMA box");
+  }
+  bool strided_out = false;
+  for (int s = 0; s < d->n_seg; ++s) strided_out |= d->seg[s].b16_sX != 0;
   if (conv_version() != 1) return conv2_launch(d, (void*)enc, stream);
+  DHD_REQUIRE(d->stride != 2 && !strided_out, "stride 2 / strided outputs need the second-generation kernel");
 
   CUtensorMap map_a, map_b;
   {

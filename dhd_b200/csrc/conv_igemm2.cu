@@ -57,8 +57,10 @@ __device__ __forceinline__ float act2(float v, int act) {
 }
 
 __device__ __forceinline__ bool tap_dead2(const dhd_conv_desc& d, int t, int x0, int y0) {
-  const int xs = x0 + d.tap_dx[t], ys = y0 + d.tap_dy[t];
-  return xs >= d.W || xs + d.bw <= 0 || ys >= d.H || ys + d.bh <= 0;
+  const int st = d.stride > 1 ? d.stride : 1;
+  const int iw = d.stride > 1 ? d.in_W : d.W, ih = d.stride > 1 ? d.in_H : d.H;
+  const int xs = x0 * st + d.tap_dx[t], ys = y0 * st + d.tap_dy[t];
+  return xs >= iw || xs + d.bw * st <= 0 || ys >= ih || ys + d.bh * st <= 0;
 }
 
 template <int NT>
@@ -126,6 +128,7 @@ conv_igemm2_kernel(const __grid_constant__ Conv2Maps M, const __grid_constant__ 
     // ===================================================== TMA producer
     if (lane == 0) {
       int it = 0;
+      const int in_stride = d.stride > 1 ? d.stride : 1;     // the tensor map strides the box (elementStrides)
       for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
         int img, x0, y0, n0;
         decode(tile, img, x0, y0, n0);
@@ -139,7 +142,7 @@ conv_igemm2_kernel(const __grid_constant__ Conv2Maps M, const __grid_constant__ 
               const uint32_t sa = base + s * C::kStageBytes, sb = sa + kA2Bytes;
               mbar_expect_tx(full_bar(s), C::kStageBytes);
               tma_load_4d(sa, &M.a, full_bar(s), d.in_coff + d.term_a[e] * d.in_part_stride + kc * kK2,
-                          x0 + d.tap_dx[t], y0 + d.tap_dy[t], img);
+                          x0 * in_stride + d.tap_dx[t], y0 * in_stride + d.tap_dy[t], img);
               tma_load_2d(sb, &M.b, full_bar(s), (t * d.w_parts + d.term_b[e]) * d.Cin + kc * kK2, n0);
             }
           }
@@ -365,8 +368,10 @@ conv_igemm2_kernel(const __grid_constant__ Conv2Maps M, const __grid_constant__ 
                 }
                 ++nstore;
               } else if (valid) {
-                __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(sg.out_b16) +
-                                    ((size_t)img * d.H * d.W + (size_t)py * d.W + px) * sg.b16_ld + sg.b16_coff +
+                const size_t pixoff = sg.b16_sX != 0
+                                          ? (size_t)img * sg.b16_sN + (size_t)py * sg.b16_sY + (size_t)px * sg.b16_sX
+                                          : ((size_t)img * d.H * d.W + (size_t)py * d.W + px) * sg.b16_ld;
+                __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(sg.out_b16) + pixoff + sg.b16_coff +
                                     (size_t)p * sg.b16_part_stride;
                 const __nv_bfloat16* hs = reinterpret_cast<const __nv_bfloat16*>(q);
 #pragma unroll
@@ -426,11 +431,13 @@ int conv2_launch(const dhd_conv_desc* d, void* encode, void* stream) {
   P.d = *d;
   const int NT = d->Cout > 128 ? 256 : 128;
   {
-    cuuint64_t dims[4] = {(cuuint64_t)d->in_ld, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
-    cuuint64_t strides[3] = {(cuuint64_t)d->in_ld * 2, (cuuint64_t)d->W * d->in_ld * 2,
-                             (cuuint64_t)d->H * d->W * d->in_ld * 2};
-    cuuint32_t box[4] = {(cuuint32_t)kK2, (cuuint32_t)d->bw, (cuuint32_t)d->bh, 1};
-    cuuint32_t es[4] = {1, 1, 1, 1};
+    const int st = d->stride > 1 ? d->stride : 1;
+    const cuuint64_t iw = st > 1 ? d->in_W : d->W, ih = st > 1 ? d->in_H : d->H;
+    cuuint64_t dims[4] = {(cuuint64_t)d->in_ld, iw, ih, (cuuint64_t)d->N};
+    cuuint64_t strides[3] = {(cuuint64_t)d->in_ld * 2, iw * d->in_ld * 2, ih * iw * d->in_ld * 2};
+    // stride-2 layers: the box spans 2*bw x 2*bh input pixels and the TMA unit keeps every 2nd one
+    cuuint32_t box[4] = {(cuuint32_t)kK2, (cuuint32_t)(d->bw * st), (cuuint32_t)(d->bh * st), 1};
+    cuuint32_t es[4] = {1, (cuuint32_t)st, (cuuint32_t)st, 1};
     CUresult r = enc(&maps.a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)d->in, dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -458,12 +465,17 @@ int conv2_launch(const dhd_conv_desc* d, void* encode, void* stream) {
     if (sg.c_lo % 32 != 0) continue;
     cuuint32_t es[4] = {1, 1, 1, 1};
     if (sg.out_b16 != nullptr && sg.b16_ld % 8 == 0 && sg.b16_coff % 8 == 0 && sg.b16_part_stride % 8 == 0 &&
-        ((uintptr_t)sg.out_b16 & 15) == 0) {
+        sg.b16_sX % 8 == 0 && sg.b16_sY % 8 == 0 && sg.b16_sN % 8 == 0 && ((uintptr_t)sg.out_b16 & 15) == 0) {
       bool ok = true;
       for (int p = 0; p < sg.b16_parts && ok; ++p) {
         cuuint64_t dims[4] = {nch, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
         cuuint64_t strides[3] = {(cuuint64_t)sg.b16_ld * 2, (cuuint64_t)d->W * sg.b16_ld * 2,
                                  (cuuint64_t)d->H * d->W * sg.b16_ld * 2};
+        if (sg.b16_sX != 0) {            // strided pixel view
+          strides[0] = (cuuint64_t)sg.b16_sX * 2;
+          strides[1] = (cuuint64_t)sg.b16_sY * 2;
+          strides[2] = (cuuint64_t)sg.b16_sN * 2;
+        }
         cuuint32_t box[4] = {32, (cuuint32_t)d->bw, (cuuint32_t)d->bh, 1};   // 64-byte rows
         void* basep = (char*)sg.out_b16 + ((size_t)sg.b16_coff + (size_t)p * sg.b16_part_stride) * 2;
         ok = enc(&maps.o16[s][p], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, basep, dims, strides, box, es,

@@ -285,6 +285,65 @@ dcn_im2col8_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int x_coff, in
   }
 }
 
+// ---- encoder helpers (backbones/unet.py:65-74 MaxPool2d(2); necks/lss_fpn.py:27-28, 41-42 bilinear
+// Upsample(align_corners=True)): bf16 NHWC in, bf16 NHWC out (possibly a channel slice of a wider buffer), 8 channels
+// per thread.
+__global__ void __launch_bounds__(256)
+maxpool2_kernel(const __nv_bfloat16* __restrict__ in, int in_ld, int in_coff, int in_ps, int N, int H, int W, int C,
+                __nv_bfloat16* __restrict__ out, int o_ld, int o_coff, int o_ps, int parts) {
+  const int oH = H / 2, oW = W / 2, cg = C / 8;
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)N * oH * oW * cg) return;
+  const int c = (int)(i % cg) * 8;
+  long p = i / cg;
+  const int ox = (int)(p % oW);
+  p /= oW;
+  const int oy = (int)(p % oH), n = (int)(p / oH);
+  float m[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+      float v[8];
+      load_parts8(in + (((size_t)n * H + 2 * oy + dy) * W + 2 * ox + dx) * in_ld + in_coff + c, parts, in_ps, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], v[j]);
+    }
+  store_parts8(out + (((size_t)n * oH + oy) * oW + ox) * o_ld + o_coff + c, m, parts, o_ps);
+}
+
+__global__ void __launch_bounds__(256)
+upsample_bilinear_kernel(const __nv_bfloat16* __restrict__ in, int in_ld, int in_coff, int in_ps, int N, int H, int W,
+                         int C, int oH, int oW, __nv_bfloat16* __restrict__ out, int o_ld, int o_coff, int o_ps,
+                         int parts) {
+  const int cg = C / 8;
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)N * oH * oW * cg) return;
+  const int c = (int)(i % cg) * 8;
+  long p = i / cg;
+  const int ox = (int)(p % oW);
+  p /= oW;
+  const int oy = (int)(p % oH), n = (int)(p / oH);
+  // align_corners=True: src = dst * (in - 1) / (out - 1), torch's area_pixel_compute_source_index
+  const float sy = oH > 1 ? (float)oy * ((float)(H - 1) / (float)(oH - 1)) : 0.f;
+  const float sx = oW > 1 ? (float)ox * ((float)(W - 1) / (float)(oW - 1)) : 0.f;
+  const int y0 = (int)sy, x0 = (int)sx;
+  const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+  const float ly = sy - (float)y0, lx = sx - (float)x0;
+  float a[8], b[8], cc[8], d[8], r[8];
+  const __nv_bfloat16* base = in + (size_t)n * H * W * in_ld + in_coff + c;
+  load_parts8(base + ((size_t)y0 * W + x0) * in_ld, parts, in_ps, a);
+  load_parts8(base + ((size_t)y0 * W + x1) * in_ld, parts, in_ps, b);
+  load_parts8(base + ((size_t)y1 * W + x0) * in_ld, parts, in_ps, cc);
+  load_parts8(base + ((size_t)y1 * W + x1) * in_ld, parts, in_ps, d);
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    r[j] = (1.f - ly) * ((1.f - lx) * a[j] + lx * b[j]) + ly * ((1.f - lx) * cc[j] + lx * d[j]);
+  store_parts8(out + (((size_t)n * oH + oy) * oW + ox) * o_ld + o_coff + c, r, parts, o_ps);
+}
+
 // ---- unpack: NHWC split-bf16 -> fp32 NCHW (hand-off to reference-layout consumers) --------
 __global__ void __launch_bounds__(256)
 unpack_nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ in, int ld, int coff, int part_stride,
@@ -643,5 +702,35 @@ extern "C" int dhd_dcn_im2col(const void* x, int x_ld, int x_coff, int x_part_st
       (const __nv_bfloat16*)x, x_ld, x_coff, x_part_stride, x_parts, C, N, H, W, offset, off_ld, ksize,
       pad, dilation, groups, (__nv_bfloat16*)out, o_ld, o_part_stride, o_parts);
   DHD_CUDA_LAUNCH_CHECK("dcn_im2col");
+  return DHD_OK;
+}
+
+extern "C" int dhd_maxpool2(const void* in, int in_ld, int in_coff, int in_part_stride, int N, int H, int W, int C,
+                            void* out, int out_ld, int out_coff, int out_part_stride, int parts, void* stream) {
+  DHD_REQUIRE(in && out && N > 0 && H >= 2 && W >= 2 && C > 0 && parts >= 1 && parts <= 3, "bad arguments");
+  DHD_REQUIRE(C % 8 == 0 && in_ld % 8 == 0 && in_coff % 8 == 0 && out_ld % 8 == 0 && out_coff % 8 == 0 &&
+                  in_part_stride % 8 == 0 && out_part_stride % 8 == 0 &&
+                  ((uintptr_t)in & 15) == 0 && ((uintptr_t)out & 15) == 0, "needs C % 8 == 0 and 16-byte aligned rows");
+  const long total = (long)N * (H / 2) * (W / 2) * (C / 8);
+  maxpool2_kernel<<<(int)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)in, in_ld, in_coff, in_part_stride, N, H, W, C, (__nv_bfloat16*)out, out_ld, out_coff,
+      out_part_stride, parts);
+  DHD_CUDA_LAUNCH_CHECK("maxpool2");
+  return DHD_OK;
+}
+
+extern "C" int dhd_upsample_bilinear(const void* in, int in_ld, int in_coff, int in_part_stride, int N, int H, int W,
+                                     int C, int out_H, int out_W, void* out, int out_ld, int out_coff,
+                                     int out_part_stride, int parts, void* stream) {
+  DHD_REQUIRE(in && out && N > 0 && H > 0 && W > 0 && C > 0 && out_H > 0 && out_W > 0 && parts >= 1 && parts <= 3,
+              "bad arguments");
+  DHD_REQUIRE(C % 8 == 0 && in_ld % 8 == 0 && in_coff % 8 == 0 && out_ld % 8 == 0 && out_coff % 8 == 0 &&
+                  in_part_stride % 8 == 0 && out_part_stride % 8 == 0 &&
+                  ((uintptr_t)in & 15) == 0 && ((uintptr_t)out & 15) == 0, "needs C % 8 == 0 and 16-byte aligned rows");
+  const long total = (long)N * out_H * out_W * (C / 8);
+  upsample_bilinear_kernel<<<(int)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)in, in_ld, in_coff, in_part_stride, N, H, W, C, out_H, out_W, (__nv_bfloat16*)out, out_ld,
+      out_coff, out_part_stride, parts);
+  DHD_CUDA_LAUNCH_CHECK("upsample_bilinear");
   return DHD_OK;
 }

@@ -35,6 +35,7 @@ class ConvSeg(ctypes.Structure):
         ('out_b16', ctypes.c_void_p),
         ('b16_ld', ctypes.c_int32), ('b16_coff', ctypes.c_int32), ('b16_parts', ctypes.c_int32),
         ('b16_part_stride', ctypes.c_int32),
+        ('b16_sN', ctypes.c_int64), ('b16_sY', ctypes.c_int64), ('b16_sX', ctypes.c_int64),
     ]
 
 
@@ -52,6 +53,7 @@ class ConvDesc(ctypes.Structure):
         ('img_gate', ctypes.c_void_p), ('residual', ctypes.c_void_p),
         ('res_sN', ctypes.c_int64), ('res_sY', ctypes.c_int64), ('res_sX', ctypes.c_int64),
         ('n_seg', ctypes.c_int32), ('seg', ConvSeg * MAX_SEGS),
+        ('stride', ctypes.c_int32), ('in_H', ctypes.c_int32), ('in_W', ctypes.c_int32),
     ]
 
 
@@ -178,16 +180,20 @@ def tile_box(H, W):
 
 
 def conv2d(x, weight, Cout, ksize=1, dilation=1, precision='fp32', scale=None, bias=None,
-           img_bias=None, img_gate=None, residual=None, segs=None):
+           img_bias=None, img_gate=None, residual=None, segs=None, stride=1):
     """One fused convolution.  x: Act; weight: pack_weight() result with PRECISIONS[precision]
     parts; segs: list of dicts {c_lo, c_hi, act, out_f32 (tensor, strides (sN,sY,sX,sC)),
-    out_act (Act or Act.slice)}.  Returns nothing: outputs are written in place."""
+    out_act (Act or Act.slice), out_view (sN, sY, sX, offset): pixel strides / start offset in bf16
+    elements when out_act is written as a strided view (ConvTranspose2d phases)}.  stride=2: 3x3 / pad 1
+    down-sampling convolution, output ceil(H/2) x ceil(W/2).  Outputs are written in place."""
     parts, terms = PRECISIONS[precision]
     if x.parts < parts or weight.shape[2] != parts:
         raise ValueError('activation has %d parts, weight %d, precision %s needs %d' %
                          (x.parts, weight.shape[2], precision, parts))
     d = ConvDesc()
-    d.N, d.H, d.W = x.N, x.H, x.W
+    oH, oW = (x.H, x.W) if stride == 1 else ((x.H + 1) // 2, (x.W + 1) // 2)
+    d.N, d.H, d.W = x.N, oH, oW
+    d.stride, d.in_H, d.in_W = stride, x.H, x.W
     d.Cin, d.Cout = x.C, Cout
     taps = ksize * ksize
     if weight.shape[0] != Cout or weight.shape[1] != taps or weight.shape[3] != x.C:
@@ -198,7 +204,7 @@ def conv2d(x, weight, Cout, ksize=1, dilation=1, precision='fp32', scale=None, b
     for t in range(taps):
         d.tap_dy[t] = (t // ksize - r) * dilation
         d.tap_dx[t] = (t % ksize - r) * dilation
-    d.bw, d.bh = tile_box(x.H, x.W)
+    d.bw, d.bh = tile_box(oH, oW)
     d.in_ = x.data.data_ptr()
     d.in_ld, d.in_coff, d.in_part_stride = x.ld, x.coff, x.part_stride
     d.weight = weight.data_ptr()
@@ -230,10 +236,13 @@ def conv2d(x, weight, Cout, ksize=1, dilation=1, precision='fp32', scale=None, b
             keep.append(t)
         if s.get('out_act') is not None:
             a = s['out_act']
-            if (a.N, a.H, a.W) != (x.N, x.H, x.W) or a.C < g.c_hi - g.c_lo:
+            view = s.get('out_view')
+            if a.C < g.c_hi - g.c_lo or (view is None and (a.N, a.H, a.W) != (x.N, oH, oW)):
                 raise ValueError('output activation does not match the layer')
-            g.out_b16 = a.data.data_ptr()
+            g.out_b16 = a.data.data_ptr() + (0 if view is None else 2 * view[3])
             g.b16_ld, g.b16_coff, g.b16_parts, g.b16_part_stride = a.ld, a.coff, a.parts, a.part_stride
+            if view is not None:
+                g.b16_sN, g.b16_sY, g.b16_sX = view[0], view[1], view[2]
             keep.append(a.data)
     _lib.check(_lib.load().dhd_conv2d_fwd(ctypes.byref(d), _stream()), 'conv2d_fwd')
     return keep

@@ -163,10 +163,13 @@ typedef struct dhd_conv_seg {
   void* out_b16;               /* or NULL; NHWC bf16, b16_ld channels per pixel, channel c-c_lo at
                                   b16_coff + part*b16_part_stride + (c-c_lo) */
   int32_t b16_ld, b16_coff, b16_parts, b16_part_stride;
+  int64_t b16_sN, b16_sY, b16_sX; /* output pixel strides in bf16 elements; all 0 = dense NHWC (H*W*ld, W*ld, ld).
+                                     A strided view lets a layer write every 2nd pixel of a larger map: the four
+                                     phases of ConvTranspose2d(kernel 2, stride 2) (backbones/unet.py:86) */
 } dhd_conv_seg;
 
 typedef struct dhd_conv_desc {
-  int32_t N, H, W;             /* images and spatial size (stride-1 convolution, same size out) */
+  int32_t N, H, W;             /* images and OUTPUT spatial size (== input size unless stride == 2) */
   int32_t Cin, Cout;           /* Cin % 64 == 0 */
   int32_t taps;                /* 1 (1x1 / linear) .. 9 */
   int32_t tap_dy[DHD_CONV_MAX_TAPS], tap_dx[DHD_CONV_MAX_TAPS]; /* input offset of tap t: (k-1)*dilation */
@@ -185,6 +188,10 @@ typedef struct dhd_conv_desc {
   int64_t res_sN, res_sY, res_sX;
   int32_t n_seg;
   dhd_conv_seg seg[DHD_CONV_MAX_SEGS];
+  int32_t stride;              /* 0 / 1: same-size convolution; 2: N,H,W describe the OUTPUT, the input is in_H x in_W
+                                  and tap t reads input pixel (stride*y + tap_dy, stride*x + tap_dx)
+                                  (CustomResNet's stride-2 blocks, backbones/resnet.py:47-52) */
+  int32_t in_H, in_W;          /* input size when stride == 2 */
 } dhd_conv_desc;
 
 int dhd_conv2d_fwd(const dhd_conv_desc* desc, void* stream);
@@ -289,6 +296,13 @@ int dhd_pack_nchw_to_nhwc(const float* in, int N, int C, int H, int W, void* out
                           int out_coff, int part_stride, int parts, void* stream);
 /* class map of predictor.get_occ (occ_head.py:141-153): out[v] = argmax_k logits[v][k] (uint8) */
 int dhd_occ_argmax(const float* logits, long nvox, int ncls, uint8_t* out, void* stream);
+/* encoder helpers, bf16 NHWC -> bf16 NHWC (the output may be a channel slice of a concatenation buffer):
+ * MaxPool2d(2) (backbones/unet.py:65-74) and bilinear Upsample(align_corners=True) (necks/lss_fpn.py:27-28, 41-42) */
+int dhd_maxpool2(const void* in, int in_ld, int in_coff, int in_part_stride, int N, int H, int W, int C,
+                 void* out, int out_ld, int out_coff, int out_part_stride, int parts, void* stream);
+int dhd_upsample_bilinear(const void* in, int in_ld, int in_coff, int in_part_stride, int N, int H, int W,
+                          int C, int out_H, int out_W, void* out, int out_ld, int out_coff,
+                          int out_part_stride, int parts, void* stream);
 /* write-bandwidth probe (measurement only): zero-fills `bytes` at dst with mode 0 = grid-stride
  * st.global.cs.v4, 1 = grid-stride st.global.v4, 2 = one contiguous run per warp (st.cs),
  * 3 = cp.async.bulk from a shared-memory zero tile, one run per CTA, 4 = same, one run per warp */

@@ -167,3 +167,57 @@ def predictor_forward(sd, x, Dz=16, num_classes=18, prefix=''):
     y = F.linear(F.softplus(F.linear(y, sd[p + 'predicter.0.weight'], sd[p + 'predicter.0.bias'])),
                  sd[p + 'predicter.2.weight'], sd[p + 'predicter.2.bias'])
     return y.view(y.shape[0], y.shape[1], y.shape[2], Dz, num_classes)
+
+
+# ------------------------------------------------------------------ BEV / voxel encoders
+def _double_conv(sd, p, x):
+    """backbones/unet.py:45-61"""
+    x = F.relu(_bn(sd, p + '.1', F.conv2d(x, sd[p + '.0.weight'], padding=1)))
+    return F.relu(_bn(sd, p + '.4', F.conv2d(x, sd[p + '.3.weight'], padding=1)))
+
+
+def unet_forward(sd, x, prefix=''):
+    """backbones/unet.py:25-40 (bilinear=False): inc, 4x (MaxPool2d(2) + DoubleConv), 4x (ConvTranspose2d(2, 2),
+    pad to the skip's size, cat([skip, up]), DoubleConv), 1x1 outc."""
+    p = prefix
+    xs = [_double_conv(sd, p + 'inc.double_conv', x)]
+    for k in range(1, 5):
+        xs.append(_double_conv(sd, p + 'down%d.maxpool_conv.1.double_conv' % k, F.max_pool2d(xs[-1], 2)))
+    y = xs[4]
+    for k in range(1, 5):
+        skip = xs[4 - k]
+        y = F.conv_transpose2d(y, sd[p + 'up%d.up.weight' % k], sd[p + 'up%d.up.bias' % k], stride=2)
+        dy, dx = skip.shape[2] - y.shape[2], skip.shape[3] - y.shape[3]
+        y = F.pad(y, [dx // 2, dx - dx // 2, dy // 2, dy - dy // 2])
+        y = _double_conv(sd, p + 'up%d.conv.double_conv' % k, torch.cat([skip, y], dim=1))
+    return F.conv2d(y, sd[p + 'outc.conv.weight'], sd[p + 'outc.conv.bias'])
+
+
+def custom_resnet_forward(sd, x, prefix='', strides=(2, 2, 2), num_layer=(2, 2, 2)):
+    """backbones/resnet.py:10-80 (block_type='Basic'): returns the list of stage outputs."""
+    feats = []
+    for i, (st, nl) in enumerate(zip(strides, num_layer)):
+        for j in range(nl):
+            p = '%slayers.%d.%d' % (prefix, i, j)
+            s = st if j == 0 else 1
+            out = F.relu(_bn(sd, p + '.bn1', F.conv2d(x, sd[p + '.conv1.weight'], stride=s, padding=1)))
+            out = _bn(sd, p + '.bn2', F.conv2d(out, sd[p + '.conv2.weight'], padding=1))
+            idn = x
+            if (p + '.downsample.weight') in sd:
+                idn = F.conv2d(x, sd[p + '.downsample.weight'], sd[p + '.downsample.bias'], stride=s, padding=1)
+            x = F.relu(out + idn)
+        feats.append(x)
+    return feats
+
+
+def fpn_lss_forward(sd, feats, prefix='', index=(0, 2), scale=4, scale2=2):
+    """necks/lss_fpn.py:62-74 (lateral=None, extra_upsample=2)."""
+    p = prefix
+    x2, x1 = feats[index[0]], feats[index[1]]
+    x1 = F.interpolate(x1, scale_factor=scale, mode='bilinear', align_corners=True)
+    x = torch.cat([x2, x1], dim=1)
+    x = F.relu(_bn(sd, p + 'conv.1', F.conv2d(x, sd[p + 'conv.0.weight'], padding=1)))
+    x = F.relu(_bn(sd, p + 'conv.4', F.conv2d(x, sd[p + 'conv.3.weight'], padding=1)))
+    x = F.interpolate(x, scale_factor=scale2, mode='bilinear', align_corners=True)
+    x = F.relu(_bn(sd, p + 'up2.2', F.conv2d(x, sd[p + 'up2.1.weight'], padding=1)))
+    return F.conv2d(x, sd[p + 'up2.4.weight'], sd[p + 'up2.4.bias'])

@@ -121,18 +121,21 @@ def _install_stubs(bev_pool_v2_impl):
     necks, heads, backbones = _Registry(), _Registry(), _Registry()
     mod('mmcv')
     mod('mmcv.runner', BaseModule=nn.Module, force_fp32=force_fp32)
-    mod('mmcv.cnn', build_conv_layer=_build_conv_layer, ConvModule=_ConvModule)
+    mod('mmcv.cnn', build_conv_layer=_build_conv_layer, ConvModule=_ConvModule,
+        build_norm_layer=lambda cfg, n, postfix='': ('bn' + str(postfix), nn.BatchNorm2d(n)))
+    mod('mmcv.cnn.bricks', ConvModule=_ConvModule).__path__ = []
+    mod('mmcv.cnn.bricks.conv_module', ConvModule=_ConvModule)
     mod('mmdet')
-    mod('mmdet.models')
+    mod('mmdet.models', NECKS=necks)
     mod('mmdet.models.backbones')
-    mod('mmdet.models.backbones.resnet', BasicBlock=_BasicBlock)
+    mod('mmdet.models.backbones.resnet', BasicBlock=_BasicBlock, Bottleneck=type('Bottleneck', (nn.Module,), {}))
     mod('mmdet3d')
     mod('mmdet3d.models', BACKBONES=backbones)
     mod('mmdet3d.models.builder', NECKS=necks, HEADS=heads, BACKBONES=backbones,
         build_loss=lambda cfg: None)
     # fake package tree so the reference's relative imports resolve
     for p in ('refplg', 'refplg.models', 'refplg.models.necks', 'refplg.models.model_utils',
-              'refplg.models.dense_heads', 'refplg.models.losses'):
+              'refplg.models.dense_heads', 'refplg.models.losses', 'refplg.models.backbones'):
         m = mod(p)
         m.__path__ = []
     mod('refplg.ops', bev_pool_v2=bev_pool_v2_impl).__path__ = []
@@ -167,7 +170,11 @@ def load_reference():
     # occ_head imports ..losses.semkitti_loss (pure torch) relatively
     sk = _exec('refplg.models.losses.semkitti_loss', 'models/losses/semkitti_loss.py')
     oh = _exec('refplg.models.dense_heads.occ_head', 'models/dense_heads/occ_head.py')
+    un = _exec('refplg.models.backbones.unet', 'models/backbones/unet.py')
+    rn = _exec('refplg.models.backbones.resnet', 'models/backbones/resnet.py')
+    fp = _exec('refplg.models.necks.lss_fpn', 'models/necks/lss_fpn.py')
     ns = types.SimpleNamespace(
+        UNet=un.UNet, CustomResNet=rn.CustomResNet, FPN_LSS=fp.FPN_LSS,
         MGHS=lh.MGHS, MGHS_Depth=lh.MGHS_Depth, MGHS_Stereo=lh.MGHS_Stereo,
         HeightNet=dn.HeightNet, DepthNet=dn.DepthNet, ASPP=dn.ASPP, SFA=mix.SFA,
         predictor=oh.predictor, lss_heightmap=lh, depthnet=dn, mix=mix, occ_head=oh)

@@ -1,3 +1,4 @@
+from .backbones import *  # noqa: F401,F403
 from .dense_heads import *  # noqa: F401,F403
 from .detectors import *  # noqa: F401,F403
 from .model_utils import *  # noqa: F401,F403

@@ -1,0 +1,4 @@
+from .resnet import CustomResNet
+from .unet import UNet
+
+__all__ = ['CustomResNet', 'UNet']

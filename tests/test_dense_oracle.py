@@ -134,3 +134,47 @@ def test_dense_modules_refuse_cpu_tensors():
         head(torch.zeros(1, 256, 8, 16))
     with pytest.raises(RuntimeError, match='CUDA'):
         hn(torch.zeros(1, 256, 8, 16), torch.zeros(1, 1, 27))
+
+
+# ---------------------------------------------------------------- BEV / voxel encoders
+def _encoder_state_dicts():
+    import projects.mmdet3d_plugin  # noqa: F401
+    from oracle import make_golden_encoders as ME
+    from projects.mmdet3d_plugin.models.backbones import CustomResNet, UNet
+    from projects.mmdet3d_plugin.models.necks import FPN_LSS
+    mods = dict(unet=UNet(256, 64), resnet=CustomResNet(64, num_channels=[128, 256, 512]), fpn=FPN_LSS(640, 256))
+    return ME, {k: DO.seeded_state_dict(m, ME.SEEDS[k]) for k, m in mods.items()}, mods
+
+
+def test_encoder_oracle_matches_reference_fixture():
+    """oracle restatement of UNet / CustomResNet / FPN_LSS against outputs of the unmodified reference classes
+    (tests/golden/encoders.npz, made by oracle/make_golden_encoders.py)."""
+    ME, sds, _ = _encoder_state_dicts()
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'encoders.npz'))
+    for k, sd in sds.items():
+        assert MG.sha_sd(sd) == str(gold['sha_' + k]), 'seeded weights differ from the fixture'
+    xu, xb = ME.inputs()
+    with torch.no_grad():
+        yu = DO.unet_forward(sds['unet'], xu)
+        feats = DO.custom_resnet_forward(sds['resnet'], xb)
+        yf = DO.fpn_lss_forward(sds['fpn'], feats)
+    for got, key in ((yu, 'unet'), (feats[0], 'feat0'), (feats[1], 'feat1'), (feats[2], 'feat2'), (yf, 'fpn')):
+        want = torch.from_numpy(gold[key])
+        assert torch.allclose(got, want, rtol=1e-5, atol=1e-5 * float(want.abs().max())), key
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason='reference tree not present')
+def test_encoder_oracle_and_plugin_names_match_real_reference():
+    ME, sds, mods = _encoder_state_dicts()
+    refs = dict(zip(('unet', 'resnet', 'fpn'), ME.build_reference_modules()))
+    for k in refs:
+        assert list(refs[k].state_dict().keys()) == list(mods[k].state_dict().keys()), k
+        assert all(refs[k].state_dict()[n].shape == mods[k].state_dict()[n].shape for n in refs[k].state_dict()), k
+        refs[k].load_state_dict(sds[k])
+    xu, xb = ME.inputs()
+    with torch.no_grad():
+        assert torch.equal(refs['unet'](xu), DO.unet_forward(sds['unet'], xu))
+        fr = refs['resnet'](xb)
+        fo = DO.custom_resnet_forward(sds['resnet'], xb)
+        assert all(torch.equal(a, b) for a, b in zip(fr, fo))
+        assert torch.equal(refs['fpn'](fr), DO.fpn_lss_forward(sds['fpn'], fo))
