@@ -45,6 +45,7 @@ def parse():
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-train', action='store_true', help='skip the training-step extra')
+    ap.add_argument('--no-encoders', action='store_true', help='skip the widened-path (real encoders) extra')
     return ap.parse_args()
 
 
@@ -103,6 +104,7 @@ class ClockSampler:
 def run_ours(args):
     import torch.distributed as dist
     from dhd_b200 import _lib
+    from dhd_b200 import shard
     from dhd_b200.pipeline import HotPathStep, algorithmic_bytes, dense_flops
     from dhd_b200 import synth as O        # the product arm never touches oracle/
 
@@ -199,6 +201,33 @@ def run_ours(args):
         torch.cuda.synchronize()
         stage_ms[name] = s0.elapsed_time(s1) / 5
 
+    # ---- extras: the widened path -- the real BEV / voxel encoders between pool and SFA
+    widened = None
+    if not args.no_encoders:
+        wide = HotPathStep(cfg, B, precision=args.precision, use_graph=not args.no_graph, encoders=True)
+        wide.alloc_static(host)
+        wide.upload(host)
+        wide_graphed = wide.capture()
+        for _ in range(3):
+            wide.run()
+        barrier()
+        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        nw = max(3, min(args.steps, 10))
+        w0.record(st)
+        for _ in range(nw):
+            wide.run()
+        w1.record(st)
+        barrier()
+        ms_wide = shard.max_over_ranks([w0.elapsed_time(w1) / nw], device='cuda')[0]
+        from dhd_b200.pipeline import encoder_flops
+        widened = {'ms_per_step': ms_wide, 'samples_per_s': world * B / (ms_wide * 1e-3), 'cuda_graph': bool(wide_graphed),
+                   'launches_per_step': wide.launches_per_step, 'stages': wide.stage_names(),
+                   'encoder_tflops_algorithmic': encoder_flops(B) / 1e12,
+                   'what': 'same step with CustomResNet + FPN_LSS and the three UNets (DHD-S.py:106-131, random-init '
+                           'weights) instead of resident encoder features: image features -> occupancy classes'}
+        del wide
+        torch.cuda.empty_cache()
+
     # ---- extras: the data-parallel TRAINING step of the path (forward, loss, backward, one gradient
     # all-reduce over NCCL, AdamW, weight re-pack), see dhd_b200.pipeline.TrainStep for what is trainable
     train = None
@@ -235,7 +264,6 @@ def run_ours(args):
                          'bf16 weight re-pack; encoders stand in as resident tensors (see TrainStep)'}
         del ts
 
-    from dhd_b200 import shard
     ms_total, ms_e2e, pool_ms_avg = shard.max_over_ranks([ms_total, ms_e2e, pool_ms_avg], device='cuda')
     if train is not None:
         train['ms_per_step'] = shard.max_over_ranks([train['ms_per_step']], device='cuda')[0]
@@ -279,7 +307,7 @@ def run_ours(args):
                 'kernel_share_of_step': pool_ms_avg / (ms_total / args.steps),
             },
             'extras': {
-                'stage_ms': stage_ms, 'pool_bwd_ms': bwd_ms, 'train_step': train,
+                'stage_ms': stage_ms, 'pool_bwd_ms': bwd_ms, 'train_step': train, 'with_encoders': widened,
                 'e2e_serialised_ms_per_step (H2D, kernels, D2H on one stream)': ms_e2e_serial,
                 'dense_tflops_algorithmic': {k: v / 1e12 for k, v in fl.items()},
                 'dense_tflop_per_s': sum(fl.values()) / 1e12 /

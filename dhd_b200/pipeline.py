@@ -67,9 +67,32 @@ def dense_flops(cfg, B, Dy=200, Dx=200):
     return {'heightnet': hn, 'depth_net': dn, 'sfa': sfa, 'predictor': head}
 
 
+def encoder_flops(B, Dy=200, Dx=200, c=64):
+    """Algorithmic forward FLOPs of the BEV encoder (CustomResNet + FPN_LSS) and the three UNets at DHD-S sizes."""
+    def conv(hw, cin, cout, k=3):
+        return 2.0 * B * hw * cin * cout * k * k
+    hw = [Dy * Dx // (4 ** i) for i in range(5)]
+    hw[4] = (Dy // 16) * (Dx // 16)
+    tot = 0.0
+    cin = c
+    for i, ch in enumerate((2 * c, 4 * c, 8 * c)):                      # CustomResNet
+        tot += conv(hw[i + 1], cin, ch) * 2 + conv(hw[i + 1], ch, ch) * 3
+        cin = ch
+    tot += conv(hw[1], 10 * c, 512) + conv(hw[1], 512, 512) + conv(hw[0], 512, 256) + conv(hw[0], 256, 256, 1)
+    for nin, ncls in ((4 * c, 64), (4 * c, 128), (8 * c, 64)):          # UNets
+        chans = [64, 128, 256, 512, 1024]
+        tot += conv(hw[0], nin, 64) + conv(hw[0], 64, 64)
+        for k in range(1, 5):
+            tot += conv(hw[k], chans[k - 1], chans[k]) + conv(hw[k], chans[k], chans[k])
+        for k in range(3, -1, -1):
+            tot += conv(hw[k + 1], chans[k + 1], chans[k], 2) + conv(hw[k], 2 * chans[k], chans[k]) + conv(hw[k], chans[k], chans[k])
+        tot += conv(hw[0], 64, ncls, 1)
+    return tot
+
+
 class HotPathStep:
     def __init__(self, cfg, B, precision='bf16', deterministic=True, device='cuda', seed=0,
-                 use_graph=True):
+                 use_graph=True, encoders=False):
         from projects.mmdet3d_plugin.models.dense_heads.occ_head import predictor
         from projects.mmdet3d_plugin.models.necks.lss_heightmap import MGHS
         from projects.mmdet3d_plugin.models.necks.mix import SFA
@@ -91,6 +114,22 @@ class HotPathStep:
         self.sfa = SFA(512, 256, precision=precision).eval().to(self.device)
         self.head = predictor(in_dim=256, out_dim=256, Dz=16, num_classes=18, use_predicter=True,
                               class_balance=False, loss_occ=None, precision=precision).eval().to(self.device)
+        self.encoders = encoders
+        if encoders:
+            # the widened path: the real BEV encoder and the three voxel encoders of
+            # DHD-S.py:106-131 between the pool and the SFA instead of resident stand-in features
+            from projects.mmdet3d_plugin.models.backbones import CustomResNet, UNet
+            from projects.mmdet3d_plugin.models.necks import FPN_LSS
+            from .encoders import CustomResNetEngine, FPNLSSEngine, UNetEngine
+            c = self.C
+            self.bev_backbone = CustomResNet(c, num_channels=[2 * c, 4 * c, 8 * c], precision=precision).eval().to(self.device)
+            self.bev_neck = FPN_LSS(8 * c + 2 * c, 256, precision=precision).eval().to(self.device)
+            self.voxel = [UNet(4 * c, 64, precision=precision), UNet(4 * c, 128, precision=precision),
+                          UNet(8 * c, 64, precision=precision)]
+            self.voxel = [u.eval().to(self.device) for u in self.voxel]
+            self.e_backbone = CustomResNetEngine(self.bev_backbone, precision, self.device)
+            self.e_neck = FPNLSSEngine(self.bev_neck, precision, self.device)
+            self.e_voxel = [UNetEngine(u, precision, self.device) for u in self.voxel]
         self.D = self.vt.D
         self.depth_engine = DepthHeadEngine(self.vt.depth_net, self.D, precision, self.device)
         self.height_engine = HeightNetEngine(self.vt.height_net, precision, self.device)
@@ -121,9 +160,11 @@ class HotPathStep:
         self._last = {}
 
     def stage_names(self):
+        mid = ['split(pool outputs -> bf16)', 'CustomResNet + FPN_LSS (BEV encoder)', '3x UNet (voxel encoders)'] \
+            if self.encoders else ['split(encoder stand-in -> bf16)']
         return ['pack', 'depth_net(1x1+softmax)', 'HeightNet(+softmax)', 'height_to_mask',
-                'mghs_prepare(geometry+binning, 4 grids)', 'mghs_pool_fwd(nhwc, fused 4-pass)',
-                'split(encoder stand-in -> bf16)', 'SFA', 'predictor', 'occ_argmax']
+                'mghs_prepare(geometry+binning, 4 grids)', 'mghs_pool_fwd(nhwc, fused 4-pass)'] + mid + \
+            ['SFA', 'predictor', 'occ_argmax']
 
     # ---- inputs -----------------------------------------------------------------------------
     def make_host_inputs(self, rig, seed):
@@ -164,8 +205,23 @@ class HotPathStep:
         L = self._last
         self.plan.raw_forward(L['depth'], L['feat'], L['pixmask'], self.outs, 'nhwc', workspace=self.workspace)
 
+    def _encode(self):
+        """pool outputs -> (B, 512, Dy, Dx) = cat(bev encoder, three voxel encoders), DM:103-114: every encoder
+        writes its channel slice of one NHWC buffer."""
+        B, H, W = self.B, self.Dy, self.Dx
+        if not hasattr(self, '_enc_act'):
+            self._enc_act = D.Act.empty(B, H, W, 512, self.parts, self.device)
+        enc = self._enc_act
+        ins = [D.pack_nhwc(o, self.parts) for o in self.outs]          # fp32 pool outputs -> bf16 activations
+        self.e_neck(self.e_backbone(ins[0]), out=enc.slice(0, 256))
+        lo = 256
+        for e, x in zip(self.e_voxel, ins[1:]):
+            e(x, out=enc.slice(lo, lo + e.n_classes))
+            lo += e.n_classes
+        return enc
+
     def _back(self):
-        enc = D.pack_nhwc(self.encoded, self.parts, want_mean=True)
+        enc = self._encode() if self.encoders else D.pack_nhwc(self.encoded, self.parts, want_mean=True)
         fused = self.sfa_engine(enc)
         logits = self.head_engine(fused)
         _lib.check(_lib.load().dhd_occ_argmax(ctypes.c_void_p(logits.data_ptr()), self.occ.numel(), 18,
