@@ -98,3 +98,53 @@ def test_bev_encoder_matches_reference_fixture(cuda_lib):
     for i, f in enumerate(feats):
         close(f.float(), torch.from_numpy(gold['feat%d' % i]))
     close(mods['fpn'](feats), torch.from_numpy(gold['fpn']))
+
+
+def _dhd_s_model_cfg():
+    """The `model` dict of projects/configs/DHD/DHD-S.py:41-155 without the image backbone / FPN."""
+    c = 64
+    grid = {'x': [-40, 40, 0.4], 'y': [-40, 40, 0.4], 'z': [-1, 5.4, 6.4], 'depth': [1.0, 45.0, 1.0]}
+    mg = lambda z: {'x': [-40, 40, 0.4], 'y': [-40, 40, 0.4], 'z': z, 'depth': [1.0, 45.0, 0.5]}
+    return dict(
+        type='DHD',
+        img_view_transformer=dict(type='MGHS', grid_config=grid, input_size=(256, 704),
+                                  height_range=[round(-1.0 + 0.1 * i, 1) for i in range(65)], height_interval=0.1,
+                                  mask_1_grid=mg([-1, 0.6, 0.4]), mask_2_grid=mg([0.6, 2.2, 0.4]), mask_3_grid=mg([2.2, 5.4, 0.4]),
+                                  mask_range=[-1.0, 0.6, 2.2, 5.4], loss_height_weight=0.1, in_channels=256, out_channels=c,
+                                  sid=False, collapse_z=True, downsample=16),
+        img_bev_encoder_backbone=dict(type='CustomResNet', numC_input=c, num_channels=[c * 2, c * 4, c * 8]),
+        img_bev_encoder_neck=dict(type='FPN_LSS', in_channels=c * 8 + c * 2, out_channels=256),
+        img_voxel_encoder0_backbone=dict(type='UNet', n_channels=c * 4, n_classes=64), img_voxel_encoder0_neck=dict(type='Identity'),
+        img_voxel_encoder1_backbone=dict(type='UNet', n_channels=c * 4, n_classes=128), img_voxel_encoder1_neck=dict(type='Identity'),
+        img_voxel_encoder2_backbone=dict(type='UNet', n_channels=c * 8, n_classes=64), img_voxel_encoder2_neck=dict(type='Identity'),
+        mix=dict(type='SFA', in_channels=512, out_channels=256),
+        occ_head=dict(type='predictor', in_dim=256, out_dim=256, Dz=16, use_mask=True, num_classes=18, use_predicter=True,
+                      class_balance=True, loss_occ=dict(type='CrossEntropyLoss', use_sigmoid=False, ignore_index=255, loss_weight=1.0)))
+
+
+def test_dhd_detector_from_config_image_features_to_occupancy(cuda_lib):
+    """The DHD detector built from the DHD-S model config through the registry (view transformer, BEV encoder,
+    three voxel encoders, SFA, occupancy head): image features -> occupancy logits at the config's full grid,
+    against the oracle's restatement of every stage after the view transform fed with the detector's own pooled
+    BEV tensors (fp32 mode)."""
+    import projects.mmdet3d_plugin  # noqa: F401
+    from dhd_b200 import compat as C
+    from dhd_b200 import synth
+    from oracle import dense_oracle as DO
+    model = C.DETECTORS.build(_dhd_s_model_cfg()).eval()
+    model.load_state_dict(DO.seeded_state_dict(model, 77))
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    model = model.cuda()
+    B, N = 1, 6
+    rig = synth.synthetic_rig(B, N, (256, 704), seed=5)
+    x = DO.seeded_tensor((B, N, 256, 16, 44), 78)
+    cams = [t.cuda() for t in rig]
+    occ, depth, height = model.forward_hot_path(x.cuda(), cams)
+    assert occ.shape == (B, 200, 200, 16, 18)
+    bev, _, _, lo, mid, hi = model.view_transform(x.cuda(), cams)
+    sub = lambda p: {k[len(p):]: v for k, v in sd.items() if k.startswith(p)}
+    with torch.no_grad():
+        x2d = DO.fpn_lss_forward(sub('img_bev_encoder_neck.'), DO.custom_resnet_forward(sub('img_bev_encoder_backbone.'), bev.cpu().contiguous()))
+        x3d = [DO.unet_forward(sub('img_voxel_encoder%d.' % i), t.cpu().contiguous()) for i, t in enumerate((lo, mid, hi))]
+        want = DO.predictor_forward(sub('occ_head.'), DO.sfa_forward(sub('mix.'), torch.cat([x2d] + x3d, dim=1)))
+    close(occ, want, 5e-4)
