@@ -376,3 +376,51 @@ def test_fused_matches_reference_cuda_path_full_size(cuda_lib):
         assert got.shape == w.shape
         assert torch.allclose(got, w, rtol=1e-5, atol=2e-6)
         assert int((got != 0).sum()) == int((w != 0).sum())       # identical support (bit-exact voxel indices)
+
+
+def _cfg_variant(input_size, depth_cfg, ncams=6):
+    cfg = dict(O.DHD_S)
+    cfg.update(input_size=input_size, depth=depth_cfg, ncams=ncams)
+    return cfg
+
+
+@pytest.mark.parametrize('name,input_size,depth_cfg,B,collapse,layout', [
+    # BASELINE.json configs[3] ("DHD-B": the DHD-S topology at 384x1056 -> 24x66 features)
+    ('cfg4_384x1056', (384, 1056), [1.0, 45.0, 1.0], 2, True, 'nchw'),
+    # BASELINE.json configs[4] (DHD-L: 512x1408 -> 32x88 features, D=88, collapse_z=False slabs, DHD-L.py:18-118)
+    ('cfg5_dhdl_512x1408', (512, 1408), [1.0, 45.0, 0.5], 2, False, 'ncdhw'),
+])
+def test_fused_matches_reference_cuda_path_other_configs(cuda_lib, name, input_size, depth_cfg, B, collapse, layout):
+    """The larger BASELINE configs as parity cases: fused pool (reference-layout outputs written directly by the
+    kernel) against the reference's CUDA path (its op sequence + its unmodified kernel) on the same inputs."""
+    from oracle import ref_cuda_path as R
+    if not R.available():
+        pytest.skip('oracle/_ref not built')
+    from dhd_b200.pool import MghsPool, height_to_mask
+    cfg = _cfg_variant(input_size, depth_cfg)
+    src = (900, 1600)
+    rig = O.synthetic_rig(B, 6, input_size, src_size=src, seed=21)
+    inputs, depth, feat, height = O.synthetic_inputs(cfg, B, seed=21, rig=rig)
+    inputs = tuple(t.cuda() for t in inputs)
+    depth, feat, height = depth.cuda(), feat.cuda(), height.cuda()
+    N, D = 6, depth.shape[1]
+    fH, fW = depth.shape[-2:]
+    C = cfg['C']
+    assert (fH, fW) == (input_size[0] // 16, input_size[1] // 16)
+    fr = O.frustum(cfg['depth'], cfg['input_size'], cfg['downsample']).cuda()
+    want = R.view_transform_cuda(inputs, depth, feat, height, fr, cfg['height_range'], cfg['mask_range'],
+                                 cfg['mask_grids'], collapse_z=collapse)
+    grids = [cfg['bev_grid']] + list(cfg['mask_grids'])
+    plan = MghsPool(B, N, D, fH, fW, C, grids[0]['x'], grids[0]['y'], [(g['z'], m) for m, g in enumerate(grids)])
+    coor = O.ego_coor(fr, inputs[1], inputs[3], inputs[4], inputs[5], inputs[6])
+    plan.prepare(coor=coor)
+    pm = height_to_mask(height, cfg['height_range'], cfg['mask_range'])
+    f_nhwc = feat.view(B, N, C, fH, fW).permute(0, 1, 3, 4, 2).contiguous()
+    outs = plan(depth, f_nhwc, pm, layout=layout)
+    for o, w in zip(outs, want):
+        assert o.shape == w.shape and o.is_contiguous()
+        assert torch.allclose(o, w, rtol=1e-5, atol=2e-6)
+    # and the single-write NHWC kernel on the same bins
+    for o, w in zip(plan(depth, f_nhwc, pm, layout='nhwc'), want):
+        ref = w if collapse else torch.cat(w.unbind(dim=2), 1)
+        assert torch.allclose(o.permute(0, 3, 1, 2), ref, rtol=1e-5, atol=2e-6)
