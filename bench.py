@@ -256,10 +256,11 @@ def run_ours(args):
         ms_train = t0.elapsed_time(t1) / nt
         train = {'ms_per_step': ms_train, 'launches_per_step': launches, 'cuda_graph': bool(train_graphed),
                  'graph_error': getattr(ts, 'train_graph_error', None),
-                 'loss': float(ts.loss[0]), 'trainable_params': ts.n_params,
+                 'loss': float(ts.loss[0]), 'loss_sem_scal': float(ts.loss[2]), 'loss_geo_scal': float(ts.loss[3]),
+                 'trainable_params': ts.n_params,
                  'gradient_all_reduce_bytes': ts.n_params * 4,
                  'loss_height': float(ts.loss_height[0]),
-                 'what': 'forward + losses (occupancy CE, height BCE) + backward of depth_net, HeightNet, SFA and predictor '
+                 'what': 'forward + losses (occupancy CE + sem_scal + geo_scal, height BCE) + backward of depth_net, HeightNet, SFA and predictor '
                          '(BatchNorm frozen), fused pool fwd+bwd, one NCCL all-reduce of the fp32 gradient bucket, AdamW, '
                          'bf16 weight re-pack; encoders stand in as resident tensors (see TrainStep)'}
         del ts

@@ -57,7 +57,9 @@ _SIGNATURES = {
     'dhd_se_gate_bwd': (ctypes.c_int, [_P, _I, _I, _P, _I, _I, _I, _I, _I, _P, _P, _I, _I, _P, _P, _P]),
     'dhd_height_loss': (ctypes.c_int, [_P, _P, _P, _I, _I, _I, ctypes.c_float, _P, _P, _P, _I, _P]),
     'dhd_dcn_col2im_bwd': (ctypes.c_int, [_P, _I, _P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _P, _P, _P]),
-    'dhd_occ_ce_loss': (ctypes.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, ctypes.c_float, _P, _P, _I, _P]),
+    'dhd_occ_loss_workspace_bytes': (ctypes.c_size_t, []),
+    'dhd_occ_ce_loss': (ctypes.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, ctypes.c_float, ctypes.c_float, ctypes.c_float, _I,
+                                       _P, _P, _I, _P, _P]),
     'dhd_depth_head_bwd': (ctypes.c_int, [_P, _P, _P, _I, _I, _I, _I, _P, _I, _P]),
     'dhd_sfa_gate_bwd_workspace_bytes': (ctypes.c_size_t, [_I, _I, _I]),
     'dhd_sfa_gate_bwd': (ctypes.c_int, [_I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _P, _P, _P, _I, _I, _P, _P, _I, _P, _P]),

@@ -134,7 +134,17 @@ ce_norm_kernel(const uint8_t* __restrict__ labels, const uint8_t* __restrict__ m
 __global__ void __launch_bounds__(256)
 ce_loss_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ labels, const uint8_t* __restrict__ mask,
                const float* __restrict__ cw, int ncls, int ignore, int B, int Dx, int Dy, int Dz, float loss_weight,
-               const float* __restrict__ norm, float* __restrict__ loss, __nv_bfloat16* __restrict__ dlogits, int ld) {
+               const float* __restrict__ norm, float* __restrict__ loss, __nv_bfloat16* __restrict__ dlogits, int ld,
+               const float* __restrict__ scal_gt, const float* __restrict__ scal_gn) {
+  // scal_gt / scal_gn (optional, [ncls]): d(sem_scal + geo_scal)/d p_k of a masked voxel for k == label / k != label
+  // (occ_scal_coeffs_kernel); chained through the softmax here so the logits are read once for all three terms
+  __shared__ float s_gt[32], s_gn[32];
+  if (threadIdx.x < 32) {
+    s_gt[threadIdx.x] = scal_gt != nullptr && threadIdx.x < ncls ? scal_gt[threadIdx.x] : 0.f;
+    s_gn[threadIdx.x] = scal_gn != nullptr && threadIdx.x < ncls ? scal_gn[threadIdx.x] : 0.f;
+  }
+  __syncthreads();
+  const bool scal = scal_gt != nullptr;
   const long nvox = (long)B * Dx * Dy * Dz;
   const float inv = loss_weight / (norm[0] + 1.1920929e-07f);
   float acc = 0.f;
@@ -148,10 +158,11 @@ ce_loss_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ lab
     const float* lg = logits + v * ncls;
     const int l = labels[v];
     float w = 0.f;
-    if (l != ignore && l < ncls && (mask == nullptr || mask[v] != 0)) w = cw != nullptr ? cw[l] : 1.f;
+    const bool in_mask = l != ignore && l < ncls && (mask == nullptr || mask[v] != 0);
+    if (in_mask) w = cw != nullptr ? cw[l] : 1.f;
     __nv_bfloat16* g = dlogits + (((size_t)b * Dy + y) * Dx + x) * ld + z * ncls;
     const bool word_ok = ((z * ncls) & 1) == 0 && (ld & 1) == 0;        // 4-byte aligned pair stores
-    if (w == 0.f) {
+    if (!in_mask) {
       if (word_ok) {
         uint32_t* g2 = reinterpret_cast<uint32_t*>(g);
         for (int k = 0; k < ncls / 2; ++k) g2[k] = 0u;
@@ -176,12 +187,22 @@ ce_loss_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ lab
       s += e[k];
     }
     acc += w * (mx + __logf(s) - ll);
-    const float wi = w * inv / s;
+    const float wi = w * inv / s, is = 1.f / s;
+    float dot = 0.f;
+    if (scal) {
+#pragma unroll
+      for (int k = 0; k < 32; ++k)
+        if (k < ncls) dot += (k == l ? s_gt[k] : s_gn[k]) * e[k] * is;
+    }
 #pragma unroll
     for (int k = 0; k < 32; k += 2) {
       if (k < ncls) {
-        const float a0 = wi * e[k] - (k == l ? w * inv : 0.f);
-        const float a1 = wi * e[k + 1] - (k + 1 == l ? w * inv : 0.f);
+        float a0 = wi * e[k] - (k == l ? w * inv : 0.f);
+        float a1 = wi * e[k + 1] - (k + 1 == l ? w * inv : 0.f);
+        if (scal) {
+          a0 += e[k] * is * ((k == l ? s_gt[k] : s_gn[k]) - dot);
+          if (k + 1 < ncls) a1 += e[k + 1] * is * ((k + 1 == l ? s_gt[k + 1] : s_gn[k + 1]) - dot);
+        }
         if (word_ok && k + 1 < ncls) {
           *reinterpret_cast<__nv_bfloat162*>(g + k) = __floats2bfloat162_rn(a0, a1);
         } else {
@@ -549,6 +570,143 @@ pack_conv_weights_kernel(const float* __restrict__ w, int Cout, int cin_total, i
   }
 }
 
+
+// ---- sem_scal / geo_scal statistics (semkitti_loss.py:136-225) ---------------------------------------------
+// Over the masked voxels (label != ignore, mask set): per class i  Sp_i = sum p_i, Nom_i = sum p_i [t == i],
+// Cnt_i = sum [t == i]; M = number of masked voxels.  Deterministic: warp shuffles in a fixed tree, per-block
+// partials [nblocks][3*32 + 1] reduced in order by occ_scal_coeffs_kernel.
+constexpr int kScalRow = 3 * 32 + 1;
+__global__ void __launch_bounds__(256)
+occ_scal_stats_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ labels, const uint8_t* __restrict__ mask,
+                      int ncls, int ignore, long nvox, float* __restrict__ partial) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  float sp[32];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) sp[k] = 0.f;
+  float nom = 0.f, cnt = 0.f, m = 0.f;               // lane i of a warp carries class i's Nom / Cnt
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long v0 = (long)blockIdx.x * blockDim.x + wid * 32; v0 < nvox; v0 += stride) {
+    const long v = v0 + lane;
+    int l = -1;
+    float pl = 0.f;
+    if (v < nvox) {
+      const int t = labels[v];
+      if (t != ignore && t < ncls && (mask == nullptr || mask[v] != 0)) {
+        l = t;
+        const float* lg = logits + v * ncls;
+        float e[32], mx = -INFINITY, s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          e[k] = k < ncls ? __ldg(lg + k) : -INFINITY;
+          mx = fmaxf(mx, e[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          e[k] = __expf(e[k] - mx);
+          s += e[k];
+        }
+        const float is = 1.f / s;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          sp[k] += e[k] * is;
+          if (k == l) pl = e[k] * is;
+        }
+        m += 1.f;
+      }
+    }
+    for (int i = 0; i < ncls; ++i) {                 // class i's target voxels of this warp iteration
+      const float a = warp_sum(l == i ? pl : 0.f), c = warp_sum(l == i ? 1.f : 0.f);
+      if (lane == i) {
+        nom += a;
+        cnt += c;
+      }
+    }
+  }
+  __shared__ float red[8][kScalRow];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    const float t = warp_sum(sp[k]);
+    if (lane == 0) red[wid][k] = t;
+  }
+  red[wid][32 + lane] = nom;
+  red[wid][64 + lane] = cnt;
+  m = warp_sum(m);
+  if (lane == 0) red[wid][96] = m;
+  __syncthreads();
+  for (int i = threadIdx.x; i < kScalRow; i += blockDim.x) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w][i];
+    partial[(size_t)blockIdx.x * kScalRow + i] = t;
+  }
+}
+
+__device__ __forceinline__ float scal_step(float x) {      // inverse_sigmoid's stepping (semkitti_loss.py:8-16)
+  if (x >= 1.f - 1e-5f) x -= 1e-5f;
+  if (x < 1e-5f) x += 1e-5f;
+  return x;
+}
+
+// One warp: lane i = class i.  out[0] = weight_sem * sem_scal, out[1] = weight_geo * geo_scal;
+// gt[i] / gn[i] = d(both terms)/d p_i of a masked voxel whose label is / is not i.
+__global__ void occ_scal_coeffs_kernel(const float* __restrict__ partial, int nblocks, int ncls, int non_empty,
+                                       float w_sem, float w_geo, float* __restrict__ out, float* __restrict__ gt,
+                                       float* __restrict__ gn) {
+  const int i = threadIdx.x;
+  float sp = 0.f, nom = 0.f, cnt = 0.f, M = 0.f;
+  for (int b = 0; b < nblocks; ++b) {
+    const float* p = partial + (size_t)b * kScalRow;
+    sp += p[i];
+    nom += p[32 + i];
+    cnt += p[64 + i];
+    M += p[96];
+  }
+  const float eps = 1e-5f;
+  float loss = 0.f, a = 0.f, bb = 0.f, sc = 0.f;          // a: d/dNom, bb: d/dSp, sc: coefficient of (1 - c)
+  const bool present = i < ncls - 1 && cnt > 0.f;
+  if (present) {
+    if (sp > 0.f) {
+      const float pr = scal_step(nom / (sp + eps));
+      loss -= __logf(pr);
+      a -= 1.f / (pr * (sp + eps));
+      bb += nom / (pr * (sp + eps) * (sp + eps));
+    }
+    const float rc = scal_step(nom / (cnt + eps));
+    loss -= __logf(rc);
+    a -= 1.f / (rc * (cnt + eps));
+    const float y = M - cnt;
+    if (y > 0.f) {
+      const float spc = scal_step((y - (sp - nom)) / (y + eps));
+      loss -= __logf(spc);
+      sc += 1.f / (spc * (y + eps));                        // d/dX = -1/(spc (y+eps)), dX/dp = -(1 - c)
+    }
+  }
+  const float npresent = warp_sum(present ? 1.f : 0.f);
+  const float lsem = npresent > 0.f ? warp_sum(loss) / npresent : 0.f;
+  const float ks = npresent > 0.f ? w_sem / npresent : 0.f;
+  float g_t = present ? ks * (a + bb) : 0.f;                // label == i: c = 1
+  float g_n = present ? ks * (bb + sc) : 0.f;               // label != i: c = 0
+  float lgeo = 0.f;
+  if (i == non_empty) {
+    // geo_scal on p_e = p[non_empty]: nonempty prob 1 - p_e, nonempty target t != non_empty
+    const float inter = (M - cnt) - (sp - nom), np = M - sp, nt = M - cnt;
+    const float pr = scal_step(inter / (np + eps)), rc = scal_step(inter / (nt + eps)), spc = scal_step(nom / (cnt + eps));
+    lgeo = -__logf(pr) - __logf(rc) - __logf(spc);
+    // label == non_empty (c = 1): d inter = 0, d np = -1, d(spec numerator) = +1
+    g_t += w_geo * (-(1.f / pr) * (inter / ((np + eps) * (np + eps))) - (1.f / spc) / (cnt + eps));
+    // label != non_empty (c = 0): d inter = -1, d np = -1
+    g_n += w_geo * (-(1.f / pr) * (-1.f / (np + eps) + inter / ((np + eps) * (np + eps))) + (1.f / rc) / (nt + eps));
+  }
+  lgeo = warp_sum(lgeo);
+  if (i < ncls) {
+    gt[i] = g_t;
+    gn[i] = g_n;
+  }
+  if (i == 0) {
+    out[0] = w_sem * lsem;
+    out[1] = w_geo * lgeo;
+  }
+}
+
 }  // namespace dhd
 
 using namespace dhd;
@@ -588,21 +746,39 @@ extern "C" int dhd_act_bwd(const void* dy, int dy_ld, int dy_coff, const void* y
   return DHD_OK;
 }
 
+extern "C" size_t dhd_occ_loss_workspace_bytes(void) {
+  return ((size_t)148 * 16 * kScalRow + 64) * sizeof(float);
+}
+
 extern "C" int dhd_occ_ce_loss(const float* logits, const uint8_t* labels, const uint8_t* mask,
                                const float* class_weight, int ncls, int ignore_index, int B, int Dx, int Dy, int Dz,
-                               float loss_weight, float* loss_and_norm, void* dlogits, int dl_ld, void* stream) {
-  DHD_REQUIRE(logits && labels && loss_and_norm && dlogits, "null pointer");
+                               float loss_weight, float weight_sem, float weight_geo, int non_empty_idx,
+                               float* losses, void* dlogits, int dl_ld, float* workspace, void* stream) {
+  DHD_REQUIRE(logits && labels && losses && dlogits, "null pointer");
   DHD_REQUIRE(B > 0 && Dx > 0 && Dy > 0 && Dz > 0 && ncls > 0 && ncls <= 32, "bad shape (ncls <= 32)");
   DHD_REQUIRE(dl_ld >= Dz * ncls, "dlogits rows are too short");
+  const bool scal = weight_sem != 0.f || weight_geo != 0.f;
+  DHD_REQUIRE(!scal || (workspace != nullptr && non_empty_idx >= 0 && non_empty_idx < ncls), "scal terms need the workspace");
   cudaStream_t st = (cudaStream_t)stream;
-  cudaError_t e = cudaMemsetAsync(loss_and_norm, 0, 2 * sizeof(float), st);
+  cudaError_t e = cudaMemsetAsync(losses, 0, 4 * sizeof(float), st);
   if (e != cudaSuccess) return fail((int)e, "%s: %ld", "memset(loss)", (long)e);
   const long nvox = (long)B * Dx * Dy * Dz;
   const int blocks = (int)min((nvox + 255) / 256, (long)sm_count() * 16);
-  ce_norm_kernel<<<blocks, 256, 0, st>>>(labels, mask, class_weight, ncls, ignore_index, nvox, loss_and_norm + 1);
+  float *gt = nullptr, *gn = nullptr;
+  if (scal) {
+    const int sblocks = (int)min((nvox + 255) / 256, (long)148 * 16);
+    gt = workspace + (size_t)148 * 16 * kScalRow;
+    gn = gt + 32;
+    occ_scal_stats_kernel<<<sblocks, 256, 0, st>>>(logits, labels, mask, ncls, ignore_index, nvox, workspace);
+    DHD_CUDA_LAUNCH_CHECK("occ_scal_stats");
+    occ_scal_coeffs_kernel<<<1, 32, 0, st>>>(workspace, sblocks, ncls, non_empty_idx, weight_sem, weight_geo, losses + 2,
+                                             gt, gn);
+    DHD_CUDA_LAUNCH_CHECK("occ_scal_coeffs");
+  }
+  ce_norm_kernel<<<blocks, 256, 0, st>>>(labels, mask, class_weight, ncls, ignore_index, nvox, losses + 1);
   DHD_CUDA_LAUNCH_CHECK("ce_norm");
   ce_loss_kernel<<<blocks, 256, 0, st>>>(logits, labels, mask, class_weight, ncls, ignore_index, B, Dx, Dy, Dz,
-                                         loss_weight, loss_and_norm + 1, loss_and_norm, (__nv_bfloat16*)dlogits, dl_ld);
+                                         loss_weight, losses + 1, losses, (__nv_bfloat16*)dlogits, dl_ld, gt, gn);
   DHD_CUDA_LAUNCH_CHECK("ce_loss");
   return DHD_OK;
 }

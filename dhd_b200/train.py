@@ -138,6 +138,8 @@ class PredictorTrainer:
         self.loss_weight = float(getattr(head.loss_occ, 'loss_weight', 1.0)) * float(head.weight_ce) \
             if head.loss_occ is not None else float(head.weight_ce)
         self.ignore_index = int(getattr(head.loss_occ, 'ignore_index', 255) or 255) if head.loss_occ is not None else 255
+        # sem_scal / geo_scal terms of predictor.loss (occ_head.py:129-131); free class = num_classes - 1
+        self.weight_sem, self.weight_geo = float(head.weight_sem), float(head.weight_geo)
         self._buf = {}
 
     def refresh(self):
@@ -167,18 +169,22 @@ class PredictorTrainer:
         self.saved = (x, t, u, out)
         return out.view(N, W, H, self.Dz, self.ncls)
 
-    def loss(self, voxel_semantics, mask_camera=None):
-        """Cross-entropy term of predictor.loss on the logits of the last forward.  Returns a 2-element
-        device tensor [loss, avg_factor]; the gradient w.r.t. the logits is kept for backward()."""
+    def loss(self, voxel_semantics, mask_camera=None, scal=True):
+        """predictor.loss on the logits of the last forward: returns a 4-element device tensor
+        [loss_occ, avg_factor, loss_voxel_sem_scal, loss_voxel_geo_scal] (the scal terms are 0 with scal=False);
+        the gradient of their sum w.r.t. the logits is kept for backward()."""
         x, t, u, out = self.saved
         N, H, W = x.N, x.H, x.W
         labels = voxel_semantics.to(torch.uint8).contiguous()
         mask = mask_camera.to(torch.uint8).contiguous() if mask_camera is not None else None
         dlog = self._act('dlog', N, H, W, self.nout_pad, zero=True)
-        res = torch.empty(2, device=self.device)
-        _lib.check(_lib.load().dhd_occ_ce_loss(_p(out), _p(labels), _p(mask), _p(self.class_weight), self.ncls,
-                                               self.ignore_index, N, W, H, self.Dz, self.loss_weight, _p(res),
-                                               _p(dlog.data), dlog.ld, _stream()), 'occ_ce_loss')
+        res = torch.empty(4, device=self.device)
+        lib = _lib.load()
+        ws = _workspace(self.device, lib.dhd_occ_loss_workspace_bytes())
+        _lib.check(lib.dhd_occ_ce_loss(_p(out), _p(labels), _p(mask), _p(self.class_weight), self.ncls,
+                                       self.ignore_index, N, W, H, self.Dz, self.loss_weight,
+                                       self.weight_sem if scal else 0.0, self.weight_geo if scal else 0.0, self.ncls - 1,
+                                       _p(res), _p(dlog.data), dlog.ld, _p(ws), _stream()), 'occ_ce_loss')
         self.dlog = dlog
         return res
 

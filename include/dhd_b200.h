@@ -234,14 +234,18 @@ int dhd_act_bwd(const void* dy, int dy_ld, int dy_coff, const void* y, int y_ld,
                 int C, int act, void* out, int out_ld, int out_coff, float* colsum, float* workspace,
                 const void* add, int add_ld, int add_coff, void* stream);
 /* (add, optional: a second bf16 gradient summed into dy first -- the identity path of a residual block) */
-/* predictor.loss, cross-entropy term (occ_head.py:102-131; mmdet CrossEntropyLoss with class_weight,
- * weight = mask_camera, avg_factor = sum mask*class_weight[label]): logits (B,Dx,Dy,Dz,ncls) fp32,
- * labels / mask (B,Dx,Dy,Dz) uint8 (mask or class_weight may be NULL).  loss_and_norm[0] = loss,
- * [1] = avg_factor; dlogits = d loss / d logits as bf16 NHWC rows [(b*Dy+y)*Dx+x][dl_ld], channel
- * z*ncls+k -- the input layout of the last Linear's backward GEMMs. */
+/* predictor.loss (occ_head.py:102-131): class-weighted masked cross-entropy (mmdet CrossEntropyLoss with
+ * class_weight, weight = mask_camera, avg_factor = sum mask*class_weight[label]) and, when weight_sem / weight_geo
+ * are non-zero, sem_scal_loss_with_mask + geo_scal_loss_with_mask (losses/semkitti_loss.py:136-225; needs
+ * workspace of dhd_occ_loss_workspace_bytes()).  logits (B,Dx,Dy,Dz,ncls) fp32, labels / mask (B,Dx,Dy,Dz) uint8
+ * (mask or class_weight may be NULL).  losses[0] = loss_occ, [1] = avg_factor, [2] = loss_voxel_sem_scal,
+ * [3] = loss_voxel_geo_scal; dlogits = d(sum of the terms)/d logits as bf16 NHWC rows [(b*Dy+y)*Dx+x][dl_ld],
+ * channel z*ncls+k -- the input layout of the last Linear's backward GEMMs. */
+size_t dhd_occ_loss_workspace_bytes(void);
 int dhd_occ_ce_loss(const float* logits, const uint8_t* labels, const uint8_t* mask,
                     const float* class_weight, int ncls, int ignore_index, int B, int Dx, int Dy, int Dz,
-                    float loss_weight, float* loss_and_norm, void* dlogits, int dl_ld, void* stream);
+                    float loss_weight, float weight_sem, float weight_geo, int non_empty_idx,
+                    float* losses, void* dlogits, int dl_ld, float* workspace, void* stream);
 /* backward of MGHS.depth_net's output head (lss_heightmap.py:482-489): depth = softmax over D (NCHW),
  * depth_grad / feat_grad from dhd_mghs_pool_bwd -> gradient w.r.t. the 1x1 convolution output, one bf16
  * NHWC row per pixel: [0,D) softmax backward, [D,D+C) feat_grad, [D+C,out_ld) zeros. */

@@ -177,7 +177,7 @@ def load_reference():
         UNet=un.UNet, CustomResNet=rn.CustomResNet, FPN_LSS=fp.FPN_LSS,
         MGHS=lh.MGHS, MGHS_Depth=lh.MGHS_Depth, MGHS_Stereo=lh.MGHS_Stereo,
         HeightNet=dn.HeightNet, DepthNet=dn.DepthNet, ASPP=dn.ASPP, SFA=mix.SFA,
-        predictor=oh.predictor, lss_heightmap=lh, depthnet=dn, mix=mix, occ_head=oh)
+        predictor=oh.predictor, lss_heightmap=lh, depthnet=dn, mix=mix, occ_head=oh, semkitti_loss=sk)
     _LOADED['ns'] = ns
     return ns
 

@@ -127,3 +127,28 @@ def test_product_synthetic_workload_matches_the_oracle_copy():
         b = O.synthetic_rig(3, 6, (256, 704), seed=seed, flip_bda=flip)
         for x, y in zip(a, b):
             assert torch.equal(x, y)
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason='reference tree not present')
+def test_loss_oracle_matches_reference_losses():
+    """oracle/loss_oracle.py (vectorised) against the unmodified semkitti_loss functions: values and gradients."""
+    from oracle import loss_oracle as LO
+    sk = ref_loader.load_reference().semkitti_loss
+    g = torch.Generator().manual_seed(4)
+    n = 4000
+    labels = torch.randint(0, 18, (n,), generator=g)
+    labels[:50] = 255
+    labels[labels == 5] = 6                         # one class absent from the target
+    mask = torch.rand(n, generator=g) < 0.6
+    for scale in (1.0, 6.0):
+        logits = (torch.randn(n, 18, generator=g) * scale)
+        for ref_fn, our_fn, kw in ((sk.sem_scal_loss_with_mask, LO.sem_scal_loss_with_mask, {}),
+                                   (sk.geo_scal_loss_with_mask, LO.geo_scal_loss_with_mask, dict(non_empty_idx=17))):
+            a = logits.clone().requires_grad_()
+            b = logits.clone().requires_grad_()
+            la = ref_fn(a, labels, mask.int(), **kw)
+            lb = our_fn(b, labels, mask, **kw)
+            la.backward()
+            lb.backward()
+            assert torch.allclose(la, lb, rtol=1e-5, atol=1e-6), (float(la), float(lb))
+            assert torch.allclose(a.grad, b.grad, rtol=1e-4, atol=1e-9)

@@ -40,12 +40,10 @@ def test_predictor_loss_and_grads(cuda_lib):
     sd = {k: v.clone().requires_grad_(v.dtype.is_floating_point) for k, v in head.state_dict().items()}
     xr = x.clone().requires_grad_()
     logits = DO.predictor_forward(sd, xr)
+    from oracle import loss_oracle as LO
     cw = head.cls_weights.float()
-    per = torch.nn.functional.cross_entropy(logits.reshape(-1, 18), labels.reshape(-1), weight=cw, reduction='none',
-                                            ignore_index=255)
-    valid = labels.reshape(-1)[mask.reshape(-1)]
-    avg = sum(((valid == i).sum() * cw[i] for i in range(18)))
-    loss = (per * mask.reshape(-1).float()).sum() / (avg + torch.finfo(torch.float32).eps)
+    terms = LO.predictor_loss(logits.reshape(-1, 18), labels.reshape(-1), mask.reshape(-1), cw)
+    loss = sum(terms.values())
     loss.backward()
     # ---- CUDA training path
     head = head.cuda()
@@ -58,8 +56,9 @@ def test_predictor_loss_and_grads(cuda_lib):
     res = tr.loss(labels.cuda(), mask.cuda())
     dx = tr.backward()
     torch.cuda.synchronize()
-    assert abs(float(res[0]) - float(loss.detach())) / float(loss.detach()) < 5e-3, (float(res[0]), float(loss.detach()))
-    assert abs(float(res[1]) - float(avg)) / float(avg) < 1e-5
+    for idx, key in ((0, 'loss_occ'), (2, 'loss_voxel_sem_scal'), (3, 'loss_voxel_geo_scal')):
+        want_l = float(terms[key].detach())
+        assert abs(float(res[idx]) - want_l) / want_l < 5e-3, (key, float(res[idx]), want_l)
     errs = {name: rel(p.grad, sd[name].grad) for name, p in head.named_parameters()}
     errs['x'] = rel(dx.float(), xr.grad)
     print('relative L2 gradient errors:', {k: round(v, 4) for k, v in errs.items()})
