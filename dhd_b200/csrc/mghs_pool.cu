@@ -853,7 +853,7 @@ struct PoolLane {          // per-lane issue state for the zero-run copies
 };
 
 template <bool HINT, int MINB>
-__global__ void __launch_bounds__(128, MINB) mghs_pool_stream_kernel(const PoolParams P, int zero_bytes, int windows, int prefetch) {
+__global__ void __launch_bounds__(128, MINB) mghs_pool_stream_kernel(const PoolParams P, int zero_bytes, int windows, int prefetch, int roles) {
   extern __shared__ __align__(128) uint8_t smem_pool[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int wpb = blockDim.x >> 5;
@@ -895,11 +895,59 @@ __global__ void __launch_bounds__(128, MINB) mghs_pool_stream_kernel(const PoolP
       }
     }
   };
+  // Warp roles (roles != 0): warp 0 of every CTA only ZERO-FILLS -- it walks the cell range in address order
+  // (256-cell chunks from its own counter) and bulk-copies the zero tile over every run of empty cells, never
+  // waiting on anything but its own cell_count loads -- while the other warps only GATHER (non-empty cells,
+  // columns out through the TMA unit).  The write stream of the 78 % empty cells then runs at fill speed
+  // whatever the gather warps are doing, instead of stalling whenever all warps sit in a dense region.
+  const bool zero_role = roles != 0 && wid == 0;
+  if (zero_role) {
+    constexpr int kZChunk = 256;
+    const int nz_chunks = (P.ncell + kZChunk - 1) / kZChunk;
+    int zc = 0;
+    if (lane == 0) zc = atomicAdd(P.sched + 2, 1);
+    zc = __shfl_sync(kFull, zc, 0);
+    while (zc < nz_chunks) {
+      int znext = 0;
+      if (lane == 0) znext = atomicAdd(P.sched + 2, 1);
+      const int c_lo = zc * kZChunk, c_hi = min(c_lo + kZChunk, P.ncell);
+      int run_lo = -1;                                  // start of the current run of empty cells (-1: none open)
+      int cnts[kZChunk / 32];                           // the whole chunk's counts: 8 independent loads in flight
+#pragma unroll
+      for (int q = 0; q < kZChunk / 32; ++q) {
+        const int c = c_lo + q * 32 + lane;
+        cnts[q] = c < c_hi && P.probe != 1 ? __ldg(P.cell_count + c) : 0;
+      }
+#pragma unroll
+      for (int q = 0; q < kZChunk / 32; ++q) {
+        const int c0 = c_lo + q * 32;
+        if (c0 >= c_hi) break;
+        const int nb = min(32, c_hi - c0);
+        const int cnt = cnts[q];
+        uint32_t nzm = __ballot_sync(kFull, cnt != 0);
+        if (nb < 32) nzm |= ~0u << nb;                  // beyond the chunk counts as "stop"
+        int pos = 0;
+        while (pos < 32) {
+          const uint32_t rest = nzm >> pos;
+          const int run = rest != 0 ? __ffs(rest) - 1 : 32 - pos;
+          if (run > 0 && run_lo < 0) run_lo = c0 + pos;
+          pos += run;
+          if (pos < 32) {                               // a non-empty cell (or the chunk end) closes the run
+            if (run_lo >= 0) zero_run(run_lo, min(c0 + pos, c_hi));
+            run_lo = -1;
+            ++pos;
+          }
+        }
+      }
+      if (run_lo >= 0) zero_run(run_lo, c_hi);
+      zc = __shfl_sync(kFull, znext, 0);
+    }
+  }
   const int per_win = (P.nch + windows - 1) / windows;
-  const int n_iter = per_win * windows;
+  const int n_iter = zero_role ? 0 : per_win * windows;
   auto fetch = [&]() {
-    int ch = 0;
-    if (lane == 0) ch = atomicAdd(P.sched, 1);
+    int ch = 0x7fffffff;                     // the zero-fill role takes no gather chunks
+    if (lane == 0 && !zero_role) ch = atomicAdd(P.sched, 1);
     return ch;                               // valid in lane 0; broadcast when consumed
   };
   int buf = 0;
@@ -1023,7 +1071,7 @@ __global__ void __launch_bounds__(128, MINB) mghs_pool_stream_kernel(const PoolP
                 buf ^= 1;
                 pos = cur_cell + 1;
               }
-              zero_run(pos, c);
+              if (!roles) zero_run(pos, c);
               pos = c;
               // ---- claim the other column buffer: its last copy must have read it; re-zero what that cell touched
               col2 = reinterpret_cast<float2*>(col_g + (size_t)buf * col_bytes);
@@ -1091,13 +1139,14 @@ __global__ void __launch_bounds__(128, MINB) mghs_pool_stream_kernel(const PoolP
         pos = cur_cell + 1;
       }
     }
-    zero_run(pos, cell_hi);
+    if (!roles) zero_run(pos, cell_hi);
   }
   if (lane == 0) {
     // the last warp to run dry re-arms the scheduler for the next launch on this workspace
     if (atomicAdd(P.sched + 1, 1) == warps - 1) {
       P.sched[0] = 0;
       P.sched[1] = 0;
+      P.sched[2] = 0;
     }
   }
   // shared memory must outlive every bulk copy that reads it
@@ -1452,7 +1501,8 @@ extern "C" int dhd_mghs_pool_fwd(const dhd_mghs_cfg* cfg, const float* depth, co
     DHD_REQUIRE(smem <= 227 * 1024, "pool column buffers do not fit in shared memory");
     const int minb = tuning("DHD_POOL_MINB", 4) >= 5 ? 5 : 4;
     const int prefetch = tuning("DHD_POOL_PREFETCH", 1);
-    void (*kern)(const PoolParams, int, int, int) =
+    const int roles = tuning("DHD_POOL_ROLES", 0);   // experiment: dedicated zero-fill warps (slower, profiles/r01_pool_sweep12/13.txt)
+    void (*kern)(const PoolParams, int, int, int, int) =
         hint ? (minb == 5 ? mghs_pool_stream_kernel<true, 5> : mghs_pool_stream_kernel<true, 4>)
              : (minb == 5 ? mghs_pool_stream_kernel<false, 5> : mghs_pool_stream_kernel<false, 4>);
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1460,7 +1510,7 @@ extern "C" int dhd_mghs_pool_fwd(const dhd_mghs_cfg* cfg, const float* depth, co
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem);
     const int per_sm = max(1, min(cap, occ));
     const int grid = min((P.nch + wpb - 1) / wpb, sm_count() * per_sm);
-    kern<<<grid, threads, smem, st>>>(P, zero_bytes, windows, prefetch);
+    kern<<<grid, threads, smem, st>>>(P, zero_bytes, windows, prefetch, roles);
     DHD_CUDA_LAUNCH_CHECK("mghs_pool_stream");
   } else if (layout == DHD_LAYOUT_NHWC && tuning("DHD_POOL_V", 4) == 3) {
     for (int p = 0; p < cfg->n_pass; ++p)
