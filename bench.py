@@ -189,7 +189,7 @@ def run_ours(args):
     bwd_ms = b0.elapsed_time(b1) / 10
     stage_ms = {}
     for name, fn in (('front(pack+depth_net+HeightNet+mask+prepare)', step._front), ('pool_fwd', step._pool),
-                     ('back(split+SFA+predictor+argmax)', step._back)):
+                     ('back(SFA+predictor+argmax)', step._back)):
         if step.graph is not None and name != 'pool_fwd':
             fn = step.graph[0].replay if name.startswith('front') else step.graph[1].replay
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -288,7 +288,8 @@ def run_ours(args):
                             'batch=%d per GPU; random-init weights' % B,
                 'stages': step.stage_names(), 'samples_per_gpu': B, 'precision': args.precision,
                 'pool_arithmetic': 'f32', 'cuda_graph': bool(graphed),
-                'encoders': 'BEV/voxel encoders are outside the path: resident synthetic (B,512,200,200) features',
+                'encoders': 'BEV/voxel encoders are outside the SURVEY 8 path: resident synthetic (B,512,200,200) bf16 NHWC features, the '
+                            'form dhd_b200.encoders produces (extras.with_encoders runs the real encoders instead)',
                 'l2': 'per-step working set > 1 GB (pool outputs 696 MB, BEV activations) > 126 MB L2, no explicit flush',
                 'sharding': 'batch axis, one process per GPU, no data-path collective',
             },
@@ -313,7 +314,7 @@ def run_ours(args):
                 'dense_tflops_algorithmic': {k: v / 1e12 for k, v in fl.items()},
                 'dense_tflop_per_s': sum(fl.values()) / 1e12 /
                 (1e-3 * max(1e-9, stage_ms['front(pack+depth_net+HeightNet+mask+prepare)'] +
-                            stage_ms['back(split+SFA+predictor+argmax)'])),
+                            stage_ms['back(SFA+predictor+argmax)'])),
                 'launches_per_step': step.launches_per_step,
                 'graph_error': getattr(step, 'graph_error', None),
             },

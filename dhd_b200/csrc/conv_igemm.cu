@@ -363,6 +363,13 @@ extern "C" int dhd_conv2d_fwd(const dhd_conv_desc* d, void* stream) {
                 "stride 2: output size must be ceil(input / 2) (3x3, pad 1)");
     DHD_REQUIRE(d->bw * 2 <= 256 && d->bh * 2 <= 256, "stride 2: tile box too large for the strided TMA box");
   }
+  if (d->mix_x != nullptr) {
+    DHD_REQUIRE(d->mix_a1 != nullptr && d->img_gate == nullptr && d->Cout % 32 == 0 && d->mix_ld % 8 == 0 &&
+                    d->mix_coff % 8 == 0 && d->mix_part_stride % 8 == 0 && ((uintptr_t)d->mix_x & 15) == 0 &&
+                    d->mix_parts >= 1 && d->mix_parts <= 3 && (d->stride == 0 || d->stride == 1),
+                "sfa mix epilogue: Cout % 32 == 0, 16-byte aligned [bev | vox] rows, no img_gate");
+    DHD_REQUIRE(conv_version() != 1, "the sfa mix epilogue needs the second-generation kernel");
+  }
   bool strided_out = false;
   for (int s = 0; s < d->n_seg; ++s) strided_out |= d->seg[s].b16_sX != 0;
   if (conv_version() != 1) return conv2_launch(d, (void*)enc, stream);

@@ -13,6 +13,8 @@
 //    (every bf16 activation and every NHWC fp32 tensor) leave through 128B-swizzled shared
 //    memory and TMA box stores: full-line coalesced writes, image borders clipped by the TMA
 //    unit; strided outputs (NCHW heads) keep the direct path.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -20,8 +22,7 @@ namespace dhd {
 
 constexpr int kM2 = 128;          // pixels per tile (TMEM lanes)
 constexpr int kK2 = 64;           // bf16 per smem row (128 B swizzle span)
-constexpr int kEpiWarps = 8;         // two groups of four: group g owns the odd/even 32-column chunks
-constexpr int kThreads2 = (kEpiWarps + 2) * 32;
+// G groups of four epilogue warps (G = 2 or 4): group g owns the 32-column chunks with chunk % G == g
 constexpr uint32_t kA2Bytes = kM2 * kK2 * 2;
 constexpr uint32_t kStageBufBytes = 16384;   // one TMA-store staging tile: 128 rows x 128 B
 
@@ -63,10 +64,12 @@ __device__ __forceinline__ bool tap_dead2(const dhd_conv_desc& d, int t, int x0,
   return xs >= iw || xs + d.bw * st <= 0 || ys >= ih || ys + d.bh * st <= 0;
 }
 
-template <int NT>
-__global__ void __launch_bounds__(kThreads2, 1)
+template <int NT, int G>
+__global__ void __launch_bounds__((4 * G + 2) * 32, 1)
 conv_igemm2_kernel(const __grid_constant__ Conv2Maps M, const __grid_constant__ Conv2Params P) {
   using C = Cfg2<NT>;
+  constexpr int kEpiWarps = 4 * G;
+  constexpr int kBufPerGroup = 4 / G;          // staging tiles per group: 4 x 16 KB in total
   extern __shared__ uint8_t smem_raw[];
   const dhd_conv_desc& d = P.d;
   const uint32_t raw = smem_u32(smem_raw);
@@ -97,7 +100,7 @@ conv_igemm2_kernel(const __grid_constant__ Conv2Maps M, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 2);          // one arrival per epilogue group
+      mbar_init(tempty_bar(s), G);          // one arrival per epilogue group
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -194,7 +197,7 @@ conv_igemm2_kernel(const __grid_constant__ Conv2Maps M, const __grid_constant__ 
     const int grp = warp >> 2;              // 0 / 1
     const int tid = threadIdx.x & 127;      // 0..127 inside the group
     const int gbar = 1 + grp;               // named barrier of this group
-    const uint32_t gstage = stagebuf + (uint32_t)grp * 2u * kStageBufBytes;
+    const uint32_t gstage = stagebuf + (uint32_t)grp * kBufPerGroup * kStageBufBytes;
     const int row = tid;
     int lt = 0;
     uint32_t nstore = 0;                    // TMA stores issued so far by this group (selects the staging buffer)
@@ -202,8 +205,8 @@ conv_igemm2_kernel(const __grid_constant__ Conv2Maps M, const __grid_constant__ 
       int img, x0, y0, n0;
       decode(tile, img, x0, y0, n0);
       const int as = lt & 1;
-      named_bar_sync(3, 256);               // everyone is done with the previous tile's vectors
-      for (int c = threadIdx.x; c < NT; c += 256) {
+      named_bar_sync(5, 128 * G);           // everyone is done with the previous tile's vectors
+      for (int c = threadIdx.x; c < NT; c += 128 * G) {
         const int ch = n0 + c;
         float sc = 1.f, bi = 0.f, ga = 1.f;
         if (ch < d.Cout) {
@@ -211,12 +214,13 @@ conv_igemm2_kernel(const __grid_constant__ Conv2Maps M, const __grid_constant__ 
           if (d.bias != nullptr) bi = __ldg(d.bias + ch);
           if (d.img_bias != nullptr) bi += __ldg(d.img_bias + (size_t)img * d.Cout + ch);
           if (d.img_gate != nullptr) ga = __ldg(d.img_gate + (size_t)img * d.Cout + ch);
+          if (d.mix_x != nullptr) ga = __ldg(d.mix_a1 + (size_t)img * d.Cout + ch);     // a1 rides in the gate slot
         }
         s_scale[c] = sc;
         s_bias[c] = bi;
         s_gate[c] = ga;
       }
-      named_bar_sync(3, 256);
+      named_bar_sync(5, 128 * G);
       mbar_wait(tfull_bar(as), (lt >> 1) & 1);
       tc_fence_after();
       const int px = x0 + row % d.bw, py = y0 + row / d.bw;
@@ -273,7 +277,7 @@ conv_igemm2_kernel(const __grid_constant__ Conv2Maps M, const __grid_constant__ 
         if (pass == 2) inv = 1.f / sum;
 #pragma unroll 1
         for (int cb = cb_lo; cb < cb_hi; ++cb) {
-          if ((npass == 1 || pass == 2) && (cb & 1) != grp) continue;     // row statistics need every chunk
+          if ((npass == 1 || pass == 2) && cb % G != grp) continue;       // row statistics need every chunk
           float v[32];
           affine(cb, v, act == DHD_ACT_SOFTMAX ? -INFINITY : 0.f);
           if (npass == 3 && pass == 0) {
@@ -305,7 +309,37 @@ conv_igemm2_kernel(const __grid_constant__ Conv2Maps M, const __grid_constant__ 
               break;
             default: break;
           }
-          if (has_gate) {
+          if (d.mix_x != nullptr) {
+            // v = spatial gate a2 -> fuse = a2 * a1*bev + (1 - a2) * (1 - a1)*vox (same operation order as dhd_sfa_mix)
+            const int cfirst_m = n0 + cb * 32;
+            if (valid && cfirst_m < d.Cout) {
+              const __nv_bfloat16* mp = reinterpret_cast<const __nv_bfloat16*>(d.mix_x) +
+                                        ((size_t)img * d.H * d.W + (size_t)py * d.W + px) * d.mix_ld + d.mix_coff + cfirst_m;
+#pragma unroll
+              for (int j8 = 0; j8 < 4; ++j8) {
+                float bev[8], vox[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) bev[j] = vox[j] = 0.f;
+                for (int p = 0; p < d.mix_parts; ++p) {
+                  const uint4 qb = __ldg(reinterpret_cast<const uint4*>(mp + (size_t)p * d.mix_part_stride + j8 * 8));
+                  const uint4 qv = __ldg(reinterpret_cast<const uint4*>(mp + (size_t)p * d.mix_part_stride + d.Cout + j8 * 8));
+                  const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&qb);
+                  const __nv_bfloat162* hv = reinterpret_cast<const __nv_bfloat162*>(&qv);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    bev[2 * j] += __low2float(hb[j]); bev[2 * j + 1] += __high2float(hb[j]);
+                    vox[2 * j] += __low2float(hv[j]); vox[2 * j + 1] += __high2float(hv[j]);
+                  }
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float a1 = s_gate[cb * 32 + j8 * 8 + j], g2 = v[j8 * 8 + j];
+                  const float b1 = __fmul_rn(a1, bev[j]), v1 = __fmul_rn(__fsub_rn(1.f, a1), vox[j]);
+                  v[j8 * 8 + j] = __fadd_rn(__fmul_rn(g2, b1), __fmul_rn(__fsub_rn(1.f, g2), v1));
+                }
+              }
+            }
+          } else if (has_gate) {
             const float4* g4 = reinterpret_cast<const float4*>(s_gate + cb * 32);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -317,8 +351,8 @@ conv_igemm2_kernel(const __grid_constant__ Conv2Maps M, const __grid_constant__ 
           // ---------------- fp32 output
           if (sg.out_f32 != nullptr) {
             if (tma32) {
-              const uint32_t buf = gstage + (nstore & 1u) * kStageBufBytes;
-              if (tid == 0) tma_store_wait_read<1>();      // the store that last used this buffer has read it
+              const uint32_t buf = gstage + (nstore % kBufPerGroup) * kStageBufBytes;
+              if (tid == 0) tma_store_wait_read<kBufPerGroup - 1>();   // the store that last used this buffer has read it
               named_bar_sync(gbar, 128);
               float4* dst = reinterpret_cast<float4*>(gen + (buf - base) + row * 128);
 #pragma unroll
@@ -354,8 +388,8 @@ conv_igemm2_kernel(const __grid_constant__ Conv2Maps M, const __grid_constant__ 
               }
               if (tma16) {
                 // 32 channels = 64-byte rows, SWIZZLE_64B: 16-byte chunk j of row r sits at j ^ ((r >> 1) & 3)
-                const uint32_t buf = gstage + (nstore & 1u) * kStageBufBytes;
-                if (tid == 0) tma_store_wait_read<1>();
+                const uint32_t buf = gstage + (nstore % kBufPerGroup) * kStageBufBytes;
+                if (tid == 0) tma_store_wait_read<kBufPerGroup - 1>();
                 named_bar_sync(gbar, 128);
                 uint4* dst = reinterpret_cast<uint4*>(gen + (buf - base) + row * 64);
 #pragma unroll
@@ -407,18 +441,18 @@ typedef CUresult (*EncodeTiledFn2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
                                    CUtensorMapFloatOOBfill);
 
-template <int NT>
+template <int NT, int G>
 static int launch2(const Conv2Maps& maps, const Conv2Params& P, cudaStream_t st) {
   using C = Cfg2<NT>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_igemm2_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_igemm2_kernel<NT, G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)C::kSmem);
     if (e != cudaSuccess) return fail((int)e, "%s: %ld", "cudaFuncSetAttribute(conv_igemm2)", (long)e);
     attr_set = true;
   }
   const int grid = min(P.total_tiles, sm_count());
-  conv_igemm2_kernel<NT><<<grid, kThreads2, C::kSmem, st>>>(maps, P);
+  conv_igemm2_kernel<NT, G><<<grid, (4 * G + 2) * 32, C::kSmem, st>>>(maps, P);
   DHD_CUDA_LAUNCH_CHECK("conv_igemm2");
   return DHD_OK;
 }
@@ -499,8 +533,16 @@ int conv2_launch(const dhd_conv_desc* d, void* encode, void* stream) {
   P.tiles_h = (d->H + d->bh - 1) / d->bh;
   P.n_tiles = (d->Cout + NT - 1) / NT;
   P.total_tiles = P.tiles_w * P.tiles_h * d->N * P.n_tiles;
-  if (NT == 256) return launch2<256>(maps, P, (cudaStream_t)stream);
-  return launch2<128>(maps, P, (cudaStream_t)stream);
+  static const int groups = [] {
+    const char* v = getenv("DHD_CONV_EPI_GROUPS");
+    return v != nullptr && atoi(v) == 4 ? 4 : 2;
+  }();
+  if (groups == 4) {
+    if (NT == 256) return launch2<256, 4>(maps, P, (cudaStream_t)stream);
+    return launch2<128, 4>(maps, P, (cudaStream_t)stream);
+  }
+  if (NT == 256) return launch2<256, 2>(maps, P, (cudaStream_t)stream);
+  return launch2<128, 2>(maps, P, (cudaStream_t)stream);
 }
 
 }  // namespace dhd

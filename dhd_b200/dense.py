@@ -54,6 +54,8 @@ class ConvDesc(ctypes.Structure):
         ('res_sN', ctypes.c_int64), ('res_sY', ctypes.c_int64), ('res_sX', ctypes.c_int64),
         ('n_seg', ctypes.c_int32), ('seg', ConvSeg * MAX_SEGS),
         ('stride', ctypes.c_int32), ('in_H', ctypes.c_int32), ('in_W', ctypes.c_int32),
+        ('mix_x', ctypes.c_void_p), ('mix_ld', ctypes.c_int32), ('mix_coff', ctypes.c_int32),
+        ('mix_parts', ctypes.c_int32), ('mix_part_stride', ctypes.c_int32), ('mix_a1', ctypes.c_void_p),
     ]
 
 
@@ -180,7 +182,7 @@ def tile_box(H, W):
 
 
 def conv2d(x, weight, Cout, ksize=1, dilation=1, precision='fp32', scale=None, bias=None,
-           img_bias=None, img_gate=None, residual=None, segs=None, stride=1):
+           img_bias=None, img_gate=None, residual=None, segs=None, stride=1, sfa_mix=None):
     """One fused convolution.  x: Act; weight: pack_weight() result with PRECISIONS[precision]
     parts; segs: list of dicts {c_lo, c_hi, act, out_f32 (tensor, strides (sN,sY,sX,sC)),
     out_act (Act or Act.slice), out_view (sN, sY, sX, offset): pixel strides / start offset in bf16
@@ -224,6 +226,14 @@ def conv2d(x, weight, Cout, ksize=1, dilation=1, precision='fp32', scale=None, b
         d.residual = rt.data_ptr()
         d.res_sN, d.res_sY, d.res_sX = sN, sY, sX
         keep.append(rt)
+    if sfa_mix is not None:                  # (x Act [bev | vox], a1 (N, Cout) fp32): SFA blend in the epilogue
+        mx, a1 = sfa_mix
+        if (mx.N, mx.H, mx.W) != (x.N, oH, oW) or mx.C < 2 * Cout or a1.shape != (x.N, Cout) or a1.dtype != torch.float32:
+            raise ValueError('sfa_mix operands do not match the layer')
+        d.mix_x, d.mix_ld, d.mix_coff = mx.data.data_ptr(), mx.ld, mx.coff
+        d.mix_parts, d.mix_part_stride = mx.parts, mx.part_stride
+        d.mix_a1 = a1.data_ptr()
+        keep += [mx.data, a1]
     d.n_seg = len(segs)
     for i, s in enumerate(segs):
         g = d.seg[i]

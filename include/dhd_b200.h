@@ -192,6 +192,13 @@ typedef struct dhd_conv_desc {
                                   and tap t reads input pixel (stride*y + tap_dy, stride*x + tap_dx)
                                   (CustomResNet's stride-2 blocks, backbones/resnet.py:47-52) */
   int32_t in_H, in_W;          /* input size when stride == 2 */
+  /* SFA spatial-gate blend fused into the epilogue (mix.py:52-57): with g = the activated output (the sigmoid
+   * gate a2), the layer writes  g * a1*bev + (1 - g) * (1 - a1)*vox  instead of g, where [bev | vox] = mix_x
+   * (bf16 NHWC, mix_parts split parts, bev at mix_coff, vox at mix_coff + Cout) and a1 = mix_a1 [N][Cout].
+   * NULL = off.  Saves the round trip of the gate tensor through HBM and the separate blend pass. */
+  const void* mix_x;
+  int32_t mix_ld, mix_coff, mix_parts, mix_part_stride;
+  const float* mix_a1;
 } dhd_conv_desc;
 
 int dhd_conv2d_fwd(const dhd_conv_desc* desc, void* stream);
