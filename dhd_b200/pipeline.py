@@ -207,7 +207,7 @@ class HotPathStep:
         L = self._last
         self.plan.raw_forward(L['depth'], L['feat'], L['pixmask'], self.outs, 'nhwc', workspace=self.workspace)
 
-    def _encode(self):
+    def _encode(self, parallel=True):
         """pool outputs -> (B, 512, Dy, Dx) = cat(bev encoder, three voxel encoders), DM:103-114: every encoder
         writes its channel slice of one NHWC buffer."""
         B, H, W = self.B, self.Dy, self.Dx
@@ -215,11 +215,22 @@ class HotPathStep:
             self._enc_act = D.Act.empty(B, H, W, 512, self.parts, self.device)
         enc = self._enc_act
         ins = [D.pack_nhwc(o, self.parts) for o in self.outs]          # fp32 pool outputs -> bf16 activations
-        self.e_neck(self.e_backbone(ins[0]), out=enc.slice(0, 256))
+        # the four encoders are independent: the three UNets run on side streams (parallel branches of the CUDA
+        # graph), so their small deep levels (12x12 .. 50x50 maps: 5-80 tiles for 148 SMs) share the GPU with the
+        # others' full-resolution layers instead of each leaving most SMs idle
+        main = torch.cuda.current_stream()
+        if not hasattr(self, '_enc_streams'):
+            self._enc_streams = [torch.cuda.Stream() for _ in self.e_voxel]
         lo = 256
-        for e, x in zip(self.e_voxel, ins[1:]):
-            e(x, out=enc.slice(lo, lo + e.n_classes))
+        for st, e, x in zip(self._enc_streams, self.e_voxel, ins[1:]):
+            st = st if parallel else main
+            st.wait_stream(main)
+            with torch.cuda.stream(st):
+                e(x, out=enc.slice(lo, lo + e.n_classes))
             lo += e.n_classes
+        self.e_neck(self.e_backbone(ins[0]), out=enc.slice(0, 256))
+        for st in self._enc_streams:
+            main.wait_stream(st)
         return enc
 
     def _back(self):

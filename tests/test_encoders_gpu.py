@@ -148,3 +148,24 @@ def test_dhd_detector_from_config_image_features_to_occupancy(cuda_lib):
         x3d = [DO.unet_forward(sub('img_voxel_encoder%d.' % i), t.cpu().contiguous()) for i, t in enumerate((lo, mid, hi))]
         want = DO.predictor_forward(sub('occ_head.'), DO.sfa_forward(sub('mix.'), torch.cat([x2d] + x3d, dim=1)))
     close(occ, want, 5e-4)
+
+
+def test_pipeline_encoders_on_parallel_streams_equal_sequential(cuda_lib):
+    """HotPathStep(encoders=True) runs the three UNets on side streams: same bits as one stream."""
+    from dhd_b200 import synth
+    from dhd_b200.pipeline import HotPathStep
+    cfg, B = synth.DHD_S, 1
+    step = HotPathStep(cfg, B, precision='bf16', use_graph=False, encoders=True)
+    host = step.make_host_inputs(synth.synthetic_rig(B, cfg['ncams'], cfg['input_size'], seed=3), seed=3)
+    step.alloc_static(host)
+    step.upload(host)
+    step._front()
+    step._pool()
+    a = step._encode(parallel=True).data.clone()
+    torch.cuda.synchronize()
+    b = step._encode(parallel=False).data.clone()
+    torch.cuda.synchronize()
+    assert torch.equal(a, b) and float(a.float().abs().max()) > 0
+    step._back()
+    torch.cuda.synchronize()
+    assert int(step.occ.max()) <= 17
