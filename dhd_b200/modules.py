@@ -160,9 +160,11 @@ class HeightNetEngine:
         h = linear_rows(h, self.se_r_w, self.se_r_b, 'relu')
         return linear_rows(h, self.se_e_w, self.se_e_b, 'sigmoid')
 
-    def __call__(self, x, mlp_input, softmax=True):
+    def __call__(self, x, mlp_input, softmax=True, hook=None):
         """x: Act (B*N, 256, fH, fW); returns height (B*N, H, fH, fW) fp32 NCHW (softmax-ed
-        unless softmax=False, which gives the raw HeightNet output the reference returns)."""
+        unless softmax=False, which gives the raw HeightNet output the reference returns).
+        hook: optional callable run once after the ASPP branches are enqueued (the pipeline forks the
+        geometry / binning kernels onto a side stream there, so they overlap the tail of this network)."""
         N, H, W, C, P, dev = x.N, x.H, x.W, self.C, self.parts, x.data.device
         new = lambda c: D.Act.empty(N, H, W, c, P, dev)
         nhwc = D.nhwc_strides(C, H, W)
@@ -170,9 +172,9 @@ class HeightNetEngine:
         h = new(C)
         h32 = torch.empty(N, H, W, C, device=dev)
         self.reduce(x, [dict(act='relu', out_act=h, out_f32=(h32, nhwc))], img_gate=gate)
-        return self.trunk(h, h32, softmax)
+        return self.trunk(h, h32, softmax, hook)
 
-    def trunk(self, h, h32, softmax=True):
+    def trunk(self, h, h32, softmax=True, hook=None):
         """BasicBlocks -> ASPP -> DCN -> 1x1 head on the gated feature map (Act + its fp32 copy)."""
         N, H, W, C, P, dev = h.N, h.H, h.W, self.C, self.parts, h.data.device
         new = lambda c: D.Act.empty(N, H, W, c, P, dev)
@@ -188,6 +190,9 @@ class HeightNetEngine:
             cat = new(4 * mid)
             for b, conv in enumerate(self.aspp_branches):
                 conv(h, [dict(act='relu', out_act=cat.slice(b * mid, (b + 1) * mid))])
+            if hook is not None:
+                hook()
+                hook = None
             x5 = linear_rows(mean_hw(h), self.gap_w, self.gap_b, 'relu')
             ib = linear_rows(x5, self.aspp_w5)
             h = new(C)
@@ -208,6 +213,8 @@ class HeightNetEngine:
                          precision=self.precision,
                          segs=[dict(out_act=out.slice(gi * cg, (gi + 1) * cg))])
             h = out
+        if hook is not None:
+            hook()
         height = torch.empty(N, self.H_bins, H, W, device=dev)
         self.head(h, [dict(act='softmax' if softmax else None,
                            out_f32=(height, D.nchw_strides(self.H_bins, H, W)))])

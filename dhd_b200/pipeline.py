@@ -192,15 +192,25 @@ class HotPathStep:
     def _front(self):
         s = self.static
         B, N = self.B, self.N
+        # geometry + binning depend on the camera tensors only: a side stream (a parallel branch of the graph)
+        # runs them under the HeightNet convolutions, which hold one CTA per SM and leave its other slots idle
+        main = torch.cuda.current_stream()
+        if not hasattr(self, '_prep_stream'):
+            self._prep_stream = torch.cuda.Stream()
+
+        def fork_prepare():        # late in HeightNet: the bins are still in L2 when the pool starts
+            self._prep_stream.wait_stream(main)
+            with torch.cuda.stream(self._prep_stream):
+                self.plan.prepare(frustum=self.frustum, sensor2ego=s['sensor2ego'], cam2imgs=s['cam2imgs'],
+                                  post_rots=s['post_rots'], post_trans=s['post_trans'], bda=s['bda'],
+                                  deterministic=self.deterministic, workspace=self.workspace)
         xa = D.pack_input(s['x'].view(B * N, self.Cin, self.fH, self.fW), self.parts)
         depth, feat = self.depth_engine(xa)
         mlp = self.vt.get_mlp_input(s['sensor2ego'], s['ego2global'], s['cam2imgs'], s['post_rots'],
                                     s['post_trans'], s['bda'])
-        height = self.height_engine(xa, mlp, softmax=True)
+        height = self.height_engine(xa, mlp, softmax=True, hook=fork_prepare)
         pixmask = height_to_mask(height, self.cfg['height_range'], self.cfg['mask_range'])
-        self.plan.prepare(frustum=self.frustum, sensor2ego=s['sensor2ego'], cam2imgs=s['cam2imgs'],
-                          post_rots=s['post_rots'], post_trans=s['post_trans'], bda=s['bda'],
-                          deterministic=self.deterministic, workspace=self.workspace)
+        main.wait_stream(self._prep_stream)
         self._last = {'depth': depth, 'feat': feat, 'height': height, 'pixmask': pixmask}
 
     def _pool(self):
