@@ -359,8 +359,8 @@ extern "C" int dhd_conv2d_fwd(const dhd_conv_desc* d, void* stream) {
                 "residual needs Cout % 32 == 0 and 16-byte aligned rows");
   DHD_REQUIRE(d->stride == 0 || d->stride == 1 || d->stride == 2, "stride must be 1 or 2");
   if (d->stride == 2) {
-    DHD_REQUIRE(d->in_H > 0 && d->in_W > 0 && d->H == (d->in_H + 1) / 2 && d->W == (d->in_W + 1) / 2,
-                "stride 2: output size must be ceil(input / 2) (3x3, pad 1)");
+    DHD_REQUIRE(d->in_H > 0 && d->in_W > 0 && d->H <= (d->in_H + 1) / 2 && d->W <= (d->in_W + 1) / 2,
+                "stride 2: output size must be at most ceil(input / 2)");
     DHD_REQUIRE(d->bw * 2 <= 256 && d->bh * 2 <= 256, "stride 2: tile box too large for the strided TMA box");
   }
   if (d->mix_x != nullptr) {
@@ -370,6 +370,9 @@ extern "C" int dhd_conv2d_fwd(const dhd_conv_desc* d, void* stream) {
                 "sfa mix epilogue: Cout % 32 == 0, 16-byte aligned [bev | vox] rows, no img_gate");
     DHD_REQUIRE(conv_version() != 1, "the sfa mix epilogue needs the second-generation kernel");
   }
+  if (d->stride != 2 && (d->in_H > 0 || d->in_W > 0))
+    DHD_REQUIRE(d->in_H >= d->H && d->in_W >= d->W && conv_version() != 1,
+                "in_H / in_W (input grid larger than the output grid) need the second-generation kernel");
   bool strided_out = false;
   for (int s = 0; s < d->n_seg; ++s) strided_out |= d->seg[s].b16_sX != 0;
   if (conv_version() != 1) return conv2_launch(d, (void*)enc, stream);

@@ -59,7 +59,7 @@ __device__ __forceinline__ float act2(float v, int act) {
 
 __device__ __forceinline__ bool tap_dead2(const dhd_conv_desc& d, int t, int x0, int y0) {
   const int st = d.stride > 1 ? d.stride : 1;
-  const int iw = d.stride > 1 ? d.in_W : d.W, ih = d.stride > 1 ? d.in_H : d.H;
+  const int iw = d.in_W > 0 ? d.in_W : d.W, ih = d.in_H > 0 ? d.in_H : d.H;
   const int xs = x0 * st + d.tap_dx[t], ys = y0 * st + d.tap_dy[t];
   return xs >= iw || xs + d.bw * st <= 0 || ys >= ih || ys + d.bh * st <= 0;
 }
@@ -466,7 +466,7 @@ int conv2_launch(const dhd_conv_desc* d, void* encode, void* stream) {
   const int NT = d->Cout > 128 ? 256 : 128;
   {
     const int st = d->stride > 1 ? d->stride : 1;
-    const cuuint64_t iw = st > 1 ? d->in_W : d->W, ih = st > 1 ? d->in_H : d->H;
+    const cuuint64_t iw = d->in_W > 0 ? d->in_W : d->W, ih = d->in_H > 0 ? d->in_H : d->H;   // input grid (>= output grid)
     cuuint64_t dims[4] = {(cuuint64_t)d->in_ld, iw, ih, (cuuint64_t)d->N};
     cuuint64_t strides[3] = {(cuuint64_t)d->in_ld * 2, iw * d->in_ld * 2, ih * iw * d->in_ld * 2};
     // stride-2 layers: the box spans 2*bw x 2*bh input pixels and the TMA unit keeps every 2nd one

@@ -105,6 +105,7 @@ conv_wgrad_kernel(const __grid_constant__ WgradMaps M, const __grid_constant__ W
   if (warp == 0) {
     if (lane == 0) {
       int it = 0;
+      const int xs = d.x_stride > 1 ? d.x_stride : 1;
       for (int t = t_lo; t < t_hi; ++t, ++it) {
         int img, x0, y0;
         decode(t, img, x0, y0);
@@ -117,7 +118,7 @@ conv_wgrad_kernel(const __grid_constant__ WgradMaps M, const __grid_constant__ W
           tma_load_4d(sa + i * kWgBoxBytes, &M.dy, full_bar(s), d.dy_coff + cob * 128 + i * 64, x0, y0, img);
         for (int i = 0; i < nbx; ++i)
           tma_load_4d(sa + (2 + i) * kWgBoxBytes, &M.x, full_bar(s), d.x_coff + cib * P.ncols + i * 64,
-                      x0 + d.tap_dx[tap], y0 + d.tap_dy[tap], img);
+                      x0 * xs + d.tap_dx[tap], y0 * xs + d.tap_dy[tap], img);
       }
     }
     __syncwarp();
@@ -235,6 +236,8 @@ extern "C" int dhd_conv2d_wgrad(const dhd_wgrad_desc* d, void* stream) {
   DHD_REQUIRE(((uintptr_t)d->x & 15) == 0 && ((uintptr_t)d->dy & 15) == 0 && ((uintptr_t)d->dw & 15) == 0 &&
                   ((uintptr_t)d->partial & 15) == 0, "pointers must be 16-byte aligned");
   DHD_REQUIRE(d->dy_coff + d->Cout <= d->dy_ld && d->x_coff + d->Cin <= d->x_ld, "channel range exceeds the row");
+  DHD_REQUIRE(d->x_stride == 0 || d->x_stride == 1 || (d->x_stride == 2 && d->x_H >= 2 * d->H - 1 && d->x_W >= 2 * d->W - 1),
+              "x_stride must be 1 or 2 (with the x_H x x_W grid covering the strided taps)");
   EncodeTiledFnW enc = (EncodeTiledFnW)conv_encode_fn();
   if (enc == nullptr) return fail(DHD_EUNSUPPORTED, "%s", "cuTensorMapEncodeTiled is unavailable");
   WgradParams P;
@@ -244,10 +247,13 @@ extern "C" int dhd_conv2d_wgrad(const dhd_wgrad_desc* d, void* stream) {
   cuuint32_t es[4] = {1, 1, 1, 1};
   {
     // the channel extent stops at the layer's last channel: a 64-channel box past it reads zeros
-    cuuint64_t dims[4] = {(cuuint64_t)(d->x_coff + d->Cin), (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
-    cuuint64_t strides[3] = {(cuuint64_t)d->x_ld * 2, (cuuint64_t)d->W * d->x_ld * 2,
-                             (cuuint64_t)d->H * d->W * d->x_ld * 2};
-    CUresult r = enc(&maps.x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)d->x, dims, strides, box, es,
+    const int xs = d->x_stride > 1 ? d->x_stride : 1;
+    const cuuint64_t xw = xs > 1 ? d->x_W : d->W, xh = xs > 1 ? d->x_H : d->H;
+    cuuint64_t dims[4] = {(cuuint64_t)(d->x_coff + d->Cin), xw, xh, (cuuint64_t)d->N};
+    cuuint64_t strides[3] = {(cuuint64_t)d->x_ld * 2, xw * d->x_ld * 2, xh * xw * d->x_ld * 2};
+    cuuint32_t xbox[4] = {64, (cuuint32_t)(P.sbw * xs), (cuuint32_t)(P.sbh * xs), 1};
+    cuuint32_t xes[4] = {1, (cuuint32_t)xs, (cuuint32_t)xs, 1};
+    CUresult r = enc(&maps.x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)d->x, dims, strides, xbox, xes,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(DHD_EINVAL, "%s: %ld", "cuTensorMapEncodeTiled(x) failed", (long)r);

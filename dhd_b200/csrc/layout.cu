@@ -344,6 +344,79 @@ upsample_bilinear_kernel(const __nv_bfloat16* __restrict__ in, int in_ld, int in
   store_parts8(out + (((size_t)n * oH + oy) * oW + ox) * o_ld + o_coff + c, r, parts, o_ps);
 }
 
+// MaxPool2d(2) backward: dx[2y+i, 2x+j] = dy[y, x] for the FIRST maximum of the window in (i, j) scan order (torch),
+// 0 elsewhere -- including the last row / column of an odd-sized map, which no window covers.
+__global__ void __launch_bounds__(256)
+maxpool2_bwd_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int x_coff, const __nv_bfloat16* __restrict__ dy,
+                    int dy_ld, int dy_coff, int N, int H, int W, int C, __nv_bfloat16* __restrict__ dx, int dx_ld,
+                    int dx_coff) {
+  const int oH = H / 2, oW = W / 2, cg = C / 8;
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)N * H * W * cg) return;
+  const int c = (int)(i % cg) * 8;
+  long p = i / cg;
+  const int xx = (int)(p % W);
+  p /= W;
+  const int yy = (int)(p % H), n = (int)(p / H);
+  float r[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) r[j] = 0.f;
+  const int oy = yy / 2, ox = xx / 2;
+  if (oy < oH && ox < oW) {
+    float g[8], v[4][8];
+    load_parts8(dy + (((size_t)n * oH + oy) * oW + ox) * dy_ld + dy_coff + c, 1, 0, g);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      load_parts8(x + (((size_t)n * H + 2 * oy + (k >> 1)) * W + 2 * ox + (k & 1)) * x_ld + x_coff + c, 1, 0, v[k]);
+    const int me = (yy & 1) * 2 + (xx & 1);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int best = 0;
+      float m = v[0][j];
+#pragma unroll
+      for (int k = 1; k < 4; ++k)
+        if (v[k][j] > m) {
+          m = v[k][j];
+          best = k;
+        }
+      if (best == me) r[j] = g[j];
+    }
+  }
+  store_parts8(dx + (((size_t)n * H + yy) * W + xx) * dx_ld + dx_coff + c, r, 1, 0);
+}
+
+// bilinear Upsample(align_corners=True) backward: every output pixel scatters its gradient to its 4 sources
+__global__ void __launch_bounds__(256)
+upsample_bilinear_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int dy_ld, int dy_coff, int N, int H, int W, int C,
+                             int oH, int oW, float* __restrict__ dx) {
+  const int cg = C / 8;
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)N * oH * oW * cg) return;
+  const int c = (int)(i % cg) * 8;
+  long p = i / cg;
+  const int ox = (int)(p % oW);
+  p /= oW;
+  const int oy = (int)(p % oH), n = (int)(p / oH);
+  const float sy = oH > 1 ? (float)oy * ((float)(H - 1) / (float)(oH - 1)) : 0.f;
+  const float sx = oW > 1 ? (float)ox * ((float)(W - 1) / (float)(oW - 1)) : 0.f;
+  const int y0 = (int)sy, x0 = (int)sx;
+  const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+  const float ly = sy - (float)y0, lx = sx - (float)x0;
+  float g[8];
+  load_parts8(dy + (((size_t)n * oH + oy) * oW + ox) * dy_ld + dy_coff + c, 1, 0, g);
+  float* base = dx + (size_t)n * H * W * C + c;
+  const float w[4] = {(1.f - ly) * (1.f - lx), (1.f - ly) * lx, ly * (1.f - lx), ly * lx};
+  const size_t off[4] = {((size_t)y0 * W + x0) * C, ((size_t)y0 * W + x1) * C, ((size_t)y1 * W + x0) * C,
+                         ((size_t)y1 * W + x1) * C};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (w[k] == 0.f) continue;
+    float4* q = reinterpret_cast<float4*>(base + off[k]);
+    atomicAdd(q, make_float4(w[k] * g[0], w[k] * g[1], w[k] * g[2], w[k] * g[3]));
+    atomicAdd(q + 1, make_float4(w[k] * g[4], w[k] * g[5], w[k] * g[6], w[k] * g[7]));
+  }
+}
+
 // ---- unpack: NHWC split-bf16 -> fp32 NCHW (hand-off to reference-layout consumers) --------
 __global__ void __launch_bounds__(256)
 unpack_nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ in, int ld, int coff, int part_stride,
@@ -732,5 +805,34 @@ extern "C" int dhd_upsample_bilinear(const void* in, int in_ld, int in_coff, int
       (const __nv_bfloat16*)in, in_ld, in_coff, in_part_stride, N, H, W, C, out_H, out_W, (__nv_bfloat16*)out, out_ld,
       out_coff, out_part_stride, parts);
   DHD_CUDA_LAUNCH_CHECK("upsample_bilinear");
+  return DHD_OK;
+}
+
+extern "C" int dhd_maxpool2_bwd(const void* x, int x_ld, int x_coff, const void* dy, int dy_ld, int dy_coff, int N,
+                                int H, int W, int C, void* dx, int dx_ld, int dx_coff, void* stream) {
+  DHD_REQUIRE(x && dy && dx && N > 0 && H >= 2 && W >= 2 && C > 0, "bad arguments");
+  DHD_REQUIRE(C % 8 == 0 && x_ld % 8 == 0 && x_coff % 8 == 0 && dy_ld % 8 == 0 && dy_coff % 8 == 0 && dx_ld % 8 == 0 &&
+                  dx_coff % 8 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)dy & 15) == 0 && ((uintptr_t)dx & 15) == 0,
+              "needs C % 8 == 0 and 16-byte aligned rows");
+  const long total = (long)N * H * W * (C / 8);
+  maxpool2_bwd_kernel<<<(int)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x, x_ld, x_coff, (const __nv_bfloat16*)dy, dy_ld, dy_coff, N, H, W, C, (__nv_bfloat16*)dx,
+      dx_ld, dx_coff);
+  DHD_CUDA_LAUNCH_CHECK("maxpool2_bwd");
+  return DHD_OK;
+}
+
+extern "C" int dhd_upsample_bilinear_bwd(const void* dy, int dy_ld, int dy_coff, int N, int H, int W, int C, int out_H,
+                                         int out_W, float* dx, void* stream) {
+  DHD_REQUIRE(dy && dx && N > 0 && H > 0 && W > 0 && C > 0 && out_H > 0 && out_W > 0, "bad arguments");
+  DHD_REQUIRE(C % 8 == 0 && dy_ld % 8 == 0 && dy_coff % 8 == 0 && ((uintptr_t)dy & 15) == 0 && ((uintptr_t)dx & 15) == 0,
+              "needs C % 8 == 0 and 16-byte aligned rows");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(dx, 0, (size_t)N * H * W * C * sizeof(float), st);
+  if (e != cudaSuccess) return fail((int)e, "%s: %ld", "memset(dx)", (long)e);
+  const long total = (long)N * out_H * out_W * (C / 8);
+  upsample_bilinear_bwd_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)dy, dy_ld, dy_coff, N, H,
+                                                                          W, C, out_H, out_W, dx);
+  DHD_CUDA_LAUNCH_CHECK("upsample_bilinear_bwd");
   return DHD_OK;
 }

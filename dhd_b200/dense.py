@@ -182,7 +182,8 @@ def tile_box(H, W):
 
 
 def conv2d(x, weight, Cout, ksize=1, dilation=1, precision='fp32', scale=None, bias=None,
-           img_bias=None, img_gate=None, residual=None, segs=None, stride=1, sfa_mix=None):
+           img_bias=None, img_gate=None, residual=None, segs=None, stride=1, sfa_mix=None, taps=None,
+           out_hw=None):
     """One fused convolution.  x: Act; weight: pack_weight() result with PRECISIONS[precision]
     parts; segs: list of dicts {c_lo, c_hi, act, out_f32 (tensor, strides (sN,sY,sX,sC)),
     out_act (Act or Act.slice), out_view (sN, sY, sX, offset): pixel strides / start offset in bf16
@@ -194,18 +195,26 @@ def conv2d(x, weight, Cout, ksize=1, dilation=1, precision='fp32', scale=None, b
                          (x.parts, weight.shape[2], precision, parts))
     d = ConvDesc()
     oH, oW = (x.H, x.W) if stride == 1 else ((x.H + 1) // 2, (x.W + 1) // 2)
+    if out_hw is not None:                   # an output grid smaller than the input allows (top-left part)
+        oH, oW = out_hw
     d.N, d.H, d.W = x.N, oH, oW
-    d.stride, d.in_H, d.in_W = stride, x.H, x.W
+    d.stride = stride
+    if stride != 1 or (oH, oW) != (x.H, x.W):
+        d.in_H, d.in_W = x.H, x.W
     d.Cin, d.Cout = x.C, Cout
-    taps = ksize * ksize
+    tap_list = taps                          # explicit input offsets [(dy, dx), ...] (must contain (0, 0))
+    taps = ksize * ksize if tap_list is None else len(tap_list)
     if weight.shape[0] != Cout or weight.shape[1] != taps or weight.shape[3] != x.C:
         raise ValueError('weight shape %s does not match Cout=%d taps=%d Cin=%d' %
                          (tuple(weight.shape), Cout, taps, x.C))
     d.taps = taps
     r = ksize // 2
     for t in range(taps):
-        d.tap_dy[t] = (t // ksize - r) * dilation
-        d.tap_dx[t] = (t % ksize - r) * dilation
+        if tap_list is not None:
+            d.tap_dy[t], d.tap_dx[t] = tap_list[t]
+        else:
+            d.tap_dy[t] = (t // ksize - r) * dilation
+            d.tap_dx[t] = (t % ksize - r) * dilation
     d.bw, d.bh = tile_box(oH, oW)
     d.in_ = x.data.data_ptr()
     d.in_ld, d.in_coff, d.in_part_stride = x.ld, x.coff, x.part_stride
@@ -277,28 +286,34 @@ class WgradDesc(ctypes.Structure):
         ('x', ctypes.c_void_p), ('x_ld', ctypes.c_int32), ('x_coff', ctypes.c_int32),
         ('dy', ctypes.c_void_p), ('dy_ld', ctypes.c_int32), ('dy_coff', ctypes.c_int32),
         ('scale', ctypes.c_void_p), ('dw', ctypes.c_void_p), ('partial', ctypes.c_void_p),
-        ('accumulate', ctypes.c_int32),
+        ('accumulate', ctypes.c_int32), ('x_stride', ctypes.c_int32), ('x_H', ctypes.c_int32), ('x_W', ctypes.c_int32),
     ]
 
 
 _WGRAD_WS = {}
 
 
-def conv2d_wgrad(x, dy, Cout, ksize=1, dilation=1, scale=None, out=None, accumulate=False):
+def conv2d_wgrad(x, dy, Cout, ksize=1, dilation=1, scale=None, out=None, accumulate=False, stride=1, taps=None):
     """Weight gradient of a stride-1 'same' convolution: x, dy are Acts (part 0 is used: bf16
     operands, fp32 accumulation).  Returns dw fp32 (Cout, ksize*ksize, Cin) -- the tap-major layout
     of pack_weight(); `weight_grad_to_torch` turns it into (Cout, Cin, kh, kw)."""
-    if (x.N, x.H, x.W) != (dy.N, dy.H, dy.W) or dy.C < Cout:
+    if x.N != dy.N or dy.C < Cout or (stride == 1 and (x.H, x.W) != (dy.H, dy.W)):
         raise ValueError('x / dy shapes do not match')
     d = WgradDesc()
-    d.N, d.H, d.W, d.Cin, d.Cout = x.N, x.H, x.W, x.C, Cout
-    taps = ksize * ksize
+    d.N, d.H, d.W, d.Cin, d.Cout = x.N, dy.H, dy.W, x.C, Cout          # the pixel loop runs over dy's grid
+    if stride != 1:                          # x sampled at (stride*y + tap, stride*x + tap) of its own grid
+        d.x_stride, d.x_H, d.x_W = stride, x.H, x.W
+    tap_list = taps
+    taps = ksize * ksize if tap_list is None else len(tap_list)
     d.taps = taps
     r = ksize // 2
     for t in range(taps):
-        d.tap_dy[t] = (t // ksize - r) * dilation
-        d.tap_dx[t] = (t % ksize - r) * dilation
-    d.bw, d.bh = tile_box(x.H, x.W)
+        if tap_list is not None:
+            d.tap_dy[t], d.tap_dx[t] = tap_list[t]
+        else:
+            d.tap_dy[t] = (t // ksize - r) * dilation
+            d.tap_dx[t] = (t % ksize - r) * dilation
+    d.bw, d.bh = tile_box(dy.H, dy.W)
     d.x, d.x_ld, d.x_coff = x.data.data_ptr(), x.ld, x.coff
     d.dy, d.dy_ld, d.dy_coff = dy.data.data_ptr(), dy.ld, dy.coff
     if scale is not None:

@@ -61,11 +61,13 @@ class _TrainConv:
     """One convolution of a trainable module: fp32 master weight lives in the torch parameter;
     `refresh()` re-packs the bf16 forward and data-gradient weights after an optimizer step."""
 
-    def __init__(self, weight, bias, bn, ksize, dilation=1, cin_pad=None, cout_pad=None, cols=None):
+    def __init__(self, weight, bias, bn, ksize, dilation=1, cin_pad=None, cout_pad=None, cols=None, stride=1):
         """cols=(lo, hi): the layer uses input-channel columns [lo, hi) of `weight` only (a branch of a
         concatenation whose other columns are handled elsewhere)."""
         self.weight, self.bias_p, self.bn = weight, bias, bn
-        self.ksize, self.dilation, self.cols = ksize, dilation, cols
+        self.ksize, self.dilation, self.cols, self.stride = ksize, dilation, cols, stride
+        if stride not in (1, 2) or (stride == 2 and (ksize != 3 or dilation != 1)):
+            raise NotImplementedError('stride-2 layers: 3x3, pad 1')
         self.Cout = weight.shape[0]
         self.Cin = weight.shape[1] if cols is None else cols[1] - cols[0]
         self.cin_pad = cin_pad or self.Cin          # forward input channels (zero padded to % 64)
@@ -96,15 +98,35 @@ class _TrainConv:
         _lib.check(_lib.load().dhd_pack_conv_weights(_p(w.detach()), self.Cout, cin_total, taps, col_lo, self.Cin,
                                                      _p(self.scale), _p(self.w_fwd), self.cin_pad, _p(self.w_bwd),
                                                      self.cout_pad, 0, _stream()), 'pack_conv_weights')
+        if self.stride == 2:
+            # data gradient of a stride-2 3x3 / pad-1 layer, one stride-1 convolution per output parity phase
+            # (py, px): dx[2u+py, 2v+px] = sum over the taps k with k = p+1 (mod 2) of dy[u + (p+1-k)/2, ...] w[k]
+            wd = w.detach().float()
+            if self.scale is not None:
+                wd = wd * self.scale.view(-1, 1, 1, 1)
+            cand = {0: [(1, 0)], 1: [(2, 0), (0, 1)]}                  # parity -> [(kernel index, dy offset)], (.., 0) first
+            self.phases = []
+            for py in range(2):
+                for px in range(2):
+                    offs, ws = [], []
+                    for ky, oy in cand[py]:
+                        for kx, ox in cand[px]:
+                            offs.append((oy, ox))
+                            ws.append(wd[:, :, ky, kx].t())           # (Cin, Cout)
+                    wp = torch.stack(ws, dim=1)                        # (Cin, taps, Cout)
+                    if self.cout_pad != self.Cout:
+                        wp = torch.nn.functional.pad(wp, (0, self.cout_pad - self.Cout))
+                    self.phases.append((py, px, offs, wp.unsqueeze(2).to(torch.bfloat16).contiguous()))
 
     def forward(self, x, segs, **kw):
         return D.conv2d(x, self.w_fwd, self.Cout, ksize=self.ksize, dilation=self.dilation, precision='bf16',
-                        scale=self.scale, bias=self.bias, segs=segs, **kw)
+                        scale=self.scale, bias=self.bias, segs=segs, stride=self.stride, **kw)
 
     def backward(self, x, dy, dx_segs=None, bias_sums=None, **kw):
         """dy: Act = gradient w.r.t. this layer's pre-activation output (channels >= Cout zero).
         Accumulates weight / bias gradients; writes dx through `dx_segs` (conv2d segs) if given."""
-        dw = D.conv2d_wgrad(x, dy, self.Cout, ksize=self.ksize, dilation=self.dilation, scale=self.scale)
+        dw = D.conv2d_wgrad(x, dy, self.Cout, ksize=self.ksize, dilation=self.dilation, scale=self.scale,
+                            stride=self.stride)
         if x.C != self.Cin:
             dw = dw[:, :, :self.Cin]
         g = D.weight_grad_to_torch(dw.contiguous(), self.ksize)
@@ -114,7 +136,15 @@ class _TrainConv:
             _acc(self.weight, g if self.weight.dim() == 4 else g[:, :, 0, 0])
         if self.bias_p is not None and bias_sums is not None:      # a conv bias under a frozen BN sees the BN scale
             _acc(self.bias_p, bias_sums[:self.Cout] if self.bn is None else bias_sums[:self.Cout] * self.scale)
-        if dx_segs is not None:
+        if dx_segs is not None and self.stride == 2:
+            if x.H % 2 or x.W % 2 or kw or len(dx_segs) != 1 or dx_segs[0].get('out_act') is None:
+                raise NotImplementedError('stride-2 data gradient: even input size, one bf16 output')
+            out = dx_segs[0]['out_act']
+            ld = out.ld
+            for py, px, offs, wp in self.phases:
+                D.conv2d(dy, wp, self.cin_pad, precision='bf16', taps=offs,
+                         segs=[dict(out_act=out, out_view=(x.H * x.W * ld, 2 * x.W * ld, 2 * ld, (py * x.W + px) * ld))])
+        elif dx_segs is not None:
             D.conv2d(dy, self.w_bwd, self.cin_pad, ksize=self.ksize, dilation=self.dilation, precision='bf16',
                      segs=dx_segs, **kw)
 
@@ -615,3 +645,356 @@ class HeightNetTrainer:
         _acc(mlp.fc1.weight, lin(dz1.t().contiguous(), m_bn.t().contiguous()))
         _acc(mlp.fc1.bias, dz1.sum(0))
         return dx
+
+
+class _TrainConvT:
+    """ConvTranspose2d(kernel 2, stride 2) (unet.py:86) for training: forward = four 1x1 GEMMs writing strided
+    views; data gradient = ONE stride-2 convolution with the 2x2 taps over the up-sampled gradient; weight gradient =
+    the wgrad kernel with the operand roles swapped (the up-sampled gradient is the strided operand)."""
+    TAPS = [(0, 0), (0, 1), (1, 0), (1, 1)]
+
+    def __init__(self, m):
+        self.m = m
+        self.Cin, self.Cout = m.weight.shape[0], m.weight.shape[1]
+        self.refresh()
+
+    def refresh(self):
+        w = self.m.weight.detach().float()                             # (Cin, Cout, 2, 2)
+        self.w_f = [w[:, :, i, j].t().contiguous()[:, None, None, :].to(torch.bfloat16).contiguous()
+                    for i in range(2) for j in range(2)]               # (Cout, 1, 1, Cin)
+        self.w_b = w.permute(0, 2, 3, 1).reshape(self.Cin, 4, 1, self.Cout).to(torch.bfloat16).contiguous()
+        self.bias = self.m.bias.detach() if self.m.bias is not None else None
+
+    def forward(self, x, out):
+        ld = out.ld
+        for i in range(2):
+            for j in range(2):
+                D.conv2d(x, self.w_f[2 * i + j], self.Cout, precision='bf16', bias=self.bias,
+                         segs=[dict(out_act=out, out_view=(out.H * out.W * ld, 2 * out.W * ld, 2 * ld,
+                                                           (i * out.W + j) * ld))])
+
+    def backward(self, x, dy, dx):
+        """x: Act (N, Cin, H, W); dy: Act slice on the (>= 2H x 2W) output grid, pad rows / columns already zeroed;
+        dx: Act (N, Cin, H, W) written."""
+        _, sums = act_bwd(dy, None, None, want_sums=True)
+        if self.m.bias is not None:
+            _acc(self.m.bias, sums[0][:self.Cout])
+        dw = D.conv2d_wgrad(dy, x, self.Cin, taps=self.TAPS, stride=2)           # (Cin, 4, Cout)
+        _acc(self.m.weight, dw.view(self.Cin, 2, 2, self.Cout).permute(0, 3, 1, 2))
+        D.conv2d(dy, self.w_b, self.Cin, precision='bf16', taps=self.TAPS, stride=2, out_hw=(x.H, x.W),
+                 segs=[dict(out_act=dx)])
+
+
+class _TrainDoubleConv:
+    """(conv3x3 -> frozen BN -> ReLU) x 2, unet.py:45-61."""
+
+    def __init__(self, seq):
+        self.c1 = _TrainConv(seq[0].weight, None, seq[1], 3)
+        self.c2 = _TrainConv(seq[3].weight, None, seq[4], 3)
+        self.mid, self.Cout = self.c1.Cout, self.c2.Cout
+
+    def refresh(self):
+        self.c1.refresh()
+        self.c2.refresh()
+
+    def forward(self, x, out, tmp):
+        self.c1.forward(x, [dict(act='relu', out_act=tmp)])
+        self.c2.forward(tmp, [dict(act='relu', out_act=out)])
+
+    def backward(self, x, tmp, dy, dtmp, dx_segs):
+        """dy: gradient w.r.t. the block output, already masked by its ReLU."""
+        self.c2.backward(tmp, dy, [dict(out_act=dtmp)])
+        act_bwd(dtmp, tmp, 'relu')
+        self.c1.backward(x, dtmp, dx_segs)
+
+
+class UNetTrainer:
+    """UNet (unet.py:6-141, bilinear=False) with frozen BatchNorm: forward with saved activations + backward."""
+
+    def __init__(self, net, device='cuda'):
+        self.net, self.device = net, device
+        self.inc = _TrainDoubleConv(net.inc.double_conv)
+        self.down = [_TrainDoubleConv(getattr(net, 'down%d' % k).maxpool_conv[1].double_conv) for k in range(1, 5)]
+        self.upT = [_TrainConvT(getattr(net, 'up%d' % k).up) for k in range(1, 5)]
+        self.upC = [_TrainDoubleConv(getattr(net, 'up%d' % k).conv.double_conv) for k in range(1, 5)]
+        self.outc = _TrainConv(net.outc.conv.weight, net.outc.conv.bias, None, 1,
+                               cout_pad=(net.outc.conv.weight.shape[0] + 63) // 64 * 64)
+        self.n_classes = self.outc.Cout
+        self._buf = {}
+
+    def refresh(self):
+        for m in [self.inc, self.outc] + self.down + self.upT + self.upC:
+            m.refresh()
+
+    def _act(self, name, N, H, W, C, zero=False):
+        key = (name, N, H, W, C)
+        if key not in self._buf:
+            a = D.Act.empty(N, H, W, C, 1, self.device)
+            if zero:
+                a.data.zero_()
+            self._buf[key] = a
+        return self._buf[key]
+
+    def forward(self, x, out=None):
+        N = x.N
+        sizes = [(x.H, x.W)]
+        for _ in range(4):
+            sizes.append((sizes[-1][0] // 2, sizes[-1][1] // 2))
+        chans = [self.inc.Cout] + [d.Cout for d in self.down]
+        cats = [self._act('cat%d' % k, N, sizes[k][0], sizes[k][1], 2 * chans[k], zero=True) for k in range(4)]
+        skip = [cats[k].slice(0, chans[k]) for k in range(4)]
+        tmps = {'inc': self._act('tmp0', N, sizes[0][0], sizes[0][1], self.inc.mid)}
+        self.inc.forward(x, skip[0], tmps['inc'])
+        cur, pooled = skip[0], []
+        from .encoders import maxpool2
+        for k in range(4):
+            H, W = sizes[k + 1]
+            pk = self._act('pool%d' % k, N, H, W, chans[k])
+            maxpool2(cur, pk)
+            pooled.append(pk)
+            dst = skip[k + 1] if k < 3 else self._act('bottom', N, H, W, chans[4])
+            tmps['d%d' % k] = self._act('tmpd%d' % k, N, H, W, self.down[k].mid)
+            self.down[k].forward(pk, dst, tmps['d%d' % k])
+            cur = dst
+        bottom, decs = cur, []
+        for k in range(4):
+            lvl = 3 - k
+            H, W = sizes[lvl]
+            self.upT[k].forward(cur, cats[lvl].slice(chans[lvl], 2 * chans[lvl]))
+            dst = self._act('dec%d' % lvl, N, H, W, self.upC[k].Cout)
+            tmps['u%d' % k] = self._act('tmpu%d' % lvl, N, H, W, self.upC[k].mid)
+            self.upC[k].forward(cats[lvl], dst, tmps['u%d' % k])
+            decs.append(dst)
+            cur = dst
+        if out is None:
+            out = self._act('out', N, sizes[0][0], sizes[0][1], self.outc.cout_pad)
+        self.outc.forward(cur, [dict(out_act=out)])
+        self.saved = dict(x=x, sizes=sizes, chans=chans, cats=cats, skip=skip, tmps=tmps, pooled=pooled, bottom=bottom,
+                          decs=decs)
+        return out
+
+    def backward(self, dout, dx_f32=None):
+        """dout: Act (>= n_classes channels; channels beyond n_classes zero).  dx_f32: optional (tensor, strides)
+        receiving dL/dx in fp32 (the layout dhd_mghs_pool_bwd reads); returns the bf16 Act otherwise."""
+        sv = self.saved
+        x, sizes, chans, cats, skip, tmps = sv['x'], sv['sizes'], sv['chans'], sv['cats'], sv['skip'], sv['tmps']
+        pooled, bottom, decs = sv['pooled'], sv['bottom'], sv['decs']
+        N = x.N
+        lib = _lib.load()
+        _, sums = act_bwd(dout, None, None, want_sums=True)
+        y4 = decs[3]
+        d = self._act('g_dec0', N, y4.H, y4.W, y4.C)
+        self.outc.backward(y4, dout, [dict(out_act=d)], bias_sums=sums[0])
+        dskip = [None] * 4
+        for k in range(3, -1, -1):                                   # up4 .. up1
+            lvl = 3 - k
+            H, W = sizes[lvl]
+            blk, y = self.upC[k], decs[k]
+            act_bwd(d, y, 'relu')
+            dcat = self._act('g_cat%d' % lvl, N, H, W, 2 * chans[lvl])
+            blk.backward(cats[lvl], tmps['u%d' % k], d, self._act('g_tmpu%d' % lvl, N, H, W, blk.mid),
+                         [dict(out_act=dcat)])
+            dskip[lvl] = dcat.slice(0, chans[lvl])
+            src = decs[k - 1] if k > 0 else bottom                    # the map the transposed conv up-sampled
+            dup = dcat.slice(chans[lvl], 2 * chans[lvl])
+            if H != 2 * src.H:                                        # pad row / column of the odd-sized level
+                dcat.data[:, 2 * src.H:, :, chans[lvl]:] = 0
+            if W != 2 * src.W:
+                dcat.data[:, :, 2 * src.W:, chans[lvl]:] = 0
+            d = self._act('g_src%d' % lvl, N, src.H, src.W, src.C)
+            self.upT[k].backward(src, dup, d)
+        # d = dL/d bottom; the contracting path, deepest first
+        for k in range(3, -1, -1):
+            blk = self.down[k]
+            y = bottom if k == 3 else skip[k + 1]
+            H, W = y.H, y.W
+            if k < 3:                                                  # decoder skip gradient + deeper level's
+                act_bwd(d, y, 'relu', add=dskip[k + 1])
+            else:
+                act_bwd(d, y, 'relu')
+            dpool = self._act('g_pool%d' % k, N, H, W, chans[k])
+            blk.backward(pooled[k], tmps['d%d' % k], d, self._act('g_tmpd%d' % k, N, H, W, blk.mid), [dict(out_act=dpool)])
+            xin = skip[k]
+            d = self._act('g_x%d' % k, N, xin.H, xin.W, chans[k])
+            _lib.check(lib.dhd_maxpool2_bwd(_p(xin.data), xin.ld, xin.coff, _p(dpool.data), dpool.ld, dpool.coff, N,
+                                            xin.H, xin.W, chans[k], _p(d.data), d.ld, d.coff, _stream()), 'maxpool2_bwd')
+        act_bwd(d, skip[0], 'relu', add=dskip[0])
+        if dx_f32 is not None:
+            segs = [dict(out_f32=dx_f32)]
+            dx = None
+        else:
+            dx = self._act('g_in', N, x.H, x.W, x.C)
+            segs = [dict(out_act=dx)]
+        self.inc.backward(x, tmps['inc'], d, self._act('g_tmp0', N, x.H, x.W, self.inc.mid), segs)
+        return dx
+
+
+class CustomResNetTrainer:
+    """CustomResNet (resnet.py:10-80, block_type='Basic') with frozen BatchNorm: forward + backward."""
+
+    def __init__(self, net, device='cuda'):
+        self.device = device
+        self.stages = []
+        for stage in net.layers:
+            blocks = []
+            for b in stage:
+                st = b.conv1.stride[0]
+                c1 = _TrainConv(b.conv1.weight, None, b.bn1, 3, stride=st)
+                c2 = _TrainConv(b.conv2.weight, None, b.bn2, 3)
+                ds = _TrainConv(b.downsample.weight, b.downsample.bias, None, 3, stride=st) if b.downsample is not None else None
+                blocks.append((c1, c2, ds))
+            self.stages.append(blocks)
+        self.output_ids = list(net.backbone_output_ids)
+        self._buf = {}
+
+    def refresh(self):
+        for blocks in self.stages:
+            for c1, c2, ds in blocks:
+                c1.refresh()
+                c2.refresh()
+                if ds is not None:
+                    ds.refresh()
+
+    def _act(self, name, N, H, W, C):
+        key = (name, N, H, W, C)
+        if key not in self._buf:
+            self._buf[key] = D.Act.empty(N, H, W, C, 1, self.device)
+        return self._buf[key]
+
+    def _f32(self, name, *shape):
+        key = (name,) + shape
+        if key not in self._buf:
+            self._buf[key] = torch.empty(*shape, device=self.device)
+        return self._buf[key]
+
+    def forward(self, x):
+        self.saved, feats, x32 = [], [], None
+        for si, blocks in enumerate(self.stages):
+            for bi, (c1, c2, ds) in enumerate(blocks):
+                tag = '%d_%d' % (si, bi)
+                oH, oW = (x.H, x.W) if c1.stride == 1 else ((x.H + 1) // 2, (x.W + 1) // 2)
+                nh = D.nhwc_strides(c2.Cout, oH, oW)
+                t = self._act('t' + tag, x.N, oH, oW, c1.Cout)
+                c1.forward(x, [dict(act='relu', out_act=t)])
+                if ds is not None:
+                    idn = self._f32('idn' + tag, x.N, oH, oW, c2.Cout)
+                    ds.forward(x, [dict(out_f32=(idn, nh))])
+                else:
+                    idn = x32
+                out, out32 = self._act('o' + tag, x.N, oH, oW, c2.Cout), self._f32('o32' + tag, x.N, oH, oW, c2.Cout)
+                c2.forward(t, [dict(act='relu', out_act=out, out_f32=(out32, nh))], residual=(idn, nh[:3]))
+                self.saved.append((x, t, out))
+                x, x32 = out, out32
+            if si in self.output_ids:
+                feats.append(x)
+        return feats
+
+    def backward(self, dfeats, dx_f32=None):
+        """dfeats: {stage index: Act gradient of that stage's output} (bf16, not yet masked)."""
+        idx, d = len(self.saved), None
+        for si in range(len(self.stages) - 1, -1, -1):
+            for bi in range(len(self.stages[si]) - 1, -1, -1):
+                idx -= 1
+                c1, c2, ds = self.stages[si][bi]
+                x, t, out = self.saved[idx]
+                tag = '%d_%d' % (si, bi)
+                last = bi == len(self.stages[si]) - 1
+                extra = dfeats.get(si) if last else None
+                if d is None:
+                    d = extra
+                    act_bwd(d, out, 'relu')
+                else:
+                    act_bwd(d, out, 'relu', add=extra)
+                # d = gradient at the block's pre-ReLU sum: goes to conv2's branch and to the identity / downsample
+                dt = self._act('g_t' + tag, t.N, t.H, t.W, t.C)
+                c2.backward(t, d, [dict(out_act=dt)])
+                act_bwd(dt, t, 'relu')
+                dxin = self._act('g_x' + tag, x.N, x.H, x.W, x.C)
+                first = idx == 0
+                if first and dx_f32 is not None and ds is not None:
+                    # the network input: both branches into one fp32 tensor through the residual input
+                    raise NotImplementedError('fp32 input gradient of a stride-2 first block: use the bf16 Act')
+                c1.backward(x, dt, [dict(out_act=dxin)])
+                if ds is not None:
+                    _, sums = act_bwd(d, None, None, want_sums=True)
+                    dxid = self._act('g_id' + tag, x.N, x.H, x.W, x.C)
+                    ds.backward(x, d, [dict(out_act=dxid)], bias_sums=sums[0])
+                    act_bwd(dxin, None, None, add=dxid)            # sum of the two paths (no mask: next block / caller masks)
+                else:
+                    act_bwd(dxin, None, None, add=d)               # identity path
+                d = dxin
+        return d
+
+
+class FPNLSSTrainer:
+    """FPN_LSS (lss_fpn.py:11-74, lateral=None, extra_upsample=2) with frozen BatchNorm: forward + backward."""
+
+    def __init__(self, neck, device='cuda'):
+        self.device = device
+        self.idx = tuple(neck.input_feature_index)
+        self.scale, self.scale2 = int(neck.up.scale_factor), int(neck.up2[0].scale_factor)
+        self.c1 = _TrainConv(neck.conv[0].weight, None, neck.conv[1], 3)
+        self.c2 = _TrainConv(neck.conv[3].weight, None, neck.conv[4], 3)
+        self.c3 = _TrainConv(neck.up2[1].weight, None, neck.up2[2], 3)
+        self.c4 = _TrainConv(neck.up2[4].weight, neck.up2[4].bias, None, 1)
+        self._buf = {}
+
+    def refresh(self):
+        for c in (self.c1, self.c2, self.c3, self.c4):
+            c.refresh()
+
+    _act = CustomResNetTrainer._act
+    _f32 = CustomResNetTrainer._f32
+
+    def forward(self, feats, out=None):
+        from .encoders import upsample_bilinear
+        x2, x1 = feats[self.idx[0]], feats[self.idx[1]]
+        N, H, W = x2.N, x2.H, x2.W
+        cat = self._act('cat', N, H, W, x2.C + x1.C)
+        upsample_bilinear(x2, cat.slice(0, x2.C))
+        upsample_bilinear(x1, cat.slice(x2.C, x2.C + x1.C))
+        t = self._act('t', N, H, W, self.c1.Cout)
+        self.c1.forward(cat, [dict(act='relu', out_act=t)])
+        u = self._act('u', N, H, W, self.c2.Cout)
+        self.c2.forward(t, [dict(act='relu', out_act=u)])
+        H2, W2 = H * self.scale2, W * self.scale2
+        v = self._act('v', N, H2, W2, u.C)
+        upsample_bilinear(u, v)
+        w = self._act('w', N, H2, W2, self.c3.Cout)
+        self.c3.forward(v, [dict(act='relu', out_act=w)])
+        if out is None:
+            out = self._act('out', N, H2, W2, self.c4.Cout)
+        self.c4.forward(w, [dict(out_act=out)])
+        self.saved = (x2, x1, cat, t, u, v, w)
+        return out
+
+    def backward(self, dout):
+        """Returns {feature index: Act gradient} for the two inputs."""
+        x2, x1, cat, t, u, v, w = self.saved
+        lib = _lib.load()
+        N = x2.N
+        _, sums = act_bwd(dout, None, None, want_sums=True)
+        dw_ = self._act('g_w', N, w.H, w.W, w.C)
+        self.c4.backward(w, dout, [dict(out_act=dw_)], bias_sums=sums[0])
+        act_bwd(dw_, w, 'relu')
+        dv = self._act('g_v', N, v.H, v.W, v.C)
+        self.c3.backward(v, dw_, [dict(out_act=dv)])
+        du32 = self._f32('g_u32', N, u.H, u.W, u.C)
+        _lib.check(lib.dhd_upsample_bilinear_bwd(_p(dv.data), dv.ld, dv.coff, N, u.H, u.W, u.C, v.H, v.W, _p(du32),
+                                                 _stream()), 'upsample_bwd')
+        du = self._act('g_u', N, u.H, u.W, u.C)
+        _lib.check(lib.dhd_add_rowvec(_p(du32), None, N, u.H * u.W, u.C, _p(du.data), du.ld, du.coff, _stream()), 'f32->bf16')
+        act_bwd(du, u, 'relu')
+        dt = self._act('g_t', N, t.H, t.W, t.C)
+        self.c2.backward(t, du, [dict(out_act=dt)])
+        act_bwd(dt, t, 'relu')
+        dcat = self._act('g_cat', N, cat.H, cat.W, cat.C)
+        self.c1.backward(cat, dt, [dict(out_act=dcat)])
+        d2 = dcat.slice(0, x2.C)                                    # identity "up-sampling": the slice is the gradient
+        d1_32 = self._f32('g_x1_32', N, x1.H, x1.W, x1.C)
+        up = dcat.slice(x2.C, x2.C + x1.C)
+        _lib.check(lib.dhd_upsample_bilinear_bwd(_p(up.data), up.ld, up.coff, N, x1.H, x1.W, x1.C, cat.H, cat.W,
+                                                 _p(d1_32), _stream()), 'upsample_bwd')
+        d1 = self._act('g_x1', N, x1.H, x1.W, x1.C)
+        _lib.check(lib.dhd_add_rowvec(_p(d1_32), None, N, x1.H * x1.W, x1.C, _p(d1.data), d1.ld, d1.coff, _stream()), 'f32->bf16')
+        return {self.idx[0]: d2, self.idx[1]: d1}

@@ -191,7 +191,8 @@ typedef struct dhd_conv_desc {
   int32_t stride;              /* 0 / 1: same-size convolution; 2: N,H,W describe the OUTPUT, the input is in_H x in_W
                                   and tap t reads input pixel (stride*y + tap_dy, stride*x + tap_dx)
                                   (CustomResNet's stride-2 blocks, backbones/resnet.py:47-52) */
-  int32_t in_H, in_W;          /* input size when stride == 2 */
+  int32_t in_H, in_W;          /* input grid when it differs from the output grid: required for stride == 2; for
+                                  stride 1 an optional larger input grid (the output covers its top-left H x W) */
   /* SFA spatial-gate blend fused into the epilogue (mix.py:52-57): with g = the activated output (the sigmoid
    * gate a2), the layer writes  g * a1*bev + (1 - g) * (1 - a1)*vox  instead of g, where [bev | vox] = mix_x
    * (bf16 NHWC, mix_parts split parts, bev at mix_coff, vox at mix_coff + Cout) and a1 = mix_a1 [N][Cout].
@@ -226,6 +227,9 @@ typedef struct dhd_wgrad_desc {
   float* dw;
   float* partial;
   int32_t accumulate;
+  int32_t x_stride;            /* 0 / 1, or 2: x is sampled at (2*y + tap_dy, 2*x + tap_dx) of an x_H x x_W grid
+                                  (stride-2 layers; ConvTranspose2d(2,2) with the operand roles swapped) */
+  int32_t x_H, x_W;
 } dhd_wgrad_desc;
 
 size_t dhd_conv2d_wgrad_workspace_bytes(const dhd_wgrad_desc* desc);
@@ -314,6 +318,12 @@ int dhd_maxpool2(const void* in, int in_ld, int in_coff, int in_part_stride, int
 int dhd_upsample_bilinear(const void* in, int in_ld, int in_coff, int in_part_stride, int N, int H, int W,
                           int C, int out_H, int out_W, void* out, int out_ld, int out_coff,
                           int out_part_stride, int parts, void* stream);
+/* backward of the encoder helpers: MaxPool2d(2) (gradient to the first maximum of each window, as torch) and
+ * bilinear Upsample(align_corners=True) (dx fp32 [N*H*W][C], zeroed here, accumulated with atomics) */
+int dhd_maxpool2_bwd(const void* x, int x_ld, int x_coff, const void* dy, int dy_ld, int dy_coff, int N, int H, int W,
+                     int C, void* dx, int dx_ld, int dx_coff, void* stream);
+int dhd_upsample_bilinear_bwd(const void* dy, int dy_ld, int dy_coff, int N, int H, int W, int C, int out_H, int out_W,
+                              float* dx, void* stream);
 /* write-bandwidth probe (measurement only): zero-fills `bytes` at dst with mode 0 = grid-stride
  * st.global.cs.v4, 1 = grid-stride st.global.v4, 2 = one contiguous run per warp (st.cs),
  * 3 = cp.async.bulk from a shared-memory zero tile, one run per CTA, 4 = same, one run per warp */
