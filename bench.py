@@ -264,6 +264,29 @@ def run_ours(args):
                          '(BatchNorm frozen), fused pool fwd+bwd, one NCCL all-reduce of the fp32 gradient bucket, AdamW, '
                          'bf16 weight re-pack; encoders stand in as resident tensors (see TrainStep)'}
         del ts
+        torch.cuda.empty_cache()
+        if not args.no_encoders:
+            # the same step with the real encoders in forward and backward: the occupancy loss reaches the pool and
+            # depth_net through them (no stand-in tensor left between the image features and the losses)
+            tse = TrainStep(cfg, B, encoders=True)
+            tse.alloc_static(host)
+            tse.upload(host)
+            tse.train_step()
+            ge = tse.capture_train() if not args.no_graph else False
+            for _ in range(2):
+                tse.train_step()
+            barrier()
+            t0.record(st)
+            for _ in range(nt):
+                tse.train_step()
+            t1.record(st)
+            barrier()
+            ms_te = shard.max_over_ranks([t0.elapsed_time(t1) / nt], device='cuda')[0]
+            train['with_encoders'] = {'ms_per_step': ms_te, 'samples_per_s': world * B / (ms_te * 1e-3), 'cuda_graph': bool(ge),
+                                      'graph_error': getattr(tse, 'train_graph_error', None),
+                                      'trainable_params': tse.n_params, 'loss': float(tse.loss[0])}
+            del tse
+            torch.cuda.empty_cache()
 
     ms_total, ms_e2e, pool_ms_avg = shard.max_over_ranks([ms_total, ms_e2e, pool_ms_avg], device='cuda')
     if train is not None:

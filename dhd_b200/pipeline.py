@@ -397,8 +397,10 @@ class TrainStep(HotPathStep):
                 bf16 forward / data-gradient weights are re-packed.
     """
 
-    def __init__(self, cfg, B, device='cuda', seed=0):
-        super().__init__(cfg, B, precision='bf16', device=device, seed=seed, use_graph=False)
+    def __init__(self, cfg, B, device='cuda', seed=0, encoders=False):
+        """encoders=True: the real BEV / voxel encoders sit between the pool and the SFA in forward AND backward, so
+        the occupancy loss reaches the pool and depth_net through them (no stand-in tensors anywhere)."""
+        super().__init__(cfg, B, precision='bf16', device=device, seed=seed, use_graph=False, encoders=encoders)
         from projects.mmdet3d_plugin.models.dense_heads.occ_head import predictor
         from . import shard
         from .train import DepthHeadTrainer, HeightNetTrainer, PredictorTrainer, SFATrainer
@@ -414,8 +416,21 @@ class TrainStep(HotPathStep):
         self.t_sfa = SFATrainer(self.sfa, self.device)
         self.t_head = PredictorTrainer(self.head, self.device)
         self.t_height = HeightNetTrainer(self.vt.height_net, self.device, loss_weight=0.1)
+        enc_params = []
+        if encoders:
+            from .train import CustomResNetTrainer, FPNLSSTrainer, UNetTrainer
+            enc_mods = [self.bev_backbone, self.bev_neck] + self.voxel
+            for m in enc_mods:
+                for sub in m.modules():
+                    if isinstance(sub, torch.nn.BatchNorm2d):
+                        for p in sub.parameters():
+                            p.requires_grad_(False)
+                enc_params += [p for p in m.parameters() if p.requires_grad]
+            self.t_backbone = CustomResNetTrainer(self.bev_backbone, self.device)
+            self.t_neck = FPNLSSTrainer(self.bev_neck, self.device)
+            self.t_voxel = [UNetTrainer(u, self.device) for u in self.voxel]
         params = list(self.vt.depth_net.parameters()) + [p for p in self.vt.height_net.parameters() if p.requires_grad] + \
-            [p for p in self.sfa.parameters() if p.requires_grad] + list(self.head.parameters())
+            enc_params + [p for p in self.sfa.parameters() if p.requires_grad] + list(self.head.parameters())
         self.bucket = shard.GradBucket(params)
         self.opt = torch.optim.AdamW(self.bucket.params, lr=2e-4, weight_decay=1e-2, fused=True)
         gen = torch.Generator(device=self.device).manual_seed(11)
@@ -457,7 +472,10 @@ class TrainStep(HotPathStep):
         return self.train_graph is not None
 
     def _refresh(self):
-        for t in (self.t_depth, self.t_height, self.t_sfa, self.t_head):
+        ts = [self.t_depth, self.t_height, self.t_sfa, self.t_head]
+        if self.encoders:
+            ts += [self.t_backbone, self.t_neck] + self.t_voxel
+        for t in ts:
             t.refresh()
 
     def train_step(self):
@@ -491,13 +509,31 @@ class TrainStep(HotPathStep):
         self._last = {'depth': depth, 'feat': feat, 'height': height, 'pixmask': pixmask}
         self._pool()
         self.loss_height = self.t_height.loss(self.height_label, self.height_fg)
-        enc = self.encoded_act
+        if self.encoders:
+            if not hasattr(self, '_enc_act'):
+                self._enc_act = D.Act.empty(B, self.Dy, self.Dx, 512, 1, self.device)
+            enc = self._enc_act
+            ins = [D.pack_nhwc(o, 1) for o in self.outs]
+            self.t_neck.forward(self.t_backbone.forward(ins[0]), out=enc.slice(0, 256))
+            lo, self._enc_slices = 256, []
+            for t, x in zip(self.t_voxel, ins[1:]):
+                t.forward(x, out=enc.slice(lo, lo + t.n_classes))
+                self._enc_slices.append((lo, lo + t.n_classes))
+                lo += t.n_classes
+        else:
+            enc = self.encoded_act
         fused = self.t_sfa.forward(enc)
         self.t_head.forward(fused)
         self.loss = self.t_head.loss(self.labels, self.mask_camera)
         # ---- backward
         dfused = self.t_head.backward()
-        self.t_sfa.backward(dfused)
+        denc = self.t_sfa.backward(dfused)
+        if self.encoders:
+            # occupancy loss -> encoders -> the four pool outputs (fp32 NHWC gradients the pool backward reads)
+            d0 = self.t_backbone.backward(self.t_neck.backward(denc.slice(0, 256)))
+            self.gouts[0].copy_(d0.data.view(self.gouts[0].shape))
+            for t, (a, b), g in zip(self.t_voxel, self._enc_slices, self.gouts[1:]):
+                t.backward(denc.slice(a, b), dx_f32=(g, D.nhwc_strides(g.shape[-1], self.Dy, self.Dx)))
         self.run_pool_bwd()
         self.t_depth.backward(self.depth_grad, self.feat_grad)
         self.t_height.backward(want_dx=True)
