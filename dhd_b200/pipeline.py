@@ -514,12 +514,19 @@ class TrainStep(HotPathStep):
                 self._enc_act = D.Act.empty(B, self.Dy, self.Dx, 512, 1, self.device)
             enc = self._enc_act
             ins = [D.pack_nhwc(o, 1) for o in self.outs]
-            self.t_neck.forward(self.t_backbone.forward(ins[0]), out=enc.slice(0, 256))
+            main = torch.cuda.current_stream()
+            if not hasattr(self, '_enc_streams'):
+                self._enc_streams = [torch.cuda.Stream() for _ in self.t_voxel]
             lo, self._enc_slices = 256, []
-            for t, x in zip(self.t_voxel, ins[1:]):
-                t.forward(x, out=enc.slice(lo, lo + t.n_classes))
+            for st, t, x in zip(self._enc_streams, self.t_voxel, ins[1:]):      # independent encoders: parallel branches
+                st.wait_stream(main)
+                with torch.cuda.stream(st):
+                    t.forward(x, out=enc.slice(lo, lo + t.n_classes))
                 self._enc_slices.append((lo, lo + t.n_classes))
                 lo += t.n_classes
+            self.t_neck.forward(self.t_backbone.forward(ins[0]), out=enc.slice(0, 256))
+            for st in self._enc_streams:
+                main.wait_stream(st)
         else:
             enc = self.encoded_act
         fused = self.t_sfa.forward(enc)
@@ -530,10 +537,15 @@ class TrainStep(HotPathStep):
         denc = self.t_sfa.backward(dfused)
         if self.encoders:
             # occupancy loss -> encoders -> the four pool outputs (fp32 NHWC gradients the pool backward reads)
+            main = torch.cuda.current_stream()
+            for st, t, (a, b), g in zip(self._enc_streams, self.t_voxel, self._enc_slices, self.gouts[1:]):
+                st.wait_stream(main)
+                with torch.cuda.stream(st):
+                    t.backward(denc.slice(a, b), dx_f32=(g, D.nhwc_strides(g.shape[-1], self.Dy, self.Dx)))
             d0 = self.t_backbone.backward(self.t_neck.backward(denc.slice(0, 256)))
             self.gouts[0].copy_(d0.data.view(self.gouts[0].shape))
-            for t, (a, b), g in zip(self.t_voxel, self._enc_slices, self.gouts[1:]):
-                t.backward(denc.slice(a, b), dx_f32=(g, D.nhwc_strides(g.shape[-1], self.Dy, self.Dx)))
+            for st in self._enc_streams:
+                main.wait_stream(st)
         self.run_pool_bwd()
         self.t_depth.backward(self.depth_grad, self.feat_grad)
         self.t_height.backward(want_dx=True)
