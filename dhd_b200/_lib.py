@@ -36,6 +36,7 @@ _I = ctypes.c_int
 _SIGNATURES = {
     'dhd_last_error': (ctypes.c_char_p, []),
     'dhd_abi_version': (ctypes.c_int, []),
+    'dhd_abi_sizeof': (ctypes.c_size_t, [ctypes.c_int]),
     'dhd_bev_pool_v2_fwd': (ctypes.c_int, [ctypes.c_int, ctypes.c_int] + [_P] * 9),
     'dhd_bev_pool_v2_bwd': (ctypes.c_int, [ctypes.c_int, ctypes.c_int] + [_P] * 11),
     'dhd_height_to_mask': (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int, ctypes.c_int, _P, _P,

@@ -126,6 +126,16 @@ using namespace dhd;
 
 extern "C" const char* dhd_last_error(void) { return dhd::g_err; }
 extern "C" int dhd_abi_version(void) { return DHD_ABI_VERSION; }
+// sizeof of the ABI structs, so a binding can verify its own layout (tests/test_abi.py does for the ctypes mirror)
+extern "C" size_t dhd_abi_sizeof(int which) {
+  switch (which) {
+    case 0: return sizeof(dhd_mghs_cfg);
+    case 1: return sizeof(dhd_conv_seg);
+    case 2: return sizeof(dhd_conv_desc);
+    case 3: return sizeof(dhd_wgrad_desc);
+    default: return 0;
+  }
+}
 
 extern "C" int dhd_bev_pool_v2_fwd(int c, int n_intervals, const float* depth, const float* feat,
                                    const int32_t* ranks_depth, const int32_t* ranks_feat,

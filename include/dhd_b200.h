@@ -73,6 +73,9 @@ typedef struct dhd_mghs_cfg {
 
 const char* dhd_last_error(void);
 int dhd_abi_version(void);
+/* sizeof(dhd_mghs_cfg | dhd_conv_seg | dhd_conv_desc | dhd_wgrad_desc) for which = 0..3: lets a binding check its
+ * own struct layout against the library it loaded */
+size_t dhd_abi_sizeof(int which);
 
 /* ---- drop-in operator (reference tensor contracts, fp32 / int32) ------------------
  * depth (B,N,D,fH,fW), feat (B,N,fH,fW,C), out (B,Dz,Dy,Dx,C) PRE-ZEROED by the caller;

@@ -76,3 +76,15 @@ def test_product_never_imports_oracle():
                     src = open(os.path.join(dp, f)).read()
                     assert not re.search(r'^\s*(from|import)\s+oracle\b', src, flags=re.M), \
                         '%s imports the oracle' % os.path.join(dp, f)
+
+
+def test_ctypes_struct_layouts_match_the_library(lib):
+    """The ctypes mirrors of the ABI structs have the sizes the compiled library reports."""
+    import ctypes
+    from dhd_b200 import dense as D
+    from dhd_b200._lib import MghsCfg
+    for which, cls in enumerate((MghsCfg, D.ConvSeg, D.ConvDesc, D.WgradDesc)):
+        assert lib.dhd_abi_sizeof(which) == ctypes.sizeof(cls), cls.__name__
+    # the same fields at the same offsets for the two structs that grew this round
+    assert D.ConvDesc.stride.offset == D.ConvDesc.seg.offset + D.MAX_SEGS * ctypes.sizeof(D.ConvSeg)
+    assert D.WgradDesc.x_stride.offset == D.WgradDesc.accumulate.offset + 4
