@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, 'libdhd_b200.so')
 
 MAX_PASSES = 4
 MAX_PLANES = 32
-LAYOUT_NHWC, LAYOUT_NCHW_COLLAPSE, LAYOUT_NCDHW, LAYOUT_NCDHW_CAT = 0, 1, 2, 3
+LAYOUT_NHWC, LAYOUT_NCHW_COLLAPSE, LAYOUT_NCDHW, LAYOUT_NCDHW_CAT, LAYOUT_NHWC_BF16 = 0, 1, 2, 3, 4
 
 
 class MghsCfg(ctypes.Structure):

@@ -15,6 +15,7 @@
 //             the cell's bin, and writes every output byte exactly once with full-line
 //             coalesced streaming stores -- zeros included.  No atomics, no memset,
 //             no layout copy.  HBM-write bound: algorithmic bytes == bytes stored.
+#include <cuda_bf16.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -321,6 +322,7 @@ struct PoolParams {
   const int2* chunks;                     // work chunks of the streaming kernel (mghs_chunks_kernel)
   int nch;
   int* sched;                             // {next chunk, finished warps}: dynamic scheduler of the v3 kernel, self-resetting
+  int out_bf16;                           // stream kernel: outputs are bf16 (b, y, x, z, c) instead of fp32
   int probe;                              // bandwidth probe (DHD_POOL_PROBE=1): treat every cell as empty
 };
 
@@ -853,7 +855,7 @@ struct PoolLane {          // per-lane issue state for the zero-run copies
 };
 
 template <bool HINT, int MINB>
-__global__ void __launch_bounds__(128, MINB) mghs_pool_stream_kernel(const PoolParams P, int zero_bytes, int windows, int prefetch, int roles) {
+__global__ void __launch_bounds__(128, MINB) mghs_pool_stream_kernel(const PoolParams P, int zero_bytes, int windows, int prefetch) {
   extern __shared__ __align__(128) uint8_t smem_pool[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int wpb = blockDim.x >> 5;
@@ -881,11 +883,12 @@ __global__ void __launch_bounds__(128, MINB) mghs_pool_stream_kernel(const PoolP
       my_out = reinterpret_cast<char*>(P.pass_ptr[p]);
     }
   }
+  const uint32_t esz = P.out_bf16 ? 8u : 16u;       // output bytes per float4 of column: bf16 halves every store
   // zero-fill cells [c0, c1) of every pass: one bulk copy per pass and zero-tile-full
   auto zero_run = [&](int c0, int c1) {
     if (c1 > c0 && my_out != nullptr) {
-      size_t bytes = (size_t)(c1 - c0) * my_q * 16;
-      char* dst = my_out + (size_t)c0 * my_q * 16;
+      size_t bytes = (size_t)(c1 - c0) * my_q * esz;
+      char* dst = my_out + (size_t)c0 * my_q * esz;
       while (bytes != 0) {
         const uint32_t b = bytes < (size_t)zero_bytes ? (uint32_t)bytes : (uint32_t)zero_bytes;
         if (HINT) bulk_store_hint(dst, zero_s, b, pol);
@@ -895,59 +898,11 @@ __global__ void __launch_bounds__(128, MINB) mghs_pool_stream_kernel(const PoolP
       }
     }
   };
-  // Warp roles (roles != 0): warp 0 of every CTA only ZERO-FILLS -- it walks the cell range in address order
-  // (256-cell chunks from its own counter) and bulk-copies the zero tile over every run of empty cells, never
-  // waiting on anything but its own cell_count loads -- while the other warps only GATHER (non-empty cells,
-  // columns out through the TMA unit).  The write stream of the 78 % empty cells then runs at fill speed
-  // whatever the gather warps are doing, instead of stalling whenever all warps sit in a dense region.
-  const bool zero_role = roles != 0 && wid == 0;
-  if (zero_role) {
-    constexpr int kZChunk = 256;
-    const int nz_chunks = (P.ncell + kZChunk - 1) / kZChunk;
-    int zc = 0;
-    if (lane == 0) zc = atomicAdd(P.sched + 2, 1);
-    zc = __shfl_sync(kFull, zc, 0);
-    while (zc < nz_chunks) {
-      int znext = 0;
-      if (lane == 0) znext = atomicAdd(P.sched + 2, 1);
-      const int c_lo = zc * kZChunk, c_hi = min(c_lo + kZChunk, P.ncell);
-      int run_lo = -1;                                  // start of the current run of empty cells (-1: none open)
-      int cnts[kZChunk / 32];                           // the whole chunk's counts: 8 independent loads in flight
-#pragma unroll
-      for (int q = 0; q < kZChunk / 32; ++q) {
-        const int c = c_lo + q * 32 + lane;
-        cnts[q] = c < c_hi && P.probe != 1 ? __ldg(P.cell_count + c) : 0;
-      }
-#pragma unroll
-      for (int q = 0; q < kZChunk / 32; ++q) {
-        const int c0 = c_lo + q * 32;
-        if (c0 >= c_hi) break;
-        const int nb = min(32, c_hi - c0);
-        const int cnt = cnts[q];
-        uint32_t nzm = __ballot_sync(kFull, cnt != 0);
-        if (nb < 32) nzm |= ~0u << nb;                  // beyond the chunk counts as "stop"
-        int pos = 0;
-        while (pos < 32) {
-          const uint32_t rest = nzm >> pos;
-          const int run = rest != 0 ? __ffs(rest) - 1 : 32 - pos;
-          if (run > 0 && run_lo < 0) run_lo = c0 + pos;
-          pos += run;
-          if (pos < 32) {                               // a non-empty cell (or the chunk end) closes the run
-            if (run_lo >= 0) zero_run(run_lo, min(c0 + pos, c_hi));
-            run_lo = -1;
-            ++pos;
-          }
-        }
-      }
-      if (run_lo >= 0) zero_run(run_lo, c_hi);
-      zc = __shfl_sync(kFull, znext, 0);
-    }
-  }
   const int per_win = (P.nch + windows - 1) / windows;
-  const int n_iter = zero_role ? 0 : per_win * windows;
+  const int n_iter = per_win * windows;
   auto fetch = [&]() {
-    int ch = 0x7fffffff;                     // the zero-fill role takes no gather chunks
-    if (lane == 0 && !zero_role) ch = atomicAdd(P.sched, 1);
+    int ch = 0;
+    if (lane == 0) ch = atomicAdd(P.sched, 1);
     return ch;                               // valid in lane 0; broadcast when consumed
   };
   int buf = 0;
@@ -982,6 +937,38 @@ __global__ void __launch_bounds__(128, MINB) mghs_pool_stream_kernel(const PoolP
     uint32_t touched = 0;
     float2* col2 = reinterpret_cast<float2*>(col_g + (size_t)buf * col_bytes);
     const int nE = e_hi - e_lo;
+    // flush the finished column of `cell`: one bulk copy per pass; then flip to the other buffer.  bf16 outputs: the
+    // column is first packed in place (plane z's 64 bf16 to byte 128 z; plane z is read before anything lands on it)
+    auto flush = [&](int cell_id) {
+      uint32_t plane_bytes = 256u;
+      if (P.out_bf16) {
+        __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(col2);
+        for (int z = 0; z < P.nplanes; ++z) {
+          const float2 v = col2[z * 32 + lane];
+          __syncwarp();
+          h2[z * 32 + lane] = __floats2bfloat162_rn(v.x, v.y);
+        }
+        touched = P.nplanes >= 32 ? 0xffffffffu : ((1u << P.nplanes) - 1u);     // the whole buffer must be re-zeroed
+        plane_bytes = 128u;
+      }
+      if (buf) touched1 = touched; else touched0 = touched;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) {
+        const uint32_t src = col_s + (uint32_t)buf * col_bytes;
+#pragma unroll
+        for (int p = 0; p < DHD_MAX_PASSES; ++p) {
+          if (p < P.npass) {
+            const uint32_t bytes = (uint32_t)P.pass_q[p] * esz;
+            char* dst = reinterpret_cast<char*>(P.pass_ptr[p]) + (size_t)cell_id * bytes;
+            if (HINT) bulk_store_hint(dst, src + (uint32_t)P.zoff[p] * plane_bytes, bytes, pol);
+            else bulk_store(dst, src + (uint32_t)P.zoff[p] * plane_bytes, bytes);
+          }
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      buf ^= 1;
+    };
     if (nE > 0) {
       // ---- software pipeline registers
       int a_pt = 0, a_pix = 0, a_cell = -1;
@@ -1051,27 +1038,10 @@ __global__ void __launch_bounds__(128, MINB) mghs_pool_stream_kernel(const PoolP
             const int c = __shfl_sync(kFull, c_cell, (j + __ffs(rem) - 1) & 31);
             if (c != cur_cell) {
               if (cur_cell >= 0) {
-                // ---- flush the finished column: one bulk copy per pass
-                if (buf) touched1 = touched; else touched0 = touched;
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) {
-                  const uint32_t src = col_s + (uint32_t)buf * col_bytes;
-#pragma unroll
-                  for (int p = 0; p < DHD_MAX_PASSES; ++p) {
-                    if (p < P.npass) {
-                      const uint32_t bytes = (uint32_t)P.pass_q[p] * 16u;
-                      char* dst = reinterpret_cast<char*>(P.pass_ptr[p]) + (size_t)cur_cell * bytes;
-                      if (HINT) bulk_store_hint(dst, src + (uint32_t)P.zoff[p] * 256u, bytes, pol);
-                      else bulk_store(dst, src + (uint32_t)P.zoff[p] * 256u, bytes);
-                    }
-                  }
-                  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                }
-                buf ^= 1;
+                flush(cur_cell);
                 pos = cur_cell + 1;
               }
-              if (!roles) zero_run(pos, c);
+              zero_run(pos, c);
               pos = c;
               // ---- claim the other column buffer: its last copy must have read it; re-zero what that cell touched
               col2 = reinterpret_cast<float2*>(col_g + (size_t)buf * col_bytes);
@@ -1119,34 +1089,17 @@ __global__ void __launch_bounds__(128, MINB) mghs_pool_stream_kernel(const PoolP
       }
       // ---- last column of the chunk
       if (cur_cell >= 0) {
-        if (buf) touched1 = touched; else touched0 = touched;
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) {
-          const uint32_t src = col_s + (uint32_t)buf * col_bytes;
-#pragma unroll
-          for (int p = 0; p < DHD_MAX_PASSES; ++p) {
-            if (p < P.npass) {
-              const uint32_t bytes = (uint32_t)P.pass_q[p] * 16u;
-              char* dst = reinterpret_cast<char*>(P.pass_ptr[p]) + (size_t)cur_cell * bytes;
-              if (HINT) bulk_store_hint(dst, src + (uint32_t)P.zoff[p] * 256u, bytes, pol);
-              else bulk_store(dst, src + (uint32_t)P.zoff[p] * 256u, bytes);
-            }
-          }
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        }
-        buf ^= 1;
+        flush(cur_cell);
         pos = cur_cell + 1;
       }
     }
-    if (!roles) zero_run(pos, cell_hi);
+    zero_run(pos, cell_hi);
   }
   if (lane == 0) {
     // the last warp to run dry re-arms the scheduler for the next launch on this workspace
     if (atomicAdd(P.sched + 1, 1) == warps - 1) {
       P.sched[0] = 0;
       P.sched[1] = 0;
-      P.sched[2] = 0;
     }
   }
   // shared memory must outlive every bulk copy that reads it
@@ -1339,6 +1292,7 @@ static int fill_pool_params(const dhd_mghs_cfg* cfg, const WsLayout& w, const vo
   }
   P->nplanes = off;
   P->probe = tuning("DHD_POOL_PROBE", 0);
+  P->out_bf16 = 0;
   return DHD_OK;
 }
 
@@ -1446,7 +1400,7 @@ extern "C" int dhd_mghs_pool_fwd(const dhd_mghs_cfg* cfg, const float* depth, co
   const long DyDx = (long)cfg->Dy * cfg->Dx;
   for (int p = 0, k = 0; p < cfg->n_pass; ++p) {
     for (int z = 0; z < cfg->dz[p]; ++z, ++k) {
-      if (layout == DHD_LAYOUT_NHWC) {
+      if (layout == DHD_LAYOUT_NHWC || layout == DHD_LAYOUT_NHWC_BF16) {
         P.plane_ptr[k] = out_host[p] + (size_t)z * kC;
         P.plane_cell_stride[k] = cfg->dz[p] * kC;
         P.plane_b_stride[k] = 0;
@@ -1487,6 +1441,11 @@ extern "C" int dhd_mghs_pool_fwd(const dhd_mghs_cfg* cfg, const float* depth, co
     P.pass_q[p] = p < cfg->n_pass ? cfg->dz[p] * kC / 4 : 0;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  if (layout == DHD_LAYOUT_NHWC_BF16) {
+    P.out_bf16 = 1;
+    layout = DHD_LAYOUT_NHWC;
+    DHD_REQUIRE(tuning("DHD_POOL_V", 4) == 4, "bf16 outputs need the streaming pool kernel");
+  }
   if (layout == DHD_LAYOUT_NHWC && tuning("DHD_POOL_V", 4) == 4) {
     for (int p = 0; p < cfg->n_pass; ++p)
       DHD_REQUIRE(((uintptr_t)out_host[p] & 15) == 0, "NHWC outputs must be 16-byte aligned");
@@ -1494,15 +1453,14 @@ extern "C" int dhd_mghs_pool_fwd(const dhd_mghs_cfg* cfg, const float* depth, co
     DHD_REQUIRE(threads == 32 || threads == 64 || threads == 128, "stream pool: 32, 64 or 128 threads per block");
     const int zero_bytes = tuning("DHD_POOL_ZT", 4096) / 256 * 256;
     const int hint = tuning("DHD_POOL_HINT", 1);
-    const int cap = tuning("DHD_POOL_PERSM", 16);
+    const int cap = tuning("DHD_POOL_PERSM", 4);
     const int windows = max(1, tuning("DHD_POOL_WINDOWS", 1));
     const int wpb = threads / 32;
     const size_t smem = (size_t)zero_bytes + (size_t)wpb * 2 * P.nplanes * 256;
     DHD_REQUIRE(smem <= 227 * 1024, "pool column buffers do not fit in shared memory");
     const int minb = tuning("DHD_POOL_MINB", 4) >= 5 ? 5 : 4;
     const int prefetch = tuning("DHD_POOL_PREFETCH", 1);
-    const int roles = tuning("DHD_POOL_ROLES", 0);   // experiment: dedicated zero-fill warps (slower, profiles/r01_pool_sweep12/13.txt)
-    void (*kern)(const PoolParams, int, int, int, int) =
+    void (*kern)(const PoolParams, int, int, int) =
         hint ? (minb == 5 ? mghs_pool_stream_kernel<true, 5> : mghs_pool_stream_kernel<true, 4>)
              : (minb == 5 ? mghs_pool_stream_kernel<false, 5> : mghs_pool_stream_kernel<false, 4>);
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1510,7 +1468,7 @@ extern "C" int dhd_mghs_pool_fwd(const dhd_mghs_cfg* cfg, const float* depth, co
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem);
     const int per_sm = max(1, min(cap, occ));
     const int grid = min((P.nch + wpb - 1) / wpb, sm_count() * per_sm);
-    kern<<<grid, threads, smem, st>>>(P, zero_bytes, windows, prefetch, roles);
+    kern<<<grid, threads, smem, st>>>(P, zero_bytes, windows, prefetch);
     DHD_CUDA_LAUNCH_CHECK("mghs_pool_stream");
   } else if (layout == DHD_LAYOUT_NHWC && tuning("DHD_POOL_V", 4) == 3) {
     for (int p = 0; p < cfg->n_pass; ++p)

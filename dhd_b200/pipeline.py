@@ -140,7 +140,10 @@ class HotPathStep:
                              [(gr['z'], m) for m, gr in enumerate(grids)])
         self.Dy, self.Dx = self.plan.Dy, self.plan.Dx
         self.workspace = torch.empty(self.plan.ws_bytes, dtype=torch.uint8, device=self.device)
-        self.outs = self.plan.alloc_outputs('nhwc', self.device)
+        # with the real encoders behind it (bf16 speed mode) the pool writes bf16 NHWC directly: the four outputs ARE
+        # the encoders' input activations (half the bytes, no conversion pass); everywhere else fp32, as the reference
+        self.pool_layout = 'nhwc_bf16' if (encoders and self.parts == 1 and type(self).__name__ == 'HotPathStep') else 'nhwc'
+        self.outs = self.plan.alloc_outputs(self.pool_layout, self.device)
         self.frustum = self.vt.frustum.to(self.device)
         gen = torch.Generator(device=self.device).manual_seed(7)
         # stand-in for the BEV / voxel encoders' output (outside the SURVEY 8 path): channels-last fp32 values, held
@@ -215,7 +218,7 @@ class HotPathStep:
 
     def _pool(self):
         L = self._last
-        self.plan.raw_forward(L['depth'], L['feat'], L['pixmask'], self.outs, 'nhwc', workspace=self.workspace)
+        self.plan.raw_forward(L['depth'], L['feat'], L['pixmask'], self.outs, self.pool_layout, workspace=self.workspace)
 
     def _encode(self, parallel=True):
         """pool outputs -> (B, 512, Dy, Dx) = cat(bev encoder, three voxel encoders), DM:103-114: every encoder
@@ -224,7 +227,10 @@ class HotPathStep:
         if not hasattr(self, '_enc_act'):
             self._enc_act = D.Act.empty(B, H, W, 512, self.parts, self.device)
         enc = self._enc_act
-        ins = [D.pack_nhwc(o, self.parts) for o in self.outs]          # fp32 pool outputs -> bf16 activations
+        if self.pool_layout == 'nhwc_bf16':
+            ins = [D.Act(o, o.shape[-1], 1) for o in self.outs]        # the pool wrote the activations themselves
+        else:
+            ins = [D.pack_nhwc(o, self.parts) for o in self.outs]      # fp32 pool outputs -> split-bf16 activations
         # the four encoders are independent: the three UNets run on side streams (parallel branches of the CUDA
         # graph), so their small deep levels (12x12 .. 50x50 maps: 5-80 tiles for 148 SMs) share the GPU with the
         # others' full-resolution layers instead of each leaving most SMs idle

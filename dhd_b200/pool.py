@@ -11,9 +11,10 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import LAYOUT_NCDHW, LAYOUT_NCDHW_CAT, LAYOUT_NCHW_COLLAPSE, LAYOUT_NHWC, MghsCfg
+from ._lib import LAYOUT_NCDHW, LAYOUT_NCDHW_CAT, LAYOUT_NCHW_COLLAPSE, LAYOUT_NHWC, LAYOUT_NHWC_BF16, MghsCfg
 
-_LAYOUTS = {'nhwc': LAYOUT_NHWC, 'nchw': LAYOUT_NCHW_COLLAPSE, 'ncdhw': LAYOUT_NCDHW, 'ncdhw_cat': LAYOUT_NCDHW_CAT}
+_LAYOUTS = {'nhwc': LAYOUT_NHWC, 'nchw': LAYOUT_NCHW_COLLAPSE, 'ncdhw': LAYOUT_NCDHW, 'ncdhw_cat': LAYOUT_NCDHW_CAT,
+            'nhwc_bf16': LAYOUT_NHWC_BF16}
 
 
 def _stream():
@@ -250,6 +251,8 @@ class MghsPool:
         for dz in self.dz:
             if layout == 'nhwc':
                 outs.append(torch.empty(self.B, self.Dy, self.Dx, dz * self.C, device=device))
+            elif layout == 'nhwc_bf16':        # forward only: the encoders' input activations
+                outs.append(torch.empty(self.B, self.Dy, self.Dx, dz * self.C, device=device, dtype=torch.bfloat16))
             elif layout == 'nchw':
                 outs.append(torch.empty(self.B, dz * self.C, self.Dy, self.Dx, device=device))
             elif layout == 'ncdhw':

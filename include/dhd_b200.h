@@ -52,8 +52,10 @@ enum {
   DHD_LAYOUT_NHWC = 0,          /* (b, y, x, z, c): channels_last of the collapsed tensor; fastest */
   DHD_LAYOUT_NCHW_COLLAPSE = 1, /* (b, z, c, y, x): contiguous (B, dz*C, Dy, Dx), the reference layout */
   DHD_LAYOUT_NCDHW = 2,         /* (b, c, z, y, x): contiguous (B, C, dz, Dy, Dx), collapse_z=False */
-  DHD_LAYOUT_NCDHW_CAT = 3      /* pass 0 as NCDHW into out[0]; passes 1.. stacked on z in ONE tensor out[1] of
+  DHD_LAYOUT_NCDHW_CAT = 3,     /* pass 0 as NCDHW into out[0]; passes 1.. stacked on z in ONE tensor out[1] of
                                    shape (B, C, sum dz[1..], Dy, Dx): MGHS_Depth's torch.cat(dim=2), lss_heightmap.py:845 */
+  DHD_LAYOUT_NHWC_BF16 = 4      /* DHD_LAYOUT_NHWC with bf16 elements (out_host[p] point at bf16): the activation layout
+                                   the encoder convolutions read -- half the bytes, no conversion pass; forward only */
 };
 
 /* One fused view-transform problem: a frustum of B*N*D*fH*fW points pooled into

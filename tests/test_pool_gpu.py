@@ -424,3 +424,30 @@ def test_fused_matches_reference_cuda_path_other_configs(cuda_lib, name, input_s
     for o, w in zip(plan(depth, f_nhwc, pm, layout='nhwc'), want):
         ref = w if collapse else torch.cat(w.unbind(dim=2), 1)
         assert torch.allclose(o.permute(0, 3, 1, 2), ref, rtol=1e-5, atol=2e-6)
+
+
+def test_bf16_output_layout_is_the_rounded_fp32_result(cuda_lib):
+    """DHD_LAYOUT_NHWC_BF16: the streaming kernel packs every column to bf16 before it leaves -- bit-identical to
+    rounding the fp32 outputs (same accumulation), zeros included, on a masked multi-pass problem."""
+    cfg, B, inputs, depth, feat, height, gold = H.load_case('dhds_b2_flip')
+    from dhd_b200.pool import MghsPool, height_to_mask
+    N, D = cfg['ncams'], depth.shape[1]
+    fH, fW = depth.shape[-2:]
+    C = cfg['C']
+    fr = O.frustum(cfg['depth'], cfg['input_size'], cfg['downsample'])
+    coor = O.ego_coor(fr, inputs[1], inputs[3], inputs[4], inputs[5], inputs[6])
+    grids = [cfg['bev_grid']] + list(cfg['mask_grids'])
+    plan = MghsPool(B, N, D, fH, fW, C, grids[0]['x'], grids[0]['y'], [(g['z'], m) for m, g in enumerate(grids)])
+    plan.prepare(coor=coor.cuda())
+    pm = height_to_mask(height.cuda(), cfg['height_range'], cfg['mask_range'])
+    f_nhwc = feat.view(B, N, C, fH, fW).permute(0, 1, 3, 4, 2).contiguous().cuda()
+    want = plan.alloc_outputs('nhwc', 'cuda')
+    got = plan.alloc_outputs('nhwc_bf16', 'cuda')
+    for t in got:
+        t.fill_(float('nan'))
+    plan.raw_forward(depth.cuda(), f_nhwc, pm, want, 'nhwc')
+    plan.raw_forward(depth.cuda(), f_nhwc, pm, got, 'nhwc_bf16')
+    plan.raw_forward(depth.cuda(), f_nhwc, pm, got, 'nhwc_bf16')       # twice: buffers re-zeroed correctly
+    torch.cuda.synchronize()
+    for g, w in zip(got, want):
+        assert g.dtype == torch.bfloat16 and torch.equal(g, w.to(torch.bfloat16))
