@@ -707,6 +707,71 @@ __global__ void occ_scal_coeffs_kernel(const float* __restrict__ partial, int nb
   }
 }
 
+
+// ---- batch-statistics BatchNorm (training mode of every conv -> BN [-> ReLU] pair of the path) -------------------
+// forward:  out = act(scale[c] * raw + shift[c] [+ residual]) [* gate[n][c]], raw = the convolution's bf16 output,
+//           scale = gamma / sqrt(var + eps), shift = beta - mean * scale from the batch statistics of raw
+//           (sums by dhd_act_bwd with act = none: [sum raw, sum raw^2]);
+// backward: d raw = k1[c] * dz + k2[c] * raw + k3[c]  with  k1 = gamma/sigma, k2 = -k1 * S2 / (M sigma^2),
+//           k3 = -k1 * (S1 / M - mean * S2 / (M sigma^2)),  S1 = sum dz, S2 = sum dz * (raw - mean)
+//           (the standard BatchNorm backward written as a per-channel affine combination of dz and raw).
+__global__ void __launch_bounds__(256)
+bn_apply_kernel(const __nv_bfloat16* __restrict__ raw, int r_ld, int r_coff, long rows, int C,
+                const float* __restrict__ scale, const float* __restrict__ shift, int act,
+                const float* __restrict__ residual, long res_ld, const float* __restrict__ gate, int rows_per_img,
+                __nv_bfloat16* __restrict__ ob, int o_ld, int o_coff, float* __restrict__ of, long f_ld) {
+  const int cg = C / 8;
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cg) return;
+  const long r = i / cg;
+  const int c = (int)(i % cg) * 8;
+  float v[8];
+  load8(raw + r * r_ld + r_coff + c, v);
+  const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + c)), s1 = __ldg(reinterpret_cast<const float4*>(scale + c) + 1);
+  const float4 t0 = __ldg(reinterpret_cast<const float4*>(shift + c)), t1 = __ldg(reinterpret_cast<const float4*>(shift + c) + 1);
+  const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+  const float sh[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
+  if (residual != nullptr) {
+    const float4 a = *reinterpret_cast<const float4*>(residual + r * res_ld + c);
+    const float4 b = *reinterpret_cast<const float4*>(residual + r * res_ld + c + 4);
+    v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (act == 1) v[j] = fmaxf(v[j], 0.f);
+    else if (act == 2) v[j] = __fdividef(1.f, 1.f + __expf(-v[j]));
+  }
+  if (gate != nullptr) {
+    const float* g = gate + (r / rows_per_img) * C + c;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] *= __ldg(g + j);
+  }
+  if (ob != nullptr) store8(ob + r * o_ld + o_coff + c, v);
+  if (of != nullptr) {
+    *reinterpret_cast<float4*>(of + r * f_ld + c) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(of + r * f_ld + c + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+affine_combine_kernel(const __nv_bfloat16* __restrict__ a, int a_ld, int a_coff, const __nv_bfloat16* __restrict__ b, int b_ld,
+                      int b_coff, long rows, int C, const float* __restrict__ k1, const float* __restrict__ k2,
+                      const float* __restrict__ k3, __nv_bfloat16* __restrict__ out, int o_ld, int o_coff) {
+  const int cg = C / 8;
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cg) return;
+  const long r = i / cg;
+  const int c = (int)(i % cg) * 8;
+  float x[8], y[8];
+  load8(a + r * a_ld + a_coff + c, x);
+  load8(b + r * b_ld + b_coff + c, y);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) x[j] = fmaf(__ldg(k1 + c + j), x[j], fmaf(__ldg(k2 + c + j), y[j], __ldg(k3 + c + j)));
+  store8(out + r * o_ld + o_coff + c, x);
+}
+
 }  // namespace dhd
 
 using namespace dhd;
@@ -899,5 +964,38 @@ extern "C" int dhd_pack_conv_weights(const float* w, int Cout, int cin_total, in
                                                                     (__nv_bfloat16*)fwd, cin_pad, (__nv_bfloat16*)bwd,
                                                                     cout_pad, bwd_mode);
   DHD_CUDA_LAUNCH_CHECK("pack_conv_weights");
+  return DHD_OK;
+}
+
+extern "C" int dhd_bn_apply(const void* raw, int raw_ld, int raw_coff, long rows, int C, const float* scale,
+                            const float* shift, int act, const float* residual, long res_ld, const float* gate,
+                            int rows_per_img, void* out_b16, int o_ld, int o_coff, float* out_f32, long f_ld,
+                            void* stream) {
+  DHD_REQUIRE(raw && scale && shift && (out_b16 || out_f32) && rows > 0 && C > 0, "bad arguments");
+  DHD_REQUIRE(act >= 0 && act <= 2, "act must be none / relu / sigmoid");
+  DHD_REQUIRE(ok8(C, raw_ld, raw_coff, raw) && ((uintptr_t)scale & 15) == 0 && ((uintptr_t)shift & 15) == 0,
+              "raw: C % 8, 16-byte aligned rows");
+  if (out_b16 != nullptr) DHD_REQUIRE(ok8(C, o_ld, o_coff, out_b16), "out_b16: 16-byte aligned rows");
+  if (out_f32 != nullptr) DHD_REQUIRE(f_ld % 4 == 0 && ((uintptr_t)out_f32 & 15) == 0, "out_f32: 16-byte aligned rows");
+  if (residual != nullptr) DHD_REQUIRE(res_ld % 4 == 0 && ((uintptr_t)residual & 15) == 0, "residual: 16-byte aligned rows");
+  DHD_REQUIRE(gate == nullptr || rows_per_img > 0, "gate needs rows_per_img");
+  const long total = rows * (C / 8);
+  bn_apply_kernel<<<(int)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)raw, raw_ld, raw_coff, rows, C, scale, shift, act, residual, res_ld, gate, rows_per_img,
+      (__nv_bfloat16*)out_b16, o_ld, o_coff, out_f32, f_ld);
+  DHD_CUDA_LAUNCH_CHECK("bn_apply");
+  return DHD_OK;
+}
+
+extern "C" int dhd_affine_combine(const void* a, int a_ld, int a_coff, const void* b, int b_ld, int b_coff, long rows, int C,
+                                  const float* k1, const float* k2, const float* k3, void* out, int o_ld, int o_coff,
+                                  void* stream) {
+  DHD_REQUIRE(a && b && k1 && k2 && k3 && out && rows > 0 && C > 0, "bad arguments");
+  DHD_REQUIRE(ok8(C, a_ld, a_coff, a) && ok8(C, b_ld, b_coff, b) && ok8(C, o_ld, o_coff, out), "C % 8, 16-byte aligned rows");
+  const long total = rows * (C / 8);
+  affine_combine_kernel<<<(int)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)a, a_ld, a_coff, (const __nv_bfloat16*)b, b_ld, b_coff, rows, C, k1, k2, k3,
+      (__nv_bfloat16*)out, o_ld, o_coff);
+  DHD_CUDA_LAUNCH_CHECK("affine_combine");
   return DHD_OK;
 }

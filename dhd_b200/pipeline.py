@@ -403,19 +403,27 @@ class TrainStep(HotPathStep):
                 bf16 forward / data-gradient weights are re-packed.
     """
 
-    def __init__(self, cfg, B, device='cuda', seed=0, encoders=False):
+    def __init__(self, cfg, B, device='cuda', seed=0, encoders=False, bn='frozen'):
         """encoders=True: the real BEV / voxel encoders sit between the pool and the SFA in forward AND backward, so
         the occupancy loss reaches the pool and depth_net through them (no stand-in tensors anywhere)."""
         super().__init__(cfg, B, precision='bf16', device=device, seed=seed, use_graph=False, encoders=encoders)
         from projects.mmdet3d_plugin.models.dense_heads.occ_head import predictor
         from . import shard
+        from . import train as T
         from .train import DepthHeadTrainer, HeightNetTrainer, PredictorTrainer, SFATrainer
+        # bn='batch': every conv -> BatchNorm2d pair runs torch's training mode (batch statistics, trainable gamma /
+        # beta, running statistics updated); the two BatchNorms that see one value per image (HeightNet's BatchNorm1d
+        # on the camera vector and the ASPP global-pool branch) stay frozen either way
+        self.bn_mode = bn
+        T.set_bn_mode(bn)
         torch.manual_seed(seed + 1)
         self.head = predictor(in_dim=256, out_dim=256, Dz=16, num_classes=18, use_predicter=True, class_balance=True,
                               loss_occ=dict(type='CrossEntropyLoss', use_sigmoid=False, ignore_index=255,
                                             loss_weight=1.0)).to(self.device)
-        for m in list(self.sfa.modules()) + list(self.vt.height_net.modules()):
-            if isinstance(m, (torch.nn.BatchNorm2d, torch.nn.BatchNorm1d)):
+        hn = self.vt.height_net
+        always_frozen = [hn.bn] + [m for m in hn.modules() if type(m).__name__ == 'ASPP' for m in [m.global_avg_pool[2]]]
+        for m in list(self.sfa.modules()) + list(hn.modules()):
+            if isinstance(m, (torch.nn.BatchNorm2d, torch.nn.BatchNorm1d)) and (bn == 'frozen' or any(m is f for f in always_frozen)):
                 for p in m.parameters():
                     p.requires_grad_(False)
         self.t_depth = DepthHeadTrainer(self.vt.depth_net, self.D, self.device)
@@ -428,7 +436,7 @@ class TrainStep(HotPathStep):
             enc_mods = [self.bev_backbone, self.bev_neck] + self.voxel
             for m in enc_mods:
                 for sub in m.modules():
-                    if isinstance(sub, torch.nn.BatchNorm2d):
+                    if isinstance(sub, torch.nn.BatchNorm2d) and bn == 'frozen':
                         for p in sub.parameters():
                             p.requires_grad_(False)
                 enc_params += [p for p in m.parameters() if p.requires_grad]
@@ -449,6 +457,7 @@ class TrainStep(HotPathStep):
         self.height_fg = (torch.rand(npix, device=self.device, generator=gen) < 0.3).to(torch.uint8)
         self.n_params = self.bucket.flat.numel()
         self.loss = None
+        T.set_bn_mode('frozen')
 
     def capture_train(self):
         """Capture forward + losses + backward (graph 1) and the weight re-pack (graph 2) into CUDA graphs:

@@ -18,6 +18,17 @@ from . import dense as D
 from .modules import _p, _stream, fold_bn
 
 ACT_ID = {None: 0, 'none': 0, 'relu': 1, 'sigmoid': 2, 'softplus': 3}
+# How the BatchNorm after a convolution behaves on the training path: 'frozen' (running statistics and affine
+# parameters fixed, folded into the convolution epilogue) or 'batch' (torch's training mode: batch statistics,
+# trainable gamma / beta, running statistics updated).  Read when a trainer is constructed.
+BN_MODE = 'frozen'
+
+
+def set_bn_mode(mode):
+    global BN_MODE
+    if mode not in ('frozen', 'batch'):
+        raise ValueError(mode)
+    BN_MODE = mode
 _WS = {}
 
 
@@ -30,19 +41,22 @@ def _workspace(dev, nbytes):
     return ws
 
 
-def act_bwd(dy, y, act, out=None, want_sums=False, add=None):
+def act_bwd(dy, y, act, out=None, want_sums=False, add=None, write=True):
     """dz = (dy [+ add]) * act'(y) (Acts, part 0).  out=None -> in place on dy.  Returns (dz Act, sums)
     with sums (2, C) fp32 = [sum_rows dz, sum_rows dz*y] when want_sums."""
     lib = _lib.load()
     C = dy.C
     out = dy if out is None else out
+    if not write:
+        out = None                                # reductions only
     sums = ws = None
     if want_sums:
         sums = torch.empty(2, C, device=dy.data.device)
         ws = _workspace(dy.data.device, lib.dhd_act_bwd_workspace_bytes(C))
     yy = y if y is not None else dy
     _lib.check(lib.dhd_act_bwd(_p(dy.data), dy.ld, dy.coff, _p(yy.data), yy.ld, yy.coff, dy.N * dy.H * dy.W, C,
-                               ACT_ID[act], _p(out.data), out.ld, out.coff, _p(sums), _p(ws),
+                               ACT_ID[act], _p(out.data) if out is not None else None, out.ld if out is not None else 0,
+                               out.coff if out is not None else 0, _p(sums), _p(ws),
                                _p(add.data) if add is not None else None, add.ld if add is not None else 0,
                                add.coff if add is not None else 0, _stream()), 'act_bwd')
     return out, sums
@@ -65,6 +79,9 @@ class _TrainConv:
         """cols=(lo, hi): the layer uses input-channel columns [lo, hi) of `weight` only (a branch of a
         concatenation whose other columns are handled elsewhere)."""
         self.weight, self.bias_p, self.bn = weight, bias, bn
+        self.batch_bn = bn is not None and BN_MODE == 'batch'
+        if self.batch_bn and cout_pad not in (None, weight.shape[0]):
+            raise NotImplementedError('batch-statistics BatchNorm on a padded output')
         self.ksize, self.dilation, self.cols, self.stride = ksize, dilation, cols, stride
         if stride not in (1, 2) or (stride == 2 and (ksize != 3 or dilation != 1)):
             raise NotImplementedError('stride-2 layers: 3x3, pad 1')
@@ -83,14 +100,14 @@ class _TrainConv:
         taps = self.ksize * self.ksize
         cin_total = w.shape[1]
         if not hasattr(self, 'w_fwd'):
-            if self.bn is not None:
+            if self.bn is not None and not self.batch_bn:
                 s, b = fold_bn(self.bn, None)
                 self.scale, self._bn_bias = s.to(dev), b.to(dev)
             else:
-                self.scale = None
+                self.scale = None                  # batch statistics: nothing to fold, BN runs as its own pass
             self.w_fwd = torch.empty(self.Cout, taps, 1, self.cin_pad, dtype=torch.bfloat16, device=dev)
             self.w_bwd = torch.empty(self.Cin, taps, 1, self.cout_pad, dtype=torch.bfloat16, device=dev)
-        if self.bn is None:
+        if self.bn is None or self.batch_bn:
             self.bias = self.bias_p.detach() if self.bias_p is not None else None     # shares the parameter's storage
         else:
             self.bias = self._bn_bias if self.bias_p is None else self._bn_bias + self.bias_p.detach() * self.scale
@@ -119,12 +136,78 @@ class _TrainConv:
                     self.phases.append((py, px, offs, wp.unsqueeze(2).to(torch.bfloat16).contiguous()))
 
     def forward(self, x, segs, **kw):
+        if self.batch_bn:
+            return self._forward_batch_bn(x, segs, **kw)
         return D.conv2d(x, self.w_fwd, self.Cout, ksize=self.ksize, dilation=self.dilation, precision='bf16',
                         scale=self.scale, bias=self.bias, segs=segs, stride=self.stride, **kw)
+
+    # ---- BatchNorm with batch statistics: conv -> raw (bf16), statistics, normalise + activation as a second pass
+    def _forward_batch_bn(self, x, segs, img_bias=None, img_gate=None, residual=None):
+        if len(segs) != 1:
+            raise NotImplementedError('batch-statistics BatchNorm: one output segment')
+        seg, bn, lib = segs[0], self.bn, _lib.load()
+        oH, oW = (x.H, x.W) if self.stride == 1 else ((x.H + 1) // 2, (x.W + 1) // 2)
+        key = (x.N, oH, oW)
+        if getattr(self, '_raw_key', None) != key:
+            self._raw = D.Act.empty(x.N, oH, oW, self.Cout, 1, x.data.device)
+            self._dyraw = D.Act.empty(x.N, oH, oW, self.cout_pad, 1, x.data.device)
+            if self.cout_pad != self.Cout:
+                self._dyraw.data.zero_()
+            self._raw_key = key
+        raw = self._raw
+        D.conv2d(x, self.w_fwd, self.Cout, ksize=self.ksize, dilation=self.dilation, precision='bf16', bias=self.bias,
+                 img_bias=img_bias, segs=[dict(out_act=raw)], stride=self.stride)
+        _, sums = act_bwd(raw, raw, None, want_sums=True, write=False)            # [sum raw, sum raw^2]
+        M = float(x.N * oH * oW)
+        mean = sums[0] / M
+        var = (sums[1] / M - mean * mean).clamp_(min=0.0)
+        invstd = torch.rsqrt(var + bn.eps)
+        scale = (bn.weight.detach() * invstd).contiguous()
+        shift = (bn.bias.detach() - mean * scale).contiguous()
+        if bn.track_running_stats:
+            m = bn.momentum if bn.momentum is not None else 0.1
+            bn.running_mean.mul_(1 - m).add_(mean, alpha=m)
+            bn.running_var.mul_(1 - m).add_(var * (M / max(M - 1.0, 1.0)), alpha=m)
+        self._bn_saved = (mean, invstd, M)
+        ob, of, f_ld = seg.get('out_act'), None, 0
+        if seg.get('out_f32') is not None:
+            of, st = seg['out_f32']
+            if st[3] != 1 or st[2] < self.Cout:
+                raise NotImplementedError('batch-statistics BatchNorm: fp32 output must be NHWC rows')
+            f_ld = st[2]
+        res, res_ld = (None, 0) if residual is None else (residual[0], residual[1][2])
+        _lib.check(lib.dhd_bn_apply(_p(raw.data), raw.ld, raw.coff, x.N * oH * oW, self.Cout, _p(scale), _p(shift),
+                                    ACT_ID[seg.get('act')], _p(res), res_ld, _p(img_gate), oH * oW,
+                                    _p(ob.data) if ob is not None else None, ob.ld if ob is not None else 0,
+                                    ob.coff if ob is not None else 0, _p(of), f_ld, _stream()), 'bn_apply')
+
+    def _backward_batch_bn(self, dy):
+        """dy: gradient at the BatchNorm output (pre-activation).  Accumulates d gamma / d beta and returns the gradient
+        at the convolution output (a scratch activation: dy itself may feed other layers and is left untouched)."""
+        bn, raw = self.bn, self._raw
+        mean, invstd, M = self._bn_saved
+        _, sums = act_bwd(dy, raw, None, want_sums=True, write=False)             # [sum dz, sum dz * raw]
+        s1 = sums[0][:self.Cout]
+        s2 = sums[1][:self.Cout] - mean * s1                                      # sum dz * (raw - mean)
+        if bn.weight.requires_grad:
+            _acc(bn.weight, s2 * invstd)
+            _acc(bn.bias, s1)
+        k1 = bn.weight.detach() * invstd
+        k2 = -k1 * s2 * invstd * invstd / M
+        k3 = -k1 * (s1 / M) - k2 * mean
+        out = self._dyraw
+        _lib.check(_lib.load().dhd_affine_combine(_p(dy.data), dy.ld, dy.coff, _p(raw.data), raw.ld, raw.coff,
+                                                  raw.N * raw.H * raw.W, self.Cout, _p(k1.contiguous()),
+                                                  _p(k2.contiguous()), _p(k3.contiguous()), _p(out.data), out.ld,
+                                                  out.coff, _stream()), 'affine_combine')
+        return out
 
     def backward(self, x, dy, dx_segs=None, bias_sums=None, **kw):
         """dy: Act = gradient w.r.t. this layer's pre-activation output (channels >= Cout zero).
         Accumulates weight / bias gradients; writes dx through `dx_segs` (conv2d segs) if given."""
+        if self.batch_bn:
+            dy = self._backward_batch_bn(dy)
+            bias_sums = None                       # a conv bias under a batch-statistics BN has zero gradient
         dw = D.conv2d_wgrad(x, dy, self.Cout, ksize=self.ksize, dilation=self.dilation, scale=self.scale,
                             stride=self.stride)
         if x.C != self.Cin:
@@ -451,6 +534,8 @@ class HeightNetTrainer:
             self.bn_scale, self.bn_shift = fold_bn(net.bn)
             self.s5, self.b5 = fold_bn(a.global_avg_pool[2])
             self.s1, _ = fold_bn(a.bn1)
+            if self.aspp_out.batch_bn:                 # batch statistics: the global branch enters the conv sum unscaled
+                self.s1 = torch.ones_like(self.s1)
             cg, k = self.C // self.groups, self.k
             self.dcn_wf = [torch.empty(cg, k * k * cg, 1, 1, dtype=torch.bfloat16, device=self.device).view(cg, 1, 1, k * k * cg)
                            for _ in range(self.groups)]
@@ -580,9 +665,11 @@ class HeightNetTrainer:
         self.dcn_offset.backward(ha, doff_a, [dict(out_act=dha)], bias_sums=sums[0], residual=(dxs, nhwc[:3]))
         # ---- ASPP
         act_bwd(dha, ha, 'relu')
-        dib = self._mean(dha) * float(HW)                                       # (N, C): sum over pixels
         dcat = self._act('d_cat', N, H, W, 4 * mid)
         self.aspp_out.backward(cat, dha, [dict(out_act=dcat)])
+        # gradient of the per-image bias the global branch adds to the conv sum: pixel sum of the gradient at the
+        # convolution output (behind the BatchNorm backward when it runs on batch statistics)
+        dib = self._mean(self.aspp_out._dyraw if self.aspp_out.batch_bn else dha) * float(HW)
         x5, meanh = sv['x5'], sv['meanh']
         s1, s5 = self.s1.to(self.device), self.s5.to(self.device)
         a = self.aspp

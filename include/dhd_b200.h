@@ -308,6 +308,18 @@ int dhd_pack_conv_weights(const float* w, int Cout, int cin_total, int taps, int
                           const float* scale, void* fwd, int cin_pad, void* bwd, int cout_pad, int bwd_mode,
                           void* stream);
 
+/* batch-statistics BatchNorm of the training path (torch BatchNorm2d in training mode after every convolution of the
+ * reference's modules).  Forward: out = act(scale[c]*raw + shift[c] [+ residual]) [* gate[n][c]] on the convolution's
+ * bf16 output `raw` (scale / shift from its batch statistics; the sums come from dhd_act_bwd(raw, raw, act none)).
+ * Backward: out = k1[c]*a + k2[c]*b + k3[c] (a = dz, b = raw; out may alias a): the BatchNorm backward as a per-channel affine
+ * combination (coefficients at bn_apply_kernel in csrc/train.cu). */
+int dhd_bn_apply(const void* raw, int raw_ld, int raw_coff, long rows, int C, const float* scale,
+                 const float* shift, int act, const float* residual, long res_ld, const float* gate,
+                 int rows_per_img, void* out_b16, int o_ld, int o_coff, float* out_f32, long f_ld, void* stream);
+int dhd_affine_combine(const void* a, int a_ld, int a_coff, const void* b, int b_ld, int b_coff, long rows, int C,
+                       const float* k1, const float* k2, const float* k3, void* out, int o_ld, int o_coff,
+                       void* stream);
+
 /* ---- streaming layout / elementwise helpers of the dense path (csrc/layout.cu) -----------
  * "split-bf16 NHWC": bf16, `ld` channels per pixel, logical channel c of part p at
  * coff + p*part_stride + c; the fp32 value is the sum of the parts. */

@@ -83,7 +83,12 @@ def seeded_tensor(shape, seed, scale=1.0):
 
 
 # ------------------------------------------------------------------ functional restatements
+BN_TRAIN = False     # True: BatchNorm2d in training mode (batch statistics), for the training-path parity tests
+
+
 def _bn(sd, p, x, eps=1e-5):
+    if BN_TRAIN and x.dim() == 4 and x.shape[2] * x.shape[3] > 1:
+        return F.batch_norm(x, None, None, sd[p + '.weight'], sd[p + '.bias'], True, 0.0, eps)
     return F.batch_norm(x, sd[p + '.running_mean'], sd[p + '.running_var'], sd[p + '.weight'],
                         sd[p + '.bias'], False, 0.0, eps)
 

@@ -101,10 +101,11 @@ def _q(t):
     return t + (t.bfloat16().float() - t).detach()
 
 
-def _sfa_forward_q(sd, x, q):
+def _sfa_forward_q(sd, x, q, qraw=lambda t: t):
     """oracle.dense_oracle.sfa_forward (mix.py:37-59, 87-90) with `q` applied where the CUDA path rounds an
-    activation to bf16 (u, t, fuse, r, out), so ReLU masks and saved values agree between the two sides and
-    the comparison measures the backward arithmetic."""
+    activation to bf16 (u, t, fuse, r, out) and `qraw` where it stores a convolution output before a batch-statistics
+    BatchNorm, so ReLU masks and saved values agree between the two sides and the comparison measures the backward
+    arithmetic."""
     import torch.nn.functional as F
     from oracle.dense_oracle import _bn
     C = x.shape[1] // 2
@@ -114,12 +115,12 @@ def _sfa_forward_q(sd, x, q):
                                 sd['mysk_7.fc.2.weight'], sd['mysk_7.fc.2.bias']))[..., None, None]
     b1, v1 = a1 * bev, (1 - a1) * vox
     k = 'mysk_7.spacial_leanring'
-    t = q(F.relu(_bn(sd, k + '.1', F.conv2d(q(b1 + v1), sd[k + '.0.weight'], sd[k + '.0.bias']))))
-    a2 = torch.sigmoid(_bn(sd, k + '.4', F.conv2d(t, sd[k + '.3.weight'], sd[k + '.3.bias'])))
+    t = q(F.relu(_bn(sd, k + '.1', qraw(F.conv2d(q(b1 + v1), sd[k + '.0.weight'], sd[k + '.0.bias'])))))
+    a2 = torch.sigmoid(_bn(sd, k + '.4', qraw(F.conv2d(t, sd[k + '.3.weight'], sd[k + '.3.bias']))))
     fuse = q(a2 * b1 + (1 - a2) * v1)
-    r = q(F.relu(_bn(sd, 'mix_residual.1', F.conv2d(fuse, sd['mix_residual.0.weight'], padding=1))))
-    r = _bn(sd, 'mix_residual.4', F.conv2d(r, sd['mix_residual.3.weight'], padding=1))
-    sc = _bn(sd, 'mix_shortcut.1', F.conv2d(x, sd['mix_shortcut.0.weight']))
+    r = q(F.relu(_bn(sd, 'mix_residual.1', qraw(F.conv2d(fuse, sd['mix_residual.0.weight'], padding=1)))))
+    r = _bn(sd, 'mix_residual.4', qraw(F.conv2d(r, sd['mix_residual.3.weight'], padding=1)))
+    sc = _bn(sd, 'mix_shortcut.1', qraw(F.conv2d(x, sd['mix_shortcut.0.weight'])))
     return q(F.relu(r + sc))
 
 
@@ -484,14 +485,15 @@ def test_bev_encoder_backward(cuda_lib):
     assert max(errs.values()) < 0.12, errs
 
 
-def test_train_step_with_encoders_end_to_end(cuda_lib):
+@pytest.mark.parametrize('bn', ['frozen', 'batch'])
+def test_train_step_with_encoders_end_to_end(cuda_lib, bn):
     """TrainStep(encoders=True): the occupancy loss reaches depth_net through SFA, the encoders and the fused pool
     backward (no stand-in tensor in between); every trainable parameter gets a finite, non-zero gradient and a few
     AdamW steps on one batch reduce the loss."""
     from dhd_b200 import synth
     from dhd_b200.pipeline import TrainStep
     cfg, B = synth.DHD_S, 1
-    ts = TrainStep(cfg, B, encoders=True)
+    ts = TrainStep(cfg, B, encoders=True, bn=bn)     # bn='batch': BatchNorm2d in training mode everywhere
     host = ts.make_host_inputs(synth.synthetic_rig(B, cfg['ncams'], cfg['input_size'], seed=3), seed=3)
     ts.alloc_static(host)
     ts.upload(host)
@@ -517,3 +519,52 @@ def test_train_step_with_encoders_end_to_end(cuda_lib):
     torch.cuda.synchronize()
     drop = (first - total()) / first
     assert 0.01 < drop < 0.06, (first, total(), drop)
+
+
+def _train_bn_sd(module, seed):
+    from oracle import dense_oracle as DO
+    return _bf16_sd(DO.seeded_state_dict(module, seed))
+
+
+def test_sfa_backward_batch_statistics_bn(cuda_lib):
+    """SFA with BatchNorm in training mode (batch statistics, trainable gamma / beta): outputs, every gradient incl.
+    the BatchNorm affine parameters, and dL/dx against autograd over the oracle with F.batch_norm(training=True)."""
+    import projects.mmdet3d_plugin  # noqa: F401
+    from dhd_b200 import dense as D
+    from dhd_b200 import train as T
+    from oracle import dense_oracle as DO
+    from projects.mmdet3d_plugin.models.necks.mix import SFA
+    sfa = SFA(512, 256).eval()
+    sfa.load_state_dict(_train_bn_sd(sfa, 1))
+    B, H, W = 2, 24, 40
+    x = DO.seeded_tensor((B, 512, H, W), 3).bfloat16().float()
+    gout = (DO.seeded_tensor((B, 256, H, W), 4) * 0.01).bfloat16().float()
+    sd = {k: v.clone().requires_grad_(v.dtype.is_floating_point and 'running' not in k) for k, v in sfa.state_dict().items()}
+    xr = x.clone().requires_grad_()
+    DO.BN_TRAIN = True
+    try:
+        y = _sfa_forward_q(sd, xr, _q, _q)
+    finally:
+        DO.BN_TRAIN = False
+    (y * gout).sum().backward()
+    sfa = sfa.cuda()
+    for p in sfa.parameters():
+        p.grad = None
+    T.set_bn_mode('batch')
+    try:
+        tr = T.SFATrainer(sfa)
+    finally:
+        T.set_bn_mode('frozen')
+    out = tr.forward(D.pack_input(x.cuda(), 1))
+    assert rel(out.float(), y.detach()) < 1e-2
+    dx = tr.backward(D.pack_input(gout.cuda(), 1))
+    torch.cuda.synchronize()
+    errs = {}
+    for name, p in sfa.named_parameters():
+        if p.grad is None:       # a conv bias under a batch-statistics BatchNorm: zero gradient (autograd: rounding noise)
+            assert name.endswith('.bias') and float(sd[name].grad.abs().max()) < 1e-5, name
+            continue
+        errs[name] = rel(p.grad, sd[name].grad)
+    errs['x'] = rel(dx.float(), xr.grad)
+    print('relative L2 gradient errors:', {k: round(v, 4) for k, v in errs.items()})
+    assert max(errs.values()) < 3e-2, errs
