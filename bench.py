@@ -235,7 +235,7 @@ def run_ours(args):
         from dhd_b200.pipeline import TrainStep
         del step.graph
         step.graph = None
-        ts = TrainStep(cfg, B)
+        ts = TrainStep(cfg, B, bn='batch')
         ts.alloc_static(host)
         ts.upload(host)
         lib = _lib.load()
@@ -261,14 +261,14 @@ def run_ours(args):
                  'gradient_all_reduce_bytes': ts.n_params * 4,
                  'loss_height': float(ts.loss_height[0]),
                  'what': 'forward + losses (occupancy CE + sem_scal + geo_scal, height BCE) + backward of depth_net, HeightNet, SFA and predictor '
-                         '(BatchNorm frozen), fused pool fwd+bwd, one NCCL all-reduce of the fp32 gradient bucket, AdamW, '
+                         '(BatchNorm2d in training mode: batch statistics, trainable affine), fused pool fwd+bwd, one NCCL all-reduce of the fp32 gradient bucket, AdamW, '
                          'bf16 weight re-pack; encoders stand in as resident tensors (see TrainStep)'}
         del ts
         torch.cuda.empty_cache()
         if not args.no_encoders:
             # the same step with the real encoders in forward and backward: the occupancy loss reaches the pool and
             # depth_net through them (no stand-in tensor left between the image features and the losses)
-            tse = TrainStep(cfg, B, encoders=True)
+            tse = TrainStep(cfg, B, encoders=True, bn='batch')
             tse.alloc_static(host)
             tse.upload(host)
             tse.train_step()

@@ -503,7 +503,8 @@ def test_train_step_with_encoders_end_to_end(cuda_lib, bn):
     assert torch.isfinite(ts.bucket.flat).all()
     for name, mod in (('depth_net', ts.vt.depth_net), ('unet0', ts.voxel[0]), ('unet2', ts.voxel[2]),
                       ('bev backbone', ts.bev_backbone), ('bev neck', ts.bev_neck), ('sfa', ts.sfa), ('head', ts.head)):
-        norms = [float(p.grad.norm()) for p in mod.parameters() if p.requires_grad]
+        norms = [float(p.grad.norm()) for n_, p in mod.named_parameters() if p.requires_grad and
+                 not (bn == 'batch' and n_.endswith('.bias'))]        # a conv bias under a batch-stat BN: zero gradient
         assert norms and min(norms) > 0.0, name
     # directional-derivative check of the WHOLE gradient: a step of -eps * g with eps = 0.03 * loss / |g|^2 must lower
     # the total loss by about 3 % (first order); a wrong sign or scale anywhere in the chain breaks this
