@@ -772,6 +772,48 @@ affine_combine_kernel(const __nv_bfloat16* __restrict__ a, int a_ld, int a_coff,
   store8(out + r * o_ld + o_coff + c, x);
 }
 
+
+// per-channel coefficients of the two BatchNorm passes in ONE small launch each (instead of a dozen tensor ops)
+__global__ void __launch_bounds__(256)
+bn_fwd_coeffs_kernel(const float* __restrict__ sums, int C, float M, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, float eps, float momentum, float* __restrict__ running_mean,
+                     float* __restrict__ running_var, float* __restrict__ scale, float* __restrict__ shift,
+                     float* __restrict__ mean_out, float* __restrict__ invstd_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float mean = sums[c] / M;
+  const float var = fmaxf(sums[C + c] / M - mean * mean, 0.f);
+  const float invstd = rsqrtf(var + eps);
+  const float sc = gamma[c] * invstd;
+  scale[c] = sc;
+  shift[c] = beta[c] - mean * sc;
+  mean_out[c] = mean;
+  invstd_out[c] = invstd;
+  if (running_mean != nullptr) {
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * var * (M / fmaxf(M - 1.f, 1.f));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+bn_bwd_coeffs_kernel(const float* __restrict__ sums, int C, int sums_stride, float M, const float* __restrict__ mean,
+                     const float* __restrict__ invstd, const float* __restrict__ gamma, float* __restrict__ k1,
+                     float* __restrict__ k2, float* __restrict__ k3, float* __restrict__ dgamma,
+                     float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float s1 = sums[c];
+  const float s2 = sums[sums_stride + c] - mean[c] * s1;        // sum dz * (raw - mean)
+  const float is = invstd[c];
+  const float a = gamma[c] * is;
+  const float b = -a * s2 * is * is / M;
+  k1[c] = a;
+  k2[c] = b;
+  k3[c] = -a * (s1 / M) - b * mean[c];
+  if (dgamma != nullptr) dgamma[c] += s2 * is;
+  if (dbeta != nullptr) dbeta[c] += s1;
+}
+
 }  // namespace dhd
 
 using namespace dhd;
@@ -997,5 +1039,27 @@ extern "C" int dhd_affine_combine(const void* a, int a_ld, int a_coff, const voi
       (const __nv_bfloat16*)a, a_ld, a_coff, (const __nv_bfloat16*)b, b_ld, b_coff, rows, C, k1, k2, k3,
       (__nv_bfloat16*)out, o_ld, o_coff);
   DHD_CUDA_LAUNCH_CHECK("affine_combine");
+  return DHD_OK;
+}
+
+extern "C" int dhd_bn_fwd_coeffs(const float* sums, int C, float M, const float* gamma, const float* beta, float eps,
+                                 float momentum, float* running_mean, float* running_var, float* scale, float* shift,
+                                 float* mean, float* invstd, void* stream) {
+  DHD_REQUIRE(sums && gamma && beta && scale && shift && mean && invstd && C > 0 && M > 0.f, "bad arguments");
+  DHD_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "running statistics come as a pair");
+  bn_fwd_coeffs_kernel<<<(C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(sums, C, M, gamma, beta, eps, momentum,
+                                                                         running_mean, running_var, scale, shift, mean,
+                                                                         invstd);
+  DHD_CUDA_LAUNCH_CHECK("bn_fwd_coeffs");
+  return DHD_OK;
+}
+
+extern "C" int dhd_bn_bwd_coeffs(const float* sums, int C, int sums_stride, float M, const float* mean,
+                                 const float* invstd, const float* gamma, float* k1, float* k2, float* k3,
+                                 float* dgamma, float* dbeta, void* stream) {
+  DHD_REQUIRE(sums && mean && invstd && gamma && k1 && k2 && k3 && C > 0 && sums_stride >= C && M > 0.f, "bad arguments");
+  bn_bwd_coeffs_kernel<<<(C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(sums, C, sums_stride, M, mean, invstd, gamma,
+                                                                         k1, k2, k3, dgamma, dbeta);
+  DHD_CUDA_LAUNCH_CHECK("bn_bwd_coeffs");
   return DHD_OK;
 }

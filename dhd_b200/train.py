@@ -159,16 +159,16 @@ class _TrainConv:
                  img_bias=img_bias, segs=[dict(out_act=raw)], stride=self.stride)
         _, sums = act_bwd(raw, raw, None, want_sums=True, write=False)            # [sum raw, sum raw^2]
         M = float(x.N * oH * oW)
-        mean = sums[0] / M
-        var = (sums[1] / M - mean * mean).clamp_(min=0.0)
-        invstd = torch.rsqrt(var + bn.eps)
-        scale = (bn.weight.detach() * invstd).contiguous()
-        shift = (bn.bias.detach() - mean * scale).contiguous()
-        if bn.track_running_stats:
-            m = bn.momentum if bn.momentum is not None else 0.1
-            bn.running_mean.mul_(1 - m).add_(mean, alpha=m)
-            bn.running_var.mul_(1 - m).add_(var * (M / max(M - 1.0, 1.0)), alpha=m)
-        self._bn_saved = (mean, invstd, M)
+        if getattr(self, '_bn_buf', None) is None:
+            self._bn_buf = torch.empty(7, self.Cout, device=x.data.device)       # scale, shift, mean, invstd, k1, k2, k3
+        bb = self._bn_buf
+        track = bn.track_running_stats
+        _lib.check(lib.dhd_bn_fwd_coeffs(_p(sums), self.Cout, M, _p(bn.weight.detach()), _p(bn.bias.detach()), bn.eps,
+                                         bn.momentum if bn.momentum is not None else 0.1,
+                                         _p(bn.running_mean) if track else None, _p(bn.running_var) if track else None,
+                                         _p(bb[0]), _p(bb[1]), _p(bb[2]), _p(bb[3]), _stream()), 'bn_fwd_coeffs')
+        scale, shift = bb[0], bb[1]
+        self._bn_saved = M
         ob, of, f_ld = seg.get('out_act'), None, 0
         if seg.get('out_f32') is not None:
             of, st = seg['out_f32']
@@ -184,22 +184,18 @@ class _TrainConv:
     def _backward_batch_bn(self, dy):
         """dy: gradient at the BatchNorm output (pre-activation).  Accumulates d gamma / d beta and returns the gradient
         at the convolution output (a scratch activation: dy itself may feed other layers and is left untouched)."""
-        bn, raw = self.bn, self._raw
-        mean, invstd, M = self._bn_saved
+        bn, raw, bb, M = self.bn, self._raw, self._bn_buf, self._bn_saved
         _, sums = act_bwd(dy, raw, None, want_sums=True, write=False)             # [sum dz, sum dz * raw]
-        s1 = sums[0][:self.Cout]
-        s2 = sums[1][:self.Cout] - mean * s1                                      # sum dz * (raw - mean)
-        if bn.weight.requires_grad:
-            _acc(bn.weight, s2 * invstd)
-            _acc(bn.bias, s1)
-        k1 = bn.weight.detach() * invstd
-        k2 = -k1 * s2 * invstd * invstd / M
-        k3 = -k1 * (s1 / M) - k2 * mean
+        train_affine = bn.weight.requires_grad
+        _lib.check(_lib.load().dhd_bn_bwd_coeffs(_p(sums), self.Cout, sums.shape[1], M, _p(bb[2]), _p(bb[3]),
+                                                 _p(bn.weight.detach()), _p(bb[4]), _p(bb[5]), _p(bb[6]),
+                                                 _p(_ensure_grad(bn.weight)) if train_affine else None,
+                                                 _p(_ensure_grad(bn.bias)) if train_affine else None, _stream()),
+                   'bn_bwd_coeffs')
         out = self._dyraw
         _lib.check(_lib.load().dhd_affine_combine(_p(dy.data), dy.ld, dy.coff, _p(raw.data), raw.ld, raw.coff,
-                                                  raw.N * raw.H * raw.W, self.Cout, _p(k1.contiguous()),
-                                                  _p(k2.contiguous()), _p(k3.contiguous()), _p(out.data), out.ld,
-                                                  out.coff, _stream()), 'affine_combine')
+                                                  raw.N * raw.H * raw.W, self.Cout, _p(bb[4]), _p(bb[5]), _p(bb[6]),
+                                                  _p(out.data), out.ld, out.coff, _stream()), 'affine_combine')
         return out
 
     def backward(self, x, dy, dx_segs=None, bias_sums=None, **kw):

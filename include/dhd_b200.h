@@ -316,6 +316,15 @@ int dhd_pack_conv_weights(const float* w, int Cout, int cin_total, int taps, int
 int dhd_bn_apply(const void* raw, int raw_ld, int raw_coff, long rows, int C, const float* scale,
                  const float* shift, int act, const float* residual, long res_ld, const float* gate,
                  int rows_per_img, void* out_b16, int o_ld, int o_coff, float* out_f32, long f_ld, void* stream);
+/* per-channel coefficients of the two passes from the reduced sums (one launch each): forward -- scale / shift (and
+ * mean / invstd for the backward, running statistics updated with `momentum` when given) from sums = [sum raw,
+ * sum raw^2]; backward -- k1 / k2 / k3 from sums = [sum dz, sum dz*raw] (second half at sums_stride), d gamma / d beta
+ * accumulated when given. */
+int dhd_bn_fwd_coeffs(const float* sums, int C, float M, const float* gamma, const float* beta, float eps,
+                      float momentum, float* running_mean, float* running_var, float* scale, float* shift,
+                      float* mean, float* invstd, void* stream);
+int dhd_bn_bwd_coeffs(const float* sums, int C, int sums_stride, float M, const float* mean, const float* invstd,
+                      const float* gamma, float* k1, float* k2, float* k3, float* dgamma, float* dbeta, void* stream);
 int dhd_affine_combine(const void* a, int a_ld, int a_coff, const void* b, int b_ld, int b_coff, long rows, int C,
                        const float* k1, const float* k2, const float* k3, void* out, int o_ld, int o_coff,
                        void* stream);
