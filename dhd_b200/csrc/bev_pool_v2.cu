@@ -133,6 +133,7 @@ extern "C" size_t dhd_abi_sizeof(int which) {
     case 1: return sizeof(dhd_conv_seg);
     case 2: return sizeof(dhd_conv_desc);
     case 3: return sizeof(dhd_wgrad_desc);
+    case 4: return sizeof(dhd_stereo_desc);
     default: return 0;
   }
 }

@@ -111,9 +111,19 @@ class HeightNetEngine:
         i = 0
         while i < len(layers) and type(layers[i]).__name__ == 'BasicBlock':
             blk = layers[i]
+            w1, ds = blk.conv1.weight.detach().float(), None
             if blk.downsample is not None:
-                raise NotImplementedError('HeightNet stereo downsample branch is not on this path yet')
-            self.blocks.append((_Conv(blk.conv1, blk.bn1, precision, dev), _Conv(blk.conv2, blk.bn2, precision, dev)))
+                # stereo DepthNet (depthnet.py:203-218): the first block reads cat(gated feature, cost volume) and
+                # carries a plain 1x1 convolution on its identity path; both weights get zero columns up to the
+                # 64-channel granule of the concatenation buffer
+                cin = w1.shape[1]
+                self.cat_channels = (cin + 63) // 64 * 64
+                pad = self.cat_channels - cin
+                wd = blk.downsample.weight.detach().float()
+                w1 = torch.nn.functional.pad(w1, (0, 0, 0, 0, 0, pad))
+                ds = _Conv(blk.downsample, None, precision, dev, weight=torch.nn.functional.pad(wd, (0, 0, 0, 0, 0, pad)))
+            self.blocks.append((_Conv(blk.conv1, blk.bn1, precision, dev, weight=w1),
+                                _Conv(blk.conv2, blk.bn2, precision, dev), ds))
             i += 1
         self.aspp = None
         if i < len(layers) and type(layers[i]).__name__ == 'ASPP':
@@ -179,8 +189,11 @@ class HeightNetEngine:
         N, H, W, C, P, dev = h.N, h.H, h.W, self.C, self.parts, h.data.device
         new = lambda c: D.Act.empty(N, H, W, c, P, dev)
         nhwc = D.nhwc_strides(C, H, W)
-        for c1, c2 in self.blocks:
+        for c1, c2, ds in self.blocks:
             t = new(C)
+            if ds is not None:                       # identity path = 1x1 convolution of the concatenated input
+                h32 = torch.empty(N, H, W, C, device=dev)
+                ds(h, [dict(out_f32=(h32, nhwc))])
             c1(h, [dict(act='relu', out_act=t)])
             h2, h2_32 = new(C), torch.empty(N, H, W, C, device=dev)
             c2(t, [dict(act='relu', out_act=h2, out_f32=(h2_32, nhwc))], residual=(h32, nhwc[:3]))
@@ -222,8 +235,8 @@ class HeightNetEngine:
 
 
 class DepthNetEngine(HeightNetEngine):
-    """DepthNet of MGHS_Depth / MGHS_Stereo (depthnet.py:172-243, 362-415), non-stereo path:
-    the reduce_conv output feeds a camera-gated context branch (1x1 conv) and a camera-gated
+    """DepthNet of MGHS_Depth / MGHS_Stereo (depthnet.py:172-243, 362-415); with stereo=True the plane-sweep cost
+    volume (dhd_b200.stereo) joins the depth trunk through cost_volumn_net.  The reduce_conv output feeds a camera-gated context branch (1x1 conv) and a camera-gated
     depth trunk (the same trunk as HeightNet).  Returns (depth (B*N, D, fH, fW) NCHW, softmax-ed
     or raw, context (B*N, fH, fW, C) NHWC) -- the pool's input layouts."""
 
@@ -236,6 +249,17 @@ class DepthNetEngine(HeightNetEngine):
         self.cse_e_w, self.cse_e_b = f(se.conv_expand.weight.flatten(1)), f(se.conv_expand.bias)
         self.context = _Conv(net.context_conv, None, precision, device)
         self.Cctx = self.context.Cout
+        self.stereo = bool(getattr(net, 'stereo', False))
+        if self.stereo:
+            # cost_volumn_net (depthnet.py:207-213): two stride-2 conv3x3 + BN on the D matching probabilities;
+            # the D channels ride in a 64-channel granule (zero weight columns for the padding)
+            cv = net.cost_volumn_net
+            self.Dcv = cv[0].in_channels
+            self.Dcv_pad = (self.Dcv + 63) // 64 * 64
+            padw = lambda c: torch.nn.functional.pad(c.weight.detach().float(), (0, 0, 0, 0, 0, self.Dcv_pad - self.Dcv))
+            self.cv1 = _Conv(cv[0], cv[1], precision, device, weight=padw(cv[0]))
+            self.cv2 = _Conv(cv[2], cv[3], precision, device, weight=padw(cv[2]))
+            self.cv_bias = float(net.bias)
 
     def context_gate(self, mlp_input):
         x = mlp_input.reshape(-1, mlp_input.shape[-1]).contiguous().float()
@@ -252,15 +276,38 @@ class DepthNetEngine(HeightNetEngine):
                                                  out.part_stride, out.parts, _p(o32), _stream()), 'gate_channels')
         return out, o32
 
-    def __call__(self, x, mlp_input, softmax=True):
+    def new_cost_volume(self, N, H, W, device, zero=False):
+        """The split-bf16 NHWC activation the cost-volume kernel fills (stereo map size H x W = 4fH x 4fW).
+        zero=True: the all-zero volume the reference feeds when there is no previous frame (depthnet.py:389-396)."""
+        a = D.Act.empty(N, H, W, self.Dcv_pad, self.parts, device)
+        if zero:
+            a.data.zero_()
+        return a
+
+    def __call__(self, x, mlp_input, softmax=True, cost_volume=None):
         N, H, W, C, dev = x.N, x.H, x.W, self.C, x.data.device
         x32 = torch.empty(N, H, W, C, device=dev)
         self.reduce(x, [dict(act='relu', out_f32=(x32, D.nhwc_strides(C, H, W)))])
         ctx, _ = self._gated(x32, self.context_gate(mlp_input), False)
         feat = torch.empty(N, H, W, self.Cctx, device=dev)
         self.context(ctx, [dict(out_f32=(feat, D.nhwc_strides(self.Cctx, H, W)))])
-        h, h32 = self._gated(x32, self.gate(mlp_input), True)
-        return self.trunk(h, h32, softmax), feat
+        if not self.stereo:
+            h, h32 = self._gated(x32, self.gate(mlp_input), True)
+            return self.trunk(h, h32, softmax), feat
+        if cost_volume is None or (cost_volume.H + 3) // 4 != H or (cost_volume.W + 3) // 4 != W:
+            raise ValueError('stereo DepthNet needs the (B*N, 4fH, 4fW, D) cost volume activation')
+        # cat([gated depth feature, cost_volumn_net(cost volume)]) as two channel slices of one zero-padded buffer
+        cat = D.Act(torch.zeros(N, H, W, self.parts * self.cat_channels, dtype=torch.bfloat16, device=dev),
+                    self.cat_channels, self.parts)
+        g = cat.slice(0, C)
+        _lib.check(_lib.load().dhd_gate_channels(_p(x32), N, H * W, C, _p(self.gate(mlp_input)), _p(g.data), g.ld, g.coff,
+                                                 g.part_stride, g.parts, None, _stream()), 'gate_channels')
+        h2, w2 = (cost_volume.H + 1) // 2, (cost_volume.W + 1) // 2
+        mid = D.Act(torch.zeros(N, h2, w2, self.parts * self.Dcv_pad, dtype=torch.bfloat16, device=dev),
+                    self.Dcv_pad, self.parts)
+        self.cv1(cost_volume, [dict(out_act=mid)], stride=2)
+        self.cv2(mid, [dict(out_act=cat.slice(C, self.cat_channels))], stride=2)
+        return self.trunk(cat, None, softmax), feat
 
 
 class DepthHeadEngine:

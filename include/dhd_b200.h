@@ -22,6 +22,8 @@
  *                            ops/bev_pool_v2/bev_pool.py:44-83
  *   dhd_conv2d_fwd        <- nn.Conv2d / nn.Linear of depth_net, HeightNet, SFA, predictor
  *                            (see the dense-layer section below)
+ *   dhd_stereo_cost_volume <- DepthNet.gen_grid + calculate_cost_volumn
+ *                            models/model_utils/depthnet.py:245-361
  *   dhd_mghs_voxel_index  <- the (kept, ranks_bev) part of voxel_pooling_prepare_v2
  *                            models/necks/lss_heightmap.py:331-354 (bit-exact parity hook)
  */
@@ -75,7 +77,7 @@ typedef struct dhd_mghs_cfg {
 
 const char* dhd_last_error(void);
 int dhd_abi_version(void);
-/* sizeof(dhd_mghs_cfg | dhd_conv_seg | dhd_conv_desc | dhd_wgrad_desc) for which = 0..3: lets a binding check its
+/* sizeof(dhd_mghs_cfg | dhd_conv_seg | dhd_conv_desc | dhd_wgrad_desc | dhd_stereo_desc) for which = 0..4: lets a binding check its
  * own struct layout against the library it loaded */
 size_t dhd_abi_sizeof(int which);
 
@@ -328,6 +330,38 @@ int dhd_bn_bwd_coeffs(const float* sums, int C, int sums_stride, float M, const 
 int dhd_affine_combine(const void* a, int a_ld, int a_coff, const void* b, int b_ld, int b_coff, long rows, int C,
                        const float* k1, const float* k2, const float* k3, void* out, int o_ld, int o_coff,
                        void* stream);
+
+/* ---- plane-sweep stereo cost volume of the camera-aware DepthNet (csrc/stereo.cu) ----------
+ * Replaces DepthNet.gen_grid + DepthNet.calculate_cost_volumn (models/model_utils/depthnet.py:245-308, 310-361):
+ * the previous frame's 1/4-resolution stereo feature is warped to every depth hypothesis of every current pixel
+ * (bilinear, zeros outside, align_corners=True), the L1 distance to the current feature is summed over the channels,
+ * `bias` is added where the reference's "warped channel C-4 == 0" test fires, and softmax(-cost) over depth is
+ * written.  Features are NHWC (BN, H, W, C), fp32 or bf16 (dhd_nchw_to_nhwc converts the reference's NCHW fp32).
+ * Per image `cam` holds DHD_STEREO_CAM_FLOATS fp32 values, all row-major:
+ *   [0..8]  inverse(post_rots)      [9..11]  post_trans      [12..20] k2s_sensor[:3,:3] @ inverse(intrins)
+ *   [21..23] k2s_sensor[:3,3]       [24..32] intrins         [33..36] post_rots[:2,:2]     [37..38] post_trans[:2]
+ * (the small inverses / products stay on the host side in torch, as in the reference, so they round identically). */
+#define DHD_STEREO_CAM_FLOATS 40
+typedef struct dhd_stereo_desc {
+  int32_t BN, C, H, W, D;      /* images, stereo channels (multiple of 4, <= 512), map size, depth hypotheses (<= 128) */
+  int32_t feat_bf16;           /* element type of prev / curr: 0 fp32, 1 bf16 */
+  const void* prev;            /* (BN, H, W, C) previous frame, already aligned to the same camera order */
+  const void* curr;            /* (BN, H, W, C) current frame */
+  const float* frustum;        /* (D, H, W, 3) = (u, v, d) template (MGHS_Stereo.cv_frustum); unused when grid != NULL */
+  const float* cam;            /* (BN, DHD_STEREO_CAM_FLOATS); unused when grid != NULL */
+  const float* grid;           /* optional (BN, D*H, W, 2): normalised sampling coordinates computed elsewhere */
+  float img_w, img_h;          /* wi, hi of gen_grid: 4 * W, 4 * H */
+  float bias;                  /* DepthNet.bias (DHD-L: 5.0); 0 disables the test */
+  float* out_f32;              /* optional fp32 result, element (bn, d, y, x) at bn*sN + d*sD + y*sY + x*sX */
+  int64_t f32_sN, f32_sD, f32_sY, f32_sX;
+  void* out_b16;               /* optional split-bf16 NHWC activation (input of cost_volumn_net) */
+  int32_t b16_ld, b16_coff, b16_parts, b16_part_stride;
+  int32_t b16_cpad;            /* channels written per part: D rounded up by the caller, the tail is zeroed */
+  float* grid_out;             /* optional (BN, D*H, W, 2): the coordinates the kernel sampled at (parity hook) */
+} dhd_stereo_desc;
+int dhd_stereo_cost_volume(const dhd_stereo_desc* d, void* stream);
+/* fp32 (N, C, HW) -> (N, HW, C) as fp32 (out_bf16 = 0) or bf16 (1) */
+int dhd_nchw_to_nhwc(const float* in, int N, int C, int HW, void* out, int out_bf16, void* stream);
 
 /* ---- streaming layout / elementwise helpers of the dense path (csrc/layout.cu) -----------
  * "split-bf16 NHWC": bf16, `ld` channels per pixel, logical channel c of part p at

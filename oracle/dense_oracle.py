@@ -5,6 +5,8 @@ reference classes (in the build container), this oracle (anywhere) and the CUDA 
   heightnet_forward   models/model_utils/depthnet.py:605-652 (trunk 418-487, ASPP 88-108,
                       Mlp 136-147, SELayer 158-169)
   depth_head_forward  models/necks/lss_heightmap.py:482-485
+  depthnet_forward    models/model_utils/depthnet.py:362-415 (ctor 172-243), stereo_sampling_grid 245-308,
+                      stereo_cost_volume 310-361
   sfa_forward         models/necks/mix.py:37-59, 87-90
   predictor_forward   models/dense_heads/occ_head.py:84-100
 
@@ -140,6 +142,98 @@ def heightnet_forward(sd, x, mlp_input, prefix=''):
         x = _dcn(sd, p + 'depth_conv.%d' % i, x)
         i += 1
     return F.conv2d(x, sd[p + 'depth_conv.%d.weight' % i], sd[p + 'depth_conv.%d.bias' % i])
+
+
+# ------------------------------------------------------------------ camera-aware DepthNet + plane-sweep cost volume
+def stereo_sampling_grid(frustum, k2s_sensor, intrins, post_rots, post_trans, hi, wi):
+    """models/model_utils/depthnet.py:245-308 (gen_grid): every point of the 1/4-resolution frustum template
+    (u, v, d) of the CURRENT image -> un-augment -> current camera -> previous camera (k2s_sensor) -> previous
+    pixel -> re-augment -> normalised [-1, 1] sampling coordinate; points behind the previous camera (z < 1e-3)
+    are sent to -2 (outside).  Returns (B*N, D*H, W, 2) fp32, the layout F.grid_sample takes."""
+    B, N = post_trans.shape[:2]
+    D, H, W, _ = frustum.shape
+    bc = lambda t, *tail: t.reshape(B, N, 1, 1, 1, *tail)
+    p = (frustum - bc(post_trans, 3)).unsqueeze(-1)
+    p = bc(torch.inverse(post_rots), 3, 3).matmul(p)
+    p = torch.cat([p[..., :2, :] * p[..., 2:3, :], p[..., 2:3, :]], dim=5)
+    to_prev = k2s_sensor[:, :, :3, :3].contiguous().matmul(torch.inverse(intrins))
+    p = bc(to_prev, 3, 3).matmul(p) + bc(k2s_sensor[:, :, :3, 3].contiguous(), 3, 1)
+    behind = p[..., 2, 0] < 1e-3
+    p = bc(intrins, 3, 3).matmul(p)
+    uv = (p[..., :2, :] / p[..., 2:3, :])
+    uv = bc(post_rots[..., :2, :2], 2, 2).matmul(uv).squeeze(-1) + bc(post_trans[..., :2], 2)
+    gx = uv[..., 0] / (wi - 1.0) * 2.0 - 1.0
+    gy = uv[..., 1] / (hi - 1.0) * 2.0 - 1.0
+    gx[behind] = -2
+    gy[behind] = -2
+    return torch.stack([gx, gy], dim=-1).view(B * N, D * H, W, 2)
+
+
+def stereo_cost_volume(prev, curr, grid, D, bias=0.0, group_size=4):
+    """depthnet.py:310-361: warp the previous frame's stereo feature to every depth hypothesis of the current
+    pixel (bilinear, zeros outside, align_corners=True), L1 distance to the current feature summed over the
+    channels (the reference accumulates it 4 channels at a time), `bias` added where the warped channel
+    C - group_size is exactly 0 (its test for "sample fell outside"), softmax over depth of the negated cost."""
+    BN, C, H, W = curr.shape
+    cost = torch.zeros(BN, D, H, W, dtype=curr.dtype, device=curr.device)
+    last = None
+    for c0 in range(0, C, group_size):
+        last = F.grid_sample(prev[:, c0:c0 + group_size], grid, align_corners=True, padding_mode='zeros')
+        last = last.view(BN, -1, D, H, W)
+        cost += (curr[:, c0:c0 + group_size, None] - last).abs().sum(dim=1)
+    if bias != 0:
+        cost = torch.where(last[:, 0] == 0, cost + bias, cost)
+    return (-cost).softmax(dim=1)
+
+
+def _camera_gate(sd, p, m, mlp, se, x):
+    """Mlp (depthnet.py:136-147, fc1-ReLU-fc2; Dropout(0) twice) -> SELayer (158-169) gate on x."""
+    g = F.linear(F.relu(F.linear(m, sd[p + mlp + '.fc1.weight'], sd[p + mlp + '.fc1.bias'])),
+                 sd[p + mlp + '.fc2.weight'], sd[p + mlp + '.fc2.bias'])[..., None, None]
+    g = F.relu(F.conv2d(g, sd[p + se + '.conv_reduce.weight'], sd[p + se + '.conv_reduce.bias']))
+    g = F.conv2d(g, sd[p + se + '.conv_expand.weight'], sd[p + se + '.conv_expand.bias'])
+    return x * torch.sigmoid(g)
+
+
+def depthnet_forward(sd, x, mlp_input, cost_volume=None, prefix=''):
+    """Eval-mode DepthNet of MGHS_Depth / MGHS_Stereo (depthnet.py:362-415).  cost_volume: None (stereo=False) or
+    the (B*N, D, 4fH, 4fW) matching probabilities (zeros when there is no previous frame, 389-396); it goes through
+    cost_volumn_net (two stride-2 conv3x3 + BN, 207-213), is concatenated to the gated depth feature, and the first
+    BasicBlock then carries the plain 1x1 `downsample` convolution on its identity path (205-206, 217-218).
+    Returns (B*N, D + C_context, fH, fW): raw depth logits then the context feature."""
+    p = prefix
+    m = F.batch_norm(mlp_input.reshape(-1, mlp_input.shape[-1]), sd[p + 'bn.running_mean'],
+                     sd[p + 'bn.running_var'], sd[p + 'bn.weight'], sd[p + 'bn.bias'], False, 0.0, 1e-5)
+    x = F.conv2d(x, sd[p + 'reduce_conv.0.weight'], sd[p + 'reduce_conv.0.bias'], padding=1)
+    x = F.relu(_bn(sd, p + 'reduce_conv.1', x))
+    context = _camera_gate(sd, p, m, 'context_mlp', 'context_se', x)
+    context = F.conv2d(context, sd[p + 'context_conv.weight'], sd[p + 'context_conv.bias'])
+    y = _camera_gate(sd, p, m, 'depth_mlp', 'depth_se', x)
+    if cost_volume is not None:
+        cv = cost_volume
+        for k in (0, 2):
+            q = p + 'cost_volumn_net.%d' % k
+            cv = _bn(sd, p + 'cost_volumn_net.%d' % (k + 1),
+                     F.conv2d(cv, sd[q + '.weight'], sd[q + '.bias'], stride=2, padding=1))
+        y = torch.cat([y, cv], dim=1)
+    i = 0
+    while (p + 'depth_conv.%d.bn2.weight' % i) in sd:
+        q = p + 'depth_conv.%d' % i
+        if (q + '.downsample.weight') in sd:
+            out = F.relu(_bn(sd, q + '.bn1', F.conv2d(y, sd[q + '.conv1.weight'], padding=1)))
+            out = _bn(sd, q + '.bn2', F.conv2d(out, sd[q + '.conv2.weight'], padding=1))
+            y = F.relu(out + F.conv2d(y, sd[q + '.downsample.weight'], sd[q + '.downsample.bias']))
+        else:
+            y = _basic_block(sd, q, y)
+        i += 1
+    if (p + 'depth_conv.%d.aspp1.atrous_conv.weight' % i) in sd:
+        y = _aspp(sd, p + 'depth_conv.%d' % i, y)
+        i += 1
+    if (p + 'depth_conv.%d.conv_offset.weight' % i) in sd:
+        y = _dcn(sd, p + 'depth_conv.%d' % i, y)
+        i += 1
+    y = F.conv2d(y, sd[p + 'depth_conv.%d.weight' % i], sd[p + 'depth_conv.%d.bias' % i])
+    return torch.cat([y, context], dim=1)
 
 
 def depth_head_forward(sd, x, n_depth, prefix='depth_net.'):

@@ -92,8 +92,8 @@ def _cost_volumn_net(depth_channels):
 
 class DepthNet(nn.Module):
     """Depth + context head of MGHS_Depth / MGHS_Stereo (reference depthnet.py:172-415).
-    stereo=True builds the reference's extra parameters (cost_volumn_net, first-block downsample)
-    so checkpoints load, but the plane-sweep cost volume itself is SURVEY 8(f) rank 3: forward raises."""
+    stereo=True adds cost_volumn_net and the first block's 1x1 downsample; the plane-sweep cost volume
+    (gen_grid + calculate_cost_volumn, 245-361) is one fused CUDA kernel, see calculate_cost_volumn."""
 
     def __init__(self, in_channels, mid_channels, context_channels, depth_channels, use_dcn=True,
                  use_aspp=True, with_cp=False, stereo=False, bias=0.0, aspp_mid_channels=-1, precision='fp32'):
@@ -109,7 +109,7 @@ class DepthNet(nn.Module):
         self.context_se = SELayer(mid_channels)
         if stereo:
             self.cost_volumn_net = _cost_volumn_net(depth_channels)
-            self.bias = bias
+        self.bias = bias
         self.depth_conv = _trunk_layers(mid_channels, depth_channels, use_dcn, use_aspp, aspp_mid_channels, stereo)
         self.with_cp, self.depth_channels, self.stereo = with_cp, depth_channels, stereo
         self.precision = precision
@@ -119,15 +119,37 @@ class DepthNet(nn.Module):
         self._engine = None
         return super()._load_from_state_dict(*a, **k)
 
-    def forward_split(self, x, mlp_input, softmax=True):
+    def calculate_cost_volumn(self, metas, out_act=None):
+        """Reference depthnet.py:310-361 (+ gen_grid 245-308) as ONE fused kernel (dhd_b200/csrc/stereo.cu):
+        (B*N, D, fH_stereo, fW_stereo) matching probabilities from stereo_metas (same dict as the reference).
+        out_act: optional split-bf16 activation to fill instead (the form cost_volumn_net reads)."""
+        from dhd_b200 import stereo as S
+        prev, curr = metas['cv_feat_list']
+        if not curr.is_cuda:
+            raise RuntimeError('dhd_b200: expected CUDA tensors (the hot path has no CPU fallback)')
+        frustum = metas['frustum']
+        D, H, W, _ = frustum.shape
+        lowp = self.precision == 'bf16'
+        with torch.no_grad():
+            cam = S.camera_table(metas['k2s_sensor'], metas['intrins'], metas['post_rots'], metas['post_trans'])
+            p = S.to_nhwc(prev.reshape(-1, prev.shape[-3], H, W).float(), bf16=lowp)
+            c = S.to_nhwc(curr.reshape(-1, curr.shape[-3], H, W).float(), bf16=lowp)
+            # gen_grid's hi, wi = 4 * (stereo map size), depthnet.py:339-340
+            out, _ = S.cost_volume(p, c, D, (H * 4, W * 4), bias=self.bias, frustum=frustum.to(curr.device), cam=cam,
+                                   out_act=out_act)
+        return out
+
+    def forward_split(self, x, mlp_input, softmax=True, stereo_metas=None):
         """-> (depth (B*N, D, fH, fW) NCHW [softmax-ed], context (B*N, fH, fW, C) NHWC): the layouts the
         fused pool consumes, written directly by the layer epilogues."""
         from dhd_b200 import dense as D
         from dhd_b200.modules import DepthNetEngine
         if self.training:
             raise NotImplementedError('dhd_b200 DepthNet: inference (eval-mode BatchNorm) only in this build')
-        if self.stereo:
-            raise NotImplementedError('DepthNet(stereo=True): the cost-volume branch is SURVEY 8(f) rank 3')
+        if self.stereo != (stereo_metas is not None):
+            # the reference fails the same way: the first BasicBlock's input width depends on the cost volume
+            raise RuntimeError('DepthNet(stereo=%s) called %s stereo_metas' %
+                               (self.stereo, 'with' if stereo_metas is not None else 'without'))
         if not isinstance(x, D.Act):
             if not x.is_cuda:
                 raise RuntimeError('dhd_b200: expected CUDA tensors (the hot path has no CPU fallback)')
@@ -135,13 +157,20 @@ class DepthNet(nn.Module):
         with torch.no_grad():
             if self._engine is None:
                 self._engine = DepthNetEngine(self, self.precision, x.data.device)
-            return self._engine(x, mlp_input, softmax=softmax)
+            cv = None
+            if self.stereo:
+                # depthnet.py:387-400: zeros when there is no previous frame, else the plane-sweep volume
+                scale = float(stereo_metas['downsample']) / stereo_metas['cv_downsample']
+                Hs, Ws = int(x.H * scale), int(x.W * scale)
+                first = stereo_metas['cv_feat_list'][0] is None
+                cv = self._engine.new_cost_volume(x.N, Hs, Ws, x.data.device, zero=first)
+                if not first:
+                    self.calculate_cost_volumn(stereo_metas, out_act=cv)
+            return self._engine(x, mlp_input, softmax=softmax, cost_volume=cv)
 
     def forward(self, x, mlp_input, stereo_metas=None):
         """Reference signature: (B*N, D + C_context, fH, fW) logits, depthnet.py:362-415."""
-        if stereo_metas is not None:
-            raise NotImplementedError('stereo_metas: SURVEY 8(f) rank 3')
-        depth, ctx = self.forward_split(x, mlp_input, softmax=False)
+        depth, ctx = self.forward_split(x, mlp_input, softmax=False, stereo_metas=stereo_metas)
         return torch.cat([depth, ctx.permute(0, 3, 1, 2)], dim=1)
 
 
@@ -160,7 +189,7 @@ class HeightNet(nn.Module):
         self.depth_se = SELayer(mid_channels)
         if stereo:
             self.cost_volumn_net = _cost_volumn_net(depth_channels)
-            self.bias = bias
+        self.bias = bias
         self.depth_conv = _trunk_layers(mid_channels, depth_channels, use_dcn, use_aspp, aspp_mid_channels, stereo)
         self.with_cp = with_cp
         self.depth_channels = depth_channels

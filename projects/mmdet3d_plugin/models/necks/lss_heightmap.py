@@ -304,13 +304,11 @@ class MGHS_Depth(MGHS):
         B, N, C, H, W = x.shape
         if self.training:
             raise NotImplementedError('dhd_b200 MGHS_Depth: the dense layers are inference-only in this build')
-        if stereo_metas is not None:
-            raise NotImplementedError('stereo_metas (plane-sweep cost volume): SURVEY 8(f) rank 3')
         if not x.is_cuda:
             raise RuntimeError('dhd_b200: expected CUDA tensors (the hot path has no CPU fallback)')
         with torch.no_grad():
             xa = D.pack_input(x.reshape(B * N, C, H, W), D.PRECISIONS[self.precision][0])
-            depth, feat = self.depth_net.forward_split(xa, mlp_input, softmax=True)
+            depth, feat = self.depth_net.forward_split(xa, mlp_input, softmax=True, stereo_metas=stereo_metas)
             height = self.height_net(xa, mlp_input, None, softmax=True)
             return self.view_transform(input, depth, None, height, feat_nhwc=feat)
 

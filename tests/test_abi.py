@@ -83,7 +83,8 @@ def test_ctypes_struct_layouts_match_the_library(lib):
     import ctypes
     from dhd_b200 import dense as D
     from dhd_b200._lib import MghsCfg
-    for which, cls in enumerate((MghsCfg, D.ConvSeg, D.ConvDesc, D.WgradDesc)):
+    from dhd_b200.stereo import StereoDesc
+    for which, cls in enumerate((MghsCfg, D.ConvSeg, D.ConvDesc, D.WgradDesc, StereoDesc)):
         assert lib.dhd_abi_sizeof(which) == ctypes.sizeof(cls), cls.__name__
     # the same fields at the same offsets for the two structs that grew this round
     assert D.ConvDesc.stride.offset == D.ConvDesc.seg.offset + D.MAX_SEGS * ctypes.sizeof(D.ConvSeg)

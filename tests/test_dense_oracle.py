@@ -178,3 +178,44 @@ def test_encoder_oracle_and_plugin_names_match_real_reference():
         fo = DO.custom_resnet_forward(sds['resnet'], xb)
         assert all(torch.equal(a, b) for a, b in zip(fr, fo))
         assert torch.equal(refs['fpn'](fr), DO.fpn_lss_forward(sds['fpn'], fo))
+
+
+def test_depthnet_oracle_matches_reference_fixture():
+    """oracle.dense_oracle.depthnet_forward / stereo_sampling_grid / stereo_cost_volume against the fixture made by
+    the UNMODIFIED reference DepthNet (oracle/make_golden_depthnet.py): DHD-M form, DHD-L stereo form, first frame."""
+    from oracle import make_golden_depthnet as MGD
+    gold = np.load(os.path.join(os.path.dirname(GOLD), 'depthnet.npz'))
+    x, mlp, prev, curr = MGD.inputs()
+    assert hashlib.sha256(b''.join(t.numpy().tobytes() for t in (x, mlp, prev, curr))).hexdigest() == str(gold['input_sha'])
+    import projects.mmdet3d_plugin  # noqa: F401
+    from projects.mmdet3d_plugin.models.model_utils.depthnet import DepthNet
+    D = MGD.n_depth()
+    mono = DepthNet(MGD.C_IN, MGD.C_MID_MONO, MGD.C_CTX, D, use_dcn=True, use_aspp=True)
+    st = DepthNet(MGD.C_IN, MGD.C_IN, MGD.C_CTX, D, use_dcn=False, aspp_mid_channels=32, stereo=True, bias=MGD.BIAS)
+    sdm, sds = DO.seeded_state_dict(mono, 41), DO.seeded_state_dict(st, 42)     # plugin parameter names == reference's
+    assert MG.sha_sd(sdm) == str(gold['sha_mono']) and MG.sha_sd(sds) == str(gold['sha_stereo'])
+    m = MGD.stereo_metas(prev, curr)
+    H, W = MGD.INPUT
+    with torch.no_grad():
+        grid = DO.stereo_sampling_grid(m['frustum'], m['k2s_sensor'], m['intrins'], m['post_rots'], m['post_trans'], H, W)
+        assert np.abs(grid.numpy() - gold['grid']).max() <= 1e-6
+        cv = DO.stereo_cost_volume(prev, curr, grid, D, MGD.BIAS)
+        assert np.abs(cv.numpy() - gold['cost_volume']).max() <= 1e-6
+        for got, key in ((DO.depthnet_forward(sdm, x, mlp), 'mono'), (DO.depthnet_forward(sds, x, mlp, cv), 'stereo'),
+                         (DO.depthnet_forward(sds, x, mlp, torch.zeros_like(cv)), 'stereo_first')):
+            ref = torch.from_numpy(gold[key])
+            assert torch.allclose(got, ref, rtol=1e-5, atol=2e-5), '%s: max abs diff %.3g' % (key, (got - ref).abs().max())
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason='reference tree not present')
+def test_depthnet_fixture_is_what_the_reference_produces_now():
+    """Re-run the unmodified reference DepthNet (stereo) in this container and compare with the committed fixture."""
+    from oracle import make_golden_depthnet as MGD
+    gold = np.load(os.path.join(os.path.dirname(GOLD), 'depthnet.npz'))
+    ns = ref_loader.load_reference()
+    st = MGD.build(ns, True)
+    st.load_state_dict(DO.seeded_state_dict(st, 42))
+    x, mlp, prev, curr = MGD.inputs()
+    with torch.no_grad():
+        y = st(x, mlp, MGD.stereo_metas(prev, curr))
+    assert torch.allclose(y, torch.from_numpy(gold['stereo']), rtol=1e-5, atol=2e-5)
