@@ -23,14 +23,27 @@ struct StereoParams {
   int tiles_x, tiles_y;
 };
 
-__device__ __forceinline__ float4 load4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
-__device__ __forceinline__ float4 load4(const __nv_bfloat16* p) {
-  const uint2 r = __ldg(reinterpret_cast<const uint2*>(p));
-  const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&r.x);
-  const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&r.y);
-  const float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
-  return make_float4(fa.x, fa.y, fb.x, fb.y);
-}
+// one 16-byte load per lane: 4 fp32 or 8 bf16 channels
+template <typename T> struct Vec;
+template <> struct Vec<float> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ void load(const float* p, float* v) {
+    const float4 r = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = r.w;
+  }
+};
+template <> struct Vec<__nv_bfloat16> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float* v) {
+    const uint4 r = __ldg(reinterpret_cast<const uint4*>(p));
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {                       // bf16 -> fp32 is a 16-bit shift
+      v[2 * i] = __uint_as_float(w[i] << 16);
+      v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+};
 
 // 3x3 (row-major) times vector, products and adds rounded separately, left to right: the order torch's batched
 // matmul gives the reference (same helper as the voxel pool's geometry, pinned there bit for bit)
@@ -65,11 +78,12 @@ __device__ __forceinline__ void sampling_coordinate(const float* __restrict__ ca
 
 // Work split inside a warp: the 32 lanes first compute the sampling parameters of 32 depth hypotheses (one each),
 // then walk them FOUR at a time -- lane group g = lane / 8 takes hypothesis 4j + g, and its 8 lanes own the channels
-// (float4 q = l + 8k of the pixel's C / 4, so one load instruction of a group covers 128 contiguous bytes of a tap).
+// (16-byte slot q = l + 8k of the pixel's row, so one load instruction of a group covers 128 contiguous bytes of a tap).
 // The L1 distance then needs a 3-step butterfly per four hypotheses instead of a 5-step one per hypothesis, and the
 // parameters travel by one indexed shuffle each.
 template <typename T, int NK>
-__global__ void __launch_bounds__(256) stereo_cost_volume_kernel(const StereoParams P) {
+__global__ void __launch_bounds__(256, 3) stereo_cost_volume_kernel(const StereoParams P) {
+  constexpr int V = Vec<T>::N;
   const dhd_stereo_desc& c = P.d;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int grp = lane >> 3, gl = lane & 7;
@@ -84,14 +98,19 @@ __global__ void __launch_bounds__(256) stereo_cost_volume_kernel(const StereoPar
   const T* prev = reinterpret_cast<const T*>(c.prev) + (size_t)bn * H * W * C;
   const T* cur_px = reinterpret_cast<const T*>(c.curr) + ((size_t)(bn * H + y) * W + x) * C;
 
-  float4 cur[NK];
+  float cur[NK][V];
 #pragma unroll
   for (int k = 0; k < NK; ++k) {
-    const int ch = (gl + 8 * k) * 4;
-    cur[k] = ch < C ? load4(cur_px + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const int ch = (gl + 8 * k) * V;
+    if (ch < C) {
+      Vec<T>::load(cur_px + ch, cur[k]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < V; ++i) cur[k][i] = 0.f;
+    }
   }
   // the reference's "sample fell outside" test looks at the first channel of the LAST group of four channels
-  const int flag_k = ((C - 4) / 4) / 8, flag_gl = ((C - 4) / 4) % 8;
+  const int flag_k = ((C - 4) / V) / 8, flag_gl = ((C - 4) / V) % 8, flag_i = (C - 4) % V;
   const float* cam = c.cam != nullptr ? c.cam + (size_t)bn * DHD_STEREO_CAM_FLOATS : nullptr;
   const float wm1 = c.img_w - 1.f, hm1 = c.img_h - 1.f;
   const float sx = (float)(W - 1), sy = (float)(H - 1);
@@ -151,16 +170,19 @@ __global__ void __launch_bounds__(256) stereo_cost_volume_kernel(const StereoPar
       bool zero_flag = false;
 #pragma unroll
       for (int k = 0; k < NK; ++k) {
-        const int ch = (gl + 8 * k) * 4;
+        const int ch = (gl + 8 * k) * V;
         if (ch < C) {
-          const float4 a = load4(p_nw + ch), bq = load4(p_ne + ch), cq = load4(p_sw + ch), dq = load4(p_se + ch);
-          float4 v;
-          v.x = a.x * a_nw + bq.x * a_ne + cq.x * a_sw + dq.x * a_se;
-          v.y = a.y * a_nw + bq.y * a_ne + cq.y * a_sw + dq.y * a_se;
-          v.z = a.z * a_nw + bq.z * a_ne + cq.z * a_sw + dq.z * a_se;
-          v.w = a.w * a_nw + bq.w * a_ne + cq.w * a_sw + dq.w * a_se;
-          acc += (fabsf(cur[k].x - v.x) + fabsf(cur[k].y - v.y)) + (fabsf(cur[k].z - v.z) + fabsf(cur[k].w - v.w));
-          if (k == flag_k) zero_flag = (v.x == 0.f);
+          float a[V], bq[V], cq[V], dq[V];
+          Vec<T>::load(p_nw + ch, a);
+          Vec<T>::load(p_ne + ch, bq);
+          Vec<T>::load(p_sw + ch, cq);
+          Vec<T>::load(p_se + ch, dq);
+#pragma unroll
+          for (int i = 0; i < V; ++i) {
+            const float v = a[i] * a_nw + bq[i] * a_ne + cq[i] * a_sw + dq[i] * a_se;
+            acc += fabsf(cur[k][i] - v);
+            if (k == flag_k && i == flag_i) zero_flag = (v == 0.f);
+          }
         }
       }
       acc += __shfl_xor_sync(kFull, acc, 1);
@@ -265,6 +287,7 @@ extern "C" int dhd_stereo_cost_volume(const dhd_stereo_desc* d, void* stream) {
   DHD_REQUIRE(d->prev && d->curr, "null feature pointer");
   DHD_REQUIRE(d->BN > 0 && d->H > 0 && d->W > 0 && d->H < 32768 && d->W < 32768, "bad map shape");
   DHD_REQUIRE(d->C >= 4 && d->C % 4 == 0 && d->C <= 512, "C must be a multiple of 4, at most 512");
+  DHD_REQUIRE(!d->feat_bf16 || d->C % 8 == 0, "bf16 features: C must be a multiple of 8");
   DHD_REQUIRE(d->D >= 1 && d->D <= 32 * kMaxBatches, "D must be in 1..128");
   DHD_REQUIRE(d->grid != nullptr || (d->frustum != nullptr && d->cam != nullptr),
               "either the sampling grid or frustum + camera matrices must be given");
@@ -282,7 +305,7 @@ extern "C" int dhd_stereo_cost_volume(const dhd_stereo_desc* d, void* stream) {
   P.tiles_y = (d->H + kTileY - 1) / kTileY;
   const long blocks = (long)P.tiles_x * P.tiles_y * d->BN;
   DHD_REQUIRE(blocks < (1L << 31), "map too large");
-  const int nk = (d->C + 31) / 32;      // float4 slots per lane of an 8-lane group
+  const int nk = d->feat_bf16 ? (d->C + 63) / 64 : (d->C + 31) / 32;      // 16-byte slots per lane of an 8-lane group
   if (d->feat_bf16)
     launch_cost_volume<__nv_bfloat16>(P, nk, (int)blocks, (cudaStream_t)stream);
   else
