@@ -49,3 +49,31 @@ def synthetic_rig(B, ncams=6, input_size=(256, 704), src_size=(900, 1600), seed=
         bda[1::2, 1, 1] = -1.0
     e2g = torch.eye(4).expand(B, ncams, 4, 4).clone()
     return s2e, e2g, K, pr, pt, bda
+
+
+# ---------------------------------------------------------------------------------------------- DHD-L (cfg-5)
+DHD_L_VIEW_TRANSFORMER = dict(      # kwargs of model.img_view_transformer in projects/configs/DHD/DHD-L.py:75-119
+    grid_config={'x': [-40, 40, 0.4], 'y': [-40, 40, 0.4], 'z': [-1, 5.4, 6.4], 'depth': [1.0, 45.0, 0.5]},
+    input_size=(512, 1408),
+    height_range=[round(-1.0 + 0.1 * i, 1) for i in range(65)], height_interval=0.1,
+    mask_range=[-1.0, 0.6, 2.2, 5.4],
+    mask_1_grid={'x': [-40, 40, 0.4], 'y': [-40, 40, 0.4], 'z': [-1, 0.6, 0.4], 'depth': [1.0, 45.0, 0.5]},
+    mask_2_grid={'x': [-40, 40, 0.4], 'y': [-40, 40, 0.4], 'z': [0.6, 2.2, 0.4], 'depth': [1.0, 45.0, 0.5]},
+    mask_3_grid={'x': [-40, 40, 0.4], 'y': [-40, 40, 0.4], 'z': [2.2, 5.4, 0.4], 'depth': [1.0, 45.0, 0.5]},
+    in_channels=512, out_channels=64, sid=False, collapse_z=False, loss_height_weight=0.1, loss_depth_weight=0.05,
+    depthnet_cfg=dict(use_dcn=False, aspp_mid_channels=96, stereo=True, bias=5.),
+    heightnet_cfg=dict(use_dcn=False, aspp_mid_channels=96),
+    downsample=16)
+DHD_L_STEREO_CHANNELS = 128         # Swin-B stage-0 width (DHD-L.py:44-63, return_stereo_feat=True)
+
+
+def synthetic_k2s_sensor(sensor2ego, forward_m=0.8, yaw_deg=1.5):
+    """Current-camera -> previous-frame-camera transforms (B, N, 4, 4) of a vehicle that drove `forward_m` metres
+    while yawing `yaw_deg`: inv(sensor2ego) @ key_ego->previous_ego @ sensor2ego (the k2s_sensor the reference derives
+    from the nuScenes poses, detectors/bevstereo4d.py)."""
+    a = math.radians(yaw_deg)
+    ego = torch.eye(4)
+    ego[:3, :3] = torch.tensor([[math.cos(a), -math.sin(a), 0.0], [math.sin(a), math.cos(a), 0.0], [0.0, 0.0, 1.0]])
+    ego[:3, 3] = torch.tensor([forward_m, 0.03, 0.0])
+    ego = ego.to(sensor2ego)
+    return torch.linalg.inv(sensor2ego) @ ego @ sensor2ego

@@ -219,3 +219,19 @@ def test_depthnet_fixture_is_what_the_reference_produces_now():
     with torch.no_grad():
         y = st(x, mlp, MGD.stereo_metas(prev, curr))
     assert torch.allclose(y, torch.from_numpy(gold['stereo']), rtol=1e-5, atol=2e-5)
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason='reference tree not present')
+def test_dhdl_view_transformer_kwargs_are_the_reference_config():
+    """dhd_b200.synth.DHD_L_VIEW_TRANSFORMER (used on the GPU box, where the reference tree is absent) is exactly
+    model.img_view_transformer of the unchanged projects/configs/DHD/DHD-L.py."""
+    from dhd_b200 import compat as C
+    from dhd_b200 import synth
+    cfg = C.Config.fromfile(os.path.join(ref_loader.load_reference_configs(), 'DHD-L.py'))
+    ref = cfg.model.img_view_transformer
+    ref = dict(ref.to_dict() if hasattr(ref, 'to_dict') else ref)
+    assert ref.pop('type') == 'MGHS_Stereo'
+    norm = lambda v: {k: norm(x) for k, x in v.items()} if isinstance(v, dict) else \
+        ([norm(x) for x in v] if isinstance(v, (list, tuple)) else v)
+    assert norm(ref) == norm(synth.DHD_L_VIEW_TRANSFORMER)
+    assert cfg.model.img_backbone.embed_dims == synth.DHD_L_STEREO_CHANNELS

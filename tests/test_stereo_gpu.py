@@ -188,3 +188,33 @@ def test_full_size_properties_and_gpu_oracle(cuda_lib):
     close(cv, want, 'cost volume at DHD-L size vs torch on the GPU', 1e-6, 2e-4)
     frac_inside = float(((grid.abs() <= 1).all(-1)).float().mean())
     assert 0.5 < frac_inside < 1.0
+
+
+def test_mghs_stereo_dhdl_full_size(cuda_lib):
+    """BASELINE configs[4]: the plugin's MGHS_Stereo with the DHD-L.py kwargs at full size (B=1: 6 cameras, 512x1408,
+    C_in=512, D=88, stereo features 128 ch @128x352).  Depth / context of the stereo DepthNet against the torch
+    restatement of the reference run on the GPU in fp32 (TF32 off) with the same seeded weights; output shapes of the
+    collapse_z=False pool (its values are pinned at this size by tests/test_pool_gpu.py)."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'scripts'))
+    import bench_dhdl
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    vt, args, metas = bench_dhdl.build('fp32', 1)
+    sd = {k: v.cuda() for k, v in DO.seeded_state_dict(vt, 77).items()}
+    vt.load_state_dict(sd)
+    with torch.no_grad():
+        bev, bev_z, depth, height = vt(args, metas)
+        x = args[0].flatten(0, 1)
+        prev, curr = metas['cv_feat_list']
+        grid = DO.stereo_sampling_grid(metas['frustum'], metas['k2s_sensor'], metas['intrins'], metas['post_rots'],
+                                       metas['post_trans'], 512, 1408)
+        cv = DO.stereo_cost_volume(prev, curr, grid, vt.D, 5.0)
+        dsd = {k[len('depth_net.'):]: v for k, v in sd.items() if k.startswith('depth_net.')}
+        y = DO.depthnet_forward(dsd, x, args[7], cv)
+        want_depth = y[:, :vt.D].softmax(1)
+        h = DO.heightnet_forward(sd, x, args[7], prefix='height_net.').softmax(1)
+    assert bev.shape == (1, 64, 1, 200, 200) and bev_z.shape == (1, 64, 16, 200, 200)
+    assert torch.isfinite(bev).all() and torch.isfinite(bev_z).all() and float(bev.abs().sum()) > 0
+    close(depth, want_depth, 'DHD-L stereo depth distribution', 1e-4, 1e-3)
+    close(height, h, 'DHD-L height distribution', 1e-4, 1e-3)
