@@ -8,6 +8,7 @@
 // distance is reduced inside 8-lane groups, and the softmax over depth happens in registers.  Nothing but the
 // probabilities is written.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -21,6 +22,7 @@ constexpr int kMaxBatches = 4;                 // 32 depth hypotheses per batch 
 struct StereoParams {
   dhd_stereo_desc d;
   int tiles_x, tiles_y;
+  int pf_rows;          // L2 prefetch distance in map rows (0 = off; DHD_STEREO_PF overrides the default)
 };
 
 // one 16-byte load per lane: 4 fp32 or 8 bf16 channels
@@ -81,7 +83,7 @@ __device__ __forceinline__ void sampling_coordinate(const float* __restrict__ ca
 // (16-byte slot q = l + 8k of the pixel's row, so one load instruction of a group covers 128 contiguous bytes of a tap).
 // The L1 distance then needs a 3-step butterfly per four hypotheses instead of a 5-step one per hypothesis, and the
 // parameters travel by one indexed shuffle each.
-template <typename T, int NK>
+template <typename T, int NK, bool FULL>
 __global__ void __launch_bounds__(256, 3) stereo_cost_volume_kernel(const StereoParams P) {
   constexpr int V = Vec<T>::N;
   const dhd_stereo_desc& c = P.d;
@@ -95,6 +97,23 @@ __global__ void __launch_bounds__(256, 3) stereo_cost_volume_kernel(const Stereo
   const int x = tx * kTileX + (warp % kTileX), y = ty * kTileY + (warp / kTileX);
   if (x >= c.W || y >= c.H) return;                          // whole warp leaves together
   const int H = c.H, W = c.W, C = c.C, D = c.D;
+  // Every feature row is first touched from DRAM exactly once, and a warp that waits ~1 us for it has nothing else to
+  // do: tiles therefore ask the L2 for the rows the grid will reach `pf_rows` rows from now (one bulk prefetch per
+  // tile row and tensor; the tile at the top of the launch also covers the first pf_rows rows).
+  if (P.pf_rows > 0) {
+    const int seg_x = tx * kTileX;
+    const unsigned bytes = (unsigned)(min(kTileX, W - seg_x) * C * (int)sizeof(T));
+    const long rows_total = (long)c.BN * H;
+    const long g0 = (long)bn * H + ty * kTileY;
+    const int n_rows = (bn == 0 && ty == 0) ? P.pf_rows + kTileY : kTileY;
+    for (int i = threadIdx.x; i < 2 * n_rows; i += blockDim.x) {
+      const long g = (n_rows == kTileY ? g0 + P.pf_rows : 0) + (i >> 1);
+      if (g < rows_total) {
+        const T* base = reinterpret_cast<const T*>((i & 1) ? c.curr : c.prev) + ((size_t)g * W + seg_x) * C;
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base), "r"(bytes) : "memory");
+      }
+    }
+  }
   const T* prev = reinterpret_cast<const T*>(c.prev) + (size_t)bn * H * W * C;
   const T* cur_px = reinterpret_cast<const T*>(c.curr) + ((size_t)(bn * H + y) * W + x) * C;
 
@@ -112,6 +131,7 @@ __global__ void __launch_bounds__(256, 3) stereo_cost_volume_kernel(const Stereo
   // the reference's "sample fell outside" test looks at the first channel of the LAST group of four channels
   const int flag_k = ((C - 4) / V) / 8, flag_gl = ((C - 4) / V) % 8, flag_i = (C - 4) % V;
   const float* cam = c.cam != nullptr ? c.cam + (size_t)bn * DHD_STEREO_CAM_FLOATS : nullptr;
+  const float fu = c.grid == nullptr ? __ldg(c.frustum_u + x) : 0.f, fv = c.grid == nullptr ? __ldg(c.frustum_v + y) : 0.f;
   const float wm1 = c.img_w - 1.f, hm1 = c.img_h - 1.f;
   const float sx = (float)(W - 1), sy = (float)(H - 1);
 
@@ -124,7 +144,7 @@ __global__ void __launch_bounds__(256, 3) stereo_cost_volume_kernel(const Stereo
     const int dl = d0 + lane;
     // ---- this lane's hypothesis: four tap weights (0 where a tap is outside) and clamped tap coordinates
     float w_nw = 0.f, w_ne = 0.f, w_sw = 0.f, w_se = 0.f;
-    int xs = 0, ys = 0;
+    int o_nw = 0, o_ne = 0, o_sw = 0, o_se = 0;
     if (dl < D) {
       float gx, gy;
       const size_t pt = ((size_t)dl * H + y) * W + x;
@@ -133,8 +153,7 @@ __global__ void __launch_bounds__(256, 3) stereo_cost_volume_kernel(const Stereo
         gx = g.x;
         gy = g.y;
       } else {
-        const float* fr = c.frustum + pt * 3;
-        sampling_coordinate(cam, __ldg(fr), __ldg(fr + 1), __ldg(fr + 2), wm1, hm1, &gx, &gy);
+        sampling_coordinate(cam, fu, fv, __ldg(c.frustum_d + dl), wm1, hm1, &gx, &gy);
       }
       if (c.grid_out != nullptr)
         reinterpret_cast<float2*>(c.grid_out)[(size_t)bn * D * H * W + pt] = make_float2(gx, gy);
@@ -151,37 +170,43 @@ __global__ void __launch_bounds__(256, 3) stereo_cost_volume_kernel(const Stereo
         w_ne = (xr && yt) ? wx1 * wy0 : 0.f;
         w_sw = (xl && yb) ? wx0 * wy1 : 0.f;
         w_se = (xr && yb) ? wx1 * wy1 : 0.f;
-        xs = max(x0, 0) | (min(x0 + 1, W - 1) << 16);
-        ys = max(y0, 0) | (min(y0 + 1, H - 1) << 16);
+        const int xa = max(x0, 0), xb = min(x0 + 1, W - 1), ya = max(y0, 0), yb2 = min(y0 + 1, H - 1);
+        o_nw = (ya * W + xa) * C;                          // element offsets inside one image (< 2^31, checked by the host)
+        o_ne = (ya * W + xb) * C;
+        o_sw = (yb2 * W + xa) * C;
+        o_se = (yb2 * W + xb) * C;
       }
     }
     const int nd = min(32, D - d0);
+#pragma unroll 1
     for (int j = 0; j * 4 < nd; ++j) {
       const int src = j * 4 + grp;
       const float a_nw = __shfl_sync(kFull, w_nw, src), a_ne = __shfl_sync(kFull, w_ne, src);
       const float a_sw = __shfl_sync(kFull, w_sw, src), a_se = __shfl_sync(kFull, w_se, src);
-      const int pxs = __shfl_sync(kFull, xs, src), pys = __shfl_sync(kFull, ys, src);
-      const int xa = pxs & 0xffff, xb = pxs >> 16, ya = pys & 0xffff, yb2 = pys >> 16;
-      const T* p_nw = prev + ((size_t)ya * W + xa) * C;
-      const T* p_ne = prev + ((size_t)ya * W + xb) * C;
-      const T* p_sw = prev + ((size_t)yb2 * W + xa) * C;
-      const T* p_se = prev + ((size_t)yb2 * W + xb) * C;
+      const T* p_nw = prev + __shfl_sync(kFull, o_nw, src) + gl * V;
+      const T* p_ne = prev + __shfl_sync(kFull, o_ne, src) + gl * V;
+      const T* p_sw = prev + __shfl_sync(kFull, o_sw, src) + gl * V;
+      const T* p_se = prev + __shfl_sync(kFull, o_se, src) + gl * V;
       float acc = 0.f;
       bool zero_flag = false;
 #pragma unroll
       for (int k = 0; k < NK; ++k) {
-        const int ch = (gl + 8 * k) * V;
-        if (ch < C) {
+        if (FULL || (gl + 8 * k) * V < C) {
           float a[V], bq[V], cq[V], dq[V];
-          Vec<T>::load(p_nw + ch, a);
-          Vec<T>::load(p_ne + ch, bq);
-          Vec<T>::load(p_sw + ch, cq);
-          Vec<T>::load(p_se + ch, dq);
+          Vec<T>::load(p_nw + 8 * k * V, a);
+          Vec<T>::load(p_ne + 8 * k * V, bq);
+          Vec<T>::load(p_sw + 8 * k * V, cq);
+          Vec<T>::load(p_se + 8 * k * V, dq);
 #pragma unroll
           for (int i = 0; i < V; ++i) {
-            const float v = a[i] * a_nw + bq[i] * a_ne + cq[i] * a_sw + dq[i] * a_se;
-            acc += fabsf(cur[k][i] - v);
-            if (k == flag_k && i == flag_i) zero_flag = (v == 0.f);
+            // cur - (a w_nw + b w_ne + c w_sw + d w_se) as four fused multiply-adds
+            const float t = fmaf(-dq[i], a_se, fmaf(-cq[i], a_sw, fmaf(-bq[i], a_ne, fmaf(-a[i], a_nw, cur[k][i]))));
+            acc += fabsf(t);
+          }
+          if (k == flag_k) {                             // the warped value itself, for the reference's `== 0` test
+            const float v0 = a[0] * a_nw + bq[0] * a_ne + cq[0] * a_sw + dq[0] * a_se;
+            const float v4 = a[V - 4] * a_nw + bq[V - 4] * a_ne + cq[V - 4] * a_sw + dq[V - 4] * a_se;
+            zero_flag = (flag_i == 0 ? v0 : v4) == 0.f;
           }
         }
       }
@@ -254,13 +279,13 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restri
   }
 }
 
-template <typename T>
+template <typename T, bool FULL>
 int launch_cost_volume(const StereoParams& P, int nk, int blocks, cudaStream_t st) {
-  if (nk <= 1) stereo_cost_volume_kernel<T, 1><<<blocks, 256, 0, st>>>(P);
-  else if (nk <= 2) stereo_cost_volume_kernel<T, 2><<<blocks, 256, 0, st>>>(P);
-  else if (nk <= 4) stereo_cost_volume_kernel<T, 4><<<blocks, 256, 0, st>>>(P);
-  else if (nk <= 8) stereo_cost_volume_kernel<T, 8><<<blocks, 256, 0, st>>>(P);
-  else stereo_cost_volume_kernel<T, 16><<<blocks, 256, 0, st>>>(P);
+  if (nk <= 1) stereo_cost_volume_kernel<T, 1, FULL><<<blocks, 256, 0, st>>>(P);
+  else if (nk <= 2) stereo_cost_volume_kernel<T, 2, FULL><<<blocks, 256, 0, st>>>(P);
+  else if (nk <= 4) stereo_cost_volume_kernel<T, 4, FULL><<<blocks, 256, 0, st>>>(P);
+  else if (nk <= 8) stereo_cost_volume_kernel<T, 8, FULL><<<blocks, 256, 0, st>>>(P);
+  else stereo_cost_volume_kernel<T, 16, FULL><<<blocks, 256, 0, st>>>(P);
   return 0;
 }
 
@@ -285,12 +310,13 @@ extern "C" int dhd_nchw_to_nhwc(const float* in, int N, int C, int HW, void* out
 extern "C" int dhd_stereo_cost_volume(const dhd_stereo_desc* d, void* stream) {
   DHD_REQUIRE(d != nullptr, "stereo desc is null");
   DHD_REQUIRE(d->prev && d->curr, "null feature pointer");
-  DHD_REQUIRE(d->BN > 0 && d->H > 0 && d->W > 0 && d->H < 32768 && d->W < 32768, "bad map shape");
+  DHD_REQUIRE(d->BN > 0 && d->H > 0 && d->W > 0 && (long)d->H * d->W * d->C < (1L << 31), "bad map shape");
   DHD_REQUIRE(d->C >= 4 && d->C % 4 == 0 && d->C <= 512, "C must be a multiple of 4, at most 512");
   DHD_REQUIRE(!d->feat_bf16 || d->C % 8 == 0, "bf16 features: C must be a multiple of 8");
   DHD_REQUIRE(d->D >= 1 && d->D <= 32 * kMaxBatches, "D must be in 1..128");
-  DHD_REQUIRE(d->grid != nullptr || (d->frustum != nullptr && d->cam != nullptr),
-              "either the sampling grid or frustum + camera matrices must be given");
+  DHD_REQUIRE(d->grid != nullptr || (d->frustum_u != nullptr && d->frustum_v != nullptr && d->frustum_d != nullptr &&
+                                     d->cam != nullptr),
+              "either the sampling grid or the frustum vectors + camera matrices must be given");
   DHD_REQUIRE(d->out_f32 != nullptr || d->out_b16 != nullptr, "no output");
   DHD_REQUIRE(((uintptr_t)d->prev & 15) == 0 && ((uintptr_t)d->curr & 15) == 0 && ((uintptr_t)d->grid & 7) == 0 &&
                   ((uintptr_t)d->grid_out & 7) == 0,
@@ -303,13 +329,25 @@ extern "C" int dhd_stereo_cost_volume(const dhd_stereo_desc* d, void* stream) {
   P.d = *d;
   P.tiles_x = (d->W + kTileX - 1) / kTileX;
   P.tiles_y = (d->H + kTileY - 1) / kTileY;
+  static const int pf_default = [] {
+    const char* e = getenv("DHD_STEREO_PF");
+    return e != nullptr ? atoi(e) : 24;
+  }();
+  P.pf_rows = ((size_t)d->C * kTileX * (d->feat_bf16 ? 2 : 4)) % 16 == 0 ? pf_default : 0;
   const long blocks = (long)P.tiles_x * P.tiles_y * d->BN;
   DHD_REQUIRE(blocks < (1L << 31), "map too large");
   const int nk = d->feat_bf16 ? (d->C + 63) / 64 : (d->C + 31) / 32;      // 16-byte slots per lane of an 8-lane group
-  if (d->feat_bf16)
-    launch_cost_volume<__nv_bfloat16>(P, nk, (int)blocks, (cudaStream_t)stream);
-  else
-    launch_cost_volume<float>(P, nk, (int)blocks, (cudaStream_t)stream);
+  const int slot = d->feat_bf16 ? 64 : 32;              // channels one k-step of an 8-lane group covers
+  const int nk_pow2 = nk <= 1 ? 1 : nk <= 2 ? 2 : nk <= 4 ? 4 : nk <= 8 ? 8 : 16;
+  const bool full = d->C == nk_pow2 * slot;             // every slot in range: the kernel drops its channel guards
+  const cudaStream_t st = (cudaStream_t)stream;
+  if (d->feat_bf16) {
+    if (full) launch_cost_volume<__nv_bfloat16, true>(P, nk, (int)blocks, st);
+    else launch_cost_volume<__nv_bfloat16, false>(P, nk, (int)blocks, st);
+  } else {
+    if (full) launch_cost_volume<float, true>(P, nk, (int)blocks, st);
+    else launch_cost_volume<float, false>(P, nk, (int)blocks, st);
+  }
   DHD_CUDA_LAUNCH_CHECK("stereo_cost_volume");
   return DHD_OK;
 }

@@ -16,7 +16,8 @@ class StereoDesc(ctypes.Structure):
     _fields_ = [
         ('BN', ctypes.c_int32), ('C', ctypes.c_int32), ('H', ctypes.c_int32), ('W', ctypes.c_int32),
         ('D', ctypes.c_int32), ('feat_bf16', ctypes.c_int32),
-        ('prev', ctypes.c_void_p), ('curr', ctypes.c_void_p), ('frustum', ctypes.c_void_p),
+        ('prev', ctypes.c_void_p), ('curr', ctypes.c_void_p),
+        ('frustum_u', ctypes.c_void_p), ('frustum_v', ctypes.c_void_p), ('frustum_d', ctypes.c_void_p),
         ('cam', ctypes.c_void_p), ('grid', ctypes.c_void_p),
         ('img_w', ctypes.c_float), ('img_h', ctypes.c_float), ('bias', ctypes.c_float),
         ('out_f32', ctypes.c_void_p),
@@ -56,6 +57,14 @@ def camera_table(k2s_sensor, intrins, post_rots, post_trans):
     return t
 
 
+def frustum_axes(frustum):
+    """(D, H, W, 3) template of create_frustum (lss_heightmap.py:105-134) -> its three axes (u (W), v (H), d (D)):
+    the template is frustum[d][y][x] = (u[x], v[y], d[d]) by construction, so the kernel reads 3 small vectors instead
+    of 12 bytes per point."""
+    f = frustum.float()
+    return f[0, 0, :, 0].contiguous(), f[0, :, 0, 1].contiguous(), f[:, 0, 0, 2].contiguous()
+
+
 def to_nhwc(x, bf16=False):
     """(N, C, H, W) fp32 contiguous -> (N, H, W, C) fp32 or bf16: the layout the kernel gathers from (every
     bilinear tap is one contiguous row of C channels)."""
@@ -75,13 +84,14 @@ def cost_volume(prev, curr, depth_bins, img_hw, bias=0.0, frustum=None, cam=None
     """softmax(-L1 matching cost) over the depth hypotheses.
 
     prev, curr : (BN, H, W, C) NHWC feature maps, both fp32 or both bf16 (see to_nhwc)
-    frustum    : (D, H, W, 3) fp32 (u, v, d) template at the stereo resolution + cam = camera_table(...): the sampling
+    frustum    : (D, H, W, 3) fp32 (u, v, d) template at the stereo resolution, or frustum_axes() of it (cacheable),
+                 + cam = camera_table(...): the sampling
                  coordinates are computed in the kernel; or grid (BN, D*H, W, 2), coordinates computed elsewhere
     out        : optional (BN, D, H, W) fp32 tensor written in the reference's NCHW layout (allocated when neither
                  `out` nor `out_act` is given)
     out_act    : optional dense.Act (BN, H, W, >= D channels): the split-bf16 NHWC input of cost_volumn_net
     Returns (out, grid_used or None)."""
-    _need_cuda(prev, curr, frustum, cam, grid)
+    _need_cuda(prev, curr, cam, grid, *(frustum if isinstance(frustum, (tuple, list)) else (frustum,)))
     if prev.shape != curr.shape or prev.dtype != curr.dtype or prev.dim() != 4:
         raise ValueError('prev / curr must be NHWC tensors of one shape and dtype')
     if prev.dtype not in (torch.float32, torch.bfloat16) or not prev.is_contiguous() or not curr.is_contiguous():
@@ -101,11 +111,13 @@ def cost_volume(prev, curr, depth_bins, img_hw, bias=0.0, frustum=None, cam=None
     else:
         if frustum is None or cam is None:
             raise ValueError('either grid or frustum + cam must be given')
-        if tuple(frustum.shape) != (D, H, W, 3) or tuple(cam.shape) != (BN, CAM_FLOATS):
-            raise ValueError('frustum must be (D, H, W, 3) and cam (BN, %d)' % CAM_FLOATS)
-        frustum, cam = frustum.float().contiguous(), cam.float().contiguous()
-        d.frustum, d.cam = frustum.data_ptr(), cam.data_ptr()
-        keep += [frustum, cam]
+        fu, fv, fd = frustum if isinstance(frustum, (tuple, list)) else frustum_axes(frustum)
+        if tuple(fu.shape) != (W,) or tuple(fv.shape) != (H,) or tuple(fd.shape) != (D,) or \
+                tuple(cam.shape) != (BN, CAM_FLOATS):
+            raise ValueError('frustum must be (D, H, W, 3) [or its (u, v, d) axes] and cam (BN, %d)' % CAM_FLOATS)
+        cam = cam.float().contiguous()
+        d.frustum_u, d.frustum_v, d.frustum_d, d.cam = fu.data_ptr(), fv.data_ptr(), fd.data_ptr(), cam.data_ptr()
+        keep += [fu, fv, fd, cam]
     d.img_h, d.img_w = float(img_hw[0]), float(img_hw[1])
     d.bias = float(bias)
     if out is None and out_act is None:

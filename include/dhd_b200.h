@@ -347,7 +347,9 @@ typedef struct dhd_stereo_desc {
   int32_t feat_bf16;           /* element type of prev / curr: 0 fp32, 1 bf16 */
   const void* prev;            /* (BN, H, W, C) previous frame, already aligned to the same camera order */
   const void* curr;            /* (BN, H, W, C) current frame */
-  const float* frustum;        /* (D, H, W, 3) = (u, v, d) template (MGHS_Stereo.cv_frustum); unused when grid != NULL */
+  const float* frustum_u;      /* (W), (H), (D): the three axes of the (D, H, W, 3) = (u, v, d) template MGHS_Stereo.cv_frustum */
+  const float* frustum_v;      /*   is built from (create_frustum, lss_heightmap.py:105-134: frustum[d][y][x] = */
+  const float* frustum_d;      /*   (u[x], v[y], d[d])); unused when grid != NULL */
   const float* cam;            /* (BN, DHD_STEREO_CAM_FLOATS); unused when grid != NULL */
   const float* grid;           /* optional (BN, D*H, W, 2): normalised sampling coordinates computed elsewhere */
   float img_w, img_h;          /* wi, hi of gen_grid: 4 * W, 4 * H */
