@@ -46,6 +46,7 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-train', action='store_true', help='skip the training-step extra')
     ap.add_argument('--no-encoders', action='store_true', help='skip the widened-path (real encoders) extra')
+    ap.add_argument('--no-dhdl', action='store_true', help='skip the DHD-L (configs[4]) view-transformer extra')
     return ap.parse_args()
 
 
@@ -261,7 +262,7 @@ def run_ours(args):
                  'gradient_all_reduce_bytes': ts.n_params * 4,
                  'loss_height': float(ts.loss_height[0]),
                  'what': 'forward + losses (occupancy CE + sem_scal + geo_scal, height BCE) + backward of depth_net, HeightNet, SFA and predictor '
-                         '(BatchNorm2d in training mode: batch statistics, trainable affine), fused pool fwd+bwd, one NCCL all-reduce of the fp32 gradient bucket, AdamW, '
+                         '(BatchNorm2d in training mode: batch statistics, trainable affine; the ASPP Dropout(0.5) on), fused pool fwd+bwd, one NCCL all-reduce of the fp32 gradient bucket, AdamW, '
                          'bf16 weight re-pack; encoders stand in as resident tensors (see TrainStep)'}
         del ts
         torch.cuda.empty_cache()
@@ -287,6 +288,10 @@ def run_ours(args):
                                       'trainable_params': tse.n_params, 'loss': float(tse.loss[0])}
             del tse
             torch.cuda.empty_cache()
+
+    dhdl = None
+    if world == 1 and not args.no_dhdl:
+        dhdl = dhdl_extra(args.precision if args.precision in ('bf16', 'fp32') else 'bf16')
 
     ms_total, ms_e2e, pool_ms_avg = shard.max_over_ranks([ms_total, ms_e2e, pool_ms_avg], device='cuda')
     if train is not None:
@@ -333,6 +338,7 @@ def run_ours(args):
             },
             'extras': {
                 'stage_ms': stage_ms, 'pool_bwd_ms': bwd_ms, 'train_step': train, 'with_encoders': widened,
+                'dhd_l_view_transformer': dhdl,
                 'e2e_serialised_ms_per_step (H2D, kernels, D2H on one stream)': ms_e2e_serial,
                 'dense_tflops_algorithmic': {k: v / 1e12 for k, v in fl.items()},
                 'dense_tflop_per_s': sum(fl.values()) / 1e12 /
@@ -347,6 +353,37 @@ def run_ours(args):
         print(json.dumps(line), file=_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def dhdl_extra(precision, B=2):
+    """BASELINE configs[4]: the plugin's MGHS_Stereo with the DHD-L.py kwargs at full size (6-cam 512x1408, C_in=512,
+    D=88, two-frame stereo features 128 ch @128x352): cost volume -> stereo DepthNet + HeightNet -> fused pool."""
+    from dhd_b200 import synth
+    vt, vargs, metas = synth.dhdl_view_transformer(precision, B)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(fn, it=10, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(it):
+            fn()
+        ev1.record()
+        torch.cuda.synchronize()
+        return ev0.elapsed_time(ev1) / it
+
+    with torch.no_grad():
+        ms = timed(lambda: vt(vargs, metas))
+        ms_cv = timed(lambda: vt.depth_net.calculate_cost_volumn(metas))
+    del vt, vargs, metas
+    torch.cuda.empty_cache()
+    return {'ms_per_step': ms, 'samples_per_s': B / ms * 1e3, 'samples': B, 'precision': precision,
+            'stereo_cost_volume_ms': ms_cv,
+            'what': 'MGHS_Stereo.forward(input, stereo_metas) of projects/configs/DHD/DHD-L.py: NCHW->NHWC of both stereo '
+                    'features, fused plane-sweep cost volume (gen_grid + 32 grid_sample groups + softmax of the reference '
+                    'in one kernel), cost_volumn_net, stereo DepthNet and HeightNet at C=512 on tcgen05, fused '
+                    'collapse_z=False voxel pool -> (B,64,1,200,200) + (B,64,16,200,200)'}
 
 
 # ----------------------------------------------------------------------- CPU oracle leg

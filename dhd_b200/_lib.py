@@ -58,6 +58,7 @@ _SIGNATURES = {
     'dhd_bn_apply': (ctypes.c_int, [_P, _I, _I, ctypes.c_long, _I, _P, _P, _I, _P, ctypes.c_long, _P, _I, _P, _I, _I, _P, ctypes.c_long, _P]),
     'dhd_bn_fwd_coeffs': (ctypes.c_int, [_P, _I, ctypes.c_float, _P, _P, ctypes.c_float, ctypes.c_float, _P, _P, _P, _P, _P, _P, _P]),
     'dhd_bn_bwd_coeffs': (ctypes.c_int, [_P, _I, _I, ctypes.c_float, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    'dhd_dropout': (ctypes.c_int, [_P, _I, _I, ctypes.c_long, _I, ctypes.c_float, _P, ctypes.c_uint, _P]),
     'dhd_affine_combine': (ctypes.c_int, [_P, _I, _I, _P, _I, _I, ctypes.c_long, _I, _P, _P, _P, _P, _I, _I, _P]),
     'dhd_se_gate_bwd': (ctypes.c_int, [_P, _I, _I, _P, _I, _I, _I, _I, _I, _P, _P, _I, _I, _P, _P, _P]),
     'dhd_height_loss': (ctypes.c_int, [_P, _P, _P, _I, _I, _I, ctypes.c_float, _P, _P, _P, _I, _P]),

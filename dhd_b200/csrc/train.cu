@@ -814,6 +814,46 @@ bn_bwd_coeffs_kernel(const float* __restrict__ sums, int C, int sums_stride, flo
   if (dbeta != nullptr) dbeta[c] += s1;
 }
 
+
+// Dropout (nn.Dropout(0.5) behind the ASPP, depthnet.py:81, 106) as a counter-based mask: Philox-4x32-10 keyed by the
+// seed, counter = (vector index, step, salt), one call per 8 channels, 16 random bits per element.  The mask is a pure
+// function of (seed, step, salt, element), so the backward multiplies the gradient by the very same mask without it
+// ever being stored; `rng` lives in device memory so a captured CUDA graph sees a new step on every replay.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u;
+    key.y += 0xBB67AE85u;
+  }
+  return ctr;
+}
+
+__global__ void __launch_bounds__(256)
+dropout_kernel(__nv_bfloat16* __restrict__ x, int ld, int coff, long rows, int C, uint32_t thresh16, float scale,
+               const long long* __restrict__ rng, uint32_t salt) {
+  const int vec_per_row = C >> 3;
+  const long v = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= rows * vec_per_row) return;
+  const long r = v / vec_per_row;
+  const int c = (int)(v - r * vec_per_row) << 3;
+  const unsigned long long seed = (unsigned long long)rng[0], step = (unsigned long long)rng[1];
+  const uint4 rnd = philox4x32_10(make_uint4((uint32_t)v, (uint32_t)((unsigned long long)v >> 32), (uint32_t)step, salt),
+                                  make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  float f[8];
+  __nv_bfloat16* p = x + r * ld + coff + c;
+  load8(p, f);
+  const uint32_t w[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint32_t r16 = (w[i >> 1] >> ((i & 1) * 16)) & 0xffffu;
+    f[i] = r16 >= thresh16 ? f[i] * scale : 0.f;           // keep with probability 1 - p
+  }
+  store8(p, f);
+}
+
 }  // namespace dhd
 
 using namespace dhd;
@@ -1061,5 +1101,18 @@ extern "C" int dhd_bn_bwd_coeffs(const float* sums, int C, int sums_stride, floa
   bn_bwd_coeffs_kernel<<<(C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(sums, C, sums_stride, M, mean, invstd, gamma,
                                                                          k1, k2, k3, dgamma, dbeta);
   DHD_CUDA_LAUNCH_CHECK("bn_bwd_coeffs");
+  return DHD_OK;
+}
+
+extern "C" int dhd_dropout(void* x, int ld, int coff, long rows, int C, float p, const long long* rng, unsigned salt,
+                           void* stream) {
+  DHD_REQUIRE(x && rng && rows > 0 && C > 0, "bad arguments");
+  DHD_REQUIRE(C % 8 == 0 && ld % 8 == 0 && coff % 8 == 0 && ((uintptr_t)x & 15) == 0, "channels must come in groups of 8");
+  DHD_REQUIRE(p >= 0.f && p < 1.f, "drop probability must be in [0, 1)");
+  const long vecs = rows * (C / 8);
+  const uint32_t thresh = (uint32_t)(p * 65536.f + 0.5f);
+  dropout_kernel<<<(unsigned)((vecs + 255) / 256), 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)x, ld, coff, rows, C, thresh,
+                                                                                 1.f / (1.f - p), rng, salt);
+  DHD_CUDA_LAUNCH_CHECK("dropout");
   return DHD_OK;
 }

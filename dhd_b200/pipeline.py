@@ -403,7 +403,7 @@ class TrainStep(HotPathStep):
                 bf16 forward / data-gradient weights are re-packed.
     """
 
-    def __init__(self, cfg, B, device='cuda', seed=0, encoders=False, bn='frozen'):
+    def __init__(self, cfg, B, device='cuda', seed=0, encoders=False, bn='frozen', dropout=None):
         """encoders=True: the real BEV / voxel encoders sit between the pool and the SFA in forward AND backward, so
         the occupancy loss reaches the pool and depth_net through them (no stand-in tensors anywhere)."""
         super().__init__(cfg, B, precision='bf16', device=device, seed=seed, use_graph=False, encoders=encoders)
@@ -429,7 +429,11 @@ class TrainStep(HotPathStep):
         self.t_depth = DepthHeadTrainer(self.vt.depth_net, self.D, self.device)
         self.t_sfa = SFATrainer(self.sfa, self.device)
         self.t_head = PredictorTrainer(self.head, self.device)
-        self.t_height = HeightNetTrainer(self.vt.height_net, self.device, loss_weight=0.1)
+        # nn.Dropout(0.5) behind HeightNet's ASPP (depthnet.py:81): on in the reference's training mode, i.e. together
+        # with batch-statistics BatchNorm; off with the frozen (eval-like) BatchNorm unless asked for
+        self.dropout = (0.5 if bn == 'batch' else 0.0) if dropout is None else float(dropout)
+        self.t_height = HeightNetTrainer(self.vt.height_net, self.device, loss_weight=0.1, dropout=self.dropout,
+                                         seed=seed + 17)
         enc_params = []
         if encoders:
             from .train import CustomResNetTrainer, FPNLSSTrainer, UNetTrainer

@@ -77,3 +77,26 @@ def synthetic_k2s_sensor(sensor2ego, forward_m=0.8, yaw_deg=1.5):
     ego[:3, 3] = torch.tensor([forward_m, 0.03, 0.0])
     ego = ego.to(sensor2ego)
     return torch.linalg.inv(sensor2ego) @ ego @ sensor2ego
+
+
+def dhdl_view_transformer(precision, B):
+    """The plugin's MGHS_Stereo built with the DHD-L.py kwargs + synthetic inputs of BASELINE configs[4]: (module,
+    forward `input` list, stereo_metas).  CUDA only."""
+    import projects.mmdet3d_plugin  # noqa: F401
+    from projects.mmdet3d_plugin.models.necks.lss_heightmap import MGHS_Stereo
+    kw = dict(DHD_L_VIEW_TRANSFORMER)
+    torch.manual_seed(0)
+    vt = MGHS_Stereo(precision=precision, **kw).eval().cuda()
+    H, W = kw['input_size']
+    rig = synthetic_rig(B, 6, kw['input_size'], seed=1)
+    s2e, e2g, K, pr, pt, bda = [t.cuda() for t in rig]
+    x = torch.randn(B, 6, kw['in_channels'], H // 16, W // 16, device='cuda')
+    mlp = vt.get_mlp_input(s2e, e2g, K, pr, pt, bda)
+    k = torch.ones(1, 1, 5, 5, device='cuda') / 25.0
+    C = DHD_L_STEREO_CHANNELS
+    feat = lambda: torch.nn.functional.conv2d(torch.randn(B * 6 * C, 1, H // 4, W // 4, device='cuda'), k,
+                                              padding=2).view(B * 6, C, H // 4, W // 4)
+    metas = dict(k2s_sensor=synthetic_k2s_sensor(s2e), intrins=K, post_rots=pr, post_trans=pt,
+                 frustum=vt.cv_frustum.cuda(), cv_downsample=4, downsample=vt.downsample, grid_config=vt.grid_config,
+                 cv_feat_list=[feat(), feat()])
+    return vt, [x, s2e, e2g, K, pr, pt, bda, mlp], metas

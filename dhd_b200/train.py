@@ -468,6 +468,13 @@ class SFATrainer:
         return dx
 
 
+def dropout_(a, p, rng, salt=0):
+    """In-place Dropout of an Act (bf16 part 0) with the counter-based mask of dhd_dropout."""
+    _lib.check(_lib.load().dhd_dropout(_p(a.data), a.ld, a.coff, a.N * a.H * a.W, a.C, float(p), _p(rng), int(salt),
+                                       _stream()), 'dropout')
+    return a
+
+
 def _ensure_grad(p):
     if p.grad is None:
         p.grad = torch.zeros_like(p)
@@ -475,15 +482,21 @@ def _ensure_grad(p):
 
 
 class HeightNetTrainer:
-    """HeightNet (depthnet.py:418-487, 605-652, non-stereo) with frozen BatchNorm and Dropout off:
+    """HeightNet (depthnet.py:418-487, 605-652, non-stereo); BatchNorm frozen or on batch statistics (set_bn_mode),
+    the ASPP's Dropout on when `dropout` > 0:
     reduce conv + camera-aware SE gate, BasicBlocks, ASPP (global branch as a per-image bias), DCN
     (deformable im2col + grouped GEMM), 1x1 head + softmax; backward of all of it, fed by the height loss
     (lss_heightmap.py:595-622)."""
 
-    def __init__(self, net, device='cuda', loss_weight=0.1):
+    def __init__(self, net, device='cuda', loss_weight=0.1, dropout=0.0, seed=0):
+        """dropout: drop probability of the ASPP's nn.Dropout (depthnet.py:81; 0.5 in the reference's train mode,
+        0 = eval behaviour).  The mask comes from a counter-based generator (dhd_dropout) keyed by (seed, step); the
+        step counter lives on the device and is bumped at the end of backward()."""
         from .modules import linear_rows, mean_hw
         self._linear, self._mean = linear_rows, mean_hw
         self.net, self.device, self.loss_weight = net, device, float(loss_weight)
+        self.dropout_p = float(dropout)
+        self.rng = torch.tensor([int(seed), 0], dtype=torch.int64, device=device)
         self.C = net.reduce_conv[0].out_channels
         self.reduce = _TrainConv(net.reduce_conv[0].weight, net.reduce_conv[0].bias, net.reduce_conv[1], 3)
         layers = list(net.depth_conv)
@@ -593,6 +606,8 @@ class HeightNetTrainer:
         ib = lin(x5, self.w5s)
         ha = self._act('ha', N, H, W, C)
         self.aspp_out.forward(cat, [dict(act='relu', out_act=ha)], img_bias=ib)
+        if self.dropout_p > 0.0:                     # in place: everything downstream (and the backward) sees the dropped map
+            dropout_(ha, self.dropout_p, self.rng, salt=1)
         k, g, cg = self.k, self.groups, C // self.groups
         off = self._f32('off', N, H, W, self.noff)
         self.dcn_offset.forward(ha, [dict(out_f32=(off, D.nhwc_strides(self.noff, H, W)))])
@@ -659,7 +674,10 @@ class HeightNetTrainer:
         _, sums = act_bwd(doff_a, None, None, want_sums=True)
         dha = self._act('d_ha', N, H, W, C)
         self.dcn_offset.backward(ha, doff_a, [dict(out_act=dha)], bias_sums=sums[0], residual=(dxs, nhwc[:3]))
-        # ---- ASPP
+        # ---- ASPP (Dropout backward = the same mask on the gradient; the ReLU test `y > 0` on the dropped map is
+        # still right for every kept element and the dropped ones are already zero)
+        if self.dropout_p > 0.0:
+            dropout_(dha, self.dropout_p, self.rng, salt=1)
         act_bwd(dha, ha, 'relu')
         dcat = self._act('d_cat', N, H, W, 4 * mid)
         self.aspp_out.backward(cat, dha, [dict(out_act=dcat)])
@@ -727,6 +745,8 @@ class HeightNetTrainer:
         dz1 = (lin(dh2, f(mlp.fc2.weight).t().contiguous()) * (h1 > 0).float()).contiguous()
         _acc(mlp.fc1.weight, lin(dz1.t().contiguous(), m_bn.t().contiguous()))
         _acc(mlp.fc1.bias, dz1.sum(0))
+        if self.dropout_p > 0.0:
+            self.rng[1:].add_(1)                   # next step, next mask (a device-side update: graph replays advance too)
         return dx
 
 

@@ -327,6 +327,12 @@ int dhd_bn_fwd_coeffs(const float* sums, int C, float M, const float* gamma, con
                       float* mean, float* invstd, void* stream);
 int dhd_bn_bwd_coeffs(const float* sums, int C, int sums_stride, float M, const float* mean, const float* invstd,
                       const float* gamma, float* k1, float* k2, float* k3, float* dgamma, float* dbeta, void* stream);
+/* nn.Dropout behind the ASPP (depthnet.py:81, 106) in training mode, in place on a bf16 NHWC activation (or on the
+ * gradient at the same place in the backward): x[r][c] *= keep(r, c) / (1 - p), keep from Philox-4x32-10 keyed by
+ * rng[0] (seed) with counter (element, rng[1] (step), salt).  rng is a DEVICE pointer to two int64: the caller bumps
+ * the step once per iteration, also inside a captured graph.  Same (seed, step, salt) => same mask. */
+int dhd_dropout(void* x, int ld, int coff, long rows, int C, float p, const long long* rng, unsigned salt,
+                void* stream);
 int dhd_affine_combine(const void* a, int a_ld, int a_coff, const void* b, int b_ld, int b_coff, long rows, int C,
                        const float* k1, const float* k2, const float* k3, void* out, int o_ld, int o_coff,
                        void* stream);

@@ -11,25 +11,7 @@ import torch  # noqa: E402
 from dhd_b200 import synth  # noqa: E402
 
 
-def build(precision, B):
-    import projects.mmdet3d_plugin  # noqa: F401
-    from projects.mmdet3d_plugin.models.necks.lss_heightmap import MGHS_Stereo
-    kw = dict(synth.DHD_L_VIEW_TRANSFORMER)
-    torch.manual_seed(0)
-    vt = MGHS_Stereo(precision=precision, **kw).eval().cuda()
-    H, W = kw['input_size']
-    rig = synth.synthetic_rig(B, 6, kw['input_size'], seed=1)
-    s2e, e2g, K, pr, pt, bda = [t.cuda() for t in rig]
-    x = torch.randn(B, 6, kw['in_channels'], H // 16, W // 16, device='cuda')
-    mlp = vt.get_mlp_input(s2e, e2g, K, pr, pt, bda)
-    k = torch.ones(1, 1, 5, 5, device='cuda') / 25.0
-    C = synth.DHD_L_STEREO_CHANNELS
-    feat = lambda: torch.nn.functional.conv2d(torch.randn(B * 6 * C, 1, H // 4, W // 4, device='cuda'), k,
-                                              padding=2).view(B * 6, C, H // 4, W // 4)
-    metas = dict(k2s_sensor=synth.synthetic_k2s_sensor(s2e), intrins=K, post_rots=pr, post_trans=pt,
-                 frustum=vt.cv_frustum.cuda(), cv_downsample=4, downsample=vt.downsample, grid_config=vt.grid_config,
-                 cv_feat_list=[feat(), feat()])
-    return vt, [x, s2e, e2g, K, pr, pt, bda, mlp], metas
+build = synth.dhdl_view_transformer
 
 
 def timed(fn, it=10, warm=3):

@@ -165,7 +165,7 @@ def test_sfa_backward(cuda_lib):
     assert max(errs.values()) < 2e-2, errs
 
 
-def _heightnet_forward_q(sd, x, mlp_input, q, keep=None):
+def _heightnet_forward_q(sd, x, mlp_input, q, keep=None, drop_mask=None):
     """oracle.dense_oracle.heightnet_forward (depthnet.py:605-652) with `q` at the points where the CUDA
     path stores an activation in bf16: after the SE gate, after every ReLU of the trunk, after the DCN."""
     import torch.nn.functional as F
@@ -192,6 +192,8 @@ def _heightnet_forward_q(sd, x, mlp_input, q, keep=None):
     g = F.relu(_bn(sd, p + '.global_avg_pool.2', F.conv2d(g, sd[p + '.global_avg_pool.1.weight'])))
     outs.append(g.expand(-1, -1, x.shape[2], x.shape[3]))
     x = q(F.relu(_bn(sd, p + '.bn1', F.conv2d(torch.cat(outs, 1), sd[p + '.conv1.weight']))))
+    if drop_mask is not None:          # nn.Dropout(0.5) of the ASPP in training mode (depthnet.py:106): mask * 1 / (1 - p)
+        x = x * drop_mask
     p = 'depth_conv.4'
     off = F.conv2d(x, sd[p + '.conv_offset.weight'], sd[p + '.conv_offset.bias'], padding=1)
     if keep is not None:
@@ -217,8 +219,38 @@ class _FShim:
         return getattr(F, name)
 
 
-def test_heightnet_loss_and_backward(cuda_lib):
-    """HeightNet (frozen BN, DCN, ASPP, SE gate) + height loss: every gradient against autograd over the oracle."""
+def test_dropout_mask_kernel(cuda_lib):
+    """dhd_dropout: values are 0 or x / (1 - p), the kept fraction is 1 - p, the mask is a pure function of
+    (seed, step, salt) -- what lets the backward reuse it without storing it -- and changes with each of them."""
+    from dhd_b200 import dense as D
+    from dhd_b200.train import dropout_
+    N, H, W, C = 3, 16, 44, 256
+
+    def mask(seed, step, salt, p=0.5):
+        a = D.Act.empty(N, H, W, C, 1, 'cuda')
+        a.data.fill_(1.0)
+        dropout_(a, p, torch.tensor([seed, step], dtype=torch.int64, device='cuda'), salt=salt)
+        return a.data.float()
+
+    m = mask(5, 0, 1)
+    assert set(m.unique().tolist()) == {0.0, 2.0}
+    n = m.numel()
+    assert abs(float((m > 0).float().mean()) - 0.5) < 4 * 0.5 / n ** 0.5
+    assert torch.equal(m, mask(5, 0, 1))
+    for other in (mask(6, 0, 1), mask(5, 1, 1), mask(5, 0, 2)):
+        assert abs(float((other != m).float().mean()) - 0.5) < 0.01
+    per_channel = (m > 0).float().mean(dim=(0, 1, 2))
+    assert float((per_channel - 0.5).abs().max()) < 6 * 0.5 / (N * H * W) ** 0.5
+    m3 = mask(5, 0, 1, p=0.25)
+    assert abs(float((m3 > 0).float().mean()) - 0.75) < 4 * 0.44 / n ** 0.5
+    kept = m3[m3 > 0]
+    assert torch.allclose(kept, torch.full_like(kept, 1.0 / 0.75), rtol=4e-3)          # bf16 rounding of 4/3
+
+
+@pytest.mark.parametrize('dropout', [0.0, 0.5])
+def test_heightnet_loss_and_backward(cuda_lib, dropout):
+    """HeightNet (frozen BN, DCN, ASPP [+ its Dropout(0.5) in training mode], SE gate) + height loss: every gradient
+    against autograd over the oracle (which multiplies the ASPP output by the mask the kernel draws)."""
     import projects.mmdet3d_plugin  # noqa: F401
     from dhd_b200 import dense as D
     from dhd_b200.train import HeightNetTrainer
@@ -242,7 +274,14 @@ def test_heightnet_loss_and_backward(cuda_lib):
     with torch.no_grad():                # the local restatement is the oracle's function
         assert torch.allclose(_heightnet_forward_q(sd, x, mlp_in, lambda t: t), DO.heightnet_forward(sd, x, mlp_in),
                               rtol=1e-5, atol=1e-6)
-    logits = _heightnet_forward_q(sd, x, mlp_in, _q)
+    drop_mask = None
+    if dropout > 0.0:
+        from dhd_b200.train import dropout_
+        ones = D.Act.empty(BN, H, W, 256, 1, 'cuda')
+        ones.data.fill_(1.0)
+        dropout_(ones, dropout, torch.tensor([123, 0], dtype=torch.int64, device='cuda'), salt=1)
+        drop_mask = ones.data.float().permute(0, 3, 1, 2).cpu()
+    logits = _heightnet_forward_q(sd, x, mlp_in, _q, drop_mask=drop_mask)
     probs = logits.softmax(1).permute(0, 2, 3, 1).reshape(-1, 65)
     onehot = torch.zeros(BN * H * W, 66)
     onehot[torch.arange(BN * H * W), (label + 1).long()] = 1.0
@@ -253,12 +292,13 @@ def test_heightnet_loss_and_backward(cuda_lib):
     net = net.cuda()
     for p in net.parameters():
         p.grad = None
-    tr = HeightNetTrainer(net)
+    tr = HeightNetTrainer(net, dropout=dropout, seed=123)
     height = tr.forward(D.pack_input(x.cuda(), 1), mlp_in.cuda())
     assert rel(height, logits.detach().softmax(1)) < 2e-2
     res = tr.loss(label.cuda(), fg.cuda())
     tr.backward()
     torch.cuda.synchronize()
+    assert int(tr.rng[1]) == (1 if dropout > 0.0 else 0)          # one mask per step
     assert abs(float(res[0]) - float(loss.detach())) / float(loss.detach()) < 2e-2, (float(res[0]), float(loss.detach()))
     errs, mods = {}, dict(net.named_modules())
     for name, p in net.named_parameters():
@@ -516,6 +556,9 @@ def test_train_step_with_encoders_end_to_end(cuda_lib, bn):
         for p in ts.bucket.params:
             p.add_(p.grad, alpha=-eps)
     ts._refresh()
+    if ts.dropout > 0.0:                     # the finite difference is taken on ONE Dropout mask: rewind the step counter
+        assert int(ts.t_height.rng[1]) == 1
+        ts.t_height.rng[1] = 0
     ts._fwd_bwd()
     torch.cuda.synchronize()
     drop = (first - total()) / first
