@@ -235,3 +235,40 @@ def test_dhdl_view_transformer_kwargs_are_the_reference_config():
         ([norm(x) for x in v] if isinstance(v, (list, tuple)) else v)
     assert norm(ref) == norm(synth.DHD_L_VIEW_TRANSFORMER)
     assert cfg.model.img_backbone.embed_dims == synth.DHD_L_STEREO_CHANNELS
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason='reference tree not present')
+def test_mghs_stereo_matches_reference_construction():
+    """MGHS_Stereo built from the DHD-L kwargs: parameter names / shapes of the stereo DepthNet (cost_volumn_net, the
+    first block's downsample) and the 1/4-resolution frustum template equal the reference's, and that template is
+    separable into the three axis vectors the cost-volume kernel reads."""
+    from dhd_b200 import stereo as S
+    from dhd_b200 import synth
+    import projects.mmdet3d_plugin.models.necks.lss_heightmap as LH
+    ns = ref_loader.load_reference()
+    kw = dict(synth.DHD_L_VIEW_TRANSFORMER)
+    ours, ref = LH.MGHS_Stereo(**kw), ns.MGHS_Stereo(**kw)
+    rs, os_ = ref.state_dict(), ours.state_dict()
+    assert list(rs.keys()) == list(os_.keys())
+    for k in rs:
+        assert rs[k].shape == os_[k].shape, k
+    assert any(k.startswith('depth_net.cost_volumn_net.') for k in os_) and 'depth_net.depth_conv.0.downsample.weight' in os_
+    assert torch.equal(ours.cv_frustum, ref.cv_frustum) and ours.depth_net.bias == ref.depth_net.bias == 5.0
+    fu, fv, fd = S.frustum_axes(ref.cv_frustum)
+    D, H, W, _ = ref.cv_frustum.shape
+    rebuilt = torch.stack((fu.view(1, 1, W).expand(D, H, W), fv.view(1, H, 1).expand(D, H, W),
+                           fd.view(D, 1, 1).expand(D, H, W)), -1)
+    assert torch.equal(rebuilt, ref.cv_frustum)
+
+
+def test_stereo_host_side_refuses_cpu_tensors():
+    """No CPU fallback on the stereo path either."""
+    from dhd_b200 import stereo as S
+    z = torch.zeros(1, 4, 4, 8)
+    with pytest.raises(RuntimeError, match='CUDA'):
+        S.cost_volume(z, z, 4, (16, 16), grid=torch.zeros(1, 16, 4, 2))
+    with pytest.raises(RuntimeError, match='CUDA'):
+        S.to_nhwc(torch.zeros(1, 8, 4, 4))
+    with pytest.raises(RuntimeError, match='CUDA'):
+        S.camera_table(torch.eye(4).view(1, 1, 4, 4), torch.eye(3).view(1, 1, 3, 3), torch.eye(3).view(1, 1, 3, 3),
+                       torch.zeros(1, 1, 3))
