@@ -131,6 +131,25 @@ ce_norm_kernel(const uint8_t* __restrict__ labels, const uint8_t* __restrict__ m
 // logits (B, Dx, Dy, Dz, ncls) fp32 (the predictor's output layout); labels / mask (B, Dx, Dy, Dz);
 // dlogits bf16 NHWC rows [(b*Dy + y)*Dx + x][ld], channel z*ncls + k (the layout the last Linear's
 // backward GEMMs read); loss[0] += sum of weighted voxel losses * loss_weight / norm.
+// one voxel's class logits into registers (-inf beyond ncls): 8-byte loads when the row is 8-byte aligned (even ncls)
+__device__ __forceinline__ void load_logits(const float* __restrict__ lg, int ncls, float (&e)[32]) {
+  if ((ncls & 1) == 0) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      if (2 * k < ncls) {
+        const float2 t = __ldg(reinterpret_cast<const float2*>(lg) + k);
+        e[2 * k] = t.x;
+        e[2 * k + 1] = t.y;
+      } else {
+        e[2 * k] = e[2 * k + 1] = -INFINITY;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 32; ++k) e[k] = k < ncls ? __ldg(lg + k) : -INFINITY;
+  }
+}
+
 __global__ void __launch_bounds__(256)
 ce_loss_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ labels, const uint8_t* __restrict__ mask,
                const float* __restrict__ cw, int ncls, int ignore, int B, int Dx, int Dy, int Dz, float loss_weight,
@@ -174,11 +193,9 @@ ce_loss_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ lab
     }
     float e[32];                     // ncls <= 32 on this path (host checks); logits stay in registers
     float mx = -INFINITY;
+    load_logits(lg, ncls, e);
 #pragma unroll
-    for (int k = 0; k < 32; ++k) {
-      e[k] = k < ncls ? __ldg(lg + k) : -INFINITY;
-      mx = fmaxf(mx, e[k]);
-    }
+    for (int k = 0; k < 32; ++k) mx = fmaxf(mx, e[k]);
     float s = 0.f, ll = 0.f;
 #pragma unroll
     for (int k = 0; k < 32; ++k) {
@@ -595,11 +612,9 @@ occ_scal_stats_kernel(const float* __restrict__ logits, const uint8_t* __restric
         l = t;
         const float* lg = logits + v * ncls;
         float e[32], mx = -INFINITY, s = 0.f;
+        load_logits(lg, ncls, e);
 #pragma unroll
-        for (int k = 0; k < 32; ++k) {
-          e[k] = k < ncls ? __ldg(lg + k) : -INFINITY;
-          mx = fmaxf(mx, e[k]);
-        }
+        for (int k = 0; k < 32; ++k) mx = fmaxf(mx, e[k]);
 #pragma unroll
         for (int k = 0; k < 32; ++k) {
           e[k] = __expf(e[k] - mx);
@@ -648,17 +663,33 @@ __device__ __forceinline__ float scal_step(float x) {      // inverse_sigmoid's 
 
 // One warp: lane i = class i.  out[0] = weight_sem * sem_scal, out[1] = weight_geo * geo_scal;
 // gt[i] / gn[i] = d(both terms)/d p_i of a masked voxel whose label is / is not i.
-__global__ void occ_scal_coeffs_kernel(const float* __restrict__ partial, int nblocks, int ncls, int non_empty,
+__global__ void __launch_bounds__(1024) occ_scal_coeffs_kernel(const float* __restrict__ partial, int nblocks, int ncls, int non_empty,
                                        float w_sem, float w_geo, float* __restrict__ out, float* __restrict__ gt,
                                        float* __restrict__ gn) {
-  const int i = threadIdx.x;
+  // every warp sums a strided share of the per-block partials (lane i = class i), warp 0 adds the warps' sums in
+  // warp order: a fixed summation tree whatever the timing (deterministic), ~nblocks / 32 dependent steps instead of nblocks
+  __shared__ float red[32][4][32];
+  const int i = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   float sp = 0.f, nom = 0.f, cnt = 0.f, M = 0.f;
-  for (int b = 0; b < nblocks; ++b) {
+  for (int b = wid; b < nblocks; b += nw) {
     const float* p = partial + (size_t)b * kScalRow;
     sp += p[i];
     nom += p[32 + i];
     cnt += p[64 + i];
     M += p[96];
+  }
+  red[wid][0][i] = sp;
+  red[wid][1][i] = nom;
+  red[wid][2][i] = cnt;
+  red[wid][3][i] = M;
+  __syncthreads();
+  if (wid != 0) return;
+  sp = nom = cnt = M = 0.f;
+  for (int w = 0; w < nw; ++w) {
+    sp += red[w][0][i];
+    nom += red[w][1][i];
+    cnt += red[w][2][i];
+    M += red[w][3][i];
   }
   const float eps = 1e-5f;
   float loss = 0.f, a = 0.f, bb = 0.f, sc = 0.f;          // a: d/dNom, bb: d/dSp, sc: coefficient of (1 - c)
@@ -755,21 +786,34 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ raw, int r_ld, int r_coff, lon
   }
 }
 
+// 256 threads = (256 / cg) rows x cg channel groups of 8; the three coefficient vectors of a thread's 8 channels stay
+// in registers while it walks the rows (grid-stride), so a row costs two 16-byte loads and one 16-byte store
 __global__ void __launch_bounds__(256)
 affine_combine_kernel(const __nv_bfloat16* __restrict__ a, int a_ld, int a_coff, const __nv_bfloat16* __restrict__ b, int b_ld,
                       int b_coff, long rows, int C, const float* __restrict__ k1, const float* __restrict__ k2,
                       const float* __restrict__ k3, __nv_bfloat16* __restrict__ out, int o_ld, int o_coff) {
-  const int cg = C / 8;
-  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= rows * cg) return;
-  const long r = i / cg;
-  const int c = (int)(i % cg) * 8;
-  float x[8], y[8];
-  load8(a + r * a_ld + a_coff + c, x);
-  load8(b + r * b_ld + b_coff + c, y);
+  const int cg = C / 8, rpb = blockDim.x / cg;
+  const int gi = threadIdx.x % cg, ri = threadIdx.x / cg;
+  if (ri >= rpb) return;
+  const int c = gi * 8;
+  float q1[8], q2[8], q3[8];
+  {
+    const float4 u0 = __ldg(reinterpret_cast<const float4*>(k1 + c)), u1 = __ldg(reinterpret_cast<const float4*>(k1 + c) + 1);
+    const float4 v0 = __ldg(reinterpret_cast<const float4*>(k2 + c)), v1 = __ldg(reinterpret_cast<const float4*>(k2 + c) + 1);
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(k3 + c)), w1 = __ldg(reinterpret_cast<const float4*>(k3 + c) + 1);
+    q1[0] = u0.x; q1[1] = u0.y; q1[2] = u0.z; q1[3] = u0.w; q1[4] = u1.x; q1[5] = u1.y; q1[6] = u1.z; q1[7] = u1.w;
+    q2[0] = v0.x; q2[1] = v0.y; q2[2] = v0.z; q2[3] = v0.w; q2[4] = v1.x; q2[5] = v1.y; q2[6] = v1.z; q2[7] = v1.w;
+    q3[0] = w0.x; q3[1] = w0.y; q3[2] = w0.z; q3[3] = w0.w; q3[4] = w1.x; q3[5] = w1.y; q3[6] = w1.z; q3[7] = w1.w;
+  }
+  const long step = (long)gridDim.x * rpb;
+  for (long r = (long)blockIdx.x * rpb + ri; r < rows; r += step) {
+    float x[8], y[8];
+    load8(a + r * a_ld + a_coff + c, x);
+    load8(b + r * b_ld + b_coff + c, y);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) x[j] = fmaf(__ldg(k1 + c + j), x[j], fmaf(__ldg(k2 + c + j), y[j], __ldg(k3 + c + j)));
-  store8(out + r * o_ld + o_coff + c, x);
+    for (int j = 0; j < 8; ++j) x[j] = fmaf(q1[j], x[j], fmaf(q2[j], y[j], q3[j]));
+    store8(out + r * o_ld + o_coff + c, x);
+  }
 }
 
 
@@ -918,7 +962,7 @@ extern "C" int dhd_occ_ce_loss(const float* logits, const uint8_t* labels, const
     gn = gt + 32;
     occ_scal_stats_kernel<<<sblocks, 256, 0, st>>>(logits, labels, mask, ncls, ignore_index, nvox, workspace);
     DHD_CUDA_LAUNCH_CHECK("occ_scal_stats");
-    occ_scal_coeffs_kernel<<<1, 32, 0, st>>>(workspace, sblocks, ncls, non_empty_idx, weight_sem, weight_geo, losses + 2,
+    occ_scal_coeffs_kernel<<<1, 1024, 0, st>>>(workspace, sblocks, ncls, non_empty_idx, weight_sem, weight_geo, losses + 2,
                                              gt, gn);
     DHD_CUDA_LAUNCH_CHECK("occ_scal_coeffs");
   }
@@ -1074,8 +1118,12 @@ extern "C" int dhd_affine_combine(const void* a, int a_ld, int a_coff, const voi
                                   void* stream) {
   DHD_REQUIRE(a && b && k1 && k2 && k3 && out && rows > 0 && C > 0, "bad arguments");
   DHD_REQUIRE(ok8(C, a_ld, a_coff, a) && ok8(C, b_ld, b_coff, b) && ok8(C, o_ld, o_coff, out), "C % 8, 16-byte aligned rows");
-  const long total = rows * (C / 8);
-  affine_combine_kernel<<<(int)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+  DHD_REQUIRE(C / 8 <= 256 && ((uintptr_t)k1 & 15) == 0 && ((uintptr_t)k2 & 15) == 0 && ((uintptr_t)k3 & 15) == 0,
+              "C <= 2048 and 16-byte aligned coefficient vectors");
+  const int rpb = 256 / (C / 8);
+  const long want = (rows + rpb - 1) / rpb;
+  const long cap = (long)sm_count() * 16;
+  affine_combine_kernel<<<(int)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)a, a_ld, a_coff, (const __nv_bfloat16*)b, b_ld, b_coff, rows, C, k1, k2, k3,
       (__nv_bfloat16*)out, o_ld, o_coff);
   DHD_CUDA_LAUNCH_CHECK("affine_combine");
