@@ -261,7 +261,7 @@ def run_ours(args):
                  'trainable_params': ts.n_params,
                  'gradient_all_reduce_bytes': ts.n_params * 4,
                  'loss_height': float(ts.loss_height[0]),
-                 'what': 'forward + losses (occupancy CE + sem_scal + geo_scal, height BCE) + backward of depth_net, HeightNet, SFA and predictor '
+                 'what': 'GT binning of the sparse gt_depth / gt_height maps + forward + losses (occupancy CE + sem_scal + geo_scal, height BCE) + backward of depth_net, HeightNet, SFA and predictor '
                          '(BatchNorm2d in training mode: batch statistics, trainable affine; the ASPP Dropout(0.5) on), fused pool fwd+bwd, one NCCL all-reduce of the fp32 gradient bucket, AdamW, '
                          'bf16 weight re-pack; encoders stand in as resident tensors (see TrainStep)'}
         del ts

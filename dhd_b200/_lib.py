@@ -61,6 +61,7 @@ _SIGNATURES = {
     'dhd_dropout': (ctypes.c_int, [_P, _I, _I, ctypes.c_long, _I, ctypes.c_float, _P, ctypes.c_uint, _P]),
     'dhd_affine_combine': (ctypes.c_int, [_P, _I, _I, _P, _I, _I, ctypes.c_long, _I, _P, _P, _P, _P, _I, _I, _P]),
     'dhd_se_gate_bwd': (ctypes.c_int, [_P, _I, _I, _P, _I, _I, _I, _I, _I, _P, _P, _I, _I, _P, _P, _P]),
+    'dhd_gt_downsample': (ctypes.c_int, [_P, _I, _I, _I, _I, ctypes.c_float, ctypes.c_float, _I, _P, _P, _P]),
     'dhd_height_loss': (ctypes.c_int, [_P, _P, _P, _I, _I, _I, ctypes.c_float, _P, _P, _P, _I, _P]),
     'dhd_dcn_col2im_bwd': (ctypes.c_int, [_P, _I, _P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _P, _P, _P]),
     'dhd_occ_loss_workspace_bytes': (ctypes.c_size_t, []),

@@ -898,6 +898,40 @@ dropout_kernel(__nv_bfloat16* __restrict__ x, int ld, int coff, long rows, int C
   store8(p, f);
 }
 
+
+// MGHS.get_downsampled_gt_depth / get_downsampled_gt_height (lss_heightmap.py:625-701): ds x ds min-pool of a sparse
+// LiDAR map with zeros ignored (the reference's 1e5 sentinel), then t = (min - lo) / interval as two separately
+// rounded fp32 operations, bins outside [0, nbins + 1) -> 0, .long() truncation; the reference's one-hot row
+// one_hot(t, nbins + 1)[1:] is returned as its index: label = t - 1 (-1 = all-zero row), valid = label >= 0.
+// One warp per output pixel.
+__global__ void __launch_bounds__(256)
+gt_downsample_kernel(const float* __restrict__ gt, long nout, int H, int W, int ds, float lo, float interval, int nbins,
+                     int32_t* __restrict__ label, uint8_t* __restrict__ valid) {
+  const long o = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (o >= nout) return;
+  const int oW = W / ds, oH = H / ds;
+  const int ox = (int)(o % oW);
+  const long t0 = o / oW;
+  const int oy = (int)(t0 % oH);
+  const long img = t0 / oH;
+  const float* base = gt + (img * H + (long)oy * ds) * W + (long)ox * ds;
+  float m = 1e5f;
+  for (int e = lane; e < ds * ds; e += 32) {
+    const float v = __ldg(base + (long)(e / ds) * W + (e % ds));
+    m = fminf(m, v == 0.f ? 1e5f : v);
+  }
+#pragma unroll
+  for (int k = 16; k > 0; k >>= 1) m = fminf(m, __shfl_xor_sync(kFull, m, k));
+  if (lane == 0) {
+    float t = __fdiv_rn(__fsub_rn(m, lo), interval);
+    if (!(t < (float)(nbins + 1) && t >= 0.f)) t = 0.f;
+    const int bin = (int)t - 1;
+    label[o] = bin;
+    if (valid != nullptr) valid[o] = bin >= 0 ? 1 : 0;
+  }
+}
+
 }  // namespace dhd
 
 using namespace dhd;
@@ -1162,5 +1196,16 @@ extern "C" int dhd_dropout(void* x, int ld, int coff, long rows, int C, float p,
   dropout_kernel<<<(unsigned)((vecs + 255) / 256), 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)x, ld, coff, rows, C, thresh,
                                                                                  1.f / (1.f - p), rng, salt);
   DHD_CUDA_LAUNCH_CHECK("dropout");
+  return DHD_OK;
+}
+
+extern "C" int dhd_gt_downsample(const float* gt, int BN, int H, int W, int ds, float lo, float interval, int nbins,
+                                 int32_t* label, uint8_t* valid, void* stream) {
+  DHD_REQUIRE(gt && label && BN > 0 && H > 0 && W > 0 && nbins > 0, "bad arguments");
+  DHD_REQUIRE(ds > 0 && H % ds == 0 && W % ds == 0, "the map must be a whole number of ds x ds blocks");
+  const long nout = (long)BN * (H / ds) * (W / ds);
+  gt_downsample_kernel<<<(unsigned)((nout * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(gt, nout, H, W, ds, lo, interval,
+                                                                                         nbins, label, valid);
+  DHD_CUDA_LAUNCH_CHECK("gt_downsample");
   return DHD_OK;
 }

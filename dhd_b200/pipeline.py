@@ -456,9 +456,19 @@ class TrainStep(HotPathStep):
         self.mask_camera = (torch.rand(B, self.Dx, self.Dy, 16, device=self.device, generator=gen) < 0.5).to(torch.uint8)
         for g in self.gouts:
             g.mul_(1e-3)
-        npix = B * self.N * self.fH * self.fW             # binned LiDAR supervision (synthetic): height bin, fg flag
-        self.height_label = torch.randint(-1, 65, (npix,), device=self.device, generator=gen).int()
-        self.height_fg = (torch.rand(npix, device=self.device, generator=gen) < 0.3).to(torch.uint8)
+        # LiDAR supervision as the reference receives it (gt_depth / gt_height, DHD-S.py Collect3D keys): sparse
+        # (B, N, H_in, W_in) maps, ~2 % of the pixels carry a return; the step bins them itself (dhd_gt_downsample =
+        # get_downsampled_gt_depth / _height, lss_heightmap.py:625-701)
+        h_in, w_in = cfg['input_size']
+        hit = torch.rand(B, self.N, h_in, w_in, device=self.device, generator=gen) < 0.02
+        self.gt_depth = torch.where(hit, 1.0 + 59.0 * torch.rand(B, self.N, h_in, w_in, device=self.device, generator=gen),
+                                    torch.zeros((), device=self.device))
+        self.gt_height = torch.where(hit, -2.0 + 8.0 * torch.rand(B, self.N, h_in, w_in, device=self.device, generator=gen),
+                                     torch.zeros((), device=self.device))
+        npix = B * self.N * self.fH * self.fW
+        self.height_label = torch.empty(npix, dtype=torch.int32, device=self.device)
+        self.depth_label = torch.empty(npix, dtype=torch.int32, device=self.device)
+        self.height_fg = torch.empty(npix, dtype=torch.uint8, device=self.device)
         self.n_params = self.bucket.flat.numel()
         self.loss = None
         T.set_bn_mode('frozen')
@@ -527,6 +537,14 @@ class TrainStep(HotPathStep):
                           deterministic=self.deterministic, workspace=self.workspace)
         self._last = {'depth': depth, 'feat': feat, 'height': height, 'pixmask': pixmask}
         self._pool()
+        # get_height_loss (lss_heightmap.py:595-622): labels from the height map, foreground = pixels whose depth
+        # return falls into a depth bin (binned with the depth config the module holds at loss time, the LH:455 quirk)
+        from . import train as T
+        dc = self.vt.mask_3_grid['depth']
+        T.gt_downsample(self.gt_depth, self.vt.downsample, dc[0] - dc[2], dc[2], self.vt.D, label=self.depth_label,
+                        valid=self.height_fg)
+        T.gt_downsample(self.gt_height, self.vt.downsample, self.vt.height_range[0], self.vt.height_interval, self.vt.H,
+                        label=self.height_label)
         self.loss_height = self.t_height.loss(self.height_label, self.height_fg)
         if self.encoders:
             if not hasattr(self, '_enc_act'):

@@ -468,6 +468,26 @@ class SFATrainer:
         return dx
 
 
+def gt_downsample(gt, ds, lo, interval, nbins, label=None, valid=None, want_valid=False):
+    """MGHS.get_downsampled_gt_depth / _height (lss_heightmap.py:625-701) as bin indices: gt (B, N, H, W) fp32 sparse
+    map -> label (B*N*H/ds*W/ds,) int32 in [-1, nbins) (the index of the reference's one-hot row, -1 = all zero) and,
+    with want_valid, the uint8 flag label >= 0.  depth: lo = d_min - d_step, interval = d_step; height: lo =
+    height_range[0], interval = height_interval."""
+    if not gt.is_cuda:
+        raise RuntimeError('dhd_b200: expected CUDA tensors (the hot path has no CPU fallback)')
+    gt = gt.float().contiguous()
+    H, W = gt.shape[-2:]
+    BN = gt.numel() // (H * W)
+    n = BN * (H // ds) * (W // ds)
+    if label is None:
+        label = torch.empty(n, dtype=torch.int32, device=gt.device)
+    if valid is None and want_valid:
+        valid = torch.empty(n, dtype=torch.uint8, device=gt.device)
+    _lib.check(_lib.load().dhd_gt_downsample(_p(gt), BN, H, W, int(ds), float(lo), float(interval), int(nbins), _p(label),
+                                             _p(valid), _stream()), 'gt_downsample')
+    return label, valid
+
+
 def dropout_(a, p, rng, salt=0):
     """In-place Dropout of an Act (bf16 part 0) with the counter-based mask of dhd_dropout."""
     _lib.check(_lib.load().dhd_dropout(_p(a.data), a.ld, a.coff, a.N * a.H * a.W, a.C, float(p), _p(rng), int(salt),

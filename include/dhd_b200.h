@@ -289,6 +289,13 @@ int dhd_add_rowvec(const float* in, const float* v, int N, int HW, int C, void* 
 int dhd_se_gate_bwd(const void* dh, int g_ld, int g_coff, const void* h, int h_ld, int h_coff, int C, int N,
                     int HW, const float* gate, void* dpre, int d_ld, int d_coff, float* gate_sums,
                     float* workspace, void* stream);
+/* MGHS.get_downsampled_gt_depth / get_downsampled_gt_height (lss_heightmap.py:625-701): gt (BN, H, W) sparse fp32 map
+ * -> per ds x ds block the minimum of the non-zero values, binned as (min - lo) / interval (depth: lo = d_min - d_step,
+ * interval = d_step; height: lo = height_range[0], interval = height_interval), label = bin - 1 in [-1, nbins)
+ * (-1: no valid return, the reference's all-zero one-hot row), valid (optional) = label >= 0 (the foreground test
+ * of get_height_loss when applied to the depth map). */
+int dhd_gt_downsample(const float* gt, int BN, int H, int W, int ds, float lo, float interval, int nbins,
+                      int32_t* label, uint8_t* valid, void* stream);
 /* MGHS.get_height_loss (lss_heightmap.py:595-622) on already binned labels: height (BN,H,HW) softmax
  * probabilities, label[pix] = GT height bin or -1 (all-zero one-hot row), fg[pix] = valid GT depth,
  * n_fg device scalar.  loss[0] = weight * sum_fg BCE / max(1, n_fg); dz = d loss / d logits (through

@@ -614,3 +614,40 @@ def test_sfa_backward_batch_statistics_bn(cuda_lib):
     # gout is random-sign, so every parameter gradient is a sqrt(N)-sized sum of N cancelling terms: a handful of ReLU
     # masks that flip under bf16 rounding (outputs within ~1e-2 of zero) already move it by 2-3 % (measured 1.4-3.0 %)
     assert max(errs.values()) < 4e-2, errs
+
+
+def test_gt_downsample_matches_the_plugin_restatement(cuda_lib):
+    """dhd_gt_downsample against MGHS.get_downsampled_gt_depth / _height (lss_heightmap.py:625-701; the plugin's torch
+    restatement is pinned to the reference's own functions by tests/test_dense_oracle.py): identical one-hot rows for
+    every pixel -- bit-exact bin indices, incl. empty blocks, out-of-range returns and values on bin edges."""
+    from dhd_b200 import synth
+    from dhd_b200.train import gt_downsample
+    from projects.mmdet3d_plugin.models.necks.lss_heightmap import MGHS
+    cfg = synth.DHD_S
+    g = cfg['mask_grids']
+    vt = MGHS(grid_config=dict(cfg['bev_grid'], depth=cfg['depth']), input_size=cfg['input_size'], in_channels=256,
+              out_channels=64, height_range=cfg['height_range'], height_interval=0.1, mask_range=cfg['mask_range'],
+              mask_1_grid=dict(g[0], depth=cfg['depth']), mask_2_grid=dict(g[1], depth=cfg['depth']),
+              mask_3_grid=dict(g[2], depth=[1.0, 45.0, 0.5]), downsample=16)
+    gen = torch.Generator().manual_seed(5)
+    B, N, H, W = 2, 6, 256, 704
+    hit = torch.rand(B, N, H, W, generator=gen) < 0.02
+    gt_d = torch.where(hit, 0.2 + 60.0 * torch.rand(B, N, H, W, generator=gen), torch.zeros(()))
+    gt_h = torch.where(hit, -2.0 + 8.5 * torch.rand(B, N, H, W, generator=gen), torch.zeros(()))
+    gt_d[0, 0, :16, :16] = 0.0                               # an empty block
+    gt_d[0, 0, 16:32, :16] = 0.0
+    gt_d[0, 0, 20, 3] = 7.5                                  # exactly on a bin edge
+    gt_h[0, 0, 16:32, :16] = 0.0
+    gt_h[0, 0, 20, 3] = 0.6
+    for depth_cfg in ([1.0, 45.0, 1.0], [1.0, 45.0, 0.5]):   # the config's own grid and the LH:455 leftover grid
+        vt.grid_config = dict(vt.grid_config, depth=depth_cfg)
+        want = vt.get_downsampled_gt_depth(gt_d)             # (npix, D) one-hot rows
+        lab, val = gt_downsample(gt_d.cuda(), 16, depth_cfg[0] - depth_cfg[2], depth_cfg[2], vt.D, want_valid=True)
+        ref_lab = torch.where(want.max(1).values > 0, want.argmax(1), torch.full((want.shape[0],), -1)).int()
+        assert torch.equal(lab.cpu(), ref_lab)
+        assert torch.equal(val.cpu().bool(), want.max(1).values > 0)
+        assert int((ref_lab >= 0).sum()) > 1000 and int((ref_lab < 0).sum()) > 10
+    want = vt.get_downsampled_gt_height(gt_h)
+    lab, _ = gt_downsample(gt_h.cuda(), 16, vt.height_range[0], vt.height_interval, vt.H)
+    ref_lab = torch.where(want.max(1).values > 0, want.argmax(1), torch.full((want.shape[0],), -1)).int()
+    assert torch.equal(lab.cpu(), ref_lab)
