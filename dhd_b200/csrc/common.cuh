@@ -52,6 +52,22 @@ __device__ __forceinline__ void st_cs(float* p, float v) {
   asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
 
+// a / b and a % b for a flat element index: 32-bit unsigned division whenever the index fits (a 64-bit division is
+// ~100 instructions, more than the rest of a streaming kernel's thread)
+__device__ __forceinline__ long fast_div(long a, int b, int* rem) {
+  if (a < (1L << 32)) {
+    const unsigned u = (unsigned)a, q = u / (unsigned)b;
+    *rem = (int)(u - q * (unsigned)b);
+    return (long)q;
+  }
+  *rem = (int)(a % b);
+  return a / b;
+}
+__device__ __forceinline__ long fast_div(long a, int b) {
+  int r;
+  return fast_div(a, b, &r);
+}
+
 inline int sm_count() {
   static int n = 0;
   if (n == 0) {

@@ -177,9 +177,10 @@ gate_channels_kernel(const float* __restrict__ x, int C, long npix_total, int HW
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const int cg = C / 8;
   if (i >= npix_total * cg) return;
-  const long pix = i / cg;
-  const int c = (int)(i % cg) * 8;
-  const int n = (int)(pix / HW);
+  int c;
+  const long pix = fast_div(i, cg, &c);
+  c *= 8;
+  const int n = (int)fast_div(pix, HW);
   const float4* xp = reinterpret_cast<const float4*>(x + (size_t)pix * C + c);
   const float4* gp = reinterpret_cast<const float4*>(gate + (size_t)n * C + c);
   const float4 a = __ldg(xp), b = __ldg(xp + 1), ga = __ldg(gp), gb = __ldg(gp + 1);
@@ -200,9 +201,10 @@ sfa_mix8_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int x_coff, int x
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const int cg = C / 8;
   if (i >= npix_total * cg) return;
-  const long pix = i / cg;
-  const int c = (int)(i % cg) * 8;
-  const int n = (int)(pix / HW);
+  int c;
+  const long pix = fast_div(i, cg, &c);
+  c *= 8;
+  const int n = (int)fast_div(pix, HW);
   float bev[8], vox[8], r[8];
   load_parts8(x + (size_t)pix * x_ld + x_coff + c, x_parts, x_ps, bev);
   load_parts8(x + (size_t)pix * x_ld + x_coff + C + c, x_parts, x_ps, vox);
@@ -231,12 +233,12 @@ dcn_im2col8_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int x_coff, in
                    int N, int H, int W, const float* __restrict__ offset, int off_ld, int ksize, int pad,
                    int dil, int groups, __nv_bfloat16* __restrict__ out, int o_ld, int o_ps, int o_parts) {
   const int lane = threadIdx.x & 31;
-  const long gw = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int taps = ksize * ksize;
-  if (gw >= (long)N * H * W * taps) return;
-  const int t = (int)(gw % taps);
-  const long pix = gw / taps;
-  const int wx = (int)(pix % W), hy = (int)((pix / W) % H), n = (int)(pix / ((long)W * H));
+  const int gw = (int)(((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);     // N*H*W*taps < 2^31 (host check):
+  const int taps = ksize * ksize;                                                // 32-bit index arithmetic throughout
+  if (gw >= N * H * W * taps) return;
+  const int t = gw % taps;
+  const int pix = gw / taps;
+  const int wx = pix % W, hy = (pix / W) % H, n = pix / (W * H);
   const float dy = __ldg(offset + (size_t)pix * off_ld + 2 * t), dx = __ldg(offset + (size_t)pix * off_ld + 2 * t + 1);
   const float sy = (float)(hy - pad + (t / ksize) * dil) + dy;
   const float sx = (float)(wx - pad + (t % ksize) * dil) + dx;
@@ -294,11 +296,11 @@ maxpool2_kernel(const __nv_bfloat16* __restrict__ in, int in_ld, int in_coff, in
   const int oH = H / 2, oW = W / 2, cg = C / 8;
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long)N * oH * oW * cg) return;
-  const int c = (int)(i % cg) * 8;
-  long p = i / cg;
-  const int ox = (int)(p % oW);
-  p /= oW;
-  const int oy = (int)(p % oH), n = (int)(p / oH);
+  int c, ox, oy;
+  long p = fast_div(i, cg, &c);
+  c *= 8;
+  p = fast_div(p, oW, &ox);
+  const int n = (int)fast_div(p, oH, &oy);
   float m[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
@@ -321,11 +323,11 @@ upsample_bilinear_kernel(const __nv_bfloat16* __restrict__ in, int in_ld, int in
   const int cg = C / 8;
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long)N * oH * oW * cg) return;
-  const int c = (int)(i % cg) * 8;
-  long p = i / cg;
-  const int ox = (int)(p % oW);
-  p /= oW;
-  const int oy = (int)(p % oH), n = (int)(p / oH);
+  int c, ox, oy;
+  long p = fast_div(i, cg, &c);
+  c *= 8;
+  p = fast_div(p, oW, &ox);
+  const int n = (int)fast_div(p, oH, &oy);
   // align_corners=True: src = dst * (in - 1) / (out - 1), torch's area_pixel_compute_source_index
   const float sy = oH > 1 ? (float)oy * ((float)(H - 1) / (float)(oH - 1)) : 0.f;
   const float sx = oW > 1 ? (float)ox * ((float)(W - 1) / (float)(oW - 1)) : 0.f;
@@ -353,11 +355,11 @@ maxpool2_bwd_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int x_coff, c
   const int oH = H / 2, oW = W / 2, cg = C / 8;
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long)N * H * W * cg) return;
-  const int c = (int)(i % cg) * 8;
-  long p = i / cg;
-  const int xx = (int)(p % W);
-  p /= W;
-  const int yy = (int)(p % H), n = (int)(p / H);
+  int c, xx, yy;
+  long p = fast_div(i, cg, &c);
+  c *= 8;
+  p = fast_div(p, W, &xx);
+  const int n = (int)fast_div(p, H, &yy);
   float r[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) r[j] = 0.f;
@@ -392,11 +394,11 @@ upsample_bilinear_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int dy_ld, in
   const int cg = C / 8;
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long)N * oH * oW * cg) return;
-  const int c = (int)(i % cg) * 8;
-  long p = i / cg;
-  const int ox = (int)(p % oW);
-  p /= oW;
-  const int oy = (int)(p % oH), n = (int)(p / oH);
+  int c, ox, oy;
+  long p = fast_div(i, cg, &c);
+  c *= 8;
+  p = fast_div(p, oW, &ox);
+  const int n = (int)fast_div(p, oH, &oy);
   const float sy = oH > 1 ? (float)oy * ((float)(H - 1) / (float)(oH - 1)) : 0.f;
   const float sx = oW > 1 ? (float)ox * ((float)(W - 1) / (float)(oW - 1)) : 0.f;
   const int y0 = (int)sy, x0 = (int)sx;
@@ -499,9 +501,10 @@ sfa_mix_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int x_coff, int x_
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;   // (pixel, channel pair)
   const int cp = C / 2;
   if (i >= npix_total * cp) return;
-  const long pix = i / cp;
-  const int c = (int)(i % cp) * 2;
-  const int n = (int)(pix / HW);
+  int c;
+  const long pix = fast_div(i, cp, &c);
+  c *= 2;
+  const int n = (int)fast_div(pix, HW);
   const __nv_bfloat16* xb = x + (size_t)pix * x_ld + x_coff + c;
   float r[2];
 #pragma unroll
@@ -763,6 +766,7 @@ extern "C" int dhd_dcn_im2col(const void* x, int x_ld, int x_coff, int x_part_st
   DHD_REQUIRE(C > 0 && groups > 0 && C % groups == 0 && (C / groups) % 2 == 0, "bad channel grouping");
   DHD_REQUIRE(N > 0 && H > 0 && W > 0 && ksize >= 1 && ksize <= 3, "bad shape");
   const long warps = (long)N * H * W * ksize * ksize;
+  DHD_REQUIRE(warps < (1L << 26), "too many sampling points for 32-bit indexing");
   if ((C / groups) % 8 == 0 && x_ld % 8 == 0 && x_coff % 8 == 0 && x_part_stride % 8 == 0 && o_ld % 8 == 0 &&
       o_part_stride % 8 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)out & 15) == 0) {
     dcn_im2col8_kernel<<<(int)((warps * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(

@@ -361,9 +361,10 @@ add_rowvec_kernel(const float* __restrict__ in, const float* __restrict__ v, lon
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const int cg = C / 8;
   if (i >= npix * cg) return;
-  const long pix = i / cg;
-  const int c = (int)(i % cg) * 8;
-  const int n = (int)(pix / HW);
+  int c;
+  const long pix = fast_div(i, cg, &c);
+  c *= 8;
+  const int n = (int)fast_div(pix, HW);
   const float4 a = *reinterpret_cast<const float4*>(in + pix * C + c), b = *reinterpret_cast<const float4*>(in + pix * C + c + 4);
   float r[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
   if (v != nullptr) {
@@ -468,12 +469,12 @@ dcn_col2im_bwd_kernel(const __nv_bfloat16* __restrict__ dcol, int c_ld, const __
                       int x_coff, int C, int N, int H, int W, const float* __restrict__ offset, int off_ld, int ksize,
                       int pad, int dil, int groups, float* __restrict__ dx, float* __restrict__ doff) {
   const int lane = threadIdx.x & 31;
-  const long gw = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int taps = ksize * ksize;
-  if (gw >= (long)N * H * W * taps) return;
-  const int t = (int)(gw % taps);
-  const long pix = gw / taps;
-  const int wx = (int)(pix % W), hy = (int)((pix / W) % H), n = (int)(pix / ((long)W * H));
+  const int gw = (int)(((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);     // N*H*W*taps < 2^31 (host check):
+  const int taps = ksize * ksize;                                                // 32-bit index arithmetic throughout
+  if (gw >= N * H * W * taps) return;
+  const int t = gw % taps;
+  const int pix = gw / taps;
+  const int wx = pix % W, hy = (pix / W) % H, n = pix / (W * H);
   const float oy = __ldg(offset + (size_t)pix * off_ld + 2 * t), ox = __ldg(offset + (size_t)pix * off_ld + 2 * t + 1);
   const float sy = (float)(hy - pad + (t / ksize) * dil) + oy;
   const float sx = (float)(wx - pad + (t % ksize) * dil) + ox;
@@ -754,8 +755,9 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ raw, int r_ld, int r_coff, lon
   const int cg = C / 8;
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * cg) return;
-  const long r = i / cg;
-  const int c = (int)(i % cg) * 8;
+  int c;
+  const long r = fast_div(i, cg, &c);
+  c *= 8;
   float v[8];
   load8(raw + r * r_ld + r_coff + c, v);
   const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + c)), s1 = __ldg(reinterpret_cast<const float4*>(scale + c) + 1);
@@ -775,7 +777,7 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ raw, int r_ld, int r_coff, lon
     else if (act == 2) v[j] = __fdividef(1.f, 1.f + __expf(-v[j]));
   }
   if (gate != nullptr) {
-    const float* g = gate + (r / rows_per_img) * C + c;
+    const float* g = gate + fast_div(r, rows_per_img) * C + c;
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] *= __ldg(g + j);
   }
@@ -881,8 +883,9 @@ dropout_kernel(__nv_bfloat16* __restrict__ x, int ld, int coff, long rows, int C
   const int vec_per_row = C >> 3;
   const long v = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= rows * vec_per_row) return;
-  const long r = v / vec_per_row;
-  const int c = (int)(v - r * vec_per_row) << 3;
+  int c;
+  const long r = fast_div(v, vec_per_row, &c);
+  c <<= 3;
   const unsigned long long seed = (unsigned long long)rng[0], step = (unsigned long long)rng[1];
   const uint4 rnd = philox4x32_10(make_uint4((uint32_t)v, (uint32_t)((unsigned long long)v >> 32), (uint32_t)step, salt),
                                   make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
@@ -1105,6 +1108,7 @@ extern "C" int dhd_dcn_col2im_bwd(const void* dcol, int col_ld, const void* x, i
   cudaError_t e = cudaMemsetAsync(dx, 0, (size_t)N * H * W * C * sizeof(float), st);
   if (e != cudaSuccess) return fail((int)e, "%s: %ld", "memset(dx)", (long)e);
   const long warps = (long)N * H * W * ksize * ksize;
+  DHD_REQUIRE(warps < (1L << 26), "too many sampling points for 32-bit indexing");
   dcn_col2im_bwd_kernel<<<(int)((warps * 32 + 255) / 256), 256, 0, st>>>(
       (const __nv_bfloat16*)dcol, col_ld, (const __nv_bfloat16*)x, x_ld, x_coff, C, N, H, W, offset, off_ld, ksize, pad,
       dilation, groups, dx, doff);

@@ -488,6 +488,33 @@ def gt_downsample(gt, ds, lo, interval, nbins, label=None, valid=None, want_vali
     return label, valid
 
 
+def lidar_losses(vt, gt_depth, gt_height, depth=None, height=None):
+    """MGHS.get_height_loss (lss_heightmap.py:595-622) and MGHS_Depth.get_depth_and_height_loss (859-897) on the CUDA
+    kernels: the sparse gt maps are binned by dhd_gt_downsample (foreground = pixels whose depth return lands in a
+    depth bin of vt.grid_config['depth'], the config the module holds at loss time), then one dhd_height_loss launch per
+    distribution gives weight * sum_fg BCE / max(1, n_fg) and its gradient at the logits (through the softmax).
+    depth / height: softmax probabilities (B*N, bins, fH, fW) fp32, either may be None.
+    Returns {'depth': (loss (1,), dz Act), 'height': (loss, dz Act)} for the ones given."""
+    dc = vt.grid_config['depth']
+    dlab, fg = gt_downsample(gt_depth, vt.downsample, dc[0] - dc[2], dc[2], vt.D, want_valid=True)
+    hlab, _ = gt_downsample(gt_height, vt.downsample, vt.height_range[0], vt.height_interval, vt.H)
+    nfg = fg.sum().float().reshape(1)
+    out = {}
+    for name, probs, lab, w in (('depth', depth, dlab, getattr(vt, 'loss_depth_weight', 0.0)),
+                                ('height', height, hlab, vt.loss_height_weight)):
+        if probs is None:
+            continue
+        if not probs.is_cuda or probs.dtype != torch.float32:
+            raise RuntimeError('dhd_b200: expected fp32 CUDA probabilities (the hot path has no CPU fallback)')
+        N, K, H, W = probs.shape
+        dz = D.Act.empty(N, H, W, (K + 63) // 64 * 64, 1, probs.device)
+        res = torch.empty(1, device=probs.device)
+        _lib.check(_lib.load().dhd_height_loss(_p(probs.contiguous()), _p(lab), _p(fg), N, K, H * W, float(w), _p(nfg),
+                                               _p(res), _p(dz.data), dz.ld, _stream()), 'height_loss')
+        out[name] = (res, dz)
+    return out
+
+
 def dropout_(a, p, rng, salt=0):
     """In-place Dropout of an Act (bf16 part 0) with the counter-based mask of dhd_dropout."""
     _lib.check(_lib.load().dhd_dropout(_p(a.data), a.ld, a.coff, a.N * a.H * a.W, a.C, float(p), _p(rng), int(salt),

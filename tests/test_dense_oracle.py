@@ -272,3 +272,27 @@ def test_stereo_host_side_refuses_cpu_tensors():
     with pytest.raises(RuntimeError, match='CUDA'):
         S.camera_table(torch.eye(4).view(1, 1, 4, 4), torch.eye(3).view(1, 1, 3, 3), torch.eye(3).view(1, 1, 3, 3),
                        torch.zeros(1, 1, 3))
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason='reference tree not present')
+def test_plugin_depth_and_height_loss_equals_the_reference():
+    """MGHS_Depth.get_depth_and_height_loss (LH:859-897) and the GT down-sampling it uses: plugin == unmodified reference
+    on the same sparse maps (this is what the CUDA loss kernels are then compared with on the GPU)."""
+    from dhd_b200 import synth
+    import projects.mmdet3d_plugin.models.necks.lss_heightmap as LH
+    ns = ref_loader.load_reference()
+    kw = dict(synth.DHD_L_VIEW_TRANSFORMER, in_channels=64)
+    kw['depthnet_cfg'] = dict(use_dcn=False, aspp_mid_channels=32, stereo=True, bias=5.)
+    kw['heightnet_cfg'] = dict(use_dcn=False, aspp_mid_channels=32)
+    ours, ref = LH.MGHS_Stereo(**kw), ns.MGHS_Stereo(**kw)
+    g = torch.Generator().manual_seed(2)
+    B, N, H, W = 1, 6, 512, 1408
+    hit = torch.rand(B, N, H, W, generator=g) < 0.02
+    gt_d = torch.where(hit, 0.2 + 60.0 * torch.rand(B, N, H, W, generator=g), torch.zeros(()))
+    gt_h = torch.where(hit, -2.0 + 8.5 * torch.rand(B, N, H, W, generator=g), torch.zeros(()))
+    assert torch.equal(ours.get_downsampled_gt_depth(gt_d), ref.get_downsampled_gt_depth(gt_d))
+    assert torch.equal(ours.get_downsampled_gt_height(gt_h), ref.get_downsampled_gt_height(gt_h))
+    d = torch.randn(B * N, ours.D, 32, 88, generator=g).softmax(1)
+    h = torch.randn(B * N, ours.H, 32, 88, generator=g).softmax(1)
+    for a, b in zip(ours.get_depth_and_height_loss(gt_d, gt_h, d, h), ref.get_depth_and_height_loss(gt_d, gt_h, d, h)):
+        assert torch.allclose(a, b, rtol=1e-6)

@@ -651,3 +651,35 @@ def test_gt_downsample_matches_the_plugin_restatement(cuda_lib):
     lab, _ = gt_downsample(gt_h.cuda(), 16, vt.height_range[0], vt.height_interval, vt.H)
     ref_lab = torch.where(want.max(1).values > 0, want.argmax(1), torch.full((want.shape[0],), -1)).int()
     assert torch.equal(lab.cpu(), ref_lab)
+
+
+def test_depth_and_height_loss_kernels_match_the_plugin_restatement(cuda_lib):
+    """train.lidar_losses (dhd_gt_downsample + dhd_height_loss) against MGHS_Depth.get_depth_and_height_loss
+    (lss_heightmap.py:859-897; the plugin's torch form is pinned to the reference's on the CPU): both loss values and
+    the gradients at the depth / height logits from autograd through the softmax."""
+    from dhd_b200.train import lidar_losses
+    from projects.mmdet3d_plugin.models.necks.lss_heightmap import MGHS_Depth
+    grids = {k: {'x': [-40, 40, 0.4], 'y': [-40, 40, 0.4], 'z': z, 'depth': [1.0, 45.0, 0.5]}
+             for k, z in (('mask_1_grid', [-1, 0.6, 0.4]), ('mask_2_grid', [0.6, 2.2, 0.4]), ('mask_3_grid', [2.2, 5.4, 0.4]))}
+    vt = MGHS_Depth(grid_config={'x': [-40, 40, 0.4], 'y': [-40, 40, 0.4], 'z': [-1, 5.4, 6.4], 'depth': [1.0, 45.0, 0.5]},
+                    input_size=(256, 704), in_channels=64, out_channels=64, height_range=[round(-1.0 + 0.1 * i, 1) for i in range(65)],
+                    height_interval=0.1, mask_range=[-1.0, 0.6, 2.2, 5.4], collapse_z=False, loss_height_weight=0.1,
+                    loss_depth_weight=0.05, depthnet_cfg=dict(use_dcn=False, aspp_mid_channels=32),
+                    heightnet_cfg=dict(use_dcn=False, aspp_mid_channels=32), downsample=16, **grids)
+    gen = torch.Generator().manual_seed(8)
+    B, N, H, W = 2, 6, 256, 704
+    hit = torch.rand(B, N, H, W, generator=gen) < 0.02
+    gt_d = torch.where(hit, 0.2 + 60.0 * torch.rand(B, N, H, W, generator=gen), torch.zeros(())).cuda()
+    gt_h = torch.where(hit, -2.0 + 8.5 * torch.rand(B, N, H, W, generator=gen), torch.zeros(())).cuda()
+    zd = torch.randn(B * N, vt.D, 16, 44, generator=gen).cuda().requires_grad_()
+    zh = torch.randn(B * N, vt.H, 16, 44, generator=gen).cuda().requires_grad_()
+    ld, lh = vt.get_depth_and_height_loss(gt_d, gt_h, zd.softmax(1), zh.softmax(1))
+    (ld + lh).backward()
+    got = lidar_losses(vt, gt_d, gt_h, depth=zd.detach().softmax(1), height=zh.detach().softmax(1))
+    torch.cuda.synchronize()
+    assert abs(float(got['depth'][0]) - float(ld)) <= 2e-4 * float(ld), (float(got['depth'][0]), float(ld))
+    assert abs(float(got['height'][0]) - float(lh)) <= 2e-4 * float(lh), (float(got['height'][0]), float(lh))
+    for (res, dz), z, K in ((got['depth'], zd, vt.D), (got['height'], zh, vt.H)):
+        g = dz.float()                                         # (BN, Kpad, fH, fW)
+        assert float(g[:, K:].abs().max()) == 0.0
+        assert rel(g[:, :K], z.grad.cpu()) < 5e-3              # bf16 storage of the gradient
