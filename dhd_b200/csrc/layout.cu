@@ -9,6 +9,8 @@
 // All are pure streaming kernels: every byte is read once / written once, coalesced.
 #include <cuda_bf16.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace dhd {
@@ -284,6 +286,74 @@ dcn_im2col8_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int x_coff, in
     }
     const int g = c / cg, cl = c % cg;
     store_parts8(out + (size_t)pix * o_ld + (size_t)g * taps * cg + (size_t)t * cg + cl, v, o_parts, o_ps);
+  }
+}
+
+// Same result, one warp per PIXEL: lane t < taps computes tap t's sampling position, bilinear weights and corner
+// offsets once; the warp then walks the taps with the parameters handed round by shuffle and the lanes over the
+// channels.  The per-(pixel, tap) kernel above spends ~400 instructions of index arithmetic per 16 bytes of payload;
+// here that arithmetic is paid once per pixel.
+__global__ void __launch_bounds__(256)
+dcn_im2col_px_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int x_coff, int x_ps, int x_parts, int C,
+                     int N, int H, int W, const float* __restrict__ offset, int off_ld, int ksize, int pad,
+                     int dil, int groups, __nv_bfloat16* __restrict__ out, int o_ld, int o_ps, int o_parts) {
+  const int lane = threadIdx.x & 31;
+  const int pix = (int)(((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (pix >= N * H * W) return;
+  const int taps = ksize * ksize;
+  const int wx = pix % W, hy = (pix / W) % H, n = pix / (W * H);
+  float w00 = 0.f, w01 = 0.f, w10 = 0.f, w11 = 0.f;
+  int o00 = -1, o01 = -1, o10 = -1, o11 = -1;           // pixel index of each corner inside the image, -1 = outside
+  if (lane < taps) {
+    const int t = lane;
+    const float dy = __ldg(offset + (size_t)pix * off_ld + 2 * t), dx = __ldg(offset + (size_t)pix * off_ld + 2 * t + 1);
+    const float sy = (float)(hy - pad + (t / ksize) * dil) + dy;
+    const float sx = (float)(wx - pad + (t % ksize) * dil) + dx;
+    if (sy > -1.f && sx > -1.f && sy < (float)H && sx < (float)W) {
+      const int y0 = (int)floorf(sy), x0 = (int)floorf(sx), y1 = y0 + 1, x1 = x0 + 1;
+      const float ly = sy - (float)y0, lx = sx - (float)x0, hy_ = 1.f - ly, hx_ = 1.f - lx;
+      w00 = hy_ * hx_; w01 = hy_ * lx; w10 = ly * hx_; w11 = ly * lx;
+      if (y0 >= 0 && x0 >= 0) o00 = y0 * W + x0;
+      if (y0 >= 0 && x1 <= W - 1) o01 = y0 * W + x1;
+      if (y1 <= H - 1 && x0 >= 0) o10 = y1 * W + x0;
+      if (y1 <= H - 1 && x1 <= W - 1) o11 = y1 * W + x1;
+    }
+  }
+  const int cg = C / groups;
+  const __nv_bfloat16* img = x + (size_t)n * H * W * x_ld + x_coff;
+  __nv_bfloat16* orow = out + (size_t)pix * o_ld;
+  for (int t = 0; t < taps; ++t) {
+    const float a00 = __shfl_sync(kFull, w00, t), a01 = __shfl_sync(kFull, w01, t);
+    const float a10 = __shfl_sync(kFull, w10, t), a11 = __shfl_sync(kFull, w11, t);
+    const int p00 = __shfl_sync(kFull, o00, t), p01 = __shfl_sync(kFull, o01, t);
+    const int p10 = __shfl_sync(kFull, o10, t), p11 = __shfl_sync(kFull, o11, t);
+    for (int c = 8 * lane; c < C; c += 256) {
+      float v[8], q[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = 0.f;
+      if (p00 >= 0) {
+        load_parts8(img + (size_t)p00 * x_ld + c, x_parts, x_ps, q);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = a00 * q[j];
+      }
+      if (p01 >= 0) {
+        load_parts8(img + (size_t)p01 * x_ld + c, x_parts, x_ps, q);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += a01 * q[j];
+      }
+      if (p10 >= 0) {
+        load_parts8(img + (size_t)p10 * x_ld + c, x_parts, x_ps, q);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += a10 * q[j];
+      }
+      if (p11 >= 0) {
+        load_parts8(img + (size_t)p11 * x_ld + c, x_parts, x_ps, q);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += a11 * q[j];
+      }
+      const int g = c / cg, cl = c - g * cg;
+      store_parts8(orow + (size_t)g * taps * cg + (size_t)t * cg + cl, v, o_parts, o_ps);
+    }
   }
 }
 
@@ -769,10 +839,22 @@ extern "C" int dhd_dcn_im2col(const void* x, int x_ld, int x_coff, int x_part_st
   DHD_REQUIRE(warps < (1L << 26), "too many sampling points for 32-bit indexing");
   if ((C / groups) % 8 == 0 && x_ld % 8 == 0 && x_coff % 8 == 0 && x_part_stride % 8 == 0 && o_ld % 8 == 0 &&
       o_part_stride % 8 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)out & 15) == 0) {
-    dcn_im2col8_kernel<<<(int)((warps * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+    static const bool per_tap = [] {                    // DHD_DCN_IM2COL=tap: the earlier warp-per-(pixel, tap) kernel (A/B)
+      const char* e = getenv("DHD_DCN_IM2COL");
+      return e != nullptr && e[0] == 't';
+    }();
+    if (per_tap) {
+      dcn_im2col8_kernel<<<(int)((warps * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+          (const __nv_bfloat16*)x, x_ld, x_coff, x_part_stride, x_parts, C, N, H, W, offset, off_ld, ksize, pad,
+          dilation, groups, (__nv_bfloat16*)out, o_ld, o_part_stride, o_parts);
+      DHD_CUDA_LAUNCH_CHECK("dcn_im2col8");
+      return DHD_OK;
+    }
+    const long pixels = (long)N * H * W;
+    dcn_im2col_px_kernel<<<(int)((pixels * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)x, x_ld, x_coff, x_part_stride, x_parts, C, N, H, W, offset, off_ld, ksize, pad,
         dilation, groups, (__nv_bfloat16*)out, o_ld, o_part_stride, o_parts);
-    DHD_CUDA_LAUNCH_CHECK("dcn_im2col8");
+    DHD_CUDA_LAUNCH_CHECK("dcn_im2col_px");
     return DHD_OK;
   }
   dcn_im2col_kernel<<<(int)((warps * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(

@@ -359,6 +359,46 @@ def test_dcn_sampling_backward_unit(cuda_lib):
     assert rel(doff, offr.grad) < 1e-4
 
 
+@pytest.mark.parametrize('parts', [1, 3])
+def test_dcn_im2col_forward_unit(cuda_lib, parts):
+    """dhd_dcn_im2col (warp per pixel, taps walked by shuffle) against the same bilinear sampling written with
+    F.grid_sample (align_corners=True, zero padding == mmcv / torchvision deformable im2col): offsets up to +-5 pixels,
+    so samples fall outside on every border; column layout [pix][group][tap][channel]."""
+    import ctypes
+    import torch.nn.functional as F
+    from dhd_b200 import _lib, dense as D
+    lib = _lib.load()
+    N, C, H, W, k, pad, dil, groups = 2, 256, 16, 44, 3, 1, 1, 4
+    cg, taps = C // groups, k * k
+    g = torch.Generator().manual_seed(13)
+    x = torch.randn(N, C, H, W, generator=g)
+    if parts == 1:
+        x = x.bfloat16().float()
+    off = torch.randn(N, H, W, 2 * taps, generator=g) * 2.5
+    ys = torch.arange(H).view(1, H, 1).float()
+    xs = torch.arange(W).view(1, 1, W).float()
+    want = torch.empty(N, H, W, groups, taps, cg)
+    for t in range(taps):
+        sy = ys - pad + (t // k) * dil + off[..., 2 * t]
+        sx = xs - pad + (t % k) * dil + off[..., 2 * t + 1]
+        grid = torch.stack((2 * sx / (W - 1) - 1, 2 * sy / (H - 1) - 1), -1)
+        samp = F.grid_sample(x, grid, mode='bilinear', padding_mode='zeros', align_corners=True)      # (N, C, H, W)
+        want[:, :, :, :, t] = samp.permute(0, 2, 3, 1).reshape(N, H, W, groups, cg)
+    xa = D.pack_input(x.cuda(), parts)
+    col = D.Act.empty(N, H, W, taps * C, parts, 'cuda')
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    _lib.check(lib.dhd_dcn_im2col(p(xa.data), xa.ld, xa.coff, xa.part_stride, xa.parts, C, N, H, W, p(off.cuda().contiguous()),
+                                  2 * taps, k, pad, dil, groups, p(col.data), col.ld, col.part_stride, col.parts,
+                                  ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), 'dcn_im2col')
+    torch.cuda.synchronize()
+    got = col.float().permute(0, 2, 3, 1).cpu()                  # (N, H, W, taps * C)
+    want = want.reshape(N, H, W, taps * C)
+    err = (got - want).abs().max().item()
+    # 1 part: the column is stored in bf16 (2^-9 relative); 3 parts carry the fp32 value
+    assert err <= (2e-2 if parts == 1 else 2e-5), err
+    assert (want == 0).float().mean() > 0.02                     # some samples did fall outside
+
+
 def _shim_oracle_call(fn, *a, **k):
     """Run an oracle.dense_oracle function with bf16 straight-through rounding after every ReLU."""
     from oracle import dense_oracle as DO
