@@ -1,3 +1,3 @@
-from .DHD_model import DHD
+from .DHD_model import DHD, DHD_stereo
 
-__all__ = ['DHD']
+__all__ = ['DHD', 'DHD_stereo']

@@ -296,3 +296,60 @@ def test_plugin_depth_and_height_loss_equals_the_reference():
     h = torch.randn(B * N, ours.H, 32, 88, generator=g).softmax(1)
     for a, b in zip(ours.get_depth_and_height_loss(gt_d, gt_h, d, h), ref.get_depth_and_height_loss(gt_d, gt_h, d, h)):
         assert torch.allclose(a, b, rtol=1e-6)
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason='reference tree not present')
+@pytest.mark.parametrize('name', ['DHD-M.py', 'DHD-L.py'])
+def test_stereo_configs_build_the_hot_path_modules(name):
+    """projects/configs/DHD/DHD-M.py / DHD-L.py, unchanged, through build_model: the DHD_stereo shell with the view
+    transformer (MGHS_Stereo + stereo DepthNet), both pre-process nets, the BEV / voxel encoders, SFA and the head,
+    under the reference's child names."""
+    import projects.mmdet3d_plugin  # noqa: F401
+    from dhd_b200 import compat as C
+    cfg = C.Config.fromfile(os.path.join(ref_loader.load_reference_configs(), name))
+    model = C.build_model(cfg.model)
+    assert type(model).__name__ == 'DHD_stereo'
+    vt = model.img_view_transformer
+    assert type(vt).__name__ == 'MGHS_Stereo' and vt.depth_net.stereo and vt.D == 88 and vt.H == 65
+    assert model.num_frame == 3 and model.temporal_frame == 2 and model.extra_ref_frames == 1
+    names = [n for n, _ in model.named_children()]
+    for want in ('img_view_transformer', 'img_bev_encoder_backbone', 'img_bev_encoder_neck', 'pre_process_net',
+                 'pre_process_net_3d', 'img_voxel_encoder0', 'img_voxel_neck0', 'img_voxel_encoder1', 'img_voxel_encoder2',
+                 'mix', 'occ_head'):
+        assert want in names and getattr(model, want) is not None, want
+    sd = model.state_dict()
+    for key in ('pre_process_net.layers.0.0.conv1.weight', 'pre_process_net_3d.layers.0.0.downsample.weight',
+                'img_view_transformer.depth_net.cost_volumn_net.0.weight', 'img_voxel_encoder2.inc.double_conv.0.weight',
+                'mix.mysk_7.fc.0.weight', 'occ_head.final_conv.conv.weight'):
+        assert key in sd, key
+    assert sd['pre_process_net_3d.layers.0.0.conv1.weight'].shape[:2] == (1024, 1024)
+    # the bev encoder sees both temporal frames on the channel axis (DHD_model.py:517)
+    first = 'img_bev_encoder_backbone.' + ('layers.0.0.conv1.weight' if name == 'DHD-L.py' else 'inc.double_conv.0.weight')
+    assert sd[first].shape[1] == 64 * 2            # CustomResNet in DHD-L, a UNet in DHD-M
+
+
+def test_stereo_detector_frame_fusion_glue():
+    """DHD_stereo.fuse_frames / pre-process restore (DHD_model.py:358-368, 517-541) with stand-in children: channel
+    order of the collapsed z axis, the 4 / 4 / 8 plane split, and that chunk + stack undoes the collapse."""
+    from projects.mmdet3d_plugin.models.detectors.DHD_model import DHD_stereo
+    m = DHD_stereo.__new__(DHD_stereo)
+    torch.nn.Module.__init__(m)
+    seen = {}
+    m._encode = lambda backbone, neck, x: x
+    m.img_bev_encoder_backbone = m.img_bev_encoder_neck = None
+    m.bev_encoder = lambda x: seen.setdefault('bev', x)
+    m.voxel_encoder = lambda i, x: seen.setdefault('vox%d' % i, x)
+    g = torch.Generator().manual_seed(0)
+    B, C, Dy, Dx = 2, 3, 5, 4
+    f2 = [torch.randn(B, C, 1, Dy, Dx, generator=g) for _ in range(2)]
+    f3 = [torch.randn(B, C, 16, Dy, Dx, generator=g) for _ in range(2)]
+    x_2d, x_3d = m.fuse_frames(f2, f3)
+    cat3 = torch.cat(f3, dim=1)                                        # (B, 2C, 16, Dy, Dx)
+    assert torch.equal(x_2d, torch.cat(f2, dim=1)[:, :, 0])
+    want0 = torch.cat([cat3[:, :, z] for z in range(0, 4)], dim=1)
+    want2 = torch.cat([cat3[:, :, z] for z in range(8, 16)], dim=1)
+    assert torch.equal(seen['vox0'], want0) and torch.equal(seen['vox2'], want2)
+    assert x_3d.shape == (B, 2 * C * 16, Dy, Dx) and torch.equal(x_3d[:, :2 * C * 4], want0)
+    col = DHD_stereo._collapse_z(f3[0])                                # channel = z * C + c
+    assert torch.equal(col[:, 5 * C + 1], f3[0][:, 1, 5])
+    assert torch.equal(torch.stack(torch.chunk(col, 16, dim=1), dim=2), f3[0])

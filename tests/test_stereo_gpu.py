@@ -218,3 +218,15 @@ def test_mghs_stereo_dhdl_full_size(cuda_lib):
     assert torch.isfinite(bev).all() and torch.isfinite(bev_z).all() and float(bev.abs().sum()) > 0
     close(depth, want_depth, 'DHD-L stereo depth distribution', 1e-4, 1e-3)
     close(height, h, 'DHD-L height distribution', 1e-4, 1e-3)
+
+
+def test_dhd_stereo_detector_end_to_end(cuda_lib):
+    """The DHD_stereo shell with the DHD-L wiring (key + previous frame + stereo reference frame, both pre-process
+    nets, CustomResNet + FPN_LSS and three UNets at the DHD-L widths, SFA, predictor) from per-frame image features
+    to occupancy classes, at a reduced image size: shapes, finiteness, a non-degenerate class map."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'scripts'))
+    import run_dhd_stereo
+    res = run_dhd_stereo.run()
+    assert res['occ'] == [1, 200, 200, 16, 18] and res['depth'] == [6, 88, 4, 11] and res['height'] == [6, 65, 4, 11]
+    assert res['finite'] and res['occ_abs_mean'] > 0 and res['classes_found'] > 1
