@@ -55,6 +55,26 @@ class predictor(BaseModule):
                 self._engine = PredictorEngine(self, self.precision, img_feats.data.device)
             return self._engine(img_feats)
 
+    def loss(self, occ_pred, voxel_semantics, mask_camera):
+        """occ_head.py:102-139: class-weighted masked cross-entropy + sem_scal + geo_scal (free class = 17), as a dict
+        of differentiable torch scalars (works on any device).  The training engine of this package computes the same
+        three terms and their gradient at the logits in one kernel pass (dhd_b200.train.PredictorTrainer.loss)."""
+        from ..losses import geo_scal_loss_with_mask, sem_scal_loss_with_mask
+        if not (self.use_mask and self.class_balance):
+            raise NotImplementedError       # as the reference (occ_head.py:133-134)
+        if self.loss_occ is None:
+            raise RuntimeError('predictor.loss needs loss_occ (e.g. dict(type="CrossEntropyLoss", ...))')
+        labels = voxel_semantics.long().reshape(-1)
+        preds = occ_pred.reshape(-1, self.num_classes)
+        mask = mask_camera.to(torch.int32).reshape(-1)
+        cw = self.cls_weights.to(preds.device)
+        valid = labels[mask.bool()]
+        valid = valid[valid < self.num_classes]
+        avg_factor = cw[valid].sum()                 # sum_i count(valid == i) * cls_weights[i], occ_head.py:114-117
+        return dict(loss_occ=self.weight_ce * self.loss_occ(cls_score=preds, label=labels, weight=mask, avg_factor=avg_factor),
+                    loss_voxel_sem_scal=self.weight_sem * sem_scal_loss_with_mask(preds, labels, mask),
+                    loss_voxel_geo_scal=self.weight_geo * geo_scal_loss_with_mask(preds, labels, mask, non_empty_idx=17))
+
     def get_occ(self, occ_pred, img_metas=None):
         """(B, Dx, Dy, Dz, C) -> list of (Dx, Dy, Dz) uint8 class maps (occ_head.py:141-153)."""
         res = occ_pred.softmax(-1).argmax(-1)

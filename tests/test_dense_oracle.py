@@ -353,3 +353,70 @@ def test_stereo_detector_frame_fusion_glue():
     col = DHD_stereo._collapse_z(f3[0])                                # channel = z * C + c
     assert torch.equal(col[:, 5 * C + 1], f3[0][:, 1, 5])
     assert torch.equal(torch.stack(torch.chunk(col, 16, dim=1), dim=2), f3[0])
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason='reference tree not present')
+def test_plugin_predictor_loss_equals_the_reference():
+    """predictor.loss (occ_head.py:102-139) of the plugin -- CrossEntropyLoss from the LOSSES registry + the vectorised
+    sem_scal / geo_scal terms -- against the UNMODIFIED reference predictor.loss driving the reference's own
+    cross_entropy_loss.py and semkitti_loss.py: the three values and the gradient at the logits.  The one mmdet helper
+    the reference file imports (mmdet 2.25.1 `weight_reduce_loss`, not in the reference tree) is restated here."""
+    import importlib.util
+    import sys
+    import types
+    import projects.mmdet3d_plugin  # noqa: F401
+    from projects.mmdet3d_plugin.models.dense_heads.occ_head import predictor
+    ns = ref_loader.load_reference()
+
+    def weight_reduce_loss(loss, weight=None, reduction='mean', avg_factor=None):      # mmdet/models/losses/utils.py
+        if weight is not None:
+            loss = loss * weight
+        if avg_factor is None:
+            return loss.mean() if reduction == 'mean' else (loss.sum() if reduction == 'sum' else loss)
+        if reduction == 'mean':
+            return loss.sum() / (avg_factor + torch.finfo(torch.float32).eps)
+        if reduction != 'none':
+            raise ValueError('avg_factor can not be used with reduction="sum"')
+        return loss
+
+    class _Reg:
+        def register_module(self, *a, **k):
+            return lambda cls: cls
+    saved = {k: sys.modules.get(k) for k in ('mmdet.models.builder', 'mmdet.models.losses', 'mmdet.models.losses.utils')}
+    sys.modules['mmdet.models.builder'] = types.SimpleNamespace(LOSSES=_Reg())
+    sys.modules['mmdet.models.losses'] = types.ModuleType('mmdet.models.losses')
+    sys.modules['mmdet.models.losses.utils'] = types.SimpleNamespace(weight_reduce_loss=weight_reduce_loss)
+    try:
+        path = os.path.join(ref_loader.REF_ROOT, 'projects', 'mmdet3d_plugin', 'models', 'losses', 'cross_entropy_loss.py')
+        spec = importlib.util.spec_from_file_location('ref_cross_entropy_loss', path)
+        ce = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(ce)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    kw = dict(in_dim=32, out_dim=32, Dz=16, use_mask=True, num_classes=18, use_predicter=True, class_balance=True,
+              weight_ce=10.0, weight_geo=0.2, weight_sem=0.2)
+    loss_cfg = dict(type='CrossEntropyLoss', use_sigmoid=False, ignore_index=255, loss_weight=1.0)
+    ours = predictor(loss_occ=loss_cfg, **kw)
+    ref = ns.predictor(loss_occ=loss_cfg, **kw)
+    ref.loss_occ = ce.CrossEntropyLoss(use_sigmoid=False, ignore_index=255, loss_weight=1.0, class_weight=ref.cls_weights)
+    assert type(ours.loss_occ).__name__ == 'CrossEntropyLoss' and ours.loss_occ.ignore_index == 255
+    g = torch.Generator().manual_seed(6)
+    B, Dx, Dy, Dz = 1, 20, 20, 16
+    labels = torch.randint(0, 18, (B, Dx, Dy, Dz), generator=g)
+    labels[labels == 5] = 6                              # a class absent from the target
+    labels[0, 0, 0, :4] = 255                            # ignored voxels
+    mask = torch.rand(B, Dx, Dy, Dz, generator=g) < 0.6
+    for scale in (1.0, 5.0):
+        logits = torch.randn(B, Dx, Dy, Dz, 18, generator=g) * scale
+        a, b = logits.clone().requires_grad_(), logits.clone().requires_grad_()
+        la, lb = ref.loss(a, labels, mask), ours.loss(b, labels, mask)
+        assert set(la) == set(lb) == {'loss_occ', 'loss_voxel_sem_scal', 'loss_voxel_geo_scal'}
+        for k in la:
+            assert torch.allclose(la[k].double(), lb[k].double(), rtol=1e-5, atol=1e-6), (k, float(la[k]), float(lb[k]))
+        sum(la.values()).backward()
+        sum(lb.values()).backward()
+        assert torch.allclose(a.grad, b.grad, rtol=1e-4, atol=1e-8)
