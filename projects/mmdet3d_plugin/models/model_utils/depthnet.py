@@ -90,7 +90,56 @@ def _cost_volumn_net(depth_channels):
     return nn.Sequential(*layers)
 
 
-class DepthNet(nn.Module):
+class _PlaneSweep:
+    """The two stereo helpers DepthNet and HeightNet share in the reference (depthnet.py:245-361, 489-603)."""
+
+    def gen_grid(self, metas, B, N, D, H, W, hi, wi):
+        """Reference depthnet.py:245-308: the (B*N, D*H, W, 2) normalised sampling coordinates of the previous frame
+        for every point of the current frame's 1/4-resolution frustum (points behind the previous camera -> -2).
+        Plain torch, for callers of the reference API; `calculate_cost_volumn` computes the same coordinates inside
+        its kernel (bit-equal, tests/test_stereo_gpu.py) and never materialises this tensor."""
+        frustum = metas['frustum']
+        view = lambda t, *tail: t.view(B, N, 1, 1, 1, *tail)
+        pts = frustum - view(metas['post_trans'], 3)
+        pts = view(torch.inverse(metas['post_rots']), 3, 3).matmul(pts.unsqueeze(-1))
+        pts = torch.cat((pts[..., :2, :] * pts[..., 2:3, :], pts[..., 2:3, :]), 5)          # (u d, v d, d)
+        k2s = metas['k2s_sensor']
+        combine = k2s[:, :, :3, :3].contiguous().matmul(torch.inverse(metas['intrins']))
+        pts = view(combine, 3, 3).matmul(pts)
+        pts = pts + view(k2s[:, :, :3, 3].contiguous(), 3, 1)                               # previous camera frame
+        behind = pts[..., 2, 0] < 1e-3
+        pts = view(metas['intrins'], 3, 3).matmul(pts)
+        pts = pts[..., :2, :] / pts[..., 2:3, :]
+        pts = view(metas['post_rots'][..., :2, :2], 2, 2).matmul(pts).squeeze(-1)
+        pts = pts + view(metas['post_trans'][..., :2], 2)
+        px = pts[..., 0] / (wi - 1.0) * 2.0 - 1.0
+        py = pts[..., 1] / (hi - 1.0) * 2.0 - 1.0
+        px[behind] = -2
+        py[behind] = -2
+        return torch.stack([px, py], dim=-1).view(B * N, D * H, W, 2)
+
+    def calculate_cost_volumn(self, metas, out_act=None):
+        """Reference depthnet.py:310-361 (+ gen_grid 245-308) as ONE fused kernel (dhd_b200/csrc/stereo.cu):
+        (B*N, D, fH_stereo, fW_stereo) matching probabilities from stereo_metas (same dict as the reference).
+        out_act: optional split-bf16 activation to fill instead (the form cost_volumn_net reads)."""
+        from dhd_b200 import stereo as S
+        prev, curr = metas['cv_feat_list']
+        if not curr.is_cuda:
+            raise RuntimeError('dhd_b200: expected CUDA tensors (the hot path has no CPU fallback)')
+        frustum = metas['frustum']
+        D, H, W, _ = frustum.shape
+        lowp = self.precision == 'bf16'
+        with torch.no_grad():
+            cam = S.camera_table(metas['k2s_sensor'], metas['intrins'], metas['post_rots'], metas['post_trans'])
+            p = S.to_nhwc(prev.reshape(-1, prev.shape[-3], H, W).float(), bf16=lowp)
+            c = S.to_nhwc(curr.reshape(-1, curr.shape[-3], H, W).float(), bf16=lowp)
+            # gen_grid's hi, wi = 4 * (stereo map size), depthnet.py:339-340
+            out, _ = S.cost_volume(p, c, D, (H * 4, W * 4), bias=self.bias, frustum=frustum.to(curr.device), cam=cam,
+                                   out_act=out_act)
+        return out
+
+
+class DepthNet(_PlaneSweep, nn.Module):
     """Depth + context head of MGHS_Depth / MGHS_Stereo (reference depthnet.py:172-415).
     stereo=True adds cost_volumn_net and the first block's 1x1 downsample; the plane-sweep cost volume
     (gen_grid + calculate_cost_volumn, 245-361) is one fused CUDA kernel, see calculate_cost_volumn."""
@@ -118,26 +167,6 @@ class DepthNet(nn.Module):
     def _load_from_state_dict(self, *a, **k):
         self._engine = None
         return super()._load_from_state_dict(*a, **k)
-
-    def calculate_cost_volumn(self, metas, out_act=None):
-        """Reference depthnet.py:310-361 (+ gen_grid 245-308) as ONE fused kernel (dhd_b200/csrc/stereo.cu):
-        (B*N, D, fH_stereo, fW_stereo) matching probabilities from stereo_metas (same dict as the reference).
-        out_act: optional split-bf16 activation to fill instead (the form cost_volumn_net reads)."""
-        from dhd_b200 import stereo as S
-        prev, curr = metas['cv_feat_list']
-        if not curr.is_cuda:
-            raise RuntimeError('dhd_b200: expected CUDA tensors (the hot path has no CPU fallback)')
-        frustum = metas['frustum']
-        D, H, W, _ = frustum.shape
-        lowp = self.precision == 'bf16'
-        with torch.no_grad():
-            cam = S.camera_table(metas['k2s_sensor'], metas['intrins'], metas['post_rots'], metas['post_trans'])
-            p = S.to_nhwc(prev.reshape(-1, prev.shape[-3], H, W).float(), bf16=lowp)
-            c = S.to_nhwc(curr.reshape(-1, curr.shape[-3], H, W).float(), bf16=lowp)
-            # gen_grid's hi, wi = 4 * (stereo map size), depthnet.py:339-340
-            out, _ = S.cost_volume(p, c, D, (H * 4, W * 4), bias=self.bias, frustum=frustum.to(curr.device), cam=cam,
-                                   out_act=out_act)
-        return out
 
     def forward_split(self, x, mlp_input, softmax=True, stereo_metas=None):
         """-> (depth (B*N, D, fH, fW) NCHW [softmax-ed], context (B*N, fH, fW, C) NHWC): the layouts the
@@ -174,7 +203,7 @@ class DepthNet(nn.Module):
         return torch.cat([depth, ctx.permute(0, 3, 1, 2)], dim=1)
 
 
-class HeightNet(nn.Module):
+class HeightNet(_PlaneSweep, nn.Module):
     """Per-pixel height distribution head (reference depthnet.py:418-652)."""
 
     def __init__(self, in_channels, mid_channels, depth_channels, use_dcn=True, use_aspp=True,

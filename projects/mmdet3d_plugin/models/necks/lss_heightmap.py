@@ -147,6 +147,16 @@ class MGHS(BaseModule):
                                     tran_feat.view(B, N, self.out_channels, H, W))
         return bev, depth
 
+    def init_acceleration_v2(self, coor):
+        """LH:234-258: the rank / interval tensors of one grid kept as attributes (what the reference's, unused,
+        accelerate path would read).  The fused path caches its bins through `pre_compute` instead."""
+        ranks_bev, ranks_depth, ranks_feat, starts, lengths = self.voxel_pooling_prepare_v2(coor)
+        self.ranks_bev = ranks_bev.int().contiguous()
+        self.ranks_feat = ranks_feat.int().contiguous()
+        self.ranks_depth = ranks_depth.int().contiguous()
+        self.interval_starts = starts.int().contiguous()
+        self.interval_lengths = lengths.int().contiguous()
+
     def pre_compute(self, input):
         """Bins depend on the camera geometry only: cache them (the reference's `accelerate`)."""
         if self.initial_flag:
@@ -255,6 +265,16 @@ class MGHS(BaseModule):
         t = t.view(B * N, H // ds, ds, W // ds, ds).permute(0, 1, 3, 2, 4).reshape(-1, ds * ds)
         t = t.min(dim=-1).values
         return t
+
+    def downsample_sparse_map(self, height_maps, downsample_factor=16):
+        """LH:566-594: (B, N, H, W) sparse map -> (B, N, H/f, W/f) minimum of the non-zero values per f x f block,
+        0 where a block is empty."""
+        B, N, H, W = height_maps.shape
+        f = downsample_factor
+        assert H % f == 0 and W % f == 0, 'the map must be a whole number of blocks'
+        t = torch.where(height_maps == 0.0, torch.full_like(height_maps, 1e5), height_maps)
+        t = t.view(B, N, H // f, f, W // f, f).permute(0, 1, 2, 4, 3, 5).reshape(B, N, -1, f * f).min(dim=-1).values
+        return torch.where(t == 1e5, torch.zeros_like(t), t).view(B, N, H // f, W // f)
 
     def get_downsampled_gt_depth(self, gt_depths):
         t = self._min_pool_sparse(gt_depths)        # empty blocks keep the 1e5 sentinel -> bin 0 below

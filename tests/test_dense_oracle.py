@@ -420,3 +420,66 @@ def test_plugin_predictor_loss_equals_the_reference():
         sum(la.values()).backward()
         sum(lb.values()).backward()
         assert torch.allclose(a.grad, b.grad, rtol=1e-4, atol=1e-8)
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason='reference tree not present')
+def test_plugin_mghs_exposes_every_reference_method():
+    """Every public method / attribute of the reference's MGHS family exists on the plugin's (SURVEY 8(b) module API),
+    and the two small helpers that are plain torch agree with the reference: downsample_sparse_map (LH:566-594) and
+    init_acceleration_v2 (LH:234-258; same interval table, ranks equal as per-interval sets -- argsort is unstable)."""
+    from dhd_b200 import synth
+    import projects.mmdet3d_plugin.models.necks.lss_heightmap as LH
+    ns = ref_loader.load_reference()
+    kw = dict(synth.DHD_L_VIEW_TRANSFORMER, in_channels=64)
+    kw['depthnet_cfg'] = dict(use_dcn=False, aspp_mid_channels=32, stereo=True, bias=5.)
+    kw['heightnet_cfg'] = dict(use_dcn=False, aspp_mid_channels=32)
+    ours, ref = LH.MGHS_Stereo(**kw), ns.MGHS_Stereo(**kw)
+    public = [n for n in dir(ref) if not n.startswith('_') and n not in dir(torch.nn.Module)]
+    missing = [n for n in public if not hasattr(ours, n)]
+    assert not missing, missing
+    g = torch.Generator().manual_seed(1)
+    m = torch.where(torch.rand(1, 2, 64, 96, generator=g) < 0.03, torch.rand(1, 2, 64, 96, generator=g) * 5 - 1, torch.zeros(()))
+    assert torch.equal(ours.downsample_sparse_map(m), ref.downsample_sparse_map(m))
+    coor = torch.rand(1, 2, 8, 4, 6, 3, generator=g) * torch.tensor([90.0, 90.0, 8.0]) - torch.tensor([45.0, 45.0, 2.0])
+    ours.init_acceleration_v2(coor)
+    ref.init_acceleration_v2(coor)
+    assert torch.equal(ours.interval_starts, ref.interval_starts) and torch.equal(ours.interval_lengths, ref.interval_lengths)
+    assert torch.equal(ours.ranks_bev, ref.ranks_bev)
+    for s, l in zip(ref.interval_starts.tolist(), ref.interval_lengths.tolist()):
+        assert sorted(ours.ranks_depth[s:s + l].tolist()) == sorted(ref.ranks_depth[s:s + l].tolist())
+
+
+def test_plugin_gen_grid_reproduces_the_reference_fixture():
+    """DepthNet.gen_grid of the plugin (torch form of the reference API, depthnet.py:245-308) is bit-equal to the grid
+    the unmodified reference produced for the fixture rig (tests/golden/depthnet.npz)."""
+    from oracle import make_golden_depthnet as MGD
+    import projects.mmdet3d_plugin  # noqa: F401
+    from projects.mmdet3d_plugin.models.model_utils.depthnet import DepthNet, HeightNet
+    gold = np.load(os.path.join(os.path.dirname(GOLD), 'depthnet.npz'))
+    x, mlp, prev, curr = MGD.inputs()
+    m = MGD.stereo_metas(prev, curr)
+    H, W = MGD.INPUT
+    for net in (DepthNet(64, 64, 32, MGD.n_depth(), stereo=True, use_dcn=False, bias=MGD.BIAS), HeightNet(64, 64, 65)):
+        grid = net.gen_grid(m, MGD.B, MGD.NCAM, MGD.n_depth(), H // 4, W // 4, H, W)
+        assert np.array_equal(grid.numpy(), gold['grid'])
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason='reference tree not present')
+def test_plugin_classes_expose_the_reference_methods():
+    """Public methods / attributes of every hot-path class of the reference exist on the plugin's class of that name."""
+    import projects.mmdet3d_plugin  # noqa: F401
+    from projects.mmdet3d_plugin.models.backbones.resnet import CustomResNet
+    from projects.mmdet3d_plugin.models.backbones.unet import UNet
+    from projects.mmdet3d_plugin.models.dense_heads.occ_head import predictor
+    from projects.mmdet3d_plugin.models.model_utils.depthnet import DepthNet, HeightNet
+    from projects.mmdet3d_plugin.models.necks.lss_fpn import FPN_LSS
+    from projects.mmdet3d_plugin.models.necks.mix import SFA
+    ns = ref_loader.load_reference()
+    pairs = [(SFA(512, 256), ns.SFA(512, 256)), (predictor(loss_occ=None), ns.predictor(loss_occ=None)),
+             (HeightNet(64, 64, 65), ns.HeightNet(64, 64, 65)),
+             (DepthNet(64, 64, 32, 88, stereo=True, use_dcn=False), ns.DepthNet(64, 64, 32, 88, stereo=True, use_dcn=False)),
+             (UNet(64, 64), ns.UNet(64, 64)), (CustomResNet(64), ns.CustomResNet(64)), (FPN_LSS(640, 256), ns.FPN_LSS(640, 256))]
+    base = set(dir(torch.nn.Module))
+    for ours, ref in pairs:
+        missing = [n for n in dir(ref) if not n.startswith('_') and n not in base and not hasattr(ours, n)]
+        assert not missing, (type(ref).__name__, missing)
