@@ -90,7 +90,7 @@ class _Conv:
 
 
 class HeightNetEngine:
-    """depthnet.py:418-487, 605-652 (non-stereo path), eval mode."""
+    """depthnet.py:418-487, 605-652, eval mode (HeightNet is always called with stereo_metas=None, lss_heightmap.py:787)."""
 
     def __init__(self, net, precision='fp32', device='cuda'):
         self.precision, self.device = precision, device

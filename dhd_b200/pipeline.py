@@ -14,8 +14,8 @@ Per step and per GPU (DHD-S, B samples = 6B camera images), everything through t
 
 The front and the back of the step are captured into two CUDA graphs (launch-bound otherwise:
 ~75 kernels); the pool kernel between them is an eager launch so it can be timed in place.
-The pool backward (a10) is timed separately by bench.py (`extras`), the dense layers being
-inference-only in this build.
+The pool backward (a10) is timed separately by bench.py (`extras`); the training step (forward with
+saved activations, losses, backward, gradient all-reduce, AdamW) is `TrainStep` below.
 """
 import ctypes
 import json

@@ -251,7 +251,8 @@ class HeightNet(_PlaneSweep, nn.Module):
         if self.training:
             raise NotImplementedError('dhd_b200 HeightNet: inference (eval-mode BatchNorm) only in this build')
         if stereo_metas is not None or self.stereo:
-            raise NotImplementedError('HeightNet stereo / cost-volume branch: SURVEY 8(f) rank 3')
+            raise NotImplementedError('HeightNet with a cost volume: no DHD module calls it that way '
+                                      '(MGHS_Depth passes stereo_metas=None, lss_heightmap.py:787)')
         if not isinstance(x, D.Act):
             if not x.is_cuda:
                 raise RuntimeError('dhd_b200: expected CUDA tensors (the hot path has no CPU fallback)')

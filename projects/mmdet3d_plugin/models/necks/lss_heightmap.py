@@ -231,7 +231,8 @@ class MGHS(BaseModule):
         mlp_input = input[7]
         B, N, C, H, W = x.shape
         if self.training:
-            raise NotImplementedError('dhd_b200 MGHS: the dense layers are inference-only in this build')
+            raise NotImplementedError('dhd_b200 MGHS.forward is the inference form (eval-mode BatchNorm, no autograd graph); '
+                                      'training runs through dhd_b200.train / dhd_b200.pipeline.TrainStep')
         if not x.is_cuda:
             raise RuntimeError('dhd_b200: expected CUDA tensors (the hot path has no CPU fallback)')
         with torch.no_grad():
@@ -323,7 +324,8 @@ class MGHS_Depth(MGHS):
         x, mlp_input = input[0], input[7]
         B, N, C, H, W = x.shape
         if self.training:
-            raise NotImplementedError('dhd_b200 MGHS_Depth: the dense layers are inference-only in this build')
+            raise NotImplementedError('dhd_b200 MGHS_Depth.forward is the inference form (eval-mode BatchNorm, no autograd '
+                                      'graph); the DepthNet backward is not built yet (DESIGN.md 7)')
         if not x.is_cuda:
             raise RuntimeError('dhd_b200: expected CUDA tensors (the hot path has no CPU fallback)')
         with torch.no_grad():
