@@ -89,3 +89,46 @@ def test_ctypes_struct_layouts_match_the_library(lib):
     # the same fields at the same offsets for the two structs that grew this round
     assert D.ConvDesc.stride.offset == D.ConvDesc.seg.offset + D.MAX_SEGS * ctypes.sizeof(D.ConvSeg)
     assert D.WgradDesc.x_stride.offset == D.WgradDesc.accumulate.offset + 4
+
+
+def test_ctypes_field_offsets_match_the_c_header(tmp_path):
+    """Every field of every ABI struct sits at the offset the C compiler gives it in include/dhd_b200.h: a tiny C program
+    prints offsetof() for each field (names parsed from the header) and the ctypes mirrors must agree one by one."""
+    import ctypes
+    import shutil
+    import subprocess
+    from dhd_b200 import dense as D
+    from dhd_b200._lib import MghsCfg
+    from dhd_b200.stereo import StereoDesc
+    if shutil.which('gcc') is None:
+        pytest.skip('no C compiler')
+    header = os.path.join(ROOT, 'include', 'dhd_b200.h')
+    text = re.sub(r'/\*.*?\*/', '', open(header).read(), flags=re.S)
+    structs = (('dhd_mghs_cfg', MghsCfg), ('dhd_conv_seg', D.ConvSeg), ('dhd_conv_desc', D.ConvDesc),
+               ('dhd_wgrad_desc', D.WgradDesc), ('dhd_stereo_desc', StereoDesc))
+    lines, expect = [], []
+    for cname, cls in structs:
+        body = re.search(r'typedef struct %s \{(.*?)\} %s;' % (cname, cname), text, flags=re.S).group(1)
+        names = []
+        for decl in body.split(';'):
+            parts = [p for p in decl.strip().split(',') if p.strip()]
+            if not parts:
+                continue
+            names.append(re.sub(r'\[.*', '', parts[0].split()[-1]).lstrip('*'))
+            names += [re.sub(r'\[.*', '', p.strip()).lstrip('*').strip() for p in parts[1:]]
+        py_names = [f[0] for f in cls._fields_]
+        assert [n.rstrip('_') for n in py_names] == names, cname          # `in_` mirrors the C field `in`
+        for c_field, py_field in zip(names, py_names):
+            lines.append('  printf("%%zu\\n", offsetof(%s, %s));' % (cname, c_field))
+            expect.append(('%s.%s' % (cname, c_field), getattr(cls, py_field).offset))
+        lines.append('  printf("%%zu\\n", sizeof(%s));' % cname)
+        expect.append((cname + ' (sizeof)', ctypes.sizeof(cls)))
+    src = tmp_path / 'offsets.c'
+    src.write_text('#include <stddef.h>\n#include <stdio.h>\n#include "%s"\nint main(void) {\n%s\n  return 0;\n}\n'
+                   % (header, '\n'.join(lines)))
+    exe = tmp_path / 'offsets'
+    subprocess.check_call(['gcc', '-std=c11', '-o', str(exe), str(src)])
+    got = [int(v) for v in subprocess.check_output([str(exe)]).split()]
+    assert len(got) == len(expect)
+    for (what, want), have in zip(expect, got):
+        assert have == want, '%s: C says %d, ctypes says %d' % (what, have, want)
