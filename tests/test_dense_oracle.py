@@ -483,3 +483,39 @@ def test_plugin_classes_expose_the_reference_methods():
     for ours, ref in pairs:
         missing = [n for n in dir(ref) if not n.startswith('_') and n not in base and not hasattr(ours, n)]
         assert not missing, (type(ref).__name__, missing)
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason='reference tree not present')
+@pytest.mark.parametrize('seed,bias,C,D', [(0, 0.0, 8, 5), (1, 5.0, 12, 9), (2, 2.5, 4, 33)])
+def test_stereo_oracle_equals_live_reference_on_random_rigs(seed, bias, C, D):
+    """oracle.stereo_sampling_grid / stereo_cost_volume (the checker of the CUDA kernel at full size) against the
+    unmodified reference DepthNet.gen_grid / calculate_cost_volumn on random camera rigs, channel counts, depth counts
+    and bias values -- including bias = 0 (the `== 0` test disabled) and points behind the previous camera."""
+    ns = ref_loader.load_reference()
+    g = torch.Generator().manual_seed(seed)
+    B, N, H, W = 1, 3, 6, 10
+    net = ns.DepthNet(16, 16, 8, D, use_dcn=False, aspp_mid_channels=8, stereo=True, bias=bias).eval()
+    d = torch.linspace(0.5, 30.0, D).view(-1, 1, 1).expand(-1, H, W)
+    u = torch.linspace(0, 4 * W - 1, W).view(1, 1, W).expand(D, H, W)
+    v = torch.linspace(0, 4 * H - 1, H).view(1, H, 1).expand(D, H, W)
+    frustum = torch.stack((u, v, d), -1)
+    K = torch.tensor([[30.0, 0.0, 20.0], [0.0, 30.0, 12.0], [0.0, 0.0, 1.0]]).expand(B, N, 3, 3).contiguous()
+    post_rots = torch.eye(3).expand(B, N, 3, 3).clone()
+    post_rots[..., 0, 0] = post_rots[..., 1, 1] = 0.9 + 0.2 * torch.rand(B, N, generator=g)
+    post_trans = torch.cat([4 * torch.rand(B, N, 2, generator=g) - 2, torch.zeros(B, N, 1)], -1)
+    k2s = torch.eye(4).expand(B, N, 4, 4).clone()
+    ang = 0.3 * (torch.rand(B, N, generator=g) - 0.5)
+    k2s[..., 0, 0], k2s[..., 0, 2], k2s[..., 2, 0], k2s[..., 2, 2] = ang.cos(), ang.sin(), -ang.sin(), ang.cos()
+    k2s[..., :3, 3] = torch.tensor([0.3, 0.0, 2.0]) * (torch.rand(B, N, 3, generator=g) - 0.2)   # some points end up behind
+    prev, curr = torch.randn(B * N, C, H, W, generator=g), torch.randn(B * N, C, H, W, generator=g)
+    prev[:, :, :2, :3] = 0.0
+    metas = dict(k2s_sensor=k2s, intrins=K, post_rots=post_rots, post_trans=post_trans, frustum=frustum,
+                 cv_downsample=4, downsample=16, grid_config=None, cv_feat_list=[prev, curr])
+    with torch.no_grad():
+        ref_grid = net.gen_grid(metas, B, N, D, H, W, 4 * H, 4 * W)
+        ref_cv = net.calculate_cost_volumn(metas)
+        grid = DO.stereo_sampling_grid(frustum, k2s, K, post_rots, post_trans, 4 * H, 4 * W)
+        cv = DO.stereo_cost_volume(prev, curr, grid, D, bias)
+    assert torch.equal(grid, ref_grid)
+    assert torch.allclose(cv, ref_cv, rtol=1e-5, atol=1e-7)
+    assert torch.allclose(cv.sum(1), torch.ones_like(cv[:, 0]), atol=1e-5)
