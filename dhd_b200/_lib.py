@@ -73,6 +73,7 @@ _SIGNATURES = {
     'dhd_add_rowvec': (ctypes.c_int, [_P, _P, _I, _I, _I, _P, _I, _I, _P]),
     'dhd_pack_nchw_to_nhwc': (ctypes.c_int, [_P] + [_I] * 4 + [_P] + [_I] * 4 + [_P]),
     'dhd_occ_argmax': (ctypes.c_int, [_P, ctypes.c_long, _I, _P, _P]),
+    'dhd_predictor_tail': (ctypes.c_int, [_P, _P]),
     'dhd_launch_count': (ctypes.c_long, []),
     'dhd_maxpool2_bwd': (ctypes.c_int, [_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _P]),
     'dhd_upsample_bilinear_bwd': (ctypes.c_int, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),

@@ -106,6 +106,52 @@ except Exception:  # noqa: BLE001
         return deco
 
 
+class EngineOwner:
+    """Mixin of the plugin modules that run on a compiled engine (folded BatchNorm, packed bf16 weights).
+
+    The engine is a SNAPSHOT of the parameters, so it is rebuilt whenever the module could have changed under it:
+    a parameter / buffer modified in place (optimizer.step, `with no_grad(): p.copy_()` -- the tensor version
+    counters), replaced or moved (`.to()`, `.cuda()`, `.half()`: `_apply`), reloaded (`load_state_dict`), or the
+    module switched between train() and eval().  One blind spot remains: `p.data.copy_(...)` (mmcv's EMA hook) does
+    not touch the version counter -- such writers are caught by the train()/eval() switch that follows them in the
+    reference's runner, or call `invalidate_engines(model)`."""
+
+    def _engine_key(self, device):
+        import itertools
+        return (str(device), bool(self.training)) + tuple(
+            (id(t), t._version) for t in itertools.chain(self.parameters(), self.buffers()))
+
+    def cached_engine(self, device, factory, slot='_engine'):
+        key = self._engine_key(device)
+        if self.__dict__.get(slot) is None or self.__dict__.get(slot + '_key') != key:
+            self.__dict__[slot] = factory()
+            self.__dict__[slot + '_key'] = key
+        return self.__dict__[slot]
+
+    def invalidate(self):
+        for k in [k for k in self.__dict__ if k.endswith('_engine') or k == '_engine']:
+            self.__dict__[k] = None
+
+    def train(self, mode=True):
+        self.invalidate()
+        return super().train(mode)
+
+    def _apply(self, fn, *a, **k):
+        self.invalidate()
+        return super()._apply(fn, *a, **k)
+
+    def _load_from_state_dict(self, *a, **k):
+        self.invalidate()
+        return super()._load_from_state_dict(*a, **k)
+
+
+def invalidate_engines(model):
+    """Drop every cached engine under `model` (after writing parameters through `.data`)."""
+    for m in model.modules():
+        if isinstance(m, EngineOwner):
+            m.invalidate()
+
+
 class ConvModule(nn.Module):
     """conv -> [norm] -> activation; mmcv's default act_cfg is ReLU (occ_head.py:52-60 relies on it).
     Parameter names: conv.{weight,bias}, bn.*"""

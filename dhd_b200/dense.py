@@ -59,6 +59,17 @@ class ConvDesc(ctypes.Structure):
     ]
 
 
+class PredictorTailDesc(ctypes.Structure):
+    """struct dhd_predictor_tail_desc (include/dhd_b200.h)."""
+    _fields_ = [
+        ('N', ctypes.c_int32), ('H', ctypes.c_int32), ('W', ctypes.c_int32),
+        ('K1', ctypes.c_int32), ('N1', ctypes.c_int32), ('Dz', ctypes.c_int32), ('n_cls', ctypes.c_int32),
+        ('in_ld', ctypes.c_int32), ('in_coff', ctypes.c_int32), ('transpose_xy', ctypes.c_int32),
+        ('in_', ctypes.c_void_p), ('w1', ctypes.c_void_p), ('b1', ctypes.c_void_p),
+        ('w2', ctypes.c_void_p), ('b2', ctypes.c_void_p), ('logits', ctypes.c_void_p), ('occ', ctypes.c_void_p),
+    ]
+
+
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -265,6 +276,35 @@ def conv2d(x, weight, Cout, ksize=1, dilation=1, precision='fp32', scale=None, b
             keep.append(a.data)
     _lib.check(_lib.load().dhd_conv2d_fwd(ctypes.byref(d), _stream()), 'conv2d_fwd')
     return keep
+
+
+def predictor_tail(x, w1, b1, w2, b2, Dz, n_cls, logits=None, occ=None, transpose_xy=True):
+    """Fused Linear + Softplus + Linear (+ per-z argmax) of the occupancy head (dhd_predictor_tail, bf16 operands).
+    x: Act (B, K1, H, W), part 0 is read; w1 / w2: pack_weight(.., 1) results; b1 / b2 fp32.
+    logits: fp32 (B, W, H, Dz*n_cls) and / or occ: uint8 (B, W, H, Dz), written in place."""
+    d = PredictorTailDesc()
+    d.N, d.H, d.W = x.N, x.H, x.W
+    d.K1, d.N1, d.Dz, d.n_cls = x.C, w1.shape[0], Dz, n_cls
+    if w1.shape[3] != x.C or w2.shape[3] != w1.shape[0] or w2.shape[0] != Dz * n_cls or w1.shape[1:3] != (1, 1) or \
+            w2.shape[1:3] != (1, 1) or w1.dtype != torch.bfloat16 or w2.dtype != torch.bfloat16:
+        raise ValueError('predictor_tail: weights must be bf16 [N1][1][1][K1] and [Dz*n_cls][1][1][N1]')
+    d.in_ld, d.in_coff, d.transpose_xy = x.ld, x.coff, int(bool(transpose_xy))
+    d.in_, d.w1, d.w2 = x.data.data_ptr(), w1.data_ptr(), w2.data_ptr()
+    for name, t, n in (('b1', b1, w1.shape[0]), ('b2', b2, w2.shape[0])):
+        if t is not None:
+            if t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != n:
+                raise ValueError(name + ' must be a contiguous fp32 vector of %d elements' % n)
+            setattr(d, name, t.data_ptr())
+    npix = x.N * x.H * x.W
+    if logits is not None:
+        if logits.dtype != torch.float32 or not logits.is_contiguous() or logits.numel() != npix * Dz * n_cls:
+            raise ValueError('logits must be contiguous fp32 with B*H*W*Dz*n_cls elements')
+        d.logits = logits.data_ptr()
+    if occ is not None:
+        if occ.dtype != torch.uint8 or not occ.is_contiguous() or occ.numel() != npix * Dz:
+            raise ValueError('occ must be contiguous uint8 with B*H*W*Dz elements')
+        d.occ = occ.data_ptr()
+    _lib.check(_lib.load().dhd_predictor_tail(ctypes.byref(d), _stream()), 'predictor_tail')
 
 
 def nchw_strides(C, H, W):

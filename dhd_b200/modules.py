@@ -393,19 +393,51 @@ class PredictorEngine:
         self.Dz, self.ncls = head.Dz, head.num_classes
         self.parts = D.PRECISIONS[precision][0]
 
-    def __call__(self, x):
-        """x: Act (B, C, Dy, Dx) -> occ_pred (B, Dx, Dy, Dz, n_cls) fp32."""
+    def fused_tail_ok(self):
+        """The back-to-back GEMM kernel (dhd_predictor_tail) serves the bf16 speed mode of the DHD head shape
+        (256 -> 512 -> 16 x 18); other shapes / the split-bf16 precision modes run layer by layer."""
+        return (self.use_predicter and self.parts == 1 and self.conv.Cout == 256 and self.fc0.Cout == 512 and
+                self.Dz == 16 and self.ncls == 18 and os.environ.get('DHD_TAIL_FUSED', '1') != '0')
+
+    def __call__(self, x, occ=None, want_logits=True):
+        """x: Act (B, C, Dy, Dx) -> occ_pred (B, Dx, Dy, Dz, n_cls) fp32 (None with want_logits=False).
+        occ: optional uint8 (B, Dx, Dy, Dz) tensor that receives predictor.get_occ's class map
+        (softmax(-1).argmax(-1), occ_head.py:141-153) -- in the fused kernel's epilogue when it runs, through
+        dhd_occ_argmax otherwise."""
         N, H, W, P, dev = x.N, x.H, x.W, self.parts, x.data.device
+        if not want_logits and occ is None:
+            raise ValueError('nothing to compute: want_logits=False and no occ buffer')
         if not self.use_predicter:
             Co = self.conv.Cout
             out = torch.empty(N, W, H, Co, device=dev)
             self.conv(x, [dict(act='relu' if self.relu else None, out_f32=(out, (W * H * Co, Co, H * Co, 1)))])
+            out = out.view(N, W, H, self.Dz, self.ncls)
+            if occ is not None:
+                occ_argmax(out, occ)
             return out
         t = D.Act.empty(N, H, W, self.conv.Cout, P, dev)
         self.conv(x, [dict(act='relu' if self.relu else None, out_act=t)])
+        Co = self.fc2.Cout
+        if self.fused_tail_ok():
+            out = torch.empty(N, W, H, Co, device=dev) if want_logits else None
+            D.predictor_tail(t, self.fc0.w, self.fc0.bias, self.fc2.w, self.fc2.bias, self.Dz, self.ncls,
+                             logits=out, occ=occ)
+            return out.view(N, W, H, self.Dz, self.ncls) if want_logits else None
         u = D.Act.empty(N, H, W, self.fc0.Cout, P, dev)
         self.fc0(t, [dict(act='softplus', out_act=u)])
-        Co = self.fc2.Cout
         out = torch.empty(N, W, H, Co, device=dev)          # (B, Dx, Dy, C): permute(0, 3, 2, 1)
         self.fc2(u, [dict(out_f32=(out, (W * H * Co, Co, H * Co, 1)))])
-        return out.view(N, W, H, self.Dz, self.ncls)
+        out = out.view(N, W, H, self.Dz, self.ncls)
+        if occ is not None:
+            occ_argmax(out, occ)
+        return out
+
+
+def occ_argmax(logits, occ):
+    """occ[v] = argmax_k logits[v][k] (uint8), first maximum wins: predictor.get_occ, occ_head.py:141-153."""
+    ncls = logits.shape[-1]
+    if occ.dtype != torch.uint8 or not occ.is_contiguous() or not logits.is_contiguous() or \
+            occ.numel() * ncls != logits.numel():
+        raise ValueError('occ must be contiguous uint8 with one element per class row of the logits')
+    _lib.check(_lib.load().dhd_occ_argmax(_p(logits), occ.numel(), ncls, _p(occ), _stream()), 'occ_argmax')
+    return occ

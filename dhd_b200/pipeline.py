@@ -10,7 +10,8 @@ Per step and per GPU (DHD-S, B samples = 6B camera images), everything through t
           fused masked lift-splat, four BEV tensors, single write       dhd_mghs_pool_fwd     (a6, a9, a11)
   back    [BEV / voxel encoders: outside the path -> resident synthetic (B,512,Dy,Dx) features]
           SFA (squeeze, 5 convs + gates), predictor (3 GEMMs)            dhd_conv2d_fwd, ...   (a14, a15)
-          class map (argmax over 18 classes) uint8                      dhd_occ_argmax
+          [bf16 mode: Linear + Softplus + Linear + per-z argmax fused    dhd_predictor_tail]
+          class map (argmax over 18 classes) uint8                      dhd_occ_argmax (split-bf16 modes)
 
 The front and the back of the step are captured into two CUDA graphs (launch-bound otherwise:
 ~75 kernels); the pool kernel between them is an eager launch so it can be timed in place.
@@ -92,7 +93,7 @@ def encoder_flops(B, Dy=200, Dx=200, c=64):
 
 class HotPathStep:
     def __init__(self, cfg, B, precision='bf16', deterministic=True, device='cuda', seed=0,
-                 use_graph=True, encoders=False):
+                 use_graph=True, encoders=False, keep_logits=False):
         from projects.mmdet3d_plugin.models.dense_heads.occ_head import predictor
         from projects.mmdet3d_plugin.models.necks.lss_heightmap import MGHS
         from projects.mmdet3d_plugin.models.necks.mix import SFA
@@ -115,6 +116,7 @@ class HotPathStep:
         self.head = predictor(in_dim=256, out_dim=256, Dz=16, num_classes=18, use_predicter=True,
                               class_balance=False, loss_occ=None, precision=precision).eval().to(self.device)
         self.encoders = encoders
+        self.keep_logits = keep_logits        # True: also write the fp32 logits (184 MB at B=4) -- parity tests
         if encoders:
             # the widened path: the real BEV encoder and the three voxel encoders of
             # DHD-S.py:106-131 between the pool and the SFA instead of resident stand-in features
@@ -252,12 +254,11 @@ class HotPathStep:
     def _back(self):
         enc = self._encode() if self.encoders else self.encoded_act
         fused = self.sfa_engine(enc)
-        logits = self.head_engine(fused)
-        _lib.check(_lib.load().dhd_occ_argmax(ctypes.c_void_p(logits.data_ptr()), self.occ.numel(), 18,
-                                              ctypes.c_void_p(self.occ.data_ptr()),
-                                              ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)),
-                   'occ_argmax')
-        self._logits = logits
+        # inference tail (occ_head.py:141-153): the class map is what leaves the step.  bf16 speed mode: ONE fused kernel
+        # (Linear + Softplus + Linear + per-z argmax, dhd_predictor_tail) -- the logits never reach HBM; the split-bf16
+        # precision modes keep the layer-by-layer head + dhd_occ_argmax and expose the logits (parity tests)
+        fused_tail = self.head_engine.fused_tail_ok() and not self.keep_logits
+        self._logits = self.head_engine(fused, occ=self.occ, want_logits=not fused_tail)
 
     def capture(self):
         """Warm up eagerly, count this library's launches for one step, then capture the front and

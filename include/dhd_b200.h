@@ -24,6 +24,8 @@
  *                            (see the dense-layer section below)
  *   dhd_stereo_cost_volume <- DepthNet.gen_grid + calculate_cost_volumn
  *                            models/model_utils/depthnet.py:245-361
+ *   dhd_predictor_tail    <- predictor.predicter (Linear, Softplus, Linear) + permute + get_occ argmax
+ *                            models/dense_heads/occ_head.py:63-67, 84-100, 141-153
  *   dhd_mghs_voxel_index  <- the (kept, ranks_bev) part of voxel_pooling_prepare_v2
  *                            models/necks/lss_heightmap.py:331-354 (bit-exact parity hook)
  */
@@ -77,7 +79,7 @@ typedef struct dhd_mghs_cfg {
 
 const char* dhd_last_error(void);
 int dhd_abi_version(void);
-/* sizeof(dhd_mghs_cfg | dhd_conv_seg | dhd_conv_desc | dhd_wgrad_desc | dhd_stereo_desc) for which = 0..4: lets a binding check its
+/* sizeof(dhd_mghs_cfg | dhd_conv_seg | dhd_conv_desc | dhd_wgrad_desc | dhd_stereo_desc | dhd_predictor_tail_desc) for which = 0..5: lets a binding check its
  * own struct layout against the library it loaded */
 size_t dhd_abi_sizeof(int which);
 
@@ -386,6 +388,31 @@ int dhd_pack_nchw_to_nhwc(const float* in, int N, int C, int H, int W, void* out
                           int out_coff, int part_stride, int parts, void* stream);
 /* class map of predictor.get_occ (occ_head.py:141-153): out[v] = argmax_k logits[v][k] (uint8) */
 int dhd_occ_argmax(const float* logits, long nvox, int ncls, uint8_t* out, void* stream);
+
+/* ---- fused occupancy-head tail ------------------------------------------------------
+ * predictor.predicter = Linear(K1 -> N1) + Softplus + Linear(N1 -> Dz * n_cls) on every BEV pixel
+ * (models/dense_heads/occ_head.py:63-67), the permute(0, 3, 2, 1) of predictor.forward (occ_head.py:84-100)
+ * and, when `occ` is given, predictor.get_occ's softmax(-1).argmax(-1) -> uint8 (occ_head.py:141-153), as ONE
+ * back-to-back tcgen05 GEMM kernel: the hidden layer stays in TMEM / shared memory, the logits leave the SM only
+ * when `logits` is given.  bf16 operands (part 0 of the input activation, bf16 weights), fp32 accumulation.
+ * in: bf16 NHWC rows [N*H*W][in_ld], channels [in_coff, in_coff + K1) = ReLU(final_conv(x)).
+ * w1: bf16 [N1][K1]; w2: bf16 [Dz*n_cls][N1] (row-major nn.Linear weights); b1 / b2 fp32 or NULL.
+ * logits: fp32 [N][W][H][Dz*n_cls] when transpose_xy (the reference's (B, Dx, Dy, Dz, n_cls)), else [N][H][W][..];
+ * occ: uint8, same pixel order, [Dz] per pixel.  This build: K1 = 256, N1 = 512, Dz = 16, n_cls = 18. */
+typedef struct dhd_predictor_tail_desc {
+  int32_t N, H, W;
+  int32_t K1, N1, Dz, n_cls;
+  int32_t in_ld, in_coff;
+  int32_t transpose_xy;
+  const void* in;
+  const void* w1;
+  const float* b1;
+  const void* w2;
+  const float* b2;
+  float* logits;
+  uint8_t* occ;
+} dhd_predictor_tail_desc;
+int dhd_predictor_tail(const dhd_predictor_tail_desc* desc, void* stream);
 /* encoder helpers, bf16 NHWC -> bf16 NHWC (the output may be a channel slice of a concatenation buffer):
  * MaxPool2d(2) (backbones/unet.py:65-74) and bilinear Upsample(align_corners=True) (necks/lss_fpn.py:27-28, 41-42) */
 int dhd_maxpool2(const void* in, int in_ld, int in_coff, int in_part_stride, int N, int H, int W, int C,

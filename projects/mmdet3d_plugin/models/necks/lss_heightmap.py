@@ -161,7 +161,7 @@ class MGHS(BaseModule):
         """Bins depend on the camera geometry only: cache them (the reference's `accelerate`)."""
         if self.initial_flag:
             self._prepare(input)
-            self.initial_flag = False
+            self.initial_flag = not self.accelerate     # without accelerate every forward re-bins anyway
 
     # ------------------------------------------------------------------ height masks (LH:528-564)
     def height_feature_to_height_map(self, height_feature, height_range):
@@ -196,6 +196,18 @@ class MGHS(BaseModule):
                      post_rots=pr.float(), post_trans=pt.float(), bda=bda.float())
         return plan
 
+    def _bins(self, input):
+        """The binned frustum of this call.  accelerate=True (the reference's dead flag, LH:56, 374-378): the bins of
+        the first call -- or of pre_compute() -- are reused while (B, N, fH, fW) stays the same; a different shape
+        (e.g. a smaller last batch) re-bins.  The camera geometry is assumed fixed, as the reference's flag does."""
+        B, N, _, H, W = input[0].shape
+        if self.accelerate and not self.initial_flag and self._plan is not None and self._plan[0] == (B, N, H, W) \
+                and self._plan[1].workspace is not None:
+            return self._plan[1]
+        plan = self._prepare(input)
+        self.initial_flag = not self.accelerate
+        return plan
+
     def view_transform(self, input, depth, tran_feat, height, feat_nhwc=None):
         """depth (B*N, D, fH, fW), tran_feat (B*N, C, fH, fW), height (B*N, H, fH, fW) ->
         (bev, depth, height, low, mid, high) like LH:407-459; the four BEV tensors have the
@@ -203,11 +215,7 @@ class MGHS(BaseModule):
         B, N, _, H, W = input[0].shape
         if not depth.is_cuda:
             raise RuntimeError('dhd_b200: expected CUDA tensors (the hot path has no CPU fallback)')
-        if self.accelerate and not self.initial_flag and self._plan is not None:
-            plan = self._plan[1]
-        else:
-            plan = self._prepare(input)
-            self.initial_flag = not self.accelerate
+        plan = self._bins(input)
         if feat_nhwc is None:
             feat_nhwc = tran_feat.view(B, N, self.out_channels, H, W).permute(0, 1, 3, 4, 2).contiguous()
         pixmask = height_to_mask(height, self.height_range, self.mask_range)
@@ -338,11 +346,7 @@ class MGHS_Depth(MGHS):
         B, N, _, H, W = input[0].shape
         if not depth.is_cuda:
             raise RuntimeError('dhd_b200: expected CUDA tensors (the hot path has no CPU fallback)')
-        if self.accelerate and not self.initial_flag and self._plan is not None:
-            plan = self._plan[1]
-        else:
-            plan = self._prepare(input)
-            self.initial_flag = not self.accelerate
+        plan = self._bins(input)
         if feat_nhwc is None:
             feat_nhwc = tran_feat.view(B, N, self.out_channels, H, W).permute(0, 1, 3, 4, 2).contiguous()
         feat_nhwc = feat_nhwc.view(B, N, H, W, self.out_channels)

@@ -451,3 +451,96 @@ def test_bf16_output_layout_is_the_rounded_fp32_result(cuda_lib):
     torch.cuda.synchronize()
     for g, w in zip(got, want):
         assert g.dtype == torch.bfloat16 and torch.equal(g, w.to(torch.bfloat16))
+
+
+def _close_scaled(got, ref, what, rtol=1e-5):
+    """rtol 1e-5 plus an absolute floor of 1e-5 x the gradient's scale (sums of signed terms in another order)."""
+    got, ref = got.float(), ref.float()
+    assert got.shape == ref.shape, what
+    atol = rtol * float(ref.abs().max())
+    err = (got - ref).abs()
+    bad = err > atol + rtol * ref.abs()
+    assert not bool(bad.any()), '%s: %d / %d off, max abs err %.3g at scale %.3g' % (
+        what, int(bad.sum()), bad.numel(), float(err.max()), float(ref.abs().max()))
+
+
+@pytest.mark.parametrize('name,input_size,depth_cfg,B,collapse,layout', [
+    # BASELINE.json configs[1]: DHD-S, B=4, 6 x 256x704, collapse_z=True
+    ('cfg2_dhds_b4', (256, 704), [1.0, 45.0, 1.0], 4, True, 'nhwc'),
+    ('cfg2_dhds_b4_nchw', (256, 704), [1.0, 45.0, 1.0], 4, True, 'nchw'),
+    # BASELINE.json configs[4]: DHD-L, B=2, 6 x 512x1408, D=88, collapse_z=False
+    ('cfg5_dhdl_b2', (512, 1408), [1.0, 45.0, 0.5], 2, False, 'ncdhw'),
+])
+def test_fused_backward_matches_reference_grad_kernel_full_size(cuda_lib, name, input_size, depth_cfg, B, collapse, layout):
+    """dhd_mghs_pool_bwd at BASELINE's full sizes against the reference's OWN bev_pool_v2_grad
+    (ops/bev_pool_v2/src/bev_pool_cuda.cu:69-123, compiled unmodified into oracle/_ref) run over the four passes
+    the way QuickCumsumCuda.backward drives it (bev_pool.py:44-83): depth_grad / feat_grad rtol 1e-5."""
+    from oracle import ref_cuda_path as R
+    if not R.available():
+        pytest.skip('oracle/_ref not built')
+    from dhd_b200.pool import MghsPool, height_to_mask
+    cfg = _cfg_variant(input_size, depth_cfg)
+    rig = O.synthetic_rig(B, 6, input_size, src_size=(900, 1600), seed=33, flip_bda=True)
+    inputs, depth, feat, height = O.synthetic_inputs(cfg, B, seed=33, rig=rig)
+    inputs = tuple(t.cuda() for t in inputs)
+    depth, feat, height = depth.cuda(), feat.cuda(), height.cuda()
+    N, D = 6, depth.shape[1]
+    fH, fW = depth.shape[-2:]
+    C = cfg['C']
+    fr = O.frustum(cfg['depth'], cfg['input_size'], cfg['downsample']).cuda()
+    grids = [cfg['bev_grid']] + list(cfg['mask_grids'])
+    plan = MghsPool(B, N, D, fH, fW, C, grids[0]['x'], grids[0]['y'], [(g['z'], m) for m, g in enumerate(grids)])
+    coor = O.ego_coor(fr, inputs[1], inputs[3], inputs[4], inputs[5], inputs[6])
+    plan.prepare(coor=coor)
+    pm = height_to_mask(height, cfg['height_range'], cfg['mask_range'])
+    d_g = depth.clone().requires_grad_()
+    f_g = feat.view(B, N, C, fH, fW).permute(0, 1, 3, 4, 2).contiguous().requires_grad_()
+    outs = plan(d_g, f_g, pm, layout=layout)
+    gen = torch.Generator(device='cuda').manual_seed(35)
+    # gradients in the REFERENCE's output layout: (B, Dz*C, Dy, Dx) collapsed, (B, C, Dz, Dy, Dx) otherwise
+    ref_shapes = [(B, dz * C, plan.Dy, plan.Dx) if collapse else (B, C, dz, plan.Dy, plan.Dx) for dz in plan.dz]
+    gref = [torch.randn(s, device='cuda', generator=gen) for s in ref_shapes]
+    loss = 0
+    for o, g in zip(outs, gref):
+        o_ref = o.permute(0, 3, 1, 2) if layout == 'nhwc' else o
+        assert o_ref.shape == g.shape
+        loss = loss + (o_ref * g).sum()
+    loss.backward()
+    want_d, want_f = R.view_transform_backward_cuda(inputs, depth, feat, height, fr, cfg['height_range'],
+                                                    cfg['mask_range'], cfg['mask_grids'], gref, collapse_z=collapse)
+    _close_scaled(d_g.grad.view(B * N, D, fH, fW), want_d, name + ' depth_grad')
+    _close_scaled(f_g.grad.view(B * N, fH, fW, C).permute(0, 3, 1, 2), want_f, name + ' feat_grad')
+    # identical support: a point outside every grid / a pixel masked out of every pass gets exactly zero
+    assert int((d_g.grad.view(-1) != 0).sum()) == int((want_d.reshape(-1) != 0).sum())
+
+
+@pytest.mark.parametrize('B,input_size,depth_cfg,pass_id', [(4, (256, 704), [1.0, 45.0, 1.0], 3),
+                                                            (2, (512, 1408), [1.0, 45.0, 0.5], 0)])
+def test_dropin_backward_matches_reference_grad_kernel_full_size(cuda_lib, B, input_size, depth_cfg, pass_id):
+    """The drop-in dhd_bev_pool_v2_bwd (QuickCumsumCuda.backward of dhd_b200.pool) against the reference's own
+    bev_pool_v2_grad on one full-size pass (DHD-S B=4 high slab, DHD-L B=2 BEV pass), same ranks."""
+    from oracle import ref_cuda_path as R
+    if not R.available():
+        pytest.skip('oracle/_ref not built')
+    from dhd_b200.pool import bev_pool_v2
+    cfg = _cfg_variant(input_size, depth_cfg)
+    rig = O.synthetic_rig(B, 6, input_size, src_size=(900, 1600), seed=41)
+    inputs, depth, feat, _height = O.synthetic_inputs(cfg, B, seed=41, rig=rig)
+    inputs = tuple(t.cuda() for t in inputs)
+    N, D = 6, depth.shape[1]
+    fH, fW = depth.shape[-2:]
+    C = cfg['C']
+    fr = O.frustum(cfg['depth'], cfg['input_size'], cfg['downsample']).cuda()
+    coor = O.ego_coor(fr, inputs[1], inputs[3], inputs[4], inputs[5], inputs[6])
+    g = ([cfg['bev_grid']] + list(cfg['mask_grids']))[pass_id]
+    lower, interval, size = O.grid_infos(g['x'], g['y'], g['z'])
+    rb, rd, rf, st, ln = R.prepare_v2_cuda(coor, lower, interval, size.cuda())
+    d5 = depth.view(B, N, D, fH, fW).cuda().requires_grad_()
+    f5 = feat.view(B, N, C, fH, fW).permute(0, 1, 3, 4, 2).contiguous().cuda().requires_grad_()
+    shape = (B, int(size[2]), int(size[1]), int(size[0]), C)
+    out = bev_pool_v2(d5, f5, rd, rf, rb, shape, st, ln)                     # (B, C, Dz, Dy, Dx)
+    gout = torch.randn(out.shape, device='cuda', generator=torch.Generator(device='cuda').manual_seed(43))
+    (out * gout).sum().backward()
+    want_d, want_f = R.bev_pool_v2_grad_ref(gout.permute(0, 2, 3, 4, 1), d5.detach(), f5.detach(), rd, rf, rb)
+    _close_scaled(d5.grad, want_d, 'drop-in depth_grad')
+    _close_scaled(f5.grad, want_f, 'drop-in feat_grad')
