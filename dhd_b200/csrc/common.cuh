@@ -68,6 +68,45 @@ __device__ __forceinline__ long fast_div(long a, int b) {
   return fast_div(a, b, &r);
 }
 
+// ---- class index of predictor.get_occ (occ_head.py:141-153): `occ_pred.softmax(-1).argmax(-1)` ----------------
+// softmax is monotone, so this is the argmax of the logits -- except where fp32 rounding of exp / the division maps
+// two DIFFERENT logits onto the SAME probability: torch then returns the lower class index.  That needs the top two
+// logits within ~2e-7 of each other; callers run the plain argmax (first maximum wins) while tracking the runner-up
+// and fall back to this restatement of torch's kernel when `best - second <= kSoftmaxTieGap`.
+// torch (aten/src/ATen/native/cuda/PersistentSoftmax.cuh, softmax_warp_forward, n <= 32: one element per lane):
+// m = max x; e_k = expf(x_k - m); s = butterfly sum over 32 lanes (masked lanes hold exp(-inf) = 0);
+// p_k = e_k / s; then argmax with the lower index winning ties.  The butterfly adds lane l and lane l ^ offset for
+// offset = W/2 .. 1, i.e. the balanced tree below (fp32 addition is commutative, so every lane holds the same sum).
+constexpr float kSoftmaxTieGap = 1e-6f;
+
+template <int N>
+__device__ __forceinline__ int softmax_argmax_torch(const float (&x)[N]) {
+  static_assert(N >= 1 && N <= 32, "one element per lane");
+  constexpr int W = N <= 1 ? 1 : N <= 2 ? 2 : N <= 4 ? 4 : N <= 8 ? 8 : N <= 16 ? 16 : 32;
+  float m = x[0];
+#pragma unroll
+  for (int k = 1; k < N; ++k) m = fmaxf(m, x[k]);
+  float e[W], t[W];
+#pragma unroll
+  for (int k = 0; k < W; ++k) e[k] = t[k] = k < N ? expf(x[k] - m) : 0.f;
+#pragma unroll
+  for (int off = W / 2; off >= 1; off >>= 1)
+#pragma unroll
+    for (int l = 0; l < off; ++l) t[l] = __fadd_rn(t[l], t[l + off]);
+  const float s = t[0];
+  float best = __fdiv_rn(e[0], s);
+  int arg = 0;
+#pragma unroll
+  for (int k = 1; k < N; ++k) {
+    const float p = __fdiv_rn(e[k], s);
+    if (p > best) {
+      best = p;
+      arg = k;
+    }
+  }
+  return arg;
+}
+
 inline int sm_count() {
   static int n = 0;
   if (n == 0) {

@@ -134,15 +134,20 @@ split_nhwc8_kernel(const float* __restrict__ in, int HW, int C, int pb, __nv_bfl
     for (int k = 1; k < rows; ++k)
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] += red[threadIdx.x + k * cg][j];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(mean_out + (size_t)n * C + gi * 8 + j, acc[j] * inv);
+    // block partial, summed over the blocks in fixed order by mean_finish_kernel (deterministic: no atomics)
+    float* dst = mean_out + ((size_t)n * gridDim.x + blockIdx.x) * C + gi * 8;
+    reinterpret_cast<float4*>(dst)[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    reinterpret_cast<float4*>(dst)[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
   }
 }
 
-// per-image channel mean of an Act, 8 channels per thread, partial sums by atomicAdd (out pre-zeroed)
+// per-image channel mean of an Act, 8 channels per thread: every block writes its partial sums [n][block][C]
+// (four independent 16-byte loads in flight per thread), mean_finish_kernel adds them in block order -- bit-identical
+// from run to run (the first version combined the blocks with fp32 atomics: 2.0 TB/s and run-to-run ulp noise that
+// reached the height head's argmax through the ASPP's global branch)
 __global__ void __launch_bounds__(256)
 mean_hw8_kernel(const __nv_bfloat16* __restrict__ in, int ld, int coff, int part_stride, int parts, int C,
-                int HW, int pb, float* __restrict__ out, float inv) {
+                int HW, int pb, float* __restrict__ partial) {
   __shared__ float red[256][9];
   const int cg = C / 8, rows = 256 / cg;
   const int gi = threadIdx.x % cg, ri = threadIdx.x / cg;
@@ -151,9 +156,27 @@ mean_hw8_kernel(const __nv_bfloat16* __restrict__ in, int ld, int coff, int part
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
   if (ri < rows) {
-    for (int p = p0 + ri; p < p1; p += rows) {
+    const __nv_bfloat16* base = in + (size_t)n * HW * ld + coff + gi * 8;
+    int p = p0 + ri;
+    if (parts == 1) {
+      for (; p + 3 * rows < p1; p += 4 * rows) {
+        uint4 q[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) q[u] = __ldg(reinterpret_cast<const uint4*>(base + (size_t)(p + u * rows) * ld));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q[u]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            acc[2 * j] += __low2float(h[j]);
+            acc[2 * j + 1] += __high2float(h[j]);
+          }
+        }
+      }
+    }
+    for (; p < p1; p += rows) {
       float v[8];
-      load_parts8(in + ((size_t)n * HW + p) * ld + coff + gi * 8, parts, part_stride, v);
+      load_parts8(base + (size_t)p * ld, parts, part_stride, v);
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] += v[j];
     }
@@ -165,9 +188,22 @@ mean_hw8_kernel(const __nv_bfloat16* __restrict__ in, int ld, int coff, int part
     for (int k = 1; k < rows; ++k)
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] += red[threadIdx.x + k * cg][j];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(out + (size_t)n * C + gi * 8 + j, acc[j] * inv);
+    float* dst = partial + ((size_t)n * gridDim.x + blockIdx.x) * C + gi * 8;
+    reinterpret_cast<float4*>(dst)[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    reinterpret_cast<float4*>(dst)[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
   }
+}
+
+// out[n][c] = inv * sum_b partial[n][b][c], b ascending: one thread per (n, c)
+__global__ void __launch_bounds__(256)
+mean_finish_kernel(const float* __restrict__ partial, int N, int nblk, int C, float* __restrict__ out, float inv) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * C) return;
+  const int n = i / C, c = i - n * C;
+  const float* src = partial + (size_t)n * nblk * C + c;
+  float s = 0.f;
+  for (int b = 0; b < nblk; ++b) s += __ldg(src + (size_t)b * C);
+  out[i] = s * inv;
 }
 
 // out = x * gate[n][c] (SELayer's multiply, depthnet.py:169, when one feature map feeds two
@@ -529,7 +565,7 @@ mean_hw_kernel(const __nv_bfloat16* __restrict__ in, int ld, int coff, int part_
   if (g == 0 && c < C) {
     s = red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x];
     if (splits == 1) out[(size_t)n * C + c] = s * inv;
-    else atomicAdd(out + (size_t)n * C + c, s * inv);
+    else out[((size_t)n * splits + blockIdx.z) * C + c] = s;        // partial [n][split][C] for mean_finish_kernel
   }
 }
 
@@ -648,14 +684,34 @@ dcn_im2col_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int x_coff, int
   }
 }
 
-// ---- occupancy class map: argmax over the class logits (softmax is monotone, so
-// predictor.get_occ's softmax -> argmax -> uint8, occ_head.py:141-153, is the argmax of the logits;
-// first maximum wins as in torch.argmax).  One thread per voxel, logits [voxel][ncls] fp32.
+// ---- occupancy class map: predictor.get_occ's softmax -> argmax -> uint8 (occ_head.py:141-153).  One thread per
+// voxel, logits [voxel][ncls] fp32: plain argmax of the logits (first maximum wins, as torch.argmax), and where the
+// runner-up sits within kSoftmaxTieGap of the maximum the exact restatement of torch's softmax kernel decides
+// (common.cuh: rounding can merge two different logits into one probability, then the lower index wins).
+template <int NCLS>
 __global__ void __launch_bounds__(256)
 occ_argmax_kernel(const float* __restrict__ logits, long nvox, int ncls, uint8_t* __restrict__ out) {
   const long v = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= nvox) return;
   const float* row = logits + v * ncls;
+  if constexpr (NCLS > 0) {
+    float x[NCLS];
+#pragma unroll
+    for (int k = 0; k < NCLS; ++k) x[k] = row[k];
+    float best = x[0], second = -INFINITY;
+    int arg = 0;
+#pragma unroll
+    for (int k = 1; k < NCLS; ++k) {
+      second = fmaxf(second, fminf(x[k], best));
+      if (x[k] > best) {
+        best = x[k];
+        arg = k;
+      }
+    }
+    if (best - second <= kSoftmaxTieGap) arg = softmax_argmax_torch<NCLS>(x);
+    out[v] = (uint8_t)arg;
+    return;
+  }
   float best = row[0];
   int arg = 0;
   for (int k = 1; k < ncls; ++k) {
@@ -677,7 +733,9 @@ extern "C" long dhd_launch_count(void) { return g_launches; }
 extern "C" int dhd_occ_argmax(const float* logits, long nvox, int ncls, uint8_t* out, void* stream) {
   DHD_REQUIRE(logits && out, "null pointer");
   DHD_REQUIRE(nvox > 0 && ncls > 0 && ncls <= 256, "bad shape");
-  occ_argmax_kernel<<<(int)((nvox + 255) / 256), 256, 0, (cudaStream_t)stream>>>(logits, nvox, ncls, out);
+  // 18 = Occ3D-nuScenes classes (every DHD config): exact softmax-tie handling; other class counts: argmax of the logits
+  if (ncls == 18) occ_argmax_kernel<18><<<(int)((nvox + 255) / 256), 256, 0, (cudaStream_t)stream>>>(logits, nvox, ncls, out);
+  else occ_argmax_kernel<0><<<(int)((nvox + 255) / 256), 256, 0, (cudaStream_t)stream>>>(logits, nvox, ncls, out);
   DHD_CUDA_LAUNCH_CHECK("occ_argmax");
   return DHD_OK;
 }
@@ -705,21 +763,34 @@ static int pixels_per_block(int N, int HW) {
   return max(16, (HW + want - 1) / want);
 }
 
+extern "C" size_t dhd_mean_workspace_bytes(int N, int C, int HW) {
+  if (N <= 0 || C <= 0 || HW <= 0) return 0;
+  const int pb = pixels_per_block(N, HW);
+  const size_t nblk = (size_t)max((HW + pb - 1) / pb, 64);
+  return (size_t)N * nblk * C * sizeof(float);
+}
+
+static int mean_finish(const float* partial, int N, int nblk, int C, float* out, float inv, cudaStream_t st) {
+  mean_finish_kernel<<<(N * C + 255) / 256, 256, 0, st>>>(partial, N, nblk, C, out, inv);
+  DHD_CUDA_LAUNCH_CHECK("mean_finish");
+  return DHD_OK;
+}
+
 extern "C" int dhd_split_nhwc_mean(const float* in, int N, int HW, int C, void* out, int out_ld, int out_coff,
-                                   int part_stride, int parts, float* mean_out, void* stream) {
+                                   int part_stride, int parts, float* mean_out, float* workspace, void* stream) {
   DHD_REQUIRE(in && out, "null pointer");
   DHD_REQUIRE(N > 0 && HW > 0 && C > 0 && parts >= 1 && parts <= 3, "bad shape");
   DHD_REQUIRE(vec8_ok(C, out_ld, out_coff, part_stride, in, out), "split_nhwc_mean needs C % 8 == 0 and 16-byte alignment");
+  DHD_REQUIRE(mean_out == nullptr || (workspace != nullptr && ((uintptr_t)workspace & 15) == 0),
+              "mean_out needs a 16-byte aligned workspace of dhd_mean_workspace_bytes()");
   cudaStream_t st = (cudaStream_t)stream;
-  if (mean_out != nullptr) {
-    cudaError_t e = cudaMemsetAsync(mean_out, 0, (size_t)N * C * sizeof(float), st);
-    if (e != cudaSuccess) return fail((int)e, "%s: %ld", "memset(mean)", (long)e);
-  }
   const int pb = pixels_per_block(N, HW);
-  split_nhwc8_kernel<<<dim3((HW + pb - 1) / pb, N), 256, 0, st>>>(in, HW, C, pb, (__nv_bfloat16*)out, out_ld,
-                                                                 out_coff, part_stride, parts, mean_out,
-                                                                 1.0f / (float)HW);
+  const int nblk = (HW + pb - 1) / pb;
+  split_nhwc8_kernel<<<dim3(nblk, N), 256, 0, st>>>(in, HW, C, pb, (__nv_bfloat16*)out, out_ld, out_coff, part_stride,
+                                                    parts, mean_out != nullptr ? workspace : nullptr,
+                                                    1.0f / (float)HW);
   DHD_CUDA_LAUNCH_CHECK("split_nhwc8");
+  if (mean_out != nullptr) return mean_finish(workspace, N, nblk, C, mean_out, 1.0f / (float)HW, st);
   return DHD_OK;
 }
 
@@ -730,7 +801,7 @@ extern "C" int dhd_split_nhwc(const float* in, long rows, int C, void* out, int 
   DHD_REQUIRE(out_ld % 2 == 0 && out_coff % 2 == 0 && part_stride % 2 == 0, "channel offsets must be even");
   DHD_REQUIRE(((uintptr_t)in & 7) == 0, "input must be 8-byte aligned");
   if (vec8_ok(C, out_ld, out_coff, part_stride, in, out) && rows < (1L << 31))
-    return dhd_split_nhwc_mean(in, 1, (int)rows, C, out, out_ld, out_coff, part_stride, parts, nullptr, stream);
+    return dhd_split_nhwc_mean(in, 1, (int)rows, C, out, out_ld, out_coff, part_stride, parts, nullptr, nullptr, stream);
   const long total = rows * (C / 2);
   split_nhwc_kernel<<<(int)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       in, rows, C, (__nv_bfloat16*)out, out_ld, out_coff, part_stride, parts);
@@ -750,32 +821,28 @@ extern "C" int dhd_unpack_nhwc_to_nchw(const void* in, int in_ld, int in_coff, i
 }
 
 extern "C" int dhd_mean_hw(const void* in, int in_ld, int in_coff, int part_stride, int parts, int N,
-                           int C, int HW, float* out, void* stream) {
+                           int C, int HW, float* out, float* workspace, void* stream) {
   DHD_REQUIRE(in && out, "null pointer");
   DHD_REQUIRE(N > 0 && C > 0 && HW > 0 && parts >= 1 && parts <= 3, "bad shape");
-  cudaStream_t st8 = (cudaStream_t)stream;
+  DHD_REQUIRE(workspace != nullptr && ((uintptr_t)workspace & 15) == 0,
+              "mean_hw needs a 16-byte aligned workspace of dhd_mean_workspace_bytes()");
+  cudaStream_t st = (cudaStream_t)stream;
   if (vec8_ok(C, in_ld, in_coff, part_stride, in, out)) {
-    cudaError_t e = cudaMemsetAsync(out, 0, (size_t)N * C * sizeof(float), st8);
-    if (e != cudaSuccess) return fail((int)e, "%s: %ld", "memset(mean)", (long)e);
     const int pb = pixels_per_block(N, HW);
-    mean_hw8_kernel<<<dim3((HW + pb - 1) / pb, N), 256, 0, st8>>>((const __nv_bfloat16*)in, in_ld, in_coff,
-                                                                 part_stride, parts, C, HW, pb, out,
-                                                                 1.0f / (float)HW);
+    const int nblk = (HW + pb - 1) / pb;
+    mean_hw8_kernel<<<dim3(nblk, N), 256, 0, st>>>((const __nv_bfloat16*)in, in_ld, in_coff, part_stride, parts, C,
+                                                   HW, pb, workspace);
     DHD_CUDA_LAUNCH_CHECK("mean_hw8");
-    return DHD_OK;
+    return mean_finish(workspace, N, nblk, C, out, 1.0f / (float)HW, st);
   }
   const int cblocks = (C + 63) / 64;
   int splits = 1;
   if (HW > 4096) splits = min(64, max(1, (sm_count() * 4) / (cblocks * N)));
-  cudaStream_t st = (cudaStream_t)stream;
-  if (splits > 1) {
-    cudaError_t e = cudaMemsetAsync(out, 0, (size_t)N * C * sizeof(float), st);
-    if (e != cudaSuccess) return fail((int)e, "%s: %ld", "memset(mean)", (long)e);
-  }
   mean_hw_kernel<<<dim3(cblocks, N, splits), 256, 0, st>>>((const __nv_bfloat16*)in, in_ld, in_coff,
-                                                          part_stride, parts, C, HW, out,
+                                                          part_stride, parts, C, HW, splits > 1 ? workspace : out,
                                                           1.0f / (float)HW, splits);
   DHD_CUDA_LAUNCH_CHECK("mean_hw");
+  if (splits > 1) return mean_finish(workspace, N, splits, C, out, 1.0f / (float)HW, st);
   return DHD_OK;
 }
 

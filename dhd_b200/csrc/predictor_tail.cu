@@ -99,6 +99,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld2(uint32_t taddr, float& a, float& b) {
+  uint32_t r0, r1;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  a = __uint_as_float(r0);
+  b = __uint_as_float(r1);
+}
+
 // torch.nn.Softplus(beta=1, threshold=20): max(x, 0) + log1p(exp(-|x|)); above 20 the second term is below half an
 // ulp of x, so no branch is needed.  ex2 / lg2 are the MUFU approximations (abs error ~1e-7); the result is rounded to
 // bf16 right after.
@@ -284,8 +292,8 @@ predictor_tail_kernel(const __grid_constant__ TailMaps M, const __grid_constant_
       float* lo = P.logits != nullptr && valid ? P.logits + pix * kN2 + grp * kN2Half : nullptr;
       const float* b2 = s_b2 + grp * kN2Half;
       const uint32_t t2 = lane_addr + kAcc2Col + (uint32_t)(grp * kN2Half);
-      uint32_t occ_lo = 0, occ_hi = 0;
-      float best = 0.f;
+      uint32_t occ_lo = 0, occ_hi = 0, tie_mask = 0;
+      float best = 0.f, second = 0.f;
       int arg = 0;
 #pragma unroll
       for (int blk = 0; blk < kN2Half / 16; ++blk) {               // 9 x 16 columns
@@ -298,20 +306,45 @@ predictor_tail_kernel(const __grid_constant__ TailMaps M, const __grid_constant_
           v[j] += b2[col];
           if (k == 0) {
             best = v[j];
+            second = -INFINITY;
             arg = 0;
-          } else if (v[j] > best) {                                // strict: the first maximum wins, as torch.argmax
-            best = v[j];
-            arg = k;
+          } else {
+            second = fmaxf(second, fminf(v[j], best));
+            if (v[j] > best) {                                     // strict: the first maximum wins, as torch.argmax
+              best = v[j];
+              arg = k;
+            }
           }
           if (k == kCls - 1) {
             if (z < 4) occ_lo |= (uint32_t)arg << (8 * z);
             else occ_hi |= (uint32_t)arg << (8 * (z - 4));
+            if (best - second <= kSoftmaxTieGap) tie_mask |= 1u << z;   // softmax rounding may merge the two: exact path
           }
         }
         if (lo != nullptr) {
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             st_cs(reinterpret_cast<float4*>(lo + blk * 16) + j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+        }
+      }
+      if (P.occ != nullptr && __any_sync(kFull, tie_mask != 0)) {
+        // rare (top two logits of a z plane within 1e-6): re-read that plane's 18 logits and let the restatement of
+        // torch's softmax kernel pick the class.  Warp-uniform control flow: tcgen05.ld is .sync.aligned.
+#pragma unroll 1
+        for (int z = 0; z < kDz / 2; ++z) {
+          if (!__any_sync(kFull, (tie_mask >> z) & 1u)) continue;
+          float x[kCls];
+#pragma unroll
+          for (int i = 0; i < kCls / 2; ++i) {
+            tmem_ld2(t2 + (uint32_t)(z * kCls + 2 * i), x[2 * i], x[2 * i + 1]);
+            x[2 * i] += b2[z * kCls + 2 * i];
+            x[2 * i + 1] += b2[z * kCls + 2 * i + 1];
+          }
+          if ((tie_mask >> z) & 1u) {
+            const uint32_t a = (uint32_t)softmax_argmax_torch<kCls>(x);
+            if (z < 4) occ_lo = (occ_lo & ~(0xffu << (8 * z))) | (a << (8 * z));
+            else occ_hi = (occ_hi & ~(0xffu << (8 * (z - 4)))) | (a << (8 * (z - 4)));
+          }
         }
       }
       tc_fence_before();

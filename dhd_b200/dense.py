@@ -149,6 +149,20 @@ def pack_input(x, parts):
     return out
 
 
+_MEAN_WS = {}
+
+
+def mean_workspace(device, N, C, HW):
+    """Scratch of the deterministic channel-mean reductions (block partials), one buffer per (device, stream)."""
+    need = _lib.load().dhd_mean_workspace_bytes(N, C, HW)
+    key = (device, torch.cuda.current_stream().cuda_stream)
+    ws = _MEAN_WS.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(max(need, 1 << 20), dtype=torch.uint8, device=device)
+        _MEAN_WS[key] = ws
+    return ws
+
+
 def pack_any(x, parts, want_mean=False):
     """Logical (N, C, H, W) fp32 tensor in either memory format -> Act."""
     if x.dim() != 4:
@@ -170,9 +184,11 @@ def pack_nhwc(x, parts, want_mean=False):
         out.data.zero_()
     if want_mean and C % 8 == 0 and 256 % (C // 8) == 0:
         mean = torch.empty(N, C, device=x.device)
+        ws = mean_workspace(x.device, N, C, H * W)
         _lib.check(lib.dhd_split_nhwc_mean(ctypes.c_void_p(x.data_ptr()), N, H * W, C,
                                            ctypes.c_void_p(out.data.data_ptr()), out.ld, 0, Cp, parts,
-                                           ctypes.c_void_p(mean.data_ptr()), _stream()), 'split_nhwc_mean')
+                                           ctypes.c_void_p(mean.data_ptr()), ctypes.c_void_p(ws.data_ptr()),
+                                           _stream()), 'split_nhwc_mean')
         out.mean = mean
         return out
     _lib.check(lib.dhd_split_nhwc(ctypes.c_void_p(x.data_ptr()), N * H * W, C,

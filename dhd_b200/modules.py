@@ -51,8 +51,9 @@ def linear_rows(x, w, b=None, act=None, in_scale=None, in_shift=None, one_minus=
 
 def mean_hw(a):
     out = torch.empty(a.N, a.C, device=a.data.device)
+    ws = D.mean_workspace(a.data.device, a.N, a.C, a.H * a.W)
     _lib.check(_lib.load().dhd_mean_hw(_p(a.data), a.ld, a.coff, a.part_stride, a.parts, a.N, a.C,
-                                       a.H * a.W, _p(out), _stream()), 'mean_hw')
+                                       a.H * a.W, _p(out), _p(ws), _stream()), 'mean_hw')
     return out
 
 

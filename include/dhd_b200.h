@@ -438,12 +438,15 @@ int dhd_split_nhwc(const float* in, long rows, int C, void* out, int out_ld, int
 /* same for an (N, HW, C) tensor, optionally also writing the per-image channel means
  * (mean_out [N][C] or NULL): the SFA squeeze (mix.py:41) fused into the one read of the tensor */
 int dhd_split_nhwc_mean(const float* in, int N, int HW, int C, void* out, int out_ld, int out_coff,
-                        int part_stride, int parts, float* mean_out, void* stream);
+                        int part_stride, int parts, float* mean_out, float* workspace, void* stream);
 int dhd_unpack_nhwc_to_nchw(const void* in, int in_ld, int in_coff, int part_stride, int parts,
                             int N, int C, int H, int W, float* out, void* stream);
 /* out[n][c] = mean over the HW pixels (AdaptiveAvgPool2d(1): depthnet.py:77-82; mix.py:41) */
 int dhd_mean_hw(const void* in, int in_ld, int in_coff, int part_stride, int parts, int N, int C,
-                int HW, float* out, void* stream);
+                int HW, float* out, float* workspace, void* stream);
+/* bytes of the caller-owned scratch the two mean producers need (block partial sums, reduced in fixed order:
+ * the means are bit-identical from run to run) */
+size_t dhd_mean_workspace_bytes(int N, int C, int HW);
 /* y[r][o] = act(sum_k (x[r][k]*in_scale[k]+in_shift[k]) * w[o][k] + b[o]); one_minus: y = 1 - y.
  * fp32 CUDA-core path for the M = B*N row MLP / SE / fc chains (depthnet.py:119-169, mix.py:20-25) */
 int dhd_linear_rows(const float* x, int R, int K, const float* w, const float* b, int O, int act,

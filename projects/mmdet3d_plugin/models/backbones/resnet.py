@@ -5,11 +5,11 @@ forward on dhd_b200.encoders.CustomResNetEngine."""
 import torch
 import torch.nn as nn
 
-from dhd_b200.compat import BACKBONES, BasicBlock
+from dhd_b200.compat import BACKBONES, BasicBlock, EngineOwner
 
 
 @BACKBONES.register_module(force=True)
-class CustomResNet(nn.Module):
+class CustomResNet(EngineOwner, nn.Module):
     def __init__(self, numC_input, num_layer=[2, 2, 2], num_channels=None, stride=[2, 2, 2],
                  backbone_output_ids=None, norm_cfg=dict(type='BN'), with_cp=False, block_type='Basic',
                  precision='fp32'):
@@ -31,23 +31,19 @@ class CustomResNet(nn.Module):
         self.with_cp, self.precision = with_cp, precision
         self._engine = None
 
-    def _load_from_state_dict(self, *a, **k):
-        self._engine = None
-        return super()._load_from_state_dict(*a, **k)
-
     def forward(self, x, return_act=False):
         """x: (B, C, Dy, Dx) -> list of (B, C_i, Dy/2^(i+1), Dx/2^(i+1)) (Acts with return_act=True)."""
         from dhd_b200 import dense as D
         from dhd_b200.encoders import CustomResNetEngine
         from dhd_b200.modules import unpack
-        if self.training:
-            raise NotImplementedError('dhd_b200 CustomResNet: inference (eval-mode BatchNorm) only in this build')
+        from dhd_b200 import autograd as A
+        if not isinstance(x, D.Act) and x.is_cuda and A.wants_grad(self, x):
+            return A.resnet_forward(self, x)         # differentiable form (dhd_b200.autograd)
         with torch.no_grad():
             if not isinstance(x, D.Act):
                 if not x.is_cuda:
                     raise RuntimeError('dhd_b200: expected CUDA tensors (the hot path has no CPU fallback)')
                 x = D.pack_any(x, D.PRECISIONS[self.precision][0])
-            if self._engine is None:
-                self._engine = CustomResNetEngine(self, self.precision, x.data.device)
-            feats = self._engine(x)
+            dev = x.data.device
+            feats = self.cached_engine(dev, lambda: CustomResNetEngine(self, self.precision, dev))(x)
             return feats if return_act else [unpack(f) for f in feats]

@@ -4,7 +4,7 @@ forward on the B200 engine (dhd_b200.encoders.UNetEngine)."""
 import torch
 import torch.nn as nn
 
-from dhd_b200.compat import BACKBONES
+from dhd_b200.compat import BACKBONES, EngineOwner
 
 
 class DoubleConv(nn.Module):
@@ -40,7 +40,7 @@ class OutConv(nn.Module):
 
 
 @BACKBONES.register_module(force=True)
-class UNet(nn.Module):
+class UNet(EngineOwner, nn.Module):
     def __init__(self, n_channels, n_classes, bilinear=False, precision='fp32'):
         super().__init__()
         self.n_channels, self.n_classes, self.bilinear = n_channels, n_classes, bilinear
@@ -53,24 +53,20 @@ class UNet(nn.Module):
         self.precision = precision
         self._engine = None
 
-    def _load_from_state_dict(self, *a, **k):
-        self._engine = None
-        return super()._load_from_state_dict(*a, **k)
-
     def forward(self, x, return_act=False, out=None):
         """x: (B, n_channels, H, W) fp32 CUDA tensor (any memory format) or a dhd_b200.dense.Act ->
         (B, n_classes, H, W) fp32 (channels_last memory), or the Act with return_act=True."""
         from dhd_b200 import dense as D
         from dhd_b200.encoders import UNetEngine
         from dhd_b200.modules import unpack
-        if self.training:
-            raise NotImplementedError('dhd_b200 UNet: inference (eval-mode BatchNorm) only in this build')
+        from dhd_b200 import autograd as A
+        if not isinstance(x, D.Act) and x.is_cuda and A.wants_grad(self, x):
+            return A.unet_forward(self, x)           # differentiable form (dhd_b200.autograd)
         with torch.no_grad():
             if not isinstance(x, D.Act):
                 if not x.is_cuda:
                     raise RuntimeError('dhd_b200: expected CUDA tensors (the hot path has no CPU fallback)')
                 x = D.pack_any(x, D.PRECISIONS[self.precision][0])
-            if self._engine is None:
-                self._engine = UNetEngine(self, self.precision, x.data.device)
-            y = self._engine(x, out=out)
+            dev = x.data.device
+            y = self.cached_engine(dev, lambda: UNetEngine(self, self.precision, dev))(x, out=out)
             return y if return_act else unpack(y.slice(0, self.n_classes))

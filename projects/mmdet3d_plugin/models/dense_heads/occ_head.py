@@ -6,7 +6,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from dhd_b200.compat import HEADS, BaseModule, ConvModule, build_loss
+from dhd_b200.compat import HEADS, BaseModule, ConvModule, EngineOwner, build_loss
 
 # class frequencies of Occ3D-nuScenes used for the class-balanced CE weights (occ_head.py:10-29)
 nusc_class_frequencies = np.array([
@@ -15,7 +15,7 @@ nusc_class_frequencies = np.array([
 
 
 @HEADS.register_module(force=True)
-class predictor(BaseModule):
+class predictor(EngineOwner, BaseModule):
     def __init__(self, in_dim=256, out_dim=256, Dz=16, use_mask=True, weight_ce=1, weight_geo=1,
                  weight_sem=1, num_classes=18, use_predicter=True, class_balance=False, loss_occ=None,
                  precision='fp32'):
@@ -38,22 +38,37 @@ class predictor(BaseModule):
         self.precision = precision
         self._engine = None
 
-    def _load_from_state_dict(self, *a, **k):
-        self._engine = None
-        return super()._load_from_state_dict(*a, **k)
-
-    def forward(self, img_feats):
-        """img_feats: (B, C, Dy, Dx) fp32 CUDA tensor or a dhd_b200.dense.Act -> (B, Dx, Dy, Dz, n_cls)."""
+    def _engine_for(self, img_feats):
         from dhd_b200 import dense as D
         from dhd_b200.modules import PredictorEngine
+        if not isinstance(img_feats, D.Act):
+            if not img_feats.is_cuda:
+                raise RuntimeError('dhd_b200: expected CUDA tensors (the hot path has no CPU fallback)')
+            img_feats = D.pack_any(img_feats, D.PRECISIONS[self.precision][0])
+        dev = img_feats.data.device
+        return self.cached_engine(dev, lambda: PredictorEngine(self, self.precision, dev)), img_feats
+
+    def forward(self, img_feats):
+        """img_feats: (B, C, Dy, Dx) fp32 CUDA tensor or a dhd_b200.dense.Act -> (B, Dx, Dy, Dz, n_cls).
+        Under autograd the call runs the training engine and is differentiable (dhd_b200.autograd)."""
+        from dhd_b200 import autograd as A
+        from dhd_b200 import dense as D
+        if not isinstance(img_feats, D.Act) and img_feats.is_cuda and A.wants_grad(self, img_feats):
+            return A.predictor_forward(self, img_feats)
         with torch.no_grad():
-            if not isinstance(img_feats, D.Act):
-                if not img_feats.is_cuda:
-                    raise RuntimeError('dhd_b200: expected CUDA tensors (the hot path has no CPU fallback)')
-                img_feats = D.pack_any(img_feats, D.PRECISIONS[self.precision][0])
-            if self._engine is None:
-                self._engine = PredictorEngine(self, self.precision, img_feats.data.device)
-            return self._engine(img_feats)
+            engine, img_feats = self._engine_for(img_feats)
+            return engine(img_feats)
+
+    def forward_occ(self, img_feats):
+        """Inference tail in one go: forward + get_occ's softmax(-1).argmax(-1) (occ_head.py:141-153) -> uint8
+        (B, Dx, Dy, Dz) on the device.  In the bf16 speed mode the class map comes out of the fused tail kernel's
+        epilogue (dhd_predictor_tail) and the logits never reach HBM."""
+        with torch.no_grad():
+            engine, img_feats = self._engine_for(img_feats)
+            occ = torch.empty(img_feats.N, img_feats.W, img_feats.H, self.Dz, dtype=torch.uint8,
+                              device=img_feats.data.device)
+            engine(img_feats, occ=occ, want_logits=False)
+            return occ
 
     def loss(self, occ_pred, voxel_semantics, mask_camera):
         """occ_head.py:102-139: class-weighted masked cross-entropy + sem_scal + geo_scal (free class = 17), as a dict
@@ -76,6 +91,15 @@ class predictor(BaseModule):
                     loss_voxel_geo_scal=self.weight_geo * geo_scal_loss_with_mask(preds, labels, mask, non_empty_idx=17))
 
     def get_occ(self, occ_pred, img_metas=None):
-        """(B, Dx, Dy, Dz, C) -> list of (Dx, Dy, Dz) uint8 class maps (occ_head.py:141-153)."""
-        res = occ_pred.softmax(-1).argmax(-1)
+        """(B, Dx, Dy, Dz, C) logits -> list of (Dx, Dy, Dz) uint8 class maps (occ_head.py:141-153).  CUDA logits go
+        through dhd_occ_argmax (== softmax(-1).argmax(-1), tested incl. rounding ties); a uint8 tensor (the result of
+        forward_occ) is passed through."""
+        if occ_pred.dtype == torch.uint8:
+            res = occ_pred
+        elif occ_pred.is_cuda and occ_pred.dtype == torch.float32:
+            from dhd_b200.modules import occ_argmax
+            res = occ_argmax(occ_pred.detach().contiguous(),
+                             torch.empty(occ_pred.shape[:-1], dtype=torch.uint8, device=occ_pred.device))
+        else:
+            res = occ_pred.softmax(-1).argmax(-1)
         return list(res.cpu().numpy().astype(np.uint8))

@@ -1,26 +1,54 @@
-"""DHD detector shell (reference: projects/mmdet3d_plugin/models/detectors/DHD_model.py:10-241).
+"""DHD detectors (reference: projects/mmdet3d_plugin/models/detectors/DHD_model.py:10-241 `DHD`, 243-560 `DHD_stereo`).
 
-Wires the hot path exactly like DHD.extract_img_feat / forward_occ_train / simple_test_occ:
-image features -> MGHS -> [BEV encoder + three voxel encoders] -> cat -> SFA -> predictor.
-The image backbone / FPN and the BEV / voxel encoders are outside this build's scope
-(SURVEY.md 8(f)); they are built from the registry when their `type` is registered (e.g. by a
-real mmdet3d install) and otherwise left as None, in which case `forward_hot_path` takes the
-encoder outputs as arguments.  Child names follow DM:22-29 so checkpoints map unchanged.
+Same registry names, constructor kwargs, child names (DM:22-29: checkpoints map unchanged) and public methods as the
+reference -- extract_img_feat / extract_feat / forward_train / forward_occ_train / simple_test / simple_test_occ /
+forward_test / forward(return_loss) / train_step -- wired over the B200 modules: image features -> MGHS -> BEV encoder +
+three voxel encoders -> cat -> SFA -> predictor.  Every module is differentiable under autograd (dhd_b200.autograd), so
+`forward_train(...)` returns the reference's loss dict and `.backward()` runs the hand-written backward kernels.
+The image backbone / FPN (mmdet ResNet / Swin + CustomFPN) are outside the hot path: they are built
+from the registry when their `type` is registered (a real mmdet3d install) and are a `MissingModule` placeholder
+otherwise; `image_encoder` then expects the (B, N, C, fH, fW) image features in the `imgs` slot of `img_inputs`.
 """
+from collections import OrderedDict
+
 import torch
 
 from dhd_b200 import compat as C
 
 
+class MissingModule(torch.nn.Module):
+    """Placeholder for a config entry whose `type` is in no registry of this environment (the image backbone / FPN of
+    the reference come from mmdet, which is not installed here and outside the hot path): the detector still builds
+    with the reference's child names, and calling the placeholder says exactly what is missing."""
+
+    def __init__(self, typ, registry):
+        super().__init__()
+        self.missing_type, self.registry = str(typ), registry
+
+    def forward(self, *a, **k):
+        raise NotImplementedError('%s is not registered in the %s registry of this environment (image backbone / FPN '
+                                  'are outside the dhd_b200 hot path): install mmdet3d, register the class, or hand '
+                                  'DHD the (B, N, C, fH, fW) image features in place of the images' %
+                                  (self.missing_type, self.registry))
+
+
 def _maybe(registry, cfg):
+    """Build `cfg` from `registry` (parent registries included when it is an mmcv registry); an unknown type gives a
+    MissingModule placeholder that raises when it is called, never a silent None."""
     if cfg is None:
         return None
     typ = cfg.get('type')
-    return registry.build(cfg) if (not isinstance(typ, str) or typ in getattr(registry, 'module_dict', {typ: 1})) else None
+    if isinstance(typ, str) and registry.get(typ) is None:
+        return MissingModule(typ, getattr(registry, 'name', '?'))
+    return registry.build(cfg)
 
 
 @C.DETECTORS.register_module(force=True)
 class DHD(C.BaseModule):
+    """reference DHD_model.py:10-241 (on BEVDet <- CenterPoint <- MVXTwoStageDetector <- Base3DDetector): the same
+    public methods with the same signatures and loss-dict keys, so the reference's runner (`model.train_step` /
+    `model(return_loss=..., **data)`, tools/train.py:276, tools/test.py:267) drives the B200 path."""
+
     def __init__(self, img_view_transformer, mix=None, occ_head=None, img_backbone=None, img_neck=None,
                  img_bev_encoder_backbone=None, img_bev_encoder_neck=None,
                  img_voxel_encoder0_backbone=None, img_voxel_encoder0_neck=None,
@@ -43,6 +71,48 @@ class DHD(C.BaseModule):
         self.upsample = upsample
         self.train_cfg, self.test_cfg = train_cfg, test_cfg
 
+    @property
+    def with_img_neck(self):
+        return self.img_neck is not None
+
+    # ------------------------------------------------------------------ BEVDet pieces (bevdet.py:21-78)
+    def image_encoder(self, img, stereo=False):
+        """bevdet.py:21-44: (B, N, 3, H, W) images -> (B, N, C, fH, fW) features [+ the 1/4 stereo feature].
+        The image backbone / neck are outside this build: when they are not registered (MissingModule) the argument
+        must already be the (B, N, C_in, fH, fW) feature map the view transformer reads -- the injection point for an
+        external backbone."""
+        B, N, C, imH, imW = img.shape
+        vt = self.img_view_transformer
+        if self.img_backbone is None or isinstance(self.img_backbone, MissingModule):
+            fH, fW = vt.input_size[0] // vt.downsample, vt.input_size[1] // vt.downsample
+            if C == vt.in_channels and (imH, imW) == (fH, fW):
+                return img, None
+            if self.img_backbone is None:
+                raise NotImplementedError('DHD was built without img_backbone: pass (B, N, %d, %d, %d) image features' %
+                                          (vt.in_channels, fH, fW))
+            return self.img_backbone(img), None            # raises with the explanation
+        x = self.img_backbone(img.view(B * N, C, imH, imW))
+        stereo_feat = None
+        if stereo:
+            stereo_feat, x = x[0], x[1:]
+        if self.with_img_neck:
+            x = self.img_neck(x)
+            if type(x) in [list, tuple]:
+                x = x[0]
+        return x.view(B, N, x.shape[1], x.shape[2], x.shape[3]), stereo_feat
+
+    def prepare_inputs(self, inputs):
+        """bevdet.py:60-78: sensor -> key-ego transforms (fp64 inverse + products, as the reference)."""
+        assert len(inputs) == 7
+        B, N = inputs[0].shape[:2]
+        imgs, sensor2egos, ego2globals, intrins, post_rots, post_trans, bda = inputs
+        sensor2egos = sensor2egos.view(B, N, 4, 4)
+        ego2globals = ego2globals.view(B, N, 4, 4)
+        keyego2global = ego2globals[:, 0, ...].unsqueeze(1)
+        global2keyego = torch.inverse(keyego2global.double())
+        sensor2keyegos = (global2keyego @ ego2globals.double() @ sensor2egos.double()).float()
+        return [imgs, sensor2keyegos, ego2globals, intrins, post_rots, post_trans, bda]
+
     # DM:32-82: bev_encoder / voxel_encoder{0,1,2} = backbone -> neck (first output if a list)
     def _encode(self, backbone, neck, x):
         if backbone is None:
@@ -58,12 +128,106 @@ class DHD(C.BaseModule):
     def voxel_encoder(self, i, x):
         return self._encode(getattr(self, 'img_voxel_encoder%d' % i), getattr(self, 'img_voxel_neck%d' % i), x)
 
+    def voxel_encoder0(self, x):
+        return self.voxel_encoder(0, x)
+
+    def voxel_encoder1(self, x):
+        return self.voxel_encoder(1, x)
+
+    def voxel_encoder2(self, x):
+        return self.voxel_encoder(2, x)
+
     def view_transform(self, img_feat, cams):
         """img_feat (B, N, C, fH, fW); cams = (sensor2egos, ego2globals, intrins, post_rots,
         post_trans, bda) -> MGHS outputs (bev, depth, height, low, mid, high), DM:84-103."""
         vt = self.img_view_transformer
         mlp_input = vt.get_mlp_input(*cams)
         return vt([img_feat] + list(cams) + [mlp_input])
+
+    # ------------------------------------------------------------------ reference detector API (DM:84-241)
+    def extract_img_feat(self, img_inputs, img_metas=None, **kwargs):
+        """DM:84-114: img_inputs = (imgs, sensor2egos, ego2globals, intrins, post_rots, post_trans, bda) ->
+        (x_2d (B, 256, Dy, Dx), x_3d (B, 256, Dy, Dx), depth (B*N, D, fH, fW), height (B*N, H, fH, fW))."""
+        imgs, sensor2keyegos, ego2globals, intrins, post_rots, post_trans, bda = self.prepare_inputs(list(img_inputs))
+        x, _ = self.image_encoder(imgs)
+        x_2d, depth, height, mask_1, mask_2, mask_3 = self.view_transform(
+            x, (sensor2keyegos, ego2globals, intrins, post_rots, post_trans, bda))
+        x_2d = self.bev_encoder(x_2d)
+        x_3d = torch.cat((self.voxel_encoder0(mask_1), self.voxel_encoder1(mask_2), self.voxel_encoder2(mask_3)), dim=1)
+        return x_2d, x_3d, depth, height
+
+    def extract_feat(self, points, img_inputs, img_metas=None, **kwargs):
+        """DM:116-133 -> (x_2d, x_3d, pts_feats=None, depth, height)."""
+        x_2d, x_3d, depth, height = self.extract_img_feat(img_inputs, img_metas, **kwargs)
+        return x_2d, x_3d, None, depth, height
+
+    def forward_train(self, points=None, img_metas=None, gt_bboxes_3d=None, gt_labels_3d=None, gt_labels=None,
+                      gt_bboxes=None, img_inputs=None, proposals=None, gt_bboxes_ignore=None, **kwargs):
+        """DM:135-186 -> dict(loss_height, loss_occ, loss_voxel_sem_scal, loss_voxel_geo_scal); kwargs carry
+        voxel_semantics / mask_camera (B, Dx, Dy, Dz), gt_depth / gt_height (B, N, H_in, W_in)."""
+        x_2d, x_3d, _pts, depth, height = self.extract_feat(points, img_inputs=img_inputs, img_metas=img_metas, **kwargs)
+        losses = dict()
+        losses['loss_height'] = self.img_view_transformer.get_height_loss(kwargs['gt_depth'], kwargs['gt_height'], height)
+        losses.update(self.forward_occ_train([x_2d, x_3d], kwargs['voxel_semantics'], kwargs['mask_camera']))
+        return losses
+
+    def forward_occ_train(self, img_feats, voxel_semantics, mask_camera):
+        """DM:188-205."""
+        outs = self.occ_head(self.mix(torch.cat(img_feats, dim=1)))
+        return self.occ_head.loss(outs, voxel_semantics, mask_camera)
+
+    def simple_test(self, points, img_metas, img=None, rescale=False, **kwargs):
+        """DM:207-226 -> list of (Dx, Dy, Dz) uint8 class maps."""
+        x_2d, x_3d, _, _, _ = self.extract_feat(points, img_inputs=img, img_metas=img_metas, **kwargs)
+        return self.simple_test_occ([x_2d, x_3d], img_metas)
+
+    def simple_test_occ(self, img_feats, img_metas=None):
+        """DM:228-241: cat -> mix -> occ_head -> get_occ.  `img_feats` may also be the logits tensor itself (the
+        round-1 calling convention).  The head's fused inference tail produces the class map directly."""
+        if isinstance(img_feats, torch.Tensor):
+            return self.occ_head.get_occ(img_feats, img_metas)
+        fused = self.mix(torch.cat(list(img_feats), dim=1), return_act=True)
+        return self.occ_head.get_occ(self.occ_head.forward_occ(fused), img_metas)
+
+    def forward_test(self, points=None, img_inputs=None, img_metas=None, **kwargs):
+        """bevdet.py:168-204: one test-time augmentation only (aug_test asserts False in the reference too)."""
+        for var, name in [(img_inputs, 'img_inputs'), (img_metas, 'img_metas')]:
+            if not isinstance(var, list):
+                raise TypeError('{} must be a list, but got {}'.format(name, type(var)))
+        if len(img_inputs) != len(img_metas):
+            raise ValueError('num of augmentations ({}) != num of image meta ({})'.format(len(img_inputs), len(img_metas)))
+        if isinstance(img_inputs[0][0], list):
+            raise AssertionError('aug_test is not implemented (reference: bevdet.py:206-208)')
+        points = [points] if points is None else points
+        return self.simple_test(points[0], img_metas[0], img_inputs[0], **kwargs)
+
+    def forward(self, return_loss=True, **kwargs):
+        """mmdet3d Base3DDetector.forward: forward_train with the losses, forward_test otherwise."""
+        return self.forward_train(**kwargs) if return_loss else self.forward_test(**kwargs)
+
+    @staticmethod
+    def _parse_losses(losses):
+        """mmdet BaseDetector._parse_losses: total of every entry whose key contains 'loss' + scalar log values."""
+        log_vars = OrderedDict()
+        for name, value in losses.items():
+            if isinstance(value, torch.Tensor):
+                log_vars[name] = value.mean()
+            elif isinstance(value, list):
+                log_vars[name] = sum(v.mean() for v in value)
+            else:
+                raise TypeError('%s is not a tensor or list of tensors' % name)
+        loss = sum(v for k, v in log_vars.items() if 'loss' in k)
+        log_vars['loss'] = loss
+        return loss, OrderedDict((k, float(v.item())) for k, v in log_vars.items())
+
+    def train_step(self, data, optimizer=None):
+        """mmdet BaseDetector.train_step: what mmcv's EpochBasedRunner calls every iteration."""
+        loss, log_vars = self._parse_losses(self(**data))
+        return dict(loss=loss, log_vars=log_vars, num_samples=len(data['img_metas']) if 'img_metas' in data else
+                    int(data['img_inputs'][0].shape[0]))
+
+    def val_step(self, data, optimizer=None):
+        return self.train_step(data, optimizer)
 
     def forward_hot_path(self, img_feat, cams, encoded=None):
         """Image features -> occupancy logits (B, Dx, Dy, Dz, n_cls).  `encoded` = (x_2d, x_3d)
@@ -76,9 +240,6 @@ class DHD(C.BaseModule):
             x_2d, x_3d = encoded
         fused = self.mix(torch.cat([x_2d, x_3d], dim=1), return_act=True)
         return self.occ_head(fused), depth, height
-
-    def simple_test_occ(self, occ_pred, img_metas=None):
-        return self.occ_head.get_occ(occ_pred, img_metas)
 
 
 @C.DETECTORS.register_module(force=True)
@@ -175,6 +336,87 @@ class DHD_stereo(DHD):
             list_2d, list_3d = [pad(list_2d[0]), list_2d[0]], [pad(list_3d[0]), list_3d[0]]
         x_2d, x_3d = self.fuse_frames(list_2d, list_3d)
         return x_2d, x_3d, depth_key, height_key
+
+    # ------------------------------------------------------------------ reference detector API (DM:377-666)
+    def prepare_inputs(self, img_inputs, stereo=False):
+        """bevdet4d.py:208-288: split the N = N_views * num_frame images / transforms into per-frame lists, derive the
+        sensor -> key-ego transforms (fp64) and, for stereo, the current -> adjacent sensor transforms."""
+        B, N = img_inputs[0].shape[:2]
+        nf = self.num_frame
+        N = N // nf
+        imgs = img_inputs[0].view(B, N, nf, *img_inputs[0].shape[2:])
+        imgs = [t.squeeze(2) for t in torch.split(imgs, 1, 2)]
+        sensor2egos, ego2globals, intrins, post_rots, post_trans, bda = img_inputs[1:7]
+        sensor2egos = sensor2egos.view(B, nf, N, 4, 4)
+        ego2globals = ego2globals.view(B, nf, N, 4, 4)
+        keyego2global = ego2globals[:, 0, 0, ...].unsqueeze(1).unsqueeze(1)
+        global2keyego = torch.inverse(keyego2global.double())
+        sensor2keyegos = (global2keyego @ ego2globals.double() @ sensor2egos.double()).float()
+        curr2adjsensor = None
+        if stereo:
+            tf = self.temporal_frame
+            s_curr, e_curr = sensor2egos[:, :tf].double(), ego2globals[:, :tf].double()
+            s_adj, e_adj = sensor2egos[:, 1:tf + 1].double(), ego2globals[:, 1:tf + 1].double()
+            c2a = (torch.inverse(e_adj @ s_adj) @ e_curr @ s_curr).float()
+            curr2adjsensor = [p.squeeze(1) for p in torch.split(c2a, 1, 1)] + [None] * self.extra_ref_frames
+            assert len(curr2adjsensor) == nf
+        extra = [sensor2keyegos, ego2globals, intrins.view(B, nf, N, 3, 3), post_rots.view(B, nf, N, 3, 3),
+                 post_trans.view(B, nf, N, 3)]
+        extra = [[p.squeeze(1) for p in torch.split(t, 1, 1)] for t in extra]
+        sensor2keyegos, ego2globals, intrins, post_rots, post_trans = extra
+        return imgs, sensor2keyegos, ego2globals, intrins, post_rots, post_trans, bda, curr2adjsensor
+
+    def extract_stereo_ref_feat(self, x):
+        """bevstereo4d.py:20-54: the first backbone stage of the extra reference frame (its 1/4 stereo feature only)."""
+        if self.img_backbone is None or isinstance(self.img_backbone, MissingModule):
+            raise NotImplementedError('extract_stereo_ref_feat needs the image backbone (outside the hot path): hand '
+                                      'DHD_stereo the per-frame (features, stereo features) instead of images')
+        return self.image_encoder(x, stereo=True)[1]
+
+    def extract_img_feat(self, img_inputs, img_metas=None, pred_prev=False, sequential=False, **kwargs):
+        """DM:377-541.  img_inputs[0]: (B, N_views * num_frame, 3, H, W) images -- or, with the image backbone outside
+        this build, the pair (feats (B, N_views * num_frame, C, fH, fW), stereo_feats (B, N_views * num_frame, C_s, 4fH,
+        4fW)) that image_encoder(img, stereo=True) would produce for every frame.
+        -> (x_2d, x_3d, depth_key_frame, height_key_frame)."""
+        if sequential or pred_prev:
+            raise NotImplementedError('sequential / pred_prev inference (DM:401-402, 450-474) is not used by the DHD configs')
+        first = img_inputs[0]
+        injected = isinstance(first, (tuple, list))
+        lead = first[0] if injected else first
+        imgs, sensor2keyegos, ego2globals, intrins, post_rots, post_trans, bda, curr2adjsensor = \
+            self.prepare_inputs([lead] + list(img_inputs[1:7]), stereo=True)
+        if injected:
+            B, NF = first[1].shape[:2]
+            N = NF // self.num_frame
+            st = first[1].view(B, N, self.num_frame, *first[1].shape[2:])
+            stereo_feats = [t.squeeze(2).reshape(B * N, *first[1].shape[2:]) for t in torch.split(st, 1, 2)]
+            feats = imgs
+        else:
+            feats, stereo_feats = [], []
+            for fid, img in enumerate(imgs):
+                if fid == self.num_frame - self.extra_ref_frames:
+                    feats.append(None)
+                    stereo_feats.append(self.extract_stereo_ref_feat(img))
+                else:
+                    x, sf = self.image_encoder(img, stereo=True)
+                    feats.append(x)
+                    stereo_feats.append(sf)
+        return self.extract_bev_feat(feats, stereo_feats, sensor2keyegos, ego2globals, intrins, post_rots, post_trans,
+                                     bda, curr2adjsensor)
+
+    def extract_feat(self, points, img_inputs, img_metas=None, **kwargs):
+        x_2d, x_3d, depth, height = self.extract_img_feat(img_inputs, img_metas, **kwargs)
+        return x_2d, x_3d, None, depth, height
+
+    def forward_train(self, points=None, img_metas=None, gt_bboxes_3d=None, gt_labels_3d=None, gt_labels=None,
+                      gt_bboxes=None, img_inputs=None, proposals=None, gt_bboxes_ignore=None, **kwargs):
+        """DM:577-614 -> dict(loss_depth, loss_height, loss_occ, loss_voxel_sem_scal, loss_voxel_geo_scal)."""
+        x_2d, x_3d, _pts, depth, height = self.extract_feat(points, img_inputs=img_inputs, img_metas=img_metas, **kwargs)
+        losses = dict()
+        losses['loss_depth'], losses['loss_height'] = self.img_view_transformer.get_depth_and_height_loss(
+            kwargs['gt_depth'], kwargs['gt_height'], depth, height)
+        losses.update(self.forward_occ_train([x_2d, x_3d], kwargs['voxel_semantics'], kwargs['mask_camera']))
+        return losses
 
     def forward_hot_path(self, feats, stereo_feats, sensor2keyegos, ego2globals, intrins, post_rots, post_trans, bda,
                          curr2adjsensor):

@@ -9,7 +9,7 @@ Initialisation follows the reference (kaiming_normal for ASPP convs, BN weight 1
 import torch
 import torch.nn as nn
 
-from dhd_b200.compat import BasicBlock, build_conv_layer
+from dhd_b200.compat import BasicBlock, EngineOwner, build_conv_layer
 
 
 class _ASPPModule(nn.Module):
@@ -139,7 +139,7 @@ class _PlaneSweep:
         return out
 
 
-class DepthNet(_PlaneSweep, nn.Module):
+class DepthNet(EngineOwner, _PlaneSweep, nn.Module):
     """Depth + context head of MGHS_Depth / MGHS_Stereo (reference depthnet.py:172-415).
     stereo=True adds cost_volumn_net and the first block's 1x1 downsample; the plane-sweep cost volume
     (gen_grid + calculate_cost_volumn, 245-361) is one fused CUDA kernel, see calculate_cost_volumn."""
@@ -164,17 +164,11 @@ class DepthNet(_PlaneSweep, nn.Module):
         self.precision = precision
         self._engine = None
 
-    def _load_from_state_dict(self, *a, **k):
-        self._engine = None
-        return super()._load_from_state_dict(*a, **k)
-
     def forward_split(self, x, mlp_input, softmax=True, stereo_metas=None):
         """-> (depth (B*N, D, fH, fW) NCHW [softmax-ed], context (B*N, fH, fW, C) NHWC): the layouts the
         fused pool consumes, written directly by the layer epilogues."""
         from dhd_b200 import dense as D
         from dhd_b200.modules import DepthNetEngine
-        if self.training:
-            raise NotImplementedError('dhd_b200 DepthNet: inference (eval-mode BatchNorm) only in this build')
         if self.stereo != (stereo_metas is not None):
             # the reference fails the same way: the first BasicBlock's input width depends on the cost volume
             raise RuntimeError('DepthNet(stereo=%s) called %s stereo_metas' %
@@ -184,18 +178,18 @@ class DepthNet(_PlaneSweep, nn.Module):
                 raise RuntimeError('dhd_b200: expected CUDA tensors (the hot path has no CPU fallback)')
             x = D.pack_input(x, D.PRECISIONS[self.precision][0])
         with torch.no_grad():
-            if self._engine is None:
-                self._engine = DepthNetEngine(self, self.precision, x.data.device)
+            dev = x.data.device
+            engine = self.cached_engine(dev, lambda: DepthNetEngine(self, self.precision, dev))
             cv = None
             if self.stereo:
                 # depthnet.py:387-400: zeros when there is no previous frame, else the plane-sweep volume
                 scale = float(stereo_metas['downsample']) / stereo_metas['cv_downsample']
                 Hs, Ws = int(x.H * scale), int(x.W * scale)
                 first = stereo_metas['cv_feat_list'][0] is None
-                cv = self._engine.new_cost_volume(x.N, Hs, Ws, x.data.device, zero=first)
+                cv = engine.new_cost_volume(x.N, Hs, Ws, x.data.device, zero=first)
                 if not first:
                     self.calculate_cost_volumn(stereo_metas, out_act=cv)
-            return self._engine(x, mlp_input, softmax=softmax, cost_volume=cv)
+            return engine(x, mlp_input, softmax=softmax, cost_volume=cv)
 
     def forward(self, x, mlp_input, stereo_metas=None):
         """Reference signature: (B*N, D + C_context, fH, fW) logits, depthnet.py:362-415."""
@@ -203,7 +197,7 @@ class DepthNet(_PlaneSweep, nn.Module):
         return torch.cat([depth, ctx.permute(0, 3, 1, 2)], dim=1)
 
 
-class HeightNet(_PlaneSweep, nn.Module):
+class HeightNet(EngineOwner, _PlaneSweep, nn.Module):
     """Per-pixel height distribution head (reference depthnet.py:418-652)."""
 
     def __init__(self, in_channels, mid_channels, depth_channels, use_dcn=True, use_aspp=True,
@@ -227,29 +221,13 @@ class HeightNet(_PlaneSweep, nn.Module):
 
     def engine(self, device):
         from dhd_b200.modules import HeightNetEngine
-        if self._engine is None or self._engine.device != device:
-            self._engine = HeightNetEngine(self, self.precision, device)
-        return self._engine
-
-    def invalidate(self):
-        """Call after changing parameters (load_state_dict does it automatically)."""
-        self._engine = None
-
-    def _load_from_state_dict(self, *a, **k):
-        self._engine = None
-        return super()._load_from_state_dict(*a, **k)
-
-    def train(self, mode=True):
-        self._engine = None
-        return super().train(mode)
+        return self.cached_engine(device, lambda: HeightNetEngine(self, self.precision, device))
 
     def forward(self, x, mlp_input, stereo_metas=None, softmax=False):
         """x: (B*N, C, fH, fW) fp32 CUDA tensor or a dhd_b200.dense.Act; mlp_input (B, N, 27).
         Returns the height logits (B*N, H, fH, fW) like the reference (softmax=True fuses the
         channel softmax MGHS.forward applies next into the last layer's epilogue)."""
         from dhd_b200 import dense as D
-        if self.training:
-            raise NotImplementedError('dhd_b200 HeightNet: inference (eval-mode BatchNorm) only in this build')
         if stereo_metas is not None or self.stereo:
             raise NotImplementedError('HeightNet with a cost volume: no DHD module calls it that way '
                                       '(MGHS_Depth passes stereo_metas=None, lss_heightmap.py:787)')

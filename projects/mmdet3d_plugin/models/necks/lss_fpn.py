@@ -4,11 +4,11 @@ conv1x1.  Same parameter names (`conv.{0,1,3,4}`, `up2.{1,2,4}`), forward on dhd
 import torch
 import torch.nn as nn
 
-from dhd_b200.compat import NECKS
+from dhd_b200.compat import NECKS, EngineOwner
 
 
 @NECKS.register_module(force=True)
-class FPN_LSS(nn.Module):
+class FPN_LSS(EngineOwner, nn.Module):
     def __init__(self, in_channels, out_channels, scale_factor=4, input_feature_index=(0, 2), norm_cfg=dict(type='BN'),
                  extra_upsample=2, lateral=None, use_input_conv=False, precision='fp32'):
         super().__init__()
@@ -34,17 +34,14 @@ class FPN_LSS(nn.Module):
         self.precision = precision
         self._engine = None
 
-    def _load_from_state_dict(self, *a, **k):
-        self._engine = None
-        return super()._load_from_state_dict(*a, **k)
-
     def forward(self, feats, return_act=False, out=None):
         """feats: list of (B, C_i, H_i, W_i) tensors or Acts -> (B, out_channels, 2H, 2W)."""
         from dhd_b200 import dense as D
         from dhd_b200.encoders import FPNLSSEngine
         from dhd_b200.modules import unpack
-        if self.training:
-            raise NotImplementedError('dhd_b200 FPN_LSS: inference (eval-mode BatchNorm) only in this build')
+        from dhd_b200 import autograd as A
+        if all(not isinstance(f, D.Act) and f.is_cuda for f in feats) and A.wants_grad(self, *feats):
+            return A.fpn_forward(self, list(feats))  # differentiable form (dhd_b200.autograd)
         with torch.no_grad():
             parts = D.PRECISIONS[self.precision][0]
             acts = []
@@ -54,7 +51,6 @@ class FPN_LSS(nn.Module):
                         raise RuntimeError('dhd_b200: expected CUDA tensors (the hot path has no CPU fallback)')
                     f = D.pack_any(f, parts)
                 acts.append(f)
-            if self._engine is None:
-                self._engine = FPNLSSEngine(self, self.precision, acts[0].data.device)
-            y = self._engine(acts, out=out)
+            dev = acts[0].data.device
+            y = self.cached_engine(dev, lambda: FPNLSSEngine(self, self.precision, dev))(acts, out=out)
             return y if return_act else unpack(y)

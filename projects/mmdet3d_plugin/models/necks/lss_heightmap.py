@@ -18,7 +18,7 @@ voxel_pooling_v2, view_transform_core) are kept for API parity and run on the dr
 import torch
 import torch.nn as nn
 
-from dhd_b200.compat import NECKS, BaseModule, force_fp32
+from dhd_b200.compat import NECKS, BaseModule, EngineOwner, force_fp32
 from dhd_b200.pool import MghsPool, height_to_mask
 
 from ...ops import bev_pool_v2
@@ -29,7 +29,7 @@ _BEV_PASS_GRID = {'x': [-40, 40, 0.4], 'y': [-40, 40, 0.4], 'z': [-1, 5.4, 6.4],
 
 
 @NECKS.register_module(force=True)
-class MGHS(BaseModule):
+class MGHS(EngineOwner, BaseModule):
     def __init__(self, grid_config, input_size, downsample=16, in_channels=512, out_channels=64,
                  heightnet_cfg=dict(), accelerate=False, sid=False, collapse_z=True,
                  height_range=[-1.5, -1, 0, 0.5, 1, 1.5, 2, 2.5, 3, 3.5, 4], height_interval=0.5,
@@ -238,22 +238,28 @@ class MGHS(BaseModule):
         x = input[0]
         mlp_input = input[7]
         B, N, C, H, W = x.shape
-        if self.training:
-            raise NotImplementedError('dhd_b200 MGHS.forward is the inference form (eval-mode BatchNorm, no autograd graph); '
-                                      'training runs through dhd_b200.train / dhd_b200.pipeline.TrainStep')
         if not x.is_cuda:
             raise RuntimeError('dhd_b200: expected CUDA tensors (the hot path has no CPU fallback)')
+        from dhd_b200 import autograd as A
+        if A.wants_grad(self, x):
+            # differentiable form (training): forward with saved activations, backward through the pool backward,
+            # depth_net and -- via the height distribution's gradient (get_height_loss) -- HeightNet
+            if stereo_metas is not None or self.height_net.stereo:
+                raise NotImplementedError('MGHS: HeightNet is never called with a cost volume (lss_heightmap.py:787)')
+            plan = self._bins(input)
+            pix = lambda h: height_to_mask(h, self.height_range, self.mask_range)
+            outs = A.mghs_forward(self, input, plan, pix)
+            self.grid_config = self.mask_3_grid            # LH:455 quirk, as in view_transform
+            self.create_grid_infos(**self.grid_config)
+            return outs
         with torch.no_grad():
             xa = D.pack_input(x.reshape(B * N, C, H, W), D.PRECISIONS[self.precision][0])
-            if self._depth_engine is None:
-                self._depth_engine = DepthHeadEngine(self.depth_net, self.D, self.precision, x.device)
-            depth, feat = self._depth_engine(xa)                       # softmax-ed depth, NHWC context
+            dev = x.device
+            engine = self.cached_engine(dev, lambda: DepthHeadEngine(self.depth_net, self.D, self.precision, dev),
+                                        slot='_depth_engine')
+            depth, feat = engine(xa)                                   # softmax-ed depth, NHWC context
             height = self.height_net(xa, mlp_input, stereo_metas, softmax=True)
             return self.view_transform(input, depth, None, height, feat_nhwc=feat)
-
-    def _load_from_state_dict(self, *a, **k):
-        self._depth_engine = None
-        return super()._load_from_state_dict(*a, **k)
 
     # ------------------------------------------------------------------ mlp input (LH:493-526)
     def get_mlp_input(self, sensor2ego, ego2global, intrin, post_rot, post_tran, bda):
@@ -331,9 +337,10 @@ class MGHS_Depth(MGHS):
         from dhd_b200 import dense as D
         x, mlp_input = input[0], input[7]
         B, N, C, H, W = x.shape
-        if self.training:
-            raise NotImplementedError('dhd_b200 MGHS_Depth.forward is the inference form (eval-mode BatchNorm, no autograd '
-                                      'graph); the DepthNet backward is not built yet (DESIGN.md 7)')
+        from dhd_b200 import autograd as A
+        if A.wants_grad(self, x):
+            raise NotImplementedError('dhd_b200 MGHS_Depth.forward under autograd: the camera-aware DepthNet has no '
+                                      'backward in this build (DESIGN.md 7); wrap the call in torch.no_grad() or use eval()')
         if not x.is_cuda:
             raise RuntimeError('dhd_b200: expected CUDA tensors (the hot path has no CPU fallback)')
         with torch.no_grad():

@@ -6,7 +6,7 @@ sigmoid / residual fused into their epilogues."""
 import torch
 import torch.nn as nn
 
-from dhd_b200.compat import NECKS, BaseModule
+from dhd_b200.compat import NECKS, BaseModule, EngineOwner
 
 
 class channel_spatial_stage(nn.Module):
@@ -25,7 +25,7 @@ class channel_spatial_stage(nn.Module):
 
 
 @NECKS.register_module(force=True)
-class SFA(BaseModule):
+class SFA(EngineOwner, BaseModule):
     def __init__(self, in_channels, out_channels, stride=1, precision='fp32'):
         super().__init__()
         if stride != 1:
@@ -44,28 +44,28 @@ class SFA(BaseModule):
         self.precision = precision
         self._engine = None
 
-    def _load_from_state_dict(self, *a, **k):
-        self._engine = None
-        return super()._load_from_state_dict(*a, **k)
-
     def forward(self, inputs, return_act=False):
         """inputs: (B, 2C, Dy, Dx) fp32 CUDA tensor (any memory format) or a dhd_b200.dense.Act.
         Returns (B, C_out, Dy, Dx) fp32 (logical NCHW, channels_last memory), or the Act when
-        return_act=True (what predictor.forward consumes without a layout round trip)."""
+        return_act=True (what predictor.forward consumes without a layout round trip).
+        Under autograd (a parameter or the input requires grad) the call runs the training engine and is
+        differentiable (dhd_b200.autograd): BatchNorm on batch statistics in train(), frozen in eval()."""
+        from dhd_b200 import autograd as A
         from dhd_b200 import dense as D
         from dhd_b200.modules import SFAEngine
-        if self.training:
-            raise NotImplementedError('dhd_b200 SFA: inference (eval-mode BatchNorm) only in this build')
+        if not isinstance(inputs, D.Act):
+            if not inputs.is_cuda:
+                raise RuntimeError('dhd_b200: expected CUDA tensors (the hot path has no CPU fallback)')
+            if A.wants_grad(self, inputs):
+                return A.sfa_forward(self, inputs)
         with torch.no_grad():
             if not isinstance(inputs, D.Act):
-                if not inputs.is_cuda:
-                    raise RuntimeError('dhd_b200: expected CUDA tensors (the hot path has no CPU fallback)')
                 inputs = D.pack_any(inputs, D.PRECISIONS[self.precision][0], want_mean=True)
-            if self._engine is None:
-                self._engine = SFAEngine(self, self.precision, inputs.data.device)
+            dev = inputs.data.device
+            engine = self.cached_engine(dev, lambda: SFAEngine(self, self.precision, dev))
             if return_act:
-                return self._engine(inputs)
+                return engine(inputs)
             N, H, W = inputs.N, inputs.H, inputs.W
-            out = torch.empty(N, H, W, self.out_channels, device=inputs.data.device)
-            self._engine(inputs, out_f32=(out, D.nhwc_strides(self.out_channels, H, W)))
+            out = torch.empty(N, H, W, self.out_channels, device=dev)
+            engine(inputs, out_f32=(out, D.nhwc_strides(self.out_channels, H, W)))
             return out.permute(0, 3, 1, 2)

@@ -48,8 +48,25 @@ def test_occ_argmax_equals_softmax_argmax_incl_ties(cuda_lib):
     last class, constant rows, large-magnitude logits."""
     g = torch.Generator(device='cuda').manual_seed(3)
     logits = torch.randn(4, 200, 200, 16, 18, device='cuda', generator=g) * 3.0
-    want = logits.cpu().softmax(-1).argmax(-1).to(torch.uint8)          # the reference runs torch's argmax
-    assert torch.equal(_occ_argmax(logits).cpu(), want)
+    want = logits.softmax(-1).argmax(-1).to(torch.uint8)                # the reference's own ops, on the GPU as it runs them
+    assert torch.equal(_occ_argmax(logits), want)
+    # near-ties: two classes 0..3 ulps apart -- fp32 softmax may round both to ONE probability and torch then returns
+    # the lower index although the higher class has the larger logit (the kernel restates torch's softmax there)
+    n = 400000
+    # (merging needs a gap below ~6e-8, i.e. 1..3 ulps of logits of magnitude < 1)
+    near = torch.randn(n, 18, device='cuda', generator=g) * 0.1
+    top = near.max(dim=1).values + 0.2 * torch.rand(n, device='cuda', generator=g)
+    a = torch.randint(0, 18, (n,), device='cuda', generator=g)
+    b = (a + torch.randint(1, 18, (n,), device='cuda', generator=g)) % 18
+    ulps = torch.randint(0, 4, (n,), device='cuda', generator=g)
+    rows_i = torch.arange(n, device='cuda')
+    near[rows_i, a] = top
+    near[rows_i, b] = (top.view(torch.int32) + torch.where(top > 0, ulps, -ulps).int()).view(torch.float32)
+    want = near.softmax(-1).argmax(-1).to(torch.uint8)
+    got = _occ_argmax(near.contiguous())
+    merged = int((want != near.argmax(-1).to(torch.uint8)).sum())
+    assert merged > 0, 'the near-tie rows never exercised the softmax-rounding case'
+    assert torch.equal(got, want), '%d of %d near-tie rows differ from softmax(-1).argmax(-1)' % (int((got != want).sum()), n)
     # crafted rows: exact ties
     rows = torch.zeros(64, 18)
     rows[0, 3] = rows[0, 9] = 2.5                       # two-way tie -> 3

@@ -67,7 +67,7 @@ def test_fused_tail_matches_bf16_rounding_reference(cuda_lib, N, H, W):
     err = (got - want).abs()
     bad = err > 1e-3 + 1e-3 * want.abs()
     assert not bad.any(), '%d / %d logits off, max abs err %.3g (scale %.3g)' % (int(bad.sum()), bad.numel(), err.max(), want.abs().max())
-    assert torch.equal(occ.cpu(), logits.cpu().softmax(-1).argmax(-1).to(torch.uint8))
+    assert torch.equal(occ, logits.softmax(-1).argmax(-1).to(torch.uint8))      # torch's own ops on the GPU
     # the class map alone (the inference mode: logits never written) is the same map
     _, occ_only = _run_tail(head, t, want_logits=False)
     assert torch.equal(occ_only, occ)
@@ -93,6 +93,20 @@ def test_fused_tail_exact_ties_take_the_first_class(cuda_lib):
     want[3], want[5] = 7, 17
     assert torch.equal(occ.cpu(), want.view(1, 1, 1, 16).expand(1, 24, 16, 16))
     assert torch.equal(logits.cpu(), b.view(1, 1, 1, 16, 18).expand(1, 24, 16, 16, 18))
+    # near-ties 1..3 ulps apart in every z plane, the larger logit in the HIGHER class: softmax may merge them and
+    # torch then answers the lower class -- the epilogue's exact path must agree with torch's own ops on the GPU
+    with torch.no_grad():
+        nb = torch.randn(16, 18, generator=torch.Generator().manual_seed(4)) * 0.05
+        for z in range(16):
+            lo_c, hi_c = z % 9, 9 + (z * 5) % 9
+            top = nb[z].max() + 0.05 + 0.02 * z              # magnitude < 1: a few ulps are a gap below 6e-8
+            nb[z, lo_c] = top
+            nb[z, hi_c] = (top.view(torch.int32) + (z % 4)).view(torch.float32)
+        head.predicter[2].bias.copy_(nb.view(-1).to(head.predicter[2].bias.device))
+    logits, occ = _run_tail(head, t)
+    want = logits.softmax(-1).argmax(-1).to(torch.uint8)
+    assert torch.equal(occ, want)
+    assert bool((want != logits.argmax(-1).to(torch.uint8)).any()), 'no plane exercised the softmax-rounding case'
 
 
 def test_fused_tail_matches_layer_by_layer_engine_at_full_size(cuda_lib):
