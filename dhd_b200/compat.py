@@ -116,16 +116,16 @@ class EngineOwner:
     not touch the version counter -- such writers are caught by the train()/eval() switch that follows them in the
     reference's runner, or call `invalidate_engines(model)`."""
 
-    def _engine_key(self, device):
+    def _engine_state(self, device):
         import itertools
         return (str(device), bool(self.training)) + tuple(
             (id(t), t._version) for t in itertools.chain(self.parameters(), self.buffers()))
 
     def cached_engine(self, device, factory, slot='_engine'):
-        key = self._engine_key(device)
-        if self.__dict__.get(slot) is None or self.__dict__.get(slot + '_key') != key:
+        key = self._engine_state(device)
+        if self.__dict__.get(slot) is None or self.__dict__.get(slot + '__state') != key:
             self.__dict__[slot] = factory()
-            self.__dict__[slot + '_key'] = key
+            self.__dict__[slot + '__state'] = key
         return self.__dict__[slot]
 
     def invalidate(self):

@@ -111,6 +111,7 @@ class HotPathStep:
                        height_interval=0.1, mask_range=cfg['mask_range'],
                        mask_1_grid=dict(g[0], depth=cfg['depth']), mask_2_grid=dict(g[1], depth=cfg['depth']),
                        mask_3_grid=dict(g[2], depth=cfg['depth']), downsample=cfg['downsample'],
+                       loss_height_weight=0.1,           # DHD-S.py:100
                        precision=precision).eval().to(self.device)
         self.sfa = SFA(512, 256, precision=precision).eval().to(self.device)
         self.head = predictor(in_dim=256, out_dim=256, Dz=16, num_classes=18, use_predicter=True,
@@ -154,6 +155,7 @@ class HotPathStep:
         self.encoded_act = D.pack_nhwc(self.encoded, self.parts)
         self.occ = torch.empty(B, self.Dx, self.Dy, 16, dtype=torch.uint8, device=self.device)
         self.host_occ = torch.empty(self.occ.shape, dtype=torch.uint8, pin_memory=True)
+        self.result, self.host_result = self.occ, self.host_occ      # what a step hands back to the host
         # pool backward leg (timed separately)
         self.gouts = [torch.randn(o.shape, device=self.device, generator=gen) for o in self.outs]
         self.depth_grad = torch.empty(B * self.N, self.D, self.fH, self.fW, device=self.device)
@@ -313,7 +315,7 @@ class HotPathStep:
         (all on the compute stream, nothing overlapped)."""
         self.upload(host)
         self.run()
-        self.host_occ.copy_(self.occ, non_blocking=True)
+        self.host_result.copy_(self.result, non_blocking=True)
 
     # ---- streamed end-to-end: the copies of neighbouring steps overlap the compute of this one ----
     def e2e_open(self, host):
@@ -351,12 +353,12 @@ class HotPathStep:
         self._stage_free[slot].record(main)
         if next_host is not None:
             self._queue_h2d(next_host, slot ^ 1)
-        main.wait_event(self._d2h_done)                 # the previous class map has left `occ`
+        main.wait_event(self._d2h_done)                 # the previous result has left the device buffer
         self.run()
         self._step_done.record(main)
         self._d2h.wait_event(self._step_done)
         with torch.cuda.stream(self._d2h):
-            self.host_occ.copy_(self.occ, non_blocking=True)
+            self.host_result.copy_(self.result, non_blocking=True)
             self._d2h_done.record(self._d2h)
         self._i += 1
 
@@ -433,7 +435,7 @@ class TrainStep(HotPathStep):
         # nn.Dropout(0.5) behind HeightNet's ASPP (depthnet.py:81): on in the reference's training mode, i.e. together
         # with batch-statistics BatchNorm; off with the frozen (eval-like) BatchNorm unless asked for
         self.dropout = (0.5 if bn == 'batch' else 0.0) if dropout is None else float(dropout)
-        self.t_height = HeightNetTrainer(self.vt.height_net, self.device, loss_weight=0.1, dropout=self.dropout,
+        self.t_height = HeightNetTrainer(self.vt.height_net, self.device, loss_weight=self.vt.loss_height_weight, dropout=self.dropout,
                                          seed=seed + 17)
         enc_params = []
         if encoders:
@@ -453,31 +455,69 @@ class TrainStep(HotPathStep):
         self.bucket = shard.GradBucket(params)
         self.opt = torch.optim.AdamW(self.bucket.params, lr=2e-4, weight_decay=1e-2, fused=True)
         gen = torch.Generator(device=self.device).manual_seed(11)
-        self.labels = torch.randint(0, 18, (B, self.Dx, self.Dy, 16), device=self.device, generator=gen).to(torch.uint8)
-        self.mask_camera = (torch.rand(B, self.Dx, self.Dy, 16, device=self.device, generator=gen) < 0.5).to(torch.uint8)
         for g in self.gouts:
             g.mul_(1e-3)
-        # LiDAR supervision as the reference receives it (gt_depth / gt_height, DHD-S.py Collect3D keys): sparse
-        # (B, N, H_in, W_in) maps, ~2 % of the pixels carry a return; the step bins them itself (dhd_gt_downsample =
-        # get_downsampled_gt_depth / _height, lss_heightmap.py:625-701)
-        h_in, w_in = cfg['input_size']
-        hit = torch.rand(B, self.N, h_in, w_in, device=self.device, generator=gen) < 0.02
-        self.gt_depth = torch.where(hit, 1.0 + 59.0 * torch.rand(B, self.N, h_in, w_in, device=self.device, generator=gen),
-                                    torch.zeros((), device=self.device))
-        self.gt_height = torch.where(hit, -2.0 + 8.0 * torch.rand(B, self.N, h_in, w_in, device=self.device, generator=gen),
-                                     torch.zeros((), device=self.device))
+        self._label_seed = seed
         npix = B * self.N * self.fH * self.fW
         self.height_label = torch.empty(npix, dtype=torch.int32, device=self.device)
         self.depth_label = torch.empty(npix, dtype=torch.int32, device=self.device)
         self.height_fg = torch.empty(npix, dtype=torch.uint8, device=self.device)
         self.n_params = self.bucket.flat.numel()
         self.loss = None
+        # what a training step hands back to the host: [loss_occ, avg_factor, sem_scal, geo_scal, loss_height]
+        self.result = torch.zeros(5, device=self.device)
+        self.host_result = torch.zeros(5, pin_memory=True)
+        self.d2h_bytes = self.host_result.numel() * 4
+        self.grad_clip = 5.0                         # DHD-S.py:263 optimizer_config grad_clip max_norm=5, norm_type=2
+        self.lr_schedule = None                      # optional callable(step_index) -> lr (warm-up / step policy hooks)
+        self._step_index = 0
         T.set_bn_mode('frozen')
 
+    # ---- inputs: image features + camera geometry + the supervision of one step ------------------
+    def make_host_inputs(self, rig, seed):
+        """Pinned host buffers of one TRAINING step: what HotPathStep takes plus voxel_semantics / mask_camera
+        (B, Dx, Dy, Dz) and the sparse LiDAR maps gt_depth / gt_height (B, N, H_in, W_in) -- the keys the reference's
+        Collect3D hands to forward_train (DHD-S.py train_pipeline; ~2 % of the pixels carry a return)."""
+        h = super().make_host_inputs(rig, seed)
+        g = torch.Generator().manual_seed(1000 + seed)
+        B = self.B
+        h_in, w_in = self.cfg['input_size']
+        hit = torch.rand(B, self.N, h_in, w_in, generator=g) < 0.02
+        extra = {
+            'voxel_semantics': torch.randint(0, 18, (B, self.Dx, self.Dy, 16), generator=g).to(torch.uint8),
+            'mask_camera': (torch.rand(B, self.Dx, self.Dy, 16, generator=g) < 0.5).to(torch.uint8),
+            'gt_depth': torch.where(hit, 1.0 + 59.0 * torch.rand(B, self.N, h_in, w_in, generator=g), torch.zeros(())),
+            'gt_height': torch.where(hit, -2.0 + 8.0 * torch.rand(B, self.N, h_in, w_in, generator=g), torch.zeros(())),
+        }
+        h.update({k: v.contiguous().pin_memory() for k, v in extra.items()})
+        self.h2d_bytes = sum(v.numel() * v.element_size() for v in h.values())
+        return h
+
+    @property
+    def labels(self):
+        return self.static['voxel_semantics']
+
+    @property
+    def mask_camera(self):
+        return self.static['mask_camera']
+
+    @property
+    def gt_depth(self):
+        return self.static['gt_depth']
+
+    @property
+    def gt_height(self):
+        return self.static['gt_height']
+
+    def run(self, pool_events=None):
+        self.train_step(pool_events)
+
     def capture_train(self):
-        """Capture forward + losses + backward (graph 1) and the weight re-pack (graph 2) into CUDA graphs:
-        the step is ~190 library launches plus the small torch ops of the gate MLPs, i.e. launch-bound
-        when issued one by one.  The all-reduce and the optimizer stay eager."""
+        """Capture the step into CUDA graphs: forward up to the binned frustum (graph 1), [the pool kernel stays an
+        eager launch so bench.py can bracket it with CUDA events inside the timed region], the rest of the forward +
+        losses + backward (graph 2), and the weight re-pack (graph 3).  The step is ~360 library launches plus the
+        small torch ops of the gate MLPs, i.e. launch-bound when issued one by one.  The all-reduce, the gradient
+        clip and the optimizer stay eager."""
         for _ in range(2):
             self.train_step()
         torch.cuda.synchronize()
@@ -489,12 +529,14 @@ class TrainStep(HotPathStep):
                 self._refresh()
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
-            g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            g1, g2, g3 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
             with torch.cuda.graph(g1):
-                self._fwd_bwd()
+                self._fwd_front()
             with torch.cuda.graph(g2):
+                self._fwd_bwd_rest()
+            with torch.cuda.graph(g3):
                 self._refresh()
-            self.train_graph = (g1, g2)
+            self.train_graph = (g1, g2, g3)
         except Exception as e:  # noqa: BLE001
             self.train_graph = None
             self.train_graph_error = repr(e)[:300]
@@ -508,21 +550,61 @@ class TrainStep(HotPathStep):
         for t in ts:
             t.refresh()
 
-    def train_step(self):
+    def clip_grad_norm(self):
+        """optimizer_config = dict(grad_clip=dict(max_norm=5, norm_type=2)) (DHD-S.py:263): one L2 norm of the flat
+        gradient bucket, scaled in place when it exceeds max_norm (torch.nn.utils.clip_grad_norm_'s rule, no host sync)."""
+        if not self.grad_clip:
+            return None
+        flat = self.bucket.flat
+        norm = torch.linalg.vector_norm(flat)
+        flat.mul_(torch.clamp(self.grad_clip / (norm + 1e-6), max=1.0))
+        return norm
+
+    def train_step(self, pool_events=None):
         g = getattr(self, 'train_graph', None)
+        st = torch.cuda.current_stream()
         if g is not None:
             g[0].replay()
         else:
-            self._fwd_bwd()
-        self.bucket.all_reduce_async()
-        self.bucket.wait()
-        self.opt.step()
+            self._fwd_front()
+        if pool_events is not None:
+            pool_events[0].record(st)
+        self._pool()
+        if pool_events is not None:
+            pool_events[1].record(st)
         if g is not None:
             g[1].replay()
         else:
+            self._fwd_bwd_rest()
+        self.bucket.all_reduce_async()
+        self.bucket.wait()
+        self.grad_norm = self.clip_grad_norm()
+        if self.lr_schedule is not None:
+            for pg in self.opt.param_groups:
+                pg['lr'] = self.lr_schedule(self._step_index)
+        self.opt.step()
+        self._step_index += 1
+        if g is not None:
+            g[2].replay()
+        else:
             self._refresh()
 
+    def weight_hash(self):
+        """Order-sensitive fingerprint of every trainable parameter (fp64 sum of value x position weight): replicas that
+        stepped in lock-step have bit-identical hashes (bench.py all-gathers and compares them)."""
+        acc = torch.zeros((), dtype=torch.float64, device=self.device)
+        for i, p in enumerate(self.bucket.params):
+            v = p.detach().double().flatten()
+            w = torch.arange(1, v.numel() + 1, device=self.device, dtype=torch.float64).remainder_(8191.0).add_(1.0)
+            acc = acc + (v * w).sum() * (1.0 + 1e-3 * i)
+        return acc
+
     def _fwd_bwd(self):
+        self._fwd_front()
+        self._pool()
+        self._fwd_bwd_rest()
+
+    def _fwd_front(self):
         s = self.static
         B, N = self.B, self.N
         self.bucket.zero()
@@ -537,7 +619,9 @@ class TrainStep(HotPathStep):
                           post_rots=s['post_rots'], post_trans=s['post_trans'], bda=s['bda'],
                           deterministic=self.deterministic, workspace=self.workspace)
         self._last = {'depth': depth, 'feat': feat, 'height': height, 'pixmask': pixmask}
-        self._pool()
+
+    def _fwd_bwd_rest(self):
+        B, N = self.B, self.N
         # get_height_loss (lss_heightmap.py:595-622): labels from the height map, foreground = pixels whose depth
         # return falls into a depth bin (binned with the depth config the module holds at loss time, the LH:455 quirk)
         from . import train as T
@@ -587,3 +671,5 @@ class TrainStep(HotPathStep):
         self.run_pool_bwd()
         self.t_depth.backward(self.depth_grad, self.feat_grad)
         self.t_height.backward(want_dx=True)
+        self.result[:4].copy_(self.loss)
+        self.result[4:].copy_(self.loss_height)

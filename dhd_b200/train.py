@@ -204,6 +204,8 @@ class _TrainConv:
         if self.batch_bn:
             dy = self._backward_batch_bn(dy)
             bias_sums = None                       # a conv bias under a batch-statistics BN has zero gradient
+            if self.bias_p is not None and self.bias_p.requires_grad:
+                _ensure_grad(self.bias_p)          # ... which torch reports as zeros, not as None
         dw = D.conv2d_wgrad(x, dy, self.Cout, ksize=self.ksize, dilation=self.dilation, scale=self.scale,
                             stride=self.stride)
         if x.C != self.Cin:
