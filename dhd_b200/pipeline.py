@@ -91,6 +91,17 @@ def encoder_flops(B, Dy=200, Dx=200, c=64):
     return tot
 
 
+def pool_traffic_bytes():
+    """dram read+write bytes per launch of the pool kernel from the committed ncu capture."""
+    p = os.path.join(_ROOT, 'profiles', 'pool_fwd_traffic.json')
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get('dram_bytes_per_launch')
+        except Exception:  # noqa: BLE001
+            return None
+    return None
+
+
 class HotPathStep:
     def __init__(self, cfg, B, precision='bf16', deterministic=True, device='cuda', seed=0,
                  use_graph=True, encoders=False, keep_logits=False):
@@ -173,7 +184,8 @@ class HotPathStep:
             if self.encoders else ['[encoder stand-in: resident bf16 NHWC features]']
         return ['pack', 'depth_net(1x1+softmax)', 'HeightNet(+softmax)', 'height_to_mask',
                 'mghs_prepare(geometry+binning, 4 grids)', 'mghs_pool_fwd(nhwc, fused 4-pass)'] + mid + \
-            ['SFA', 'predictor', 'occ_argmax']
+            ['SFA', 'predictor 3x3 conv', 'fused head tail: Linear+Softplus+Linear+per-z argmax (dhd_predictor_tail)'
+             if self.head_engine.fused_tail_ok() and not self.keep_logits else 'predictor MLP (2 GEMMs) + occ_argmax']
 
     # ---- inputs -----------------------------------------------------------------------------
     def make_host_inputs(self, rig, seed):
@@ -378,14 +390,7 @@ class HotPathStep:
             ctypes.c_void_p(st.cuda_stream)), 'mghs_pool_bwd')
 
     def ncu_traffic_bytes(self):
-        """dram read+write bytes per launch of the pool kernel from the committed ncu capture."""
-        p = os.path.join(_ROOT, 'profiles', 'pool_fwd_traffic.json')
-        if os.path.exists(p):
-            try:
-                return json.load(open(p)).get('dram_bytes_per_launch')
-            except Exception:  # noqa: BLE001
-                return None
-        return None
+        return pool_traffic_bytes()
 
 
 class TrainStep(HotPathStep):
@@ -511,6 +516,15 @@ class TrainStep(HotPathStep):
 
     def run(self, pool_events=None):
         self.train_step(pool_events)
+
+    def stage_names(self):
+        mid = ['split(pool outputs -> bf16)', 'CustomResNet + FPN_LSS', '3x UNet'] if self.encoders else \
+            ['[encoder stand-in: resident features / resident pool-output gradients]']
+        return ['pack', 'depth_net(1x1+softmax)', 'HeightNet(+softmax, BatchNorm batch statistics, Dropout)', 'height_to_mask',
+                'mghs_prepare', 'mghs_pool_fwd', 'gt_downsample x2 + height loss'] + mid + \
+            ['SFA fwd', 'predictor fwd', 'occupancy loss (CE + sem_scal + geo_scal)', 'predictor bwd', 'SFA bwd'] + \
+            (['encoders bwd'] if self.encoders else []) + \
+            ['mghs_pool_bwd', 'depth_net bwd', 'HeightNet bwd', 'gradient all-reduce (NCCL)', 'grad clip', 'AdamW', 'weight re-pack']
 
     def capture_train(self):
         """Capture the step into CUDA graphs: forward up to the binned frustum (graph 1), [the pool kernel stays an

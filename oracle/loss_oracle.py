@@ -69,3 +69,26 @@ def predictor_loss(preds, labels, mask, class_weight, weight_ce=1.0, weight_sem=
     return dict(loss_occ=weight_ce * ce_loss(preds, labels, mask, class_weight),
                 loss_voxel_sem_scal=weight_sem * sem_scal_loss_with_mask(preds, labels, mask),
                 loss_voxel_geo_scal=weight_geo * geo_scal_loss_with_mask(preds, labels, mask, non_empty_idx=17))
+
+
+def _min_pool_bins(gt, ds, lo, interval, nbins):
+    """LH:625-701 (get_downsampled_gt_depth / _height, sid=False): ds x ds min-pool of a sparse (B, N, H, W) map with
+    zeros ignored (1e5 sentinel), binned; one-hot over nbins + 1 classes with class 0 (= out of range) dropped."""
+    B, N, H, W = gt.shape
+    t = torch.where(gt == 0.0, torch.full_like(gt, 1e5), gt)
+    t = t.view(B * N, H // ds, ds, W // ds, ds).permute(0, 1, 3, 2, 4).reshape(-1, ds * ds).min(dim=-1).values
+    t = (t - lo) / interval
+    t = torch.where((t < nbins + 1) & (t >= 0.0), t, torch.zeros_like(t))
+    return F.one_hot(t.long(), num_classes=nbins + 1).view(-1, nbins + 1)[:, 1:].float()
+
+
+def height_loss(gt_depth, gt_height, height, depth_cfg, n_depth, height_lo, height_interval, weight, downsample=16):
+    """MGHS.get_height_loss (LH:595-622): BCE between the height distribution (B*N, H, fH, fW) and the binned LiDAR
+    height on the pixels whose LiDAR depth falls into a depth bin, / max(1, #foreground), x loss_height_weight.
+    depth_cfg: the [lo, hi, step] the module holds at loss time (mask_3_grid['depth'] for MGHS, the LH:455 quirk)."""
+    H = height.shape[1]
+    labels = _min_pool_bins(gt_height, downsample, height_lo, height_interval, H)
+    fg = _min_pool_bins(gt_depth, downsample, depth_cfg[0] - depth_cfg[2], depth_cfg[2], n_depth).max(dim=1).values > 0.0
+    preds = height.permute(0, 2, 3, 1).contiguous().view(-1, H)
+    loss = F.binary_cross_entropy(preds[fg].float(), labels[fg], reduction='none').sum()
+    return weight * loss / max(1.0, float(fg.sum()))
