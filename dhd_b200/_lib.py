@@ -79,7 +79,6 @@ _SIGNATURES = {
     'dhd_upsample_bilinear_bwd': (ctypes.c_int, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     'dhd_maxpool2': (ctypes.c_int, [_P] + [_I] * 7 + [_P, _I, _I, _I, _I, _P]),
     'dhd_upsample_bilinear': (ctypes.c_int, [_P] + [_I] * 9 + [_P, _I, _I, _I, _I, _P]),
-    'dhd_probe_write_bw': (ctypes.c_int, [_P, ctypes.c_size_t, _I, _I, _I, _P]),
     'dhd_split_nhwc': (ctypes.c_int, [_P, ctypes.c_long, _I, _P] + [_I] * 4 + [_P]),
     'dhd_split_nhwc_mean': (ctypes.c_int, [_P, _I, _I, _I, _P] + [_I] * 4 + [_P, _P, _P]),
     'dhd_mean_workspace_bytes': (ctypes.c_size_t, [_I, _I, _I]),

@@ -194,16 +194,27 @@ mean_hw8_kernel(const __nv_bfloat16* __restrict__ in, int ld, int coff, int part
   }
 }
 
-// out[n][c] = inv * sum_b partial[n][b][c], b ascending: one thread per (n, c)
+// out[n][c] = inv * sum_b partial[n][b][c] in a FIXED order: 8 slices per (n, c) (slice s adds the blocks b = s, s + 8,
+// ... ascending), then the 8 slice sums ascending -- one block = 32 channels x 8 slices, coalesced over the channels
 __global__ void __launch_bounds__(256)
 mean_finish_kernel(const float* __restrict__ partial, int N, int nblk, int C, float* __restrict__ out, float inv) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N * C) return;
-  const int n = i / C, c = i - n * C;
-  const float* src = partial + (size_t)n * nblk * C + c;
+  __shared__ float red[8][33];
+  const int cl = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int cblocks = (C + 31) / 32;
+  const int n = blockIdx.x / cblocks, c = (blockIdx.x % cblocks) * 32 + cl;
   float s = 0.f;
-  for (int b = 0; b < nblk; ++b) s += __ldg(src + (size_t)b * C);
-  out[i] = s * inv;
+  if (c < C) {
+    const float* src = partial + (size_t)n * nblk * C + c;
+    for (int b = sl; b < nblk; b += 8) s += __ldg(src + (size_t)b * C);
+  }
+  red[sl][cl] = s;
+  __syncthreads();
+  if (sl == 0 && c < C) {
+    float t = red[0][cl];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) t += red[k][cl];
+    out[(size_t)n * C + c] = t * inv;
+  }
 }
 
 // out = x * gate[n][c] (SELayer's multiply, depthnet.py:169, when one feature map feeds two
@@ -771,7 +782,7 @@ extern "C" size_t dhd_mean_workspace_bytes(int N, int C, int HW) {
 }
 
 static int mean_finish(const float* partial, int N, int nblk, int C, float* out, float inv, cudaStream_t st) {
-  mean_finish_kernel<<<(N * C + 255) / 256, 256, 0, st>>>(partial, N, nblk, C, out, inv);
+  mean_finish_kernel<<<N * ((C + 31) / 32), 256, 0, st>>>(partial, N, nblk, C, out, inv);
   DHD_CUDA_LAUNCH_CHECK("mean_finish");
   return DHD_OK;
 }

@@ -421,147 +421,10 @@ __device__ __forceinline__ void gather_cell(const PoolParams& P, int cell, int l
   }
 }
 
-template <int MAXZ, int MINB>
-__global__ void __launch_bounds__(256, MINB) mghs_pool_nhwc_kernel(const PoolParams P) {
-  const int lane = threadIdx.x & 31;
-  const int warps = (gridDim.x * blockDim.x) >> 5;
-  for (int cell = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; cell < P.ncell; cell += warps) {
-    float2 acc[MAXZ];
-#pragma unroll
-    for (int k = 0; k < MAXZ; ++k) acc[k] = make_float2(0.f, 0.f);
-    gather_cell<MAXZ, false>(P, cell, lane, 0, acc);
-#pragma unroll
-    for (int k = 0; k < MAXZ; ++k) {
-      if (k < P.nplanes) {
-        float* dst = P.plane_ptr[k] + (size_t)cell * P.plane_cell_stride[k];
-        st_cs(reinterpret_cast<float2*>(dst) + lane, acc[k]);
-      }
-    }
-  }
-}
-
-// v2 of the NHWC pool: the cell's output column lives in SHARED memory (one private column
-// per warp, planes x 64 floats), so the plane index is a plain address (no register-array
-// switch), registers drop to ~40 and six blocks fit per SM.  Lane l accumulates channels
-// (2l, 2l+1) of every plane into its own smem slots -- no atomics, no barriers -- and the
-// column then leaves as 16-byte streaming stores, one contiguous dz*256-byte run per pass.
-// Empty cells (78 % of a DHD-S grid) skip shared memory and store zeros straight away.
-//
-// Work split: a warp owns a CONTIGUOUS run of cells chosen so that every warp gets the same
-// cost, cost(cell) = kCellCost + entries(cell).  The bins of a DHD-S frame are heavy-tailed
-// (median 16, max 256 entries; a strided split leaves the slowest warp with 4x the mean), and
-// the exclusive scan made by prepare already is the cumulative cost, so each warp finds its run
-// with one binary search over it -- deterministic, no atomics, contiguous output per warp.
-constexpr int kCellCost = 2;
-
-__device__ __forceinline__ int bin_start(const PoolParams& P, int cell) {
-  return __ldg(P.cell_start + cell) + __ldg(P.blk_prefix + cell / kScanChunk);
-}
-// smallest cell in [0, ncell] whose cumulative cost reaches `target`
-__device__ __forceinline__ int find_cell(const PoolParams& P, long target, int total) {
-  int lo = 0, hi = P.ncell;
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    const long cum = (long)kCellCost * mid + (mid < P.ncell ? bin_start(P, mid) : total);
-    if (cum >= target) hi = mid;
-    else lo = mid + 1;
-  }
-  return lo;
-}
-
-__global__ void __launch_bounds__(256, 6) mghs_pool_nhwc_smem_kernel(const PoolParams P) {
-  extern __shared__ float4 col_all[];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int warps = (gridDim.x * blockDim.x) >> 5;
-  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  float4* col4 = col_all + (size_t)wid * P.nplanes * 16;     // [plane][16] float4
-  float2* col2 = reinterpret_cast<float2*>(col4);            // [plane][32] float2
-  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  const int nq = P.nplanes * 16;                             // float4 per column
-  const int total = __ldg(P.total_entries);
-  const long cost = (long)kCellCost * P.ncell + total;
-  int cell = find_cell(P, cost * gw / warps, total);
-  const int cell_end = gw + 1 == warps ? P.ncell : find_cell(P, cost * (gw + 1) / warps, total);
-  int n = cell < cell_end && !P.probe ? __ldg(P.cell_count + cell) : 0;
-  while (cell < cell_end) {
-    const int next = cell + 1;
-    const int n_next = next < cell_end && !P.probe ? __ldg(P.cell_count + next) : 0;   // prefetch
-    if (n != 0) {
-      for (int i = lane; i < nq; i += 32) col4[i] = zero4;
-      __syncwarp();
-      const int s = bin_start(P, cell);
-      for (int base = 0; base < n; base += 32) {
-        const int m = min(32, n - base);
-        int pix = 0;
-        float dv = 0.f;
-        uint32_t bits = 0;
-        if (lane < m) {
-          const int4 e = __ldg(P.entries + s + base + lane);
-          pix = e.y;
-          dv = __ldg(P.depth + e.x);
-          const int pm = P.pixmask != nullptr ? (int)__ldg(P.pixmask + pix) : 0;
-          bits = plane_bits(P, (uint32_t)e.z, pm);
-        }
-        for (int j = 0; j < m; j += 4) {
-          int px[4];
-          float d[4];
-          uint32_t pb[4];
-          float2 f[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int jj = min(j + u, 31);
-            px[u] = __shfl_sync(kFull, pix, jj);
-            d[u] = __shfl_sync(kFull, dv, jj);
-            pb[u] = __shfl_sync(kFull, bits, jj);
-            if (j + u >= m) pb[u] = 0;
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            f[u] = make_float2(0.f, 0.f);
-            if (pb[u] != 0) f[u] = __ldg(reinterpret_cast<const float2*>(P.feat + (size_t)px[u] * kC) + lane);
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            uint32_t b = pb[u];
-            while (b != 0) {
-              const int z = __ffs(b) - 1;
-              b &= b - 1;
-              float2 a = col2[z * 32 + lane];
-              a.x = fmaf(f[u].x, d[u], a.x);
-              a.y = fmaf(f[u].y, d[u], a.y);
-              col2[z * 32 + lane] = a;
-            }
-          }
-        }
-      }
-      __syncwarp();
-    }
-#pragma unroll
-    for (int p = 0; p < DHD_MAX_PASSES; ++p) {
-      if (p < P.npass) {
-        const int q = P.pass_q[p];                                  // dz * 16 float4
-        float4* dst = reinterpret_cast<float4*>(P.pass_ptr[p]) + (size_t)cell * q;
-        const float4* src = col4 + P.zoff[p] * 16;
-        for (int i = lane; i < q; i += 32) st_cs(dst + i, n != 0 ? src[i] : zero4);
-      }
-    }
-    if (n != 0) __syncwarp();
-    cell = next;
-    n = n_next;
-  }
-}
-
-// v3 of the NHWC pool: the same cell-owner gather, but every output byte leaves the SM through
-// the TMA unit (cp.async.bulk shared -> global) instead of the LSU:
-//   * a run of empty cells is ONE bulk copy per pass out of a zero tile in shared memory that is
-//     never written after set-up (lanes 0..npass-1 issue one pass each, nothing to wait for);
-//   * a non-empty cell accumulates into the warp's private shared-memory column exactly as in v2
-//     and the column then leaves as one bulk copy per pass (dz*256 contiguous bytes).  Columns are
-//     double-buffered per warp, so the gather of the next cell overlaps the TMA read of this one;
-//     only the planes a cell touched are re-zeroed when its buffer comes round again.
-// The warps therefore issue almost no store instructions (v2 spent 41 % of its issue slots in
-// the store loop, profiles/r01_pool_fwd_v3.txt) and never stall on store back-pressure: the SM's
-// instruction stream is the gather alone while the TMA engine keeps HBM writes saturated.
+// (The register-column, shared-memory-column and per-cell TMA kernels that preceded the streaming kernel -- v1..v3,
+// profiles/r01_pool_fwd_v1_regs.txt .. r01_pool_fwd_v3.txt -- were removed in round 2; git history keeps them.)
+// Output bytes leave the SM through the TMA unit (cp.async.bulk shared -> global): a run of empty cells is ONE bulk
+// copy per pass out of a zero tile, a finished column one bulk copy per pass.
 __device__ __forceinline__ void bulk_store(void* gdst, uint32_t ssrc, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc),
                "r"(bytes)
@@ -575,234 +438,8 @@ __device__ __forceinline__ void bulk_store_hint(void* gdst, uint32_t ssrc, uint3
 __device__ __forceinline__ uint32_t smem_addr(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
 }
-__device__ __forceinline__ int find_cell_c(const PoolParams& P, long target, int total, int cell_cost) {
-  int lo = 0, hi = P.ncell;
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    const long cum = (long)cell_cost * mid + (mid < P.ncell ? bin_start(P, mid) : total);
-    if (cum >= target) hi = mid;
-    else lo = mid + 1;
-  }
-  return lo;
-}
 
-
-// Gather of one cell's bin into the warp's shared-memory column (lane l owns channels 2l, 2l+1
-// of every plane).  Entries are consumed in ascending order, 8 at a time:
-//   * the 8 context rows of group g+1 are requested before group g is accumulated (register
-//     double buffer), and the next 32 binned entries before the current 32 are consumed, so the
-//     L2 latency of one request overlaps the arithmetic of the previous one;
-//   * accumulation is plane-major: for every plane touched by the group the column slot is read
-//     once, receives the (up to 8) products in entry order, and is written once -- the slot of a
-//     plane no longer makes a shared-memory read-after-write round trip per entry (every entry
-//     hits the BEV plane).
-// The summation order per output element is ascending frustum-point order, as in v2.
-// Returns the planes written.
-constexpr int kG = 8;
-struct Batch { int pix; float dv; uint32_t bits; };
-__device__ __forceinline__ Batch load_batch(const PoolParams& P, int s, int n, int base, int lane) {
-  Batch b = {0, 0.f, 0u};
-  if (base + lane < n) {
-    const int4 e = __ldg(P.entries + s + base + lane);
-    b.pix = e.y;
-    b.dv = __ldg(P.depth + e.x);
-    const int pm = P.pixmask != nullptr ? (int)__ldg(P.pixmask + b.pix) : 0;
-    b.bits = plane_bits(P, (uint32_t)e.z, pm);
-    if (P.probe == 3) b.bits = b.dv == 123.456f ? 1u : 0u;
-  }
-  return b;
-}
-__device__ __forceinline__ void load_group(const PoolParams& P, const Batch& b, int j, int lane, float2 (&f)[kG]) {
-#pragma unroll
-  for (int u = 0; u < kG; ++u) {
-    const int px = __shfl_sync(kFull, b.pix, (j + u) & 31);
-    const uint32_t pb = __shfl_sync(kFull, b.bits, (j + u) & 31);
-    f[u] = make_float2(0.f, 0.f);
-    if (j + u < 32 && pb != 0) f[u] = __ldg(reinterpret_cast<const float2*>(P.feat + (size_t)px * kC) + lane);
-  }
-}
-__device__ __forceinline__ uint32_t gather_cell_smem(const PoolParams& P, int s, int n, float2* col2, int lane) {
-  uint32_t touched = 0;
-  Batch cur = load_batch(P, s, n, 0, lane);
-  float2 f[kG], fn[kG];
-  load_group(P, cur, 0, lane, f);
-  for (int base = 0; base < n; base += 32) {
-    const int m = min(32, n - base);
-    const bool more = base + 32 < n;
-    Batch nxt = {0, 0.f, 0u};
-    if (more) nxt = load_batch(P, s, n, base + 32, lane);
-    touched |= __reduce_or_sync(kFull, cur.bits);
-    for (int j = 0; j < m; j += kG) {
-      // request the next group's rows (of this batch, or the first group of the next batch)
-      if (j + kG < m) load_group(P, cur, j + kG, lane, fn);
-      else if (more) load_group(P, nxt, 0, lane, fn);
-      float d[kG];
-      uint32_t pb[kG];
-      uint32_t uni = 0;
-#pragma unroll
-      for (int u = 0; u < kG; ++u) {
-        d[u] = __shfl_sync(kFull, cur.dv, (j + u) & 31);
-        pb[u] = __shfl_sync(kFull, cur.bits, (j + u) & 31);
-        if (j + u >= 32) pb[u] = 0;            // lanes >= m carry bits == 0 already
-        uni |= pb[u];
-      }
-      while (uni != 0) {
-        const int z = __ffs(uni) - 1;
-        uni &= uni - 1;
-        float2 a = col2[z * 32 + lane];
-#pragma unroll
-        for (int u = 0; u < kG; ++u) {
-          if ((pb[u] >> z) & 1u) {
-            a.x = fmaf(f[u].x, d[u], a.x);
-            a.y = fmaf(f[u].y, d[u], a.y);
-          }
-        }
-        col2[z * 32 + lane] = a;
-      }
-#pragma unroll
-      for (int u = 0; u < kG; ++u) f[u] = fn[u];
-    }
-    cur = nxt;
-  }
-  return touched;
-}
-
-template <bool HINT>
-__global__ void __launch_bounds__(256, 2) mghs_pool_nhwc_tma_kernel(const PoolParams P, int cell_cost,
-                                                                 int zero_bytes, int chunk_cells, int windows) {
-  extern __shared__ __align__(128) uint8_t smem_pool[];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int wpb = blockDim.x >> 5;
-  const uint32_t col_bytes = (uint32_t)P.nplanes * 256u;
-  {
-    float4* z = reinterpret_cast<float4*>(smem_pool);
-    const int n16 = (zero_bytes + wpb * 2 * (int)col_bytes) / 16;
-    for (int i = threadIdx.x; i < n16; i += blockDim.x) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  __syncthreads();
-  uint64_t pol = 0;
-  if (HINT) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-  const uint32_t zero_s = smem_addr(smem_pool);
-  uint8_t* col_g = smem_pool + zero_bytes + (size_t)wid * 2 * col_bytes;
-  const uint32_t col_s = smem_addr(col_g);
-
-  const int warps = (gridDim.x * blockDim.x) >> 5;
-  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int total = __ldg(P.total_entries);
-  const long cost = (long)cell_cost * P.ncell + total;
-  // Work distribution.  chunk_cells > 0 (default): warps take chunks of consecutive cells from a
-  // global counter, so at any moment the whole GPU writes inside one sliding window of each
-  // output tensor -- the address pattern of a plain fill (measured: a fill with one private
-  // contiguous run per warp reaches 4.9 TB/s, a sliding window 5.9 TB/s, scripts/bench_pool.py
-  // probes) -- and heavy bins cannot leave a tail.  chunk_cells == 0: the static cost-balanced
-  // split of v2 (one contiguous run per warp).
-  int cell = 0, cell_end = 0;
-  if (chunk_cells == 0) {
-    cell = find_cell_c(P, cost * gw / warps, total, cell_cost);
-    cell_end = gw + 1 == warps ? P.ncell : find_cell_c(P, cost * (gw + 1) / warps, total, cell_cost);
-  }
-  // this lane's pass when it issues the zero-run copies
-  int my_q = 0;
-  char* my_out = nullptr;
-#pragma unroll
-  for (int p = 0; p < DHD_MAX_PASSES; ++p) {
-    if (p < P.npass && lane == p) {
-      my_q = P.pass_q[p];
-      my_out = reinterpret_cast<char*>(P.pass_ptr[p]);
-    }
-  }
-  int buf = 0;
-  uint32_t touched0 = 0, touched1 = 0;     // planes written in column buffer 0 / 1 by its last cell
-
-  for (;;) {
-  if (chunk_cells != 0) {
-    int ch = 0;
-    if (lane == 0) ch = atomicAdd(P.sched, 1);
-    ch = __shfl_sync(kFull, ch, 0);
-    // `windows` sliding windows evenly spaced over the cell range advance together, so dense
-    // (gather-heavy) and empty (write-only) regions of the grid are in flight at the same time
-    const int nchunks = (P.ncell + chunk_cells - 1) / chunk_cells;
-    const int per_win = (nchunks + windows - 1) / windows;
-    if (ch >= per_win * windows) break;
-    const int cidx = (ch % windows) * per_win + ch / windows;
-    if (cidx >= nchunks) continue;
-    cell = cidx * chunk_cells;
-    cell_end = min(cell + chunk_cells, P.ncell);
-  }
-  while (cell < cell_end) {
-    const int nb = min(32, cell_end - cell);
-    const int cnt = lane < nb && P.probe != 1 ? __ldg(P.cell_count + cell + lane) : 0;
-    const int s_mine = (lane < nb && cnt != 0) ? bin_start(P, cell + lane) : 0;
-    const uint32_t nz = __ballot_sync(kFull, cnt != 0);
-    int pos = 0;
-    while (pos < nb) {
-      const uint32_t rest = nz >> pos;
-      const int run = rest != 0 ? __ffs(rest) - 1 : nb - pos;
-      if (run > 0) {
-        if (my_out != nullptr) {
-          size_t bytes = (size_t)run * my_q * 16;
-          char* dst = my_out + (size_t)(cell + pos) * my_q * 16;
-          while (bytes != 0) {
-            const uint32_t b = bytes < (size_t)zero_bytes ? (uint32_t)bytes : (uint32_t)zero_bytes;
-            if (HINT) bulk_store_hint(dst, zero_s, b, pol);
-            else bulk_store(dst, zero_s, b);
-            dst += b;
-            bytes -= b;
-          }
-        }
-        pos += run;
-      }
-      if (pos >= nb) break;
-      // ---------------------------------------------------------------- non-empty cell
-      const int c = cell + pos;
-      const int n = __shfl_sync(kFull, cnt, pos);
-      const int s = __shfl_sync(kFull, s_mine, pos);
-      float2* col2 = reinterpret_cast<float2*>(col_g + (size_t)buf * col_bytes);
-      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");       // the copy that last read this buffer is done with it
-      __syncwarp();
-      uint32_t t = buf ? touched1 : touched0;
-      while (t != 0) {
-        const int z = __ffs(t) - 1;
-        t &= t - 1;
-        col2[z * 32 + lane] = make_float2(0.f, 0.f);
-      }
-      const uint32_t touched = P.probe == 2 ? 0u : gather_cell_smem(P, s, n, col2, lane);
-      if (buf) touched1 = touched; else touched0 = touched;
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) {
-        const uint32_t src = col_s + (uint32_t)buf * col_bytes;
-#pragma unroll
-        for (int p = 0; p < DHD_MAX_PASSES; ++p) {
-          if (p < P.npass) {
-            const uint32_t bytes = (uint32_t)P.pass_q[p] * 16u;
-            char* dst = reinterpret_cast<char*>(P.pass_ptr[p]) + (size_t)c * bytes;
-            if (HINT) bulk_store_hint(dst, src + (uint32_t)P.zoff[p] * 256u, bytes, pol);
-            else bulk_store(dst, src + (uint32_t)P.zoff[p] * 256u, bytes);
-          }
-        }
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      }
-      buf ^= 1;
-      ++pos;
-    }
-    cell += nb;
-  }
-  if (chunk_cells == 0) break;
-  }
-  if (chunk_cells != 0 && lane == 0) {
-    // the last warp to run dry re-arms the scheduler for the next launch on this workspace
-    if (atomicAdd(P.sched + 1, 1) == warps - 1) {
-      P.sched[0] = 0;
-      P.sched[1] = 0;
-    }
-  }
-  // shared memory must outlive every bulk copy that reads it
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-}
-
+constexpr int kG = 8;       // context rows requested per group (register double buffer)
 
 // v4 of the NHWC pool ("stream"): same single-write output path as v3 (TMA bulk copies of zero
 // runs and of finished columns), but the gather no longer walks one cell at a time.  Under a
@@ -1256,15 +893,23 @@ height_to_mask_kernel(const float* __restrict__ height, int npix, int H, int HW,
   pixmask[pix] = (int8_t)id;
 }
 
-// integer tuning knob read once from the environment (bench / profiling experiments only)
-static int tuning(const char* name, int dflt) {
+// Integer tuning knobs of the streaming kernel.  Read ONCE per process (function-local statics): prepare and the pool
+// launch always see the same values.  DHD_POOL_SWEEP=1 (scripts/bench_pool.py only) re-reads the environment on every
+// call so one process can sweep them.
+static int tuning_env(const char* name, int dflt) {
   const char* v = getenv(name);
   return v != nullptr && *v != 0 ? atoi(v) : dflt;
 }
+static bool tuning_sweep() {
+  static const bool on = tuning_env("DHD_POOL_SWEEP", 0) != 0;
+  return on;
+}
+#define DHD_TUNE(name, dflt) \
+  ([]() -> int { static const int v = tuning_env(name, dflt); return tuning_sweep() ? tuning_env(name, dflt) : v; }())
 
 // number of equal-cost work chunks (same value in prepare and in the pool launch)
 static int pool_nch(int ncell) {
-  int n = tuning("DHD_POOL_NCH", 16384);
+  int n = DHD_TUNE("DHD_POOL_NCH", 32768);
   if (n > kMaxChunks) n = kMaxChunks;
   if (n > ncell) n = ncell;
   return n < 1 ? 1 : n;
@@ -1291,7 +936,7 @@ static int fill_pool_params(const dhd_mghs_cfg* cfg, const WsLayout& w, const vo
     if (p < cfg->n_pass) off += cfg->dz[p];
   }
   P->nplanes = off;
-  P->probe = tuning("DHD_POOL_PROBE", 0);
+  P->probe = DHD_TUNE("DHD_POOL_PROBE", 0);
   P->out_bf16 = 0;
   return DHD_OK;
 }
@@ -1373,7 +1018,7 @@ extern "C" int dhd_mghs_prepare(const dhd_mghs_cfg* cfg, const float* coor, cons
     const int nch = pool_nch(w.ncell);
     mghs_chunks_kernel<<<(w.ncell + 1 + 255) / 256, 256, 0, st>>>(
         (const int*)(ws + w.cell_start), (const int*)(ws + w.blk_prefix), (const int*)(ws + w.total_entries),
-        w.ncell, nch, max(1, tuning("DHD_POOL_CELLCOST", 8)), (int2*)(ws + w.chunks));
+        w.ncell, nch, max(1, DHD_TUNE("DHD_POOL_CELLCOST", 8)), (int2*)(ws + w.chunks));
     DHD_CUDA_LAUNCH_CHECK("mghs_chunks");
   }
   return DHD_OK;
@@ -1444,22 +1089,21 @@ extern "C" int dhd_mghs_pool_fwd(const dhd_mghs_cfg* cfg, const float* depth, co
   if (layout == DHD_LAYOUT_NHWC_BF16) {
     P.out_bf16 = 1;
     layout = DHD_LAYOUT_NHWC;
-    DHD_REQUIRE(tuning("DHD_POOL_V", 4) == 4, "bf16 outputs need the streaming pool kernel");
   }
-  if (layout == DHD_LAYOUT_NHWC && tuning("DHD_POOL_V", 4) == 4) {
+  if (layout == DHD_LAYOUT_NHWC) {
     for (int p = 0; p < cfg->n_pass; ++p)
       DHD_REQUIRE(((uintptr_t)out_host[p] & 15) == 0, "NHWC outputs must be 16-byte aligned");
-    const int threads = tuning("DHD_POOL_THREADS", 128);
+    const int threads = DHD_TUNE("DHD_POOL_THREADS", 128);
     DHD_REQUIRE(threads == 32 || threads == 64 || threads == 128, "stream pool: 32, 64 or 128 threads per block");
-    const int zero_bytes = tuning("DHD_POOL_ZT", 4096) / 256 * 256;
-    const int hint = tuning("DHD_POOL_HINT", 1);
-    const int cap = tuning("DHD_POOL_PERSM", 4);
-    const int windows = max(1, tuning("DHD_POOL_WINDOWS", 1));
+    const int zero_bytes = DHD_TUNE("DHD_POOL_ZT", 4096) / 256 * 256;
+    const int hint = DHD_TUNE("DHD_POOL_HINT", 1);
+    const int cap = DHD_TUNE("DHD_POOL_PERSM", 4);
+    const int windows = max(1, DHD_TUNE("DHD_POOL_WINDOWS", 1));
     const int wpb = threads / 32;
     const size_t smem = (size_t)zero_bytes + (size_t)wpb * 2 * P.nplanes * 256;
     DHD_REQUIRE(smem <= 227 * 1024, "pool column buffers do not fit in shared memory");
-    const int minb = tuning("DHD_POOL_MINB", 4) >= 5 ? 5 : 4;
-    const int prefetch = tuning("DHD_POOL_PREFETCH", 1);
+    const int minb = DHD_TUNE("DHD_POOL_MINB", 4) >= 5 ? 5 : 4;
+    const int prefetch = DHD_TUNE("DHD_POOL_PREFETCH", 1);
     void (*kern)(const PoolParams, int, int, int) =
         hint ? (minb == 5 ? mghs_pool_stream_kernel<true, 5> : mghs_pool_stream_kernel<true, 4>)
              : (minb == 5 ? mghs_pool_stream_kernel<false, 5> : mghs_pool_stream_kernel<false, 4>);
@@ -1470,59 +1114,6 @@ extern "C" int dhd_mghs_pool_fwd(const dhd_mghs_cfg* cfg, const float* depth, co
     const int grid = min((P.nch + wpb - 1) / wpb, sm_count() * per_sm);
     kern<<<grid, threads, smem, st>>>(P, zero_bytes, windows, prefetch);
     DHD_CUDA_LAUNCH_CHECK("mghs_pool_stream");
-  } else if (layout == DHD_LAYOUT_NHWC && tuning("DHD_POOL_V", 4) == 3) {
-    for (int p = 0; p < cfg->n_pass; ++p)
-      DHD_REQUIRE(((uintptr_t)out_host[p] & 15) == 0, "NHWC outputs must be 16-byte aligned");
-    const int threads = tuning("DHD_POOL_THREADS", 256);
-    const int zero_bytes = tuning("DHD_POOL_ZT", 4096) / 256 * 256;
-    const int cell_cost = tuning("DHD_POOL_CELLCOST", 2);
-    const int hint = tuning("DHD_POOL_HINT", 0);
-    const int cap = tuning("DHD_POOL_PERSM", 8);
-    const int chunk_cells = tuning("DHD_POOL_CHUNK", 8);
-    const int windows = max(1, tuning("DHD_POOL_WINDOWS", 8));
-    const int wpb = threads / 32;
-    const size_t smem = (size_t)zero_bytes + (size_t)wpb * 2 * P.nplanes * 256;
-    DHD_REQUIRE(smem <= 227 * 1024, "pool column buffers do not fit in shared memory");
-    static size_t smem_set[2] = {0, 0};
-    if (smem > smem_set[hint != 0]) {
-      if (hint) cudaFuncSetAttribute(mghs_pool_nhwc_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      else cudaFuncSetAttribute(mghs_pool_nhwc_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      smem_set[hint != 0] = smem;
-    }
-    const int per_sm = max(1, min(min(cap, 2048 / threads), (int)((227 * 1024) / (smem + 1024))));
-    const int need = (w.ncell + wpb - 1) / wpb;
-    const int grid = min(need, sm_count() * per_sm);
-    if (hint) mghs_pool_nhwc_tma_kernel<true><<<grid, threads, smem, st>>>(P, cell_cost, zero_bytes, chunk_cells, windows);
-    else mghs_pool_nhwc_tma_kernel<false><<<grid, threads, smem, st>>>(P, cell_cost, zero_bytes, chunk_cells, windows);
-    DHD_CUDA_LAUNCH_CHECK("mghs_pool_nhwc_tma");
-  } else if (layout == DHD_LAYOUT_NHWC && tuning("DHD_POOL_V", 4) == 2) {
-    for (int p = 0; p < cfg->n_pass; ++p)
-      DHD_REQUIRE(((uintptr_t)out_host[p] & 15) == 0, "NHWC outputs must be 16-byte aligned");
-    const size_t smem = (size_t)8 * P.nplanes * kC * sizeof(float);
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
-      cudaFuncSetAttribute(mghs_pool_nhwc_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)smem);
-      smem_set = smem;
-    }
-    const int per_sm = max(1, min(6, (int)((227 * 1024) / (smem + 1024))));
-    const int need = (w.ncell + 7) / 8;
-    mghs_pool_nhwc_smem_kernel<<<min(need, sm_count() * per_sm), 256, smem, st>>>(P);
-    DHD_CUDA_LAUNCH_CHECK("mghs_pool_nhwc_smem");
-  } else if (layout == DHD_LAYOUT_NHWC) {
-    // grid = one full wave of resident blocks (MINB per SM); warps stride over the cells
-    const int minb = tuning("DHD_POOL_MINB", 3);
-    const int need = (w.ncell + 7) / 8;
-#define DHD_LAUNCH_NHWC(MAXZ, MINB)                                            \
-  mghs_pool_nhwc_kernel<MAXZ, MINB><<<min(need, sm_count() * MINB), 256, 0, st>>>(P)
-    if (P.nplanes <= 8) DHD_LAUNCH_NHWC(8, 4);
-    else if (P.nplanes <= 17) {
-      if (minb >= 4) DHD_LAUNCH_NHWC(17, 4);
-      else if (minb == 3) DHD_LAUNCH_NHWC(17, 3);
-      else DHD_LAUNCH_NHWC(17, 2);
-    } else DHD_LAUNCH_NHWC(32, 2);
-#undef DHD_LAUNCH_NHWC
-    DHD_CUDA_LAUNCH_CHECK("mghs_pool_nhwc");
   } else {
     constexpr int PZ = 6;
     const int tiles_per_b = (int)((DyDx + 31) / 32);

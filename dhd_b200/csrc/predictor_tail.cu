@@ -11,10 +11,15 @@
 //     G1(c)  acc1[c % 3] (TMEM, 64 cols)  = A x W1[c]^T            16 x tcgen05.mma 128x64x16, W1 streamed by TMA
 //     epi(c) 8 warps: tcgen05.ld -> + b1 -> softplus (ex2 / lg2) -> bf16 -> 128B-swizzled smem tile h[c % 2]
 //     G2(c)  acc2 (TMEM, 288 cols)       += h[c % 2] x W2[:, c]^T   4 k-steps x 2 x tcgen05.mma 128x144x16
-//   final    8 warps: tcgen05.ld acc2 -> + b2 -> fp32 logits (optional) and / or per-z argmax over the classes -> uint8
+//   final    8 more warps: tcgen05.ld acc2 -> + b2 -> fp32 logits (optional) and / or per-z argmax over the classes -> uint8
 //
-// The MMA warp issues G1(g) before G2(g - 1) over the flattened chunk sequence of all its tiles, so the tensor pipe works
-// on the next chunk while the epilogue warps run the softplus of the previous one; acc1 is triple-buffered, h double.
+// Warp roles (20 warps): 0-7 chunk epilogue, 8 G1 issuer, 9 G2 issuer, 10 weight producer, 11 A producer, 12-19 logits
+// epilogue.  The first version had ONE issuing thread for both GEMMs and the chunk-epilogue warps also drained the
+// logits: ncu (profiles/r02_tail_full.txt) showed the tensor pipe 33 % active -- the issuing thread's ~430 scalar
+// instructions per chunk and its blocking wait for h[c] before it could issue G1(c + 1) put issuer and epilogue into
+// lock-step, and every tile boundary stalled the whole pipeline behind the 288-column logits drain.  Now G1 runs up to
+// three chunks ahead (acc1 triple-buffered) on its own warp, G2 follows the epilogue on another, and the logits of
+// tile t are drained by their own warps while tile t + 1's chunks are already in flight.
 // Shared memory: A 64 KB + W1 ring 6 x 8 KB + W2 ring 2 x 36 KB + h 2 x 16 KB + biases = 220 KB; TMEM 480 of 512 cols.
 // Roofline: 89 GFLOP at DHD-S B=4 (160 000 pixels) -> 64 us at the sustained bf16 peak; weights are re-streamed from
 // L2 per tile (544 KB / tile), which bounds a single-CTA design at ~65 us.
@@ -60,8 +65,9 @@ constexpr int kBarAcc2Full = kBarHEmpty + kHBufs;        // [1]
 constexpr int kBarAcc2Empty = kBarAcc2Full + 1;          // [1]  epilogue (256 arrivals) -> MMA
 constexpr int kNumBars = kBarAcc2Empty + 1;
 constexpr uint32_t kSmem = kOffBar + kNumBars * 8 + 16 + 1024;     // + tmem slot + alignment slack
-constexpr int kEpiThreads = 256;
-constexpr int kThreads = kEpiThreads + 3 * 32;       // + MMA warp, weight producer warp, A producer warp
+constexpr int kEpiThreads = 256;                     // warps 0-7: softplus epilogue of the hidden chunks
+constexpr int kFinThreads = 256;                     // warps 12-19: logits epilogue (argmax / store), off the chunk pipeline
+constexpr int kThreads = kEpiThreads + 4 * 32 + kFinThreads;   // + G1 issuer, G2 issuer, weight producer, A producer
 constexpr uint32_t kAcc2Col = kAcc1Bufs * kChunk;    // 192
 static_assert(kAcc2Col + kN2 <= 512, "TMEM columns");
 static_assert(kSmem <= 232448, "shared memory");
@@ -130,16 +136,16 @@ predictor_tail_kernel(const __grid_constant__ TailMaps M, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + kOffBar + kNumBars * 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int kMmaWarp = kEpiThreads / 32, kWWarp = kMmaWarp + 1, kAWarp = kMmaWarp + 2;
+  constexpr int kMmaWarp = kEpiThreads / 32, kG2Warp = kMmaWarp + 1, kWWarp = kMmaWarp + 2, kAWarp = kMmaWarp + 3;
+  constexpr int kFinWarp0 = kMmaWarp + 4;              // 12: a multiple of 4, so warp % 4 is again the TMEM lane quarter
 
   if (warp == kWWarp && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&M.a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&M.w1) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&M.w2) : "memory");
     for (int i = 0; i < kNumBars; ++i) {
-      const bool many = (i >= kBarAcc1Empty && i < kBarAcc1Empty + kAcc1Bufs) ||
-                        (i >= kBarHFull && i < kBarHFull + kHBufs) || i == kBarAcc2Empty;
-      mbar_init(bar(i), many ? (uint32_t)kEpiThreads : 1u);
+      const bool many = (i >= kBarAcc1Empty && i < kBarAcc1Empty + kAcc1Bufs) || (i >= kBarHFull && i < kBarHFull + kHBufs);
+      mbar_init(bar(i), many ? (uint32_t)kEpiThreads : i == kBarAcc2Empty ? (uint32_t)kFinThreads : 1u);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -193,22 +199,20 @@ predictor_tail_kernel(const __grid_constant__ TailMaps M, const __grid_constant_
       }
     }
   } else if (warp == kMmaWarp) {
-    // ===================================================== MMA issuer
+    // ===================================================== G1 issuer: hidden chunk g = A x W1[c]^T, up to 3 chunks ahead
     if (lane == 0) {
       constexpr uint32_t kIdesc1 = umma_instr_desc_bf16(kM, kChunk);
-      constexpr uint32_t kIdesc2 = umma_instr_desc_bf16(kM, kN2Half);
       const int total = my_tiles * kNChunks;
-      int i1 = 0;
-      auto issue_g1 = [&](int g) {
-        const int c = g % kNChunks, lt = g / kNChunks;
-        const int ab = g % kAcc1Bufs;
-        mbar_wait(bar(kBarAcc1Empty + ab), (uint32_t)((g / kAcc1Bufs) & 1) ^ 1u);
+      int s = 0, ab = 0, c = 0;
+      uint32_t ws_par = 0, ab_par = 0, a_par = 0;            // phase parities of the W1 ring, the acc1 ring, the A tile
+      for (int g = 0; g < total; ++g) {
+        mbar_wait(bar(kBarAcc1Empty + ab), ab_par ^ 1u);
         tc_fence_after();
         const uint32_t tacc = tmem_base + (uint32_t)(ab * kChunk);
-        for (int kc = 0; kc < kKc1; ++kc, ++i1) {
-          if (c == 0) mbar_wait(bar(kBarAFull + kc), (uint32_t)(lt & 1));
-          const int s = i1 % kW1Stages;
-          mbar_wait(bar(kBarW1Full + s), (uint32_t)((i1 / kW1Stages) & 1));
+#pragma unroll 1
+        for (int kc = 0; kc < kKc1; ++kc) {
+          if (c == 0) mbar_wait(bar(kBarAFull + kc), a_par);
+          mbar_wait(bar(kBarW1Full + s), ws_par);
           tc_fence_after();
           const uint64_t da = umma_desc_sw128(base + kOffA + kc * kABytes);
           const uint64_t db = umma_desc_sw128(base + kOffW1 + s * kW1Bytes);
@@ -216,46 +220,56 @@ predictor_tail_kernel(const __grid_constant__ TailMaps M, const __grid_constant_
           for (int k = 0; k < 64 / kUmmaK; ++k)
             umma_bf16(tacc, da + 2u * k, db + 2u * k, kIdesc1, (kc == 0 && k == 0) ? 0u : 1u);
           umma_commit(bar(kBarW1Empty + s));
+          if (++s == kW1Stages) { s = 0; ws_par ^= 1u; }
         }
         umma_commit(bar(kBarAcc1Full + ab));
-        if (c == kNChunks - 1) umma_commit(bar(kBarAEmpty));       // every G1 of this tile has read A
-      };
-      auto issue_g2 = [&](int g) {
-        const int c = g % kNChunks, lt = g / kNChunks;
-        const int hb = g % kHBufs, s = g % kW2Stages;
-        if (c == 0) {                                              // the epilogue has drained the previous tile's logits
-          mbar_wait(bar(kBarAcc2Empty), (uint32_t)(lt & 1) ^ 1u);
+        if (++ab == kAcc1Bufs) { ab = 0; ab_par ^= 1u; }
+        if (++c == kNChunks) {
+          c = 0;
+          a_par ^= 1u;
+          umma_commit(bar(kBarAEmpty));                      // every G1 of this tile has read A
         }
-        mbar_wait(bar(kBarHFull + hb), (uint32_t)((g / kHBufs) & 1));
-        mbar_wait(bar(kBarW2Full + s), (uint32_t)((g / kW2Stages) & 1));
+      }
+    }
+  } else if (warp == kG2Warp) {
+    // ===================================================== G2 issuer: logits += h[c] x W2[:, c]^T, behind the epilogue
+    if (lane == 0) {
+      constexpr uint32_t kIdesc2 = umma_instr_desc_bf16(kM, kN2Half);
+      const int total = my_tiles * kNChunks;
+      const uint32_t tacc = tmem_base + kAcc2Col;
+      int c = 0;
+      uint32_t t_par = 0;                                    // tile parity (acc2)
+      for (int g = 0; g < total; ++g) {
+        const int hb = g & 1;                                // kHBufs == kW2Stages == 2
+        const uint32_t par = (uint32_t)(g >> 1) & 1u;
+        if (c == 0) mbar_wait(bar(kBarAcc2Empty), t_par ^ 1u);          // the previous tile's logits have been drained
+        mbar_wait(bar(kBarHFull + hb), par);
+        mbar_wait(bar(kBarW2Full + hb), par);
         tc_fence_after();
         const uint64_t da = umma_desc_sw128(base + kOffH + hb * kHBytes);
-        const uint64_t db = umma_desc_sw128(base + kOffW2 + s * kW2Bytes);
-        const uint32_t tacc = tmem_base + kAcc2Col;
+        const uint64_t db = umma_desc_sw128(base + kOffW2 + hb * kW2Bytes);
 #pragma unroll
         for (int k = 0; k < 64 / kUmmaK; ++k) {
           const uint32_t acc = (c == 0 && k == 0) ? 0u : 1u;
           umma_bf16(tacc, da + 2u * k, db + 2u * k, kIdesc2, acc);
           umma_bf16(tacc + kN2Half, da + 2u * k, db + (uint64_t)((kN2Half * 128) >> 4) + 2u * k, kIdesc2, acc);
         }
-        umma_commit(bar(kBarW2Empty + s));
+        umma_commit(bar(kBarW2Empty + hb));
         umma_commit(bar(kBarHEmpty + hb));
-        if (c == kNChunks - 1) umma_commit(bar(kBarAcc2Full));
-      };
-      for (int g = 0; g < total; ++g) {
-        issue_g1(g);
-        if (g > 0) issue_g2(g - 1);
+        if (++c == kNChunks) {
+          c = 0;
+          t_par ^= 1u;
+          umma_commit(bar(kBarAcc2Full));
+        }
       }
-      if (total > 0) issue_g2(total - 1);
     }
-  } else {
-    // ===================================================== epilogue: 8 warps, warp w owns TMEM lanes 32 * (w % 4) ..
-    const int grp = warp >> 2;                     // 0 / 1: which half of a chunk / of the logits
+  } else if (warp < kMmaWarp) {
+    // ===================================================== chunk epilogue: 8 warps, warp w owns TMEM lanes 32 * (w % 4) ..
+    const int grp = warp >> 2;                     // 0 / 1: which half of a chunk
     const int row = (warp & 3) * 32 + lane;        // pixel row of the tile = TMEM lane
     const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     int g = 0;
     for (int lt = 0; lt < my_tiles; ++lt) {
-      const int tile = blockIdx.x + lt * gridDim.x;
       for (int c = 0; c < kNChunks; ++c, ++g) {
         const int ab = g % kAcc1Bufs, hb = g % kHBufs;
         mbar_wait(bar(kBarAcc1Full + ab), (uint32_t)((g / kAcc1Bufs) & 1));
@@ -278,7 +292,16 @@ predictor_tail_kernel(const __grid_constant__ TailMaps M, const __grid_constant_
         fence_proxy_async_smem();
         mbar_arrive(bar(kBarHFull + hb));
       }
-      // ---- logits of this tile: group g owns z planes [8 * grp, 8 * grp + 8) = columns [144 * grp, +144)
+    }
+  } else {
+    // ===================================================== logits epilogue: 8 warps, group g owns z planes
+    // [8 * grp, 8 * grp + 8) = columns [144 * grp, +144) of the rows of its TMEM lane quarter
+    const int fw = warp - kFinWarp0;
+    const int grp = fw >> 2;
+    const int row = (fw & 3) * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)((fw & 3) * 32) << 16);
+    for (int lt = 0; lt < my_tiles; ++lt) {
+      const int tile = blockIdx.x + lt * gridDim.x;
       mbar_wait(bar(kBarAcc2Full), (uint32_t)(lt & 1));
       tc_fence_after();
       const long m = (long)tile * kM + row;

@@ -423,6 +423,8 @@ class TrainStep(HotPathStep):
         # beta, running statistics updated); the two BatchNorms that see one value per image (HeightNet's BatchNorm1d
         # on the camera vector and the ASPP global-pool branch) stay frozen either way
         self.bn_mode = bn
+        if getattr(self.vt, 'sid', False):
+            raise NotImplementedError('TrainStep bins gt_depth linearly (dhd_gt_downsample); sid=True is not used by any DHD config')
         T.set_bn_mode(bn)
         torch.manual_seed(seed + 1)
         self.head = predictor(in_dim=256, out_dim=256, Dz=16, num_classes=18, use_predicter=True, class_balance=True,

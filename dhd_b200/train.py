@@ -497,6 +497,9 @@ def lidar_losses(vt, gt_depth, gt_height, depth=None, height=None):
     distribution gives weight * sum_fg BCE / max(1, n_fg) and its gradient at the logits (through the softmax).
     depth / height: softmax probabilities (B*N, bins, fH, fW) fp32, either may be None.
     Returns {'depth': (loss (1,), dz Act), 'height': (loss, dz Act)} for the ones given."""
+    if getattr(vt, 'sid', False):
+        raise NotImplementedError('dhd_gt_downsample bins depth linearly; sid=True (log-spaced bins, lss_heightmap.py:646-653) '
+                                  'is not used by any DHD config -- use the plugin torch form MGHS.get_downsampled_gt_depth')
     dc = vt.grid_config['depth']
     dlab, fg = gt_downsample(gt_depth, vt.downsample, dc[0] - dc[2], dc[2], vt.D, want_valid=True)
     hlab, _ = gt_downsample(gt_height, vt.downsample, vt.height_range[0], vt.height_interval, vt.H)

@@ -426,10 +426,6 @@ int dhd_maxpool2_bwd(const void* x, int x_ld, int x_coff, const void* dy, int dy
                      int C, void* dx, int dx_ld, int dx_coff, void* stream);
 int dhd_upsample_bilinear_bwd(const void* dy, int dy_ld, int dy_coff, int N, int H, int W, int C, int out_H, int out_W,
                               float* dx, void* stream);
-/* write-bandwidth probe (measurement only): zero-fills `bytes` at dst with mode 0 = grid-stride
- * st.global.cs.v4, 1 = grid-stride st.global.v4, 2 = one contiguous run per warp (st.cs),
- * 3 = cp.async.bulk from a shared-memory zero tile, one run per CTA, 4 = same, one run per warp */
-int dhd_probe_write_bw(void* dst, size_t bytes, int mode, int chunk_bytes, int blocks_per_sm, void* stream);
 /* number of kernels this library has enqueued since it was loaded (bench bookkeeping) */
 long dhd_launch_count(void);
 /* fp32 rows [rows][C] (NHWC) -> split-bf16 rows */

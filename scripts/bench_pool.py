@@ -1,6 +1,7 @@
 """Pool-forward micro-benchmark on the DHD-S B=4 workload: sweeps the env tunables of
-dhd_mghs_pool_fwd (csrc/mghs_pool.cu) and checks every variant bit-for-bit against the v2 kernel.
-Usage: python scripts/bench_pool.py ["V=3,ZT=4096,THREADS=256,CELLCOST=2,HINT=0,PERSM=8" ...]"""
+dhd_mghs_pool_fwd (csrc/mghs_pool.cu) and checks every variant bit-for-bit against the default configuration
+(PROBE=1 = every cell treated as empty: the write-only ceiling of the kernel's own address pattern).
+Usage: python scripts/bench_pool.py ["ZT=4096,THREADS=128,CELLCOST=8,HINT=1,PERSM=4,NCH=32768" ...]"""
 import os
 import sys
 
@@ -13,7 +14,8 @@ from oracle import mghs_oracle as O  # noqa: E402
 
 
 def main():
-    variants = sys.argv[1:] or ['V=2', 'V=3']
+    variants = sys.argv[1:] or ['NCH=32768', 'PROBE=1']
+    os.environ['DHD_POOL_SWEEP'] = '1'          # the library re-reads its tunables on every call
     cfg, B = O.DHD_S, 4
     step = HotPathStep(cfg, B, precision='bf16', use_graph=False)
     rig = O.synthetic_rig(B, cfg['ncams'], cfg['input_size'], seed=100)
@@ -23,16 +25,15 @@ def main():
     step._front()
     torch.cuda.synchronize()
     alg = algorithmic_bytes(cfg, B)['pool_fwd_bytes']
-    os.environ['DHD_POOL_V'] = '2'
     for o in step.outs:
         o.fill_(float('nan'))
     step._pool()
     torch.cuda.synchronize()
-    want = [o.clone() for o in step.outs]
+    want = [o.clone() for o in step.outs]          # the default configuration is the reference every variant must equal
     st = torch.cuda.current_stream()
     for v in variants:
         for k in list(os.environ):
-            if k.startswith('DHD_POOL_'):
+            if k.startswith('DHD_POOL_') and k != 'DHD_POOL_SWEEP':
                 del os.environ[k]
         for kv in v.split(','):
             k, val = kv.split('=')
@@ -59,49 +60,5 @@ def main():
               (v, same, avg * 1e3, ts[0] * 1e3, alg / avg / 1e6, 100 * alg / avg / 1e6 / 6538.6), flush=True)
 
 
-def probes():
-    import ctypes
-    from dhd_b200 import _lib
-    lib = _lib.load()
-    nbytes = 696320000 // 256 * 256
-    buf = torch.empty(nbytes, dtype=torch.uint8, device='cuda')
-    st = torch.cuda.current_stream()
-    combos = [(0, 0, 8), (0, 0, 4), (1, 0, 8), (2, 0, 8), (3, 16384, 4), (3, 4096, 8), (3, 65536, 2), (4, 4096, 4),
-              (4, 2048, 4), (4, 1024, 4), (4, 256, 4)]
-    for mode, chunk, bps in combos:
-        def run():
-            _lib.check(lib.dhd_probe_write_bw(ctypes.c_void_p(buf.data_ptr()), nbytes, mode, max(chunk, 256), bps,
-                                              ctypes.c_void_p(st.cuda_stream)), 'probe')
-        for _ in range(3):
-            run()
-        ts = []
-        for _ in range(20):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(st); run(); e1.record(st)
-            torch.cuda.synchronize()
-            ts.append(e0.elapsed_time(e1))
-        ts.sort()
-        avg = sum(ts) / len(ts)
-        print('probe mode=%d chunk=%-6d blocks/SM=%d   avg %.1f us  min %.1f us  %.0f GB/s avg' %
-              (mode, chunk, bps, avg * 1e3, ts[0] * 1e3, nbytes / avg / 1e6), flush=True)
-    a = torch.empty(nbytes, dtype=torch.uint8, device='cuda')
-    for name, fn in (('cudaMemset (torch zero_)', lambda: buf.zero_()), ('torch copy_ (r+w bytes)', lambda: buf.copy_(a))):
-        for _ in range(3):
-            fn()
-        ts = []
-        for _ in range(20):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(st); fn(); e1.record(st)
-            torch.cuda.synchronize()
-            ts.append(e0.elapsed_time(e1))
-        ts.sort()
-        avg = sum(ts) / len(ts)
-        mult = 2 if 'copy' in name else 1
-        print('%-30s avg %.1f us  min %.1f us  %.0f GB/s avg' % (name, avg * 1e3, ts[0] * 1e3, mult * nbytes / avg / 1e6), flush=True)
-
-
 if __name__ == '__main__':
-    if len(sys.argv) > 1 and sys.argv[1] == 'probes':
-        sys.argv.pop(1)
-        probes()
     main()
