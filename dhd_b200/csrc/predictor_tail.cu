@@ -163,8 +163,12 @@ predictor_tail_kernel(const __grid_constant__ TailMaps M, const __grid_constant_
   const int my_tiles = (P.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (warp == kAWarp) {
-    // ===================================================== A producer: one 128 x 256 pixel tile per tile
+    // ===================================================== G1 operand producer: the tile's A (128 x 256 pixels, once per
+    // tile) and the W1 chunks.  W2 has its own producer warp: with one producer for both rings (first version) the
+    // thread sat in the W2 ring's empty-wait -- G2 runs a chunk or two behind G1 by design -- and could not issue the W1
+    // loads G1 was waiting for (ncu: 750 k retries on W2-empty, G1 and the producer ping-ponging on the W1 ring).
     if (lane == 0) {
+      int i1 = 0;
       for (int lt = 0; lt < my_tiles; ++lt) {
         const int tile = blockIdx.x + lt * gridDim.x;
         mbar_wait(bar(kBarAEmpty), (uint32_t)(lt & 1) ^ 1u);
@@ -172,30 +176,27 @@ predictor_tail_kernel(const __grid_constant__ TailMaps M, const __grid_constant_
           mbar_expect_tx(bar(kBarAFull + kc), kABytes);
           tma_load_2d(base + kOffA + kc * kABytes, &M.a, bar(kBarAFull + kc), P.in_coff + kc * 64, tile * kM);
         }
+        for (int c = 0; c < kNChunks; ++c) {
+          for (int kc = 0; kc < kKc1; ++kc, ++i1) {
+            const int s = i1 % kW1Stages;
+            mbar_wait(bar(kBarW1Empty + s), (uint32_t)((i1 / kW1Stages) & 1) ^ 1u);
+            mbar_expect_tx(bar(kBarW1Full + s), kW1Bytes);
+            tma_load_2d(base + kOffW1 + s * kW1Bytes, &M.w1, bar(kBarW1Full + s), kc * 64, c * kChunk);
+          }
+        }
       }
     }
   } else if (warp == kWWarp) {
-    // ===================================================== weight producer: W1 / W2 chunks, the same for every tile
+    // ===================================================== W2 producer: one 288 x 64 chunk per hidden chunk
     if (lane == 0) {
-      int i1 = 0, i2 = 0;
       const int total = my_tiles * kNChunks;
       for (int g = 0; g < total; ++g) {
-        const int c = g % kNChunks;
-        for (int kc = 0; kc < kKc1; ++kc, ++i1) {
-          const int s = i1 % kW1Stages;
-          mbar_wait(bar(kBarW1Empty + s), (uint32_t)((i1 / kW1Stages) & 1) ^ 1u);
-          mbar_expect_tx(bar(kBarW1Full + s), kW1Bytes);
-          tma_load_2d(base + kOffW1 + s * kW1Bytes, &M.w1, bar(kBarW1Full + s), kc * 64, c * kChunk);
-        }
-        {
-          const int s = i2 % kW2Stages;
-          mbar_wait(bar(kBarW2Empty + s), (uint32_t)((i2 / kW2Stages) & 1) ^ 1u);
-          mbar_expect_tx(bar(kBarW2Full + s), kW2Bytes);
-          const uint32_t dst = base + kOffW2 + s * kW2Bytes;
-          tma_load_2d(dst, &M.w2, bar(kBarW2Full + s), c * kChunk, 0);
-          tma_load_2d(dst + kN2Half * 128, &M.w2, bar(kBarW2Full + s), c * kChunk, kN2Half);
-          ++i2;
-        }
+        const int c = g % kNChunks, s = g % kW2Stages;
+        mbar_wait(bar(kBarW2Empty + s), (uint32_t)((g / kW2Stages) & 1) ^ 1u);
+        mbar_expect_tx(bar(kBarW2Full + s), kW2Bytes);
+        const uint32_t dst = base + kOffW2 + s * kW2Bytes;
+        tma_load_2d(dst, &M.w2, bar(kBarW2Full + s), c * kChunk, 0);
+        tma_load_2d(dst + kN2Half * 128, &M.w2, bar(kBarW2Full + s), c * kChunk, kN2Half);
       }
     }
   } else if (warp == kMmaWarp) {
