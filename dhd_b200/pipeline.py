@@ -460,6 +460,11 @@ class TrainStep(HotPathStep):
         params = list(self.vt.depth_net.parameters()) + [p for p in self.vt.height_net.parameters() if p.requires_grad] + \
             enc_params + [p for p in self.sfa.parameters() if p.requires_grad] + list(self.head.parameters())
         self.bucket = shard.GradBucket(params)
+        # flat-buffer spans of the three backward segments (parameter order above: depth_net, HeightNet | encoders | SFA, head)
+        self._spans = {'front': self.bucket.span(list(self.vt.depth_net.parameters()) + list(self.vt.height_net.parameters())),
+                       'enc': self.bucket.span(enc_params),
+                       'tail': self.bucket.span(list(self.sfa.parameters()) + list(self.head.parameters()))}
+        self.grad_bf16 = os.environ.get('DHD_GRAD_BF16', '0') != '0'      # gradients travel as bf16 (half the NCCL bytes)
         self.opt = torch.optim.AdamW(self.bucket.params, lr=2e-4, weight_decay=1e-2, fused=True)
         gen = torch.Generator(device=self.device).manual_seed(11)
         for g in self.gouts:
@@ -545,14 +550,21 @@ class TrainStep(HotPathStep):
                 self._refresh()
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
-            g1, g2, g3 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            g1, g2, g2b, g2c, g3 = (torch.cuda.CUDAGraph() for _ in range(5))
             with torch.cuda.graph(g1):
                 self._fwd_front()
             with torch.cuda.graph(g2):
                 self._fwd_bwd_rest()
+            if self.encoders:
+                with torch.cuda.graph(g2b):
+                    self._bwd_encoders()
+            else:
+                g2b = None
+            with torch.cuda.graph(g2c):
+                self._bwd_front()
             with torch.cuda.graph(g3):
                 self._refresh()
-            self.train_graph = (g1, g2, g3)
+            self.train_graph = (g1, g2, g2b, g2c, g3)
         except Exception as e:  # noqa: BLE001
             self.train_graph = None
             self.train_graph_error = repr(e)[:300]
@@ -588,11 +600,26 @@ class TrainStep(HotPathStep):
         self._pool()
         if pool_events is not None:
             pool_events[1].record(st)
+        # the gradient exchange is launched per backward segment, as soon as that segment's gradients are final, and
+        # runs on NCCL's stream under the segments that follow (torch DDP's bucketed overlap, tools/train.py:195):
+        # [head + SFA] -> all-reduce | [encoders] -> all-reduce | [pool, depth_net, HeightNet] -> all-reduce -> join
         if g is not None:
             g[1].replay()
         else:
             self._fwd_bwd_rest()
-        self.bucket.all_reduce_async()
+        lo_tail, hi_tail = self._spans['tail']
+        self.bucket.all_reduce_async(lo_tail, hi_tail, bf16=self.grad_bf16)
+        if self.encoders:
+            if g is not None:
+                g[2].replay()
+            else:
+                self._bwd_encoders()
+            self.bucket.all_reduce_async(*self._spans['enc'], bf16=self.grad_bf16)
+        if g is not None:
+            g[3].replay()
+        else:
+            self._bwd_front()
+        self.bucket.all_reduce_async(*self._spans['front'], bf16=self.grad_bf16)
         self.bucket.wait()
         self.grad_norm = self.clip_grad_norm()
         if self.lr_schedule is not None:
@@ -601,7 +628,7 @@ class TrainStep(HotPathStep):
         self.opt.step()
         self._step_index += 1
         if g is not None:
-            g[2].replay()
+            g[4].replay()
         else:
             self._refresh()
 
@@ -619,6 +646,8 @@ class TrainStep(HotPathStep):
         self._fwd_front()
         self._pool()
         self._fwd_bwd_rest()
+        self._bwd_encoders()
+        self._bwd_front()
 
     def _fwd_front(self):
         s = self.static
@@ -672,7 +701,11 @@ class TrainStep(HotPathStep):
         self.loss = self.t_head.loss(self.labels, self.mask_camera)
         # ---- backward
         dfused = self.t_head.backward()
-        denc = self.t_sfa.backward(dfused)
+        self._denc = self.t_sfa.backward(dfused)
+
+    def _bwd_encoders(self):
+        """Middle segment of the backward (only with the real encoders): occupancy loss -> encoders -> pool outputs."""
+        denc = self._denc
         if self.encoders:
             # occupancy loss -> encoders -> the four pool outputs (fp32 NHWC gradients the pool backward reads)
             main = torch.cuda.current_stream()
@@ -684,6 +717,9 @@ class TrainStep(HotPathStep):
             self.gouts[0].copy_(d0.data.view(self.gouts[0].shape))
             for st in self._enc_streams:
                 main.wait_stream(st)
+
+    def _bwd_front(self):
+        """Last segment of the backward: pool backward -> depth_net, and the height loss gradient -> HeightNet."""
         self.run_pool_bwd()
         self.t_depth.backward(self.depth_grad, self.feat_grad)
         self.t_height.backward(want_dx=True)

@@ -63,17 +63,52 @@ class GradBucket:
         for p in self.params:
             p.grad = self.flat[o:o + p.numel()].view(p.shape)
             o += p.numel()
-        self._work = None
+        self._works = []
 
     def zero(self):
         self.flat.zero_()
 
-    def all_reduce_async(self):
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            self._work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, async_op=True)
+    def span(self, params):
+        """[lo, hi) of the flat buffer covered by `params` (a contiguous run of this bucket's parameter list)."""
+        ids = {id(p) for p in params if p.requires_grad}
+        lo = hi = None
+        o = 0
+        for p in self.params:
+            if id(p) in ids:
+                lo = o if lo is None else lo
+                hi = o + p.numel()
+            o += p.numel()
+        if lo is None:
+            return 0, 0
+        if sum(p.numel() for p in self.params if id(p) in ids) != hi - lo:
+            raise ValueError('the parameters are not contiguous in the bucket')
+        return lo, hi
+
+    def all_reduce_async(self, lo=None, hi=None, bf16=False):
+        """Launch the all-reduce of flat[lo:hi] (default: everything) on the process group's stream; it starts when the
+        kernels enqueued so far have finished and overlaps whatever is enqueued afterwards (the rest of the backward).
+        bf16=True: the slice travels as bf16 (half the bytes; torch DDP's bf16 compression hook) and is widened again
+        in wait()."""
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            return
+        lo = 0 if lo is None else lo
+        hi = self.flat.numel() if hi is None else hi
+        if hi <= lo:
+            return
+        sl = self.flat[lo:hi]
+        if bf16:
+            buf = sl.to(torch.bfloat16)
+            self._works.append((dist.all_reduce(buf, op=dist.ReduceOp.SUM, async_op=True), sl, buf))
+        else:
+            self._works.append((dist.all_reduce(sl, op=dist.ReduceOp.SUM, async_op=True), sl, None))
 
     def wait(self):
-        if self._work is not None:
-            self._work.wait()
-            self._work = None
-            self.flat.mul_(1.0 / dist.get_world_size())
+        if not self._works:
+            return
+        inv = 1.0 / dist.get_world_size()
+        for work, sl, buf in self._works:
+            work.wait()
+            if buf is not None:
+                sl.copy_(buf)
+            sl.mul_(inv)
+        self._works = []

@@ -93,3 +93,48 @@ def test_gradient_bucket_single_all_reduce():
     for rank, w, bias, n, aliased in out:
         assert w == [1.5] * 15 and bias == [15.0] * 3      # mean of (1, 2) and of (10, 20)
         assert n == 18 and aliased
+
+
+def _span_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        a, b_, c = torch.nn.Linear(4, 2), torch.nn.Linear(3, 3), torch.nn.Linear(2, 5)
+        bucket = shard.GradBucket(list(a.parameters()) + list(b_.parameters()) + list(c.parameters()))
+        spans = [bucket.span(list(m.parameters())) for m in (a, b_, c)]
+        bucket.zero()
+        for k, m in enumerate((a, b_, c)):
+            for p in m.parameters():
+                p.grad.add_(float((rank + 1) * (k + 1)))
+        # the training step's order: the LAST modules' gradients are final first and travel while the rest is computed
+        bucket.all_reduce_async(*spans[2])
+        bucket.all_reduce_async(*spans[1], bf16=True)          # compressed exchange of one segment
+        bucket.all_reduce_async(*spans[0])
+        bucket.wait()
+        try:
+            bucket.span([a.weight, c.weight])
+            contiguous_error = False
+        except ValueError:
+            contiguous_error = True
+        q.put((rank, spans, [float(m.weight.grad.flatten()[0]) for m in (a, b_, c)], contiguous_error))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gradient_bucket_segmented_overlapped_exchange():
+    """Per-segment all-reduces (head + SFA first, then the encoders, then the front) tile the flat buffer exactly and
+    give the same mean as the single exchange; a bf16-compressed segment too (small integers are exact in bf16)."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_span_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, spans, firsts, contiguous_error in out:
+        assert spans == [(0, 10), (10, 22), (22, 37)]
+        assert firsts == [1.5, 3.0, 4.5]                        # mean over ranks of (rank + 1) * (k + 1)
+        assert contiguous_error
