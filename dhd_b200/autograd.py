@@ -259,3 +259,79 @@ def mghs_forward(vt, input, plan, pixmask_fn):
     layout = vt.out_layout if vt.collapse_z else 'ncdhw'
     params = _params(vt.depth_net) + _params(vt.height_net)
     return _MGHSFn.apply(x, vt, t_depth, t_height, plan, pixmask_fn, mlp_input, layout, *params)
+
+
+# ------------------------------------------------------------------------------------------------ MGHS_Depth / MGHS_Stereo
+class _MGHSDepthFn(torch.autograd.Function):
+    """MGHS_Depth.forward (lss_heightmap.py:751-856) with a backward: pool backward -> camera-aware DepthNet (both
+    gated branches, cost_volumn_net when stereo), the depth / height distributions' own gradients
+    (get_depth_and_height_loss, LH:859-897) -> DepthNet / HeightNet.  The plane-sweep cost volume is a constant of the
+    step (computed under no_grad, as the reference does, depthnet.py:405-407)."""
+
+    @staticmethod
+    def forward(ctx, x, vt, t_depth, t_height, plan, pixmask_fn, mlp_input, cost_volume, layout, *params):
+        B, N, C, H, W = x.shape
+        xa = D.pack_input(x.detach().reshape(B * N, C, H, W).float(), 1)
+        depth, feat = t_depth.forward(xa, mlp_input, cost_volume)
+        height = t_height.forward(xa, mlp_input)
+        pixmask = pixmask_fn(height)
+        outs = plan.alloc_outputs(layout, x.device)
+        plan.raw_forward(depth, feat, pixmask, outs, layout)
+        ctx.state = (t_depth, t_height, plan, pixmask, depth, feat, layout, plan.workspace, (B, N, C, H, W))
+        return tuple(outs) + (depth.clone(), height.clone())
+
+    @staticmethod
+    def backward(ctx, *gs):
+        t_depth, t_height, plan, pixmask, depth, feat, layout, ws, (B, N, C, H, W) = ctx.state
+        gouts, g_depth, g_height = list(gs[:-2]), gs[-2], gs[-1]
+        want_dx = ctx.needs_input_grad[0]
+        dgrad = fgrad = None
+        if any(g is not None for g in gouts):
+            dgrad, fgrad = plan._backward(depth, feat.view(B, N, H, W, -1), pixmask, gouts, layout, ws)
+            dgrad = dgrad.view(B * N, -1, H, W)
+            fgrad = fgrad.view(B * N, H, W, -1)
+        if g_depth is not None:
+            dgrad = g_depth if dgrad is None else dgrad + g_depth
+        dx = None
+        if dgrad is not None or fgrad is not None:
+            dx = t_depth.backward(depth_grad=dgrad, feat_grad=fgrad, want_dx=want_dx)
+        if g_height is not None:
+            p = t_height.saved['height']
+            dlog = p * (g_height - (p * g_height).sum(dim=1, keepdim=True))
+            dz = t_height._act('dz', B * N, H, W, t_height.head.cout_pad)
+            dz.data.zero_()
+            dz.data[..., :dlog.shape[1]].copy_(dlog.permute(0, 2, 3, 1))
+            t_height.dz = dz
+            dxh = t_height.backward(want_dx=want_dx)
+            if dxh is not None:
+                dx = dxh if dx is None else D.Act(dx.data + dxh.data, dx.C, 1)
+        gx = from_act(dx, C).reshape(B, N, C, H, W) if (dx is not None and want_dx) else None
+        return (gx,) + (None,) * (len(ctx.needs_input_grad) - 1)
+
+
+def mghs_depth_forward(vt, input, stereo_metas, plan, pixmask_fn):
+    """-> (bev, bev_w_z, depth, height) of MGHS_Depth / MGHS_Stereo under autograd."""
+    x, mlp_input = input[0], input[7]
+    dev = x.device
+    dn, hn = vt.depth_net, vt.height_net
+    drop = 0.5 if vt.training else 0.0
+    t_depth = trainer_of(dn, lambda: T.DepthNetTrainer(dn, dev, loss_weight=vt.loss_depth_weight, dropout=drop), dev)
+    t_height = trainer_of(hn, lambda: T.HeightNetTrainer(hn, dev, loss_weight=vt.loss_height_weight, dropout=drop), dev)
+    cv = None
+    if dn.stereo:
+        if stereo_metas is None:
+            raise RuntimeError('DepthNet(stereo=True) called without stereo_metas')
+        B, N, _, H, W = x.shape
+        scale = float(stereo_metas['downsample']) / stereo_metas['cv_downsample']
+        Hs, Ws = int(H * scale), int(W * scale)
+        cv = D.Act(torch.zeros(B * N, Hs, Ws, t_depth.Dcv_pad, dtype=torch.bfloat16, device=dev), t_depth.Dcv_pad, 1)
+        if stereo_metas['cv_feat_list'][0] is not None:            # zeros when there is no previous frame (depthnet.py:389-396)
+            with torch.no_grad():
+                dn.calculate_cost_volumn(stereo_metas, out_act=cv)
+    elif stereo_metas is not None:
+        raise RuntimeError('DepthNet(stereo=False) called with stereo_metas')
+    if vt.collapse_z:
+        raise NotImplementedError('MGHS_Depth under autograd: collapse_z=False (every DHD-M / DHD-L config)')
+    params = _params(dn) + _params(hn)
+    outs = _MGHSDepthFn.apply(x, vt, t_depth, t_height, plan, pixmask_fn, mlp_input, cv, 'ncdhw_cat', *params)
+    return outs[0], outs[1], outs[2], outs[3]

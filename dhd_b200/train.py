@@ -80,8 +80,8 @@ class _TrainConv:
         concatenation whose other columns are handled elsewhere)."""
         self.weight, self.bias_p, self.bn = weight, bias, bn
         self.batch_bn = bn is not None and BN_MODE == 'batch'
-        if self.batch_bn and cout_pad not in (None, weight.shape[0]):
-            raise NotImplementedError('batch-statistics BatchNorm on a padded output')
+        if self.batch_bn and cout_pad not in (None, weight.shape[0]) and weight.shape[0] % 8 != 0:
+            raise NotImplementedError('batch-statistics BatchNorm on a padded output needs Cout % 8 == 0')
         self.ksize, self.dilation, self.cols, self.stride = ksize, dilation, cols, stride
         if stride not in (1, 2) or (stride == 2 and (ksize != 3 or dilation != 1)):
             raise NotImplementedError('stride-2 layers: 3x3, pad 1')
@@ -534,11 +534,12 @@ def _ensure_grad(p):
 
 
 class HeightNetTrainer:
-    """HeightNet (depthnet.py:418-487, 605-652, non-stereo); BatchNorm frozen or on batch statistics (set_bn_mode),
-    the ASPP's Dropout on when `dropout` > 0:
-    reduce conv + camera-aware SE gate, BasicBlocks, ASPP (global branch as a per-image bias), DCN
-    (deformable im2col + grouped GEMM), 1x1 head + softmax; backward of all of it, fed by the height loss
-    (lss_heightmap.py:595-622)."""
+    """HeightNet (depthnet.py:418-487, 605-652, non-stereo) -- and, through `DepthNetTrainer`, the trunk of the
+    camera-aware DepthNet; BatchNorm frozen or on batch statistics (set_bn_mode), the ASPP's Dropout on when
+    `dropout` > 0: reduce conv + camera-aware SE gate, BasicBlocks (the first one optionally on a concatenated input
+    with a 1x1 `downsample` identity path: stereo DepthNet), ASPP (global branch as a per-image bias), optional DCN
+    (deformable im2col + grouped GEMM; off in DHD-M / DHD-L), 1x1 head + softmax; backward of all of it, fed by the
+    height / depth loss (lss_heightmap.py:595-622, 859-897)."""
 
     def __init__(self, net, device='cuda', loss_weight=0.1, dropout=0.0, seed=0):
         """dropout: drop probability of the ASPP's nn.Dropout (depthnet.py:81; 0.5 in the reference's train mode,
@@ -553,31 +554,47 @@ class HeightNetTrainer:
         self.reduce = _TrainConv(net.reduce_conv[0].weight, net.reduce_conv[0].bias, net.reduce_conv[1], 3)
         layers = list(net.depth_conv)
         self.blocks, i = [], 0
+        self.cat_channels = None
         while i < len(layers) and type(layers[i]).__name__ == 'BasicBlock':
             b = layers[i]
             if b.downsample is not None:
-                raise NotImplementedError('stereo downsample branch')
-            self.blocks.append((_TrainConv(b.conv1.weight, None, b.bn1, 3), _TrainConv(b.conv2.weight, None, b.bn2, 3)))
+                # stereo DepthNet (depthnet.py:203-218): the first block reads cat(gated feature, cost_volumn_net output),
+                # channels zero-padded to the 64-channel granule of the concatenation buffer, and carries a plain 1x1
+                # convolution (with bias, no BatchNorm) on its identity path
+                cin = b.conv1.weight.shape[1]
+                self.cat_channels = (cin + 63) // 64 * 64
+                self.blocks.append((_TrainConv(b.conv1.weight, None, b.bn1, 3, cin_pad=self.cat_channels),
+                                    _TrainConv(b.conv2.weight, None, b.bn2, 3),
+                                    _TrainConv(b.downsample.weight, b.downsample.bias, None, 1, cin_pad=self.cat_channels)))
+            else:
+                self.blocks.append((_TrainConv(b.conv1.weight, None, b.bn1, 3), _TrainConv(b.conv2.weight, None, b.bn2, 3), None))
             i += 1
         a = layers[i]
         if type(a).__name__ != 'ASPP':
-            raise NotImplementedError('HeightNet without ASPP')
+            raise NotImplementedError('trunk without ASPP')
         self.aspp = a
         self.mid = mid = a.aspp1.atrous_conv.out_channels
-        self.branches = [_TrainConv(b.atrous_conv.weight, None, b.bn, b.atrous_conv.kernel_size[0], b.atrous_conv.dilation[0])
+        self.mid_pad = (mid + 63) // 64 * 64              # branch slices of the concatenation buffer start on 64-channel granules
+        self.branches = [_TrainConv(b.atrous_conv.weight, None, b.bn, b.atrous_conv.kernel_size[0], b.atrous_conv.dilation[0],
+                                    cout_pad=self.mid_pad)
                          for b in (a.aspp1, a.aspp2, a.aspp3, a.aspp4)]
-        self.aspp_out = _TrainConv(a.conv1.weight, None, a.bn1, 1, cols=(0, 4 * mid))
+        if self.mid_pad != mid:
+            # aspp_mid_channels=96 (DHD-M / DHD-L): conv1's input columns are spread over the padded slices
+            w = a.conv1.weight
+            self._aspp_cols = torch.cat([torch.arange(b * self.mid_pad, b * self.mid_pad + mid) for b in range(4)])
+            self.aspp_out = _TrainConvScatter(w, a.bn1, 4 * mid, 4 * self.mid_pad, self._aspp_cols)
+        else:
+            self.aspp_out = _TrainConv(a.conv1.weight, None, a.bn1, 1, cols=(0, 4 * mid))
         i += 1
         self.dcn = layers[i] if hasattr(layers[i], 'conv_offset') else None
-        if self.dcn is None:
-            raise NotImplementedError('HeightNet without DCN (DHD-L): use_dcn=False trunk')
-        dc = self.dcn
-        self.k, self.groups = dc.weight.shape[2], dc.groups
-        self.pad = dc.padding if isinstance(dc.padding, int) else dc.padding[0]
-        self.dil = dc.dilation if isinstance(dc.dilation, int) else dc.dilation[0]
-        self.noff = 2 * self.k * self.k
-        self.dcn_offset = _TrainConv(dc.conv_offset.weight, dc.conv_offset.bias, None, self.k, cout_pad=64)
-        i += 1
+        if self.dcn is not None:
+            dc = self.dcn
+            self.k, self.groups = dc.weight.shape[2], dc.groups
+            self.pad = dc.padding if isinstance(dc.padding, int) else dc.padding[0]
+            self.dil = dc.dilation if isinstance(dc.dilation, int) else dc.dilation[0]
+            self.noff = 2 * self.k * self.k
+            self.dcn_offset = _TrainConv(dc.conv_offset.weight, dc.conv_offset.bias, None, self.k, cout_pad=64)
+            i += 1
         head = layers[i]
         self.H_bins = head.weight.shape[0]
         self.head = _TrainConv(head.weight, head.bias, None, 1, cout_pad=(self.H_bins + 63) // 64 * 64)
@@ -585,9 +602,14 @@ class HeightNetTrainer:
         self.refresh()
 
     # ---- weights -------------------------------------------------------------------------------
+    def _convs(self):
+        cs = [self.reduce, self.aspp_out, self.head] + self.branches + [c for tr in self.blocks for c in tr if c is not None]
+        if self.dcn is not None:
+            cs.append(self.dcn_offset)
+        return cs
+
     def refresh(self):
-        for c in [self.reduce, self.aspp_out, self.dcn_offset, self.head] + self.branches + \
-                [c for pair in self.blocks for c in pair]:
+        for c in self._convs():
             c.refresh()
         f = lambda t: t.detach().float().contiguous()
         net, a, dc = self.net, self.aspp, self.dcn
@@ -597,13 +619,16 @@ class HeightNetTrainer:
             self.s1, _ = fold_bn(a.bn1)
             if self.aspp_out.batch_bn:                 # batch statistics: the global branch enters the conv sum unscaled
                 self.s1 = torch.ones_like(self.s1)
-            cg, k = self.C // self.groups, self.k
-            self.dcn_wf = [torch.empty(cg, k * k * cg, 1, 1, dtype=torch.bfloat16, device=self.device).view(cg, 1, 1, k * k * cg)
-                           for _ in range(self.groups)]
-            self.dcn_wb = [torch.empty(k * k * cg, 1, 1, cg, dtype=torch.bfloat16, device=self.device)
-                           for _ in range(self.groups)]
+            if dc is not None:
+                cg, k = self.C // self.groups, self.k
+                self.dcn_wf = [torch.empty(cg, k * k * cg, 1, 1, dtype=torch.bfloat16, device=self.device).view(cg, 1, 1, k * k * cg)
+                               for _ in range(self.groups)]
+                self.dcn_wb = [torch.empty(k * k * cg, 1, 1, cg, dtype=torch.bfloat16, device=self.device)
+                               for _ in range(self.groups)]
         self.gap_ws = f(a.global_avg_pool[1].weight.flatten(1) * self.s5[:, None])
         self.w5s = f(a.conv1.weight.detach()[:, 4 * self.mid:].flatten(1) * self.s1[:, None])
+        if dc is None:
+            return
         cg, k = self.C // self.groups, self.k
         lib, wd = _lib.load(), dc.weight.detach()
         for g in range(self.groups):
@@ -612,10 +637,12 @@ class HeightNetTrainer:
                                                  0, cg, None, _p(self.dcn_wf[g]), cg, _p(self.dcn_wb[g]), cg, 1,
                                                  _stream()), 'pack_conv_weights(dcn)')
 
-    def _act(self, name, N, H, W, C):
+    def _act(self, name, N, H, W, C, zero=False):
         key = (name, N, H, W, C)
         if key not in self._buf:
             self._buf[key] = D.Act.empty(N, H, W, C, 1, self.device)
+            if zero:
+                self._buf[key].data.zero_()
         return self._buf[key]
 
     def _f32(self, name, *shape):
@@ -624,35 +651,71 @@ class HeightNetTrainer:
             self._buf[key] = torch.empty(*shape, device=self.device)
         return self._buf[key]
 
-    # ---- forward -------------------------------------------------------------------------------
-    def forward(self, x, mlp_input):
-        """x: Act (B*N, C_in, fH, fW); mlp_input (B, N, 27).  Returns softmax height (B*N, H, fH, fW) fp32."""
-        net, lin = self.net, self._linear
-        N, H, W, C = x.N, x.H, x.W, self.C
+    # ---- camera-aware gate: BatchNorm1d (frozen) -> Mlp -> SELayer -> sigmoid (depthnet.py:119-169, 624-629) -------
+    def _gate_forward(self, m_in, mlp, se):
+        lin = self._linear
         f = lambda t: t.detach().float().contiguous()
-        m_in = mlp_input.reshape(-1, mlp_input.shape[-1]).contiguous().float()
-        mlp, se = net.depth_mlp, net.depth_se
         h1 = lin(m_in, f(mlp.fc1.weight), f(mlp.fc1.bias), 'relu', self.bn_scale, self.bn_shift)
         h2 = lin(h1, f(mlp.fc2.weight), f(mlp.fc2.bias))
         h3 = lin(h2, f(se.conv_reduce.weight.flatten(1)), f(se.conv_reduce.bias), 'relu')
         gate = lin(h3, f(se.conv_expand.weight.flatten(1)), f(se.conv_expand.bias), 'sigmoid')
+        return dict(h1=h1, h2=h2, h3=h3, gate=gate)
+
+    def _gate_backward(self, gsum, gs, m_in, mlp, se):
+        """gsum (N, C) = dL/d gate (per image and channel) -> gradients of the SELayer and the Mlp."""
+        lin = self._linear
+        f = lambda t: t.detach().float().contiguous()
+        h1, h2, h3, gate = gs['h1'], gs['h2'], gs['h3'], gs['gate']
+        m_bn = m_in * self.bn_scale.to(self.device) + self.bn_shift.to(self.device)
+        dze = (gsum * gate * (1.0 - gate)).contiguous()
+        _acc(se.conv_expand.weight, lin(dze.t().contiguous(), h3.t().contiguous()))
+        _acc(se.conv_expand.bias, dze.sum(0))
+        dzr = (lin(dze, f(se.conv_expand.weight.flatten(1)).t().contiguous()) * (h3 > 0).float()).contiguous()
+        _acc(se.conv_reduce.weight, lin(dzr.t().contiguous(), h2.t().contiguous()))
+        _acc(se.conv_reduce.bias, dzr.sum(0))
+        dh2 = lin(dzr, f(se.conv_reduce.weight.flatten(1)).t().contiguous())
+        _acc(mlp.fc2.weight, lin(dh2.t().contiguous(), h1.t().contiguous()))
+        _acc(mlp.fc2.bias, dh2.sum(0))
+        dz1 = (lin(dh2, f(mlp.fc2.weight).t().contiguous()) * (h1 > 0).float()).contiguous()
+        _acc(mlp.fc1.weight, lin(dz1.t().contiguous(), m_bn.t().contiguous()))
+        _acc(mlp.fc1.bias, dz1.sum(0))
+
+    # ---- forward -------------------------------------------------------------------------------
+    def forward(self, x, mlp_input):
+        """x: Act (B*N, C_in, fH, fW); mlp_input (B, N, 27).  Returns softmax height (B*N, H, fH, fW) fp32."""
+        net = self.net
+        N, H, W, C = x.N, x.H, x.W, self.C
+        m_in = mlp_input.reshape(-1, mlp_input.shape[-1]).contiguous().float()
+        gs = self._gate_forward(m_in, net.depth_mlp, net.depth_se)
         nhwc = D.nhwc_strides(C, H, W)
         h = self._act('h0', N, H, W, C)
         h32 = self._f32('h0_32', N, H, W, C)
-        self.reduce.forward(x, [dict(act='relu', out_act=h, out_f32=(h32, nhwc))], img_gate=gate)
+        self.reduce.forward(x, [dict(act='relu', out_act=h, out_f32=(h32, nhwc))], img_gate=gs['gate'])
+        self.saved = dict(x=x, m_in=m_in, gs=gs, gate=gs['gate'])
+        return self._trunk_forward(h, h32)
+
+    def _trunk_forward(self, h, h32):
+        """BasicBlocks -> ASPP (-> Dropout) -> [DCN] -> 1x1 head + softmax on the (gated / concatenated) feature map `h`
+        (Act; h32 = its fp32 copy for the first residual, None when the first block has a `downsample` path)."""
+        lin = self._linear
+        N, H, W, C = h.N, h.H, h.W, self.C
+        nhwc = D.nhwc_strides(C, H, W)
         hs, ts = [h], []
-        for bi, (c1, c2) in enumerate(self.blocks):
+        for bi, (c1, c2, ds) in enumerate(self.blocks):
             t = self._act('t%d' % bi, N, H, W, C)
+            if ds is not None:                      # identity path = 1x1 convolution of the concatenated input
+                h32 = self._f32('idn%d' % bi, N, H, W, C)
+                ds.forward(h, [dict(out_f32=(h32, nhwc))])
             c1.forward(h, [dict(act='relu', out_act=t)])
             hn, hn32 = self._act('h%d' % (bi + 1), N, H, W, C), self._f32('h%d_32' % (bi + 1), N, H, W, C)
             c2.forward(t, [dict(act='relu', out_act=hn, out_f32=(hn32, nhwc))], residual=(h32, nhwc[:3]))
             h, h32 = hn, hn32
             hs.append(h)
             ts.append(t)
-        mid = self.mid
-        cat = self._act('cat', N, H, W, 4 * mid)
+        mid, mp = self.mid, self.mid_pad
+        cat = self._act('cat', N, H, W, 4 * mp, zero=True)
         for b, conv in enumerate(self.branches):
-            conv.forward(h, [dict(act='relu', out_act=cat.slice(b * mid, (b + 1) * mid))])
+            conv.forward(h, [dict(act='relu', out_act=cat.slice(b * mp, b * mp + mid))])
         meanh = self._mean(h)
         x5 = lin(meanh, self.gap_ws, self.b5.to(self.device), 'relu')
         ib = lin(x5, self.w5s)
@@ -660,27 +723,32 @@ class HeightNetTrainer:
         self.aspp_out.forward(cat, [dict(act='relu', out_act=ha)], img_bias=ib)
         if self.dropout_p > 0.0:                     # in place: everything downstream (and the backward) sees the dropped map
             dropout_(ha, self.dropout_p, self.rng, salt=1)
-        k, g, cg = self.k, self.groups, C // self.groups
-        off = self._f32('off', N, H, W, self.noff)
-        self.dcn_offset.forward(ha, [dict(out_f32=(off, D.nhwc_strides(self.noff, H, W)))])
-        col = self._act('col', N, H, W, k * k * C)
-        _lib.check(_lib.load().dhd_dcn_im2col(_p(ha.data), ha.ld, ha.coff, ha.part_stride, ha.parts, C, N, H, W,
-                                              _p(off), self.noff, k, self.pad, self.dil, g, _p(col.data), col.ld,
-                                              col.part_stride, col.parts, _stream()), 'dcn_im2col')
-        out = self._act('dcn_out', N, H, W, C)
-        for gi in range(g):
-            D.conv2d(col.slice(gi * k * k * cg, (gi + 1) * k * k * cg), self.dcn_wf[gi], cg, precision='bf16',
-                     segs=[dict(out_act=out.slice(gi * cg, (gi + 1) * cg))])
+        sv = self.saved
+        sv.update(hs=hs, ts=ts, cat=cat, meanh=meanh, x5=x5, ha=ha)
+        out = ha
+        if self.dcn is not None:
+            k, g, cg = self.k, self.groups, C // self.groups
+            off = self._f32('off', N, H, W, self.noff)
+            self.dcn_offset.forward(ha, [dict(out_f32=(off, D.nhwc_strides(self.noff, H, W)))])
+            col = self._act('col', N, H, W, k * k * C)
+            _lib.check(_lib.load().dhd_dcn_im2col(_p(ha.data), ha.ld, ha.coff, ha.part_stride, ha.parts, C, N, H, W,
+                                                  _p(off), self.noff, k, self.pad, self.dil, g, _p(col.data), col.ld,
+                                                  col.part_stride, col.parts, _stream()), 'dcn_im2col')
+            out = self._act('dcn_out', N, H, W, C)
+            for gi in range(g):
+                D.conv2d(col.slice(gi * k * k * cg, (gi + 1) * k * k * cg), self.dcn_wf[gi], cg, precision='bf16',
+                         segs=[dict(out_act=out.slice(gi * cg, (gi + 1) * cg))])
+            sv.update(off=off, col=col)
         height = torch.empty(N, self.H_bins, H, W, device=self.device)
         self.head.forward(out, [dict(act='softmax', out_f32=(height, D.nchw_strides(self.H_bins, H, W)))])
-        self.saved = dict(x=x, m_in=m_in, h1=h1, h2=h2, h3=h3, gate=gate, hs=hs, ts=ts, cat=cat, meanh=meanh, x5=x5,
-                          ha=ha, off=off, col=col, out=out, height=height)
+        sv.update(out=out, height=height)
         return height
 
     # ---- loss ----------------------------------------------------------------------------------
     def loss(self, label, fg):
-        """label (npix,) int32 GT height bin (-1: none), fg (npix,) uint8/bool: MGHS.get_height_loss on
-        binned labels.  Returns a 1-element device tensor; keeps d loss / d logits for backward()."""
+        """label (npix,) int32 GT bin (-1: none), fg (npix,) uint8/bool: MGHS.get_height_loss (and the depth term of
+        get_depth_and_height_loss) on binned labels.  Returns a 1-element device tensor; keeps d loss / d logits for
+        backward()."""
         sv = self.saved
         h = sv['height']
         N, Hb, H, W = h.shape
@@ -695,43 +763,50 @@ class HeightNetTrainer:
         return res
 
     # ---- backward ------------------------------------------------------------------------------
-    def backward(self, want_dx=False):
+    def _trunk_backward(self):
+        """From self.dz (gradient at the head's logits) down to the trunk's input: returns dL/d hs[0] as an Act with the
+        channel count of that input (C, or cat_channels for the stereo first block) -- no activation mask applied."""
         sv, lin, lib = self.saved, self._linear, _lib.load()
-        x, hs, ts, cat, ha, off, col, out = sv['x'], sv['hs'], sv['ts'], sv['cat'], sv['ha'], sv['off'], sv['col'], sv['out']
-        N, H, W, C = x.N, x.H, x.W, self.C
+        hs, ts, cat, ha, out = sv['hs'], sv['ts'], sv['cat'], sv['ha'], sv['out']
+        N, H, W, C = ha.N, ha.H, ha.W, self.C
         HW = H * W
-        k, g, cg, mid = self.k, self.groups, C // self.groups, self.mid
+        mid, mp = self.mid, self.mid_pad
         nhwc = D.nhwc_strides(C, H, W)
         dz = self.dz
         _, sums = act_bwd(dz, None, None, want_sums=True)
-        dout = self._act('d_out', N, H, W, C)
-        self.head.backward(out, dz, [dict(out_act=dout)], bias_sums=sums[0])
-        # ---- DCN: grouped GEMM backward, then the sampling backward
-        dcol = self._act('d_col', N, H, W, k * k * C)
-        wgrad = _ensure_grad(self.dcn.weight)
-        for gi in range(g):
-            cs, ds = col.slice(gi * k * k * cg, (gi + 1) * k * k * cg), dout.slice(gi * cg, (gi + 1) * cg)
-            dw = D.conv2d_wgrad(cs, ds, cg)                                   # (cg, 1, k*k*cg), K = (tap, c)
-            wgrad[gi * cg:(gi + 1) * cg].add_(dw.view(cg, k, k, cg).permute(0, 3, 1, 2))
-            D.conv2d(ds, self.dcn_wb[gi], k * k * cg, precision='bf16',
-                     segs=[dict(out_act=dcol.slice(gi * k * k * cg, (gi + 1) * k * k * cg))])
-        dxs = self._f32('d_sample', N, H, W, C)
-        doff = self._f32('d_off', N, H, W, self.noff)
-        _lib.check(lib.dhd_dcn_col2im_bwd(_p(dcol.data), dcol.ld, _p(ha.data), ha.ld, ha.coff, C, N, H, W, _p(off),
-                                          self.noff, k, self.pad, self.dil, g, _p(dxs), _p(doff), _stream()),
-                   'dcn_col2im_bwd')
-        doff_a = self._act('d_off_a', N, H, W, self.dcn_offset.cout_pad)
-        doff_a.data.zero_()
-        doff_a.data[..., :self.noff] = doff.to(torch.bfloat16)
-        _, sums = act_bwd(doff_a, None, None, want_sums=True)
         dha = self._act('d_ha', N, H, W, C)
-        self.dcn_offset.backward(ha, doff_a, [dict(out_act=dha)], bias_sums=sums[0], residual=(dxs, nhwc[:3]))
+        if self.dcn is None:
+            self.head.backward(out, dz, [dict(out_act=dha)], bias_sums=sums[0])
+        else:
+            off, col = sv['off'], sv['col']
+            k, g, cg = self.k, self.groups, C // self.groups
+            dout = self._act('d_out', N, H, W, C)
+            self.head.backward(out, dz, [dict(out_act=dout)], bias_sums=sums[0])
+            # ---- DCN: grouped GEMM backward, then the sampling backward
+            dcol = self._act('d_col', N, H, W, k * k * C)
+            wgrad = _ensure_grad(self.dcn.weight)
+            for gi in range(g):
+                cs, ds = col.slice(gi * k * k * cg, (gi + 1) * k * k * cg), dout.slice(gi * cg, (gi + 1) * cg)
+                dw = D.conv2d_wgrad(cs, ds, cg)                                   # (cg, 1, k*k*cg), K = (tap, c)
+                wgrad[gi * cg:(gi + 1) * cg].add_(dw.view(cg, k, k, cg).permute(0, 3, 1, 2))
+                D.conv2d(ds, self.dcn_wb[gi], k * k * cg, precision='bf16',
+                         segs=[dict(out_act=dcol.slice(gi * k * k * cg, (gi + 1) * k * k * cg))])
+            dxs = self._f32('d_sample', N, H, W, C)
+            doff = self._f32('d_off', N, H, W, self.noff)
+            _lib.check(lib.dhd_dcn_col2im_bwd(_p(dcol.data), dcol.ld, _p(ha.data), ha.ld, ha.coff, C, N, H, W, _p(off),
+                                              self.noff, k, self.pad, self.dil, g, _p(dxs), _p(doff), _stream()),
+                       'dcn_col2im_bwd')
+            doff_a = self._act('d_off_a', N, H, W, self.dcn_offset.cout_pad)
+            doff_a.data.zero_()
+            doff_a.data[..., :self.noff] = doff.to(torch.bfloat16)
+            _, sums = act_bwd(doff_a, None, None, want_sums=True)
+            self.dcn_offset.backward(ha, doff_a, [dict(out_act=dha)], bias_sums=sums[0], residual=(dxs, nhwc[:3]))
         # ---- ASPP (Dropout backward = the same mask on the gradient; the ReLU test `y > 0` on the dropped map is
         # still right for every kept element and the dropped ones are already zero)
         if self.dropout_p > 0.0:
             dropout_(dha, self.dropout_p, self.rng, salt=1)
         act_bwd(dha, ha, 'relu')
-        dcat = self._act('d_cat', N, H, W, 4 * mid)
+        dcat = self._act('d_cat', N, H, W, 4 * mp)
         self.aspp_out.backward(cat, dha, [dict(out_act=dcat)])
         # gradient of the per-image bias the global branch adds to the conv sum: pixel sum of the gradient at the
         # convolution output (behind the BatchNorm backward when it runs on batch statistics)
@@ -751,7 +826,7 @@ class HeightNetTrainer:
         for b, conv in enumerate(self.branches):
             dst = A if b % 2 == 0 else B
             kw = {} if src is None else dict(residual=(src, nhwc[:3]))
-            conv.backward(hl, dcat.slice(b * mid, (b + 1) * mid), [dict(out_f32=(dst, nhwc))], **kw)
+            conv.backward(hl, dcat.slice(b * mp, (b + 1) * mp), [dict(out_f32=(dst, nhwc))], **kw)
             src = dst
         dh = self._act('d_h', N, H, W, C)
         _lib.check(lib.dhd_add_rowvec(_p(src), _p(dmean.contiguous()), N, HW, C, _p(dh.data), dh.ld, dh.coff,
@@ -759,46 +834,195 @@ class HeightNetTrainer:
         act_bwd(dh, hl, 'relu')
         # ---- BasicBlocks, last to first
         for bi in range(len(self.blocks) - 1, -1, -1):
-            c1, c2 = self.blocks[bi]
+            c1, c2, ds = self.blocks[bi]
             t, hin = ts[bi], hs[bi]
             dt = self._act('d_t', N, H, W, C)
             c2.backward(t, dh, [dict(out_act=dt)])
             act_bwd(dt, t, 'relu')
-            dhin = self._act('d_hin%d' % (bi & 1), N, H, W, C)
+            dhin = self._act('d_hin%d' % (bi & 1), N, H, W, hin.C)
             c1.backward(hin, dt, [dict(out_act=dhin)])
-            act_bwd(dhin, hin if bi > 0 else None, 'relu' if bi > 0 else None, add=dh)     # + identity path
+            if ds is not None:                        # identity path = the 1x1 downsample convolution of the concatenated input
+                _, sums = act_bwd(dh, None, None, want_sums=True)
+                did = self._act('d_id', N, H, W, hin.C)
+                ds.backward(hin, dh, [dict(out_act=did)], bias_sums=sums[0])
+                act_bwd(dhin, None, None, add=did)
+            else:
+                act_bwd(dhin, hin if bi > 0 else None, 'relu' if bi > 0 else None, add=dh)     # + identity path
             dh = dhin
+        return dh
+
+    def backward(self, want_dx=False):
+        sv, lib = self.saved, _lib.load()
+        x = sv['x']
+        N, H, W, C = x.N, x.H, x.W, self.C
+        HW = H * W
+        dh = self._trunk_backward()
         # ---- reduce conv + SE gate
-        gate = sv['gate']
+        gate, h0 = sv['gate'], sv['hs'][0]
         dpre = self._act('d_pre', N, H, W, C)
         gsum = self._f32('gsum', N, C)
         ws = _workspace(self.device, lib.dhd_sfa_gate_bwd_workspace_bytes(N, HW, C))
-        _lib.check(lib.dhd_se_gate_bwd(_p(dh.data), dh.ld, dh.coff, _p(hs[0].data), hs[0].ld, hs[0].coff, C, N, HW,
+        _lib.check(lib.dhd_se_gate_bwd(_p(dh.data), dh.ld, dh.coff, _p(h0.data), h0.ld, h0.coff, C, N, HW,
                                        _p(gate), _p(dpre.data), dpre.ld, dpre.coff, _p(gsum), _p(ws), _stream()),
                    'se_gate_bwd')
         _, sums = act_bwd(dpre, None, None, want_sums=True)
         dx = self._act('d_x', N, H, W, x.C) if want_dx else None
         self.reduce.backward(x, dpre, [dict(out_act=dx)] if want_dx else None, bias_sums=sums[0])
         # ---- camera-aware gate MLP (B*N rows)
-        net = self.net
-        mlp, se = net.depth_mlp, net.depth_se
-        f = lambda t: t.detach().float().contiguous()
-        h1, h2, h3, m_in = sv['h1'], sv['h2'], sv['h3'], sv['m_in']
-        m_bn = m_in * self.bn_scale.to(self.device) + self.bn_shift.to(self.device)
-        dze = (gsum * gate * (1.0 - gate)).contiguous()
-        _acc(se.conv_expand.weight, lin(dze.t().contiguous(), h3.t().contiguous()))
-        _acc(se.conv_expand.bias, dze.sum(0))
-        dzr = (lin(dze, f(se.conv_expand.weight.flatten(1)).t().contiguous()) * (h3 > 0).float()).contiguous()
-        _acc(se.conv_reduce.weight, lin(dzr.t().contiguous(), h2.t().contiguous()))
-        _acc(se.conv_reduce.bias, dzr.sum(0))
-        dh2 = lin(dzr, f(se.conv_reduce.weight.flatten(1)).t().contiguous())
-        _acc(mlp.fc2.weight, lin(dh2.t().contiguous(), h1.t().contiguous()))
-        _acc(mlp.fc2.bias, dh2.sum(0))
-        dz1 = (lin(dh2, f(mlp.fc2.weight).t().contiguous()) * (h1 > 0).float()).contiguous()
-        _acc(mlp.fc1.weight, lin(dz1.t().contiguous(), m_bn.t().contiguous()))
-        _acc(mlp.fc1.bias, dz1.sum(0))
+        self._gate_backward(gsum, sv['gs'], sv['m_in'], self.net.depth_mlp, self.net.depth_se)
         if self.dropout_p > 0.0:
             self.rng[1:].add_(1)                   # next step, next mask (a device-side update: graph replays advance too)
+        return dx
+
+
+class _TrainConvScatter(_TrainConv):
+    """A 1x1 convolution whose input channels sit at scattered positions of a wider, zero-padded buffer (the ASPP's
+    conv1 when aspp_mid_channels is not a multiple of 64: the four branch slices start on 64-channel granules).  The
+    master weight keeps the reference's (Cout, n_used + extra, 1, 1) shape; forward / data-gradient weights are packed
+    from a scattered copy and the weight gradient is gathered back."""
+
+    def __init__(self, weight, bn, n_used, n_padded, cols):
+        self._full, self._cols, self._n_used, self._n_pad = weight, cols, n_used, n_padded
+        self._wide = torch.zeros(weight.shape[0], n_padded, 1, 1, device=weight.device)
+        super().__init__(self._wide, None, bn, 1)
+
+    def refresh(self):
+        self._wide.zero_()
+        self._wide[:, self._cols.to(self._wide.device)] = self._full.detach()[:, :self._n_used].float()
+        super().refresh()
+
+    def backward(self, x, dy, dx_segs=None, bias_sums=None, **kw):
+        self._wide.grad = None
+        super().backward(x, dy, dx_segs, bias_sums, **kw)
+        g = self._wide.grad
+        _ensure_grad(self._full)[:, :self._n_used].add_(g[:, self._cols.to(g.device)])
+        self._wide.grad = None
+
+
+class DepthNetTrainer(HeightNetTrainer):
+    """Camera-aware DepthNet of MGHS_Depth / MGHS_Stereo (depthnet.py:172-243, 362-415) in training: the reduce conv feeds
+    TWO camera-gated branches -- context (SE gate -> 1x1 context_conv -> the pool's context feature) and depth (SE gate
+    [-> cat with cost_volumn_net(cost volume) when stereo] -> the HeightNet trunk -> softmax over D) -- and the backward
+    of all of it from the pool's depth / context gradients plus the depth loss (lss_heightmap.py:859-897).  The plane-sweep
+    cost volume itself is a constant of the step (the reference computes it under no_grad, depthnet.py:405-407);
+    cost_volumn_net is trained."""
+
+    def __init__(self, net, device='cuda', loss_weight=0.05, dropout=0.0, seed=0):
+        self.stereo = bool(getattr(net, 'stereo', False))
+        if self.stereo:
+            cv = net.cost_volumn_net
+            self.Dcv = cv[0].in_channels
+            self.Dcv_pad = (self.Dcv + 63) // 64 * 64
+            self.cv1 = _TrainConv(cv[0].weight, cv[0].bias, cv[1], 3, stride=2, cin_pad=self.Dcv_pad, cout_pad=self.Dcv_pad)
+            self.cv2 = _TrainConv(cv[2].weight, cv[2].bias, cv[3], 3, stride=2, cin_pad=self.Dcv_pad, cout_pad=self.Dcv_pad)
+        super().__init__(net, device, loss_weight, dropout, seed)
+        self.context = _TrainConv(net.context_conv.weight, net.context_conv.bias, None, 1,
+                                  cout_pad=(net.context_conv.weight.shape[0] + 63) // 64 * 64)
+        self.Cctx = net.context_conv.weight.shape[0]
+        self.D_bins = self.H_bins
+
+    def _convs(self):
+        cs = super()._convs()
+        if hasattr(self, 'context'):
+            cs.append(self.context)
+        if self.stereo:
+            cs += [self.cv1, self.cv2]
+        return cs
+
+    def _gated(self, x32, gate, name, C_out=None, want32=False):
+        N, H, W, C = x32.shape
+        out = self._act(name, N, H, W, C_out or C, zero=C_out is not None)
+        o32 = self._f32(name + '_32', N, H, W, C) if want32 else None
+        _lib.check(_lib.load().dhd_gate_channels(_p(x32), N, H * W, C, _p(gate), _p(out.data), out.ld, out.coff,
+                                                 out.part_stride, out.parts, _p(o32), _stream()), 'gate_channels')
+        return out, o32
+
+    def forward(self, x, mlp_input, cost_volume=None):
+        """x: Act (B*N, C_in, fH, fW); cost_volume: Act (B*N, Dcv_pad, 4fH, 4fW) matching probabilities (stereo) --
+        zeros when there is no previous frame.  Returns (softmax depth (B*N, D, fH, fW) NCHW, context (B*N, fH, fW, C))."""
+        net = self.net
+        N, H, W, C = x.N, x.H, x.W, self.C
+        if self.stereo != (cost_volume is not None):
+            raise RuntimeError('DepthNet(stereo=%s) called %s a cost volume' % (self.stereo, 'with' if cost_volume is not None else 'without'))
+        m_in = mlp_input.reshape(-1, mlp_input.shape[-1]).contiguous().float()
+        gd = self._gate_forward(m_in, net.depth_mlp, net.depth_se)
+        gc = self._gate_forward(m_in, net.context_mlp, net.context_se)
+        nhwc = D.nhwc_strides(C, H, W)
+        x32 = self._f32('x32', N, H, W, C)
+        self.reduce.forward(x, [dict(act='relu', out_f32=(x32, nhwc))])
+        ctx, _ = self._gated(x32, gc['gate'], 'ctx')
+        feat = torch.empty(N, H, W, self.Cctx, device=self.device)
+        self.context.forward(ctx, [dict(out_f32=(feat, D.nhwc_strides(self.Cctx, H, W)))])
+        self.saved = dict(x=x, m_in=m_in, gs=gd, gate=gd['gate'], gc=gc, ctx=ctx)
+        if not self.stereo:
+            h, h32 = self._gated(x32, gd['gate'], 'h0', want32=True)
+            depth = self._trunk_forward(h, h32)
+        else:
+            cat, _ = self._gated(x32, gd['gate'], 'h0cat', C_out=self.cat_channels)       # channels [0, C) of the zeroed cat buffer
+            h2, w2 = (cost_volume.H + 1) // 2, (cost_volume.W + 1) // 2
+            cmid = self._act('cv_mid', N, h2, w2, self.Dcv_pad, zero=True)
+            self.cv1.forward(cost_volume, [dict(out_act=cmid)])
+            self.cv2.forward(cmid, [dict(out_act=cat.slice(C, C + self.Dcv_pad if C + self.Dcv_pad <= self.cat_channels else self.cat_channels))])
+            self.saved.update(cv=cost_volume, cmid=cmid)
+            depth = self._trunk_forward(cat, None)
+        return depth, feat
+
+    def backward(self, depth_grad=None, feat_grad=None, want_dx=True):
+        """depth_grad (B*N, D, fH, fW) fp32: gradient at the softmax depth coming from the pool (added to the depth loss
+        gradient kept by loss(); either may be absent); feat_grad (B*N, fH, fW, C) fp32: gradient at the context feature."""
+        sv, lib = self.saved, _lib.load()
+        x = sv['x']
+        N, H, W, C = x.N, x.H, x.W, self.C
+        HW = H * W
+        if depth_grad is not None:
+            # through the softmax: p * (g - sum_k p_k g_k), joined with the loss gradient at the logits
+            p = sv['height']
+            dlog = p * (depth_grad - (p * depth_grad).sum(dim=1, keepdim=True))
+            if getattr(self, 'dz', None) is None:
+                self.dz = self._act('dz', N, H, W, self.head.cout_pad, zero=True)
+                self.dz.data.zero_()
+            self.dz.data[..., :self.D_bins].add_(dlog.permute(0, 2, 3, 1))
+        dcat = self._trunk_backward()                                    # dL/d (gated depth feature [| cost_volumn_net output])
+        self.dz = None
+        ws = _workspace(self.device, lib.dhd_sfa_gate_bwd_workspace_bytes(N, HW, C))
+        # ---- depth branch gate
+        hd = sv['hs'][0]
+        dpre = self._act('d_pre', N, H, W, C)
+        gsum_d = self._f32('gsum_d', N, C)
+        _lib.check(lib.dhd_se_gate_bwd(_p(dcat.data), dcat.ld, dcat.coff, _p(hd.data), hd.ld, hd.coff, C, N, HW,
+                                       _p(sv['gate']), _p(dpre.data), dpre.ld, dpre.coff, _p(gsum_d), _p(ws), _stream()),
+                   'se_gate_bwd(depth)')
+        if self.stereo:
+            # ---- cost_volumn_net: weight / bias / BatchNorm gradients only (its input is a constant)
+            dcv = dcat.slice(C, C + self.Dcv_pad) if C + self.Dcv_pad <= self.cat_channels else dcat.slice(C, self.cat_channels)
+            dmid = self._act('d_cvmid', N, sv['cmid'].H, sv['cmid'].W, self.Dcv_pad)
+            _, sums = act_bwd(dcv, None, None, want_sums=True)
+            self.cv2.backward(sv['cmid'], dcv, [dict(out_act=dmid)], bias_sums=sums[0])
+            _, sums = act_bwd(dmid, None, None, want_sums=True)
+            self.cv1.backward(sv['cv'], dmid, None, bias_sums=sums[0])
+        # ---- context branch: 1x1 conv + gate
+        gsum_c = None
+        if feat_grad is not None:
+            dfe = self._act('d_feat', N, H, W, self.context.cout_pad, zero=True)
+            dfe.data[..., :self.Cctx].copy_(feat_grad.reshape(N, H, W, self.Cctx))
+            _, sums = act_bwd(dfe, None, None, want_sums=True)
+            dctx = self._act('d_ctx', N, H, W, C)
+            self.context.backward(sv['ctx'], dfe, [dict(out_act=dctx)], bias_sums=sums[0])
+            dpre_c = self._act('d_pre_c', N, H, W, C)
+            gsum_c = self._f32('gsum_c', N, C)
+            _lib.check(lib.dhd_se_gate_bwd(_p(dctx.data), dctx.ld, dctx.coff, _p(sv['ctx'].data), sv['ctx'].ld, sv['ctx'].coff,
+                                           C, N, HW, _p(sv['gc']['gate']), _p(dpre_c.data), dpre_c.ld, dpre_c.coff,
+                                           _p(gsum_c), _p(ws), _stream()), 'se_gate_bwd(context)')
+            act_bwd(dpre, None, None, add=dpre_c)                         # both branches meet at the reduce conv's output
+        _, sums = act_bwd(dpre, None, None, want_sums=True)
+        dx = self._act('d_x', N, H, W, x.C) if want_dx else None
+        self.reduce.backward(x, dpre, [dict(out_act=dx)] if want_dx else None, bias_sums=sums[0])
+        net = self.net
+        self._gate_backward(gsum_d, sv['gs'], sv['m_in'], net.depth_mlp, net.depth_se)
+        if gsum_c is not None:
+            self._gate_backward(gsum_c, sv['gc'], sv['m_in'], net.context_mlp, net.context_se)
+        if self.dropout_p > 0.0:
+            self.rng[1:].add_(1)
         return dx
 
 

@@ -338,9 +338,14 @@ class MGHS_Depth(MGHS):
         x, mlp_input = input[0], input[7]
         B, N, C, H, W = x.shape
         from dhd_b200 import autograd as A
-        if A.wants_grad(self, x):
-            raise NotImplementedError('dhd_b200 MGHS_Depth.forward under autograd: the camera-aware DepthNet has no '
-                                      'backward in this build (DESIGN.md 7); wrap the call in torch.no_grad() or use eval()')
+        if x.is_cuda and A.wants_grad(self, x):
+            # differentiable form (training): DepthNetTrainer + HeightNetTrainer + pool backward (dhd_b200.autograd)
+            plan = self._bins(input)
+            pix = lambda h: height_to_mask(h, self.height_range, self.mask_range)
+            outs = A.mghs_depth_forward(self, input, stereo_metas, plan, pix)
+            self.grid_config = dict(_BEV_PASS_GRID)        # "reset grid_config!", LH:848-854
+            self.create_grid_infos(**self.grid_config)
+            return outs
         if not x.is_cuda:
             raise RuntimeError('dhd_b200: expected CUDA tensors (the hot path has no CPU fallback)')
         with torch.no_grad():

@@ -187,3 +187,68 @@ def test_detector_reference_api_inference(cuda_lib):
     out['loss'].backward()
     assert model.occ_head.predicter[2].weight.grad is not None
     assert model.img_view_transformer.depth_net.weight.grad is not None
+
+
+def test_dhd_stereo_forward_train_two_frames(cuda_lib):
+    """DHD_stereo (DHD-M wiring at reduced image size: two temporal frames + the stereo reference frame) through the
+    reference's entry point: forward_train -> dict(loss_depth, loss_height, loss_occ, sem_scal, geo_scal)
+    (DHD_model.py:577-614) -> backward reaches the camera-aware DepthNet (incl. cost_volumn_net), HeightNet, both
+    pre-process nets, the encoders, SFA and the head; the previous frame runs under no_grad on the inference engines."""
+    import projects.mmdet3d_plugin  # noqa: F401
+    from dhd_b200 import compat as C
+    from dhd_b200 import synth
+    from tests.test_encoders_gpu import _dhd_s_model_cfg
+    c, D_, size = 64, 88, (128, 352)
+    cfg = _dhd_s_model_cfg()
+    grid = dict(cfg['img_view_transformer']['grid_config'], depth=[1.0, 45.0, 0.5])
+    vt = dict(cfg['img_view_transformer'], type='MGHS_Stereo', grid_config=grid, input_size=size, collapse_z=False,
+              loss_depth_weight=0.05, depthnet_cfg=dict(use_dcn=False, aspp_mid_channels=96, stereo=True, bias=5.0),
+              heightnet_cfg=dict(use_dcn=False, aspp_mid_channels=96))
+    for k in ('mask_1_grid', 'mask_2_grid', 'mask_3_grid'):
+        vt[k] = dict(vt[k], depth=[1.0, 45.0, 0.5])
+    cfg.update(type='DHD_stereo', img_view_transformer=vt, num_adj=1, align_after_view_transfromation=False,
+               pre_process=dict(type='CustomResNet', numC_input=c, num_layer=[1], num_channels=[c], stride=[1], backbone_output_ids=[0]),
+               pre_process_net_3d=dict(type='CustomResNet', numC_input=c * 16, num_layer=[1], num_channels=[c * 16], stride=[1],
+                                       backbone_output_ids=[0]),
+               img_bev_encoder_backbone=dict(type='CustomResNet', numC_input=c * 2, num_channels=[c * 2, c * 4, c * 8]),
+               img_voxel_encoder0_backbone=dict(type='UNet', n_channels=c * 8, n_classes=64),
+               img_voxel_encoder1_backbone=dict(type='UNet', n_channels=c * 8, n_classes=128),
+               img_voxel_encoder2_backbone=dict(type='UNet', n_channels=c * 16, n_classes=64))
+    model = C.DETECTORS.build(cfg)
+    model.load_state_dict(DO.seeded_state_dict(model, 91))
+    model = model.cuda().train()
+    B, N, nf = 1, 6, model.num_frame                       # 3 = key + previous + stereo reference
+    fH, fW = size[0] // 16, size[1] // 16
+    rig = synth.synthetic_rig(B, N, size, seed=7)
+    rep = lambda t: torch.cat([t] * nf, dim=1).cuda()      # the same rig for every frame (ego at rest)
+    s2e, e2g, K, pr, pt, bda = rig
+    feats = DO.seeded_tensor((B, N * nf, 256, fH, fW), 92).cuda().requires_grad_(True)
+    stereo = DO.seeded_tensor((B, N * nf, 64, 4 * fH, 4 * fW), 93).cuda()
+    img_inputs = [(feats, stereo), rep(s2e), rep(e2g), rep(K), rep(pr), rep(pt), bda.cuda()]
+    g = torch.Generator(device='cuda').manual_seed(4)
+    hit = torch.rand(B, N, *size, device='cuda', generator=g) < 0.03
+    kw = dict(voxel_semantics=torch.randint(0, 18, (B, 200, 200, 16), device='cuda', generator=g),
+              mask_camera=torch.rand(B, 200, 200, 16, device='cuda', generator=g) < 0.5,
+              gt_depth=torch.where(hit, 1.0 + 40.0 * torch.rand(B, N, *size, device='cuda', generator=g), torch.zeros((), device='cuda')),
+              gt_height=torch.where(hit, -1.0 + 6.0 * torch.rand(B, N, *size, device='cuda', generator=g), torch.zeros((), device='cuda')))
+    losses = model.forward_train(img_inputs=img_inputs, img_metas=[{}] * B, **kw)
+    assert set(losses) == {'loss_depth', 'loss_height', 'loss_occ', 'loss_voxel_sem_scal', 'loss_voxel_geo_scal'}
+    total = sum(losses.values())
+    assert torch.isfinite(total)
+    total.backward()
+    vtm = model.img_view_transformer
+    for name, p in (('depth_net.context_conv', vtm.depth_net.context_conv.weight),
+                    ('depth_net.cost_volumn_net', vtm.depth_net.cost_volumn_net[0].weight),
+                    ('depth_net.depth_conv.0.downsample', vtm.depth_net.depth_conv[0].downsample.weight),
+                    ('height_net head', list(vtm.height_net.depth_conv)[-1].weight),
+                    ('pre_process_net', model.pre_process_net.layers[0][0].conv1.weight),
+                    ('pre_process_net_3d', model.pre_process_net_3d.layers[0][0].conv1.weight),
+                    ('voxel encoder 2', model.img_voxel_encoder2.inc.double_conv[0].weight),
+                    ('occ head', model.occ_head.predicter[2].weight)):
+        assert p.grad is not None and torch.isfinite(p.grad).all() and float(p.grad.abs().max()) > 0, name
+    assert feats.grad is not None and float(feats.grad[:, :N].abs().max()) >= 0.0
+    # inference through the same detector (eval, no_grad): the reference's list of uint8 maps
+    model.eval()
+    with torch.no_grad():
+        occ = model.simple_test(None, [{}] * B, img=img_inputs)
+    assert len(occ) == B and occ[0].shape == (200, 200, 16) and occ[0].dtype == np.uint8

@@ -724,3 +724,70 @@ def test_depth_and_height_loss_kernels_match_the_plugin_restatement(cuda_lib):
         g = dz.float()                                         # (BN, Kpad, fH, fW)
         assert float(g[:, K:].abs().max()) == 0.0
         assert rel(g[:, :K], z.grad.cpu()) < 5e-3              # bf16 storage of the gradient
+
+
+@pytest.mark.parametrize('stereo,use_dcn,aspp_mid', [(True, False, 96),      # DHD-M / DHD-L depthnet_cfg (DHD-M.py:103-106)
+                                                     (False, True, -1)])     # MGHS_Depth defaults (DCN, ASPP 256)
+def test_depthnet_trainer_loss_and_backward(cuda_lib, stereo, use_dcn, aspp_mid):
+    """Camera-aware DepthNet (depthnet.py:172-243, 362-415) on the training path: forward + depth loss + backward of both
+    SE-gated branches, the context conv, cost_volumn_net (stereo), the first block's 1x1 `downsample` path, ASPP with 96
+    mid channels, DCN on / off -- every gradient against torch autograd over the oracle (bf16 straight-through rounding
+    after every ReLU), fed by the depth loss AND pool-style gradients at the depth distribution and the context."""
+    import projects.mmdet3d_plugin  # noqa: F401
+    from dhd_b200 import dense as D
+    from dhd_b200.train import DepthNetTrainer
+    from oracle import dense_oracle as DO
+    from projects.mmdet3d_plugin.models.model_utils.depthnet import DepthNet
+    Dn, Cc = 88, 64
+    net = DepthNet(256, 256, Cc, Dn, use_dcn=use_dcn, stereo=stereo, aspp_mid_channels=aspp_mid, bias=5.0).eval()
+    sd0 = _bf16_sd(DO.seeded_state_dict(net, 14))
+    for k in sd0:
+        if 'conv_offset' in k:
+            sd0[k] = (sd0[k] * 0.05).bfloat16().float()
+    net.load_state_dict(sd0)
+    BN, H, W = 6, 16, 44
+    x = DO.seeded_tensor((BN, 256, H, W), 15).bfloat16().float()
+    mlp_in = DO.seeded_tensor((1, BN, 27), 16)
+    cv = DO.seeded_tensor((BN, Dn, 4 * H, 4 * W), 17).softmax(1).bfloat16().float() if stereo else None
+    g = torch.Generator().manual_seed(19)
+    label = torch.randint(-1, Dn, (BN * H * W,), generator=g).int()
+    fg = torch.rand(BN * H * W, generator=g) < 0.3
+    g_depth = (torch.randn(BN, Dn, H, W, generator=g) * 1e-3)
+    g_feat = (torch.randn(BN, H, W, Cc, generator=g) * 1e-3)
+    # ---- oracle: autograd over the restatement
+    sd = {k: v.clone().requires_grad_(v.dtype.is_floating_point and 'running' not in k) for k, v in net.state_dict().items()}
+    y = _shim_oracle_call(DO.depthnet_forward, sd, x, mlp_in, cost_volume=cv)
+    probs, ctx = y[:, :Dn].softmax(1), y[:, Dn:]
+    p2 = probs.permute(0, 2, 3, 1).reshape(-1, Dn)
+    onehot = torch.zeros(BN * H * W, Dn + 1)
+    onehot[torch.arange(BN * H * W), (label + 1).long()] = 1.0
+    onehot = onehot[:, 1:]
+    loss = 0.05 * torch.nn.functional.binary_cross_entropy(p2[fg], onehot[fg], reduction='none').sum() / max(1.0, float(fg.sum()))
+    (loss + (probs * g_depth).sum() + (ctx.permute(0, 2, 3, 1) * g_feat).sum()).backward()
+    # ---- CUDA training path
+    net = net.cuda()
+    for p in net.parameters():
+        p.grad = None
+    tr = DepthNetTrainer(net, loss_weight=0.05)
+    cva = None
+    if stereo:
+        cva = D.Act(torch.zeros(BN, 4 * H, 4 * W, tr.Dcv_pad, dtype=torch.bfloat16, device='cuda'), tr.Dcv_pad, 1)
+        cva.data[..., :Dn].copy_(cv.permute(0, 2, 3, 1))
+    depth, feat = tr.forward(D.pack_input(x.cuda(), 1), mlp_in.cuda(), cva)
+    assert rel(depth, probs.detach()) < 2e-2 and rel(feat.permute(0, 3, 1, 2), ctx.detach()) < 2e-2
+    res = tr.loss(label.cuda(), fg.cuda())
+    assert abs(float(res[0]) - float(loss.detach())) / float(loss.detach()) < 2e-2
+    dx = tr.backward(depth_grad=g_depth.cuda(), feat_grad=g_feat.cuda(), want_dx=True)
+    torch.cuda.synchronize()
+    errs = _grad_errors(net, sd)
+    print('relative L2 gradient errors:', {k: round(v, 4) for k, v in errs.items()})
+    assert torch.isfinite(dx.data.float()).all()
+    # same bound as the HeightNet trunk it shares (bf16 forward differences amplified by the DCN offsets when on);
+    # the branches that do not pass through the DCN are tight
+    assert max(errs.values()) < (0.12 if use_dcn else 0.05), errs
+    for name, p in net.named_parameters():
+        if name in errs:
+            assert cos(p.grad, sd[name].grad) > 0.99, name
+    assert errs['context_conv.weight'] < 2e-2 and errs['context_mlp.fc1.weight'] < 5e-2
+    if stereo:
+        assert errs['cost_volumn_net.0.weight'] < 5e-2 and errs['depth_conv.0.downsample.weight'] < 5e-2
