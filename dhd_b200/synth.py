@@ -100,3 +100,31 @@ def dhdl_view_transformer(precision, B):
                  frustum=vt.cv_frustum.cuda(), cv_downsample=4, downsample=vt.downsample, grid_config=vt.grid_config,
                  cv_feat_list=[feat(), feat()])
     return vt, [x, s2e, e2g, K, pr, pt, bda, mlp], metas
+
+
+# ---------------------------------------------------------------------------------------------- cfg-4 ("DHD-B") / cfg-5 model dicts
+DHD_B = dict(DHD_S, input_size=(384, 1056))       # BASELINE configs[3]: the DHD-S topology at 384x1056 (24x66 features)
+
+
+def dhd_l_model_cfg(precision='bf16'):
+    """`model` of projects/configs/DHD/DHD-L.py:41-190 without the image backbone / neck (Swin-B + FPN_LSS, outside the hot
+    path: the detector takes the per-frame image features instead of images)."""
+    c = 64
+    vt = dict(DHD_L_VIEW_TRANSFORMER, type='MGHS_Stereo', precision=precision)
+    enc = lambda n_in, n_out: dict(type='UNet', n_channels=n_in, n_classes=n_out, precision=precision)
+    return dict(
+        type='DHD_stereo', align_after_view_transfromation=False, num_adj=1,
+        img_view_transformer=vt,
+        img_bev_encoder_backbone=dict(type='CustomResNet', numC_input=c * 2, num_channels=[c * 2, c * 4, c * 8], precision=precision),
+        img_bev_encoder_neck=dict(type='FPN_LSS', in_channels=c * 8 + c * 2, out_channels=256, precision=precision),
+        pre_process=dict(type='CustomResNet', numC_input=c, num_layer=[1], num_channels=[c], stride=[1], backbone_output_ids=[0],
+                         precision=precision),
+        pre_process_net_3d=dict(type='CustomResNet', numC_input=c * 16, num_layer=[1], num_channels=[c * 16], stride=[1],
+                                backbone_output_ids=[0], precision=precision),
+        img_voxel_encoder0_backbone=enc(c * 8, 64), img_voxel_encoder0_neck=dict(type='Identity'),
+        img_voxel_encoder1_backbone=enc(c * 8, 128), img_voxel_encoder1_neck=dict(type='Identity'),
+        img_voxel_encoder2_backbone=enc(c * 16, 64), img_voxel_encoder2_neck=dict(type='Identity'),
+        mix=dict(type='SFA', in_channels=512, out_channels=256, precision=precision),
+        occ_head=dict(type='predictor', in_dim=256, out_dim=256, Dz=16, use_mask=True, num_classes=18, use_predicter=True,
+                      class_balance=True, weight_ce=10.0, precision=precision,
+                      loss_occ=dict(type='CrossEntropyLoss', use_sigmoid=False, ignore_index=255, loss_weight=1.0)))

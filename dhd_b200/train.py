@@ -106,7 +106,8 @@ class _TrainConv:
             else:
                 self.scale = None                  # batch statistics: nothing to fold, BN runs as its own pass
             self.w_fwd = torch.empty(self.Cout, taps, 1, self.cin_pad, dtype=torch.bfloat16, device=dev)
-            self.w_bwd = torch.empty(self.Cin, taps, 1, self.cout_pad, dtype=torch.bfloat16, device=dev)
+            # data-gradient weight [ci][tap][co]: rows beyond Cin (zero-padded input channels) stay zero
+            self.w_bwd = torch.zeros(self.cin_pad, taps, 1, self.cout_pad, dtype=torch.bfloat16, device=dev)
         if self.bn is None or self.batch_bn:
             self.bias = self.bias_p.detach() if self.bias_p is not None else None     # shares the parameter's storage
         else:
