@@ -132,8 +132,8 @@ class _TrainConv:
                             offs.append((oy, ox))
                             ws.append(wd[:, :, ky, kx].t())           # (Cin, Cout)
                     wp = torch.stack(ws, dim=1)                        # (Cin, taps, Cout)
-                    if self.cout_pad != self.Cout:
-                        wp = torch.nn.functional.pad(wp, (0, self.cout_pad - self.Cout))
+                    if self.cout_pad != self.Cout or self.cin_pad != wp.shape[0]:      # zero columns / rows of the padding
+                        wp = torch.nn.functional.pad(wp, (0, self.cout_pad - self.Cout, 0, 0, 0, self.cin_pad - wp.shape[0]))
                     self.phases.append((py, px, offs, wp.unsqueeze(2).to(torch.bfloat16).contiguous()))
 
     def forward(self, x, segs, **kw):
