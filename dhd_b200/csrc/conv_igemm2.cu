@@ -40,11 +40,13 @@ struct Conv2Params {
   dhd_conv_desc d;
   int tiles_w, tiles_h, n_tiles, total_tiles;
   int seg_b16_tma[DHD_CONV_MAX_SEGS], seg_f32_tma[DHD_CONV_MAX_SEGS];
+  int seg_b16_wide[DHD_CONV_MAX_SEGS];      // bf16 output leaves in 64-channel (128-byte row) TMA boxes
 };
 
 struct Conv2Maps {
   CUtensorMap a, b;
   CUtensorMap o16[DHD_CONV_MAX_SEGS][3];
+  CUtensorMap o16w[DHD_CONV_MAX_SEGS];      // 64-channel boxes, SWIZZLE_128B (single-part bf16 outputs)
   CUtensorMap o32[DHD_CONV_MAX_SEGS];
 };
 
@@ -268,6 +270,71 @@ conv_igemm2_kernel(const __grid_constant__ Conv2Maps M, const __grid_constant__ 
             }
           }
         };
+        if (P.seg_b16_wide[sgi] != 0) {
+          // ---- bf16-only output, 64 channels (one 128-byte row) per TMA store.  The 32-channel path below issues one
+          // 8 KB box store (128 rows x 64 B) per chunk and waits for the store two chunks back to release its staging
+          // tile: on the 1x1 layers (4 k-steps per 256 columns) that store cadence bounds the tile (ncu
+          // profiles/r02_conv_sfa_full.txt: tensor pipe 14 % active, the epilogue warps parked behind
+          // cp.async.bulk.wait_group.read).  Twice the bytes per store and per barrier pair halves both.
+          const int wb_lo = (c_lo - n0) / 64, wb_hi = (c_hi - n0 + 63) / 64;
+#pragma unroll 1
+          for (int wb = wb_lo; wb < wb_hi; ++wb) {
+            if (wb % G != grp) continue;
+            uint4 q[8];
+            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(q);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              const int cb = wb * 2 + half;
+              float v[32];
+              if (n0 + cb * 32 < c_hi) {
+                affine(cb, v, 0.f);
+                switch (act) {
+                  case DHD_ACT_RELU:
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                    break;
+                  case DHD_ACT_SIGMOID:
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __fdividef(1.f, 1.f + __expf(-v[j]));
+                    break;
+                  case DHD_ACT_SOFTPLUS:
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = v[j] > 20.f ? v[j] : __logf(1.f + __expf(v[j]));
+                    break;
+                  default: break;
+                }
+                if (has_gate) {
+                  const float4* g4 = reinterpret_cast<const float4*>(s_gate + cb * 32);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) {
+                    const float4 g = g4[j];
+                    v[4 * j] *= g.x; v[4 * j + 1] *= g.y; v[4 * j + 2] *= g.z; v[4 * j + 3] *= g.w;
+                  }
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = 0.f;
+              }
+#pragma unroll
+              for (int j = 0; j < 16; ++j) h[half * 16 + j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+            }
+            const uint32_t buf = gstage + (nstore % kBufPerGroup) * kStageBufBytes;
+            if (tid == 0) tma_store_wait_read<kBufPerGroup - 1>();
+            named_bar_sync(gbar, 128);
+            // 64 channels = 128-byte rows, SWIZZLE_128B: 16-byte chunk j of row r sits at j ^ (r & 7)
+            uint4* dst = reinterpret_cast<uint4*>(gen + (buf - base) + row * 128);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dst[j ^ (row & 7)] = q[j];
+            fence_proxy_async_smem();
+            named_bar_sync(gbar, 128);
+            if (tid == 0) {
+              tma_store_4d(&M.o16w[sgi], buf, n0 + wb * 64 - sg.c_lo, x0, y0, img);
+              tma_store_commit();
+            }
+            ++nstore;
+          }
+          continue;
+        }
         // one rolled loop nest: softmax makes three passes over the chunks (max, sum, write), every
         // other activation one; a single inlined copy of `affine` keeps the code small
         float mx = -INFINITY, sum = 0.f, inv = 1.f;
@@ -491,6 +558,7 @@ int conv2_launch(const dhd_conv_desc* d, void* encode, void* stream) {
   for (int s = 0; s < DHD_CONV_MAX_SEGS; ++s) {
     P.seg_b16_tma[s] = 0;
     P.seg_f32_tma[s] = 0;
+    P.seg_b16_wide[s] = 0;
     if (s >= d->n_seg) continue;
     const dhd_conv_seg& sg = d->seg[s];
     const cuuint64_t nch = (cuuint64_t)(sg.c_hi - sg.c_lo);
@@ -517,6 +585,24 @@ int conv2_launch(const dhd_conv_desc* d, void* encode, void* stream) {
                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
       }
       P.seg_b16_tma[s] = ok ? 1 : 0;
+      // single-part bf16-only segments whose channel range starts on a 64-channel boundary of the N tile: wide boxes
+      static const bool wide_ok = [] { const char* v = getenv("DHD_CONV_WIDE_STORE"); return v == nullptr || atoi(v) != 0; }();
+      if (ok && wide_ok && sg.b16_parts == 1 && sg.out_f32 == nullptr && sg.act != DHD_ACT_SOFTMAX && d->mix_x == nullptr &&
+          sg.c_lo % 64 == 0) {
+        cuuint64_t dims[4] = {nch, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
+        cuuint64_t strides[3] = {(cuuint64_t)sg.b16_ld * 2, (cuuint64_t)d->W * sg.b16_ld * 2,
+                                 (cuuint64_t)d->H * d->W * sg.b16_ld * 2};
+        if (sg.b16_sX != 0) {
+          strides[0] = (cuuint64_t)sg.b16_sX * 2;
+          strides[1] = (cuuint64_t)sg.b16_sY * 2;
+          strides[2] = (cuuint64_t)sg.b16_sN * 2;
+        }
+        cuuint32_t box[4] = {64, (cuuint32_t)d->bw, (cuuint32_t)d->bh, 1};   // 128-byte rows
+        void* basep = (char*)sg.out_b16 + (size_t)sg.b16_coff * 2;
+        P.seg_b16_wide[s] = enc(&maps.o16w[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, basep, dims, strides, box, es,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS ? 1 : 0;
+      }
     }
     if (sg.out_f32 != nullptr && sg.f32_sC == 1 && sg.f32_sX % 4 == 0 && sg.f32_sY % 4 == 0 &&
         sg.f32_sN % 4 == 0 && ((uintptr_t)sg.out_f32 & 15) == 0 && sg.act != DHD_ACT_SOFTMAX) {
