@@ -726,9 +726,11 @@ def test_depth_and_height_loss_kernels_match_the_plugin_restatement(cuda_lib):
         assert rel(g[:, :K], z.grad.cpu()) < 5e-3              # bf16 storage of the gradient
 
 
-@pytest.mark.parametrize('stereo,use_dcn,aspp_mid', [(True, False, 96),      # DHD-M / DHD-L depthnet_cfg (DHD-M.py:103-106)
-                                                     (False, True, -1)])     # MGHS_Depth defaults (DCN, ASPP 256)
-def test_depthnet_trainer_loss_and_backward(cuda_lib, stereo, use_dcn, aspp_mid):
+@pytest.mark.parametrize('stereo,use_dcn,aspp_mid,labels', [
+    (True, False, 96, 'random'),        # DHD-M / DHD-L depthnet_cfg (DHD-M.py:103-106)
+    (True, False, 96, 'consistent'),    # same, labels = the network's own argmax on every pixel: a well-conditioned gradient
+    (False, True, -1, 'random')])       # MGHS_Depth defaults (DCN, ASPP 256)
+def test_depthnet_trainer_loss_and_backward(cuda_lib, stereo, use_dcn, aspp_mid, labels):
     """Camera-aware DepthNet (depthnet.py:172-243, 362-415) on the training path: forward + depth loss + backward of both
     SE-gated branches, the context conv, cost_volumn_net (stereo), the first block's 1x1 `downsample` path, ASPP with 96
     mid channels, DCN on / off -- every gradient against torch autograd over the oracle (bf16 straight-through rounding
@@ -758,6 +760,15 @@ def test_depthnet_trainer_loss_and_backward(cuda_lib, stereo, use_dcn, aspp_mid)
     sd = {k: v.clone().requires_grad_(v.dtype.is_floating_point and 'running' not in k) for k, v in net.state_dict().items()}
     y = _shim_oracle_call(DO.depthnet_forward, sd, x, mlp_in, cost_volume=cv)
     probs, ctx = y[:, :Dn].softmax(1), y[:, Dn:]
+    if labels == 'consistent':
+        # Random labels / random-sign upstream gradients make every parameter gradient a sqrt(N)-sized sum of N cancelling
+        # terms, which turns 0.3 % of bf16 rounding into 3-10 % of relative error (the 'random' cases, bound 0.12).  With
+        # ONE coherent objective -- every pixel pushed towards the class the network already prefers, no other gradient
+        # source -- the terms add up and the same kernels must agree with fp32 autograd to a few 1e-3: a wrong mask,
+        # stride or scale anywhere in the chain would show as >= 10 %.
+        label = probs.detach().permute(0, 2, 3, 1).reshape(-1, Dn).argmax(1).int()
+        fg = torch.ones(BN * H * W, dtype=torch.bool)
+        g_depth, g_feat = torch.zeros_like(g_depth), torch.zeros_like(g_feat)
     p2 = probs.permute(0, 2, 3, 1).reshape(-1, Dn)
     onehot = torch.zeros(BN * H * W, Dn + 1)
     onehot[torch.arange(BN * H * W), (label + 1).long()] = 1.0
@@ -785,6 +796,10 @@ def test_depthnet_trainer_loss_and_backward(cuda_lib, stereo, use_dcn, aspp_mid)
     # same bound as the HeightNet trunk it shares: the gradient of this random-label loss is a sum of cancelling terms,
     # so the bf16 rounding of the trunk's activations (0.3 % at the head) grows to 3-10 % (relative L2) eleven layers
     # upstream while the direction stays within cos > 0.99; the layers next to the losses are tight (< 1 %)
+    if labels == 'consistent':
+        depth_side = {k: v for k, v in errs.items() if not k.startswith('context')}      # no gradient reaches the context branch
+        assert max(depth_side.values()) < 2e-2, depth_side
+        return
     assert max(errs.values()) < 0.12, errs
     assert errs['depth_conv.%d.weight' % (len(list(net.depth_conv)) - 1)] < 1e-2 and errs['reduce_conv.0.weight'] < 1e-2
     for name, p in net.named_parameters():
