@@ -749,6 +749,8 @@ def test_depthnet_trainer_loss_and_backward(cuda_lib, stereo, use_dcn, aspp_mid,
     net.load_state_dict(sd0)
     BN, H, W = 6, 16, 44
     x = DO.seeded_tensor((BN, 256, H, W), 15).bfloat16().float()
+    if labels == 'consistent':
+        x = x.abs()                 # non-negative image features (what a ReLU backbone hands over): x (x) dy sums coherently too
     mlp_in = DO.seeded_tensor((1, BN, 27), 16)
     cv = DO.seeded_tensor((BN, Dn, 4 * H, 4 * W), 17).softmax(1).bfloat16().float() if stereo else None
     g = torch.Generator().manual_seed(19)
