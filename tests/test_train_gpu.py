@@ -247,8 +247,8 @@ def test_dropout_mask_kernel(cuda_lib):
     assert torch.allclose(kept, torch.full_like(kept, 1.0 / 0.75), rtol=4e-3)          # bf16 rounding of 4/3
 
 
-@pytest.mark.parametrize('dropout', [0.0, 0.5])
-def test_heightnet_loss_and_backward(cuda_lib, dropout):
+@pytest.mark.parametrize('dropout,objective', [(0.0, 'random'), (0.5, 'random'), (0.0, 'coherent')])
+def test_heightnet_loss_and_backward(cuda_lib, dropout, objective):
     """HeightNet (frozen BN, DCN, ASPP [+ its Dropout(0.5) in training mode], SE gate) + height loss: every gradient
     against autograd over the oracle (which multiplies the ASPP output by the mask the kernel draws)."""
     import projects.mmdet3d_plugin  # noqa: F401
@@ -265,6 +265,8 @@ def test_heightnet_loss_and_backward(cuda_lib, dropout):
     net.load_state_dict(sd0)
     BN, H, W = 6, 16, 44
     x = DO.seeded_tensor((BN, 256, H, W), 5).bfloat16().float()
+    if objective == 'coherent':
+        x = x.abs()
     mlp_in = DO.seeded_tensor((1, BN, 27), 6)
     g = torch.Generator().manual_seed(9)
     label = torch.randint(-1, 65, (BN * H * W,), generator=g).int()
@@ -283,6 +285,11 @@ def test_heightnet_loss_and_backward(cuda_lib, dropout):
         drop_mask = ones.data.float().permute(0, 3, 1, 2).cpu()
     logits = _heightnet_forward_q(sd, x, mlp_in, _q, drop_mask=drop_mask)
     probs = logits.softmax(1).permute(0, 2, 3, 1).reshape(-1, 65)
+    if objective == 'coherent':
+        # every pixel pushed towards the bin the network already prefers: a well-conditioned gradient (no cancellation),
+        # so bf16 rounding stays at rounding level and a wrong mask / stride / scale would stand out (see test_unet_backward)
+        label = probs.detach().argmax(1).int()
+        fg = torch.ones(BN * H * W, dtype=torch.bool)
     onehot = torch.zeros(BN * H * W, 66)
     onehot[torch.arange(BN * H * W), (label + 1).long()] = 1.0
     onehot = onehot[:, 1:]
@@ -314,6 +321,9 @@ def test_heightnet_loss_and_backward(cuda_lib, dropout):
     # Tolerance: the offset gradient of the DCN is a spatial derivative of the ASPP output, so the 0.4 % bf16
     # difference between the two forward passes shows up ~10x amplified in it (and in everything upstream);
     # the sampling backward itself is pinned exactly by test_dcn_sampling_backward_unit below.
+    if objective == 'coherent':
+        assert max(errs.values()) < 3e-2, errs
+        return
     assert max(errs.values()) < 0.12, errs
     assert max(v for k, v in errs.items() if k.startswith(('depth_conv.5', 'depth_conv.4.weight'))) < 1e-2
     for name, p in net.named_parameters():
@@ -425,8 +435,13 @@ def _grad_errors(module, sd):
     return errs
 
 
-def test_unet_backward(cuda_lib):
-    """UNet (frozen BN) incl. the odd-sized level (5 -> 2 -> 4 padded to 5): gradients vs autograd over the oracle."""
+@pytest.mark.parametrize('objective', ['random', 'coherent'])
+def test_unet_backward(cuda_lib, objective):
+    """UNet (frozen BN) incl. the odd-sized level (5 -> 2 -> 4 padded to 5): gradients vs autograd over the oracle.
+    objective='random': random-sign upstream gradient (every parameter gradient is a sum of cancelling terms: bf16
+    rounding shows up amplified, bound 0.12 + direction); 'coherent': L = 0.005 * sum(y^2) on non-negative inputs -- the
+    terms add up, and the same kernels must then agree with fp32 autograd to rounding level (bound 3e-2): what tells
+    rounding from a bug."""
     import projects.mmdet3d_plugin  # noqa: F401
     from dhd_b200 import dense as D
     from dhd_b200.train import UNetTrainer
@@ -437,9 +452,13 @@ def test_unet_backward(cuda_lib):
     B, H, W = 1, 40, 56
     x = DO.seeded_tensor((B, 256, H, W), 34).bfloat16().float()
     gout = (DO.seeded_tensor((B, 64, H, W), 36) * 0.01).bfloat16().float()
+    if objective == 'coherent':
+        x = x.abs()
     sd = {k: v.clone().requires_grad_(v.dtype.is_floating_point and 'running' not in k) for k, v in net.state_dict().items()}
     xr = x.clone().requires_grad_()
     y = _shim_oracle_call(DO.unet_forward, sd, xr)
+    if objective == 'coherent':
+        gout = (0.01 * y.detach()).bfloat16().float()
     (y * gout).sum().backward()
     net = net.cuda()
     for p in net.parameters():
@@ -454,7 +473,7 @@ def test_unet_backward(cuda_lib):
     print('relative L2 gradient errors:', {k: round(v, 4) for k, v in errs.items()})
     # 23 convolutions deep with bf16 activations on one side only: rounding noise plus the occasional ReLU mask /
     # max-pool argmax decided differently; every piece is pinned exactly by test_encoder_backward_primitives_unit
-    assert max(errs.values()) < 0.12, errs
+    assert max(errs.values()) < (0.12 if objective == 'random' else 3e-2), errs
     for name, p in net.named_parameters():
         if name in errs:
             assert cos(p.grad, sd[name].grad) > 0.99, name
@@ -530,8 +549,10 @@ def test_encoder_backward_primitives_unit(cuda_lib):
     assert rel(dxf.permute(0, 3, 1, 2), xr.grad) < 1e-5
 
 
-def test_bev_encoder_backward(cuda_lib):
-    """CustomResNet + FPN_LSS (frozen BN): gradients of both modules and dL/dx vs autograd over the oracle."""
+@pytest.mark.parametrize('objective', ['random', 'coherent'])
+def test_bev_encoder_backward(cuda_lib, objective):
+    """CustomResNet + FPN_LSS (frozen BN): gradients of both modules and dL/dx vs autograd over the oracle (objective:
+    see test_unet_backward)."""
     import projects.mmdet3d_plugin  # noqa: F401
     from dhd_b200 import dense as D
     from dhd_b200.train import CustomResNetTrainer, FPNLSSTrainer
@@ -544,10 +565,14 @@ def test_bev_encoder_backward(cuda_lib):
     B, H, W = 1, 40, 56
     x = DO.seeded_tensor((B, 64, H, W), 35).bfloat16().float()
     gout = (DO.seeded_tensor((B, 256, H, W), 37) * 0.01).bfloat16().float()
+    if objective == 'coherent':
+        x = x.abs()
     mk = lambda m: {k: v.clone().requires_grad_(v.dtype.is_floating_point and 'running' not in k) for k, v in m.state_dict().items()}
     sdr, sdf = mk(r), mk(f)
     xr = x.clone().requires_grad_()
     y = _shim_oracle_call(lambda: DO.fpn_lss_forward(sdf, DO.custom_resnet_forward(sdr, xr)))
+    if objective == 'coherent':
+        gout = (0.01 * y.detach()).bfloat16().float()
     (y * gout).sum().backward()
     r, f = r.cuda(), f.cuda()
     for p in list(r.parameters()) + list(f.parameters()):
@@ -562,7 +587,7 @@ def test_bev_encoder_backward(cuda_lib):
     errs.update({'resnet.' + k: v for k, v in _grad_errors(r, sdr).items()})
     errs['x'] = rel(dx.float(), xr.grad)
     print('relative L2 gradient errors:', {k: round(v, 4) for k, v in errs.items()})
-    assert max(errs.values()) < 0.12, errs
+    assert max(errs.values()) < (0.12 if objective == 'random' else 3e-2), errs
 
 
 @pytest.mark.parametrize('bn', ['frozen', 'batch'])
