@@ -87,6 +87,8 @@ _SIGNATURES = {
     'dhd_linear_rows': (ctypes.c_int, [_P, _I, _I, _P, _P, _I, _I, _P, _P, _I, _P, _P]),
     'dhd_gate_channels': (ctypes.c_int, [_P, _I, _I, _I, _P, _P] + [_I] * 4 + [_P, _P]),
     'dhd_sfa_mix': (ctypes.c_int, [_P] + [_I] * 7 + [_P, _P, _P] + [_I] * 4 + [_P]),
+    'dhd_sfa_blend_b16': (ctypes.c_int, [_P] + [_I] * 5 + [_P, _P, _I, _I, _P, _I, _I, _P]),
+    'dhd_sfa_fold_gate': (ctypes.c_int, [_P, _P, _I, _I, _I, _P, _P]),
     'dhd_stereo_cost_volume': (ctypes.c_int, [_P, _P]),
     'dhd_nchw_to_nhwc': (ctypes.c_int, [_P, _I, _I, _I, _P, _I, _P]),
     'dhd_dcn_im2col': (ctypes.c_int, [_P] + [_I] * 8 + [_P] + [_I] * 5 + [_P] + [_I] * 3 + [_P]),

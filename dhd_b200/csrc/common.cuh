@@ -118,4 +118,13 @@ inline int sm_count() {
   return n;
 }
 
+// 16-byte streaming load through the read-only path without polluting L1
+__device__ __forceinline__ uint4 ld_nc_u4(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p));
+  return v;
+}
+
 }  // namespace dhd

@@ -91,6 +91,11 @@ extern "C" int dhd_conv2d_fwd(const dhd_conv_desc* d, void* stream) {
     DHD_REQUIRE(d->Cout % 32 == 0 && ((uintptr_t)d->residual & 15) == 0 && d->res_sN % 4 == 0 &&
                     d->res_sY % 4 == 0 && d->res_sX % 4 == 0,
                 "residual needs Cout % 32 == 0 and 16-byte aligned rows");
+  if (d->res_b16 != nullptr)
+    DHD_REQUIRE(d->Cout % 32 == 0 && ((uintptr_t)d->res_b16 & 15) == 0 && d->res_b16_ld % 8 == 0 &&
+                    d->res_b16_coff % 8 == 0 && d->residual == nullptr && (d->stride == 0 || d->stride == 1),
+                "bf16 residual needs Cout % 32 == 0, 16-byte aligned rows, stride 1 and no fp32 residual");
+  DHD_REQUIRE(d->w_image_rows == 0 || d->w_image_rows >= d->Cout, "w_image_rows must be 0 or >= Cout");
   DHD_REQUIRE(d->stride == 0 || d->stride == 1 || d->stride == 2, "stride must be 1 or 2");
   if (d->stride == 2) {
     DHD_REQUIRE(d->in_H > 0 && d->in_W > 0 && d->H <= (d->in_H + 1) / 2 && d->W <= (d->in_W + 1) / 2,

@@ -25,6 +25,7 @@ constexpr int kK2 = 64;           // bf16 per smem row (128 B swizzle span)
 // G groups of four epilogue warps (G = 2 or 4): group g owns the 32-column chunks with chunk % G == g
 constexpr uint32_t kA2Bytes = kM2 * kK2 * 2;
 constexpr uint32_t kStageBufBytes = 16384;   // one TMA-store staging tile: 128 rows x 128 B
+constexpr int kMaxConvBatch = DHD_CONV_MAX_BATCH;
 
 template <int NT>
 struct Cfg2 {
@@ -50,6 +51,20 @@ struct Conv2Maps {
   CUtensorMap o32[DHD_CONV_MAX_SEGS];
 };
 
+// One launch = NP independent convolutions ("problems") with the same N-tile class: the persistent CTAs walk the
+// concatenated tile list (problem 0's tiles, then problem 1's, ...).  Layers that read the same activation and are
+// each too small to fill the GPU (the four ASPP branches, the groups of the deformable convolution, depth_net next to
+// HeightNet's first convolution: 132 tiles for 148 SMs, one tile per CTA, nothing overlaps) become one launch whose
+// CTAs hold 3-4 tiles each, so tile i's epilogue runs under tile i+1's main loop and the prologue is paid once.
+// Everything sits in kernel parameter space (<= 32 KB since CUDA 12.1), indexed by the problem id.
+template <int NP>
+struct ConvBatch {
+  Conv2Maps M[NP];
+  Conv2Params P[NP];
+  int n;                 // problems in use
+  int tile_end[NP];      // running total of tiles
+};
+
 __device__ __forceinline__ float act2(float v, int act) {
   switch (act) {
     case DHD_ACT_RELU: return fmaxf(v, 0.f);
@@ -66,14 +81,14 @@ __device__ __forceinline__ bool tap_dead2(const dhd_conv_desc& d, int t, int x0,
   return xs >= iw || xs + d.bw * st <= 0 || ys >= ih || ys + d.bh * st <= 0;
 }
 
-template <int NT, int G>
+template <int NT, int G, int NP>
 __global__ void __launch_bounds__((4 * G + 2) * 32, 1)
-conv_igemm2_kernel(const __grid_constant__ Conv2Maps M, const __grid_constant__ Conv2Params P) {
+conv_igemm2_kernel(const __grid_constant__ ConvBatch<NP> B) {
   using C = Cfg2<NT>;
   constexpr int kEpiWarps = 4 * G;
   constexpr int kBufPerGroup = 4 / G;          // staging tiles per group: 4 x 16 KB in total
   extern __shared__ uint8_t smem_raw[];
-  const dhd_conv_desc& d = P.d;
+  const int total_tiles = B.tile_end[B.n - 1];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   const uint32_t stagebuf = base + C::kStages * C::kStageBytes;            // 2 groups x 2 x 16 KB, 1024-aligned
@@ -90,12 +105,11 @@ conv_igemm2_kernel(const __grid_constant__ Conv2Maps M, const __grid_constant__ 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + (bar_base - base) + 8u * (2 * C::kStages + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kchunks = d.Cin / kK2;
   constexpr uint32_t kIdesc = umma_instr_desc_bf16(kM2, NT);
 
   if (warp == kEpiWarps && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&M.a) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&M.b) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&B.M[0].a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&B.M[0].b) : "memory");
     for (int s = 0; s < C::kStages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -117,15 +131,24 @@ conv_igemm2_kernel(const __grid_constant__ Conv2Maps M, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  auto decode = [&](int tile, int& img, int& x0, int& y0, int& n0) {
+  // global tile index -> problem id (and the tile index inside that problem)
+  auto problem_of = [&](int& tile) {
+    int p = 0;
+    if (NP > 1) {
+      while (tile >= B.tile_end[p]) ++p;
+      if (p > 0) tile -= B.tile_end[p - 1];
+    }
+    return p;
+  };
+  auto decode = [&](const Conv2Params& P, int tile, int& img, int& x0, int& y0, int& n0) {
     const int nt = tile % P.n_tiles;
     int mt = tile / P.n_tiles;
     const int tx = mt % P.tiles_w;
     mt /= P.tiles_w;
     const int ty = mt % P.tiles_h;
     img = mt / P.tiles_h;
-    x0 = tx * d.bw;
-    y0 = ty * d.bh;
+    x0 = tx * P.d.bw;
+    y0 = ty * P.d.bh;
     n0 = nt * NT;
   };
 
@@ -133,10 +156,16 @@ conv_igemm2_kernel(const __grid_constant__ Conv2Maps M, const __grid_constant__ 
     // ===================================================== TMA producer
     if (lane == 0) {
       int it = 0;
-      const int in_stride = d.stride > 1 ? d.stride : 1;     // the tensor map strides the box (elementStrides)
-      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+      for (int gtile = blockIdx.x; gtile < total_tiles; gtile += gridDim.x) {
+        int tile = gtile;
+        const int pid = problem_of(tile);
+        const Conv2Params& P = B.P[pid];
+        const Conv2Maps& M = B.M[pid];
+        const dhd_conv_desc& d = P.d;
+        const int kchunks = d.Cin / kK2;
+        const int in_stride = d.stride > 1 ? d.stride : 1;     // the tensor map strides the box (elementStrides)
         int img, x0, y0, n0;
-        decode(tile, img, x0, y0, n0);
+        decode(P, tile, img, x0, y0, n0);
         for (int t = 0; t < d.taps; ++t) {
           if (tap_dead2(d, t, x0, y0)) continue;
           for (int kc = 0; kc < kchunks; ++kc) {
@@ -148,7 +177,7 @@ conv_igemm2_kernel(const __grid_constant__ Conv2Maps M, const __grid_constant__ 
               mbar_expect_tx(full_bar(s), C::kStageBytes);
               tma_load_4d(sa, &M.a, full_bar(s), d.in_coff + d.term_a[e] * d.in_part_stride + kc * kK2,
                           x0 * in_stride + d.tap_dx[t], y0 * in_stride + d.tap_dy[t], img);
-              tma_load_2d(sb, &M.b, full_bar(s), (t * d.w_parts + d.term_b[e]) * d.Cin + kc * kK2, n0);
+              tma_load_2d(sb, &M.b, full_bar(s), (t * d.w_parts + d.term_b[e]) * d.Cin + kc * kK2, n0 + img * d.w_image_rows);
             }
           }
         }
@@ -158,9 +187,14 @@ conv_igemm2_kernel(const __grid_constant__ Conv2Maps M, const __grid_constant__ 
     // ===================================================== MMA issuer
     if (lane == 0) {
       int it = 0, lt = 0;
-      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++lt) {
+      for (int gtile = blockIdx.x; gtile < total_tiles; gtile += gridDim.x, ++lt) {
+        int tile = gtile;
+        const int pid = problem_of(tile);
+        const Conv2Params& P = B.P[pid];
+        const dhd_conv_desc& d = P.d;
+        const int kchunks = d.Cin / kK2;
         int img, x0, y0, n0;
-        decode(tile, img, x0, y0, n0);
+        decode(P, tile, img, x0, y0, n0);
         const int as = lt & 1;
         mbar_wait(tempty_bar(as), ((lt >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
         tc_fence_after();
@@ -203,9 +237,14 @@ conv_igemm2_kernel(const __grid_constant__ Conv2Maps M, const __grid_constant__ 
     const int row = tid;
     int lt = 0;
     uint32_t nstore = 0;                    // TMA stores issued so far by this group (selects the staging buffer)
-    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++lt) {
+    for (int gtile = blockIdx.x; gtile < total_tiles; gtile += gridDim.x, ++lt) {
+      int tile = gtile;
+      const int pid = problem_of(tile);
+      const Conv2Params& P = B.P[pid];
+      const Conv2Maps& M = B.M[pid];
+      const dhd_conv_desc& d = P.d;
       int img, x0, y0, n0;
-      decode(tile, img, x0, y0, n0);
+      decode(P, tile, img, x0, y0, n0);
       const int as = lt & 1;
       named_bar_sync(5, 128 * G);           // everyone is done with the previous tile's vectors
       for (int c = threadIdx.x; c < NT; c += 128 * G) {
@@ -231,6 +270,10 @@ conv_igemm2_kernel(const __grid_constant__ Conv2Maps M, const __grid_constant__ 
       const float* res = nullptr;
       if (d.residual != nullptr && valid)
         res = d.residual + (size_t)img * d.res_sN + (size_t)py * d.res_sY + (size_t)px * d.res_sX + n0;
+      const __nv_bfloat16* resb = nullptr;
+      if (d.res_b16 != nullptr && valid)
+        resb = reinterpret_cast<const __nv_bfloat16*>(d.res_b16) +
+               ((size_t)img * d.H * d.W + (size_t)py * d.W + px) * d.res_b16_ld + d.res_b16_coff + n0;
       const bool has_gate = d.img_gate != nullptr;
 
 #pragma unroll 1
@@ -260,6 +303,19 @@ conv_igemm2_kernel(const __grid_constant__ Conv2Maps M, const __grid_constant__ 
             for (int j = 0; j < 8; ++j) {     // host guarantees 16-byte alignment and Cout % 32 == 0
               const float4 q = __ldg(reinterpret_cast<const float4*>(rp) + j);
               v[4 * j] += q.x; v[4 * j + 1] += q.y; v[4 * j + 2] += q.z; v[4 * j + 3] += q.w;
+            }
+          }
+          if (resb != nullptr) {
+            const uint4* rp = reinterpret_cast<const uint4*>(resb + cb * 32);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {     // host guarantees 16-byte alignment and Cout % 32 == 0
+              const uint4 q = __ldg(rp + j);
+              const __nv_bfloat162* hq = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                v[8 * j + 2 * i] += __low2float(hq[i]);
+                v[8 * j + 2 * i + 1] += __high2float(hq[i]);
+              }
             }
           }
           if (n0 + cb * 32 < c_lo || n0 + cb * 32 + 32 > c_hi) {
@@ -508,29 +564,71 @@ typedef CUresult (*EncodeTiledFn2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
                                    CUtensorMapFloatOOBfill);
 
-template <int NT, int G>
-static int launch2(const Conv2Maps& maps, const Conv2Params& P, cudaStream_t st) {
+template <int NT, int G, int NP>
+static int launch2(const ConvBatch<NP>& batch, cudaStream_t st) {
   using C = Cfg2<NT>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_igemm2_kernel<NT, G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_igemm2_kernel<NT, G, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)C::kSmem);
     if (e != cudaSuccess) return fail((int)e, "%s: %ld", "cudaFuncSetAttribute(conv_igemm2)", (long)e);
     attr_set = true;
   }
-  const int grid = min(P.total_tiles, sm_count());
-  conv_igemm2_kernel<NT, G><<<grid, (4 * G + 2) * 32, C::kSmem, st>>>(maps, P);
+  const int grid = min(batch.tile_end[batch.n - 1], sm_count());
+  conv_igemm2_kernel<NT, G, NP><<<grid, (4 * G + 2) * 32, C::kSmem, st>>>(batch);
   DHD_CUDA_LAUNCH_CHECK("conv_igemm2");
   return DHD_OK;
 }
 
+static int epi_groups() {
+  static const int groups = [] {
+    const char* v = getenv("DHD_CONV_EPI_GROUPS");
+    return v != nullptr && atoi(v) == 4 ? 4 : 2;
+  }();
+  return groups;
+}
+
+static int conv2_fill(const dhd_conv_desc* d, EncodeTiledFn2 enc, Conv2Maps& maps, Conv2Params& P, int NT);
+
 // called by dhd_conv2d_fwd (conv_igemm.cu) after argument validation
 int conv2_launch(const dhd_conv_desc* d, void* encode, void* stream) {
-  EncodeTiledFn2 enc = (EncodeTiledFn2)encode;
-  Conv2Maps maps;
-  Conv2Params P;
-  P.d = *d;
   const int NT = d->Cout > 128 ? 256 : 128;
+  ConvBatch<1> batch;
+  int rc = conv2_fill(d, (EncodeTiledFn2)encode, batch.M[0], batch.P[0], NT);
+  if (rc != DHD_OK) return rc;
+  batch.n = 1;
+  batch.tile_end[0] = batch.P[0].total_tiles;
+  if (epi_groups() == 4) {
+    if (NT == 256) return launch2<256, 4, 1>(batch, (cudaStream_t)stream);
+    return launch2<128, 4, 1>(batch, (cudaStream_t)stream);
+  }
+  if (NT == 256) return launch2<256, 2, 1>(batch, (cudaStream_t)stream);
+  return launch2<128, 2, 1>(batch, (cudaStream_t)stream);
+}
+
+// dhd_conv2d_fwd_batch: n <= kMaxConvBatch validated descriptors in one launch.  The N tile is 256 wide when any
+// problem has Cout > 128 (a narrower problem then wastes tensor-core columns, not time that matters at these sizes).
+int conv2_launch_batch(const dhd_conv_desc* const* descs, int n, void* encode, void* stream) {
+  int NT = 128;
+  for (int i = 0; i < n; ++i)
+    if (descs[i]->Cout > 128) NT = 256;
+  ConvBatch<kMaxConvBatch> batch;
+  int total = 0;
+  for (int i = 0; i < kMaxConvBatch; ++i) {
+    if (i < n) {
+      int rc = conv2_fill(descs[i], (EncodeTiledFn2)encode, batch.M[i], batch.P[i], NT);
+      if (rc != DHD_OK) return rc;
+      total += batch.P[i].total_tiles;
+    }
+    batch.tile_end[i] = total;
+  }
+  batch.n = n;
+  if (NT == 256) return launch2<256, 2, kMaxConvBatch>(batch, (cudaStream_t)stream);
+  return launch2<128, 2, kMaxConvBatch>(batch, (cudaStream_t)stream);
+}
+
+static int conv2_fill(const dhd_conv_desc* d, EncodeTiledFn2 enc, Conv2Maps& maps, Conv2Params& P, int NT) {
+  P.d = *d;
   {
     const int st = d->stride > 1 ? d->stride : 1;
     const cuuint64_t iw = d->in_W > 0 ? d->in_W : d->W, ih = d->in_H > 0 ? d->in_H : d->H;   // input grid (>= output grid)
@@ -546,7 +644,8 @@ int conv2_launch(const dhd_conv_desc* d, void* encode, void* stream) {
   }
   {
     const cuuint64_t ktot = (cuuint64_t)d->taps * d->w_parts * d->Cin;
-    cuuint64_t dims[2] = {ktot, (cuuint64_t)d->Cout};
+    const cuuint64_t wrows = d->w_image_rows > 0 ? (cuuint64_t)d->w_image_rows * d->N : (cuuint64_t)d->Cout;
+    cuuint64_t dims[2] = {ktot, wrows};
     cuuint64_t strides[1] = {ktot * 2};
     cuuint32_t box[2] = {(cuuint32_t)kK2, (cuuint32_t)NT};
     cuuint32_t es[2] = {1, 1};
@@ -619,16 +718,7 @@ int conv2_launch(const dhd_conv_desc* d, void* encode, void* stream) {
   P.tiles_h = (d->H + d->bh - 1) / d->bh;
   P.n_tiles = (d->Cout + NT - 1) / NT;
   P.total_tiles = P.tiles_w * P.tiles_h * d->N * P.n_tiles;
-  static const int groups = [] {
-    const char* v = getenv("DHD_CONV_EPI_GROUPS");
-    return v != nullptr && atoi(v) == 4 ? 4 : 2;
-  }();
-  if (groups == 4) {
-    if (NT == 256) return launch2<256, 4>(maps, P, (cudaStream_t)stream);
-    return launch2<128, 4>(maps, P, (cudaStream_t)stream);
-  }
-  if (NT == 256) return launch2<256, 2>(maps, P, (cudaStream_t)stream);
-  return launch2<128, 2>(maps, P, (cudaStream_t)stream);
+  return DHD_OK;
 }
 
 }  // namespace dhd

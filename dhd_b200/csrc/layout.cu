@@ -276,6 +276,61 @@ sfa_mix8_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int x_coff, int x
   store_parts8(out + (size_t)pix * o_ld + o_coff + c, r, o_parts, o_ps);
 }
 
+// bf16 speed mode of the second SFA blend: the spatial gate a2 arrives as a bf16 activation (written by the gate
+// convolution's 128-byte-row TMA stores) instead of an fp32 tensor -- 16 B of gate per 8 channels instead of 32
+__global__ void __launch_bounds__(256)
+sfa_blend_b16_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int x_coff, int C, long npix_total, int HW,
+                     const float* __restrict__ a1, const __nv_bfloat16* __restrict__ a2, int a2_ld, int a2_coff,
+                     __nv_bfloat16* __restrict__ out, int o_ld, int o_coff) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int cg = C / 8;
+  if (i >= npix_total * cg) return;
+  int c;
+  const long pix = fast_div(i, cg, &c);
+  c *= 8;
+  const int n = (int)fast_div(pix, HW);
+  const uint4 qb = ld_nc_u4(x + (size_t)pix * x_ld + x_coff + c);
+  const uint4 qv = ld_nc_u4(x + (size_t)pix * x_ld + x_coff + C + c);
+  const uint4 qg = ld_nc_u4(a2 + (size_t)pix * a2_ld + a2_coff + c);
+  const float4* g1p = reinterpret_cast<const float4*>(a1 + (size_t)n * C + c);
+  const float4 ga = __ldg(g1p), gb = __ldg(g1p + 1);
+  const float g1[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+  const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&qb);
+  const __nv_bfloat162* hv = reinterpret_cast<const __nv_bfloat162*>(&qv);
+  const __nv_bfloat162* hg = reinterpret_cast<const __nv_bfloat162*>(&qg);
+  uint4 qo;
+  __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&qo);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float r[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const float bev = e == 0 ? __low2float(hb[j]) : __high2float(hb[j]);
+      const float vox = e == 0 ? __low2float(hv[j]) : __high2float(hv[j]);
+      const float g2 = e == 0 ? __low2float(hg[j]) : __high2float(hg[j]);
+      const float b1 = __fmul_rn(g1[2 * j + e], bev);
+      const float v1 = __fmul_rn(__fsub_rn(1.f, g1[2 * j + e]), vox);
+      r[e] = __fadd_rn(__fmul_rn(g2, b1), __fmul_rn(__fsub_rn(1.f, g2), v1));
+    }
+    ho[j] = __floats2bfloat162_rn(r[0], r[1]);
+  }
+  *reinterpret_cast<uint4*>(out + (size_t)pix * o_ld + o_coff + c) = qo;
+}
+
+// SFA's channel gate folded into the weights of the 1x1 convolution that consumes the gated blend (mix.py:41-50):
+// wq[n][co][c] = w[co][c] * a1[n][c], wq[n][co][C + c] = w[co][c] * (1 - a1[n][c]), bf16
+__global__ void __launch_bounds__(256)
+sfa_fold_gate_kernel(const float* __restrict__ w, const float* __restrict__ a1, int N, int Cout, int C,
+                     __nv_bfloat16* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * Cout * C) return;
+  const int c = i % C, co = (i / C) % Cout, n = i / (C * Cout);
+  const float g = __ldg(a1 + (size_t)n * C + c), wv = __ldg(w + (size_t)co * C + c);
+  __nv_bfloat16* o = out + ((size_t)n * Cout + co) * 2 * C;
+  o[c] = __float2bfloat16_rn(__fmul_rn(wv, g));
+  o[C + c] = __float2bfloat16_rn(__fmul_rn(wv, __fsub_rn(1.f, g)));
+}
+
 // deformable im2col, one warp per (pixel, tap), 8 channels per lane (C multiple of 256 per pass)
 __global__ void __launch_bounds__(256)
 dcn_im2col8_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int x_coff, int x_ps, int x_parts, int C,
@@ -903,6 +958,32 @@ extern "C" int dhd_sfa_mix(const void* x, int x_ld, int x_coff, int x_part_strid
       (const __nv_bfloat16*)x, x_ld, x_coff, x_part_stride, x_parts, C, (long)N * HW, HW, a1, a2,
       (__nv_bfloat16*)out, o_ld, o_coff, o_part_stride, o_parts);
   DHD_CUDA_LAUNCH_CHECK("sfa_mix");
+  return DHD_OK;
+}
+
+extern "C" int dhd_sfa_blend_b16(const void* x, int x_ld, int x_coff, int C, int N, int HW, const float* a1,
+                                 const void* a2, int a2_ld, int a2_coff, void* out, int o_ld, int o_coff,
+                                 void* stream) {
+  DHD_REQUIRE(x && a1 && a2 && out, "null pointer");
+  DHD_REQUIRE(C > 0 && C % 8 == 0 && N > 0 && HW > 0, "C must be a positive multiple of 8");
+  DHD_REQUIRE(x_ld % 8 == 0 && x_coff % 8 == 0 && a2_ld % 8 == 0 && a2_coff % 8 == 0 && o_ld % 8 == 0 && o_coff % 8 == 0 &&
+                  ((uintptr_t)x & 15) == 0 && ((uintptr_t)a2 & 15) == 0 && ((uintptr_t)out & 15) == 0 &&
+                  ((uintptr_t)a1 & 15) == 0, "16-byte aligned rows required");
+  const long total8 = (long)N * HW * (C / 8);
+  DHD_REQUIRE(total8 < (1L << 31) * 256, "tensor too large");
+  sfa_blend_b16_kernel<<<(int)((total8 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x, x_ld, x_coff, C, (long)N * HW, HW, a1, (const __nv_bfloat16*)a2, a2_ld, a2_coff,
+      (__nv_bfloat16*)out, o_ld, o_coff);
+  DHD_CUDA_LAUNCH_CHECK("sfa_blend_b16");
+  return DHD_OK;
+}
+
+extern "C" int dhd_sfa_fold_gate(const float* w, const float* a1, int N, int Cout, int C, void* out, void* stream) {
+  DHD_REQUIRE(w && a1 && out, "null pointer");
+  DHD_REQUIRE(N > 0 && Cout > 0 && C > 0 && (long)N * Cout * C < (1L << 31), "bad shape");
+  const int total = N * Cout * C;
+  sfa_fold_gate_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, a1, N, Cout, C, (__nv_bfloat16*)out);
+  DHD_CUDA_LAUNCH_CHECK("sfa_fold_gate");
   return DHD_OK;
 }
 

@@ -56,6 +56,8 @@ class ConvDesc(ctypes.Structure):
         ('stride', ctypes.c_int32), ('in_H', ctypes.c_int32), ('in_W', ctypes.c_int32),
         ('mix_x', ctypes.c_void_p), ('mix_ld', ctypes.c_int32), ('mix_coff', ctypes.c_int32),
         ('mix_parts', ctypes.c_int32), ('mix_part_stride', ctypes.c_int32), ('mix_a1', ctypes.c_void_p),
+        ('w_image_rows', ctypes.c_int32), ('res_b16_ld', ctypes.c_int32), ('res_b16_coff', ctypes.c_int32),
+        ('res_b16', ctypes.c_void_p),
     ]
 
 
@@ -210,12 +212,14 @@ def tile_box(H, W):
 
 def conv2d(x, weight, Cout, ksize=1, dilation=1, precision='fp32', scale=None, bias=None,
            img_bias=None, img_gate=None, residual=None, segs=None, stride=1, sfa_mix=None, taps=None,
-           out_hw=None):
+           out_hw=None, residual_act=None, image_weights=False):
     """One fused convolution.  x: Act; weight: pack_weight() result with PRECISIONS[precision]
     parts; segs: list of dicts {c_lo, c_hi, act, out_f32 (tensor, strides (sN,sY,sX,sC)),
     out_act (Act or Act.slice), out_view (sN, sY, sX, offset): pixel strides / start offset in bf16
     elements when out_act is written as a strided view (ConvTranspose2d phases)}.  stride=2: 3x3 / pad 1
-    down-sampling convolution, output ceil(H/2) x ceil(W/2).  Outputs are written in place."""
+    down-sampling convolution, output ceil(H/2) x ceil(W/2).  Outputs are written in place.
+    residual_act: single-part bf16 Act added before the activation (bf16 speed mode's identity path);
+    image_weights=True: `weight` is [N*Cout][taps][parts][Cin], image n convolves with its own Cout rows."""
     parts, terms = PRECISIONS[precision]
     if x.parts < parts or weight.shape[2] != parts:
         raise ValueError('activation has %d parts, weight %d, precision %s needs %d' %
@@ -231,7 +235,11 @@ def conv2d(x, weight, Cout, ksize=1, dilation=1, precision='fp32', scale=None, b
     d.Cin, d.Cout = x.C, Cout
     tap_list = taps                          # explicit input offsets [(dy, dx), ...] (must contain (0, 0))
     taps = ksize * ksize if tap_list is None else len(tap_list)
-    if weight.shape[0] != Cout or weight.shape[1] != taps or weight.shape[3] != x.C:
+    if image_weights:
+        if weight.shape[0] != Cout * x.N:
+            raise ValueError('per-image weights need N*Cout = %d rows, got %d' % (Cout * x.N, weight.shape[0]))
+        d.w_image_rows = Cout
+    if weight.shape[0] != (Cout * x.N if image_weights else Cout) or weight.shape[1] != taps or weight.shape[3] != x.C:
         raise ValueError('weight shape %s does not match Cout=%d taps=%d Cin=%d' %
                          (tuple(weight.shape), Cout, taps, x.C))
     d.taps = taps
@@ -262,6 +270,12 @@ def conv2d(x, weight, Cout, ksize=1, dilation=1, precision='fp32', scale=None, b
         d.residual = rt.data_ptr()
         d.res_sN, d.res_sY, d.res_sX = sN, sY, sX
         keep.append(rt)
+    if residual_act is not None:
+        ra = residual_act
+        if (ra.N, ra.H, ra.W) != (x.N, oH, oW) or ra.C < Cout or residual is not None:
+            raise ValueError('residual_act does not match the layer (or an fp32 residual is also given)')
+        d.res_b16, d.res_b16_ld, d.res_b16_coff = ra.data.data_ptr(), ra.ld, ra.coff
+        keep.append(ra.data)
     if sfa_mix is not None:                  # (x Act [bev | vox], a1 (N, Cout) fp32): SFA blend in the epilogue
         mx, a1 = sfa_mix
         if (mx.N, mx.H, mx.W) != (x.N, oH, oW) or mx.C < 2 * Cout or a1.shape != (x.N, Cout) or a1.dtype != torch.float32:

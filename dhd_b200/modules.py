@@ -171,16 +171,21 @@ class HeightNetEngine:
         h = linear_rows(h, self.se_r_w, self.se_r_b, 'relu')
         return linear_rows(h, self.se_e_w, self.se_e_b, 'sigmoid')
 
-    def __call__(self, x, mlp_input, softmax=True, hook=None):
+    def __call__(self, x, mlp_input, softmax=True, hook=None, gate=None):
         """x: Act (B*N, 256, fH, fW); returns height (B*N, H, fH, fW) fp32 NCHW (softmax-ed
         unless softmax=False, which gives the raw HeightNet output the reference returns).
         hook: optional callable run once after the ASPP branches are enqueued (the pipeline forks the
-        geometry / binning kernels onto a side stream there, so they overlap the tail of this network)."""
+        geometry / binning kernels onto a side stream there, so they overlap the tail of this network).
+        gate: the result of self.gate(mlp_input) when the caller computed it ahead (on another stream)."""
         N, H, W, C, P, dev = x.N, x.H, x.W, self.C, self.parts, x.data.device
         new = lambda c: D.Act.empty(N, H, W, c, P, dev)
         nhwc = D.nhwc_strides(C, H, W)
-        gate = self.gate(mlp_input)
+        if gate is None:
+            gate = self.gate(mlp_input)
         h = new(C)
+        if P == 1 and os.environ.get('DHD_BF16_RESIDUAL', '1') != '0':
+            self.reduce(x, [dict(act='relu', out_act=h)], img_gate=gate)
+            return self.trunk(h, None, softmax, hook)
         h32 = torch.empty(N, H, W, C, device=dev)
         self.reduce(x, [dict(act='relu', out_act=h, out_f32=(h32, nhwc))], img_gate=gate)
         return self.trunk(h, h32, softmax, hook)
@@ -190,8 +195,21 @@ class HeightNetEngine:
         N, H, W, C, P, dev = h.N, h.H, h.W, self.C, self.parts, h.data.device
         new = lambda c: D.Act.empty(N, H, W, c, P, dev)
         nhwc = D.nhwc_strides(C, H, W)
+        lean = P == 1 and os.environ.get('DHD_BF16_RESIDUAL', '1') != '0'
         for c1, c2, ds in self.blocks:
             t = new(C)
+            if lean:
+                # bf16 speed mode: the identity path is the bf16 activation itself (no fp32 copy written by one block
+                # and re-read by the next: 3 x 34 MB per block at DHD-S B=4) and every store is a 128-byte row
+                idn = h
+                if ds is not None:
+                    idn = new(C)
+                    ds(h, [dict(out_act=idn)])
+                c1(h, [dict(act='relu', out_act=t)])
+                h2 = new(C)
+                c2(t, [dict(act='relu', out_act=h2)], residual_act=idn)
+                h = h2
+                continue
             if ds is not None:                       # identity path = 1x1 convolution of the concatenated input
                 h32 = torch.empty(N, H, W, C, device=dev)
                 ds(h, [dict(out_f32=(h32, nhwc))])
@@ -293,7 +311,8 @@ class DepthNetEngine(HeightNetEngine):
         feat = torch.empty(N, H, W, self.Cctx, device=dev)
         self.context(ctx, [dict(out_f32=(feat, D.nhwc_strides(self.Cctx, H, W)))])
         if not self.stereo:
-            h, h32 = self._gated(x32, self.gate(mlp_input), True)
+            lean = self.parts == 1 and os.environ.get('DHD_BF16_RESIDUAL', '1') != '0'     # trunk() then ignores h32
+            h, h32 = self._gated(x32, self.gate(mlp_input), not lean)
             return self.trunk(h, h32, softmax), feat
         if cost_volume is None or (cost_volume.H + 3) // 4 != H or (cost_volume.W + 3) // 4 != W:
             raise ValueError('stereo DepthNet needs the (B*N, 4fH, 4fW, D) cost volume activation')
@@ -340,6 +359,7 @@ class SFAEngine:
         self.fc2_w, self.fc2_b = f(st.fc[2].weight), f(st.fc[2].bias)
         sl = st.spacial_leanring
         self.sp1 = _Conv(sl[0], sl[1], precision, device)
+        self.sp1_w32 = f(sl[0].weight.flatten(1))           # [C][C] fp32: the gate is folded into it per call (_lean)
         self.sp2 = _Conv(sl[3], sl[4], precision, device)
         mr = sfa.mix_residual
         self.res1 = _Conv(mr[0], mr[1], precision, device)
@@ -358,6 +378,8 @@ class SFAEngine:
         new = lambda c: D.Act.empty(N, H, W, c, P, dev)
         s = x.mean if getattr(x, 'mean', None) is not None else mean_hw(x)
         a1 = linear_rows(linear_rows(s, self.fc0_w, self.fc0_b, 'relu'), self.fc2_w, self.fc2_b, 'sigmoid')
+        if P == 1 and x.parts == 1 and os.environ.get('DHD_SFA_LEAN', '1') != '0':
+            return self._lean(x, a1, out_f32)
         u = new(C)
         self._mix(x, a1, None, u)
         t = new(C)
@@ -377,6 +399,37 @@ class SFAEngine:
         if out_f32 is not None:
             seg['out_f32'] = out_f32
         self.res2(t, [seg], residual=(sc, D.nhwc_strides(self.Cout, H, W)[:3]))
+        return out
+
+
+    def _lean(self, x, a1, out_f32):
+        """bf16 speed mode: three memory passes less than the layer-by-layer form.
+        (1) The channel-gated blend u = a1*bev + (1-a1)*vox is never materialised: it only feeds the 1x1 convolution
+            spacial_leanring[0], and W u = [W diag(a1) | W diag(1-a1)] [bev ; vox], so the gate is folded into per-image
+            weights (dhd_sfa_fold_gate, 4 x 256 x 512 values) and the convolution reads x directly.
+        (2) The spatial gate a2 and the shortcut branch stay bf16 (128-byte-row TMA stores) instead of fp32 tensors.
+        (3) The shortcut is added in mix_residual's last epilogue from its bf16 activation."""
+        N, H, W, C, dev = x.N, x.H, x.W, self.C, x.data.device
+        new = lambda c: D.Act.empty(N, H, W, c, 1, dev)
+        lib = _lib.load()
+        wq = torch.empty(N * C, 1, 1, 2 * C, dtype=torch.bfloat16, device=dev)
+        _lib.check(lib.dhd_sfa_fold_gate(_p(self.sp1_w32), _p(a1), N, C, C, _p(wq), _stream()), 'sfa_fold_gate')
+        t = new(C)
+        D.conv2d(x, wq, C, precision='bf16', scale=self.sp1.scale, bias=self.sp1.bias, image_weights=True,
+                 segs=[dict(act='relu', out_act=t)])
+        a2 = new(C)
+        self.sp2(t, [dict(act='sigmoid', out_act=a2)])
+        fuse = t                                   # t is dead once the gate exists
+        _lib.check(lib.dhd_sfa_blend_b16(_p(x.data), x.ld, x.coff, C, N, H * W, _p(a1), _p(a2.data), a2.ld, a2.coff,
+                                         _p(fuse.data), fuse.ld, fuse.coff, _stream()), 'sfa_blend_b16')
+        sc = new(self.Cout)
+        self.short(x, [dict(out_act=sc)])
+        self.res1(fuse, [dict(act='relu', out_act=a2)])      # a2 is dead after the blend: reuse as res1's output
+        out = t if self.Cout == C else new(self.Cout)
+        seg = dict(act='relu', out_act=out)
+        if out_f32 is not None:
+            seg['out_f32'] = out_f32
+        self.res2(a2, [seg], residual_act=sc)
         return out
 
 

@@ -217,17 +217,27 @@ class HotPathStep:
         if not hasattr(self, '_prep_stream'):
             self._prep_stream = torch.cuda.Stream()
 
+        # the per-camera 3x3s (the reference's own torch.inverse / matmul calls: ~25 tiny library launches) start at once
+        self._prep_stream.wait_stream(main)
+        with torch.cuda.stream(self._prep_stream):
+            # ... and so does the camera-aware SE gate of HeightNet (get_mlp_input + Mlp + SELayer: camera tensors only)
+            mlp = self.vt.get_mlp_input(s['sensor2ego'], s['ego2global'], s['cam2imgs'], s['post_rots'],
+                                        s['post_trans'], s['bda'])
+            gate = self.height_engine.gate(mlp)
+            gate.record_stream(main)
+            gate_ready = torch.cuda.Event()
+            gate_ready.record(self._prep_stream)
+            cam_mats = self.plan.camera_matrices(s['sensor2ego'], s['cam2imgs'], s['post_rots'], s['post_trans'], s['bda'])
+
         def fork_prepare():        # late in HeightNet: the bins are still in L2 when the pool starts
             self._prep_stream.wait_stream(main)
             with torch.cuda.stream(self._prep_stream):
-                self.plan.prepare(frustum=self.frustum, sensor2ego=s['sensor2ego'], cam2imgs=s['cam2imgs'],
-                                  post_rots=s['post_rots'], post_trans=s['post_trans'], bda=s['bda'],
+                self.plan.prepare(frustum=self.frustum, cam_mats=cam_mats,
                                   deterministic=self.deterministic, workspace=self.workspace)
         xa = D.pack_input(s['x'].view(B * N, self.Cin, self.fH, self.fW), self.parts)
         depth, feat = self.depth_engine(xa)
-        mlp = self.vt.get_mlp_input(s['sensor2ego'], s['ego2global'], s['cam2imgs'], s['post_rots'],
-                                    s['post_trans'], s['bda'])
-        height = self.height_engine(xa, mlp, softmax=True, hook=fork_prepare)
+        main.wait_event(gate_ready)
+        height = self.height_engine(xa, mlp, softmax=True, hook=fork_prepare, gate=gate)
         pixmask = height_to_mask(height, self.cfg['height_range'], self.cfg['mask_range'])
         main.wait_stream(self._prep_stream)
         self._last = {'depth': depth, 'feat': feat, 'height': height, 'pixmask': pixmask}
@@ -653,6 +663,17 @@ class TrainStep(HotPathStep):
         s = self.static
         B, N = self.B, self.N
         self.bucket.zero()
+        # geometry + binning depend on the camera tensors only: a parallel branch of the captured graph (the ~25 tiny
+        # library launches of the reference's torch.inverse / matmul calls and the binning kernels run under the
+        # dense front instead of after it)
+        main = torch.cuda.current_stream()
+        if not hasattr(self, '_prep_stream'):
+            self._prep_stream = torch.cuda.Stream()
+        self._prep_stream.wait_stream(main)
+        with torch.cuda.stream(self._prep_stream):
+            self.plan.prepare(frustum=self.frustum, sensor2ego=s['sensor2ego'], cam2imgs=s['cam2imgs'],
+                              post_rots=s['post_rots'], post_trans=s['post_trans'], bda=s['bda'],
+                              deterministic=self.deterministic, workspace=self.workspace)
         # ---- forward
         xa = D.pack_input(s['x'].view(B * N, self.Cin, self.fH, self.fW), 1)
         depth, feat = self.t_depth.forward(xa)
@@ -660,9 +681,7 @@ class TrainStep(HotPathStep):
                                     s['post_trans'], s['bda'])
         height = self.t_height.forward(xa, mlp)
         pixmask = height_to_mask(height, self.cfg['height_range'], self.cfg['mask_range'])
-        self.plan.prepare(frustum=self.frustum, sensor2ego=s['sensor2ego'], cam2imgs=s['cam2imgs'],
-                          post_rots=s['post_rots'], post_trans=s['post_trans'], bda=s['bda'],
-                          deterministic=self.deterministic, workspace=self.workspace)
+        main.wait_stream(self._prep_stream)
         self._last = {'depth': depth, 'feat': feat, 'height': height, 'pixmask': pixmask}
 
     def _fwd_bwd_rest(self):

@@ -218,10 +218,12 @@ class MghsPool:
             ipr, ptn, comb, tr, bda3 = [m.contiguous().float() for m in cam_mats]
             if ipr.numel() != self.B * self.N * 9 or bda3.numel() != self.B * 9:
                 raise ValueError('camera matrices do not match (B, N)')
-            f = frustum.to(device=dev, dtype=torch.float32)
-            fu = f[0, 0, :, 0].contiguous()
-            fv = f[0, :, 0, 1].contiguous()
-            fd = f[:, 0, 0, 2].contiguous()
+            fkey = (frustum.data_ptr(), frustum._version, str(dev))
+            if getattr(self, '_fvec_key', None) != fkey:     # the frustum is a constant buffer: slice it once
+                f = frustum.to(device=dev, dtype=torch.float32)
+                self._fvec = (f[0, 0, :, 0].contiguous(), f[0, :, 0, 1].contiguous(), f[:, 0, 0, 2].contiguous())
+                self._fvec_key = fkey
+            fu, fv, fd = self._fvec
             args[1:] = [fu, fv, fd, ipr, ptn, comb, tr, bda3]
         _lib.check(self._lib.dhd_mghs_prepare(
             ctypes.byref(self.cfg), *[_ptr(a) for a in args], _ptr(ws), int(bool(deterministic)),

@@ -209,6 +209,15 @@ typedef struct dhd_conv_desc {
   const void* mix_x;
   int32_t mix_ld, mix_coff, mix_parts, mix_part_stride;
   const float* mix_a1;
+  /* Per-image weights: 0 = one weight matrix for every image; > 0 = `weight` holds N matrices of w_image_rows
+   * (>= Cout) rows each, image n convolves with rows [n*w_image_rows, n*w_image_rows + Cout).  This is how SFA's
+   * channel gate (mix.py:41-50: u = a1*bev + (1-a1)*vox, a1 per image and channel) is folded into the 1x1
+   * convolution that consumes u: W*u = [W diag(a1) | W diag(1-a1)] * [bev ; vox] (dhd_sfa_fold_gate). */
+  int32_t w_image_rows;
+  /* bf16 residual (same pixel grid as the output, channel c at res_b16_coff + c of res_b16_ld), added to the
+   * pre-activation value like `residual`; the bf16 speed mode's identity paths.  NULL = off. */
+  int32_t res_b16_ld, res_b16_coff;
+  const void* res_b16;
 } dhd_conv_desc;
 
 int dhd_conv2d_fwd(const dhd_conv_desc* desc, void* stream);
@@ -459,6 +468,15 @@ int dhd_gate_channels(const float* x, int N, int HW, int C, const float* gate, v
 int dhd_sfa_mix(const void* x, int x_ld, int x_coff, int x_part_stride, int x_parts, int C, int N,
                 int HW, const float* a1, const float* a2, void* out, int o_ld, int o_coff,
                 int o_part_stride, int o_parts, void* stream);
+/* bf16 speed mode of the second blend: a2 is a single-part bf16 NHWC activation (channel c at a2_coff + c of a2_ld),
+ * x and out single-part bf16; same arithmetic and operation order as dhd_sfa_mix */
+int dhd_sfa_blend_b16(const void* x, int x_ld, int x_coff, int C, int N, int HW, const float* a1, const void* a2,
+                      int a2_ld, int a2_coff, void* out, int o_ld, int o_coff, void* stream);
+/* The first blend folded into the weights of the convolution that consumes it (mix.py:41-50, 28-29): for a 1x1
+ * weight w [Cout][C] fp32 and the channel gate a1 [N][C], writes out [N][Cout][2C] bf16 with
+ * out[n][co][c] = w[co][c]*a1[n][c], out[n][co][C+c] = w[co][c]*(1-a1[n][c]) -- the per-image weights
+ * (dhd_conv_desc.w_image_rows = Cout) of a 1x1 convolution over x = [bev | vox] that equals conv(w, a1*bev+(1-a1)*vox) */
+int dhd_sfa_fold_gate(const float* w, const float* a1, int N, int Cout, int C, void* out, void* stream);
 /* deformable bilinear im2col of mmcv DeformConv2dPack (depthnet.py:225-236, 466-477), stride 1,
  * deform_groups 1; offset fp32 [pix][off_ld] with (dy, dx) per tap; out channels ordered
  * [group][tap][C/groups] */

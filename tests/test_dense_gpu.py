@@ -104,6 +104,74 @@ def test_bf16_speed_mode_is_close(cuda_lib):
     assert (h - ref).abs().max() <= 3e-2 * ref.abs().max()
 
 
+def test_conv_per_image_weights_and_bf16_residual(cuda_lib):
+    """dhd_conv_desc.w_image_rows (image n convolves with its own weight rows) and res_b16 (bf16 identity path added
+    before the activation) against torch on the same bf16-rounded operands."""
+    from dhd_b200 import dense as D
+    g = torch.Generator().manual_seed(5)
+    N, H, W, Cin, Cout = 3, 20, 24, 128, 192
+    x = torch.randn(N, Cin, H, W, generator=g).bfloat16().float()
+    w = (torch.randn(N, Cout, Cin, generator=g) / Cin ** 0.5).bfloat16().float()
+    r = torch.randn(N, Cout, H, W, generator=g).bfloat16().float()
+    bias = torch.randn(Cout, generator=g)
+    ref = torch.relu(torch.einsum('nchw,noc->nohw', x, w) + bias[None, :, None, None] + r)
+    xa = D.pack_input(x.cuda(), 1)
+    ra = D.pack_input(r.cuda(), 1)
+    out = D.Act.empty(N, H, W, Cout, 1, 'cuda')
+    wq = w.reshape(N * Cout, 1, 1, Cin).bfloat16().cuda().contiguous()
+    D.conv2d(xa, wq, Cout, precision='bf16', bias=bias.cuda(), image_weights=True, residual_act=ra,
+             segs=[dict(act='relu', out_act=out)])
+    got = out.float().cpu()
+    assert (got - ref).abs().max() <= 1e-2 * ref.abs().max() + 1e-3        # bf16 output rounding
+    # 3x3 with a bf16 residual, shared weights
+    w3 = (torch.randn(Cout, Cin, 3, 3, generator=g) / (9 * Cin) ** 0.5).bfloat16().float()
+    ref3 = torch.nn.functional.conv2d(x, w3, padding=1) + r
+    out3 = torch.empty(N, H, W, Cout, device='cuda')
+    D.conv2d(xa, D.pack_weight(w3.cuda(), 1), Cout, ksize=3, precision='bf16', residual_act=ra,
+             segs=[dict(out_f32=(out3, D.nhwc_strides(Cout, H, W)))])
+    assert (out3.permute(0, 3, 1, 2).cpu() - ref3).abs().max() <= 2e-5 * ref3.abs().max() + 2e-5
+
+
+def test_sfa_fold_gate_and_bf16_blend_kernels(cuda_lib):
+    """dhd_sfa_fold_gate / dhd_sfa_blend_b16 against their definitions (mix.py:41-57)."""
+    import ctypes
+    from dhd_b200 import _lib
+    from dhd_b200 import dense as D
+    g = torch.Generator().manual_seed(6)
+    N, C, Co, HW = 2, 64, 48, 37 * 5
+    w, a1 = torch.randn(Co, C, generator=g).cuda(), torch.rand(N, C, generator=g).cuda()
+    out = torch.empty(N, Co, 2 * C, dtype=torch.bfloat16, device='cuda')
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    _lib.check(_lib.load().dhd_sfa_fold_gate(P(w), P(a1), N, Co, C, P(out), st), 'fold')
+    want = torch.cat([w[None] * a1[:, None], w[None] * (1 - a1[:, None])], 2).bfloat16()
+    assert torch.equal(out, want)
+    x = torch.randn(N, 37, 5, 2 * C, generator=g).bfloat16().cuda()
+    a2 = torch.rand(N, 37, 5, C, generator=g).bfloat16().cuda()
+    res = torch.empty(N, 37, 5, C, dtype=torch.bfloat16, device='cuda')
+    _lib.check(_lib.load().dhd_sfa_blend_b16(P(x), 2 * C, 0, C, N, HW, P(a1), P(a2), C, 0, P(res), C, 0, st), 'blend')
+    bev, vox, g1, g2 = x[..., :C].float(), x[..., C:].float(), a1[:, None, None, :], a2.float()
+    want = (g2 * (g1 * bev) + (1 - g2) * ((1 - g1) * vox)).bfloat16()
+    assert torch.equal(res, want)
+
+
+def test_bf16_lean_paths_match_layer_by_layer(cuda_lib, monkeypatch):
+    """bf16 speed mode: SFA with the channel gate folded into per-image weights and bf16 gate / shortcut tensors, and
+    HeightNet with bf16 identity paths, against the layer-by-layer form of the same mode (fp32 side tensors)."""
+    hn, sfa, head, _ = build('bf16')
+    x, mlp, bev = MG.inputs()
+    outs = {}
+    for lean in ('1', '0'):
+        monkeypatch.setenv('DHD_SFA_LEAN', lean)
+        monkeypatch.setenv('DHD_BF16_RESIDUAL', lean)
+        outs[lean] = (sfa(bev.cuda()).cpu(), hn(x.cuda(), mlp.cuda()).cpu())
+    for a, b, what in zip(outs['1'], outs['0'], ('SFA', 'HeightNet')):
+        assert (a - b).abs().max() <= 1.5e-2 * b.abs().max(), (what, float((a - b).abs().max()), float(b.abs().max()))
+    gold = np.load(GOLD)
+    ref = torch.from_numpy(gold['sfa'])
+    assert (outs['1'][0] - ref).abs().max() <= 2e-2 * ref.abs().max()
+
+
 def test_mghs_forward_end_to_end(cuda_lib):
     """Plugin MGHS.forward (dense front + fused pool) on the MINI rig: dense outputs against the
     oracle, pooled BEV tensors against the oracle's view_transform fed with the SAME depth /
