@@ -48,13 +48,15 @@ static EncodeTiledFn encode_fn() {
 }
 
 int conv2_launch(const dhd_conv_desc* d, void* encode, void* stream);   // conv_igemm2.cu
+int conv2_launch_batch(const dhd_conv_desc* const* descs, int n, void* encode, void* stream);
+int conv2_pair_mode(int set);
 void* conv_encode_fn() { return (void*)encode_fn(); }                  // used by conv_wgrad.cu
 
 }  // namespace dhd
 
 using namespace dhd;
 
-extern "C" int dhd_conv2d_fwd(const dhd_conv_desc* d, void* stream) {
+static int validate_conv(const dhd_conv_desc* d) {
   DHD_REQUIRE(d != nullptr, "conv desc is null");
   DHD_REQUIRE(d->in != nullptr && d->weight != nullptr, "null input / weight pointer");
   DHD_REQUIRE(d->N > 0 && d->H > 0 && d->W > 0, "bad image shape");
@@ -81,9 +83,6 @@ extern "C" int dhd_conv2d_fwd(const dhd_conv_desc* d, void* stream) {
       DHD_REQUIRE(sg.c_lo / kBlockN == (sg.c_hi - 1) / kBlockN, "softmax range must sit in one 128-channel tile");
     if (sg.out_b16 != nullptr) DHD_REQUIRE(sg.b16_parts >= 1 && sg.b16_parts <= 3, "bad b16_parts");
   }
-  EncodeTiledFn enc = encode_fn();
-  if (enc == nullptr) return fail(DHD_EUNSUPPORTED, "%s", "cuTensorMapEncodeTiled is unavailable");
-
   bool centre = false;
   for (int t = 0; t < d->taps; ++t) centre |= d->tap_dx[t] == 0 && d->tap_dy[t] == 0;
   DHD_REQUIRE(centre, "the filter must contain the (0, 0) tap");
@@ -110,8 +109,29 @@ extern "C" int dhd_conv2d_fwd(const dhd_conv_desc* d, void* stream) {
   }
   if (d->stride != 2 && (d->in_H > 0 || d->in_W > 0))
     DHD_REQUIRE(d->in_H >= d->H && d->in_W >= d->W, "in_H / in_W must be at least the output grid");
-  bool strided_out = false;
-  for (int s = 0; s < d->n_seg; ++s) strided_out |= d->seg[s].b16_sX != 0;
-  (void)strided_out;
+  return DHD_OK;
+}
+
+extern "C" int dhd_conv2d_fwd(const dhd_conv_desc* d, void* stream) {
+  const int rc = validate_conv(d);
+  if (rc != DHD_OK) return rc;
+  EncodeTiledFn enc = encode_fn();
+  if (enc == nullptr) return fail(DHD_EUNSUPPORTED, "%s", "cuTensorMapEncodeTiled is unavailable");
   return conv2_launch(d, (void*)enc, stream);
 }
+
+extern "C" int dhd_conv2d_fwd_batch(const dhd_conv_desc* descs, int n, void* stream) {
+  DHD_REQUIRE(descs != nullptr && n >= 1 && n <= DHD_CONV_MAX_BATCH, "batch of 1..DHD_CONV_MAX_BATCH descriptors");
+  const dhd_conv_desc* ptrs[DHD_CONV_MAX_BATCH];
+  for (int i = 0; i < n; ++i) {
+    const int rc = validate_conv(descs + i);
+    if (rc != DHD_OK) return rc;
+    ptrs[i] = descs + i;
+  }
+  EncodeTiledFn enc = encode_fn();
+  if (enc == nullptr) return fail(DHD_EUNSUPPORTED, "%s", "cuTensorMapEncodeTiled is unavailable");
+  if (n == 1) return conv2_launch(ptrs[0], (void*)enc, stream);
+  return conv2_launch_batch(ptrs, n, (void*)enc, stream);
+}
+
+extern "C" int dhd_conv_pair_mode(int mode) { return conv2_pair_mode(mode); }

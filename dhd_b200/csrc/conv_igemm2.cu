@@ -27,10 +27,15 @@ constexpr uint32_t kA2Bytes = kM2 * kK2 * 2;
 constexpr uint32_t kStageBufBytes = 16384;   // one TMA-store staging tile: 128 rows x 128 B
 constexpr int kMaxConvBatch = DHD_CONV_MAX_BATCH;
 
-template <int NT>
+// CTAS = 2: a CTA pair (cluster of two on one TPC) computes a 256-pixel x NT tile with ONE tcgen05.mma.cta_group::2
+// per k-step: each CTA stages its own 128 pixels of A and HALF of the weight tile, so a k-step moves 32 KB per SM
+// instead of 48 KB.  The 3x3 layers at 200x200 ran at 0.49 us per 64-channel step against 0.27 us of tensor-core time
+// (profiles/r01_conv3x3_sfa_full.txt: the pipe waits on operand tiles, L2 -> shared memory at ~14 TB/s chip-wide);
+// fewer bytes per FLOP and a fourth ring stage in the freed shared memory attack exactly that.
+template <int NT, int CTAS = 1>
 struct Cfg2 {
-  static constexpr int kStages = NT == 256 ? 3 : 4;
-  static constexpr uint32_t kBBytes = NT * kK2 * 2;
+  static constexpr int kStages = CTAS == 2 ? 4 : (NT == 256 ? 3 : 4);
+  static constexpr uint32_t kBBytes = (NT / CTAS) * kK2 * 2;
   static constexpr uint32_t kStageBytes = kA2Bytes + kBBytes;
   static constexpr uint32_t kVecBytes = 3 * NT * 4;            // scale, bias(+img_bias), gate
   static constexpr uint32_t kSmem = kStages * kStageBytes + 4 * kStageBufBytes + kVecBytes + 256 + 1024;
@@ -81,14 +86,21 @@ __device__ __forceinline__ bool tap_dead2(const dhd_conv_desc& d, int t, int x0,
   return xs >= iw || xs + d.bw * st <= 0 || ys >= ih || ys + d.bh * st <= 0;
 }
 
-template <int NT, int G, int NP>
+template <int NT, int G, int NP, int CTAS>
 __global__ void __launch_bounds__((4 * G + 2) * 32, 1)
 conv_igemm2_kernel(const __grid_constant__ ConvBatch<NP> B) {
-  using C = Cfg2<NT>;
+  static_assert(CTAS == 1 || (NP == 1 && NT == 256), "CTA pairs: single problem, 256-wide N tile");
+  using C = Cfg2<NT, CTAS>;
   constexpr int kEpiWarps = 4 * G;
   constexpr int kBufPerGroup = 4 / G;          // staging tiles per group: 4 x 16 KB in total
   extern __shared__ uint8_t smem_raw[];
-  const int total_tiles = B.tile_end[B.n - 1];
+  // CTAS == 2: work items are PAIRS of M tiles (2i, 2i+1) x one N tile; cluster c walks items c, c + #clusters, ..
+  const uint32_t crank = CTAS == 2 ? cluster_ctarank() : 0u;
+  const bool leader = crank == 0;
+  const int total_tiles = CTAS == 2 ? ((B.P[0].total_tiles / B.P[0].n_tiles + 1) / 2) * B.P[0].n_tiles
+                                    : B.tile_end[B.n - 1];
+  const int tile_first = CTAS == 2 ? (int)cluster_id_x() : (int)blockIdx.x;
+  const int tile_step = CTAS == 2 ? (int)cluster_nid_x() : (int)gridDim.x;
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   const uint32_t stagebuf = base + C::kStages * C::kStageBytes;            // 2 groups x 2 x 16 KB, 1024-aligned
@@ -105,7 +117,7 @@ conv_igemm2_kernel(const __grid_constant__ ConvBatch<NP> B) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + (bar_base - base) + 8u * (2 * C::kStages + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr uint32_t kIdesc = umma_instr_desc_bf16(kM2, NT);
+  constexpr uint32_t kIdesc = umma_instr_desc_bf16(kM2 * CTAS, NT);
 
   if (warp == kEpiWarps && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&B.M[0].a) : "memory");
@@ -116,18 +128,26 @@ conv_igemm2_kernel(const __grid_constant__ ConvBatch<NP> B) {
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), G);          // one arrival per epilogue group
+      mbar_init(tempty_bar(s), G * CTAS);   // one arrival per epilogue group (of both CTAs of a pair)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kEpiWarps + 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "n"(C::kTmemCols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CTAS == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "n"(C::kTmemCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "n"(C::kTmemCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (CTAS == 2) cluster_sync_all();          // the peer's barriers exist before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -140,23 +160,43 @@ conv_igemm2_kernel(const __grid_constant__ ConvBatch<NP> B) {
     }
     return p;
   };
-  auto decode = [&](const Conv2Params& P, int tile, int& img, int& x0, int& y0, int& n0) {
+  // CTAS == 2: `tile` is a pair item; rank r of the pair owns M tile 2*(item / n_tiles) + r.  Returns false for the
+  // missing second tile of an odd tile count (img = N: every TMA box is out of bounds -> zeros, nothing is stored)
+  auto decode = [&](const Conv2Params& P, int tile, int& img, int& x0, int& y0, int& n0, uint32_t rank = 0u) -> bool {
     const int nt = tile % P.n_tiles;
     int mt = tile / P.n_tiles;
+    if (CTAS == 2) mt = 2 * mt + (int)rank;
+    n0 = nt * NT;
+    if (CTAS == 2 && mt >= P.total_tiles / P.n_tiles) {
+      img = P.d.N;
+      x0 = y0 = 0;
+      return false;
+    }
     const int tx = mt % P.tiles_w;
     mt /= P.tiles_w;
     const int ty = mt % P.tiles_h;
     img = mt / P.tiles_h;
     x0 = tx * P.d.bw;
     y0 = ty * P.d.bh;
-    n0 = nt * NT;
+    return true;
+  };
+  // a filter tap is skipped when its shifted box lies outside the image -- for a CTA pair: outside for BOTH tiles
+  auto tap_skipped = [&](const Conv2Params& P, int t, int item, int x0, int y0, bool valid) {
+    bool dead = !valid || tap_dead2(P.d, t, x0, y0);
+    if (CTAS == 2 && dead) {
+      int img2, x2, y2, n2;
+      const bool v2 = decode(P, item, img2, x2, y2, n2, crank ^ 1u);
+      dead = !v2 || tap_dead2(P.d, t, x2, y2);
+    }
+    return dead;
   };
 
   if (warp == kEpiWarps) {
     // ===================================================== TMA producer
     if (lane == 0) {
       int it = 0;
-      for (int gtile = blockIdx.x; gtile < total_tiles; gtile += gridDim.x) {
+      const uint32_t lead_full0 = CTAS == 2 ? mapa_u32(full_bar(0), 0u) : 0u;
+      for (int gtile = tile_first; gtile < total_tiles; gtile += tile_step) {
         int tile = gtile;
         const int pid = problem_of(tile);
         const Conv2Params& P = B.P[pid];
@@ -165,15 +205,25 @@ conv_igemm2_kernel(const __grid_constant__ ConvBatch<NP> B) {
         const int kchunks = d.Cin / kK2;
         const int in_stride = d.stride > 1 ? d.stride : 1;     // the tensor map strides the box (elementStrides)
         int img, x0, y0, n0;
-        decode(P, tile, img, x0, y0, n0);
+        const bool tvalid = decode(P, tile, img, x0, y0, n0, crank);
         for (int t = 0; t < d.taps; ++t) {
-          if (tap_dead2(d, t, x0, y0)) continue;
+          if (tap_skipped(P, t, tile, x0, y0, tvalid)) continue;
           for (int kc = 0; kc < kchunks; ++kc) {
             for (int e = 0; e < d.n_terms; ++e, ++it) {
               const int s = it % C::kStages;
               const uint32_t ph = (it / C::kStages) & 1;
               mbar_wait(empty_bar(s), ph ^ 1);
               const uint32_t sa = base + s * C::kStageBytes, sb = sa + kA2Bytes;
+              if (CTAS == 2) {
+                // both CTAs' bytes are counted by the LEADER's barrier (the MMA issuer waits there)
+                if (leader) mbar_expect_tx(full_bar(s), 2 * C::kStageBytes);
+                const uint32_t lf = lead_full0 + 8u * s;
+                tma_load_4d_2sm(sa, &M.a, lf, d.in_coff + d.term_a[e] * d.in_part_stride + kc * kK2,
+                                x0 * in_stride + d.tap_dx[t], y0 * in_stride + d.tap_dy[t], img);
+                tma_load_2d_2sm(sb, &M.b, lf, (t * d.w_parts + d.term_b[e]) * d.Cin + kc * kK2,
+                                n0 + (int)crank * (NT / 2));
+                continue;
+              }
               mbar_expect_tx(full_bar(s), C::kStageBytes);
               tma_load_4d(sa, &M.a, full_bar(s), d.in_coff + d.term_a[e] * d.in_part_stride + kc * kK2,
                           x0 * in_stride + d.tap_dx[t], y0 * in_stride + d.tap_dy[t], img);
@@ -185,23 +235,23 @@ conv_igemm2_kernel(const __grid_constant__ ConvBatch<NP> B) {
     }
   } else if (warp == kEpiWarps + 1) {
     // ===================================================== MMA issuer
-    if (lane == 0) {
+    if (lane == 0 && leader) {
       int it = 0, lt = 0;
-      for (int gtile = blockIdx.x; gtile < total_tiles; gtile += gridDim.x, ++lt) {
+      for (int gtile = tile_first; gtile < total_tiles; gtile += tile_step, ++lt) {
         int tile = gtile;
         const int pid = problem_of(tile);
         const Conv2Params& P = B.P[pid];
         const dhd_conv_desc& d = P.d;
         const int kchunks = d.Cin / kK2;
         int img, x0, y0, n0;
-        decode(P, tile, img, x0, y0, n0);
+        const bool tvalid = decode(P, tile, img, x0, y0, n0, crank);
         const int as = lt & 1;
         mbar_wait(tempty_bar(as), ((lt >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tacc = tmem_base + (uint32_t)(as * NT);
         int first = 1;
         for (int t = 0; t < d.taps; ++t) {
-          if (tap_dead2(d, t, x0, y0)) continue;
+          if (tap_skipped(P, t, tile, x0, y0, tvalid)) continue;
           for (int kc = 0; kc < kchunks; ++kc) {
             for (int e = 0; e < d.n_terms; ++e, ++it) {
               const int s = it % C::kStages;
@@ -211,14 +261,18 @@ conv_igemm2_kernel(const __grid_constant__ ConvBatch<NP> B) {
               const uint32_t sa = base + s * C::kStageBytes, sb = sa + kA2Bytes;
               const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sb);
 #pragma unroll
-              for (int k = 0; k < kK2 / kUmmaK; ++k)
-                umma_bf16(tacc, da + 2u * k, db + 2u * k, kIdesc, (first && k == 0) ? 0u : 1u);
+              for (int k = 0; k < kK2 / kUmmaK; ++k) {
+                if (CTAS == 2) umma_bf16_2sm(tacc, da + 2u * k, db + 2u * k, kIdesc, (first && k == 0) ? 0u : 1u);
+                else umma_bf16(tacc, da + 2u * k, db + 2u * k, kIdesc, (first && k == 0) ? 0u : 1u);
+              }
               first = 0;
-              umma_commit(empty_bar(s));
+              if (CTAS == 2) umma_commit_2sm(empty_bar(s));      // frees the stage in both CTAs
+              else umma_commit(empty_bar(s));
             }
           }
         }
-        umma_commit(tfull_bar(as));
+        if (CTAS == 2) umma_commit_2sm(tfull_bar(as));
+        else umma_commit(tfull_bar(as));
       }
     }
   } else {
@@ -237,15 +291,23 @@ conv_igemm2_kernel(const __grid_constant__ ConvBatch<NP> B) {
     const int row = tid;
     int lt = 0;
     uint32_t nstore = 0;                    // TMA stores issued so far by this group (selects the staging buffer)
-    for (int gtile = blockIdx.x; gtile < total_tiles; gtile += gridDim.x, ++lt) {
+    const uint32_t lead_tempty0 = CTAS == 2 ? mapa_u32(tempty_bar(0), 0u) : 0u;
+    for (int gtile = tile_first; gtile < total_tiles; gtile += tile_step, ++lt) {
       int tile = gtile;
       const int pid = problem_of(tile);
       const Conv2Params& P = B.P[pid];
       const Conv2Maps& M = B.M[pid];
       const dhd_conv_desc& d = P.d;
       int img, x0, y0, n0;
-      decode(P, tile, img, x0, y0, n0);
+      const bool tvalid = decode(P, tile, img, x0, y0, n0, crank);
       const int as = lt & 1;
+      if (CTAS == 2 && !tvalid) {             // the missing half of the last pair: only the accumulator hand-shake
+        mbar_wait(tfull_bar(as), (lt >> 1) & 1);
+        tc_fence_before();
+        named_bar_sync(gbar, 128);
+        if (tid == 0) mbar_arrive_cluster(lead_tempty0 + 8u * as);
+        continue;
+      }
       named_bar_sync(5, 128 * G);           // everyone is done with the previous tile's vectors
       for (int c = threadIdx.x; c < NT; c += 128 * G) {
         const int ch = n0 + c;
@@ -546,16 +608,22 @@ conv_igemm2_kernel(const __grid_constant__ ConvBatch<NP> B) {
       tc_fence_before();
       named_bar_sync(gbar, 128);
       if (tid == 0) {
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty_bar(as)) : "memory");
+        if (CTAS == 2) mbar_arrive_cluster(lead_tempty0 + 8u * as);     // the pair's MMA issuer lives in the leader CTA
+        else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty_bar(as)) : "memory");
       }
     }
     if (tid == 0) tma_store_wait<0>();      // all bulk stores complete before the CTA exits
   }
   __syncthreads();
+  if (CTAS == 2) cluster_sync_all();          // the leader's MMAs read the peer's shared memory and write its TMEM
   if (warp == kEpiWarps + 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::kTmemCols)
-                 : "memory");
+    if (CTAS == 2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::kTmemCols)
+                   : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::kTmemCols)
+                   : "memory");
   }
 }
 
@@ -566,17 +634,72 @@ typedef CUresult (*EncodeTiledFn2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
 
 template <int NT, int G, int NP>
 static int launch2(const ConvBatch<NP>& batch, cudaStream_t st) {
-  using C = Cfg2<NT>;
+  using C = Cfg2<NT, 1>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_igemm2_kernel<NT, G, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_igemm2_kernel<NT, G, NP, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)C::kSmem);
     if (e != cudaSuccess) return fail((int)e, "%s: %ld", "cudaFuncSetAttribute(conv_igemm2)", (long)e);
     attr_set = true;
   }
   const int grid = min(batch.tile_end[batch.n - 1], sm_count());
-  conv_igemm2_kernel<NT, G, NP><<<grid, (4 * G + 2) * 32, C::kSmem, st>>>(batch);
+  conv_igemm2_kernel<NT, G, NP, 1><<<grid, (4 * G + 2) * 32, C::kSmem, st>>>(batch);
   DHD_CUDA_LAUNCH_CHECK("conv_igemm2");
+  return DHD_OK;
+}
+
+static int epi_groups();
+
+// CTA-pair variant (NT = 256, one problem): a cluster of two CTAs per work item.  Returns DHD_EUNSUPPORTED when the
+// device cannot co-schedule a single pair (the caller then uses the one-CTA kernel).
+static int max_pair_clusters() {
+  using C = Cfg2<256, 2>;
+  static int n = -1;
+  if (n < 0) {
+    auto kern = conv_igemm2_kernel<256, 2, 1, 2>;
+    n = 0;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem) == cudaSuccess) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(2 * sm_count());
+      cfg.blockDim = dim3(10 * 32);
+      cfg.dynamicSmemBytes = C::kSmem;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 2;
+      at[0].val.clusterDim.y = 1;
+      at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      int c = 0;
+      if (cudaOccupancyMaxActiveClusters(&c, kern, &cfg) == cudaSuccess) n = c;
+      else cudaGetLastError();
+    }
+  }
+  return n;
+}
+
+static int launch2_pair(const ConvBatch<1>& batch, cudaStream_t st) {
+  using C = Cfg2<256, 2>;
+  const int clusters_max = max_pair_clusters();
+  if (clusters_max <= 0) return DHD_EUNSUPPORTED;
+  const Conv2Params& P = batch.P[0];
+  const int items = ((P.total_tiles / P.n_tiles + 1) / 2) * P.n_tiles;
+  const int clusters = min(items, clusters_max);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * clusters);
+  cfg.blockDim = dim3(10 * 32);
+  cfg.dynamicSmemBytes = C::kSmem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_igemm2_kernel<256, 2, 1, 2>, batch);
+  if (e != cudaSuccess) return fail((int)e, "%s: %ld", "conv_igemm2 (CTA pairs) launch failed", (long)e);
+  ++g_launches;
   return DHD_OK;
 }
 
@@ -588,16 +711,42 @@ static int epi_groups() {
   return groups;
 }
 
-static int conv2_fill(const dhd_conv_desc* d, EncodeTiledFn2 enc, Conv2Maps& maps, Conv2Params& P, int NT);
+static int conv2_fill(const dhd_conv_desc* d, EncodeTiledFn2 enc, Conv2Maps& maps, Conv2Params& P, int NT, int ctas);
+
+// CTA pairs serve the wide layers (Cout > 128) with shared weights; DHD_CONV_CTA2=0 keeps everything on one-CTA tiles
+static int g_pair_mode = -1;            // -1: not read yet; 0 off; 1 where it pays; 2 wherever it is possible
+int conv2_pair_mode(int set) {          // dhd_conv_pair_mode (conv_igemm.cu): A/B switch for tests and benchmarks
+  if (g_pair_mode < 0) {
+    const char* v = getenv("DHD_CONV_CTA2");
+    g_pair_mode = v == nullptr ? 1 : max(0, min(2, atoi(v)));
+  }
+  const int prev = g_pair_mode;
+  if (set >= 0) g_pair_mode = min(set, 2);
+  return prev;
+}
+// Measured on B200 (profiles/r02_conv_pair_ab.txt, sustained clocks): pairs win on the tensor-bound layers with many
+// tiles per SM (3x3 256->256 at 4x200x200: 172.9 -> 167.2 us) and lose on the epilogue-bound 1x1 layers (+5..13 %) and
+// on single-wave layers (132 tiles: 20.4 -> 21.3 us), so mode 1 uses them for K >= 1024 and >= 4 tiles per SM only.
+static bool pair_mode(const dhd_conv_desc* d) {
+  const int mode = conv2_pair_mode(-1);
+  if (mode == 0 || d->Cout <= 128 || d->w_image_rows != 0 || epi_groups() != 2) return false;
+  if (mode == 1) {
+    const long tiles = (long)((d->W + d->bw - 1) / d->bw) * ((d->H + d->bh - 1) / d->bh) * d->N;
+    if ((long)d->taps * d->Cin * d->n_terms < 1024 || tiles < 4L * sm_count()) return false;
+  }
+  return max_pair_clusters() > 0;
+}
 
 // called by dhd_conv2d_fwd (conv_igemm.cu) after argument validation
 int conv2_launch(const dhd_conv_desc* d, void* encode, void* stream) {
   const int NT = d->Cout > 128 ? 256 : 128;
   ConvBatch<1> batch;
-  int rc = conv2_fill(d, (EncodeTiledFn2)encode, batch.M[0], batch.P[0], NT);
+  const bool pair = pair_mode(d);
+  int rc = conv2_fill(d, (EncodeTiledFn2)encode, batch.M[0], batch.P[0], NT, pair ? 2 : 1);
   if (rc != DHD_OK) return rc;
   batch.n = 1;
   batch.tile_end[0] = batch.P[0].total_tiles;
+  if (pair) return launch2_pair(batch, (cudaStream_t)stream);
   if (epi_groups() == 4) {
     if (NT == 256) return launch2<256, 4, 1>(batch, (cudaStream_t)stream);
     return launch2<128, 4, 1>(batch, (cudaStream_t)stream);
@@ -616,7 +765,7 @@ int conv2_launch_batch(const dhd_conv_desc* const* descs, int n, void* encode, v
   int total = 0;
   for (int i = 0; i < kMaxConvBatch; ++i) {
     if (i < n) {
-      int rc = conv2_fill(descs[i], (EncodeTiledFn2)encode, batch.M[i], batch.P[i], NT);
+      int rc = conv2_fill(descs[i], (EncodeTiledFn2)encode, batch.M[i], batch.P[i], NT, 1);
       if (rc != DHD_OK) return rc;
       total += batch.P[i].total_tiles;
     }
@@ -627,7 +776,7 @@ int conv2_launch_batch(const dhd_conv_desc* const* descs, int n, void* encode, v
   return launch2<128, 2, kMaxConvBatch>(batch, (cudaStream_t)stream);
 }
 
-static int conv2_fill(const dhd_conv_desc* d, EncodeTiledFn2 enc, Conv2Maps& maps, Conv2Params& P, int NT) {
+static int conv2_fill(const dhd_conv_desc* d, EncodeTiledFn2 enc, Conv2Maps& maps, Conv2Params& P, int NT, int ctas) {
   P.d = *d;
   {
     const int st = d->stride > 1 ? d->stride : 1;
@@ -647,7 +796,7 @@ static int conv2_fill(const dhd_conv_desc* d, EncodeTiledFn2 enc, Conv2Maps& map
     const cuuint64_t wrows = d->w_image_rows > 0 ? (cuuint64_t)d->w_image_rows * d->N : (cuuint64_t)d->Cout;
     cuuint64_t dims[2] = {ktot, wrows};
     cuuint64_t strides[1] = {ktot * 2};
-    cuuint32_t box[2] = {(cuuint32_t)kK2, (cuuint32_t)NT};
+    cuuint32_t box[2] = {(cuuint32_t)kK2, (cuuint32_t)(NT / ctas)};      // a CTA pair: each CTA stages half the rows
     cuuint32_t es[2] = {1, 1};
     CUresult r = enc(&maps.b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)d->weight, dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,

@@ -212,14 +212,15 @@ def tile_box(H, W):
 
 def conv2d(x, weight, Cout, ksize=1, dilation=1, precision='fp32', scale=None, bias=None,
            img_bias=None, img_gate=None, residual=None, segs=None, stride=1, sfa_mix=None, taps=None,
-           out_hw=None, residual_act=None, image_weights=False):
+           out_hw=None, residual_act=None, image_weights=False, defer=False):
     """One fused convolution.  x: Act; weight: pack_weight() result with PRECISIONS[precision]
     parts; segs: list of dicts {c_lo, c_hi, act, out_f32 (tensor, strides (sN,sY,sX,sC)),
     out_act (Act or Act.slice), out_view (sN, sY, sX, offset): pixel strides / start offset in bf16
     elements when out_act is written as a strided view (ConvTranspose2d phases)}.  stride=2: 3x3 / pad 1
     down-sampling convolution, output ceil(H/2) x ceil(W/2).  Outputs are written in place.
     residual_act: single-part bf16 Act added before the activation (bf16 speed mode's identity path);
-    image_weights=True: `weight` is [N*Cout][taps][parts][Cin], image n convolves with its own Cout rows."""
+    image_weights=True: `weight` is [N*Cout][taps][parts][Cin], image n convolves with its own Cout rows.
+    defer=True: nothing is launched; returns (descriptor, tensors to keep alive) for conv2d_batch()."""
     parts, terms = PRECISIONS[precision]
     if x.parts < parts or weight.shape[2] != parts:
         raise ValueError('activation has %d parts, weight %d, precision %s needs %d' %
@@ -304,8 +305,27 @@ def conv2d(x, weight, Cout, ksize=1, dilation=1, precision='fp32', scale=None, b
             if view is not None:
                 g.b16_sN, g.b16_sY, g.b16_sX = view[0], view[1], view[2]
             keep.append(a.data)
+    if defer:
+        return d, keep
     _lib.check(_lib.load().dhd_conv2d_fwd(ctypes.byref(d), _stream()), 'conv2d_fwd')
     return keep
+
+
+MAX_BATCH = 4
+
+
+def conv2d_batch(deferred):
+    """Launch the convolutions prepared with conv2d(..., defer=True) MAX_BATCH at a time in one persistent kernel each
+    (dhd_conv2d_fwd_batch): for independent layers that are individually too small to fill the GPU."""
+    deferred = [x for x in deferred if x is not None]
+    lib = _lib.load()
+    for i in range(0, len(deferred), MAX_BATCH):
+        chunk = deferred[i:i + MAX_BATCH]
+        arr = (ConvDesc * len(chunk))()
+        for j, (d, _) in enumerate(chunk):
+            ctypes.memmove(ctypes.addressof(arr[j]), ctypes.addressof(d), ctypes.sizeof(ConvDesc))
+        _lib.check(lib.dhd_conv2d_fwd_batch(arr, len(chunk), _stream()), 'conv2d_fwd_batch')
+    return [k for _, k in deferred]
 
 
 def predictor_tail(x, w1, b1, w2, b2, Dz, n_cls, logits=None, occ=None, transpose_xy=True):

@@ -171,12 +171,14 @@ class HeightNetEngine:
         h = linear_rows(h, self.se_r_w, self.se_r_b, 'relu')
         return linear_rows(h, self.se_e_w, self.se_e_b, 'sigmoid')
 
-    def __call__(self, x, mlp_input, softmax=True, hook=None, gate=None):
+    def __call__(self, x, mlp_input, softmax=True, hook=None, gate=None, batch_with=None):
         """x: Act (B*N, 256, fH, fW); returns height (B*N, H, fH, fW) fp32 NCHW (softmax-ed
         unless softmax=False, which gives the raw HeightNet output the reference returns).
         hook: optional callable run once after the ASPP branches are enqueued (the pipeline forks the
         geometry / binning kernels onto a side stream there, so they overlap the tail of this network).
-        gate: the result of self.gate(mlp_input) when the caller computed it ahead (on another stream)."""
+        gate: the result of self.gate(mlp_input) when the caller computed it ahead (on another stream).
+        batch_with: deferred convolutions (D.conv2d(..., defer=True)) that read other tensors and ride in the launch
+        of the first BasicBlock convolution (the pipeline passes depth_net's 1x1 here)."""
         N, H, W, C, P, dev = x.N, x.H, x.W, self.C, self.parts, x.data.device
         new = lambda c: D.Act.empty(N, H, W, c, P, dev)
         nhwc = D.nhwc_strides(C, H, W)
@@ -185,12 +187,12 @@ class HeightNetEngine:
         h = new(C)
         if P == 1 and os.environ.get('DHD_BF16_RESIDUAL', '1') != '0':
             self.reduce(x, [dict(act='relu', out_act=h)], img_gate=gate)
-            return self.trunk(h, None, softmax, hook)
+            return self.trunk(h, None, softmax, hook, batch_with)
         h32 = torch.empty(N, H, W, C, device=dev)
         self.reduce(x, [dict(act='relu', out_act=h, out_f32=(h32, nhwc))], img_gate=gate)
-        return self.trunk(h, h32, softmax, hook)
+        return self.trunk(h, h32, softmax, hook, batch_with)
 
-    def trunk(self, h, h32, softmax=True, hook=None):
+    def trunk(self, h, h32, softmax=True, hook=None, batch_with=None):
         """BasicBlocks -> ASPP -> DCN -> 1x1 head on the gated feature map (Act + its fp32 copy)."""
         N, H, W, C, P, dev = h.N, h.H, h.W, self.C, self.parts, h.data.device
         new = lambda c: D.Act.empty(N, H, W, c, P, dev)
@@ -205,7 +207,11 @@ class HeightNetEngine:
                 if ds is not None:
                     idn = new(C)
                     ds(h, [dict(out_act=idn)])
-                c1(h, [dict(act='relu', out_act=t)])
+                if batch_with:
+                    D.conv2d_batch([c1(h, [dict(act='relu', out_act=t)], defer=True)] + list(batch_with))
+                    batch_with = None
+                else:
+                    c1(h, [dict(act='relu', out_act=t)])
                 h2 = new(C)
                 c2(t, [dict(act='relu', out_act=h2)], residual_act=idn)
                 h = h2
@@ -213,15 +219,22 @@ class HeightNetEngine:
             if ds is not None:                       # identity path = 1x1 convolution of the concatenated input
                 h32 = torch.empty(N, H, W, C, device=dev)
                 ds(h, [dict(out_f32=(h32, nhwc))])
-            c1(h, [dict(act='relu', out_act=t)])
+            if batch_with:
+                D.conv2d_batch([c1(h, [dict(act='relu', out_act=t)], defer=True)] + list(batch_with))
+                batch_with = None
+            else:
+                c1(h, [dict(act='relu', out_act=t)])
             h2, h2_32 = new(C), torch.empty(N, H, W, C, device=dev)
             c2(t, [dict(act='relu', out_act=h2, out_f32=(h2_32, nhwc))], residual=(h32, nhwc[:3]))
             h, h32 = h2, h2_32
+        if batch_with:                               # no BasicBlock took them along
+            D.conv2d_batch(list(batch_with))
         if self.aspp is not None:
             mid = self.aspp_mid
             cat = new(4 * mid)
-            for b, conv in enumerate(self.aspp_branches):
-                conv(h, [dict(act='relu', out_act=cat.slice(b * mid, (b + 1) * mid))])
+            # the four branches read the same map and are 132 tiles each at DHD-S size: one persistent launch
+            D.conv2d_batch([conv(h, [dict(act='relu', out_act=cat.slice(b * mid, (b + 1) * mid))], defer=True)
+                            for b, conv in enumerate(self.aspp_branches)])
             if hook is not None:
                 hook()
                 hook = None
@@ -240,10 +253,9 @@ class HeightNetEngine:
                 _stream()), 'dcn_im2col')
             out = new(C)
             cg = C // g
-            for gi in range(g):
-                D.conv2d(col.slice(gi * k * k * cg, (gi + 1) * k * k * cg), self.dcn_w[gi], cg,
-                         precision=self.precision,
-                         segs=[dict(out_act=out.slice(gi * cg, (gi + 1) * cg))])
+            D.conv2d_batch([D.conv2d(col.slice(gi * k * k * cg, (gi + 1) * k * k * cg), self.dcn_w[gi], cg,
+                                     precision=self.precision, defer=True,
+                                     segs=[dict(out_act=out.slice(gi * cg, (gi + 1) * cg))]) for gi in range(g)])
             h = out
         if hook is not None:
             hook()
@@ -338,13 +350,15 @@ class DepthHeadEngine:
         self.D = n_depth
         self.C = self.conv.Cout - n_depth
 
-    def __call__(self, x):
+    def __call__(self, x, defer=False):
+        """defer=True: returns (depth, feat, deferred convolution) -- the caller launches it inside a batch."""
         N, H, W, dev = x.N, x.H, x.W, x.data.device
         depth = torch.empty(N, self.D, H, W, device=dev)
         feat = torch.empty(N, H, W, self.C, device=dev)
-        self.conv(x, [dict(c_lo=0, c_hi=self.D, act='softmax', out_f32=(depth, D.nchw_strides(self.D, H, W))),
-                      dict(c_lo=self.D, c_hi=self.D + self.C, out_f32=(feat, D.nhwc_strides(self.C, H, W)))])
-        return depth, feat
+        r = self.conv(x, [dict(c_lo=0, c_hi=self.D, act='softmax', out_f32=(depth, D.nchw_strides(self.D, H, W))),
+                          dict(c_lo=self.D, c_hi=self.D + self.C, out_f32=(feat, D.nhwc_strides(self.C, H, W)))],
+                      defer=defer)
+        return (depth, feat, r) if defer else (depth, feat)
 
 
 class SFAEngine:

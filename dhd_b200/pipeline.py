@@ -235,9 +235,10 @@ class HotPathStep:
                 self.plan.prepare(frustum=self.frustum, cam_mats=cam_mats,
                                   deterministic=self.deterministic, workspace=self.workspace)
         xa = D.pack_input(s['x'].view(B * N, self.Cin, self.fH, self.fW), self.parts)
-        depth, feat = self.depth_engine(xa)
+        # depth_net's 1x1 (132 tiles) rides in the launch of HeightNet's first BasicBlock convolution
+        depth, feat, depth_conv = self.depth_engine(xa, defer=True)
         main.wait_event(gate_ready)
-        height = self.height_engine(xa, mlp, softmax=True, hook=fork_prepare, gate=gate)
+        height = self.height_engine(xa, mlp, softmax=True, hook=fork_prepare, gate=gate, batch_with=[depth_conv])
         pixmask = height_to_mask(height, self.cfg['height_range'], self.cfg['mask_range'])
         main.wait_stream(self._prep_stream)
         self._last = {'depth': depth, 'feat': feat, 'height': height, 'pixmask': pixmask}

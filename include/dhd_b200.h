@@ -155,6 +155,7 @@ size_t dhd_mghs_workspace_count_offset(const dhd_mghs_cfg* cfg);
 #define DHD_CONV_MAX_TAPS 9
 #define DHD_CONV_MAX_TERMS 6
 #define DHD_CONV_MAX_SEGS 2
+#define DHD_CONV_MAX_BATCH 4   /* convolutions per dhd_conv2d_fwd_batch launch */
 
 enum {
   DHD_ACT_NONE = 0,
@@ -221,6 +222,18 @@ typedef struct dhd_conv_desc {
 } dhd_conv_desc;
 
 int dhd_conv2d_fwd(const dhd_conv_desc* desc, void* stream);
+/* n (<= DHD_CONV_MAX_BATCH) independent convolutions in ONE persistent launch: `descs` is an array of n descriptors
+ * (same contract as dhd_conv2d_fwd each).  For layers that are individually too small to fill the GPU and do not
+ * depend on each other: the four ASPP branches (depthnet.py:87-106), the groups of the deformable convolution,
+ * depth_net next to HeightNet's reduce_conv (lss_heightmap.py:482-487 -- both read the image feature).  Outputs of
+ * one problem must not be inputs of another. */
+int dhd_conv2d_fwd_batch(const dhd_conv_desc* descs, int n, void* stream);
+/* Layers with Cout > 128 and shared weights run on CTA PAIRS (clusters of two CTAs, tcgen05.mma.cta_group::2, M = 256:
+ * each CTA stages its own 128 pixels and half of the weight tile) where that pays: K = taps*Cin >= 1024 and at
+ * least four tiles per SM (mode 1, the default).  mode 0: never; mode 2: wherever the kernel supports it; mode < 0
+ * only queries.  Returns the previous setting (initially 1, or the DHD_CONV_CTA2 environment variable).  A/B switch
+ * for tests and benchmarks -- results are bit-identical either way. */
+int dhd_conv_pair_mode(int mode);
 
 /* ---- backward of the dense layers ------------------------------------------------------
  * (torch autograd of nn.Conv2d / nn.Linear in the modules listed above; the reference trains them

@@ -43,9 +43,53 @@ def wgrad():
         print('%-40s %-7s %8.1f us  %7.1f TFLOP/s algorithmic' % (name, 'wgrad', ms * 1e3, flops / ms / 1e9), flush=True)
 
 
+def pair_ab():
+    """CTA pairs (tcgen05.mma.cta_group::2) against one-CTA tiles, per layer shape: 20 launches captured in a CUDA
+    graph (no host time in the figure), replayed once (burst) and back to back for ~1 s (sustained clocks)."""
+    from dhd_b200 import _lib
+    lib = _lib.load()
+    for name, N, Cin, Cout, H, W, k, dil in SHAPES + [('predictor 3x3 256->256 @4x200x200 (2nd)', 4, 256, 256, 200, 200, 3, 1)]:
+        x = D.Act.empty(N, H, W, Cin, 1, 'cuda')
+        x.data.normal_()
+        w = torch.randn(Cout, k * k, 1, Cin, device='cuda').to(torch.bfloat16)
+        out = D.Act.empty(N, H, W, (Cout + 63) // 64 * 64, 1, 'cuda')
+        res = {}
+        for mode in (0, 2):
+            lib.dhd_conv_pair_mode(mode)
+            run = lambda: D.conv2d(x, w, Cout, ksize=k, dilation=dil, precision='bf16', segs=[dict(act='relu', out_act=out)])
+            run()
+            torch.cuda.synchronize()
+            it = 20
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for _ in range(it):
+                    run()
+            g.replay()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            g.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            burst = e0.elapsed_time(e1) / it
+            reps = max(1, int(1000.0 / (burst * it)))
+            e0.record()
+            for _ in range(reps):
+                g.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            res[mode] = (burst * 1e3, e0.elapsed_time(e1) / (it * reps) * 1e3)
+        lib.dhd_conv_pair_mode(1)
+        flops = 2.0 * N * H * W * Cout * Cin * k * k
+        print('%-42s one-CTA %7.1f us burst %7.1f us sustained (%6.1f TF/s) | pairs %7.1f us burst %7.1f us sustained (%6.1f TF/s)' %
+              (name, res[0][0], res[0][1], flops / res[0][1] / 1e6, res[2][0], res[2][1], flops / res[2][1] / 1e6), flush=True)
+
+
 def main():
     if sys.argv[1:] == ['wgrad']:
         return wgrad()
+    if sys.argv[1:] == ['pair']:
+        return pair_ab()
     precs = sys.argv[1:] or ['bf16', 'bf16x3', 'fp32']
     for name, N, Cin, Cout, H, W, k, dil in SHAPES:
         for prec in precs:

@@ -132,6 +132,78 @@ def test_conv_per_image_weights_and_bf16_residual(cuda_lib):
     assert (out3.permute(0, 3, 1, 2).cpu() - ref3).abs().max() <= 2e-5 * ref3.abs().max() + 2e-5
 
 
+@pytest.mark.parametrize('shape', [(2, 200, 200, 256, 256, 3, 1), (6, 16, 44, 256, 256, 3, 1), (1, 24, 40, 512, 320, 1, 1),
+                                   (3, 50, 50, 128, 512, 3, 6), (1, 33, 21, 64, 160, 3, 1), (1, 8, 16, 64, 256, 1, 1)])
+def test_conv_cta_pair_kernel_is_bit_equal_to_single_cta(cuda_lib, shape):
+    """tcgen05.mma.cta_group::2 path (clusters of two CTAs, M = 256, half of the weight tile per CTA) == the one-CTA
+    kernel, bit for bit: odd tile counts (a pair with a missing half), several N tiles, dilated taps that are dead for
+    one tile of a pair only, a single tile, bias / ReLU / bf16 residual epilogues, and against torch."""
+    from dhd_b200 import _lib
+    from dhd_b200 import dense as D
+    N, H, W, Cin, Cout, k, dil = shape
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(N, Cin, H, W, generator=g).bfloat16().float()
+    w = (torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).bfloat16().float()
+    r = torch.randn(N, Cout, H, W, generator=g).bfloat16().float()
+    bias = torch.randn(Cout, generator=g)
+    xa, ra, wq = D.pack_input(x.cuda(), 1), D.pack_input(r.cuda(), 1), D.pack_weight(w.cuda(), 1)
+    lib = _lib.load()
+    outs = []
+    prev = lib.dhd_conv_pair_mode(-1)
+    try:
+        for mode in (2, 0):
+            lib.dhd_conv_pair_mode(mode)
+            o16 = D.Act.empty(N, H, W, (Cout + 63) // 64 * 64, 1, 'cuda')
+            o16.data.zero_()
+            o32 = torch.empty(N, H, W, Cout, device='cuda')
+            D.conv2d(xa, wq, Cout, ksize=k, dilation=dil, precision='bf16', bias=bias.cuda(), residual_act=ra if Cout % 64 == 0 else None,
+                     segs=[dict(act='relu', out_act=o16)])
+            D.conv2d(xa, wq, Cout, ksize=k, dilation=dil, precision='bf16',
+                     segs=[dict(out_f32=(o32, D.nhwc_strides(Cout, H, W)))])
+            torch.cuda.synchronize()
+            outs.append((o16.data.clone(), o32))
+    finally:
+        lib.dhd_conv_pair_mode(prev)
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    ref = torch.nn.functional.conv2d(x.cuda(), w.cuda(), padding=dil * (k // 2), dilation=dil)
+    err = (outs[0][1].permute(0, 3, 1, 2) - ref).abs().max()
+    assert float(err) <= 1e-4 * float(ref.abs().max()) + 1e-5, float(err)
+
+
+def test_conv_batch_launch_is_bit_equal_to_single_launches(cuda_lib):
+    """dhd_conv2d_fwd_batch: four heterogeneous convolutions (1x1, dilated 3x3 with dead taps, a narrow softmax head
+    with two segments, a different input tensor) in one persistent launch == the same layers launched one by one."""
+    from dhd_b200 import dense as D
+    g = torch.Generator().manual_seed(7)
+    N, H, W = 3, 16, 44
+    xa = D.pack_input(torch.randn(N, 256, H, W, generator=g).cuda(), 1)
+    xb = D.pack_input(torch.randn(N, 128, H, W, generator=g).cuda(), 1)
+    mk = lambda co, ci, k: D.pack_weight((torch.randn(co, ci, k, k, generator=g) / (ci * k * k) ** 0.5).cuda(), 1)
+    w1, w2, w3, w4 = mk(256, 256, 1), mk(256, 256, 3), mk(108, 256, 1), mk(192, 128, 3)
+    bias = torch.randn(256, generator=g).cuda()
+
+    def layers(defer):
+        o1 = D.Act.empty(N, H, W, 256, 1, 'cuda')
+        o2 = D.Act.empty(N, H, W, 256, 1, 'cuda')
+        dep, ctx = torch.empty(N, 44, H, W, device='cuda'), torch.empty(N, H, W, 64, device='cuda')
+        o4 = torch.empty(N, H, W, 192, device='cuda')
+        r = [D.conv2d(xa, w1, 256, precision='bf16', bias=bias, segs=[dict(act='relu', out_act=o1)], defer=defer),
+             D.conv2d(xa, w2, 256, ksize=3, dilation=18, precision='bf16', segs=[dict(act='relu', out_act=o2)], defer=defer),
+             D.conv2d(xa, w3, 108, precision='bf16', defer=defer,
+                      segs=[dict(c_lo=0, c_hi=44, act='softmax', out_f32=(dep, D.nchw_strides(44, H, W))),
+                            dict(c_lo=44, c_hi=108, out_f32=(ctx, D.nhwc_strides(64, H, W)))]),
+             D.conv2d(xb, w4, 192, ksize=3, precision='bf16', defer=defer,
+                      segs=[dict(out_f32=(o4, D.nhwc_strides(192, H, W)))])]
+        return r, (o1.data, o2.data, dep, ctx, o4)
+    _, single = layers(False)
+    deferred, batched = layers(True)
+    D.conv2d_batch(deferred)
+    torch.cuda.synchronize()
+    for a, b, what in zip(single, batched, ('1x1', 'dilated 3x3', 'depth softmax', 'context', '3x3 on another input')):
+        assert torch.equal(a, b), what
+    assert float(batched[2].sum(1).sub(1).abs().max()) < 1e-5
+
+
 def test_sfa_fold_gate_and_bf16_blend_kernels(cuda_lib):
     """dhd_sfa_fold_gate / dhd_sfa_blend_b16 against their definitions (mix.py:41-57)."""
     import ctypes
