@@ -52,6 +52,8 @@ _SIGNATURES = {
     'dhd_conv2d_fwd': (ctypes.c_int, [_P, _P]),
     'dhd_conv2d_fwd_batch': (ctypes.c_int, [_P, _I, _P]),
     'dhd_conv_pair_mode': (ctypes.c_int, [_I]),
+    'dhd_conv2d_stat_rows': (ctypes.c_int, [_P]),
+    'dhd_colsum_finish': (ctypes.c_int, [_P, _I, _I, _P, _P]),
     'dhd_conv2d_wgrad_workspace_bytes': (ctypes.c_size_t, [_P]),
     'dhd_conv2d_wgrad': (ctypes.c_int, [_P, _P]),
     'dhd_act_bwd_workspace_bytes': (ctypes.c_size_t, [_I]),

@@ -95,6 +95,14 @@ static int validate_conv(const dhd_conv_desc* d) {
                     d->res_b16_coff % 8 == 0 && d->residual == nullptr && (d->stride == 0 || d->stride == 1),
                 "bf16 residual needs Cout % 32 == 0, 16-byte aligned rows, stride 1 and no fp32 residual");
   DHD_REQUIRE(d->w_image_rows == 0 || d->w_image_rows >= d->Cout, "w_image_rows must be 0 or >= Cout");
+  if (d->stat_partial != nullptr) {
+    const dhd_conv_seg& sg = d->seg[0];
+    DHD_REQUIRE(d->n_seg == 1 && sg.c_lo == 0 && sg.c_hi == d->Cout && sg.out_b16 != nullptr && sg.out_f32 == nullptr &&
+                    sg.b16_parts == 1 && sg.act != DHD_ACT_SOFTMAX && d->mix_x == nullptr && d->Cout % 2 == 0 &&
+                    sg.b16_ld % 8 == 0 && sg.b16_coff % 8 == 0 && sg.b16_sX % 8 == 0 && sg.b16_sY % 8 == 0 &&
+                    sg.b16_sN % 8 == 0 && ((uintptr_t)sg.out_b16 & 15) == 0 && ((uintptr_t)d->stat_partial & 7) == 0,
+                "fused statistics: one single-part bf16 output over all channels (16-byte aligned rows), even Cout");
+  }
   DHD_REQUIRE(d->stride == 0 || d->stride == 1 || d->stride == 2, "stride must be 1 or 2");
   if (d->stride == 2) {
     DHD_REQUIRE(d->in_H > 0 && d->in_W > 0 && d->H <= (d->in_H + 1) / 2 && d->W <= (d->in_W + 1) / 2,
@@ -135,3 +143,8 @@ extern "C" int dhd_conv2d_fwd_batch(const dhd_conv_desc* descs, int n, void* str
 }
 
 extern "C" int dhd_conv_pair_mode(int mode) { return conv2_pair_mode(mode); }
+
+extern "C" int dhd_conv2d_stat_rows(const dhd_conv_desc* d) {
+  if (d == nullptr || d->bw <= 0 || d->bh <= 0) return 0;
+  return ((d->W + d->bw - 1) / d->bw) * ((d->H + d->bh - 1) / d->bh) * d->N;
+}

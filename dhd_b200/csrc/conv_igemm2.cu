@@ -37,7 +37,7 @@ struct Cfg2 {
   static constexpr int kStages = CTAS == 2 ? 4 : (NT == 256 ? 3 : 4);
   static constexpr uint32_t kBBytes = (NT / CTAS) * kK2 * 2;
   static constexpr uint32_t kStageBytes = kA2Bytes + kBBytes;
-  static constexpr uint32_t kVecBytes = 3 * NT * 4;            // scale, bias(+img_bias), gate
+  static constexpr uint32_t kVecBytes = 3 * NT * 4 + 4 * 2048; // scale, bias(+img_bias), gate; statistics scratch per group
   static constexpr uint32_t kSmem = kStages * kStageBytes + 4 * kStageBufBytes + kVecBytes + 256 + 1024;
   static constexpr int kTmemCols = 2 * NT;
 };
@@ -114,6 +114,7 @@ conv_igemm2_kernel(const __grid_constant__ ConvBatch<NP> B) {
   float* s_scale = reinterpret_cast<float*>(gen + (vec_base - base));
   float* s_bias = s_scale + NT;
   float* s_gate = s_bias + NT;
+  float* s_stat = s_gate + NT;          // [group][4 warps][64 channels][sum, sum of squares]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + (bar_base - base) + 8u * (2 * C::kStages + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -436,6 +437,11 @@ conv_igemm2_kernel(const __grid_constant__ ConvBatch<NP> B) {
 #pragma unroll
               for (int j = 0; j < 16; ++j) h[half * 16 + j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
             }
+            const bool stats = d.stat_partial != nullptr;
+            if (stats && !valid) {                // rows beyond the image border must not count (the TMA store clips them)
+#pragma unroll
+              for (int j = 0; j < 8; ++j) q[j] = make_uint4(0u, 0u, 0u, 0u);
+            }
             const uint32_t buf = gstage + (nstore % kBufPerGroup) * kStageBufBytes;
             if (tid == 0) tma_store_wait_read<kBufPerGroup - 1>();
             named_bar_sync(gbar, 128);
@@ -450,6 +456,41 @@ conv_igemm2_kernel(const __grid_constant__ ConvBatch<NP> B) {
               tma_store_commit();
             }
             ++nstore;
+            if (stats) {
+              // BatchNorm batch statistics of the layer output, from the staged tile (the bf16 values the consumer will
+              // read): warp w sums rows [32w, 32w+32) of the 64 channels, lane = channel pair (one bank per lane), the
+              // four warps meet in shared memory, and partial row `tile` = [sum | sum of squares][Cout] goes to global
+              // memory; dhd_colsum_finish adds the rows in fixed order
+              const int cp = tid & 31, qr = tid >> 5;
+              const uint8_t* tb = gen + (buf - base);
+              float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll 8
+              for (int rr = 0; rr < 32; ++rr) {
+                const int r = qr * 32 + rr;
+                const uint32_t wv = *reinterpret_cast<const uint32_t*>(tb + r * 128 + (((cp >> 2) ^ (r & 7)) << 4) + ((cp & 3) << 2));
+                const float lo = __uint_as_float(wv << 16), hi = __uint_as_float(wv & 0xFFFF0000u);
+                s0 += lo; q0 = fmaf(lo, lo, q0);
+                s1 += hi; q1 = fmaf(hi, hi, q1);
+              }
+              float4* sred = reinterpret_cast<float4*>(s_stat + grp * 512);
+              sred[qr * 32 + cp] = make_float4(s0, q0, s1, q1);          // channel 2cp: (sum, sq), channel 2cp+1: (sum, sq)
+              named_bar_sync(gbar, 128);
+              const int ch = n0 + wb * 64 + tid;
+              if (tid < 64 && ch < d.Cout) {
+                const float2* sr = reinterpret_cast<const float2*>(s_stat + grp * 512);
+                float2 a = sr[tid];
+#pragma unroll
+                for (int w4 = 1; w4 < 4; ++w4) {                         // fixed order
+                  const float2 b = sr[w4 * 64 + tid];
+                  a.x += b.x;
+                  a.y += b.y;
+                }
+                const int mt_idx = CTAS == 2 ? 2 * (tile / P.n_tiles) + (int)crank : tile / P.n_tiles;
+                float* pr = d.stat_partial + (size_t)mt_idx * 2 * d.Cout + ch;
+                pr[0] = a.x;
+                pr[d.Cout] = a.y;
+              }
+            }
           }
           continue;
         }
@@ -863,6 +904,8 @@ static int conv2_fill(const dhd_conv_desc* d, EncodeTiledFn2 enc, Conv2Maps& map
                              ? 1 : 0;
     }
   }
+  if (d->stat_partial != nullptr && P.seg_b16_wide[0] == 0)
+    return fail(DHD_EUNSUPPORTED, "%s", "fused statistics need the 64-channel TMA store path (DHD_CONV_WIDE_STORE=0 or a bad view?)");
   P.tiles_w = (d->W + d->bw - 1) / d->bw;
   P.tiles_h = (d->H + d->bh - 1) / d->bh;
   P.n_tiles = (d->Cout + NT - 1) / NT;

@@ -22,6 +22,14 @@ __device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&v)[8]) {
     v[2 * j + 1] = __high2float(h[j]);
   }
 }
+__device__ __forceinline__ void unpack8(const uint4& q, float (&v)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    v[2 * j] = __low2float(h[j]);
+    v[2 * j + 1] = __high2float(h[j]);
+  }
+}
 __device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&v)[8]) {
   uint4 q;
   __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&q);
@@ -47,27 +55,47 @@ act_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int dy_ld, int dy_coff, con
 #pragma unroll
   for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
   if (ri < rpb) {
-    for (long r = r0 + ri; r < r1; r += rpb) {
-      float g[8], v[8];
-      load8(dy + r * dy_ld + dy_coff + gi * 8, g);
+    // two rows per trip: every load of both rows is issued before the first use (the kernel is a pure HBM stream; with
+    // one row per trip a thread had 32-48 bytes in flight and the launch reached 0.66 of the copy bandwidth)
+    const bool need_y = act != 0 || partial != nullptr;
+    for (long r = r0 + ri; r < r1; r += 2 * rpb) {
+      const long rb = r + rpb;
+      const bool two = rb < r1;
+      uint4 qg[2], qa[2], qv[2];
+      qg[0] = ld_nc_u4(dy + r * dy_ld + dy_coff + gi * 8);
+      if (two) qg[1] = ld_nc_u4(dy + rb * dy_ld + dy_coff + gi * 8);
       if (add != nullptr) {            // a second gradient path into the same tensor (residual connection)
-        float a[8];
-        load8(add + r * add_ld + add_coff + gi * 8, a);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) g[j] += a[j];
+        qa[0] = ld_nc_u4(add + r * add_ld + add_coff + gi * 8);
+        if (two) qa[1] = ld_nc_u4(add + rb * add_ld + add_coff + gi * 8);
       }
-      if (act != 0 || partial != nullptr) load8(y + r * y_ld + y_coff + gi * 8, v);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float d = 1.f;
-        if (act == 1) d = v[j] > 0.f ? 1.f : 0.f;
-        else if (act == 2) d = v[j] * (1.f - v[j]);
-        else if (act == 3) d = 1.f - __expf(-v[j]);
-        g[j] *= d;
-        s1[j] += g[j];
-        s2[j] += g[j] * v[j];
+      if (need_y) {
+        qv[0] = ld_nc_u4(y + r * y_ld + y_coff + gi * 8);
+        if (two) qv[1] = ld_nc_u4(y + rb * y_ld + y_coff + gi * 8);
       }
-      if (out != nullptr) store8(out + r * out_ld + out_coff + gi * 8, g);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (h == 1 && !two) break;
+        float g[8], v[8];
+        unpack8(qg[h], g);
+        if (add != nullptr) {
+          float a[8];
+          unpack8(qa[h], a);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) g[j] += a[j];
+        }
+        if (need_y) unpack8(qv[h], v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float d = 1.f;
+          if (act == 1) d = v[j] > 0.f ? 1.f : 0.f;
+          else if (act == 2) d = v[j] * (1.f - v[j]);
+          else if (act == 3) d = 1.f - __expf(-v[j]);
+          g[j] *= d;
+          s1[j] += g[j];
+          s2[j] += g[j] * v[j];
+        }
+        if (out != nullptr) store8(out + (h == 0 ? r : rb) * out_ld + out_coff + gi * 8, g);
+      }
     }
   }
   if (partial == nullptr) return;
@@ -971,6 +999,39 @@ extern "C" int dhd_act_bwd(const void* dy, int dy_ld, int dy_coff, const void* y
     colsum_reduce_kernel<<<(2 * C * 32 + 255) / 256, 256, 0, st>>>(workspace, nblocks, 2 * C, colsum);
     DHD_CUDA_LAUNCH_CHECK("colsum_reduce");
   }
+  return DHD_OK;
+}
+
+// sums[i] = sum over rows of partial[row][i], rows in a fixed order: a block owns 32 columns (lane = column: 128-byte
+// coalesced row reads), its 8 warps stride over the rows, and the 8 partial sums meet in shared memory
+__global__ void __launch_bounds__(256)
+colsum_finish_kernel(const float* __restrict__ partial, int rows, int n, float* __restrict__ sums) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;
+  float a0 = 0.f, a1 = 0.f;
+  if (i < n) {
+    int r = w;
+    for (; r + 8 < rows; r += 16) {
+      a0 += __ldg(partial + (size_t)r * n + i);
+      a1 += __ldg(partial + (size_t)(r + 8) * n + i);
+    }
+    if (r < rows) a0 += __ldg(partial + (size_t)r * n + i);
+  }
+  __shared__ float sh[8][32];
+  sh[w][lane] = a0 + a1;
+  __syncthreads();
+  if (w == 0 && i < n) {
+    float t = sh[0][lane];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) t += sh[k][lane];
+    sums[i] = t;
+  }
+}
+
+extern "C" int dhd_colsum_finish(const float* partial, int rows, int n, float* sums, void* stream) {
+  DHD_REQUIRE(partial && sums && rows > 0 && n > 0, "bad arguments");
+  colsum_finish_kernel<<<(n + 31) / 32, 256, 0, (cudaStream_t)stream>>>(partial, rows, n, sums);
+  DHD_CUDA_LAUNCH_CHECK("colsum_finish");
   return DHD_OK;
 }
 

@@ -57,7 +57,7 @@ class ConvDesc(ctypes.Structure):
         ('mix_x', ctypes.c_void_p), ('mix_ld', ctypes.c_int32), ('mix_coff', ctypes.c_int32),
         ('mix_parts', ctypes.c_int32), ('mix_part_stride', ctypes.c_int32), ('mix_a1', ctypes.c_void_p),
         ('w_image_rows', ctypes.c_int32), ('res_b16_ld', ctypes.c_int32), ('res_b16_coff', ctypes.c_int32),
-        ('res_b16', ctypes.c_void_p),
+        ('res_b16', ctypes.c_void_p), ('stat_partial', ctypes.c_void_p),
     ]
 
 
@@ -212,7 +212,7 @@ def tile_box(H, W):
 
 def conv2d(x, weight, Cout, ksize=1, dilation=1, precision='fp32', scale=None, bias=None,
            img_bias=None, img_gate=None, residual=None, segs=None, stride=1, sfa_mix=None, taps=None,
-           out_hw=None, residual_act=None, image_weights=False, defer=False):
+           out_hw=None, residual_act=None, image_weights=False, defer=False, stats=None):
     """One fused convolution.  x: Act; weight: pack_weight() result with PRECISIONS[precision]
     parts; segs: list of dicts {c_lo, c_hi, act, out_f32 (tensor, strides (sN,sY,sX,sC)),
     out_act (Act or Act.slice), out_view (sN, sY, sX, offset): pixel strides / start offset in bf16
@@ -305,10 +305,33 @@ def conv2d(x, weight, Cout, ksize=1, dilation=1, precision='fp32', scale=None, b
             if view is not None:
                 g.b16_sN, g.b16_sY, g.b16_sX = view[0], view[1], view[2]
             keep.append(a.data)
+    if stats is not None:                    # (2, Cout) fp32: [sum, sum of squares] of the bf16 output per channel
+        lib = _lib.load()
+        rows = lib.dhd_conv2d_stat_rows(ctypes.byref(d))
+        part = _stat_workspace(x.data.device, rows * 2 * Cout * 4)
+        d.stat_partial = part.data_ptr()
+        keep.append(part)
+        if defer:
+            raise ValueError('stats with defer is not supported')
+        _lib.check(lib.dhd_conv2d_fwd(ctypes.byref(d), _stream()), 'conv2d_fwd')
+        _lib.check(lib.dhd_colsum_finish(part.data_ptr(), rows, 2 * Cout, stats.data_ptr(), _stream()), 'colsum_finish')
+        return keep
     if defer:
         return d, keep
     _lib.check(_lib.load().dhd_conv2d_fwd(ctypes.byref(d), _stream()), 'conv2d_fwd')
     return keep
+
+
+_STAT_WS = {}
+
+
+def _stat_workspace(device, nbytes):
+    key = (str(device), torch.cuda.current_stream().cuda_stream)
+    ws = _STAT_WS.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 22), dtype=torch.uint8, device=device)
+        _STAT_WS[key] = ws
+    return ws
 
 
 MAX_BATCH = 4

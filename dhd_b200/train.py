@@ -22,6 +22,9 @@ ACT_ID = {None: 0, 'none': 0, 'relu': 1, 'sigmoid': 2, 'softplus': 3}
 # parameters fixed, folded into the convolution epilogue) or 'batch' (torch's training mode: batch statistics,
 # trainable gamma / beta, running statistics updated).  Read when a trainer is constructed.
 BN_MODE = 'frozen'
+# batch-statistics BatchNorm: sums from the convolution epilogue (True) or from a separate pass over the output (A/B)
+import os as _os
+FUSED_BN_STATS = _os.environ.get('DHD_FUSED_BN_STATS', '1') != '0'
 
 
 def set_bn_mode(mode):
@@ -156,9 +159,18 @@ class _TrainConv:
                 self._dyraw.data.zero_()
             self._raw_key = key
         raw = self._raw
-        D.conv2d(x, self.w_fwd, self.Cout, ksize=self.ksize, dilation=self.dilation, precision='bf16', bias=self.bias,
-                 img_bias=img_bias, segs=[dict(out_act=raw)], stride=self.stride)
-        _, sums = act_bwd(raw, raw, None, want_sums=True, write=False)            # [sum raw, sum raw^2]
+        if FUSED_BN_STATS and self.Cout % 2 == 0:
+            # [sum raw, sum raw^2] per channel come out of the convolution's epilogue (per-tile partials of the staged
+            # bf16 tile + a fixed-order finish): the separate read of `raw` is gone
+            if getattr(self, '_sums', None) is None:
+                self._sums = torch.empty(2, self.Cout, device=x.data.device)
+            sums = self._sums
+            D.conv2d(x, self.w_fwd, self.Cout, ksize=self.ksize, dilation=self.dilation, precision='bf16', bias=self.bias,
+                     img_bias=img_bias, segs=[dict(out_act=raw)], stride=self.stride, stats=sums)
+        else:
+            D.conv2d(x, self.w_fwd, self.Cout, ksize=self.ksize, dilation=self.dilation, precision='bf16', bias=self.bias,
+                     img_bias=img_bias, segs=[dict(out_act=raw)], stride=self.stride)
+            _, sums = act_bwd(raw, raw, None, want_sums=True, write=False)            # [sum raw, sum raw^2]
         M = float(x.N * oH * oW)
         if getattr(self, '_bn_buf', None) is None:
             self._bn_buf = torch.empty(7, self.Cout, device=x.data.device)       # scale, shift, mean, invstd, k1, k2, k3

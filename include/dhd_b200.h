@@ -219,6 +219,12 @@ typedef struct dhd_conv_desc {
    * pre-activation value like `residual`; the bf16 speed mode's identity paths.  NULL = off. */
   int32_t res_b16_ld, res_b16_coff;
   const void* res_b16;
+  /* BatchNorm batch statistics fused into the epilogue (training mode: the convolution writes its raw bf16 output and
+   * torch's BatchNorm needs sum / sum of squares per channel over all pixels).  NULL = off.  Otherwise fp32
+   * [dhd_conv2d_stat_rows(desc)][2][Cout]: per-tile partial sums of the bf16-rounded output, [.][0][c] = sum,
+   * [.][1][c] = sum of squares, written completely; dhd_colsum_finish adds the rows in fixed order.  Requires one
+   * single-part bf16 output segment over all channels, no activation-dependent consumers, Cout even. */
+  float* stat_partial;
 } dhd_conv_desc;
 
 int dhd_conv2d_fwd(const dhd_conv_desc* desc, void* stream);
@@ -227,6 +233,10 @@ int dhd_conv2d_fwd(const dhd_conv_desc* desc, void* stream);
  * depend on each other: the four ASPP branches (depthnet.py:87-106), the groups of the deformable convolution,
  * depth_net next to HeightNet's reduce_conv (lss_heightmap.py:482-487 -- both read the image feature).  Outputs of
  * one problem must not be inputs of another. */
+/* rows of dhd_conv_desc.stat_partial for this layer (one per 128-pixel tile) */
+int dhd_conv2d_stat_rows(const dhd_conv_desc* desc);
+/* sums[i] = sum over rows of partial[row][i], i < n, rows added in a fixed order (deterministic) */
+int dhd_colsum_finish(const float* partial, int rows, int n, float* sums, void* stream);
 int dhd_conv2d_fwd_batch(const dhd_conv_desc* descs, int n, void* stream);
 /* Layers with Cout > 128 and shared weights run on CTA PAIRS (clusters of two CTAs, tcgen05.mma.cta_group::2, M = 256:
  * each CTA stages its own 128 pixels and half of the weight tile) where that pays: K = taps*Cin >= 1024 and at

@@ -59,3 +59,34 @@ def test_dgrad_matches_torch(cuda_lib, N, H, W, Cin, Cout, k, dil):
     got = out.permute(0, 3, 1, 2)
     scale = float(want.abs().max())
     assert torch.allclose(got, want, rtol=2e-3, atol=2e-4 * scale), float((got - want).abs().max()) / scale
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('shape', [(2, 37, 53, 128, 256, 3), (4, 16, 44, 256, 96, 1), (1, 200, 200, 64, 320, 3)])
+def test_conv_epilogue_batchnorm_statistics(cuda_lib, shape):
+    """dhd_conv_desc.stat_partial + dhd_colsum_finish: per-channel sum / sum of squares of the layer's bf16 output
+    (BatchNorm batch statistics) == the same sums taken from the stored output, in both the one-CTA and the CTA-pair
+    kernel; partial tiles at the image border and a channel count that is not a multiple of 64 included."""
+    from dhd_b200 import _lib
+    from dhd_b200 import dense as D
+    N, H, W, Cin, Cout, k = shape
+    g = torch.Generator().manual_seed(3)
+    xa = D.pack_input(torch.randn(N, Cin, H, W, generator=g).cuda(), 1)
+    wq = D.pack_weight((torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).cuda(), 1)
+    bias = torch.randn(Cout, generator=g).cuda()
+    lib = _lib.load()
+    prev = lib.dhd_conv_pair_mode(-1)
+    try:
+        for mode in (0, 2):
+            lib.dhd_conv_pair_mode(mode)
+            out = D.Act.empty(N, H, W, (Cout + 63) // 64 * 64, 1, 'cuda')
+            out.data.zero_()
+            sums = torch.full((2, Cout), float('nan'), device='cuda')
+            D.conv2d(xa, wq, Cout, ksize=k, precision='bf16', bias=bias, segs=[dict(out_act=out)], stats=sums)
+            torch.cuda.synchronize()
+            y = out.data[..., :Cout].double()
+            want = torch.stack([y.sum((0, 1, 2)), (y * y).sum((0, 1, 2))])
+            err = (sums.double() - want).abs() / (want.abs() + 1.0)
+            assert float(err.max()) < 2e-5, (mode, float(err.max()))
+    finally:
+        lib.dhd_conv_pair_mode(prev)
