@@ -135,6 +135,7 @@ extern "C" size_t dhd_abi_sizeof(int which) {
     case 3: return sizeof(dhd_wgrad_desc);
     case 4: return sizeof(dhd_stereo_desc);
     case 5: return sizeof(dhd_predictor_tail_desc);
+    case 6: return sizeof(dhd_pack_desc);
     default: return 0;
   }
 }

@@ -185,6 +185,63 @@ wgrad_reduce_kernel(const float* __restrict__ partial, int splits, long n, int p
   dw[i] = accumulate ? dw[i] + a : a;
 }
 
+// dw_torch layout: dw is the parameter's gradient [Cout][cin_total][taps].  One thread per (co, ci) sums the slices
+// of its `taps` values (reads coalesced over ci), the block stages them in shared memory in output order and writes /
+// accumulates them back with consecutive threads on consecutive addresses (a thread-per-value mapping writes with a
+// stride of `taps` floats: 9x the sectors on a 3x3 layer).
+__global__ void __launch_bounds__(256)
+wgrad_reduce_torch_kernel(const float* __restrict__ partial, int splits, long n, const float* __restrict__ scale,
+                          float* __restrict__ dw, int accumulate, int Cout, int Cin, int taps, int cin_total, int cin_lo,
+                          int cin_used) {
+  __shared__ float stage[256 * DHD_CONV_MAX_TAPS];
+  // 32-bit index arithmetic throughout (host check: Cout * cin_total * taps < 2^31)
+  const unsigned p0 = blockIdx.x * 256u;
+  const unsigned npairs = (unsigned)Cout * (unsigned)cin_used;
+  const unsigned p = p0 + threadIdx.x;
+  if (p < npairs) {
+    const unsigned co = p / (unsigned)cin_used, ci = p - co * (unsigned)cin_used;
+    const float sc = scale != nullptr ? scale[co] : 1.f;
+    float acc[DHD_CONV_MAX_TAPS];
+#pragma unroll
+    for (int t = 0; t < DHD_CONV_MAX_TAPS; ++t) acc[t] = 0.f;
+    const size_t i0 = (size_t)co * taps * Cin + ci;
+    // slices in a fixed order, four at a time: every load of a group is issued before the first add (a 1x1 layer has
+    // one tile row of work items and up to 148 slices: one dependent load per trip made this pass latency-bound)
+    int s = 0;
+    for (; s + 4 <= splits; s += 4) {
+      float q[4][DHD_CONV_MAX_TAPS];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float* ps = partial + (size_t)(s + u) * n + i0;
+#pragma unroll
+        for (int t = 0; t < DHD_CONV_MAX_TAPS; ++t)
+          if (t < taps) q[u][t] = __ldg(ps + (size_t)t * Cin);
+      }
+#pragma unroll
+      for (int t = 0; t < DHD_CONV_MAX_TAPS; ++t)
+        if (t < taps) acc[t] += (q[0][t] + q[1][t]) + (q[2][t] + q[3][t]);
+    }
+    for (; s < splits; ++s) {
+      const float* ps = partial + (size_t)s * n + i0;
+#pragma unroll
+      for (int t = 0; t < DHD_CONV_MAX_TAPS; ++t)
+        if (t < taps) acc[t] += __ldg(ps + (size_t)t * Cin);
+    }
+#pragma unroll
+    for (int t = 0; t < DHD_CONV_MAX_TAPS; ++t)
+      if (t < taps) stage[threadIdx.x * taps + t] = acc[t] * sc;
+  }
+  __syncthreads();
+  const unsigned cnt = min(256u, npairs - p0) * (unsigned)taps;
+  for (unsigned k = threadIdx.x; k < cnt; k += 256u) {
+    const unsigned lp = k / (unsigned)taps, t = k - lp * (unsigned)taps;
+    const unsigned q = p0 + lp;
+    const unsigned co = q / (unsigned)cin_used, ci = q - co * (unsigned)cin_used;
+    const unsigned o = (co * (unsigned)cin_total + (unsigned)cin_lo + ci) * (unsigned)taps + t;
+    dw[o] = accumulate ? dw[o] + stage[k] : stage[k];
+  }
+}
+
 typedef CUresult (*EncodeTiledFnW)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
@@ -233,8 +290,12 @@ extern "C" int dhd_conv2d_wgrad(const dhd_wgrad_desc* d, void* stream) {
               "tile box must cover exactly 128 pixels");
   DHD_REQUIRE(d->x_ld % 8 == 0 && d->x_coff % 8 == 0 && d->dy_ld % 8 == 0 && d->dy_coff % 8 == 0,
               "channel offsets must be multiples of 8 (16-byte TMA alignment)");
-  DHD_REQUIRE(((uintptr_t)d->x & 15) == 0 && ((uintptr_t)d->dy & 15) == 0 && ((uintptr_t)d->dw & 15) == 0 &&
-                  ((uintptr_t)d->partial & 15) == 0, "pointers must be 16-byte aligned");
+  DHD_REQUIRE(((uintptr_t)d->x & 15) == 0 && ((uintptr_t)d->dy & 15) == 0 && ((uintptr_t)d->dw & 3) == 0 &&
+                  ((uintptr_t)d->partial & 15) == 0, "x / dy / partial must be 16-byte aligned");
+  if (d->dw_torch != 0)
+    DHD_REQUIRE(d->dw_cin_used > 0 && d->dw_cin_used <= d->Cin && d->dw_cin_lo >= 0 &&
+                    d->dw_cin_lo + d->dw_cin_used <= d->dw_cin_total &&
+                    (long)d->Cout * d->dw_cin_total * d->taps < (1L << 31), "dw_torch: bad input-channel window");
   DHD_REQUIRE(d->dy_coff + d->Cout <= d->dy_ld && d->x_coff + d->Cin <= d->x_ld, "channel range exceeds the row");
   DHD_REQUIRE(d->x_stride == 0 || d->x_stride == 1 || (d->x_stride == 2 && d->x_H >= 2 * d->H - 1 && d->x_W >= 2 * d->W - 1),
               "x_stride must be 1 or 2 (with the x_H x x_W grid covering the strided taps)");
@@ -279,8 +340,15 @@ extern "C" int dhd_conv2d_wgrad(const dhd_wgrad_desc* d, void* stream) {
   conv_wgrad_kernel<<<grid, kWgThreads, smem, st>>>(maps, P);
   DHD_CUDA_LAUNCH_CHECK("conv_wgrad");
   const long n = (long)d->Cout * d->taps * d->Cin;
-  wgrad_reduce_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(d->partial, P.splits, n, d->taps * d->Cin, d->scale,
-                                                              d->dw, d->accumulate);
+  if (d->dw_torch != 0) {
+    const long npairs = (long)d->Cout * d->dw_cin_used;
+    wgrad_reduce_torch_kernel<<<(int)((npairs + 255) / 256), 256, 0, st>>>(
+        d->partial, P.splits, n, d->scale, d->dw, d->accumulate, d->Cout, d->Cin, d->taps, d->dw_cin_total, d->dw_cin_lo,
+        d->dw_cin_used);
+  } else {
+    wgrad_reduce_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(d->partial, P.splits, n, d->taps * d->Cin, d->scale,
+                                                                d->dw, d->accumulate);
+  }
   DHD_CUDA_LAUNCH_CHECK("wgrad_reduce");
   return DHD_OK;
 }

@@ -133,6 +133,35 @@ colsum_reduce_kernel(const float* __restrict__ partial, int nblocks, int n, floa
   if (lane == 0) sums[i] = a;
 }
 
+// sums[i] = sum over rows of partial[row][i], rows in a fixed order: a block owns 32 columns (lane = column: 128-byte
+// coalesced row reads), its 32 warps stride over the rows with four independent loads in flight each, and the 32
+// partial sums meet in shared memory
+__global__ void __launch_bounds__(1024)
+colsum_finish_kernel(const float* __restrict__ partial, int rows, int n, float* __restrict__ sums) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (i < n) {
+    int r = w;
+    for (; r + 96 < rows; r += 128) {
+      a0 += __ldg(partial + (size_t)r * n + i);
+      a1 += __ldg(partial + (size_t)(r + 32) * n + i);
+      a2 += __ldg(partial + (size_t)(r + 64) * n + i);
+      a3 += __ldg(partial + (size_t)(r + 96) * n + i);
+    }
+    for (; r < rows; r += 32) a0 += __ldg(partial + (size_t)r * n + i);
+  }
+  __shared__ float sh[32][33];
+  sh[w][lane] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if (w == 0 && i < n) {
+    float t = sh[0][lane];
+#pragma unroll
+    for (int k = 1; k < 32; ++k) t += sh[k][lane];
+    sums[i] = t;
+  }
+}
+
 // ---- occupancy cross-entropy ---------------------------------------------------------------
 // norm[0] = sum over voxels of mask * class_weight[label]   (the reference's num_total_samples)
 __global__ void __launch_bounds__(256)
@@ -617,6 +646,91 @@ pack_conv_weights_kernel(const float* __restrict__ w, int Cout, int cin_total, i
 }
 
 
+struct PackBatch {
+  dhd_pack_desc d[DHD_PACK_MAX_BATCH];
+};
+// blockIdx.y = layer; same element mapping as pack_conv_weights_kernel
+__global__ void __launch_bounds__(256)
+pack_conv_weights_batch_kernel(const __grid_constant__ PackBatch B) {
+  const dhd_pack_desc& L = B.d[blockIdx.y];
+  const float* __restrict__ w = L.w;
+  const float* __restrict__ scale = L.scale;
+  __nv_bfloat16* __restrict__ fwd = (__nv_bfloat16*)L.fwd;
+  __nv_bfloat16* __restrict__ bwd = (__nv_bfloat16*)L.bwd;
+  const unsigned Cout = L.Cout, cin_total = L.cin_total, taps = L.taps, col_lo = L.col_lo, Cin = L.Cin, cin_pad = L.cin_pad,
+                 cout_pad = L.cout_pad;
+  const int bwd_mode = L.bwd_mode;
+  // 32-bit index arithmetic (host check: both element counts < 2^31): a 64-bit / or % costs ~100 instructions
+  const unsigned nf = fwd != nullptr ? Cout * taps * cin_pad : 0u;
+  const unsigned nb = bwd != nullptr ? Cin * taps * cout_pad : 0u;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < nf + nb; i += gridDim.x * blockDim.x) {
+    if (i < nf) {
+      const unsigned ci = i % cin_pad, r = i / cin_pad;
+      const unsigned t = r % taps, co = r / taps;
+      const float v = ci < Cin ? w[((size_t)co * cin_total + col_lo + ci) * taps + t] : 0.f;
+      fwd[i] = __float2bfloat16(v);
+    } else {
+      const unsigned j = i - nf;
+      const unsigned co = j % cout_pad, r = j / cout_pad;
+      unsigned ci, t;
+      if (bwd_mode == 0) {
+        t = r % taps;
+        ci = r / taps;
+      } else {
+        ci = r % Cin;
+        t = r / Cin;
+      }
+      float v = 0.f;
+      if (co < Cout) {
+        const unsigned ts = bwd_mode == 0 ? taps - 1 - t : t;
+        v = w[((size_t)co * cin_total + col_lo + ci) * taps + ts];
+        if (scale != nullptr) v *= scale[co];
+      }
+      bwd[j] = __float2bfloat16(v);
+    }
+  }
+}
+
+// torch.optim.AdamW, single tensor form (torch/optim/adamw.py _single_tensor_adamw): 4 values per thread
+__global__ void __launch_bounds__(256)
+adamw_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                  long n, float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2_sqrt,
+                  const float* __restrict__ grad_scale) {
+  const float gs = grad_scale != nullptr ? __ldg(grad_scale) : 1.f;
+  const float step_size = lr / bc1;
+  const long i4 = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i4 >= n) return;
+  float pv[4], gv[4], mv[4], vv[4];
+  const bool full = i4 + 4 <= n && ((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0);
+  if (full) {
+    *reinterpret_cast<float4*>(pv) = *reinterpret_cast<const float4*>(p + i4);
+    *reinterpret_cast<float4*>(gv) = *reinterpret_cast<const float4*>(g + i4);
+    *reinterpret_cast<float4*>(mv) = *reinterpret_cast<const float4*>(m + i4);
+    *reinterpret_cast<float4*>(vv) = *reinterpret_cast<const float4*>(v + i4);
+  } else {
+    for (int j = 0; j < 4; ++j)
+      if (i4 + j < n) { pv[j] = p[i4 + j]; gv[j] = g[i4 + j]; mv[j] = m[i4 + j]; vv[j] = v[i4 + j]; }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float gr = gv[j] * gs;
+    float pp = pv[j] * (1.f - lr * wd);
+    mv[j] = mv[j] + (1.f - beta1) * (gr - mv[j]);             // lerp(m, g, 1 - beta1)
+    vv[j] = beta2 * vv[j] + (1.f - beta2) * gr * gr;
+    const float denom = sqrtf(vv[j]) / bc2_sqrt + eps;
+    pp -= step_size * (mv[j] / denom);
+    pv[j] = pp;
+  }
+  if (full) {
+    *reinterpret_cast<float4*>(p + i4) = *reinterpret_cast<const float4*>(pv);
+    *reinterpret_cast<float4*>(m + i4) = *reinterpret_cast<const float4*>(mv);
+    *reinterpret_cast<float4*>(v + i4) = *reinterpret_cast<const float4*>(vv);
+  } else {
+    for (int j = 0; j < 4; ++j)
+      if (i4 + j < n) { p[i4 + j] = pv[j]; m[i4 + j] = mv[j]; v[i4 + j] = vv[j]; }
+  }
+}
+
 // ---- sem_scal / geo_scal statistics (semkitti_loss.py:136-225) ---------------------------------------------
 // Over the masked voxels (label != ignore, mask set): per class i  Sp_i = sum p_i, Nom_i = sum p_i [t == i],
 // Cnt_i = sum [t == i]; M = number of masked voxels.  Deterministic: warp shuffles in a fixed tree, per-block
@@ -996,41 +1110,15 @@ extern "C" int dhd_act_bwd(const void* dy, int dy_ld, int dy_coff, const void* y
                                           (const __nv_bfloat16*)add, add_ld, add_coff);
   DHD_CUDA_LAUNCH_CHECK("act_bwd");
   if (colsum != nullptr) {
-    colsum_reduce_kernel<<<(2 * C * 32 + 255) / 256, 256, 0, st>>>(workspace, nblocks, 2 * C, colsum);
+    colsum_finish_kernel<<<(2 * C + 31) / 32, 1024, 0, st>>>(workspace, nblocks, 2 * C, colsum);
     DHD_CUDA_LAUNCH_CHECK("colsum_reduce");
   }
   return DHD_OK;
 }
 
-// sums[i] = sum over rows of partial[row][i], rows in a fixed order: a block owns 32 columns (lane = column: 128-byte
-// coalesced row reads), its 8 warps stride over the rows, and the 8 partial sums meet in shared memory
-__global__ void __launch_bounds__(256)
-colsum_finish_kernel(const float* __restrict__ partial, int rows, int n, float* __restrict__ sums) {
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int i = blockIdx.x * 32 + lane;
-  float a0 = 0.f, a1 = 0.f;
-  if (i < n) {
-    int r = w;
-    for (; r + 8 < rows; r += 16) {
-      a0 += __ldg(partial + (size_t)r * n + i);
-      a1 += __ldg(partial + (size_t)(r + 8) * n + i);
-    }
-    if (r < rows) a0 += __ldg(partial + (size_t)r * n + i);
-  }
-  __shared__ float sh[8][32];
-  sh[w][lane] = a0 + a1;
-  __syncthreads();
-  if (w == 0 && i < n) {
-    float t = sh[0][lane];
-#pragma unroll
-    for (int k = 1; k < 8; ++k) t += sh[k][lane];
-    sums[i] = t;
-  }
-}
-
 extern "C" int dhd_colsum_finish(const float* partial, int rows, int n, float* sums, void* stream) {
   DHD_REQUIRE(partial && sums && rows > 0 && n > 0, "bad arguments");
-  colsum_finish_kernel<<<(n + 31) / 32, 256, 0, (cudaStream_t)stream>>>(partial, rows, n, sums);
+  colsum_finish_kernel<<<(n + 31) / 32, 1024, 0, (cudaStream_t)stream>>>(partial, rows, n, sums);
   DHD_CUDA_LAUNCH_CHECK("colsum_finish");
   return DHD_OK;
 }
@@ -1189,6 +1277,38 @@ extern "C" int dhd_pack_conv_weights(const float* w, int Cout, int cin_total, in
                                                                     (__nv_bfloat16*)fwd, cin_pad, (__nv_bfloat16*)bwd,
                                                                     cout_pad, bwd_mode);
   DHD_CUDA_LAUNCH_CHECK("pack_conv_weights");
+  return DHD_OK;
+}
+
+extern "C" int dhd_pack_conv_weights_batch(const dhd_pack_desc* descs, int n, void* stream) {
+  DHD_REQUIRE(descs != nullptr && n >= 1 && n <= DHD_PACK_MAX_BATCH, "1..DHD_PACK_MAX_BATCH layers");
+  PackBatch B;
+  long nmax = 0;
+  for (int i = 0; i < n; ++i) {
+    const dhd_pack_desc& L = descs[i];
+    DHD_REQUIRE(L.w && (L.fwd || L.bwd), "null pointer");
+    DHD_REQUIRE(L.Cout > 0 && L.Cin > 0 && L.taps >= 1 && L.col_lo >= 0 && L.col_lo + L.Cin <= L.cin_total, "bad shape");
+    DHD_REQUIRE(L.cin_pad >= L.Cin && L.cout_pad >= L.Cout && (L.bwd_mode == 0 || L.bwd_mode == 1), "bad padding / mode");
+    B.d[i] = L;
+    const long e = (L.fwd ? (long)L.Cout * L.taps * L.cin_pad : 0) + (L.bwd ? (long)L.Cin * L.taps * L.cout_pad : 0);
+    DHD_REQUIRE(e < (1L << 31), "layer too large for 32-bit indexing");
+    nmax = e > nmax ? e : nmax;
+  }
+  for (int i = n; i < DHD_PACK_MAX_BATCH; ++i) B.d[i] = descs[0];
+  const int bx = (int)min((nmax + 255) / 256, (long)sm_count() * 2);
+  pack_conv_weights_batch_kernel<<<dim3(bx, n), 256, 0, (cudaStream_t)stream>>>(B);
+  DHD_CUDA_LAUNCH_CHECK("pack_conv_weights_batch");
+  return DHD_OK;
+}
+
+extern "C" int dhd_adamw_flat(float* p, const float* g, float* m, float* v, long n, float lr, float beta1, float beta2,
+                              float eps, float weight_decay, float bc1, float bc2, const float* grad_scale, void* stream) {
+  DHD_REQUIRE(p && g && m && v && n > 0, "null pointer / empty");
+  DHD_REQUIRE(bc1 > 0.f && bc2 > 0.f && lr >= 0.f, "bad step constants");
+  const long threads = (n + 3) / 4;
+  adamw_flat_kernel<<<(int)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps,
+                                                                                  weight_decay, bc1, sqrtf(bc2), grad_scale);
+  DHD_CUDA_LAUNCH_CHECK("adamw_flat");
   return DHD_OK;
 }
 

@@ -400,16 +400,21 @@ class WgradDesc(ctypes.Structure):
         ('dy', ctypes.c_void_p), ('dy_ld', ctypes.c_int32), ('dy_coff', ctypes.c_int32),
         ('scale', ctypes.c_void_p), ('dw', ctypes.c_void_p), ('partial', ctypes.c_void_p),
         ('accumulate', ctypes.c_int32), ('x_stride', ctypes.c_int32), ('x_H', ctypes.c_int32), ('x_W', ctypes.c_int32),
+        ('dw_torch', ctypes.c_int32), ('dw_cin_total', ctypes.c_int32), ('dw_cin_lo', ctypes.c_int32),
+        ('dw_cin_used', ctypes.c_int32),
     ]
 
 
 _WGRAD_WS = {}
 
 
-def conv2d_wgrad(x, dy, Cout, ksize=1, dilation=1, scale=None, out=None, accumulate=False, stride=1, taps=None):
+def conv2d_wgrad(x, dy, Cout, ksize=1, dilation=1, scale=None, out=None, accumulate=False, stride=1, taps=None,
+                 grad=None):
     """Weight gradient of a stride-1 'same' convolution: x, dy are Acts (part 0 is used: bf16
     operands, fp32 accumulation).  Returns dw fp32 (Cout, ksize*ksize, Cin) -- the tap-major layout
-    of pack_weight(); `weight_grad_to_torch` turns it into (Cout, Cin, kh, kw)."""
+    of pack_weight(); `weight_grad_to_torch` turns it into (Cout, Cin, kh, kw).
+    grad=(tensor, cin_lo, cin_used): ADD the gradient straight into `tensor`, the contiguous fp32 gradient of an
+    nn.Conv2d / nn.Linear weight (Cout, Cin_total[, kh, kw]): input channel ci < cin_used goes to column cin_lo + ci."""
     if x.N != dy.N or dy.C < Cout or (stride == 1 and (x.H, x.W) != (dy.H, dy.W)):
         raise ValueError('x / dy shapes do not match')
     d = WgradDesc()
@@ -431,7 +436,14 @@ def conv2d_wgrad(x, dy, Cout, ksize=1, dilation=1, scale=None, out=None, accumul
     d.dy, d.dy_ld, d.dy_coff = dy.data.data_ptr(), dy.ld, dy.coff
     if scale is not None:
         d.scale = scale.data_ptr()
-    if out is None:
+    if grad is not None:
+        out, cin_lo, cin_used = grad
+        if out.dtype != torch.float32 or not out.is_contiguous() or out.shape[0] != Cout or \
+                out.numel() != Cout * out.shape[1] * taps:
+            raise ValueError('grad must be the contiguous fp32 (Cout, Cin_total[, kh, kw]) gradient tensor')
+        d.dw_torch, d.dw_cin_total, d.dw_cin_lo, d.dw_cin_used = 1, out.shape[1], cin_lo, cin_used
+        accumulate = True
+    elif out is None:
         out = torch.empty(Cout, taps, x.C, device=x.data.device)
         accumulate = False
     d.dw = out.data_ptr()

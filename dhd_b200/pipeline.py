@@ -476,7 +476,8 @@ class TrainStep(HotPathStep):
                        'enc': self.bucket.span(enc_params),
                        'tail': self.bucket.span(list(self.sfa.parameters()) + list(self.head.parameters()))}
         self.grad_bf16 = os.environ.get('DHD_GRAD_BF16', '0') != '0'      # gradients travel as bf16 (half the NCCL bytes)
-        self.opt = torch.optim.AdamW(self.bucket.params, lr=2e-4, weight_decay=1e-2, fused=True)
+        self.opt = shard.FlatAdamW(self.bucket, lr=2e-4, weight_decay=1e-2)      # DHD-S.py:262
+        self._refresh()                              # the parameters moved into the flat buffer: re-bind every cached view
         gen = torch.Generator(device=self.device).manual_seed(11)
         for g in self.gouts:
             g.mul_(1e-3)
@@ -586,17 +587,19 @@ class TrainStep(HotPathStep):
         ts = [self.t_depth, self.t_height, self.t_sfa, self.t_head]
         if self.encoders:
             ts += [self.t_backbone, self.t_neck] + self.t_voxel
-        for t in ts:
-            t.refresh()
+        from . import train as T
+        with T.batched_repack():                  # every layer's bf16 operands in a few launches instead of one each
+            for t in ts:
+                t.refresh()
 
     def clip_grad_norm(self):
         """optimizer_config = dict(grad_clip=dict(max_norm=5, norm_type=2)) (DHD-S.py:263): one L2 norm of the flat
         gradient bucket, scaled in place when it exceeds max_norm (torch.nn.utils.clip_grad_norm_'s rule, no host sync)."""
         if not self.grad_clip:
             return None
-        flat = self.bucket.flat
-        norm = torch.linalg.vector_norm(flat)
-        flat.mul_(torch.clamp(self.grad_clip / (norm + 1e-6), max=1.0))
+        norm = torch.linalg.vector_norm(self.bucket.flat)
+        # the coefficient stays a device scalar and is applied inside the AdamW kernel (no scaling pass over the bucket)
+        self._clip_coef = torch.clamp(self.grad_clip / (norm + 1e-6), max=1.0).float()
         return norm
 
     def train_step(self, pool_events=None):
@@ -636,7 +639,7 @@ class TrainStep(HotPathStep):
         if self.lr_schedule is not None:
             for pg in self.opt.param_groups:
                 pg['lr'] = self.lr_schedule(self._step_index)
-        self.opt.step()
+        self.opt.step(grad_scale=self._clip_coef if self.grad_clip else None)
         self._step_index += 1
         if g is not None:
             g[4].replay()

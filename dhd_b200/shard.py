@@ -68,6 +68,22 @@ class GradBucket:
     def zero(self):
         self.flat.zero_()
 
+    def flatten_params(self):
+        """Move every parameter's storage into ONE flat fp32 buffer (same order as the gradients): `p.data` becomes a
+        view, modules keep their Parameter objects.  Lets the optimizer run as a single kernel over flat buffers."""
+        if getattr(self, 'flat_params', None) is None:
+            if any(p.dtype != torch.float32 for p in self.params):
+                raise ValueError('flat parameters need fp32 master weights')
+            self.flat_params = torch.empty_like(self.flat)
+            o = 0
+            for p in self.params:
+                v = self.flat_params[o:o + p.numel()].view(p.shape)
+                v.copy_(p.data)
+                p.data = v
+                o += p.numel()
+        return self.flat_params
+
+
     def span(self, params):
         """[lo, hi) of the flat buffer covered by `params` (a contiguous run of this bucket's parameter list)."""
         ids = {id(p) for p in params if p.requires_grad}
@@ -112,3 +128,39 @@ class GradBucket:
                 sl.copy_(buf)
             sl.mul_(inv)
         self._works = []
+
+
+class FlatAdamW:
+    """torch.optim.AdamW (decoupled weight decay; the reference's optimizer, DHD-S.py:262) as ONE kernel over the flat
+    parameter / gradient buffers of a GradBucket (dhd_adamw_flat), instead of torch's multi-tensor launches over ~80
+    tensors.  `step(grad_scale=t)` multiplies the gradient by the device scalar t on the fly (gradient clipping).
+    `param_groups[0]` carries lr / betas / eps / weight_decay like a torch optimizer (schedulers write lr there)."""
+
+    def __init__(self, bucket, lr=2e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
+        self.bucket = bucket
+        self.p = bucket.flatten_params()
+        self.m = torch.zeros_like(self.p)
+        self.v = torch.zeros_like(self.p)
+        self.t = 0
+        self.param_groups = [dict(params=bucket.params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)]
+
+    def step(self, grad_scale=None):
+        import ctypes
+        from . import _lib
+        g = self.param_groups[0]
+        self.t += 1
+        b1, b2 = g['betas']
+        P = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+        _lib.check(_lib.load().dhd_adamw_flat(P(self.p), P(self.bucket.flat), P(self.m), P(self.v), self.p.numel(),
+                                              g['lr'], b1, b2, g['eps'], g['weight_decay'], 1.0 - b1 ** self.t,
+                                              1.0 - b2 ** self.t, P(grad_scale),
+                                              ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), 'adamw_flat')
+
+    def state_dict(self):
+        return dict(step=self.t, exp_avg=self.m, exp_avg_sq=self.v, param_groups=[{k: v for k, v in self.param_groups[0].items() if k != 'params'}])
+
+    def load_state_dict(self, sd):
+        self.t = int(sd['step'])
+        self.m.copy_(sd['exp_avg'])
+        self.v.copy_(sd['exp_avg_sq'])
+        self.param_groups[0].update(sd['param_groups'][0])

@@ -65,6 +65,44 @@ def act_bwd(dy, y, act, out=None, want_sums=False, add=None, write=True):
     return out, sums
 
 
+class PackDesc(ctypes.Structure):
+    """struct dhd_pack_desc (include/dhd_b200.h)."""
+    _fields_ = [('w', ctypes.c_void_p), ('scale', ctypes.c_void_p), ('fwd', ctypes.c_void_p), ('bwd', ctypes.c_void_p),
+                ('Cout', ctypes.c_int32), ('cin_total', ctypes.c_int32), ('taps', ctypes.c_int32), ('col_lo', ctypes.c_int32),
+                ('Cin', ctypes.c_int32), ('cin_pad', ctypes.c_int32), ('cout_pad', ctypes.c_int32), ('bwd_mode', ctypes.c_int32)]
+
+
+_PACK_BATCH = None
+PACK_MAX_BATCH = 32
+
+
+class batched_repack:
+    """Context manager: _TrainConv.refresh() calls inside it queue their weight re-pack and the queue is flushed
+    PACK_MAX_BATCH layers per launch (dhd_pack_conv_weights_batch) on exit."""
+
+    def __enter__(self):
+        global _PACK_BATCH
+        self.prev, _PACK_BATCH = _PACK_BATCH, []
+        return self
+
+    def __exit__(self, *exc):
+        global _PACK_BATCH
+        queue, _PACK_BATCH = _PACK_BATCH, self.prev
+        if exc[0] is not None:
+            return False
+        lib = _lib.load()
+        for i in range(0, len(queue), PACK_MAX_BATCH):
+            chunk = queue[i:i + PACK_MAX_BATCH]
+            arr = (PackDesc * len(chunk))()
+            for d, (w, scale, fwd, bwd, Cout, cin_total, taps, col_lo, Cin, cin_pad, cout_pad, mode) in zip(arr, chunk):
+                d.w, d.scale = w.data_ptr(), (scale.data_ptr() if scale is not None else None)
+                d.fwd, d.bwd = fwd.data_ptr(), bwd.data_ptr()
+                d.Cout, d.cin_total, d.taps, d.col_lo, d.Cin = Cout, cin_total, taps, col_lo, Cin
+                d.cin_pad, d.cout_pad, d.bwd_mode = cin_pad, cout_pad, mode
+            _lib.check(lib.dhd_pack_conv_weights_batch(arr, len(chunk), _stream()), 'pack_conv_weights_batch')
+        return False
+
+
 def _acc(param, g):
     """param.grad += g (fp32), allocating on first use."""
     g = g.reshape(param.shape).to(param.dtype)
@@ -116,9 +154,13 @@ class _TrainConv:
         else:
             self.bias = self._bn_bias if self.bias_p is None else self._bn_bias + self.bias_p.detach() * self.scale
         col_lo = 0 if self.cols is None else self.cols[0]
-        _lib.check(_lib.load().dhd_pack_conv_weights(_p(w.detach()), self.Cout, cin_total, taps, col_lo, self.Cin,
-                                                     _p(self.scale), _p(self.w_fwd), self.cin_pad, _p(self.w_bwd),
-                                                     self.cout_pad, 0, _stream()), 'pack_conv_weights')
+        if _PACK_BATCH is not None:
+            _PACK_BATCH.append((w.detach(), self.scale, self.w_fwd, self.w_bwd, self.Cout, cin_total, taps, col_lo,
+                                self.Cin, self.cin_pad, self.cout_pad, 0))
+        else:
+            _lib.check(_lib.load().dhd_pack_conv_weights(_p(w.detach()), self.Cout, cin_total, taps, col_lo, self.Cin,
+                                                         _p(self.scale), _p(self.w_fwd), self.cin_pad, _p(self.w_bwd),
+                                                         self.cout_pad, 0, _stream()), 'pack_conv_weights')
         if self.stride == 2:
             # data gradient of a stride-2 3x3 / pad-1 layer, one stride-1 convolution per output parity phase
             # (py, px): dx[2u+py, 2v+px] = sum over the taps k with k = p+1 (mod 2) of dy[u + (p+1-k)/2, ...] w[k]
@@ -219,15 +261,21 @@ class _TrainConv:
             bias_sums = None                       # a conv bias under a batch-statistics BN has zero gradient
             if self.bias_p is not None and self.bias_p.requires_grad:
                 _ensure_grad(self.bias_p)          # ... which torch reports as zeros, not as None
-        dw = D.conv2d_wgrad(x, dy, self.Cout, ksize=self.ksize, dilation=self.dilation, scale=self.scale,
-                            stride=self.stride)
-        if x.C != self.Cin:
-            dw = dw[:, :, :self.Cin]
-        g = D.weight_grad_to_torch(dw.contiguous(), self.ksize)
-        if self.cols is not None:
-            _ensure_grad(self.weight)[:, self.cols[0]:self.cols[1]].add_(g)
+        # the reduce pass of the weight-gradient kernel adds straight into param.grad (torch layout, its column window)
+        gw = _ensure_grad(self.weight)
+        if gw.is_contiguous() and gw.dtype == torch.float32:
+            D.conv2d_wgrad(x, dy, self.Cout, ksize=self.ksize, dilation=self.dilation, scale=self.scale,
+                           stride=self.stride, grad=(gw, 0 if self.cols is None else self.cols[0], self.Cin))
         else:
-            _acc(self.weight, g if self.weight.dim() == 4 else g[:, :, 0, 0])
+            dw = D.conv2d_wgrad(x, dy, self.Cout, ksize=self.ksize, dilation=self.dilation, scale=self.scale,
+                                stride=self.stride)
+            if x.C != self.Cin:
+                dw = dw[:, :, :self.Cin]
+            g = D.weight_grad_to_torch(dw.contiguous(), self.ksize)
+            if self.cols is not None:
+                gw[:, self.cols[0]:self.cols[1]].add_(g)
+            else:
+                _acc(self.weight, g if self.weight.dim() == 4 else g[:, :, 0, 0])
         if self.bias_p is not None and bias_sums is not None:      # a conv bias under a frozen BN sees the BN scale
             _acc(self.bias_p, bias_sums[:self.Cout] if self.bn is None else bias_sums[:self.Cout] * self.scale)
         if dx_segs is not None and self.stride == 2:

@@ -271,6 +271,11 @@ typedef struct dhd_wgrad_desc {
   int32_t x_stride;            /* 0 / 1, or 2: x is sampled at (2*y + tap_dy, 2*x + tap_dx) of an x_H x x_W grid
                                   (stride-2 layers; ConvTranspose2d(2,2) with the operand roles swapped) */
   int32_t x_H, x_W;
+  /* Output layout.  dw_torch == 0: dw is [Cout][taps][Cin] (the packed forward layout).  dw_torch != 0: dw is the
+   * nn.Conv2d / nn.Linear gradient tensor itself, [Cout][dw_cin_total][taps]; input channel ci < dw_cin_used lands
+   * in column dw_cin_lo + ci and the zero-padded channels ci >= dw_cin_used are dropped -- with accumulate != 0 the
+   * kernel adds straight into param.grad (a view into the data-parallel gradient bucket), no repack / add launches. */
+  int32_t dw_torch, dw_cin_total, dw_cin_lo, dw_cin_used;
 } dhd_wgrad_desc;
 
 size_t dhd_conv2d_wgrad_workspace_bytes(const dhd_wgrad_desc* desc);
@@ -350,6 +355,25 @@ int dhd_dcn_col2im_bwd(const void* dcol, int col_ld, const void* x, int x_ld, in
 int dhd_pack_conv_weights(const float* w, int Cout, int cin_total, int taps, int col_lo, int Cin,
                           const float* scale, void* fwd, int cin_pad, void* bwd, int cout_pad, int bwd_mode,
                           void* stream);
+
+/* the same for up to DHD_PACK_MAX_BATCH layers in ONE launch (the re-pack after an optimizer step is ~30 independent
+ * few-microsecond kernels otherwise) */
+#define DHD_PACK_MAX_BATCH 32
+typedef struct dhd_pack_desc {
+  const float* w;
+  const float* scale;
+  void* fwd;
+  void* bwd;
+  int32_t Cout, cin_total, taps, col_lo, Cin, cin_pad, cout_pad, bwd_mode;
+} dhd_pack_desc;
+int dhd_pack_conv_weights_batch(const dhd_pack_desc* descs, int n, void* stream);
+
+/* AdamW (torch.optim.AdamW: decoupled weight decay, bias-corrected moments; the reference's optimizer,
+ * projects/configs/DHD/DHD-S.py:262) over FLAT fp32 buffers: p, m, v updated in place from g, all of n elements.
+ * bc1 = 1 - beta1^t, bc2 = 1 - beta2^t for this step t.  grad_scale: optional DEVICE scalar multiplied into g on
+ * the fly (the gradient-clipping coefficient min(1, max_norm / (norm + 1e-6)): no separate scaling pass). */
+int dhd_adamw_flat(float* p, const float* g, float* m, float* v, long n, float lr, float beta1, float beta2, float eps,
+                   float weight_decay, float bc1, float bc2, const float* grad_scale, void* stream);
 
 /* batch-statistics BatchNorm of the training path (torch BatchNorm2d in training mode after every convolution of the
  * reference's modules).  Forward: out = act(scale[c]*raw + shift[c] [+ residual]) [* gate[n][c]] on the convolution's

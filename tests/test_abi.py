@@ -84,7 +84,8 @@ def test_ctypes_struct_layouts_match_the_library(lib):
     from dhd_b200 import dense as D
     from dhd_b200._lib import MghsCfg
     from dhd_b200.stereo import StereoDesc
-    for which, cls in enumerate((MghsCfg, D.ConvSeg, D.ConvDesc, D.WgradDesc, StereoDesc, D.PredictorTailDesc)):
+    from dhd_b200.train import PackDesc
+    for which, cls in enumerate((MghsCfg, D.ConvSeg, D.ConvDesc, D.WgradDesc, StereoDesc, D.PredictorTailDesc, PackDesc)):
         assert lib.dhd_abi_sizeof(which) == ctypes.sizeof(cls), cls.__name__
     # the same fields at the same offsets for the two structs that grew this round
     assert D.ConvDesc.stride.offset == D.ConvDesc.seg.offset + D.MAX_SEGS * ctypes.sizeof(D.ConvSeg)
@@ -100,13 +101,14 @@ def test_ctypes_field_offsets_match_the_c_header(tmp_path):
     from dhd_b200 import dense as D
     from dhd_b200._lib import MghsCfg
     from dhd_b200.stereo import StereoDesc
+    from dhd_b200.train import PackDesc
     if shutil.which('gcc') is None:
         pytest.skip('no C compiler')
     header = os.path.join(ROOT, 'include', 'dhd_b200.h')
     text = re.sub(r'/\*.*?\*/', '', open(header).read(), flags=re.S)
     structs = (('dhd_mghs_cfg', MghsCfg), ('dhd_conv_seg', D.ConvSeg), ('dhd_conv_desc', D.ConvDesc),
                ('dhd_wgrad_desc', D.WgradDesc), ('dhd_stereo_desc', StereoDesc),
-               ('dhd_predictor_tail_desc', D.PredictorTailDesc))
+               ('dhd_predictor_tail_desc', D.PredictorTailDesc), ('dhd_pack_desc', PackDesc))
     lines, expect = [], []
     for cname, cls in structs:
         body = re.search(r'typedef struct %s \{(.*?)\} %s;' % (cname, cname), text, flags=re.S).group(1)

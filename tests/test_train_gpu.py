@@ -844,3 +844,51 @@ def test_depthnet_trainer_loss_and_backward(cuda_lib, stereo, use_dcn, aspp_mid,
         if name in errs:
             assert cos(p.grad, sd[name].grad) > 0.99, name
     assert errs['context_conv.weight'] < 1e-2 and errs['context_mlp.fc1.weight'] < 2e-2
+
+
+def test_flat_adamw_matches_torch_adamw(cuda_lib):
+    """dhd_adamw_flat over the flat buffers of a GradBucket == torch.optim.AdamW on the same parameters and gradients
+    (three steps, decoupled weight decay, bias correction), and the gradient-clipping coefficient applied on the fly ==
+    scaling the gradients first."""
+    from dhd_b200 import shard
+    g = torch.Generator().manual_seed(2)
+    shapes = [(64, 32, 3, 3), (64,), (10, 64), (7,), (3, 5, 1, 1)]
+    ours = [torch.nn.Parameter(torch.randn(*s, generator=g).cuda()) for s in shapes]
+    ref = [torch.nn.Parameter(p.detach().clone()) for p in ours]
+    bucket = shard.GradBucket(ours)
+    opt = shard.FlatAdamW(bucket, lr=2e-3, weight_decay=1e-2)
+    topt = torch.optim.AdamW(ref, lr=2e-3, weight_decay=1e-2)
+    for step in range(3):
+        coef = torch.tensor(0.5 if step == 1 else 1.0, device='cuda')
+        for p, q in zip(ours, ref):
+            gr = torch.randn(p.shape, generator=g).cuda()
+            p.grad.copy_(gr)
+            q.grad = gr * coef
+        opt.step(grad_scale=coef)
+        topt.step()
+    for p, q in zip(ours, ref):
+        assert p.data_ptr() >= bucket.flat_params.data_ptr()                      # still a view into the flat buffer
+        assert float((p - q).abs().max()) <= 2e-6 * float(q.abs().max()) + 1e-7
+
+
+def test_batched_weight_repack_equals_per_layer_repack(cuda_lib):
+    """dhd_pack_conv_weights_batch (all layers of a trainer in one launch) writes the same bf16 operands as the
+    per-layer launches."""
+    import projects.mmdet3d_plugin  # noqa: F401
+    from dhd_b200 import train as T
+    from projects.mmdet3d_plugin.models.necks.mix import SFA
+    sfa = SFA(512, 256).cuda()
+    tr = T.SFATrainer(sfa)
+    with torch.no_grad():
+        for p in sfa.parameters():
+            p.add_(torch.randn_like(p) * 0.01)
+    tr.refresh()
+    want = [(c.w_fwd.clone(), c.w_bwd.clone()) for c in (tr.sp1, tr.sp2, tr.res1, tr.res2, tr.short)]
+    for c in (tr.sp1, tr.sp2, tr.res1, tr.res2, tr.short):
+        c.w_fwd.zero_()
+        c.w_bwd.zero_()
+    with T.batched_repack():
+        tr.refresh()
+    torch.cuda.synchronize()
+    for c, (f, b) in zip((tr.sp1, tr.sp2, tr.res1, tr.res2, tr.short), want):
+        assert torch.equal(c.w_fwd, f) and torch.equal(c.w_bwd, b)
