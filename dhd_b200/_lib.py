@@ -54,6 +54,8 @@ _SIGNATURES = {
     'dhd_conv_pair_mode': (ctypes.c_int, [_I]),
     'dhd_conv2d_stat_rows': (ctypes.c_int, [_P]),
     'dhd_pack_conv_weights_batch': (ctypes.c_int, [_P, _I, _P]),
+    'dhd_bn_fwd_coeffs_partial': (ctypes.c_int, [_P, _I, _I, ctypes.c_float, _P, _P, ctypes.c_float, ctypes.c_float] + [_P] * 7),
+    'dhd_bn_bwd_sums_coeffs': (ctypes.c_int, [_P, _I, _I, _P, _I, _I, ctypes.c_long, _I, _P, ctypes.c_float] + [_P] * 9),
     'dhd_adamw_flat': (ctypes.c_int, [_P, _P, _P, _P, ctypes.c_long] + [ctypes.c_float] * 7 + [_P, _P]),
     'dhd_colsum_finish': (ctypes.c_int, [_P, _I, _I, _P, _P]),
     'dhd_conv2d_wgrad_workspace_bytes': (ctypes.c_size_t, [_P]),

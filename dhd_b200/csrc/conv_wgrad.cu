@@ -185,60 +185,63 @@ wgrad_reduce_kernel(const float* __restrict__ partial, int splits, long n, int p
   dw[i] = accumulate ? dw[i] + a : a;
 }
 
-// dw_torch layout: dw is the parameter's gradient [Cout][cin_total][taps].  One thread per (co, ci) sums the slices
-// of its `taps` values (reads coalesced over ci), the block stages them in shared memory in output order and writes /
-// accumulates them back with consecutive threads on consecutive addresses (a thread-per-value mapping writes with a
-// stride of `taps` floats: 9x the sectors on a 3x3 layer).
+// dw_torch layout: dw is the parameter's gradient [Cout][cin_total][taps].  A block owns 32 (co, ci) pairs (lane = ci:
+// reads coalesced) x 8 slice groups (warp g adds slices g, g+8, .. in order: a 1x1 layer has up to 148 slices and one
+// thread per value made this pass a chain of dependent loads); the 8 group sums meet in shared memory, are added in
+// order and leave in output order with consecutive threads on consecutive addresses (a thread-per-value mapping
+// writes with a stride of `taps` floats: 9x the sectors on a 3x3 layer).  32-bit index arithmetic throughout.
 __global__ void __launch_bounds__(256)
 wgrad_reduce_torch_kernel(const float* __restrict__ partial, int splits, long n, const float* __restrict__ scale,
                           float* __restrict__ dw, int accumulate, int Cout, int Cin, int taps, int cin_total, int cin_lo,
                           int cin_used) {
-  __shared__ float stage[256 * DHD_CONV_MAX_TAPS];
-  // 32-bit index arithmetic throughout (host check: Cout * cin_total * taps < 2^31)
-  const unsigned p0 = blockIdx.x * 256u;
+  __shared__ float grp[8][32][DHD_CONV_MAX_TAPS + 1];
+  const unsigned lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const unsigned p0 = blockIdx.x * 32u;
   const unsigned npairs = (unsigned)Cout * (unsigned)cin_used;
-  const unsigned p = p0 + threadIdx.x;
+  const unsigned p = p0 + lane;
+  float acc[DHD_CONV_MAX_TAPS];
+#pragma unroll
+  for (int t = 0; t < DHD_CONV_MAX_TAPS; ++t) acc[t] = 0.f;
   if (p < npairs) {
     const unsigned co = p / (unsigned)cin_used, ci = p - co * (unsigned)cin_used;
-    const float sc = scale != nullptr ? scale[co] : 1.f;
-    float acc[DHD_CONV_MAX_TAPS];
-#pragma unroll
-    for (int t = 0; t < DHD_CONV_MAX_TAPS; ++t) acc[t] = 0.f;
     const size_t i0 = (size_t)co * taps * Cin + ci;
-    // slices in a fixed order, four at a time: every load of a group is issued before the first add (a 1x1 layer has
-    // one tile row of work items and up to 148 slices: one dependent load per trip made this pass latency-bound)
-    int s = 0;
-    for (; s + 4 <= splits; s += 4) {
-      float q[4][DHD_CONV_MAX_TAPS];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const float* ps = partial + (size_t)(s + u) * n + i0;
-#pragma unroll
-        for (int t = 0; t < DHD_CONV_MAX_TAPS; ++t)
-          if (t < taps) q[u][t] = __ldg(ps + (size_t)t * Cin);
-      }
+    int s = (int)g;
+    for (; s + 8 < splits; s += 16) {             // two slices per trip, loads first
+      const float* pa = partial + (size_t)s * n + i0;
+      const float* pb = partial + (size_t)(s + 8) * n + i0;
+      float qa[DHD_CONV_MAX_TAPS], qb[DHD_CONV_MAX_TAPS];
 #pragma unroll
       for (int t = 0; t < DHD_CONV_MAX_TAPS; ++t)
-        if (t < taps) acc[t] += (q[0][t] + q[1][t]) + (q[2][t] + q[3][t]);
-    }
-    for (; s < splits; ++s) {
-      const float* ps = partial + (size_t)s * n + i0;
+        if (t < taps) {
+          qa[t] = __ldg(pa + (size_t)t * Cin);
+          qb[t] = __ldg(pb + (size_t)t * Cin);
+        }
 #pragma unroll
       for (int t = 0; t < DHD_CONV_MAX_TAPS; ++t)
-        if (t < taps) acc[t] += __ldg(ps + (size_t)t * Cin);
+        if (t < taps) acc[t] += qa[t] + qb[t];
     }
+    if (s < splits) {
+      const float* pa = partial + (size_t)s * n + i0;
 #pragma unroll
-    for (int t = 0; t < DHD_CONV_MAX_TAPS; ++t)
-      if (t < taps) stage[threadIdx.x * taps + t] = acc[t] * sc;
+      for (int t = 0; t < DHD_CONV_MAX_TAPS; ++t)
+        if (t < taps) acc[t] += __ldg(pa + (size_t)t * Cin);
+    }
   }
+#pragma unroll
+  for (int t = 0; t < DHD_CONV_MAX_TAPS; ++t)
+    if (t < taps) grp[g][lane][t] = acc[t];
   __syncthreads();
-  const unsigned cnt = min(256u, npairs - p0) * (unsigned)taps;
+  const unsigned cnt = min(32u, npairs - p0) * (unsigned)taps;
   for (unsigned k = threadIdx.x; k < cnt; k += 256u) {
     const unsigned lp = k / (unsigned)taps, t = k - lp * (unsigned)taps;
+    float a = grp[0][lp][t];
+#pragma unroll
+    for (int gg = 1; gg < 8; ++gg) a += grp[gg][lp][t];
     const unsigned q = p0 + lp;
     const unsigned co = q / (unsigned)cin_used, ci = q - co * (unsigned)cin_used;
+    if (scale != nullptr) a *= scale[co];
     const unsigned o = (co * (unsigned)cin_total + (unsigned)cin_lo + ci) * (unsigned)taps + t;
-    dw[o] = accumulate ? dw[o] + stage[k] : stage[k];
+    dw[o] = accumulate ? dw[o] + a : a;
   }
 }
 
@@ -342,7 +345,7 @@ extern "C" int dhd_conv2d_wgrad(const dhd_wgrad_desc* d, void* stream) {
   const long n = (long)d->Cout * d->taps * d->Cin;
   if (d->dw_torch != 0) {
     const long npairs = (long)d->Cout * d->dw_cin_used;
-    wgrad_reduce_torch_kernel<<<(int)((npairs + 255) / 256), 256, 0, st>>>(
+    wgrad_reduce_torch_kernel<<<(int)((npairs + 31) / 32), 256, 0, st>>>(
         d->partial, P.splits, n, d->scale, d->dw, d->accumulate, d->Cout, d->Cin, d->taps, d->dw_cin_total, d->dw_cin_lo,
         d->dw_cin_used);
   } else {

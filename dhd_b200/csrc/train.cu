@@ -11,7 +11,7 @@
 
 namespace dhd {
 
-constexpr int kMaxSumBlocks = 1024;
+constexpr int kMaxSumBlocks = 1184;   // 8 resident blocks x 148 SMs: one full wave
 
 __device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&v)[8]) {
   const uint4 q = *reinterpret_cast<const uint4*>(p);
@@ -1003,6 +1003,74 @@ bn_bwd_coeffs_kernel(const float* __restrict__ sums, int C, int sums_stride, flo
 }
 
 
+// The fixed-order finish of per-block partial sums [rows][2C] fused with the per-channel coefficient formulas above
+// (one launch instead of finish + coefficients): a block owns 32 channels, lane = channel, its 32 warps stride over the
+// rows for column c and column C + c, the warp partials meet in shared memory, warp 0 adds them in order.
+// MODE 1: BatchNorm forward (sums = [sum raw, sum raw^2]); MODE 2: backward (sums = [sum dz, sum dz*raw]).
+struct BnFinishArgs {
+  float M, eps, momentum;
+  const float *gamma, *beta, *mean_in, *invstd_in;
+  float *running_mean, *running_var, *o0, *o1, *o2, *o3, *dgamma, *dbeta;
+};
+template <int MODE>
+__global__ void __launch_bounds__(1024)
+bn_finish_kernel(const float* __restrict__ partial, int rows, int C, const BnFinishArgs A) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+  if (c < C) {
+    const size_t n = 2 * (size_t)C;
+    int r = w;
+    for (; r + 32 < rows; r += 64) {
+      const float* p0 = partial + (size_t)r * n + c;
+      const float* p1 = partial + (size_t)(r + 32) * n + c;
+      a0 += __ldg(p0);
+      b0 += __ldg(p0 + C);
+      a1 += __ldg(p1);
+      b1 += __ldg(p1 + C);
+    }
+    if (r < rows) {
+      a0 += __ldg(partial + (size_t)r * n + c);
+      b0 += __ldg(partial + (size_t)r * n + C + c);
+    }
+  }
+  __shared__ float sa[32][33], sb[32][33];
+  sa[w][lane] = a0 + a1;
+  sb[w][lane] = b0 + b1;
+  __syncthreads();
+  if (w != 0 || c >= C) return;
+  float s1 = sa[0][lane], s2 = sb[0][lane];
+#pragma unroll
+  for (int k = 1; k < 32; ++k) {
+    s1 += sa[k][lane];
+    s2 += sb[k][lane];
+  }
+  if (MODE == 1) {
+    const float mean = s1 / A.M;
+    const float var = fmaxf(s2 / A.M - mean * mean, 0.f);
+    const float invstd = rsqrtf(var + A.eps);
+    const float sc = A.gamma[c] * invstd;
+    A.o0[c] = sc;                               // scale
+    A.o1[c] = A.beta[c] - mean * sc;            // shift
+    A.o2[c] = mean;
+    A.o3[c] = invstd;
+    if (A.running_mean != nullptr) {
+      A.running_mean[c] = (1.f - A.momentum) * A.running_mean[c] + A.momentum * mean;
+      A.running_var[c] = (1.f - A.momentum) * A.running_var[c] + A.momentum * var * (A.M / fmaxf(A.M - 1.f, 1.f));
+    }
+  } else {
+    const float mean = A.mean_in[c], is = A.invstd_in[c];
+    const float t2 = s2 - mean * s1;            // sum dz * (raw - mean)
+    const float a = A.gamma[c] * is;
+    const float b = -a * t2 * is * is / A.M;
+    A.o0[c] = a;                                // k1
+    A.o1[c] = b;                                // k2
+    A.o2[c] = -a * (s1 / A.M) - b * mean;       // k3
+    if (A.dgamma != nullptr) A.dgamma[c] += t2 * is;
+    if (A.dbeta != nullptr) A.dbeta[c] += s1;
+  }
+}
+
 // Dropout (nn.Dropout(0.5) behind the ASPP, depthnet.py:81, 106) as a counter-based mask: Philox-4x32-10 keyed by the
 // seed, counter = (vector index, step, salt), one call per 8 channels, 16 random bits per element.  The mask is a pure
 // function of (seed, step, salt, element), so the backward multiplies the gradient by the very same mask without it
@@ -1358,6 +1426,44 @@ extern "C" int dhd_bn_fwd_coeffs(const float* sums, int C, float M, const float*
                                                                          running_mean, running_var, scale, shift, mean,
                                                                          invstd);
   DHD_CUDA_LAUNCH_CHECK("bn_fwd_coeffs");
+  return DHD_OK;
+}
+
+extern "C" int dhd_bn_fwd_coeffs_partial(const float* partial, int rows, int C, float M, const float* gamma,
+                                         const float* beta, float eps, float momentum, float* running_mean,
+                                         float* running_var, float* scale, float* shift, float* mean, float* invstd,
+                                         void* stream) {
+  DHD_REQUIRE(partial && rows > 0 && gamma && beta && scale && shift && mean && invstd && C > 0 && M > 0.f, "bad arguments");
+  DHD_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "running statistics come as a pair");
+  BnFinishArgs A = {};
+  A.M = M; A.eps = eps; A.momentum = momentum; A.gamma = gamma; A.beta = beta;
+  A.running_mean = running_mean; A.running_var = running_var;
+  A.o0 = scale; A.o1 = shift; A.o2 = mean; A.o3 = invstd;
+  bn_finish_kernel<1><<<(C + 31) / 32, 1024, 0, (cudaStream_t)stream>>>(partial, rows, C, A);
+  DHD_CUDA_LAUNCH_CHECK("bn_finish_fwd");
+  return DHD_OK;
+}
+
+extern "C" int dhd_bn_bwd_sums_coeffs(const void* dy, int dy_ld, int dy_coff, const void* raw, int raw_ld, int raw_coff,
+                                      long rows, int C, float* workspace, float M, const float* mean, const float* invstd,
+                                      const float* gamma, float* k1, float* k2, float* k3, float* dgamma, float* dbeta,
+                                      void* stream) {
+  DHD_REQUIRE(dy && raw && workspace && mean && invstd && gamma && k1 && k2 && k3 && rows > 0 && C > 0 && M > 0.f,
+              "bad arguments");
+  DHD_REQUIRE(C <= 2048 && ok8(C, dy_ld, dy_coff, dy) && ok8(C, raw_ld, raw_coff, raw), "C % 8, 16-byte aligned rows");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int rpb = 256 / (C / 8);
+  long rows_per_block = (rows + kMaxSumBlocks - 1) / kMaxSumBlocks;
+  if (rows_per_block < 4L * rpb) rows_per_block = 4L * rpb;
+  const int nblocks = (int)((rows + rows_per_block - 1) / rows_per_block);
+  act_bwd_kernel<<<nblocks, 256, 0, st>>>((const __nv_bfloat16*)dy, dy_ld, dy_coff, (const __nv_bfloat16*)raw, raw_ld,
+                                          raw_coff, rows, C, 0, nullptr, 0, 0, workspace, rows_per_block, nullptr, 0, 0);
+  DHD_CUDA_LAUNCH_CHECK("act_bwd(bn sums)");
+  BnFinishArgs A = {};
+  A.M = M; A.gamma = gamma; A.mean_in = mean; A.invstd_in = invstd;
+  A.o0 = k1; A.o1 = k2; A.o2 = k3; A.dgamma = dgamma; A.dbeta = dbeta;
+  bn_finish_kernel<2><<<(C + 31) / 32, 1024, 0, st>>>(workspace, nblocks, C, A);
+  DHD_CUDA_LAUNCH_CHECK("bn_finish_bwd");
   return DHD_OK;
 }
 

@@ -314,6 +314,8 @@ def conv2d(x, weight, Cout, ksize=1, dilation=1, precision='fp32', scale=None, b
         if defer:
             raise ValueError('stats with defer is not supported')
         _lib.check(lib.dhd_conv2d_fwd(ctypes.byref(d), _stream()), 'conv2d_fwd')
+        if isinstance(stats, str):               # 'partial': the caller finishes (e.g. fused with the BatchNorm formulas)
+            return part, rows
         _lib.check(lib.dhd_colsum_finish(part.data_ptr(), rows, 2 * Cout, stats.data_ptr(), _stream()), 'colsum_finish')
         return keep
     if defer:

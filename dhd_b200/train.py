@@ -49,9 +49,10 @@ def act_bwd(dy, y, act, out=None, want_sums=False, add=None, write=True):
     with sums (2, C) fp32 = [sum_rows dz, sum_rows dz*y] when want_sums."""
     lib = _lib.load()
     C = dy.C
+    in_place = out is None
     out = dy if out is None else out
-    if not write:
-        out = None                                # reductions only
+    if not write or (in_place and act in (None, 'none') and add is None):
+        out = None                                # reductions only (an in-place identity pass would rewrite dy unchanged)
     sums = ws = None
     if want_sums:
         sums = torch.empty(2, C, device=dy.data.device)
@@ -62,7 +63,7 @@ def act_bwd(dy, y, act, out=None, want_sums=False, add=None, write=True):
                                out.coff if out is not None else 0, _p(sums), _p(ws),
                                _p(add.data) if add is not None else None, add.ld if add is not None else 0,
                                add.coff if add is not None else 0, _stream()), 'act_bwd')
-    return out, sums
+    return (out if out is not None else dy), sums
 
 
 class PackDesc(ctypes.Structure):
@@ -204,11 +205,10 @@ class _TrainConv:
         if FUSED_BN_STATS and self.Cout % 2 == 0:
             # [sum raw, sum raw^2] per channel come out of the convolution's epilogue (per-tile partials of the staged
             # bf16 tile + a fixed-order finish): the separate read of `raw` is gone
-            if getattr(self, '_sums', None) is None:
-                self._sums = torch.empty(2, self.Cout, device=x.data.device)
-            sums = self._sums
-            D.conv2d(x, self.w_fwd, self.Cout, ksize=self.ksize, dilation=self.dilation, precision='bf16', bias=self.bias,
-                     img_bias=img_bias, segs=[dict(out_act=raw)], stride=self.stride, stats=sums)
+            part, prows = D.conv2d(x, self.w_fwd, self.Cout, ksize=self.ksize, dilation=self.dilation, precision='bf16',
+                                   bias=self.bias, img_bias=img_bias, segs=[dict(out_act=raw)], stride=self.stride,
+                                   stats='partial')
+            sums = None
         else:
             D.conv2d(x, self.w_fwd, self.Cout, ksize=self.ksize, dilation=self.dilation, precision='bf16', bias=self.bias,
                      img_bias=img_bias, segs=[dict(out_act=raw)], stride=self.stride)
@@ -218,10 +218,17 @@ class _TrainConv:
             self._bn_buf = torch.empty(7, self.Cout, device=x.data.device)       # scale, shift, mean, invstd, k1, k2, k3
         bb = self._bn_buf
         track = bn.track_running_stats
-        _lib.check(lib.dhd_bn_fwd_coeffs(_p(sums), self.Cout, M, _p(bn.weight.detach()), _p(bn.bias.detach()), bn.eps,
-                                         bn.momentum if bn.momentum is not None else 0.1,
-                                         _p(bn.running_mean) if track else None, _p(bn.running_var) if track else None,
-                                         _p(bb[0]), _p(bb[1]), _p(bb[2]), _p(bb[3]), _stream()), 'bn_fwd_coeffs')
+        mom = bn.momentum if bn.momentum is not None else 0.1
+        if sums is None:                          # finish of the epilogue's partial sums + coefficient formulas: one launch
+            _lib.check(lib.dhd_bn_fwd_coeffs_partial(_p(part), prows, self.Cout, M, _p(bn.weight.detach()),
+                                                     _p(bn.bias.detach()), bn.eps, mom,
+                                                     _p(bn.running_mean) if track else None,
+                                                     _p(bn.running_var) if track else None,
+                                                     _p(bb[0]), _p(bb[1]), _p(bb[2]), _p(bb[3]), _stream()), 'bn_fwd_coeffs_partial')
+        else:
+            _lib.check(lib.dhd_bn_fwd_coeffs(_p(sums), self.Cout, M, _p(bn.weight.detach()), _p(bn.bias.detach()), bn.eps,
+                                             mom, _p(bn.running_mean) if track else None, _p(bn.running_var) if track else None,
+                                             _p(bb[0]), _p(bb[1]), _p(bb[2]), _p(bb[3]), _stream()), 'bn_fwd_coeffs')
         scale, shift = bb[0], bb[1]
         self._bn_saved = M
         ob, of, f_ld = seg.get('out_act'), None, 0
@@ -240,13 +247,16 @@ class _TrainConv:
         """dy: gradient at the BatchNorm output (pre-activation).  Accumulates d gamma / d beta and returns the gradient
         at the convolution output (a scratch activation: dy itself may feed other layers and is left untouched)."""
         bn, raw, bb, M = self.bn, self._raw, self._bn_buf, self._bn_saved
-        _, sums = act_bwd(dy, raw, None, want_sums=True, write=False)             # [sum dz, sum dz * raw]
         train_affine = bn.weight.requires_grad
-        _lib.check(_lib.load().dhd_bn_bwd_coeffs(_p(sums), self.Cout, sums.shape[1], M, _p(bb[2]), _p(bb[3]),
-                                                 _p(bn.weight.detach()), _p(bb[4]), _p(bb[5]), _p(bb[6]),
-                                                 _p(_ensure_grad(bn.weight)) if train_affine else None,
-                                                 _p(_ensure_grad(bn.bias)) if train_affine else None, _stream()),
-                   'bn_bwd_coeffs')
+        lib = _lib.load()
+        # [sum dz, sum dz * raw] per channel (one pass over dy and raw), then finish + k1 / k2 / k3 + d gamma / d beta
+        ws = _workspace(dy.data.device, lib.dhd_act_bwd_workspace_bytes(self.Cout))
+        _lib.check(lib.dhd_bn_bwd_sums_coeffs(_p(dy.data), dy.ld, dy.coff, _p(raw.data), raw.ld, raw.coff,
+                                              raw.N * raw.H * raw.W, self.Cout, _p(ws), M, _p(bb[2]), _p(bb[3]),
+                                              _p(bn.weight.detach()), _p(bb[4]), _p(bb[5]), _p(bb[6]),
+                                              _p(_ensure_grad(bn.weight)) if train_affine else None,
+                                              _p(_ensure_grad(bn.bias)) if train_affine else None, _stream()),
+                   'bn_bwd_sums_coeffs')
         out = self._dyraw
         _lib.check(_lib.load().dhd_affine_combine(_p(dy.data), dy.ld, dy.coff, _p(raw.data), raw.ld, raw.coff,
                                                   raw.N * raw.H * raw.W, self.Cout, _p(bb[4]), _p(bb[5]), _p(bb[6]),

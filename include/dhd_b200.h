@@ -392,6 +392,15 @@ int dhd_bn_fwd_coeffs(const float* sums, int C, float M, const float* gamma, con
                       float* mean, float* invstd, void* stream);
 int dhd_bn_bwd_coeffs(const float* sums, int C, int sums_stride, float M, const float* mean, const float* invstd,
                       const float* gamma, float* k1, float* k2, float* k3, float* dgamma, float* dbeta, void* stream);
+/* the same coefficients straight from per-block partial sums (one launch = fixed-order finish + formulas):
+ * forward from the convolution epilogue's statistics (dhd_conv_desc.stat_partial, rows = dhd_conv2d_stat_rows);
+ * backward = the reduction pass over (dy, raw) + finish + formulas (workspace: dhd_act_bwd_workspace_bytes(C)). */
+int dhd_bn_fwd_coeffs_partial(const float* partial, int rows, int C, float M, const float* gamma, const float* beta,
+                              float eps, float momentum, float* running_mean, float* running_var, float* scale,
+                              float* shift, float* mean, float* invstd, void* stream);
+int dhd_bn_bwd_sums_coeffs(const void* dy, int dy_ld, int dy_coff, const void* raw, int raw_ld, int raw_coff, long rows,
+                           int C, float* workspace, float M, const float* mean, const float* invstd, const float* gamma,
+                           float* k1, float* k2, float* k3, float* dgamma, float* dbeta, void* stream);
 /* nn.Dropout behind the ASPP (depthnet.py:81, 106) in training mode, in place on a bf16 NHWC activation (or on the
  * gradient at the same place in the backward): x[r][c] *= keep(r, c) / (1 - p), keep from Philox-4x32-10 keyed by
  * rng[0] (seed) with counter (element, rng[1] (step), salt).  rng is a DEVICE pointer to two int64: the caller bumps
