@@ -82,6 +82,8 @@ struct TailParams {
   float* logits;                   // [(n * W + x) * H + y][288] (transpose_xy) or [m][288]; may be null
   uint8_t* occ;                    // same pixel order, [16] per pixel; may be null
   int transpose_xy;
+  __nv_bfloat16* hidden;           // [m][hidden_ld] Softplus output (training), channel c at hidden_coff + c; may be null
+  int hidden_ld, hidden_coff;
 };
 
 struct TailMaps {
@@ -271,6 +273,7 @@ predictor_tail_kernel(const __grid_constant__ TailMaps M, const __grid_constant_
     const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     int g = 0;
     for (int lt = 0; lt < my_tiles; ++lt) {
+      const long m_row = (long)(blockIdx.x + lt * gridDim.x) * kM + row;
       for (int c = 0; c < kNChunks; ++c, ++g) {
         const int ab = g % kAcc1Bufs, hb = g % kHBufs;
         mbar_wait(bar(kBarAcc1Full + ab), (uint32_t)((g / kAcc1Bufs) & 1));
@@ -285,6 +288,11 @@ predictor_tail_kernel(const __grid_constant__ TailMaps M, const __grid_constant_
 #pragma unroll
         for (int j = 0; j < 16; ++j)
           h2[j] = __floats2bfloat162_rn(softplus_fast(v[2 * j] + b[2 * j]), softplus_fast(v[2 * j + 1] + b[2 * j + 1]));
+        if (P.hidden != nullptr && m_row < (long)P.M) {       // training: the backward needs the hidden layer (64 B per thread)
+          uint4* hp = reinterpret_cast<uint4*>(P.hidden + m_row * P.hidden_ld + P.hidden_coff + c * kChunk + grp * 32);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) hp[j] = q[j];
+        }
         mbar_wait(bar(kBarHEmpty + hb), (uint32_t)((g / kHBufs) & 1) ^ 1u);     // G2(g - 2) has read this buffer
         // K-major SWIZZLE_128B operand tile: 16-byte chunk j of row r sits at chunk j ^ (r & 7)
         uint4* dst = reinterpret_cast<uint4*>(gen + kOffH + hb * kHBytes + row * 128);
@@ -433,6 +441,12 @@ extern "C" int dhd_predictor_tail(const dhd_predictor_tail_desc* d, void* stream
   P.logits = d->logits;
   P.occ = d->occ;
   P.transpose_xy = d->transpose_xy;
+  P.hidden = (__nv_bfloat16*)d->hidden;
+  P.hidden_ld = d->hidden_ld;
+  P.hidden_coff = d->hidden_coff;
+  if (d->hidden != nullptr)
+    DHD_REQUIRE(d->hidden_ld % 8 == 0 && d->hidden_coff % 8 == 0 && d->hidden_coff + pt::kN1 <= d->hidden_ld &&
+                    ((uintptr_t)d->hidden & 15) == 0, "hidden rows must be 16-byte aligned and hold N1 channels");
   int rc = encode_2d(enc, &maps.a, d->in, (uint64_t)d->in_ld, (uint64_t)P.M, (uint64_t)d->in_ld, pt::kM, "A");
   if (rc != DHD_OK) return rc;
   rc = encode_2d(enc, &maps.w1, d->w1, pt::kK1, pt::kN1, pt::kK1, pt::kChunk, "W1");

@@ -69,6 +69,7 @@ class PredictorTailDesc(ctypes.Structure):
         ('in_ld', ctypes.c_int32), ('in_coff', ctypes.c_int32), ('transpose_xy', ctypes.c_int32),
         ('in_', ctypes.c_void_p), ('w1', ctypes.c_void_p), ('b1', ctypes.c_void_p),
         ('w2', ctypes.c_void_p), ('b2', ctypes.c_void_p), ('logits', ctypes.c_void_p), ('occ', ctypes.c_void_p),
+        ('hidden', ctypes.c_void_p), ('hidden_ld', ctypes.c_int32), ('hidden_coff', ctypes.c_int32),
     ]
 
 
@@ -353,7 +354,7 @@ def conv2d_batch(deferred):
     return [k for _, k in deferred]
 
 
-def predictor_tail(x, w1, b1, w2, b2, Dz, n_cls, logits=None, occ=None, transpose_xy=True):
+def predictor_tail(x, w1, b1, w2, b2, Dz, n_cls, logits=None, occ=None, transpose_xy=True, hidden=None):
     """Fused Linear + Softplus + Linear (+ per-z argmax) of the occupancy head (dhd_predictor_tail, bf16 operands).
     x: Act (B, K1, H, W), part 0 is read; w1 / w2: pack_weight(.., 1) results; b1 / b2 fp32.
     logits: fp32 (B, W, H, Dz*n_cls) and / or occ: uint8 (B, W, H, Dz), written in place."""
@@ -379,6 +380,10 @@ def predictor_tail(x, w1, b1, w2, b2, Dz, n_cls, logits=None, occ=None, transpos
         if occ.dtype != torch.uint8 or not occ.is_contiguous() or occ.numel() != npix * Dz:
             raise ValueError('occ must be contiguous uint8 with B*H*W*Dz elements')
         d.occ = occ.data_ptr()
+    if hidden is not None:                   # Act (N, H, W, >= N1): the Softplus output, saved for the backward
+        if (hidden.N, hidden.H, hidden.W) != (x.N, x.H, x.W) or hidden.C < w1.shape[0]:
+            raise ValueError('hidden activation does not match the layer')
+        d.hidden, d.hidden_ld, d.hidden_coff = hidden.data.data_ptr(), hidden.ld, hidden.coff
     _lib.check(_lib.load().dhd_predictor_tail(ctypes.byref(d), _stream()), 'predictor_tail')
 
 

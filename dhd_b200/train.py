@@ -25,6 +25,8 @@ BN_MODE = 'frozen'
 # batch-statistics BatchNorm: sums from the convolution epilogue (True) or from a separate pass over the output (A/B)
 import os as _os
 FUSED_BN_STATS = _os.environ.get('DHD_FUSED_BN_STATS', '1') != '0'
+# the occupancy head's Linear + Softplus + Linear in training: one fused launch (True) or two convolution launches (A/B)
+FUSED_TAIL = _os.environ.get('DHD_TRAIN_FUSED_TAIL', '1') != '0'
 
 
 def set_bn_mode(mode):
@@ -344,10 +346,17 @@ class PredictorTrainer:
         t = self._act('t', N, H, W, self.conv.Cout)
         self.conv.forward(x, [dict(act='relu' if self.relu else None, out_act=t)])
         u = self._act('u', N, H, W, self.fc0.Cout)
-        self.fc0.forward(t, [dict(act='softplus', out_act=u)])
         Co = self.nout
         out = torch.empty(N, W, H, Co, device=self.device)
-        self.fc2.forward(u, [dict(out_f32=(out, (W * H * Co, Co, H * Co, 1)))])
+        if FUSED_TAIL and self.conv.Cout == 256 and self.fc0.Cout == 512 and self.Dz == 16 and self.ncls == 18 and \
+                self.fc0.cin_pad == 256 and self.fc2.cin_pad == 512:
+            # Linear + Softplus + Linear as the back-to-back GEMM kernel of the inference path (dhd_predictor_tail); the
+            # hidden layer is written once for the backward instead of written by one launch and re-read by the next
+            D.predictor_tail(t, self.fc0.w_fwd, self.fc0.bias, self.fc2.w_fwd, self.fc2.bias, self.Dz, self.ncls,
+                             logits=out, hidden=u)
+        else:
+            self.fc0.forward(t, [dict(act='softplus', out_act=u)])
+            self.fc2.forward(u, [dict(out_f32=(out, (W * H * Co, Co, H * Co, 1)))])
         self.saved = (x, t, u, out)
         return out.view(N, W, H, self.Dz, self.ncls)
 

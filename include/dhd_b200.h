@@ -476,6 +476,10 @@ typedef struct dhd_predictor_tail_desc {
   const float* b2;
   float* logits;
   uint8_t* occ;
+  /* training: the Softplus output (bf16 [N*H*W][hidden_ld], channel c at hidden_coff + c, input pixel order) is also
+   * written, for the backward of the two Linear layers; NULL = the hidden layer never leaves the SM */
+  void* hidden;
+  int32_t hidden_ld, hidden_coff;
 } dhd_predictor_tail_desc;
 int dhd_predictor_tail(const dhd_predictor_tail_desc* desc, void* stream);
 /* encoder helpers, bf16 NHWC -> bf16 NHWC (the output may be a channel slice of a concatenation buffer):

@@ -139,3 +139,30 @@ def test_fused_tail_matches_layer_by_layer_engine_at_full_size(cuda_lib):
     assert eng(x, occ=occ_only, want_logits=False) is None
     torch.cuda.synchronize()
     assert torch.equal(occ_only, occ_f)
+
+
+def test_fused_tail_hidden_output_for_training(cuda_lib):
+    """dhd_predictor_tail with `hidden`: the Softplus output it writes for the backward == the hidden layer of the
+    layer-by-layer path (bf16 rounding of the same fp32 values up to the MUFU softplus: 1 bf16 ulp), and the logits are
+    unchanged by asking for it."""
+    from dhd_b200 import dense as D
+    g = torch.Generator().manual_seed(21)
+    N, H, W = 2, 37, 29
+    x = D.pack_input(torch.randn(N, 256, H, W, generator=g).cuda(), 1)
+    w1 = (torch.randn(512, 256, generator=g) / 16).cuda()
+    w2 = (torch.randn(288, 512, generator=g) / 22).cuda()
+    b1, b2 = torch.randn(512, generator=g).cuda(), torch.randn(288, generator=g).cuda()
+    p1, p2 = D.pack_weight(w1[:, :, None, None], 1), D.pack_weight(w2[:, :, None, None], 1)
+    lo_a = torch.empty(N, W, H, 288, device='cuda')
+    lo_b = torch.empty(N, W, H, 288, device='cuda')
+    hid = D.Act.empty(N, H, W, 512, 1, 'cuda')
+    hid.data.fill_(float('nan'))
+    D.predictor_tail(x, p1, b1, p2, b2, 16, 18, logits=lo_a)
+    D.predictor_tail(x, p1, b1, p2, b2, 16, 18, logits=lo_b, hidden=hid)
+    torch.cuda.synchronize()
+    assert torch.equal(lo_a, lo_b)
+    xin = x.data.float().view(N * H * W, 256)
+    want = torch.nn.functional.softplus(xin @ w1.bfloat16().float().t() + b1)
+    got = hid.data.float().view(N * H * W, 512)
+    assert torch.isfinite(got).all()
+    assert float((got - want).abs().max()) <= 2 ** -7 * float(want.abs().max())
