@@ -78,6 +78,8 @@ _SIGNATURES = {
     'dhd_depth_head_bwd': (ctypes.c_int, [_P, _P, _P, _I, _I, _I, _I, _P, _I, _P]),
     'dhd_sfa_gate_bwd_workspace_bytes': (ctypes.c_size_t, [_I, _I, _I]),
     'dhd_sfa_gate_bwd': (ctypes.c_int, [_I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _P, _P, _P, _I, _I, _P, _P, _I, _P, _P]),
+    'dhd_sfa_gate_bwd_b16': (ctypes.c_int, [_I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _P, _P, _P, _I, _I, _P, _I, _I, _P, _I, _P, _P]),
+    'dhd_sfa_dx_combine': (ctypes.c_int, [_P, _I, _I, _P, _I, _I, _P, _P, _I, _I, _I, _P, _I, _I, _P]),
     'dhd_add_rowvec': (ctypes.c_int, [_P, _P, _I, _I, _I, _P, _I, _I, _P]),
     'dhd_pack_nchw_to_nhwc': (ctypes.c_int, [_P] + [_I] * 4 + [_P] + [_I] * 4 + [_P]),
     'dhd_occ_argmax': (ctypes.c_int, [_P, ctypes.c_long, _I, _P, _P]),

@@ -330,11 +330,17 @@ depth_head_bwd_kernel(const float* __restrict__ depth, const float* __restrict__
 //    dx[bev]     += g * a1             dx[vox] += g * (1-a1)        (fp32, accumulated)
 //    s[n][c]     += g * (bev - vox)
 // Blocks cover `pb` pixels of one image; their partial sums go to partial[(n*gridDim.x + bx)][C].
+// DXB16 (the bf16 form used by the training step: 2C fp32 channels per pixel written, re-read by the shortcut's
+// data-gradient epilogue, read-modified-written by mode 1 and read once more by the final row-vector add were ~2 GB of
+// traffic per step): mode 0 writes dx as a bf16 activation (dxh: [pix][dxh_ld], bev at dxh_coff, vox at dxh_coff + C),
+// mode 1 only reduces s -- its dx terms a1*g / (1-a1)*g need no x and are added by sfa_dx_combine_kernel.
+template <bool DXB16>
 __global__ void __launch_bounds__(256)
 sfa_gate_bwd_kernel(int mode, const __nv_bfloat16* __restrict__ g, int g_ld, int g_coff, const __nv_bfloat16* __restrict__ x,
                     int x_ld, int x_coff, int C, int HW, int pb, const float* __restrict__ a1,
                     const float* __restrict__ a2, __nv_bfloat16* __restrict__ dpre2, int d_ld, int d_coff,
-                    float* __restrict__ dx, float* __restrict__ partial) {
+                    float* __restrict__ dx, float* __restrict__ partial, __nv_bfloat16* __restrict__ dxh, int dxh_ld,
+                    int dxh_coff) {
   __shared__ float red[256][9];
   const int cg = C / 8, rows = 256 / cg;
   const int gi = threadIdx.x % cg, ri = threadIdx.x / cg;
@@ -352,8 +358,8 @@ sfa_gate_bwd_kernel(int mode, const __nv_bfloat16* __restrict__ g, int g_ld, int
       load8(g + r * g_ld + g_coff + gi * 8, gv);
       load8(x + r * x_ld + x_coff + gi * 8, bev);
       load8(x + r * x_ld + x_coff + C + gi * 8, vox);
-      float* db = dx + r * (size_t)(2 * C) + gi * 8;
-      float* dv = db + C;
+      float* db = DXB16 ? nullptr : dx + r * (size_t)(2 * C) + gi * 8;
+      float* dv = DXB16 ? nullptr : db + C;
       float ob[8], ov[8];
       if (mode == 0) {
         const float4* g2p = reinterpret_cast<const float4*>(a2 + r * C + gi * 8);
@@ -369,6 +375,10 @@ sfa_gate_bwd_kernel(int mode, const __nv_bfloat16* __restrict__ g, int g_ld, int
           acc[j] += gv[j] * (g2[j] * bev[j] - (1.f - g2[j]) * vox[j]);
         }
         store8(dpre2 + r * d_ld + d_coff + gi * 8, dp);
+      } else if (DXB16) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += gv[j] * (bev[j] - vox[j]);
+        continue;
       } else {
         const float4 b0 = *reinterpret_cast<const float4*>(db), b1 = *reinterpret_cast<const float4*>(db + 4);
         const float4 v0 = *reinterpret_cast<const float4*>(dv), v1 = *reinterpret_cast<const float4*>(dv + 4);
@@ -380,6 +390,11 @@ sfa_gate_bwd_kernel(int mode, const __nv_bfloat16* __restrict__ g, int g_ld, int
           ov[j] = pvv[j] + gv[j] * (1.f - g1[j]);
           acc[j] += gv[j] * (bev[j] - vox[j]);
         }
+      }
+      if (DXB16) {
+        store8(dxh + r * dxh_ld + dxh_coff + gi * 8, ob);
+        store8(dxh + r * dxh_ld + dxh_coff + C + gi * 8, ov);
+        continue;
       }
       *reinterpret_cast<float4*>(db) = make_float4(ob[0], ob[1], ob[2], ob[3]);
       *reinterpret_cast<float4*>(db + 4) = make_float4(ob[4], ob[5], ob[6], ob[7]);
@@ -398,6 +413,43 @@ sfa_gate_bwd_kernel(int mode, const __nv_bfloat16* __restrict__ g, int g_ld, int
 #pragma unroll
     for (int j = 0; j < 8; ++j) pp[j] = acc[j];
   }
+}
+
+// dx = dxb + [a1 * du | (1 - a1) * du] + ds[n]  (the channel-gate blend's data gradient and the squeeze path's per-image
+// row vector joined with what the fuse blend and the shortcut left in dxb); 8 channels of both halves per thread
+__global__ void __launch_bounds__(256)
+sfa_dx_combine_kernel(const __nv_bfloat16* __restrict__ dxb, int b_ld, int b_coff, const __nv_bfloat16* __restrict__ du,
+                      int u_ld, int u_coff, const float* __restrict__ a1, const float* __restrict__ ds, int C, long npix,
+                      int HW, __nv_bfloat16* __restrict__ out, int o_ld, int o_coff) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int cg = C / 8;
+  if (i >= npix * cg) return;
+  int c;
+  const long pix = fast_div(i, cg, &c);
+  c *= 8;
+  const int n = (int)fast_div(pix, HW);
+  float b[8], v[8], g[8];
+  unpack8(ld_nc_u4(dxb + pix * b_ld + b_coff + c), b);
+  unpack8(ld_nc_u4(dxb + pix * b_ld + b_coff + C + c), v);
+  unpack8(ld_nc_u4(du + pix * u_ld + u_coff + c), g);
+  const float4* gp = reinterpret_cast<const float4*>(a1 + (size_t)n * C + c);
+  const float4 ga = __ldg(gp), gb = __ldg(gp + 1);
+  const float g1[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    b[j] += g[j] * g1[j];
+    v[j] += g[j] * (1.f - g1[j]);
+  }
+  if (ds != nullptr) {
+    const float* dp = ds + (size_t)n * 2 * C + c;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      b[j] += __ldg(dp + j);
+      v[j] += __ldg(dp + C + j);
+    }
+  }
+  store8(out + pix * o_ld + o_coff + c, b);
+  store8(out + pix * o_ld + o_coff + C + c, v);
 }
 
 // sums[n][c] (+)= sum over the image's blocks (ascending)
@@ -1262,12 +1314,51 @@ extern "C" int dhd_sfa_gate_bwd(int mode, const void* g, int g_ld, int g_coff, c
   if (mode == 0) DHD_REQUIRE(ok8(C, d_ld, d_coff, dpre2) && ((uintptr_t)a2 & 15) == 0, "dpre2 / a2 alignment");
   cudaStream_t st = (cudaStream_t)stream;
   const int pb = sfa_pb(N, HW), nb = (HW + pb - 1) / pb;
-  sfa_gate_bwd_kernel<<<dim3(nb, N), 256, 0, st>>>(mode, (const __nv_bfloat16*)g, g_ld, g_coff, (const __nv_bfloat16*)x,
-                                                   x_ld, x_coff, C, HW, pb, a1, a2, (__nv_bfloat16*)dpre2, d_ld, d_coff,
-                                                   dx, workspace);
+  sfa_gate_bwd_kernel<false><<<dim3(nb, N), 256, 0, st>>>(mode, (const __nv_bfloat16*)g, g_ld, g_coff,
+                                                          (const __nv_bfloat16*)x, x_ld, x_coff, C, HW, pb, a1, a2,
+                                                          (__nv_bfloat16*)dpre2, d_ld, d_coff, dx, workspace, nullptr, 0, 0);
   DHD_CUDA_LAUNCH_CHECK("sfa_gate_bwd");
   image_sum_reduce_kernel<<<(N * C + 255) / 256, 256, 0, st>>>(workspace, nb, N, C, a1_sums, accumulate_sums);
   DHD_CUDA_LAUNCH_CHECK("image_sum_reduce");
+  return DHD_OK;
+}
+
+extern "C" int dhd_sfa_gate_bwd_b16(int mode, const void* g, int g_ld, int g_coff, const void* x, int x_ld, int x_coff,
+                                    int C, int N, int HW, const float* a1, const float* a2, void* dpre2, int d_ld,
+                                    int d_coff, void* dx, int dx_ld, int dx_coff, float* a1_sums, int accumulate_sums,
+                                    float* workspace, void* stream) {
+  DHD_REQUIRE(g && x && a1 && a1_sums && workspace, "null pointer");
+  DHD_REQUIRE(mode == 0 || mode == 1, "mode must be 0 (fuse) or 1 (u)");
+  DHD_REQUIRE(mode == 1 || (a2 != nullptr && dpre2 != nullptr && dx != nullptr), "mode 0 needs a2, dpre2 and dx");
+  DHD_REQUIRE(N > 0 && HW > 0 && C > 0 && C <= 2048, "bad shape");
+  DHD_REQUIRE(ok8(C, g_ld, g_coff, g) && ok8(C, x_ld, x_coff, x) && ((uintptr_t)a1 & 15) == 0,
+              "needs C % 8 == 0 and 16-byte aligned rows");
+  if (mode == 0)
+    DHD_REQUIRE(ok8(C, d_ld, d_coff, dpre2) && ((uintptr_t)a2 & 15) == 0 && ok8(C, dx_ld, dx_coff, dx) && dx_coff + 2 * C <= dx_ld,
+                "dpre2 / a2 / dx alignment");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int pb = sfa_pb(N, HW), nb = (HW + pb - 1) / pb;
+  sfa_gate_bwd_kernel<true><<<dim3(nb, N), 256, 0, st>>>(mode, (const __nv_bfloat16*)g, g_ld, g_coff, (const __nv_bfloat16*)x,
+                                                         x_ld, x_coff, C, HW, pb, a1, a2, (__nv_bfloat16*)dpre2, d_ld, d_coff,
+                                                         nullptr, workspace, (__nv_bfloat16*)dx, dx_ld, dx_coff);
+  DHD_CUDA_LAUNCH_CHECK("sfa_gate_bwd_b16");
+  image_sum_reduce_kernel<<<(N * C + 255) / 256, 256, 0, st>>>(workspace, nb, N, C, a1_sums, accumulate_sums);
+  DHD_CUDA_LAUNCH_CHECK("image_sum_reduce");
+  return DHD_OK;
+}
+
+extern "C" int dhd_sfa_dx_combine(const void* dxb, int b_ld, int b_coff, const void* du, int u_ld, int u_coff,
+                                  const float* a1, const float* ds, int C, int N, int HW, void* out, int o_ld, int o_coff,
+                                  void* stream) {
+  DHD_REQUIRE(dxb && du && a1 && out && N > 0 && HW > 0 && C > 0, "bad arguments");
+  DHD_REQUIRE(ok8(C, b_ld, b_coff, dxb) && ok8(C, u_ld, u_coff, du) && ok8(C, o_ld, o_coff, out) &&
+                  b_coff + 2 * C <= b_ld && o_coff + 2 * C <= o_ld && ((uintptr_t)a1 & 15) == 0,
+              "needs C % 8 == 0, 16-byte aligned rows holding 2C channels");
+  const long total = (long)N * HW * (C / 8);
+  sfa_dx_combine_kernel<<<(int)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)dxb, b_ld, b_coff, (const __nv_bfloat16*)du, u_ld, u_coff, a1, ds, C, (long)N * HW, HW,
+      (__nv_bfloat16*)out, o_ld, o_coff);
+  DHD_CUDA_LAUNCH_CHECK("sfa_dx_combine");
   return DHD_OK;
 }
 

@@ -27,6 +27,8 @@ import os as _os
 FUSED_BN_STATS = _os.environ.get('DHD_FUSED_BN_STATS', '1') != '0'
 # the occupancy head's Linear + Softplus + Linear in training: one fused launch (True) or two convolution launches (A/B)
 FUSED_TAIL = _os.environ.get('DHD_TRAIN_FUSED_TAIL', '1') != '0'
+# SFA backward: dL/dx collected in bf16 activations (True) or in fp32 tensors (A/B)
+SFA_BF16_DX = _os.environ.get('DHD_SFA_BF16_DX', '1') != '0'
 
 
 def set_bn_mode(mode):
@@ -512,26 +514,44 @@ class SFATrainer:
         act_bwd(dr, r, 'relu')
         dfuse = self._act('dfuse', N, H, W, C)
         self.res1.backward(fuse, dr, [dict(out_act=dfuse)])
-        dxa = self._f32('dxa', N, H, W, 2 * C)
-        dxb = self._f32('dxb', N, H, W, 2 * C)
+        lean = SFA_BF16_DX
         dpre2 = self._act('dpre2', N, H, W, C)
         S = self._f32('S', N, C)
         ws = _workspace(self.device, lib.dhd_sfa_gate_bwd_workspace_bytes(N, H * W, C))
-        _lib.check(lib.dhd_sfa_gate_bwd(0, _p(dfuse.data), dfuse.ld, dfuse.coff, _p(x.data), x.ld, x.coff, C, N, H * W,
-                                        _p(a1), _p(a2), _p(dpre2.data), dpre2.ld, dpre2.coff, _p(dxa), _p(S), 0,
-                                        _p(ws), _stream()), 'sfa_gate_bwd(fuse)')
-        # shortcut: weight gradient, and dxb = dxa + dgrad(dout) through the residual input of the epilogue
-        st2 = D.nhwc_strides(2 * C, H, W)
-        self.short.backward(x, dout, [dict(out_f32=(dxb, st2))], residual=(dxa, st2[:3]))
+        if lean:
+            # dL/dx is collected in bf16 activations: the fuse blend's part (dxa), + the shortcut's data gradient through
+            # the bf16 residual input of its epilogue (dxb), + the channel-gate blend's and the squeeze path's parts in
+            # one final pass (dhd_sfa_dx_combine) -- instead of 2C fp32 values per pixel written, re-read, read-modified-
+            # written and read again (~2 GB of traffic at DHD-S B=4)
+            dxa = self._act('dxa16', N, H, W, 2 * C)
+            dxb = self._act('dxb16', N, H, W, 2 * C)
+            _lib.check(lib.dhd_sfa_gate_bwd_b16(0, _p(dfuse.data), dfuse.ld, dfuse.coff, _p(x.data), x.ld, x.coff, C, N, H * W,
+                                                _p(a1), _p(a2), _p(dpre2.data), dpre2.ld, dpre2.coff, _p(dxa.data), dxa.ld,
+                                                dxa.coff, _p(S), 0, _p(ws), _stream()), 'sfa_gate_bwd_b16(fuse)')
+            self.short.backward(x, dout, [dict(out_act=dxb)], residual_act=dxa)
+        else:
+            dxa = self._f32('dxa', N, H, W, 2 * C)
+            dxb = self._f32('dxb', N, H, W, 2 * C)
+            _lib.check(lib.dhd_sfa_gate_bwd(0, _p(dfuse.data), dfuse.ld, dfuse.coff, _p(x.data), x.ld, x.coff, C, N, H * W,
+                                            _p(a1), _p(a2), _p(dpre2.data), dpre2.ld, dpre2.coff, _p(dxa), _p(S), 0,
+                                            _p(ws), _stream()), 'sfa_gate_bwd(fuse)')
+            # shortcut: weight gradient, and dxb = dxa + dgrad(dout) through the residual input of the epilogue
+            st2 = D.nhwc_strides(2 * C, H, W)
+            self.short.backward(x, dout, [dict(out_f32=(dxb, st2))], residual=(dxa, st2[:3]))
         dt = self._act('dt', N, H, W, C)
         _, sums = act_bwd(dpre2, None, None, want_sums=True)
         self.sp2.backward(t, dpre2, [dict(out_act=dt)], bias_sums=sums[0])
         _, sums = act_bwd(dt, t, 'relu', want_sums=True)
         du = self._act('du', N, H, W, C)
         self.sp1.backward(u, dt, [dict(out_act=du)], bias_sums=sums[0])
-        _lib.check(lib.dhd_sfa_gate_bwd(1, _p(du.data), du.ld, du.coff, _p(x.data), x.ld, x.coff, C, N, H * W,
-                                        _p(a1), None, None, 0, 0, _p(dxb), _p(S), 1, _p(ws), _stream()),
-                   'sfa_gate_bwd(u)')
+        if lean:
+            _lib.check(lib.dhd_sfa_gate_bwd_b16(1, _p(du.data), du.ld, du.coff, _p(x.data), x.ld, x.coff, C, N, H * W,
+                                                _p(a1), None, None, 0, 0, None, 0, 0, _p(S), 1, _p(ws), _stream()),
+                       'sfa_gate_bwd_b16(u)')
+        else:
+            _lib.check(lib.dhd_sfa_gate_bwd(1, _p(du.data), du.ld, du.coff, _p(x.data), x.ld, x.coff, C, N, H * W,
+                                            _p(a1), None, None, 0, 0, _p(dxb), _p(S), 1, _p(ws), _stream()),
+                       'sfa_gate_bwd(u)')
         # squeeze MLP (B rows): CUDA-core products through dhd_linear_rows
         lin = self._linear
         dz2 = (S * a1 * (1.0 - a1)).contiguous()
@@ -544,6 +564,12 @@ class SFATrainer:
         if not want_dx:
             return None
         ds = lin(dz0, self.fc0.weight.detach().float().t().contiguous()) * (1.0 / (H * W))
+        if lean:
+            dx = dxb                              # in place: every element is read and written by the same thread
+            _lib.check(lib.dhd_sfa_dx_combine(_p(dxb.data), dxb.ld, dxb.coff, _p(du.data), du.ld, du.coff, _p(a1),
+                                              _p(ds.contiguous()), C, N, H * W, _p(dx.data), dx.ld, dx.coff, _stream()),
+                       'sfa_dx_combine')
+            return dx
         dx = self._act('dx', N, H, W, 2 * C)
         _lib.check(lib.dhd_add_rowvec(_p(dxb), _p(ds.contiguous()), N, H * W, 2 * C, _p(dx.data), dx.ld, dx.coff,
                                       _stream()), 'add_rowvec')

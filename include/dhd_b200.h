@@ -318,6 +318,15 @@ int dhd_sfa_gate_bwd(int mode, const void* g, int g_ld, int g_coff, const void* 
                      int C, int N, int HW, const float* a1, const float* a2, void* dpre2, int d_ld,
                      int d_coff, float* dx, float* a1_sums, int accumulate_sums, float* workspace,
                      void* stream);
+/* bf16 form of the same (the training step's): mode 0 writes dx as a bf16 activation ([pix][dx_ld], bev at dx_coff,
+ * vox at dx_coff + C) instead of 2C fp32 values per pixel; mode 1 only reduces a1_sums (dx may be NULL) -- its data
+ * gradient a1*du | (1-a1)*du needs no x and is added by dhd_sfa_dx_combine:
+ *   out = dxb + [a1 * du | (1 - a1) * du] + ds[n]   (ds: [N][2C] per-image row vector or NULL; out may alias dxb) */
+int dhd_sfa_gate_bwd_b16(int mode, const void* g, int g_ld, int g_coff, const void* x, int x_ld, int x_coff, int C, int N,
+                         int HW, const float* a1, const float* a2, void* dpre2, int d_ld, int d_coff, void* dx, int dx_ld,
+                         int dx_coff, float* a1_sums, int accumulate_sums, float* workspace, void* stream);
+int dhd_sfa_dx_combine(const void* dxb, int b_ld, int b_coff, const void* du, int u_ld, int u_coff, const float* a1,
+                       const float* ds, int C, int N, int HW, void* out, int o_ld, int o_coff, void* stream);
 /* out (bf16 NHWC) = in (fp32 [N*HW][C]) + v[n][c] (v may be NULL) */
 int dhd_add_rowvec(const float* in, const float* v, int N, int HW, int C, void* out, int out_ld,
                    int out_coff, void* stream);
