@@ -185,62 +185,46 @@ wgrad_reduce_kernel(const float* __restrict__ partial, int splits, long n, int p
   dw[i] = accumulate ? dw[i] + a : a;
 }
 
-// dw_torch layout: dw is the parameter's gradient [Cout][cin_total][taps].  A block owns 32 (co, ci) pairs (lane = ci:
-// reads coalesced) x 8 slice groups (warp g adds slices g, g+8, .. in order: a 1x1 layer has up to 148 slices and one
-// thread per value made this pass a chain of dependent loads); the 8 group sums meet in shared memory, are added in
-// order and leave in output order with consecutive threads on consecutive addresses (a thread-per-value mapping
-// writes with a stride of `taps` floats: 9x the sectors on a 3x3 layer).  32-bit index arithmetic throughout.
-__global__ void __launch_bounds__(256)
+// dw_torch layout: dw is the parameter's gradient [Cout][cin_total][taps].  A block owns 32 (co, ci) pairs; thread =
+// (slice group g, tap t, lane = ci): reads are 128-byte coalesced, every thread has four independent loads in flight
+// and almost no state (the first version kept all taps of a pair in one thread: 64 registers, 38 % occupancy, and ncu
+// showed the pass waiting on DRAM latency -- the partials are NOT L2 hits -- at 17 % of the HBM bandwidth).  Group g adds
+// slices g, g+G, .. in order; the G group sums meet in shared memory, are added in order and leave in OUTPUT order with
+// consecutive threads on consecutive addresses.  32-bit index arithmetic throughout.
+__global__ void __launch_bounds__(320)
 wgrad_reduce_torch_kernel(const float* __restrict__ partial, int splits, long n, const float* __restrict__ scale,
                           float* __restrict__ dw, int accumulate, int Cout, int Cin, int taps, int cin_total, int cin_lo,
-                          int cin_used) {
-  __shared__ float grp[8][32][DHD_CONV_MAX_TAPS + 1];
-  const unsigned lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+                          int cin_used, int G) {
+  extern __shared__ float grp[];                 // [G][32 * taps]
+  const unsigned lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;      // warp = (g, t)
+  const unsigned g = wrp / (unsigned)taps, t = wrp - g * (unsigned)taps;
   const unsigned p0 = blockIdx.x * 32u;
   const unsigned npairs = (unsigned)Cout * (unsigned)cin_used;
   const unsigned p = p0 + lane;
-  float acc[DHD_CONV_MAX_TAPS];
-#pragma unroll
-  for (int t = 0; t < DHD_CONV_MAX_TAPS; ++t) acc[t] = 0.f;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
   if (p < npairs) {
     const unsigned co = p / (unsigned)cin_used, ci = p - co * (unsigned)cin_used;
-    const size_t i0 = (size_t)co * taps * Cin + ci;
-    int s = (int)g;
-    for (; s + 8 < splits; s += 16) {             // two slices per trip, loads first
-      const float* pa = partial + (size_t)s * n + i0;
-      const float* pb = partial + (size_t)(s + 8) * n + i0;
-      float qa[DHD_CONV_MAX_TAPS], qb[DHD_CONV_MAX_TAPS];
-#pragma unroll
-      for (int t = 0; t < DHD_CONV_MAX_TAPS; ++t)
-        if (t < taps) {
-          qa[t] = __ldg(pa + (size_t)t * Cin);
-          qb[t] = __ldg(pb + (size_t)t * Cin);
-        }
-#pragma unroll
-      for (int t = 0; t < DHD_CONV_MAX_TAPS; ++t)
-        if (t < taps) acc[t] += qa[t] + qb[t];
+    const float* src = partial + ((size_t)co * taps + t) * Cin + ci;
+    int sl = (int)g;
+    for (; sl + 3 * G < splits; sl += 4 * G) {
+      a0 += __ldg(src + (size_t)sl * n);
+      a1 += __ldg(src + (size_t)(sl + G) * n);
+      a2 += __ldg(src + (size_t)(sl + 2 * G) * n);
+      a3 += __ldg(src + (size_t)(sl + 3 * G) * n);
     }
-    if (s < splits) {
-      const float* pa = partial + (size_t)s * n + i0;
-#pragma unroll
-      for (int t = 0; t < DHD_CONV_MAX_TAPS; ++t)
-        if (t < taps) acc[t] += __ldg(pa + (size_t)t * Cin);
-    }
+    for (; sl < splits; sl += G) a0 += __ldg(src + (size_t)sl * n);
   }
-#pragma unroll
-  for (int t = 0; t < DHD_CONV_MAX_TAPS; ++t)
-    if (t < taps) grp[g][lane][t] = acc[t];
+  grp[g * 32u * taps + lane * taps + t] = (a0 + a1) + (a2 + a3);
   __syncthreads();
   const unsigned cnt = min(32u, npairs - p0) * (unsigned)taps;
-  for (unsigned k = threadIdx.x; k < cnt; k += 256u) {
-    const unsigned lp = k / (unsigned)taps, t = k - lp * (unsigned)taps;
-    float a = grp[0][lp][t];
-#pragma unroll
-    for (int gg = 1; gg < 8; ++gg) a += grp[gg][lp][t];
+  for (unsigned k = threadIdx.x; k < cnt; k += blockDim.x) {
+    float a = grp[k];
+    for (int gg = 1; gg < G; ++gg) a += grp[gg * 32u * taps + k];
+    const unsigned lp = k / (unsigned)taps, tt = k - lp * (unsigned)taps;
     const unsigned q = p0 + lp;
     const unsigned co = q / (unsigned)cin_used, ci = q - co * (unsigned)cin_used;
     if (scale != nullptr) a *= scale[co];
-    const unsigned o = (co * (unsigned)cin_total + (unsigned)cin_lo + ci) * (unsigned)taps + t;
+    const unsigned o = (co * (unsigned)cin_total + (unsigned)cin_lo + ci) * (unsigned)taps + tt;
     dw[o] = accumulate ? dw[o] + a : a;
   }
 }
@@ -345,9 +329,13 @@ extern "C" int dhd_conv2d_wgrad(const dhd_wgrad_desc* d, void* stream) {
   const long n = (long)d->Cout * d->taps * d->Cin;
   if (d->dw_torch != 0) {
     const long npairs = (long)d->Cout * d->dw_cin_used;
-    wgrad_reduce_torch_kernel<<<(int)((npairs + 31) / 32), 256, 0, st>>>(
+    int G = 8 / d->taps;                          // warps per block = G * taps <= 10
+    if (G < 1) G = 1;
+    if (G > P.splits) G = P.splits;
+    const int threads = 32 * d->taps * G;
+    wgrad_reduce_torch_kernel<<<(int)((npairs + 31) / 32), threads, (size_t)G * 32 * d->taps * sizeof(float), st>>>(
         d->partial, P.splits, n, d->scale, d->dw, d->accumulate, d->Cout, d->Cin, d->taps, d->dw_cin_total, d->dw_cin_lo,
-        d->dw_cin_used);
+        d->dw_cin_used, G);
   } else {
     wgrad_reduce_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(d->partial, P.splits, n, d->taps * d->Cin, d->scale,
                                                                 d->dw, d->accumulate);

@@ -1115,17 +1115,20 @@ extern "C" int dhd_mghs_pool_fwd(const dhd_mghs_cfg* cfg, const float* depth, co
     kern<<<grid, threads, smem, st>>>(P, zero_bytes, windows, prefetch);
     DHD_CUDA_LAUNCH_CHECK("mghs_pool_stream");
   } else {
-    constexpr int PZ = 6;
+    // planes per CTA: every plane group repeats the gather of its 32 cells, so fewer groups = fewer passes over the
+    // entry lists (DHD-L has 4x the frustum points of DHD-S for half the output bytes: its pool is gather-bound), at the
+    // price of shared memory (PZ * 8.4 KB) and therefore resident CTAs.  DHD_POOL_PZ = 6 | 9 | 17.
+    const int pz = DHD_TUNE("DHD_POOL_PZ", 6);   // measured (profiles/r02_pool_layouts_pz.txt): 6 is fastest, the gather is latency-bound and wants resident CTAs
     const int tiles_per_b = (int)((DyDx + 31) / 32);
-    const size_t smem = (size_t)PZ * kC * 33 * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaFuncSetAttribute(mghs_pool_nchw_kernel<PZ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)smem);
-      attr_set = true;
-    }
-    dim3 grid(cfg->B * tiles_per_b, (P.nplanes + PZ - 1) / PZ);
-    mghs_pool_nchw_kernel<PZ><<<grid, 256, smem, st>>>(P, tiles_per_b);
+    auto launch = [&](auto kern, int PZv) {
+      const size_t smem = (size_t)PZv * kC * 33 * sizeof(float);
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      dim3 grid(cfg->B * tiles_per_b, (P.nplanes + PZv - 1) / PZv);
+      kern<<<grid, 256, smem, st>>>(P, tiles_per_b);
+    };
+    if (pz >= 17) launch(mghs_pool_nchw_kernel<17>, 17);
+    else if (pz >= 9) launch(mghs_pool_nchw_kernel<9>, 9);
+    else launch(mghs_pool_nchw_kernel<6>, 6);
     DHD_CUDA_LAUNCH_CHECK("mghs_pool_nchw");
   }
   return DHD_OK;
