@@ -11,7 +11,7 @@
 
 namespace dhd {
 
-constexpr int kMaxSumBlocks = 1184;   // 8 resident blocks x 148 SMs: one full wave
+constexpr int kMaxSumBlocks = 592;    // 4 resident blocks (64 registers, 17 KB of shared memory each) x 148 SMs: one full wave
 
 __device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&v)[8]) {
   const uint4 q = *reinterpret_cast<const uint4*>(p);
@@ -42,7 +42,7 @@ __device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&v)[8]) {
 // act: 0 none, 1 relu (y > 0), 2 sigmoid (y (1 - y)), 3 softplus (1 - exp(-y)).
 // gate (optional, [N][C], rows_per_img rows per image): dz *= gate (a per-image channel gate that was
 // applied AFTER the activation in the forward epilogue, e.g. the SE gate).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 act_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int dy_ld, int dy_coff, const __nv_bfloat16* __restrict__ y,
                int y_ld, int y_coff, long rows, int C, int act, __nv_bfloat16* __restrict__ out, int out_ld,
                int out_coff, float* __restrict__ partial, long rows_per_block,
@@ -189,10 +189,13 @@ ce_norm_kernel(const uint8_t* __restrict__ labels, const uint8_t* __restrict__ m
 // dlogits bf16 NHWC rows [(b*Dy + y)*Dx + x][ld], channel z*ncls + k (the layout the last Linear's
 // backward GEMMs read); loss[0] += sum of weighted voxel losses * loss_weight / norm.
 // one voxel's class logits into registers (-inf beyond ncls): 8-byte loads when the row is 8-byte aligned (even ncls)
-__device__ __forceinline__ void load_logits(const float* __restrict__ lg, int ncls, float (&e)[32]) {
-  if ((ncls & 1) == 0) {
+// NC = compile-time bound of the class loops (18 for the DHD heads: no work on the 14 padding slots of the generic
+// 32-wide form; ncu showed both loss kernels issue-bound), ncls <= NC the run-time class count
+template <int NC>
+__device__ __forceinline__ void load_logits(const float* __restrict__ lg, int ncls, float (&e)[NC]) {
+  if ((ncls & 1) == 0 && (NC & 1) == 0) {
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
+    for (int k = 0; k < NC / 2; ++k) {
       if (2 * k < ncls) {
         const float2 t = __ldg(reinterpret_cast<const float2*>(lg) + k);
         e[2 * k] = t.x;
@@ -203,10 +206,11 @@ __device__ __forceinline__ void load_logits(const float* __restrict__ lg, int nc
     }
   } else {
 #pragma unroll
-    for (int k = 0; k < 32; ++k) e[k] = k < ncls ? __ldg(lg + k) : -INFINITY;
+    for (int k = 0; k < NC; ++k) e[k] = k < ncls ? __ldg(lg + k) : -INFINITY;
   }
 }
 
+template <int NC>
 __global__ void __launch_bounds__(256)
 ce_loss_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ labels, const uint8_t* __restrict__ mask,
                const float* __restrict__ cw, int ncls, int ignore, int B, int Dx, int Dy, int Dz, float loss_weight,
@@ -224,13 +228,16 @@ ce_loss_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ lab
   const long nvox = (long)B * Dx * Dy * Dz;
   const float inv = loss_weight / (norm[0] + 1.1920929e-07f);
   float acc = 0.f;
-  for (long v = (long)blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += (long)gridDim.x * blockDim.x) {
-    const int z = (int)(v % Dz);
-    long t = v / Dz;
-    const int y = (int)(t % Dy);
-    t /= Dy;
-    const int x = (int)(t % Dx);
-    const int b = (int)(t / Dx);
+  // 32-bit index arithmetic (host check: nvox * ncls < 2^31 is NOT required, only nvox < 2^31): the four 64-bit
+  // divisions per voxel were ~400 of this kernel's ~1150 instructions per warp trip
+  for (unsigned vv = blockIdx.x * blockDim.x + threadIdx.x; vv < (unsigned)nvox; vv += gridDim.x * blockDim.x) {
+    const long v = (long)vv;
+    const unsigned t1 = vv / (unsigned)Dz;
+    const int z = (int)(vv - t1 * (unsigned)Dz);
+    const unsigned t2 = t1 / (unsigned)Dy;
+    const int y = (int)(t1 - t2 * (unsigned)Dy);
+    const int b = (int)(t2 / (unsigned)Dx);
+    const int x = (int)(t2 - (unsigned)b * (unsigned)Dx);
     const float* lg = logits + v * ncls;
     const int l = labels[v];
     float w = 0.f;
@@ -248,14 +255,14 @@ ce_loss_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ lab
       }
       continue;
     }
-    float e[32];                     // ncls <= 32 on this path (host checks); logits stay in registers
+    float e[NC];                     // ncls <= NC (host dispatch); logits stay in registers
     float mx = -INFINITY;
     load_logits(lg, ncls, e);
 #pragma unroll
-    for (int k = 0; k < 32; ++k) mx = fmaxf(mx, e[k]);
+    for (int k = 0; k < NC; ++k) mx = fmaxf(mx, e[k]);
     float s = 0.f, ll = 0.f;
 #pragma unroll
-    for (int k = 0; k < 32; ++k) {
+    for (int k = 0; k < NC; ++k) {
       if (k == l) ll = e[k];
       e[k] = __expf(e[k] - mx);      // exp(-inf) = 0 beyond ncls
       s += e[k];
@@ -265,17 +272,17 @@ ce_loss_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ lab
     float dot = 0.f;
     if (scal) {
 #pragma unroll
-      for (int k = 0; k < 32; ++k)
+      for (int k = 0; k < NC; ++k)
         if (k < ncls) dot += (k == l ? s_gt[k] : s_gn[k]) * e[k] * is;
     }
 #pragma unroll
-    for (int k = 0; k < 32; k += 2) {
+    for (int k = 0; k < NC; k += 2) {
       if (k < ncls) {
         float a0 = wi * e[k] - (k == l ? w * inv : 0.f);
-        float a1 = wi * e[k + 1] - (k + 1 == l ? w * inv : 0.f);
+        float a1 = k + 1 < NC ? wi * e[k + 1 < NC ? k + 1 : k] - (k + 1 == l ? w * inv : 0.f) : 0.f;
         if (scal) {
           a0 += e[k] * is * ((k == l ? s_gt[k] : s_gn[k]) - dot);
-          if (k + 1 < ncls) a1 += e[k + 1] * is * ((k + 1 == l ? s_gt[k + 1] : s_gn[k + 1]) - dot);
+          if (k + 1 < ncls) a1 += e[k + 1 < NC ? k + 1 : k] * is * ((k + 1 == l ? s_gt[k + 1] : s_gn[k + 1]) - dot);
         }
         if (word_ok && k + 1 < ncls) {
           *reinterpret_cast<__nv_bfloat162*>(g + k) = __floats2bfloat162_rn(a0, a1);
@@ -788,13 +795,17 @@ adamw_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __r
 // Cnt_i = sum [t == i]; M = number of masked voxels.  Deterministic: warp shuffles in a fixed tree, per-block
 // partials [nblocks][3*32 + 1] reduced in order by occ_scal_coeffs_kernel.
 constexpr int kScalRow = 3 * 32 + 1;
+template <int NC>
 __global__ void __launch_bounds__(256)
 occ_scal_stats_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ labels, const uint8_t* __restrict__ mask,
                       int ncls, int ignore, long nvox, float* __restrict__ partial) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  float sp[32];
+  extern __shared__ float2 cls_acc[];                // [256 threads][33]: (Nom, Cnt) of class k for this thread's voxels
+  for (int i = threadIdx.x; i < 256 * 33; i += 256) cls_acc[i] = make_float2(0.f, 0.f);
+  __syncthreads();
+  float sp[NC];
 #pragma unroll
-  for (int k = 0; k < 32; ++k) sp[k] = 0.f;
+  for (int k = 0; k < NC; ++k) sp[k] = 0.f;
   float nom = 0.f, cnt = 0.f, m = 0.f;               // lane i of a warp carries class i's Nom / Cnt
   const long stride = (long)gridDim.x * blockDim.x;
   for (long v0 = (long)blockIdx.x * blockDim.x + wid * 32; v0 < nvox; v0 += stride) {
@@ -806,38 +817,56 @@ occ_scal_stats_kernel(const float* __restrict__ logits, const uint8_t* __restric
       if (t != ignore && t < ncls && (mask == nullptr || mask[v] != 0)) {
         l = t;
         const float* lg = logits + v * ncls;
-        float e[32], mx = -INFINITY, s = 0.f;
+        float e[NC], mx = -INFINITY, s = 0.f;
         load_logits(lg, ncls, e);
 #pragma unroll
-        for (int k = 0; k < 32; ++k) mx = fmaxf(mx, e[k]);
+        for (int k = 0; k < NC; ++k) mx = fmaxf(mx, e[k]);
 #pragma unroll
-        for (int k = 0; k < 32; ++k) {
+        for (int k = 0; k < NC; ++k) {
           e[k] = __expf(e[k] - mx);
           s += e[k];
         }
         const float is = 1.f / s;
 #pragma unroll
-        for (int k = 0; k < 32; ++k) {
+        for (int k = 0; k < NC; ++k) {
           sp[k] += e[k] * is;
           if (k == l) pl = e[k] * is;
         }
         m += 1.f;
       }
     }
-    for (int i = 0; i < ncls; ++i) {                 // class i's target voxels of this warp iteration
-      const float a = warp_sum(l == i ? pl : 0.f), c = warp_sum(l == i ? 1.f : 0.f);
-      if (lane == i) {
-        nom += a;
-        cnt += c;
+    // class l's Nom / Cnt: every thread keeps its own per-class pair in shared memory (no atomics: deterministic).
+    // The first version reduced every class over the warp in every trip: 18 x 2 five-step shuffle trees = ~1000 of the
+    // ~1150 instructions per trip, and ncu showed the kernel issue-bound (profiles/r02_loss_kernels.txt).
+    if (l >= 0) {
+      float2* mine = cls_acc + threadIdx.x * 33 + l;
+      float2 t = *mine;
+      t.x += pl;
+      t.y += 1.f;
+      *mine = t;
+    }
+  }
+  __syncwarp();
+  for (int i = 0; i < ncls; ++i) {                   // once per kernel: lane i <- class i over the warp's 32 threads, in order
+    float a = 0.f, c = 0.f;
+    if (lane == i) {
+      for (int t = 0; t < 32; ++t) {
+        const float2 q = cls_acc[(wid * 32 + t) * 33 + i];
+        a += q.x;
+        c += q.y;
       }
+      nom = a;
+      cnt = c;
     }
   }
   __shared__ float red[8][kScalRow];
 #pragma unroll
-  for (int k = 0; k < 32; ++k) {
+  for (int k = 0; k < NC; ++k) {
     const float t = warp_sum(sp[k]);
     if (lane == 0) red[wid][k] = t;
   }
+  if (lane == 0)
+    for (int k = NC; k < 32; ++k) red[wid][k] = 0.f;
   red[wid][32 + lane] = nom;
   red[wid][64 + lane] = cnt;
   m = warp_sum(m);
@@ -1254,6 +1283,7 @@ extern "C" int dhd_occ_ce_loss(const float* logits, const uint8_t* labels, const
   DHD_REQUIRE(logits && labels && losses && dlogits, "null pointer");
   DHD_REQUIRE(B > 0 && Dx > 0 && Dy > 0 && Dz > 0 && ncls > 0 && ncls <= 32, "bad shape (ncls <= 32)");
   DHD_REQUIRE(dl_ld >= Dz * ncls, "dlogits rows are too short");
+  DHD_REQUIRE((long)B * Dx * Dy * Dz < (1L << 31), "too many voxels for 32-bit indexing");
   const bool scal = weight_sem != 0.f || weight_geo != 0.f;
   DHD_REQUIRE(!scal || (workspace != nullptr && non_empty_idx >= 0 && non_empty_idx < ncls), "scal terms need the workspace");
   cudaStream_t st = (cudaStream_t)stream;
@@ -1266,7 +1296,17 @@ extern "C" int dhd_occ_ce_loss(const float* logits, const uint8_t* labels, const
     const int sblocks = (int)min((nvox + 255) / 256, (long)148 * 16);
     gt = workspace + (size_t)148 * 16 * kScalRow;
     gn = gt + 32;
-    occ_scal_stats_kernel<<<sblocks, 256, 0, st>>>(logits, labels, mask, ncls, ignore_index, nvox, workspace);
+    static bool stats_attr = false;
+    const size_t stats_smem = (size_t)256 * 33 * sizeof(float2);
+    if (!stats_attr) {
+      cudaFuncSetAttribute(occ_scal_stats_kernel<18>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stats_smem);
+      cudaFuncSetAttribute(occ_scal_stats_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stats_smem);
+      stats_attr = true;
+    }
+    if (ncls <= 18)
+      occ_scal_stats_kernel<18><<<sblocks, 256, stats_smem, st>>>(logits, labels, mask, ncls, ignore_index, nvox, workspace);
+    else
+      occ_scal_stats_kernel<32><<<sblocks, 256, stats_smem, st>>>(logits, labels, mask, ncls, ignore_index, nvox, workspace);
     DHD_CUDA_LAUNCH_CHECK("occ_scal_stats");
     occ_scal_coeffs_kernel<<<1, 1024, 0, st>>>(workspace, sblocks, ncls, non_empty_idx, weight_sem, weight_geo, losses + 2,
                                              gt, gn);
@@ -1274,7 +1314,11 @@ extern "C" int dhd_occ_ce_loss(const float* logits, const uint8_t* labels, const
   }
   ce_norm_kernel<<<blocks, 256, 0, st>>>(labels, mask, class_weight, ncls, ignore_index, nvox, losses + 1);
   DHD_CUDA_LAUNCH_CHECK("ce_norm");
-  ce_loss_kernel<<<blocks, 256, 0, st>>>(logits, labels, mask, class_weight, ncls, ignore_index, B, Dx, Dy, Dz,
+  if (ncls <= 18)
+    ce_loss_kernel<18><<<blocks, 256, 0, st>>>(logits, labels, mask, class_weight, ncls, ignore_index, B, Dx, Dy, Dz,
+                                         loss_weight, losses + 1, losses, (__nv_bfloat16*)dlogits, dl_ld, gt, gn);
+  else
+    ce_loss_kernel<32><<<blocks, 256, 0, st>>>(logits, labels, mask, class_weight, ncls, ignore_index, B, Dx, Dy, Dz,
                                          loss_weight, losses + 1, losses, (__nv_bfloat16*)dlogits, dl_ld, gt, gn);
   DHD_CUDA_LAUNCH_CHECK("ce_loss");
   return DHD_OK;
