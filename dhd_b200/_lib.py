@@ -53,6 +53,9 @@ _SIGNATURES = {
     'dhd_conv2d_fwd_batch': (ctypes.c_int, [_P, _I, _P]),
     'dhd_conv_pair_mode': (ctypes.c_int, [_I]),
     'dhd_conv2d_stat_rows': (ctypes.c_int, [_P]),
+    'dhd_stem_im2col': (ctypes.c_int, [_P] + [_I] * 7 + [_P, _I, _I, _I, _P]),
+    'dhd_maxpool3s2': (ctypes.c_int, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _P]),
+    'dhd_upsample_nearest_add': (ctypes.c_int, [_P, _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     'dhd_pack_conv_weights_batch': (ctypes.c_int, [_P, _I, _P]),
     'dhd_bn_fwd_coeffs_partial': (ctypes.c_int, [_P, _I, _I, ctypes.c_float, _P, _P, ctypes.c_float, ctypes.c_float] + [_P] * 7),
     'dhd_bn_bwd_sums_coeffs': (ctypes.c_int, [_P, _I, _I, _P, _I, _I, ctypes.c_long, _I, _P, ctypes.c_float] + [_P] * 9),

@@ -488,6 +488,90 @@ maxpool2_kernel(const __nv_bfloat16* __restrict__ in, int in_ld, int in_coff, in
   store_parts8(out + (((size_t)n * oH + oy) * oW + ox) * o_ld + o_coff + c, m, parts, o_ps);
 }
 
+// ---- image backbone helpers (mmdet ResNet stem / CustomFPN top-down path) ---------------------------------------
+// im2col of the ResNet stem (conv1: 7x7, stride 2, pad 3 on 3-channel images, torchvision / mmdet `ResNet.conv1`): the
+// K axis is (ky, kx, c) = ksize*ksize*Cin values zero-padded to Kpad (a multiple of 64), so the convolution becomes a
+// 1x1 tcgen05 GEMM over [N*oH*oW][Kpad].  img fp32 NCHW; 8 consecutive K values per thread.
+__global__ void __launch_bounds__(256)
+stem_im2col_kernel(const float* __restrict__ img, int N, int Cin, int H, int W, int ksize, int stride, int pad, int oH,
+                   int oW, int K, __nv_bfloat16* __restrict__ out, int o_ld, int o_ps, int parts) {
+  const int groups = (K + 7) / 8;                    // groups of 8 K values that hold data; the rest of the row stays 0
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)N * oH * oW * groups) return;
+  int g, ox, oy;
+  long p = fast_div(i, groups, &g);
+  p = fast_div(p, oW, &ox);
+  const int n = (int)fast_div(p, oH, &oy);
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = g * 8 + j;
+    float val = 0.f;
+    if (k < K) {
+      const int c = k % Cin, t = k / Cin;
+      const int kx = t % ksize, ky = t / ksize;
+      const int iy = oy * stride - pad + ky, ix = ox * stride - pad + kx;
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W) val = __ldg(img + (((size_t)n * Cin + c) * H + iy) * W + ix);
+    }
+    v[j] = val;
+  }
+  store_parts8(out + (((size_t)n * oH + oy) * oW + ox) * o_ld + g * 8, v, parts, o_ps);
+}
+
+// MaxPool2d(kernel 3, stride 2, padding 1) (ResNet.maxpool): bf16 NHWC (split parts summed before the max)
+__global__ void __launch_bounds__(256)
+maxpool3s2_kernel(const __nv_bfloat16* __restrict__ in, int in_ld, int in_coff, int in_ps, int N, int H, int W, int C,
+                  int oH, int oW, __nv_bfloat16* __restrict__ out, int o_ld, int o_coff, int o_ps, int parts) {
+  const int cg = C / 8;
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)N * oH * oW * cg) return;
+  int c, ox, oy;
+  long p = fast_div(i, cg, &c);
+  c *= 8;
+  p = fast_div(p, oW, &ox);
+  const int n = (int)fast_div(p, oH, &oy);
+  float m[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+#pragma unroll
+  for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+    for (int dx = -1; dx <= 1; ++dx) {
+      const int iy = 2 * oy + dy, ix = 2 * ox + dx;
+      if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
+      float v[8];
+      load_parts8(in + (((size_t)n * H + iy) * W + ix) * in_ld + in_coff + c, parts, in_ps, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], v[j]);
+    }
+  store_parts8(out + (((size_t)n * oH + oy) * oW + ox) * o_ld + o_coff + c, m, parts, o_ps);
+}
+
+// io += F.interpolate(lo, size=(H, W), mode='nearest') (CustomFPN's top-down path, necks/fpn.py:166-176):
+// src index = floor(dst * in / out), torch's nearest rule
+__global__ void __launch_bounds__(256)
+upsample_nearest_add_kernel(const __nv_bfloat16* __restrict__ lo, int l_ld, int l_coff, int l_ps, int h, int w,
+                            __nv_bfloat16* __restrict__ io, int o_ld, int o_coff, int o_ps, int N, int H, int W, int C,
+                            int parts) {
+  const int cg = C / 8;
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)N * H * W * cg) return;
+  int c, ox, oy;
+  long p = fast_div(i, cg, &c);
+  c *= 8;
+  p = fast_div(p, W, &ox);
+  const int n = (int)fast_div(p, H, &oy);
+  const int sy = min((int)floorf((float)oy * ((float)h / (float)H)), h - 1);
+  const int sx = min((int)floorf((float)ox * ((float)w / (float)W)), w - 1);
+  float a[8], b[8];
+  __nv_bfloat16* dst = io + (((size_t)n * H + oy) * W + ox) * o_ld + o_coff + c;
+  load_parts8(dst, parts, o_ps, a);
+  load_parts8(lo + (((size_t)n * h + sy) * w + sx) * l_ld + l_coff + c, parts, l_ps, b);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] += b[j];
+  store_parts8(dst, a, parts, o_ps);
+}
+
 __global__ void __launch_bounds__(256)
 upsample_bilinear_kernel(const __nv_bfloat16* __restrict__ in, int in_ld, int in_coff, int in_ps, int N, int H, int W,
                          int C, int oH, int oW, __nv_bfloat16* __restrict__ out, int o_ld, int o_coff, int o_ps,
@@ -1050,6 +1134,53 @@ extern "C" int dhd_upsample_bilinear(const void* in, int in_ld, int in_coff, int
       (const __nv_bfloat16*)in, in_ld, in_coff, in_part_stride, N, H, W, C, out_H, out_W, (__nv_bfloat16*)out, out_ld,
       out_coff, out_part_stride, parts);
   DHD_CUDA_LAUNCH_CHECK("upsample_bilinear");
+  return DHD_OK;
+}
+
+extern "C" int dhd_stem_im2col(const float* img, int N, int Cin, int H, int W, int ksize, int stride, int pad, void* out,
+                               int out_ld, int out_part_stride, int parts, void* stream) {
+  DHD_REQUIRE(img && out && N > 0 && Cin > 0 && H > 0 && W > 0 && ksize >= 1 && stride >= 1 && pad >= 0 && parts >= 1 &&
+                  parts <= 3, "bad arguments");
+  const int K = ksize * ksize * Cin;
+  DHD_REQUIRE(out_part_stride % 8 == 0 && out_part_stride >= (K + 7) / 8 * 8 && out_ld % 8 == 0 &&
+                  out_ld >= (parts - 1) * out_part_stride + (K + 7) / 8 * 8 && ((uintptr_t)out & 15) == 0,
+              "output rows must hold ksize*ksize*Cin values per part, 16-byte aligned");
+  const int oH = (H + 2 * pad - ksize) / stride + 1, oW = (W + 2 * pad - ksize) / stride + 1;
+  const long total = (long)N * oH * oW * ((K + 7) / 8);
+  DHD_REQUIRE(total < (1L << 31) * 256L, "image batch too large");
+  stem_im2col_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      img, N, Cin, H, W, ksize, stride, pad, oH, oW, K, (__nv_bfloat16*)out, out_ld, out_part_stride, parts);
+  DHD_CUDA_LAUNCH_CHECK("stem_im2col");
+  return DHD_OK;
+}
+
+extern "C" int dhd_maxpool3s2(const void* in, int in_ld, int in_coff, int in_part_stride, int N, int H, int W, int C,
+                              void* out, int out_ld, int out_coff, int out_part_stride, int parts, void* stream) {
+  DHD_REQUIRE(in && out && N > 0 && H >= 1 && W >= 1 && C > 0 && parts >= 1 && parts <= 3, "bad arguments");
+  DHD_REQUIRE(C % 8 == 0 && in_ld % 8 == 0 && in_coff % 8 == 0 && out_ld % 8 == 0 && out_coff % 8 == 0 &&
+                  in_part_stride % 8 == 0 && out_part_stride % 8 == 0 &&
+                  ((uintptr_t)in & 15) == 0 && ((uintptr_t)out & 15) == 0, "needs C % 8 == 0 and 16-byte aligned rows");
+  const int oH = (H - 1) / 2 + 1, oW = (W - 1) / 2 + 1;                  // floor((H + 2 - 3) / 2) + 1
+  const long total = (long)N * oH * oW * (C / 8);
+  maxpool3s2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)in, in_ld, in_coff, in_part_stride, N, H, W, C, oH, oW, (__nv_bfloat16*)out, out_ld, out_coff,
+      out_part_stride, parts);
+  DHD_CUDA_LAUNCH_CHECK("maxpool3s2");
+  return DHD_OK;
+}
+
+extern "C" int dhd_upsample_nearest_add(const void* lo, int lo_ld, int lo_coff, int lo_part_stride, int h, int w, void* io,
+                                        int io_ld, int io_coff, int io_part_stride, int N, int H, int W, int C, int parts,
+                                        void* stream) {
+  DHD_REQUIRE(lo && io && N > 0 && h > 0 && w > 0 && H > 0 && W > 0 && C > 0 && parts >= 1 && parts <= 3, "bad arguments");
+  DHD_REQUIRE(C % 8 == 0 && lo_ld % 8 == 0 && lo_coff % 8 == 0 && io_ld % 8 == 0 && io_coff % 8 == 0 &&
+                  lo_part_stride % 8 == 0 && io_part_stride % 8 == 0 &&
+                  ((uintptr_t)lo & 15) == 0 && ((uintptr_t)io & 15) == 0, "needs C % 8 == 0 and 16-byte aligned rows");
+  const long total = (long)N * H * W * (C / 8);
+  upsample_nearest_add_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)lo, lo_ld, lo_coff, lo_part_stride, h, w, (__nv_bfloat16*)io, io_ld, io_coff, io_part_stride, N,
+      H, W, C, parts);
+  DHD_CUDA_LAUNCH_CHECK("upsample_nearest_add");
   return DHD_OK;
 }
 

@@ -498,6 +498,17 @@ int dhd_maxpool2(const void* in, int in_ld, int in_coff, int in_part_stride, int
 int dhd_upsample_bilinear(const void* in, int in_ld, int in_coff, int in_part_stride, int N, int H, int W,
                           int C, int out_H, int out_W, void* out, int out_ld, int out_coff,
                           int out_part_stride, int parts, void* stream);
+/* image backbone helpers (the §8(f)-4 widening: mmdet ResNet-50 / -101 `img_backbone` + necks/fpn.py CustomFPN):
+ * stem im2col -- conv1 (7x7, stride 2, pad 3, 3-channel fp32 NCHW images) becomes a 1x1 tcgen05 GEMM over rows of
+ * K = ksize*ksize*Cin values ordered (ky, kx, c), zero-padded to the row length (split-bf16 parts at out_part_stride;
+ * the caller zero-fills the padding once);  MaxPool2d(3, 2, 1);  io += F.interpolate(lo, size=(H, W), 'nearest')
+ * (fpn.py:166-176) */
+int dhd_stem_im2col(const float* img, int N, int Cin, int H, int W, int ksize, int stride, int pad, void* out, int out_ld,
+                    int out_part_stride, int parts, void* stream);
+int dhd_maxpool3s2(const void* in, int in_ld, int in_coff, int in_part_stride, int N, int H, int W, int C, void* out,
+                   int out_ld, int out_coff, int out_part_stride, int parts, void* stream);
+int dhd_upsample_nearest_add(const void* lo, int lo_ld, int lo_coff, int lo_part_stride, int h, int w, void* io, int io_ld,
+                             int io_coff, int io_part_stride, int N, int H, int W, int C, int parts, void* stream);
 /* backward of the encoder helpers: MaxPool2d(2) (gradient to the first maximum of each window, as torch) and
  * bilinear Upsample(align_corners=True) (dx fp32 [N*H*W][C], zeroed here, accumulated with atomics) */
 int dhd_maxpool2_bwd(const void* x, int x_ld, int x_coff, const void* dy, int dy_ld, int dy_coff, int N, int H, int W,

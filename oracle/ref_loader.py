@@ -100,6 +100,14 @@ def _build_conv_layer(cfg, *args, **kwargs):
     raise KeyError(typ)
 
 
+class _BaseModule(nn.Module):
+    """mmcv.runner.BaseModule: an nn.Module whose constructor takes (and here ignores) init_cfg."""
+
+    def __init__(self, init_cfg=None):
+        super().__init__()
+        self.init_cfg = init_cfg
+
+
 _LOADED = {}
 
 
@@ -120,7 +128,7 @@ def _install_stubs(bev_pool_v2_impl):
 
     necks, heads, backbones = _Registry(), _Registry(), _Registry()
     mod('mmcv')
-    mod('mmcv.runner', BaseModule=nn.Module, force_fp32=force_fp32)
+    mod('mmcv.runner', BaseModule=_BaseModule, force_fp32=force_fp32, auto_fp16=force_fp32)
     mod('mmcv.cnn', build_conv_layer=_build_conv_layer, ConvModule=_ConvModule,
         build_norm_layer=lambda cfg, n, postfix='': ('bn' + str(postfix), nn.BatchNorm2d(n)))
     mod('mmcv.cnn.bricks', ConvModule=_ConvModule).__path__ = []
@@ -173,8 +181,9 @@ def load_reference():
     un = _exec('refplg.models.backbones.unet', 'models/backbones/unet.py')
     rn = _exec('refplg.models.backbones.resnet', 'models/backbones/resnet.py')
     fp = _exec('refplg.models.necks.lss_fpn', 'models/necks/lss_fpn.py')
+    cf = _exec('refplg.models.necks.fpn', 'models/necks/fpn.py')
     ns = types.SimpleNamespace(
-        UNet=un.UNet, CustomResNet=rn.CustomResNet, FPN_LSS=fp.FPN_LSS,
+        UNet=un.UNet, CustomResNet=rn.CustomResNet, FPN_LSS=fp.FPN_LSS, CustomFPN=cf.CustomFPN,
         MGHS=lh.MGHS, MGHS_Depth=lh.MGHS_Depth, MGHS_Stereo=lh.MGHS_Stereo,
         HeightNet=dn.HeightNet, DepthNet=dn.DepthNet, ASPP=dn.ASPP, SFA=mix.SFA,
         predictor=oh.predictor, lss_heightmap=lh, depthnet=dn, mix=mix, occ_head=oh, semkitti_loss=sk)

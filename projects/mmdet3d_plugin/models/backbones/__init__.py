@@ -1,3 +1,4 @@
+from .image_resnet import ResNet
 from .resnet import CustomResNet
 from .unet import UNet
 

@@ -83,8 +83,10 @@ class DHD(C.BaseModule):
         external backbone."""
         B, N, C, imH, imW = img.shape
         vt = self.img_view_transformer
+        fH, fW = vt.input_size[0] // vt.downsample, vt.input_size[1] // vt.downsample
+        if C == vt.in_channels and (imH, imW) == (fH, fW) and not stereo:
+            return img, None                              # already the feature map the view transformer reads
         if self.img_backbone is None or isinstance(self.img_backbone, MissingModule):
-            fH, fW = vt.input_size[0] // vt.downsample, vt.input_size[1] // vt.downsample
             if C == vt.in_channels and (imH, imW) == (fH, fW):
                 return img, None
             if self.img_backbone is None:

@@ -1,3 +1,4 @@
+from .fpn import CustomFPN
 from .identity import Identity
 from .lss_fpn import FPN_LSS
 from .lss_heightmap import MGHS, MGHS_Depth, MGHS_Stereo

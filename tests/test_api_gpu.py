@@ -153,7 +153,7 @@ def test_detector_reference_api_inference(cuda_lib):
     from dhd_b200 import synth
     from tests.test_encoders_gpu import _dhd_s_model_cfg
     cfg = _dhd_s_model_cfg()
-    cfg['img_backbone'] = dict(type='ResNet', depth=50)          # mmdet's: not registered in this environment
+    cfg['img_backbone'] = dict(type='SwinTransformer', embed_dims=128)     # DHD-L's backbone: not part of this build
     model = C.DETECTORS.build(cfg).eval()
     model.load_state_dict(DO.seeded_state_dict(model, 77))
     model = model.cuda()
