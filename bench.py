@@ -252,18 +252,25 @@ def run_ours(args):
         torch.cuda.empty_cache()
 
     # ---- inference (the round-1 headline): image features -> occupancy class map
-    def inference(precision, encoders, seconds):
-        step = HotPathStep(cfg, B, precision=precision, use_graph=not args.no_graph, encoders=encoders)
-        step.make_host_inputs(rig, seed=100 + rank)
-        step.alloc_static(host_infer)
-        step.upload(host_infer)
+    def inference(precision, encoders, seconds, images=False):
+        step = HotPathStep(cfg, B, precision=precision, use_graph=not args.no_graph, encoders=encoders, images=images)
+        h_in = step.make_host_inputs(rig, seed=100 + rank)
+        if not images:
+            h_in = host_infer
+        step.alloc_static(h_in)
+        step.upload(h_in)
         g = step.capture()
         for _ in range(3):
             step.run()
         ms, n, _, pms = _region(lambda ev: step.run(pool_events=ev), K, seconds, barrier, st, shard, events=64)
         out = {'precision': precision, 'ms_per_step': None, 'cuda_graph': bool(g), 'launches_per_step': step.launches_per_step,
                'stages': step.stage_names(), 'graph_error': getattr(step, 'graph_error', None)}
-        if not encoders and precision == args.precision:
+        if images:
+            ms_e, n_e = _e2e_region(step, h_in, K, seconds, barrier, st, shard, ms / n)
+            ms_e = shard.max_over_ranks([ms_e], device='cuda')[0]
+            out['e2e'] = {'value': world * B * n_e / (ms_e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': step.h2d_bytes,
+                          'd2h_bytes_per_step': step.d2h_bytes}
+        if not encoders and not images and precision == args.precision:
             ms_e, n_e = _e2e_region(step, host_infer, K, seconds, barrier, st, shard, ms / n)
             ms_e = shard.max_over_ranks([ms_e], device='cuda')[0]
             out['e2e'] = {'value': world * B * n_e / (ms_e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': step.h2d_bytes,
@@ -316,6 +323,13 @@ def run_ours(args):
         extras['inference_with_encoders'] = inference(args.precision, True, 0.2 if quick else 1.0)
         from dhd_b200.pipeline import encoder_flops
         extras['inference_with_encoders']['encoder_tflops_algorithmic'] = encoder_flops(B) / 1e12
+    if not args.no_encoders:
+        # the whole detector: camera IMAGES -> ResNet-50 + CustomFPN -> view transformer -> encoders -> SFA -> head
+        extras['inference_from_images'] = inference(args.precision, True, 0.2 if quick else 1.0, images=True)
+        extras['inference_from_images']['what'] = (
+            'DHD-S end to end from the 6 x 256x704 camera images (img_backbone ResNet-50 + img_neck CustomFPN of DHD-S.py:44-62 '
+            'on the tcgen05 convolution kernel, then the widened hot path with the real BEV / voxel encoders) to the uint8 '
+            'class map; e2e = pinned host images in, class map out')
     if world == 1 and not args.no_dhdl:
         extras['dhd_l_view_transformer'] = dhdl_extra(args.precision if args.precision in ('bf16', 'fp32') else 'bf16')
     if world == 1 and not quick:

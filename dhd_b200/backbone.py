@@ -32,7 +32,7 @@ def stem_im2col(img, ksize, stride, pad, parts):
     K = ksize * ksize * Cin
     Kp = (K + 63) // 64 * 64
     oH, oW = (H + 2 * pad - ksize) // stride + 1, (W + 2 * pad - ksize) // stride + 1
-    out = D.Act(torch.zeros(N, oH, oW, parts * Kp, dtype=torch.bfloat16, device=img.device), Kp, parts)
+    out = D.Act.empty(N, oH, oW, Kp, parts, img.device)          # the kernel writes the zero padding of every row too
     _lib.check(_lib.load().dhd_stem_im2col(_p(img), N, Cin, H, W, ksize, stride, pad, _p(out.data), out.ld, out.part_stride,
                                            parts, _stream()), 'stem_im2col')
     return out

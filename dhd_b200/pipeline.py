@@ -104,7 +104,7 @@ def pool_traffic_bytes():
 
 class HotPathStep:
     def __init__(self, cfg, B, precision='bf16', deterministic=True, device='cuda', seed=0,
-                 use_graph=True, encoders=False, keep_logits=False):
+                 use_graph=True, encoders=False, keep_logits=False, images=False, backbone_depth=50):
         from projects.mmdet3d_plugin.models.dense_heads.occ_head import predictor
         from projects.mmdet3d_plugin.models.necks.lss_heightmap import MGHS
         from projects.mmdet3d_plugin.models.necks.mix import SFA
@@ -128,6 +128,17 @@ class HotPathStep:
         self.head = predictor(in_dim=256, out_dim=256, Dz=16, num_classes=18, use_predicter=True,
                               class_balance=False, loss_occ=None, precision=precision).eval().to(self.device)
         self.encoders = encoders
+        self.images = images                  # True: the step starts from the camera IMAGES (ResNet + CustomFPN, 8(f)-4)
+        if images:
+            # img_backbone / img_neck of DHD-S.py:44-62 (ResNet-50, out_indices (2, 3) -> CustomFPN 256 ch at 1/16)
+            from projects.mmdet3d_plugin.models.backbones.image_resnet import ResNet
+            from projects.mmdet3d_plugin.models.necks.fpn import CustomFPN
+            from .backbone import CustomFPNEngine, ResNetEngine
+            self.img_backbone = ResNet(depth=backbone_depth, out_indices=(2, 3), precision=precision).eval().to(self.device)
+            self.img_neck = CustomFPN(in_channels=[1024, 2048], out_channels=self.Cin, num_outs=1, start_level=0, out_ids=[0],
+                                      precision=precision).eval().to(self.device)
+            self.e_img_backbone = ResNetEngine(self.img_backbone, precision, self.device)
+            self.e_img_neck = CustomFPNEngine(self.img_neck, precision, self.device)
         self.keep_logits = keep_logits        # True: also write the fp32 logits (184 MB at B=4) -- parity tests
         if encoders:
             # the widened path: the real BEV encoder and the three voxel encoders of
@@ -182,7 +193,9 @@ class HotPathStep:
     def stage_names(self):
         mid = ['split(pool outputs -> bf16)', 'CustomResNet + FPN_LSS (BEV encoder)', '3x UNet (voxel encoders)'] \
             if self.encoders else ['[encoder stand-in: resident bf16 NHWC features]']
-        return ['pack', 'depth_net(1x1+softmax)', 'HeightNet(+softmax)', 'height_to_mask',
+        first = ['ResNet-%d image backbone (stem im2col + tcgen05 GEMM, MaxPool, Bottleneck stages)' % self.img_backbone.depth,
+                 'CustomFPN'] if self.images else ['pack']
+        return first + ['depth_net(1x1+softmax)', 'HeightNet(+softmax)', 'height_to_mask',
                 'mghs_prepare(geometry+binning, 4 grids)', 'mghs_pool_fwd(nhwc, fused 4-pass)'] + mid + \
             ['SFA', 'predictor 3x3 conv', 'fused head tail: Linear+Softplus+Linear+per-z argmax (dhd_predictor_tail)'
              if self.head_engine.fused_tail_ok() and not self.keep_logits else 'predictor MLP (2 GEMMs) + occ_argmax']
@@ -192,7 +205,11 @@ class HotPathStep:
         """Pinned host buffers of one step: image features + camera geometry."""
         s2e, e2g, K, pr, pt, bda = rig
         g = torch.Generator().manual_seed(seed)
-        x = torch.randn(self.B, self.N, self.Cin, self.fH, self.fW, generator=g)
+        if self.images:
+            ih, iw = self.cfg['input_size']
+            x = torch.randn(self.B, self.N, 3, ih, iw, generator=g)       # normalised camera images
+        else:
+            x = torch.randn(self.B, self.N, self.Cin, self.fH, self.fW, generator=g)
         h = {'x': x, 'sensor2ego': s2e.contiguous(), 'ego2global': e2g.contiguous(), 'cam2imgs': K.contiguous(),
              'post_rots': pr.contiguous(), 'post_trans': pt.contiguous(), 'bda': bda.contiguous()}
         h = {k: v.pin_memory() for k, v in h.items()}
@@ -234,7 +251,11 @@ class HotPathStep:
             with torch.cuda.stream(self._prep_stream):
                 self.plan.prepare(frustum=self.frustum, cam_mats=cam_mats,
                                   deterministic=self.deterministic, workspace=self.workspace)
-        xa = D.pack_input(s['x'].view(B * N, self.Cin, self.fH, self.fW), self.parts)
+        if self.images:
+            feats = self.e_img_backbone(s['x'].view(B * N, 3, *self.cfg['input_size']))
+            xa = self.e_img_neck(feats)[0]
+        else:
+            xa = D.pack_input(s['x'].view(B * N, self.Cin, self.fH, self.fW), self.parts)
         # depth_net's 1x1 (132 tiles) rides in the launch of HeightNet's first BasicBlock convolution
         depth, feat, depth_conv = self.depth_engine(xa, defer=True)
         main.wait_event(gate_ready)

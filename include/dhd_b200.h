@@ -500,8 +500,8 @@ int dhd_upsample_bilinear(const void* in, int in_ld, int in_coff, int in_part_st
                           int out_part_stride, int parts, void* stream);
 /* image backbone helpers (the §8(f)-4 widening: mmdet ResNet-50 / -101 `img_backbone` + necks/fpn.py CustomFPN):
  * stem im2col -- conv1 (7x7, stride 2, pad 3, 3-channel fp32 NCHW images) becomes a 1x1 tcgen05 GEMM over rows of
- * K = ksize*ksize*Cin values ordered (ky, kx, c), zero-padded to the row length (split-bf16 parts at out_part_stride;
- * the caller zero-fills the padding once);  MaxPool2d(3, 2, 1);  io += F.interpolate(lo, size=(H, W), 'nearest')
+ * K = ksize*ksize*Cin (<= 512) values ordered (ky, kx, c), zero-padded to out_part_stride (split-bf16 parts at
+ * out_part_stride; the padding is written by the kernel);  MaxPool2d(3, 2, 1);  io += F.interpolate(lo, size=(H, W), 'nearest')
  * (fpn.py:166-176) */
 int dhd_stem_im2col(const float* img, int N, int Cin, int H, int W, int ksize, int stride, int pad, void* out, int out_ld,
                     int out_part_stride, int parts, void* stream);

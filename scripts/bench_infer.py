@@ -1,6 +1,6 @@
 """Inference step of the hot path alone (eager launches, for ncu launch lists / --set full captures).  Usage:
 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file out.csv \
-    python scripts/bench_infer.py [steps] [precision] [encoders]"""
+    python scripts/bench_infer.py [steps] [precision] [encoders] [images]"""
 import os
 import sys
 
@@ -14,8 +14,9 @@ from dhd_b200 import synth as O  # noqa: E402
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 precision = sys.argv[2] if len(sys.argv) > 2 else 'bf16'
 encoders = len(sys.argv) > 3 and sys.argv[3] not in ('0', 'no')
+images = len(sys.argv) > 4 and sys.argv[4] not in ('0', 'no')
 cfg, B = O.DHD_S, 4
-step = HotPathStep(cfg, B, precision=precision, use_graph=False, encoders=encoders)
+step = HotPathStep(cfg, B, precision=precision, use_graph=False, encoders=encoders, images=images)
 host = step.make_host_inputs(O.synthetic_rig(B, cfg['ncams'], cfg['input_size'], seed=100), seed=100)
 step.alloc_static(host)
 step.upload(host)
