@@ -695,16 +695,24 @@ class TrainStep(HotPathStep):
         if not hasattr(self, '_prep_stream'):
             self._prep_stream = torch.cuda.Stream()
         self._prep_stream.wait_stream(main)
-        with torch.cuda.stream(self._prep_stream):
-            self.plan.prepare(frustum=self.frustum, sensor2ego=s['sensor2ego'], cam2imgs=s['cam2imgs'],
-                              post_rots=s['post_rots'], post_trans=s['post_trans'], bda=s['bda'],
-                              deterministic=self.deterministic, workspace=self.workspace)
+        with torch.cuda.stream(self._prep_stream):     # the ~25 tiny library launches of the per-camera 3x3s: at once
+            cam_mats = self.plan.camera_matrices(s['sensor2ego'], s['cam2imgs'], s['post_rots'], s['post_trans'], s['bda'])
+
+        def fork_prepare():        # the binning kernels late in HeightNet: the bins are still in L2 when the pool starts
+            self._prep_stream.wait_stream(main)
+            with torch.cuda.stream(self._prep_stream):
+                self.plan.prepare(frustum=self.frustum, cam_mats=cam_mats, deterministic=self.deterministic,
+                                  workspace=self.workspace)
+        self.t_height.trunk_hook = fork_prepare
         # ---- forward
         xa = D.pack_input(s['x'].view(B * N, self.Cin, self.fH, self.fW), 1)
         depth, feat = self.t_depth.forward(xa)
         mlp = self.vt.get_mlp_input(s['sensor2ego'], s['ego2global'], s['cam2imgs'], s['post_rots'],
                                     s['post_trans'], s['bda'])
         height = self.t_height.forward(xa, mlp)
+        if self.t_height.trunk_hook is not None:     # a trunk without ASPP never fired it
+            self.t_height.trunk_hook = None
+            fork_prepare()
         pixmask = height_to_mask(height, self.cfg['height_range'], self.cfg['mask_range'])
         main.wait_stream(self._prep_stream)
         self._last = {'depth': depth, 'feat': feat, 'height': height, 'pixmask': pixmask}

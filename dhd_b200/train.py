@@ -827,6 +827,9 @@ class HeightNetTrainer:
         ib = lin(x5, self.w5s)
         ha = self._act('ha', N, H, W, C)
         self.aspp_out.forward(cat, [dict(act='relu', out_act=ha)], img_bias=ib)
+        hook, self.trunk_hook = getattr(self, 'trunk_hook', None), None
+        if hook is not None:                      # one-shot: the pipeline forks the binning kernels here (late, L2-hot bins)
+            hook()
         if self.dropout_p > 0.0:                     # in place: everything downstream (and the backward) sees the dropped map
             dropout_(ha, self.dropout_p, self.rng, salt=1)
         sv = self.saved
