@@ -8,7 +8,7 @@ import re
 import subprocess
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-PAT = re.compile(r'\b(UTCHMMA|UTMALDG(?:\.\dD)?|UTMASTG(?:\.\dD)?|LDTM(?:\.x\d+)?|UBLKCP(?:\.[A-Z.]+)?|UTCBAR|UTCATOMSWS|SYNCS\.[A-Z]+|MUFU\.[A-Z0-9]+)')
+PAT = re.compile(r'\b(UTCHMMA(?:\.2CTA)?|UTMALDG(?:\.\dD)?(?:\.2CTA)?|UTMASTG(?:\.\dD)?|LDTM(?:\.x\d+)?|UBLKCP(?:\.[A-Z.]+)?|UTCBAR(?:\.2CTA)?(?:\.MULTICAST)?|UTCATOMSWS(?:\.2CTA)?|SYNCS\.[A-Z]+|MUFU\.[A-Z0-9]+)')
 
 
 def main():
