@@ -1,5 +1,5 @@
 """Training step of the hot path alone (eager launches, for ncu launch lists).  Usage:
-ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file out.csv python scripts/bench_train.py [steps]"""
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file out.csv python scripts/bench_train.py [steps] [frozen|batch] [encoders]"""
 import os
 import sys
 
@@ -12,8 +12,9 @@ from dhd_b200 import synth as O  # noqa: E402
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 bn = sys.argv[2] if len(sys.argv) > 2 else 'frozen'          # 'batch': BatchNorm2d in training mode + Dropout
+encoders = len(sys.argv) > 3 and sys.argv[3] not in ('0', 'no')
 cfg, B = O.DHD_S, 4
-ts = TrainStep(cfg, B, bn=bn)
+ts = TrainStep(cfg, B, bn=bn, encoders=encoders)
 host = ts.make_host_inputs(O.synthetic_rig(B, cfg['ncams'], cfg['input_size'], seed=100), seed=100)
 ts.alloc_static(host)
 ts.upload(host)
