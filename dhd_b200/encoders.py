@@ -11,6 +11,8 @@ ReLU / residual live in the epilogues, and concatenations are channel slices of 
 producers write in place -- no torch.cat, no F.pad, no layout copies."""
 import ctypes
 
+import os
+
 import torch
 
 from . import _lib
@@ -143,6 +145,16 @@ class _ResBlock:
         nh = D.nhwc_strides(self.Cout, oH, oW)
         t = new(x.N, oH, oW, self.Cout)
         self.c1(x, [dict(act='relu', out_act=t)], stride=self.stride)
+        if x.parts == 1 and os.environ.get('DHD_BF16_RESIDUAL', '1') != '0':
+            # bf16 speed mode: the identity path is the bf16 activation itself / the downsample conv's bf16 output -- no
+            # fp32 copy written by one block and re-read by the next (at DHD-L's 1024-channel 200x200 maps: 328 MB each)
+            idn = x
+            if self.ds is not None:
+                idn = new(x.N, oH, oW, self.Cout)
+                self.ds(x, [dict(out_act=idn)], stride=self.stride)
+            out = new(x.N, oH, oW, self.Cout)
+            self.c2(t, [dict(act='relu', out_act=out)], residual_act=idn)
+            return out, None
         if self.ds is not None:
             idn = new32(x.N, oH, oW, self.Cout)
             self.ds(x, [dict(out_f32=(idn, nh))], stride=self.stride)
