@@ -112,7 +112,7 @@ class EngineOwner:
     The engine is a SNAPSHOT of the parameters, so it is rebuilt whenever the module could have changed under it:
     a parameter / buffer modified in place (optimizer.step, `with no_grad(): p.copy_()` -- the tensor version
     counters), replaced or moved (`.to()`, `.cuda()`, `.half()`: `_apply`), reloaded (`load_state_dict`), or the
-    module switched between train() and eval().  One blind spot remains: `p.data.copy_(...)` (mmcv's EMA hook) does
+    module switched between train() and eval() (a repeated call with the same mode keeps them).  One blind spot remains: `p.data.copy_(...)` (mmcv's EMA hook) does
     not touch the version counter -- such writers are caught by the train()/eval() switch that follows them in the
     reference's runner, or call `invalidate_engines(model)`."""
 
@@ -133,7 +133,10 @@ class EngineOwner:
             self.__dict__[k] = None
 
     def train(self, mode=True):
-        self.invalidate()
+        # only a real switch drops the engines: a runner that calls model.eval() before every test batch must not pay
+        # a rebuild (BatchNorm folding + weight packing of the whole model) per batch
+        if bool(mode) != bool(self.training):
+            self.invalidate()
         return super().train(mode)
 
     def _apply(self, fn, *a, **k):

@@ -142,6 +142,16 @@ def test_engine_follows_in_place_weight_updates(cuda_lib):
     sd['mix_shortcut.1.weight'] *= 2.0
     sfa.load_state_dict(sd)
     assert torch.allclose(head(sfa(x)), b, atol=1e-4)           # back to the previous weights
+    # a runner that calls model.eval() before every test batch keeps the compiled engines; a real train() / eval() switch
+    # (what follows a `.data` writer such as mmcv's EMA hook) drops them
+    eng = sfa._engine
+    sfa.eval()
+    head(sfa(x))
+    assert sfa._engine is eng, 'eval() on a module already in eval mode rebuilt the engine'
+    sfa.train()
+    sfa.eval()
+    head(sfa(x))
+    assert sfa._engine is not eng
 
 
 def test_detector_reference_api_inference(cuda_lib):
