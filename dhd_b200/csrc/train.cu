@@ -1492,7 +1492,6 @@ extern "C" int dhd_pack_conv_weights(const float* w, int Cout, int cin_total, in
 extern "C" int dhd_pack_conv_weights_batch(const dhd_pack_desc* descs, int n, void* stream) {
   DHD_REQUIRE(descs != nullptr && n >= 1 && n <= DHD_PACK_MAX_BATCH, "1..DHD_PACK_MAX_BATCH layers");
   PackBatch B;
-  long nmax = 0;
   for (int i = 0; i < n; ++i) {
     const dhd_pack_desc& L = descs[i];
     DHD_REQUIRE(L.w && (L.fwd || L.bwd), "null pointer");
@@ -1501,7 +1500,6 @@ extern "C" int dhd_pack_conv_weights_batch(const dhd_pack_desc* descs, int n, vo
     B.d[i] = L;
     const long e = (L.fwd ? (long)L.Cout * L.taps * L.cin_pad : 0) + (L.bwd ? (long)L.Cin * L.taps * L.cout_pad : 0);
     DHD_REQUIRE(e < (1L << 31), "layer too large for 32-bit indexing");
-    nmax = e > nmax ? e : nmax;
   }
   for (int i = n; i < DHD_PACK_MAX_BATCH; ++i) B.d[i] = descs[0];
   int tiles_max = 0, taps_max = 1;
