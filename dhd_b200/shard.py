@@ -155,6 +155,15 @@ class FlatAdamW:
                                               g['lr'], b1, b2, g['eps'], g['weight_decay'], 1.0 - b1 ** self.t,
                                               1.0 - b2 ** self.t, P(grad_scale),
                                               ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), 'adamw_flat')
+        # the kernel wrote the parameters through raw pointers: bump their version counters like an in-place torch op
+        # would, so everything keyed on them (the compiled inference engines, dhd_b200.compat.EngineOwner) sees the step
+        try:
+            torch._C._increment_version(self.bucket.params)
+        except (AttributeError, TypeError):             # no such hook in this torch: drop the engines explicitly instead
+            from .compat import EngineOwner
+            for m in getattr(self, 'modules', ()):
+                if isinstance(m, EngineOwner):
+                    m.invalidate()
 
     def state_dict(self):
         return dict(step=self.t, exp_avg=self.m, exp_avg_sq=self.v, param_groups=[{k: v for k, v in self.param_groups[0].items() if k != 'params'}])

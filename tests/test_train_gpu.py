@@ -892,3 +892,23 @@ def test_batched_weight_repack_equals_per_layer_repack(cuda_lib):
     torch.cuda.synchronize()
     for c, (f, b) in zip((tr.sp1, tr.sp2, tr.res1, tr.res2, tr.short), want):
         assert torch.equal(c.w_fwd, f) and torch.equal(c.w_bwd, b)
+
+
+def test_flat_adamw_step_invalidates_compiled_engines(cuda_lib):
+    """The flat AdamW kernel writes parameters through raw pointers; the version counters are bumped so that a module
+    that stays in eval() rebuilds its compiled inference engine after the step (dhd_b200.compat.EngineOwner)."""
+    import projects.mmdet3d_plugin  # noqa: F401
+    from dhd_b200 import shard
+    from oracle import dense_oracle as DO
+    from projects.mmdet3d_plugin.models.necks.mix import SFA
+    sfa = SFA(512, 256, precision='bf16').eval()
+    sfa.load_state_dict(DO.seeded_state_dict(sfa, 5))
+    sfa = sfa.cuda()
+    x = DO.seeded_tensor((1, 512, 8, 16), 6).cuda()
+    a = sfa(x).clone()
+    bucket = shard.GradBucket(list(sfa.parameters()))
+    opt = shard.FlatAdamW(bucket, lr=1e-1, weight_decay=0.0)
+    bucket.flat.fill_(1.0)
+    opt.step()
+    b = sfa(x)
+    assert not torch.allclose(a, b, atol=1e-3), 'the engine kept the weights from before the optimizer step'
