@@ -37,14 +37,16 @@ def wants_grad(module, *tensors):
     return bool(module.training) and any(p.requires_grad for p in module.parameters())
 
 
-def trainer_of(module, factory, device):
+def trainer_of(module, factory, device, batch_bn=None):
     """The module's training engine, built once per (device, train/eval mode) and re-packed (`refresh`) whenever a
-    parameter changed since (optimizer.step bumps the tensors' version counters)."""
-    key = (str(device), bool(module.training))
+    parameter changed since (optimizer.step bumps the tensors' version counters).  batch_bn overrides the BatchNorm
+    mode implied by module.training (mmdet's ResNet keeps its BatchNorms in eval mode under train() when norm_eval)."""
+    batch = bool(module.training) if batch_bn is None else bool(batch_bn)
+    key = (str(device), batch)
     versions = tuple((id(p), p._version) for p in module.parameters())
     slot = module.__dict__.get('_trainer')
     if slot is None or slot[0] != key:
-        T.set_bn_mode('batch' if module.training else 'frozen')
+        T.set_bn_mode('batch' if batch else 'frozen')
         try:
             tr = factory()
         finally:
@@ -195,6 +197,59 @@ def fpn_forward(module, feats):
     dev = feats[0].device
     tr = trainer_of(module, lambda: T.FPNLSSTrainer(module, dev), dev)
     return _FPNFn.apply(tr, len(feats), *feats, *_params(module))
+
+
+# ------------------------------------------------------------------------------------------------ image backbone + neck
+class _ImageResNetFn(torch.autograd.Function):
+    """mmdet ResNet (projects/configs/DHD/DHD-S.py:44-55) under autograd: the images carry no gradient, the parameters
+    do (dhd_b200.train_backbone.ImageResNetTrainer)."""
+
+    @staticmethod
+    def forward(ctx, img, trainer, *params):
+        if not img.is_cuda:
+            raise RuntimeError('dhd_b200: expected CUDA tensors (the hot path has no CPU fallback)')
+        feats = trainer.forward(img.detach())
+        ctx.trainer = trainer
+        return tuple(from_act(f) for f in feats)
+
+    @staticmethod
+    def backward(ctx, *gs):
+        tr = ctx.trainer
+        tr.backward({li: grad_to_act(g) for li, g in zip(tr.out_indices, gs) if g is not None})
+        return (None,) * len(ctx.needs_input_grad)
+
+
+def image_resnet_forward(module, img):
+    from .train_backbone import ImageResNetTrainer
+    if module.frozen_stages >= 0:
+        raise NotImplementedError('ResNet(frozen_stages >= 0) under autograd: the DHD configs train every stage '
+                                  '(frozen_stages=-1); freeze the whole backbone instead')
+    dev = img.device
+    tr = trainer_of(module, lambda: ImageResNetTrainer(module, dev), dev,
+                    batch_bn=module.training and not module.norm_eval)
+    return _ImageResNetFn.apply(img, tr, *_params(module))
+
+
+class _CustomFPNFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, trainer, n_feats, *args):
+        outs = trainer.forward([to_act(f) for f in args[:n_feats]])
+        ctx.trainer, ctx.n_feats = trainer, n_feats
+        return tuple(from_act(o) for o in outs)
+
+    @staticmethod
+    def backward(ctx, *gs):
+        tr = ctx.trainer
+        d = tr.backward([None if g is None else grad_to_act(g) for g in gs])
+        grads = [from_act(d[i]) if (i in d and ctx.needs_input_grad[2 + i]) else None for i in range(ctx.n_feats)]
+        return (None, None) + tuple(grads) + (None,) * (len(ctx.needs_input_grad) - 2 - ctx.n_feats)
+
+
+def custom_fpn_forward(module, feats):
+    from .train_backbone import CustomFPNTrainer
+    dev = feats[0].device
+    tr = trainer_of(module, lambda: CustomFPNTrainer(module, dev), dev)
+    return list(_CustomFPNFn.apply(tr, len(feats), *feats, *_params(module)))
 
 
 # ------------------------------------------------------------------------------------------------ MGHS (DHD-S)

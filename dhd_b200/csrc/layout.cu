@@ -598,6 +598,67 @@ maxpool3s2_kernel(const __nv_bfloat16* __restrict__ in, int in_ld, int in_coff, 
   store_parts8(out + (((size_t)n * oH + oy) * oW + ox) * o_ld + o_coff + c, m, parts, o_ps);
 }
 
+// MaxPool2d(kernel 3, stride 2, padding 1) backward (ResNet.maxpool under training): one thread per INPUT pixel and
+// 8 channels gathers from the <= 4 windows that cover it -- window o spans input rows 2o-1 .. 2o+1, so an even row
+// belongs to one window row and an odd row to two.  A window's gradient goes to its FIRST maximum in (ky, kx) scan
+// order (torch's rule: `val > maxval` replaces), recomputed from x; no atomics, no index tensor, deterministic.
+// relu_mask: x is the ReLU output that fed the pool -- the gradient is also multiplied by [x > 0] (the stem's ReLU
+// backward fused into this pass).
+__global__ void __launch_bounds__(256)
+maxpool3s2_bwd_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int x_coff, const __nv_bfloat16* __restrict__ dy,
+                      int dy_ld, int dy_coff, int N, int H, int W, int C, int oH, int oW, __nv_bfloat16* __restrict__ dx,
+                      int dx_ld, int dx_coff, int relu_mask) {
+  const int cg = C / 8;
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)N * H * W * cg) return;
+  int c, xx, yy;
+  long p = fast_div(i, cg, &c);
+  c *= 8;
+  p = fast_div(p, W, &xx);
+  const int n = (int)fast_div(p, H, &yy);
+  float r[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) r[j] = 0.f;
+  const int oy1 = min((yy + 1) >> 1, oH - 1), ox1 = min((xx + 1) >> 1, oW - 1);
+  for (int oy = yy >> 1; oy <= oy1; ++oy)
+    for (int ox = xx >> 1; ox <= ox1; ++ox) {
+      const int me = (yy - (2 * oy - 1)) * 3 + (xx - (2 * ox - 1));      // this pixel's place in the window's scan
+      float m[8];
+      int best[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        m[j] = -INFINITY;
+        best[j] = -1;
+      }
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        const int iy = 2 * oy - 1 + k / 3, ix = 2 * ox - 1 + k % 3;
+        if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
+        float v[8];
+        load_parts8(x + (((size_t)n * H + iy) * W + ix) * x_ld + x_coff + c, 1, 0, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (v[j] > m[j] || best[j] < 0) {
+            m[j] = v[j];
+            best[j] = k;
+          }
+      }
+      float g[8];
+      load_parts8(dy + (((size_t)n * oH + oy) * oW + ox) * dy_ld + dy_coff + c, 1, 0, g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (best[j] == me) r[j] += g[j];
+    }
+  if (relu_mask) {
+    float v[8];
+    load_parts8(x + (((size_t)n * H + yy) * W + xx) * x_ld + x_coff + c, 1, 0, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (!(v[j] > 0.f)) r[j] = 0.f;
+  }
+  store_parts8(dx + (((size_t)n * H + yy) * W + xx) * dx_ld + dx_coff + c, r, 1, 0);
+}
+
 // io += F.interpolate(lo, size=(H, W), mode='nearest') (CustomFPN's top-down path, necks/fpn.py:166-176):
 // src index = floor(dst * in / out), torch's nearest rule
 __global__ void __launch_bounds__(256)
@@ -1242,6 +1303,21 @@ extern "C" int dhd_upsample_nearest_add(const void* lo, int lo_ld, int lo_coff, 
       (const __nv_bfloat16*)lo, lo_ld, lo_coff, lo_part_stride, h, w, (__nv_bfloat16*)io, io_ld, io_coff, io_part_stride, N,
       H, W, C, parts);
   DHD_CUDA_LAUNCH_CHECK("upsample_nearest_add");
+  return DHD_OK;
+}
+
+extern "C" int dhd_maxpool3s2_bwd(const void* x, int x_ld, int x_coff, const void* dy, int dy_ld, int dy_coff, int N,
+                                  int H, int W, int C, void* dx, int dx_ld, int dx_coff, int relu_mask, void* stream) {
+  DHD_REQUIRE(x && dy && dx && N > 0 && H > 0 && W > 0 && C > 0, "bad arguments");
+  DHD_REQUIRE(C % 8 == 0 && x_ld % 8 == 0 && x_coff % 8 == 0 && dy_ld % 8 == 0 && dy_coff % 8 == 0 && dx_ld % 8 == 0 &&
+                  dx_coff % 8 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)dy & 15) == 0 && ((uintptr_t)dx & 15) == 0,
+              "needs C % 8 == 0 and 16-byte aligned rows");
+  const int oH = (H - 1) / 2 + 1, oW = (W - 1) / 2 + 1;
+  const long total = (long)N * H * W * (C / 8);
+  maxpool3s2_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x, x_ld, x_coff, (const __nv_bfloat16*)dy, dy_ld, dy_coff, N, H, W, C, oH, oW,
+      (__nv_bfloat16*)dx, dx_ld, dx_coff, relu_mask);
+  DHD_CUDA_LAUNCH_CHECK("maxpool3s2_bwd");
   return DHD_OK;
 }
 

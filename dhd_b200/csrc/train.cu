@@ -980,7 +980,8 @@ __global__ void __launch_bounds__(256)
 bn_apply_kernel(const __nv_bfloat16* __restrict__ raw, int r_ld, int r_coff, long rows, int C,
                 const float* __restrict__ scale, const float* __restrict__ shift, int act,
                 const float* __restrict__ residual, long res_ld, const float* __restrict__ gate, int rows_per_img,
-                __nv_bfloat16* __restrict__ ob, int o_ld, int o_coff, float* __restrict__ of, long f_ld) {
+                __nv_bfloat16* __restrict__ ob, int o_ld, int o_coff, float* __restrict__ of, long f_ld,
+                const __nv_bfloat16* __restrict__ res16, int res16_ld, int res16_coff) {
   const int cg = C / 8;
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * cg) return;
@@ -999,6 +1000,12 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ raw, int r_ld, int r_coff, lon
     const float4 a = *reinterpret_cast<const float4*>(residual + r * res_ld + c);
     const float4 b = *reinterpret_cast<const float4*>(residual + r * res_ld + c + 4);
     v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+  }
+  if (res16 != nullptr) {                          // bf16 identity path (Bottleneck blocks of the image backbone)
+    float q[8];
+    load8(res16 + r * res16_ld + res16_coff + c, q);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] += q[j];
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -1104,23 +1111,34 @@ __global__ void __launch_bounds__(1024)
 bn_finish_kernel(const float* __restrict__ partial, int rows, int C, const BnFinishArgs A) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane;
-  float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
   if (c < C) {
+    // every load of this loop is a DRAM / L2 round trip on a one-wave grid of 8 blocks: eight independent loads per trip
     const size_t n = 2 * (size_t)C;
     int r = w;
-    for (; r + 32 < rows; r += 64) {
+    for (; r + 96 < rows; r += 128) {
       const float* p0 = partial + (size_t)r * n + c;
-      const float* p1 = partial + (size_t)(r + 32) * n + c;
+      const float* p1 = p0 + 32 * n;
+      const float* p2 = p0 + 64 * n;
+      const float* p3 = p0 + 96 * n;
       a0 += __ldg(p0);
       b0 += __ldg(p0 + C);
       a1 += __ldg(p1);
       b1 += __ldg(p1 + C);
+      a2 += __ldg(p2);
+      b2 += __ldg(p2 + C);
+      a3 += __ldg(p3);
+      b3 += __ldg(p3 + C);
     }
-    if (r < rows) {
+    for (; r < rows; r += 32) {
       a0 += __ldg(partial + (size_t)r * n + c);
       b0 += __ldg(partial + (size_t)r * n + C + c);
     }
   }
+  a0 += a2;
+  a1 += a3;
+  b0 += b2;
+  b1 += b3;
   __shared__ float sa[32][33], sb[32][33];
   sa[w][lane] = a0 + a1;
   sb[w][lane] = b0 + b1;
@@ -1528,10 +1546,10 @@ extern "C" int dhd_adamw_flat(float* p, const float* g, float* m, float* v, long
   return DHD_OK;
 }
 
-extern "C" int dhd_bn_apply(const void* raw, int raw_ld, int raw_coff, long rows, int C, const float* scale,
-                            const float* shift, int act, const float* residual, long res_ld, const float* gate,
-                            int rows_per_img, void* out_b16, int o_ld, int o_coff, float* out_f32, long f_ld,
-                            void* stream) {
+static int bn_apply_launch(const void* raw, int raw_ld, int raw_coff, long rows, int C, const float* scale,
+                           const float* shift, int act, const float* residual, long res_ld, const float* gate,
+                           int rows_per_img, void* out_b16, int o_ld, int o_coff, float* out_f32, long f_ld,
+                           const void* res16, int res16_ld, int res16_coff, void* stream) {
   DHD_REQUIRE(raw && scale && shift && (out_b16 || out_f32) && rows > 0 && C > 0, "bad arguments");
   DHD_REQUIRE(act >= 0 && act <= 2, "act must be none / relu / sigmoid");
   DHD_REQUIRE(ok8(C, raw_ld, raw_coff, raw) && ((uintptr_t)scale & 15) == 0 && ((uintptr_t)shift & 15) == 0,
@@ -1539,13 +1557,29 @@ extern "C" int dhd_bn_apply(const void* raw, int raw_ld, int raw_coff, long rows
   if (out_b16 != nullptr) DHD_REQUIRE(ok8(C, o_ld, o_coff, out_b16), "out_b16: 16-byte aligned rows");
   if (out_f32 != nullptr) DHD_REQUIRE(f_ld % 4 == 0 && ((uintptr_t)out_f32 & 15) == 0, "out_f32: 16-byte aligned rows");
   if (residual != nullptr) DHD_REQUIRE(res_ld % 4 == 0 && ((uintptr_t)residual & 15) == 0, "residual: 16-byte aligned rows");
+  if (res16 != nullptr) DHD_REQUIRE(ok8(C, res16_ld, res16_coff, res16), "bf16 residual: 16-byte aligned rows");
   DHD_REQUIRE(gate == nullptr || rows_per_img > 0, "gate needs rows_per_img");
   const long total = rows * (C / 8);
   bn_apply_kernel<<<(int)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)raw, raw_ld, raw_coff, rows, C, scale, shift, act, residual, res_ld, gate, rows_per_img,
-      (__nv_bfloat16*)out_b16, o_ld, o_coff, out_f32, f_ld);
+      (__nv_bfloat16*)out_b16, o_ld, o_coff, out_f32, f_ld, (const __nv_bfloat16*)res16, res16_ld, res16_coff);
   DHD_CUDA_LAUNCH_CHECK("bn_apply");
   return DHD_OK;
+}
+
+extern "C" int dhd_bn_apply(const void* raw, int raw_ld, int raw_coff, long rows, int C, const float* scale,
+                            const float* shift, int act, const float* residual, long res_ld, const float* gate,
+                            int rows_per_img, void* out_b16, int o_ld, int o_coff, float* out_f32, long f_ld,
+                            void* stream) {
+  return bn_apply_launch(raw, raw_ld, raw_coff, rows, C, scale, shift, act, residual, res_ld, gate, rows_per_img, out_b16,
+                         o_ld, o_coff, out_f32, f_ld, nullptr, 0, 0, stream);
+}
+
+extern "C" int dhd_bn_apply_res16(const void* raw, int raw_ld, int raw_coff, long rows, int C, const float* scale,
+                                  const float* shift, int act, const void* res16, int res16_ld, int res16_coff,
+                                  void* out_b16, int o_ld, int o_coff, void* stream) {
+  return bn_apply_launch(raw, raw_ld, raw_coff, rows, C, scale, shift, act, nullptr, 0, nullptr, 0, out_b16, o_ld, o_coff,
+                         nullptr, 0, res16, res16_ld, res16_coff, stream);
 }
 
 extern "C" int dhd_affine_combine(const void* a, int a_ld, int a_coff, const void* b, int b_ld, int b_coff, long rows, int C,

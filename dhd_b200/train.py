@@ -193,7 +193,7 @@ class _TrainConv:
                         scale=self.scale, bias=self.bias, segs=segs, stride=self.stride, **kw)
 
     # ---- BatchNorm with batch statistics: conv -> raw (bf16), statistics, normalise + activation as a second pass
-    def _forward_batch_bn(self, x, segs, img_bias=None, img_gate=None, residual=None):
+    def _forward_batch_bn(self, x, segs, img_bias=None, img_gate=None, residual=None, residual_act=None):
         if len(segs) != 1:
             raise NotImplementedError('batch-statistics BatchNorm: one output segment')
         seg, bn, lib = segs[0], self.bn, _lib.load()
@@ -241,6 +241,15 @@ class _TrainConv:
             if st[3] != 1 or st[2] < self.Cout:
                 raise NotImplementedError('batch-statistics BatchNorm: fp32 output must be NHWC rows')
             f_ld = st[2]
+        if residual_act is not None:              # bf16 identity path (image backbone): act(scale*raw + shift + identity)
+            ra = residual_act
+            if residual is not None or img_gate is not None or of is not None or ob is None or \
+                    (ra.N, ra.H, ra.W) != (x.N, oH, oW) or ra.C < self.Cout:
+                raise NotImplementedError('batch-statistics BatchNorm with a bf16 identity: one bf16 output, no gate')
+            _lib.check(lib.dhd_bn_apply_res16(_p(raw.data), raw.ld, raw.coff, x.N * oH * oW, self.Cout, _p(scale), _p(shift),
+                                              ACT_ID[seg.get('act')], _p(ra.data), ra.ld, ra.coff, _p(ob.data), ob.ld,
+                                              ob.coff, _stream()), 'bn_apply_res16')
+            return
         res, res_ld = (None, 0) if residual is None else (residual[0], residual[1][2])
         _lib.check(lib.dhd_bn_apply(_p(raw.data), raw.ld, raw.coff, x.N * oH * oW, self.Cout, _p(scale), _p(shift),
                                     ACT_ID[seg.get('act')], _p(res), res_ld, _p(img_gate), oH * oW,

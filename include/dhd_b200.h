@@ -392,6 +392,11 @@ int dhd_adamw_flat(float* p, const float* g, float* m, float* v, long n, float l
 int dhd_bn_apply(const void* raw, int raw_ld, int raw_coff, long rows, int C, const float* scale,
                  const float* shift, int act, const float* residual, long res_ld, const float* gate,
                  int rows_per_img, void* out_b16, int o_ld, int o_coff, float* out_f32, long f_ld, void* stream);
+/* the same forward pass with a bf16 identity path: out = act(scale[c]*raw + shift[c] + res16) (the Bottleneck blocks of
+ * the image backbone keep their residual stream in bf16) */
+int dhd_bn_apply_res16(const void* raw, int raw_ld, int raw_coff, long rows, int C, const float* scale, const float* shift,
+                       int act, const void* res16, int res16_ld, int res16_coff, void* out_b16, int o_ld, int o_coff,
+                       void* stream);
 /* per-channel coefficients of the two passes from the reduced sums (one launch each): forward -- scale / shift (and
  * mean / invstd for the backward, running statistics updated with `momentum` when given) from sums = [sum raw,
  * sum raw^2]; backward -- k1 / k2 / k3 from sums = [sum dz, sum dz*raw] (second half at sums_stride), d gamma / d beta
@@ -515,6 +520,13 @@ int dhd_maxpool2_bwd(const void* x, int x_ld, int x_coff, const void* dy, int dy
                      int C, void* dx, int dx_ld, int dx_coff, void* stream);
 int dhd_upsample_bilinear_bwd(const void* dy, int dy_ld, int dy_coff, int N, int H, int W, int C, int out_H, int out_W,
                               float* dx, void* stream);
+/* MaxPool2d(kernel 3, stride 2, padding 1) backward (mmdet ResNet.maxpool when the image backbone trains, DHD-S.py:44-55
+ * `norm_eval=False, frozen_stages=-1`): x (N, H, W, C) is the pool's bf16 input, dy (N, oH, oW, C) the gradient of its
+ * output, dx (N, H, W, C) is written completely.  The gradient of a window goes to its first maximum in scan order
+ * (torch's rule), gathered per input pixel: deterministic.  relu_mask != 0: dx is also multiplied by [x > 0] (x is the
+ * output of the stem's ReLU). */
+int dhd_maxpool3s2_bwd(const void* x, int x_ld, int x_coff, const void* dy, int dy_ld, int dy_coff, int N, int H, int W,
+                       int C, void* dx, int dx_ld, int dx_coff, int relu_mask, void* stream);
 /* number of kernels this library has enqueued since it was loaded (bench bookkeeping) */
 long dhd_launch_count(void);
 /* fp32 rows [rows][C] (NHWC) -> split-bf16 rows */

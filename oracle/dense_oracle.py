@@ -323,13 +323,13 @@ def fpn_lss_forward(sd, feats, prefix='', index=(0, 2), scale=4, scale2=2):
 
 
 # ------------------------------------------------------------------ image backbone + neck (the 8(f)-4 widening)
-def image_resnet_forward(sd, img, depth=50, out_indices=(2, 3), prefix=''):
+def image_resnet_forward(sd, img, depth=50, out_indices=(2, 3), prefix='', num_stages=4):
     """mmdet 2.25.1 `ResNet(depth, style='pytorch')` in eval mode = the torchvision ResNet the reference's configs load
     (`pretrained='torchvision://resnet50'`, projects/configs/DHD/DHD-S.py:44-55): conv1 7x7/2 + bn + relu, maxpool 3x3/2,
     Bottleneck stages (1x1, 3x3 with the stage stride, 1x1; a 1x1 stride-s conv + bn on the identity of every stage's
-    first block).  mmdet is not part of the reference tree: pinned against torchvision.models.resnet50 (tests)."""
-    import torch.nn.functional as F
-    blocks = {50: (3, 4, 6, 3), 101: (3, 4, 23, 3), 152: (3, 8, 36, 3)}[depth]
+    first block).  mmdet is not part of the reference tree: pinned against torchvision.models.resnet50 (tests).  With
+    BN_TRAIN the BatchNorms use batch statistics (mmdet's train() with norm_eval=False, DHD-S.py:50-51)."""
+    blocks = {50: (3, 4, 6, 3), 101: (3, 4, 23, 3), 152: (3, 8, 36, 3)}[depth][:num_stages]
     x = F.relu(_bn(sd, prefix + 'bn1', F.conv2d(img, sd[prefix + 'conv1.weight'], stride=2, padding=3)))
     x = F.max_pool2d(x, 3, stride=2, padding=1)
     outs = []
@@ -352,7 +352,6 @@ def image_resnet_forward(sd, img, depth=50, out_indices=(2, 3), prefix=''):
 def custom_fpn_forward(sd, inputs, out_ids=(0,), start_level=0, prefix=''):
     """projects/mmdet3d_plugin/models/necks/fpn.py:153-176 for norm_cfg=None / act_cfg=None / no extra convs (the DHD
     configs): lateral 1x1 convs, laterals[i-1] += nearest-interpolated laterals[i], 3x3 conv on the out_ids levels."""
-    import torch.nn.functional as F
     n = len(inputs) - start_level
     lats = [F.conv2d(inputs[i + start_level], sd['%slateral_convs.%d.conv.weight' % (prefix, i)],
                      sd['%slateral_convs.%d.conv.bias' % (prefix, i)]) for i in range(n)]

@@ -4,8 +4,9 @@ pretrained='torchvision://resnet50')`, projects/configs/DHD/DHD-S.py:44-55; the 
 `mmdet.models.backbones.ResNet`, which is not part of the reference tree: the architecture is torchvision's ResNet, whose
 parameter names -- conv1 / bn1 / layer{1..4}.{i}.conv{1,2,3} / bn{1,2,3} / downsample.{0,1} -- the `torchvision://`
 checkpoints carry).  Same registry name, constructor kwargs and state_dict keys; eval-mode forward on
-dhd_b200.backbone.ResNetEngine (tcgen05 convolutions).  Training the image backbone is outside this build: a forward
-in training mode with gradients enabled raises."""
+dhd_b200.backbone.ResNetEngine (tcgen05 convolutions); under autograd (train() mode, or eval() with trainable
+parameters and gradients enabled) the forward runs dhd_b200.train_backbone.ImageResNetTrainer and `.backward()` its
+hand-written backward: BatchNorm on batch statistics in train() unless `norm_eval` (mmdet's rule), frozen otherwise."""
 import torch
 import torch.nn as nn
 
@@ -75,9 +76,12 @@ class ResNet(EngineOwner, nn.Module):
         from dhd_b200.modules import unpack
         if not x.is_cuda:
             raise RuntimeError('dhd_b200: expected CUDA tensors (the hot path has no CPU fallback)')
-        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError('training the image backbone is outside this build (DESIGN.md section 7): '
-                                      'call it in eval() / under torch.no_grad(), or freeze its parameters')
+        from dhd_b200 import autograd as A
+        if A.wants_grad(self):
+            feats = A.image_resnet_forward(self, x)      # differentiable form (dhd_b200.train_backbone)
+            if return_act:
+                raise NotImplementedError('return_act=True is the inference hand-off; under autograd tensors are returned')
+            return tuple(feats)
         with torch.no_grad():
             dev = x.device
             feats = self.cached_engine(dev, lambda: ResNetEngine(self, self.precision, dev))(x)

@@ -1,7 +1,8 @@
 """CustomFPN image neck (reference: projects/mmdet3d_plugin/models/necks/fpn.py:11-203; DHD-S.py:56-62
 `dict(type='CustomFPN', in_channels=[1024, 2048], out_channels=256, num_outs=1, start_level=0, out_ids=[0])`): 1x1
 lateral convs, top-down nearest up-sampling + add, 3x3 output conv on the levels in `out_ids`.  Same constructor kwargs and
-parameter names (`lateral_convs.{i}.conv`, `fpn_convs.{j}.conv`); forward on dhd_b200.backbone.CustomFPNEngine."""
+parameter names (`lateral_convs.{i}.conv`, `fpn_convs.{j}.conv`); forward on dhd_b200.backbone.CustomFPNEngine, under
+autograd on dhd_b200.train_backbone.CustomFPNTrainer (forward with saved activations + hand-written backward)."""
 import torch
 import torch.nn as nn
 
@@ -39,8 +40,10 @@ class CustomFPN(EngineOwner, BaseModule):
         from dhd_b200.backbone import CustomFPNEngine
         from dhd_b200.modules import unpack
         assert len(inputs) == len(self.in_channels)
-        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError('training the image neck is outside this build (DESIGN.md section 7)')
+        from dhd_b200 import autograd as A
+        if not any(isinstance(t, D.Act) for t in inputs) and A.wants_grad(self, *inputs):
+            outs = A.custom_fpn_forward(self, list(inputs))       # differentiable form (dhd_b200.train_backbone)
+            return outs
         with torch.no_grad():
             acts = []
             for t in inputs:
