@@ -14,8 +14,8 @@ Layer map:
                                           precision modes: fp32 identity), ReLU fused
   CustomFPN                               1x1 lateral convs (bias), += nearest up-sampling (dhd_upsample_nearest_add),
                                           3x3 output conv
-Eval-mode BatchNorm only (a frozen / pretrained backbone at inference); training the image backbone is not part of this
-build.
+This file is the inference form (eval-mode BatchNorm folded into the epilogues); the training form -- forward with saved
+activations, batch-statistics BatchNorm and the hand-written backward -- is dhd_b200/train_backbone.py.
 """
 import ctypes
 

@@ -23,6 +23,8 @@ class DetectorStep:
         self.size = tuple(vt.input_size)
         self.fH, self.fW = self.size[0] // vt.downsample, self.size[1] // vt.downsample
         self.Cin = vt.in_channels
+        bb = getattr(self.model, 'img_backbone', None)
+        self.images = bb is not None and type(bb).__name__ != 'MissingModule' and not self.stereo
         self.Cs = stereo_channels or synth.DHD_L_STEREO_CHANNELS
         self.grad_clip = grad_clip
         self.bucket = shard.GradBucket([p for p in self.model.parameters() if p.requires_grad])
@@ -37,7 +39,10 @@ class DetectorStep:
         rig = [t.to(dev) for t in synth.synthetic_rig(B, N, self.size, seed=seed)]
         s2e, e2g, K, pr, pt, bda = rig
         rep = lambda t: torch.cat([t] * nf, dim=1)
-        feats = torch.randn(B, N * nf, self.Cin, self.fH, self.fW, device=dev, generator=g)
+        if self.images:                                # the detector owns its image backbone: camera images in
+            feats = torch.randn(B, N * nf, 3, *self.size, device=dev, generator=g)
+        else:
+            feats = torch.randn(B, N * nf, self.Cin, self.fH, self.fW, device=dev, generator=g)
         first = feats
         if self.stereo:
             st = torch.randn(B, N * nf, self.Cs, 4 * self.fH, 4 * self.fW, device=dev, generator=g)

@@ -128,3 +128,36 @@ def dhd_l_model_cfg(precision='bf16'):
         occ_head=dict(type='predictor', in_dim=256, out_dim=256, Dz=16, use_mask=True, num_classes=18, use_predicter=True,
                       class_balance=True, weight_ce=10.0, precision=precision,
                       loss_occ=dict(type='CrossEntropyLoss', use_sigmoid=False, ignore_index=255, loss_weight=1.0)))
+
+
+def dhd_s_model_cfg(precision='bf16', images=True, input_size=(256, 704), depth=50):
+    """`model` of projects/configs/DHD/DHD-S.py:41-155: with images=True INCLUDING the image backbone / neck entries
+    (DHD-S.py:44-62: mmdet ResNet-50 trained with batch-statistics BatchNorm, CustomFPN) -- the detector then takes the
+    camera images, as under the reference's runner; depth=101 + input_size=(384, 1056) is BASELINE configs[3] ("DHD-B")."""
+    c = 64
+    grid = {'x': [-40, 40, 0.4], 'y': [-40, 40, 0.4], 'z': [-1, 5.4, 6.4], 'depth': [1.0, 45.0, 1.0]}
+    mg = lambda z: {'x': [-40, 40, 0.4], 'y': [-40, 40, 0.4], 'z': z, 'depth': [1.0, 45.0, 0.5]}
+    enc = lambda n_in, n_out: dict(type='UNet', n_channels=n_in, n_classes=n_out, precision=precision)
+    cfg = dict(
+        type='DHD',
+        img_view_transformer=dict(type='MGHS', grid_config=grid, input_size=tuple(input_size),
+                                  height_range=[round(-1.0 + 0.1 * i, 1) for i in range(65)], height_interval=0.1,
+                                  mask_1_grid=mg([-1, 0.6, 0.4]), mask_2_grid=mg([0.6, 2.2, 0.4]), mask_3_grid=mg([2.2, 5.4, 0.4]),
+                                  mask_range=[-1.0, 0.6, 2.2, 5.4], loss_height_weight=0.1, in_channels=256, out_channels=c,
+                                  sid=False, collapse_z=True, downsample=16, precision=precision),
+        img_bev_encoder_backbone=dict(type='CustomResNet', numC_input=c, num_channels=[c * 2, c * 4, c * 8], precision=precision),
+        img_bev_encoder_neck=dict(type='FPN_LSS', in_channels=c * 8 + c * 2, out_channels=256, precision=precision),
+        img_voxel_encoder0_backbone=enc(c * 4, 64), img_voxel_encoder0_neck=dict(type='Identity'),
+        img_voxel_encoder1_backbone=enc(c * 4, 128), img_voxel_encoder1_neck=dict(type='Identity'),
+        img_voxel_encoder2_backbone=enc(c * 8, 64), img_voxel_encoder2_neck=dict(type='Identity'),
+        mix=dict(type='SFA', in_channels=512, out_channels=256, precision=precision),
+        occ_head=dict(type='predictor', in_dim=256, out_dim=256, Dz=16, use_mask=True, num_classes=18, use_predicter=True,
+                      class_balance=True, precision=precision,
+                      loss_occ=dict(type='CrossEntropyLoss', use_sigmoid=False, ignore_index=255, loss_weight=1.0)))
+    if images:
+        cfg['img_backbone'] = dict(type='ResNet', depth=depth, num_stages=4, out_indices=(2, 3), frozen_stages=-1,
+                                   norm_cfg=dict(type='BN', requires_grad=True), norm_eval=False, with_cp=True, style='pytorch',
+                                   pretrained='torchvision://resnet%d' % depth, precision=precision)
+        cfg['img_neck'] = dict(type='CustomFPN', in_channels=[1024, 2048], out_channels=256, num_outs=1, start_level=0,
+                               out_ids=[0], precision=precision)
+    return cfg

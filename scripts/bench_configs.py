@@ -76,6 +76,31 @@ def main():
                                    'what': 'hot-path training step (as bench.py value): fwd + losses + bwd + NCCL all-reduce + clip + AdamW'},
                     'inference': {'value': world * B / (ms_i * 1e-3), 'ms_per_step': ms_i, 'timed_passes': n_i,
                                   'what': 'HotPathStep: image features -> uint8 class map'}})
+    for tag, depth, size, label in (('dhd_s_images', 50, (256, 704), 'DHD-S from camera images: ResNet-50 + CustomFPN (DHD-S.py:44-62) + the '
+                                     'whole detector'),
+                                    ('dhd_b_images', 101, (384, 1056), 'BASELINE configs[3] "DHD-B" from camera images: ResNet-101 at '
+                                     '6-cam 384x1056 + CustomFPN + the whole detector')):
+        if tag not in which:
+            continue
+        from dhd_b200.detector_step import DetectorStep
+        B = 4
+        step = DetectorStep(synth.dhd_s_model_cfg('bf16', images=True, input_size=size, depth=depth), B, seed=rank)
+        img_inputs, kw = step.make_inputs(300 + rank)
+        losses = step.train_step(img_inputs, kw)
+        ms_t, n_t = timed(lambda: step.train_step(img_inputs, kw), 2.0, warm=2, kmin=3)
+        ms_i, n_i = timed(lambda: step.infer_step(img_inputs), 1.0, warm=2, kmin=3)
+        out.append({'config': label + ', 200x200x16 grid, bf16, batch 4 per GPU', 'n_gpus': world, 'unit': 'samples/s',
+                    'scaling': 'weak',
+                    'train_step': {'value': world * B / (ms_t * 1e-3), 'ms_per_step': ms_t, 'timed_passes': n_t, 'cuda_graph': False,
+                                   'trainable_params': step.n_params, 'losses': {k: float(v) for k, v in losses.items()},
+                                   'what': 'DHD.forward_train (DHD_model.py:135-186) on camera IMAGES through the plugin detector in '
+                                           'train() mode: image backbone + neck with batch-statistics BatchNorm (trained, as DHD-S.py '
+                                           'does), view transformer, BEV / voxel encoders, SFA, head, four losses, backward through '
+                                           'every module, ONE NCCL gradient all-reduce, clip 5, AdamW; eager launches'},
+                    'inference': {'value': world * B / (ms_i * 1e-3), 'ms_per_step': ms_i, 'timed_passes': n_i,
+                                  'what': 'DHD.simple_test: camera images -> list of (200, 200, 16) uint8 class maps (incl. D2H)'}})
+        del step
+        torch.cuda.empty_cache()
     if 'dhd_l' in which:
         from dhd_b200.detector_step import DetectorStep
         B = 2

@@ -3,6 +3,8 @@ functional restatement of the same modules (oracle/dense_oracle.py) with the sam
 Operands are bf16 on the CUDA side (mixed-precision training), so gradients are compared by
 relative L2 error: <= 1e-2 and cosine >= 0.999 (bf16 has 8 mantissa bits: weights, saved activations
 and every intermediate gradient are rounded to it, and the deepest gradient passes through 6 GEMMs)."""
+import os
+
 import pytest
 import torch
 
@@ -331,6 +333,78 @@ def test_heightnet_loss_and_backward(cuda_lib, dropout, objective):
             assert cos(p.grad, sd[name].grad) > 0.99, name
 
 
+def test_heightnet_backward_teacher_forced(cuda_lib):
+    """The tight pin of the HeightNet trainer (SE gate, three BasicBlocks, ASPP, DCN, head + height loss) under the
+    RANDOM-label objective of test_heightnet_loss_and_backward: the reference continues from the 15 activations the CUDA
+    path stored (tests/helpers.py Forced: gated input, every ReLU output of the trunk, the four ASPP branches, the ASPP
+    output, the DCN output), so masks and the DCN's sampling positions agree and the comparison measures the backward
+    kernels; the free-running test keeps its 0.12 bound for the amplified forward rounding."""
+    import projects.mmdet3d_plugin  # noqa: F401
+    from dhd_b200 import dense as D
+    from dhd_b200.train import HeightNetTrainer
+    from oracle import dense_oracle as DO
+    from projects.mmdet3d_plugin.models.model_utils.depthnet import HeightNet
+    from tests.helpers import Forced
+    net = HeightNet(256, 256, 65).eval()
+    sd0 = _bf16_sd(DO.seeded_state_dict(net, 4))
+    for k in sd0:
+        if 'conv_offset' in k:
+            sd0[k] = (sd0[k] * 0.05).bfloat16().float()
+    net.load_state_dict(sd0)
+    BN, H, W = 6, 16, 44
+    x = DO.seeded_tensor((BN, 256, H, W), 5).bfloat16().float()
+    mlp_in = DO.seeded_tensor((1, BN, 27), 6)
+    g = torch.Generator().manual_seed(9)
+    label = torch.randint(-1, 65, (BN * H * W,), generator=g).int()
+    fg = torch.rand(BN * H * W, generator=g) < 0.3
+    sd = {k: v.clone().requires_grad_(v.dtype.is_floating_point and 'running' not in k) for k, v in net.state_dict().items()}
+    net = net.cuda()
+    for p in net.parameters():
+        p.grad = None
+    tr = HeightNetTrainer(net, dropout=0.0, seed=123)
+    height = tr.forward(D.pack_input(x.cuda(), 1), mlp_in.cuda())
+    sv = tr.saved
+    stored = [sv['hs'][0]]
+    for t, h in zip(sv['ts'], sv['hs'][1:]):
+        stored += [t, h]
+    mp, mid = tr.mid_pad, tr.mid
+    stored += [sv['cat'].slice(b * mp, b * mp + mid) for b in range(4)] + [sv['ha'], sv['out']]
+    stored = [a.float().cpu() for a in stored]
+    drift = []
+
+    def q(t):
+        v = stored.pop(0)
+        drift.append(rel(t.detach(), v))
+        return Forced.apply(t, v)
+
+    logits = _heightnet_forward_q(sd, x, mlp_in, q)
+    assert not stored
+    probs = logits.softmax(1).permute(0, 2, 3, 1).reshape(-1, 65)
+    onehot = torch.zeros(BN * H * W, 66)
+    onehot[torch.arange(BN * H * W), (label + 1).long()] = 1.0
+    onehot = onehot[:, 1:]
+    loss = 0.1 * torch.nn.functional.binary_cross_entropy(probs[fg], onehot[fg], reduction='none').sum() / max(1.0, float(fg.sum()))
+    loss.backward()
+    res = tr.loss(label.cuda(), fg.cuda())
+    tr.backward()
+    torch.cuda.synchronize()
+    errs, mods = {}, dict(net.named_modules())
+    for name, p in net.named_parameters():
+        if isinstance(mods[name.rsplit('.', 1)[0]], (torch.nn.BatchNorm2d, torch.nn.BatchNorm1d)):
+            continue
+        errs[name] = rel(p.grad, sd[name].grad)
+    worst = sorted(errs.items(), key=lambda kv: -kv[1])[:6]
+    print('per-layer forward drift %.4f, height %.4f, worst gradients' % (max(drift), rel(height.cpu(), logits.detach().softmax(1))),
+          [(k, round(v, 4)) for k, v in worst])
+    import json
+    os.makedirs('gpurun_out', exist_ok=True)
+    json.dump(dict({k: round(v, 5) for k, v in errs.items()}, drift=max(drift)),
+              open('gpurun_out/heightnet_forced_grad_errs.json', 'w'), indent=0)
+    assert max(drift) < 1e-2 and rel(height.cpu(), logits.detach().softmax(1)) < 1e-2
+    assert abs(float(res[0]) - float(loss.detach())) / float(loss.detach()) < 5e-3
+    assert max(errs.values()) < 3e-2, worst
+
+
 def test_dcn_sampling_backward_unit(cuda_lib):
     """dhd_dcn_col2im_bwd against autograd of the same bilinear sampling written with F.grid_sample
     (align_corners=True, zero padding == mmcv / torchvision deformable im2col), identical inputs."""
@@ -599,6 +673,100 @@ def test_bev_encoder_backward(cuda_lib, objective):
         # branch of the first block, each rounded to bf16 before they partly cancel) 9 %
         assert max(v for k, v in errs.items() if k != 'x') < 5e-2, errs
     assert max(errs.values()) < 0.12, errs
+
+
+def _forced_oracle_call(shim, fn):
+    from oracle import dense_oracle as DO
+    saved = DO.F
+    DO.F = shim
+    try:
+        return fn()
+    finally:
+        DO.F = saved
+
+
+def test_encoders_backward_teacher_forced(cuda_lib):
+    """The tight pin of the encoder trainers (UNet; CustomResNet + FPN_LSS) under a RANDOM-sign objective: the reference
+    (torch autograd over the oracle) continues from the activations the CUDA path stored (tests/helpers.py ForcedF), so
+    ReLU masks and max-pool winners are identical on both sides and the gradients differ by the backward kernels'
+    own rounding only.  test_unet_backward / test_bev_encoder_backward keep the free-running comparison, whose 0.12
+    bound absorbs the mask flips of a deep bf16 trunk (a flipped fraction f moves a random-sign gradient by sqrt(f))."""
+    import projects.mmdet3d_plugin  # noqa: F401
+    from dhd_b200 import dense as D
+    from dhd_b200.train import CustomResNetTrainer, FPNLSSTrainer, UNetTrainer
+    from oracle import dense_oracle as DO
+    from projects.mmdet3d_plugin.models.backbones import CustomResNet, UNet
+    from projects.mmdet3d_plugin.models.necks import FPN_LSS
+    from tests.helpers import ForcedF
+    cpu = lambda a: a.float().cpu()
+    mk = lambda m: {k: v.clone().requires_grad_(v.dtype.is_floating_point and 'running' not in k) for k, v in m.state_dict().items()}
+    report = {}
+    B, H, W = 1, 40, 56
+    # ---- UNet
+    net = UNet(256, 64).eval()
+    net.load_state_dict(_bf16_sd(DO.seeded_state_dict(net, 31)))
+    x = DO.seeded_tensor((B, 256, H, W), 34).bfloat16().float()
+    gout = (DO.seeded_tensor((B, 64, H, W), 36) * 0.01).bfloat16().float()
+    sd = mk(net)
+    net = net.cuda()
+    for p in net.parameters():
+        p.grad = None
+    tr = UNetTrainer(net)
+    out = tr.forward(D.pack_input(x.cuda(), 1))
+    S = tr.saved
+    relu = [S['tmps']['inc'], S['skip'][0]]
+    for k in range(4):
+        relu += [S['tmps']['d%d' % k], S['skip'][k + 1] if k < 3 else S['bottom']]
+    for k in range(4):
+        relu += [S['tmps']['u%d' % k], S['decs'][k]]
+    shim = ForcedF({'relu': [cpu(a) for a in relu]}, rounded=('conv_transpose2d',))
+    xr = x.clone().requires_grad_()
+    y = _forced_oracle_call(shim, lambda: DO.unet_forward(sd, xr))
+    assert shim.exhausted()
+    (y * gout).sum().backward()
+    dx = tr.backward(D.pack_input(gout.cuda(), 1))
+    torch.cuda.synchronize()
+    errs = _grad_errors(net, sd)
+    errs['x'] = rel(dx.float(), xr.grad)
+    report['unet'] = dict(drift=max(shim.drift['relu']), out=rel(out.slice(0, 64).float(), y.detach()), **errs)
+    # ---- CustomResNet + FPN_LSS
+    r, f = CustomResNet(64, num_channels=[128, 256, 512]).eval(), FPN_LSS(640, 256).eval()
+    r.load_state_dict(_bf16_sd(DO.seeded_state_dict(r, 32)))
+    f.load_state_dict(_bf16_sd(DO.seeded_state_dict(f, 33)))
+    x = DO.seeded_tensor((B, 64, H, W), 35).bfloat16().float()
+    gout = (DO.seeded_tensor((B, 256, H, W), 37) * 0.01).bfloat16().float()
+    sdr, sdf = mk(r), mk(f)
+    r, f = r.cuda(), f.cuda()
+    for p in list(r.parameters()) + list(f.parameters()):
+        p.grad = None
+    tr, tf = CustomResNetTrainer(r), FPNLSSTrainer(f)
+    out = tf.forward(tr.forward(D.pack_input(x.cuda(), 1)))
+    relu = []
+    for (_, t, o) in tr.saved:
+        relu += [t, o]
+    x2, x1, cat, t, u, v, w = tf.saved
+    relu += [t, u, w]
+    shim = ForcedF({'relu': [cpu(a) for a in relu], 'interpolate': [cpu(cat.slice(x2.C, x2.C + x1.C)), cpu(v)]})
+    xr = x.clone().requires_grad_()
+    y = _forced_oracle_call(shim, lambda: DO.fpn_lss_forward(sdf, DO.custom_resnet_forward(sdr, xr)))
+    assert shim.exhausted()
+    (y * gout).sum().backward()
+    dx = tr.backward(tf.backward(D.pack_input(gout.cuda(), 1)))
+    torch.cuda.synchronize()
+    errs = dict(_grad_errors(f, sdf))
+    errs.update({'resnet.' + k: v for k, v in _grad_errors(r, sdr).items()})
+    errs['x'] = rel(dx.float(), xr.grad)
+    report['bev'] = dict(drift=max(shim.drift['relu'] + shim.drift['interpolate']), out=rel(out.float(), y.detach()), **errs)
+    import json
+    os.makedirs('gpurun_out', exist_ok=True)
+    json.dump({k: {a: round(b, 5) for a, b in v.items()} for k, v in report.items()},
+              open('gpurun_out/encoder_forced_grad_errs.json', 'w'), indent=0)
+    for name, rep in report.items():
+        worst = sorted(((k, v) for k, v in rep.items() if k not in ('drift', 'out')), key=lambda kv: -kv[1])[:5]
+        print(name, 'per-layer forward drift %.4f, output %.4f, worst gradients' % (rep['drift'], rep['out']),
+              [(k, round(v, 4)) for k, v in worst])
+        assert rep['drift'] < 1e-2 and rep['out'] < 1e-2, (name, rep['drift'], rep['out'])
+        assert max(v for k, v in rep.items() if k not in ('drift', 'out')) < 2e-2, (name, worst)
 
 
 @pytest.mark.parametrize('bn', ['frozen', 'batch'])
