@@ -93,6 +93,7 @@ class _SFAFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, trainer, *params):
         out = trainer.forward(to_act(x))
+        T.flush_bn_counters()
         ctx.trainer = trainer
         return from_act(out)
 
@@ -112,6 +113,7 @@ class _PredictorFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, trainer, *params):
         out = trainer.forward(to_act(x))                     # (B, Dx, Dy, Dz, n_cls) fp32, a fresh tensor per call
+        T.flush_bn_counters()
         ctx.trainer = trainer
         return out
 
@@ -138,6 +140,7 @@ class _UNetFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, trainer, *params):
         out = trainer.forward(to_act(x))
+        T.flush_bn_counters()
         ctx.trainer = trainer
         return from_act(out, trainer.n_classes)
 
@@ -157,6 +160,7 @@ class _ResNetFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, trainer, *params):
         feats = trainer.forward(to_act(x))
+        T.flush_bn_counters()
         ctx.trainer = trainer
         return tuple(from_act(f) for f in feats)
 
@@ -182,6 +186,7 @@ class _FPNFn(torch.autograd.Function):
     def forward(ctx, trainer, n_feats, *args):
         feats = [to_act(f) for f in args[:n_feats]]
         out = trainer.forward(feats)
+        T.flush_bn_counters()
         ctx.trainer, ctx.n_feats = trainer, n_feats
         return from_act(out)
 
@@ -209,6 +214,7 @@ class _ImageResNetFn(torch.autograd.Function):
         if not img.is_cuda:
             raise RuntimeError('dhd_b200: expected CUDA tensors (the hot path has no CPU fallback)')
         feats = trainer.forward(img.detach())
+        T.flush_bn_counters()
         ctx.trainer = trainer
         return tuple(from_act(f) for f in feats)
 
@@ -234,6 +240,7 @@ class _CustomFPNFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, trainer, n_feats, *args):
         outs = trainer.forward([to_act(f) for f in args[:n_feats]])
+        T.flush_bn_counters()
         ctx.trainer, ctx.n_feats = trainer, n_feats
         return tuple(from_act(o) for o in outs)
 
@@ -264,6 +271,7 @@ class _MGHSFn(torch.autograd.Function):
         xa = D.pack_input(x.detach().reshape(B * N, C, H, W).float(), 1)
         depth, feat = t_depth.forward(xa)
         height = t_height.forward(xa, mlp_input)
+        T.flush_bn_counters()
         pixmask = pixmask_fn(height)
         outs = plan.alloc_outputs(layout, x.device)
         plan.raw_forward(depth, feat, pixmask, outs, layout)
@@ -329,6 +337,7 @@ class _MGHSDepthFn(torch.autograd.Function):
         xa = D.pack_input(x.detach().reshape(B * N, C, H, W).float(), 1)
         depth, feat = t_depth.forward(xa, mlp_input, cost_volume)
         height = t_height.forward(xa, mlp_input)
+        T.flush_bn_counters()
         pixmask = pixmask_fn(height)
         outs = plan.alloc_outputs(layout, x.device)
         plan.raw_forward(depth, feat, pixmask, outs, layout)

@@ -11,7 +11,7 @@
 namespace dhd {
 
 thread_local char g_err[512] = "";
-long g_launches = 0;
+std::atomic<long> g_launches{0};
 
 template <int CPL>  // channels per lane: C <= 32*CPL
 __global__ void __launch_bounds__(256)

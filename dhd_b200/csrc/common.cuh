@@ -1,5 +1,6 @@
 // Shared helpers for the dhd_b200 sm_100a kernels.
 #pragma once
+#include <atomic>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -20,11 +21,11 @@ inline int fail(int code, const char* fmt, const char* a = "", long b = 0, long 
     if (!(cond)) return ::dhd::fail(DHD_EINVAL, "%s (" #cond ")", msg);            \
   } while (0)
 
-extern long g_launches;  // kernels enqueued by this library since load (bench bookkeeping)
+extern std::atomic<long> g_launches;  // kernels enqueued by this library since load (bench bookkeeping; any host thread)
 
 #define DHD_CUDA_LAUNCH_CHECK(name)                                               \
   do {                                                                            \
-    ++::dhd::g_launches;                                                          \
+    ::dhd::g_launches.fetch_add(1, std::memory_order_relaxed);                    \
     cudaError_t e__ = cudaGetLastError();                                         \
     if (e__ != cudaSuccess)                                                       \
       return ::dhd::fail((int)e__, "%s launch failed: %ld", name, (long)e__);      \

@@ -740,7 +740,7 @@ static int launch2_pair(const ConvBatch<1>& batch, cudaStream_t st) {
   cfg.numAttrs = 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, conv_igemm2_kernel<256, 2, 1, 2>, batch);
   if (e != cudaSuccess) return fail((int)e, "%s: %ld", "conv_igemm2 (CTA pairs) launch failed", (long)e);
-  ++g_launches;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
   return DHD_OK;
 }
 

@@ -990,7 +990,7 @@ occ_argmax_kernel(const float* __restrict__ logits, long nvox, int ncls, uint8_t
 
 using namespace dhd;
 
-extern "C" long dhd_launch_count(void) { return g_launches; }
+extern "C" long dhd_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 extern "C" int dhd_occ_argmax(const float* logits, long nvox, int ncls, uint8_t* out, void* stream) {
   DHD_REQUIRE(logits && out, "null pointer");

@@ -750,6 +750,8 @@ class TrainStep(HotPathStep):
             enc = self.encoded_act
         fused = self.t_sfa.forward(enc)
         self.t_head.forward(fused)
+        from . import train as T
+        T.flush_bn_counters()                        # num_batches_tracked of every batch-statistics BatchNorm of the step
         self.loss = self.t_head.loss(self.labels, self.mask_camera)
         # ---- backward
         dfused = self.t_head.backward()

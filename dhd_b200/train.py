@@ -31,6 +31,18 @@ FUSED_TAIL = _os.environ.get('DHD_TRAIN_FUSED_TAIL', '1') != '0'
 SFA_BF16_DX = _os.environ.get('DHD_SFA_BF16_DX', '1') != '0'
 
 
+_BN_COUNTERS = []
+
+
+def flush_bn_counters():
+    """`num_batches_tracked += 1` for every BatchNorm that ran on batch statistics since the last call (torch bumps the
+    counter in each training-mode forward; here the bumps of a whole step are ONE multi-tensor launch)."""
+    global _BN_COUNTERS
+    if _BN_COUNTERS:
+        cs, _BN_COUNTERS = _BN_COUNTERS, []
+        torch._foreach_add_(cs, 1)
+
+
 def set_bn_mode(mode):
     global BN_MODE
     if mode not in ('frozen', 'batch'):
@@ -235,6 +247,10 @@ class _TrainConv:
                                              _p(bb[0]), _p(bb[1]), _p(bb[2]), _p(bb[3]), _stream()), 'bn_fwd_coeffs')
         scale, shift = bb[0], bb[1]
         self._bn_saved = M
+        if track and getattr(bn, 'num_batches_tracked', None) is not None:
+            _BN_COUNTERS.append(bn.num_batches_tracked)
+            if len(_BN_COUNTERS) >= 1024:            # a caller that never flushes (direct use of a trainer)
+                flush_bn_counters()
         ob, of, f_ld = seg.get('out_act'), None, 0
         if seg.get('out_f32') is not None:
             of, st = seg['out_f32']

@@ -112,8 +112,10 @@ def test_modules_are_differentiable_like_the_reference(cuda_lib):
         vals.append(float(total))
         opt.step()
     assert vals[2] < vals[0], 'three SGD steps on one batch did not lower the loss: %s' % vals
-    # BatchNorm really ran on batch statistics: the running means moved off their initial zeros
+    # BatchNorm really ran on batch statistics: the running means moved off their initial zeros, and the step counter
+    # follows torch's (one bump per training-mode forward)
     assert float(sfa.mix_residual[1].running_mean.abs().max()) > 0
+    assert int(sfa.mix_residual[1].num_batches_tracked) == 3
 
 
 def test_engine_follows_in_place_weight_updates(cuda_lib):
