@@ -284,6 +284,13 @@ class DHD_stereo(DHD):
         metas = dict(k2s_sensor=k2s_sensor, intrins=intrin, post_rots=post_rot, post_trans=post_tran,
                      frustum=vt.cv_frustum.to(x), cv_downsample=4, downsample=vt.downsample,
                      grid_config=vt.grid_config, cv_feat_list=[feat_prev_iv, stereo_feat])
+        if getattr(self, '_act_path', False):
+            # inference fast path: bf16 NHWC activations from the pool kernel to the SFA, no fp32 / NCDHW round trips
+            bev_2d, bev_3d, depth, height = vt([x, sensor2keyego, ego2global, intrin, post_rot, post_tran, bda, mlp_input],
+                                               metas, return_act=True)
+            bev_2d = self.pre_process_net(bev_2d, return_act=True)[0]
+            bev_3d = self.pre_process_net_3d(bev_3d, return_act=True)[0]
+            return bev_2d, bev_3d, depth, height, stereo_feat
         bev_2d, bev_3d, depth, height = vt([x, sensor2keyego, ego2global, intrin, post_rot, post_tran, bda, mlp_input],
                                            metas)
         if self.pre_process and bev_3d.dim() == 5:
@@ -297,12 +304,70 @@ class DHD_stereo(DHD):
     def fuse_frames(self, bev_feat_2d_list, bev_feat_3d_list):
         """DHD_model.py:517-541: frames concatenated on the channel axis, z collapsed into channels, the 16 height
         planes split 4 / 4 / 8 for the three voxel encoders.  -> (x_2d, x_3d), each (B, C_out, Dy, Dx)."""
+        if getattr(self, '_act_path', False):
+            return self._fuse_frames_acts(bev_feat_2d_list, bev_feat_3d_list), None
         bev_2d = self._collapse_z(torch.cat(bev_feat_2d_list, dim=1))
         bev_3d = torch.cat(bev_feat_3d_list, dim=1)
         slabs = (bev_3d[:, :, :4], bev_3d[:, :, 4:8], bev_3d[:, :, 8:])
         x_2d = self.bev_encoder(bev_2d)
         x_3d = torch.cat([self.voxel_encoder(i, self._collapse_z(s)) for i, s in enumerate(slabs)], dim=1)
         return x_2d, x_3d
+
+    def _fuse_frames_acts(self, acts_2d, acts_3d):
+        """fuse_frames on bf16 NHWC activations (channel = z*C + c per frame) -> the SFA's 512-channel input, every
+        encoder writing its channel slice in place.  Channel orders as the reference's cat / unbind produce them: frames
+        concatenated on C first, then z collapsed, i.e. channel = z*(F*C) + f*C + c."""
+        from dhd_b200 import dense as D
+        rows = lambda a: a.data.view(a.N, a.H, a.W, a.ld)[..., a.coff:a.coff + a.C]
+        a0 = acts_3d[0]
+        B, H, W, dev = a0.N, a0.H, a0.W, a0.data.device
+        C = acts_2d[0].C                                                  # channels per z plane
+        nz = a0.C // C
+        x2 = torch.cat([rows(a) for a in acts_2d], dim=-1).contiguous()
+        planes = torch.stack([rows(a).reshape(B, H, W, nz, C) for a in acts_3d], dim=4)      # (B, H, W, z, frame, C)
+        enc = D.Act.empty(B, H, W, 512, 1, dev)
+        feats = self.img_bev_encoder_backbone(D.Act(x2, x2.shape[-1], 1), return_act=True)
+        self.img_bev_encoder_neck(feats, return_act=True, out=enc.slice(0, 256))
+        lo = 256
+        for i, (z0, z1) in enumerate(((0, 4), (4, 8), (8, nz))):
+            slab = planes[:, :, :, z0:z1].reshape(B, H, W, -1).contiguous()
+            net = getattr(self, 'img_voxel_encoder%d' % i)
+            net(D.Act(slab, slab.shape[-1], 1), return_act=True, out=enc.slice(lo, lo + net.n_classes))
+            lo += net.n_classes
+        assert lo == 512
+        return enc
+
+    def _act_path_ok(self):
+        """The inference fast path applies to the DHD-M / DHD-L wiring in the bf16 speed mode (every module of the
+        chain hands bf16 NHWC activations to the next one)."""
+        import os
+        if os.environ.get('DHD_ACT_PATH', '1') == '0' or not getattr(self, 'act_path', True):
+            return False
+        if self.training or not self.pre_process or self.align_after_view_transfromation or not self.with_prev:
+            return False
+        vt = self.img_view_transformer
+        mods = [vt, self.pre_process_net, self.pre_process_net_3d, self.img_bev_encoder_backbone, self.img_bev_encoder_neck,
+                self.mix, self.occ_head] + [getattr(self, 'img_voxel_encoder%d' % i, None) for i in range(3)]
+        if any(m is None or getattr(m, 'precision', None) != 'bf16' for m in mods) or getattr(vt, 'collapse_z', True):
+            return False
+        if any(type(getattr(self, 'img_voxel_neck%d' % i, None)).__name__ != 'Identity' for i in range(3)):
+            return False
+        widths = sum(getattr(self, 'img_voxel_encoder%d' % i).n_classes for i in range(3))
+        return widths == 256 and getattr(self.mix, 'mix_channels', None) == 512
+
+    def simple_test(self, points, img_metas, img=None, rescale=False, **kwargs):
+        """DM:207-226; in the bf16 speed mode the chain pool -> pre-process nets -> encoders -> SFA -> head runs on bf16 NHWC
+        activations end to end (`act_path = False` or DHD_ACT_PATH=0 selects the module-by-module tensor path)."""
+        if not self._act_path_ok():
+            return super().simple_test(points, img_metas, img=img, rescale=rescale, **kwargs)
+        self._act_path = True
+        try:
+            with torch.no_grad():
+                enc = self.extract_feat(points, img_inputs=img, img_metas=img_metas, **kwargs)[0]
+                fused = self.mix(enc, return_act=True)
+                return self.occ_head.get_occ(self.occ_head.forward_occ(fused), img_metas)
+        finally:
+            self._act_path = False
 
     def extract_bev_feat(self, feats, stereo_feats, sensor2keyegos, ego2globals, intrins, post_rots, post_trans, bda,
                          curr2adjsensor):

@@ -333,12 +333,17 @@ class MGHS_Depth(MGHS):
                                   context_channels=self.out_channels, depth_channels=self.D,
                                   precision=self.precision, **depthnet_cfg)
 
-    def forward(self, input, stereo_metas=None):
+    def forward(self, input, stereo_metas=None, return_act=False):
+        """return_act=True (inference, bf16 speed mode, collapse_z=False): bev / bev_w_z come back as bf16 NHWC
+        activations (dhd_b200.dense.Act) with the z planes collapsed into channels (channel = z*C + c, what the
+        detectors' `torch.cat(x.unbind(dim=2), 1)` produces) -- the pool kernel writes them in that form directly."""
         from dhd_b200 import dense as D
         x, mlp_input = input[0], input[7]
         B, N, C, H, W = x.shape
         from dhd_b200 import autograd as A
         if x.is_cuda and A.wants_grad(self, x):
+            if return_act:
+                raise NotImplementedError('return_act=True is the inference hand-off')
             # differentiable form (training): DepthNetTrainer + HeightNetTrainer + pool backward (dhd_b200.autograd)
             plan = self._bins(input)
             pix = lambda h: height_to_mask(h, self.height_range, self.mask_range)
@@ -352,9 +357,9 @@ class MGHS_Depth(MGHS):
             xa = D.pack_input(x.reshape(B * N, C, H, W), D.PRECISIONS[self.precision][0])
             depth, feat = self.depth_net.forward_split(xa, mlp_input, softmax=True, stereo_metas=stereo_metas)
             height = self.height_net(xa, mlp_input, None, softmax=True)
-            return self.view_transform(input, depth, None, height, feat_nhwc=feat)
+            return self.view_transform(input, depth, None, height, feat_nhwc=feat, return_act=return_act)
 
-    def view_transform(self, input, depth, tran_feat, height, feat_nhwc=None):
+    def view_transform(self, input, depth, tran_feat, height, feat_nhwc=None, return_act=False):
         B, N, _, H, W = input[0].shape
         if not depth.is_cuda:
             raise RuntimeError('dhd_b200: expected CUDA tensors (the hot path has no CPU fallback)')
@@ -363,7 +368,15 @@ class MGHS_Depth(MGHS):
             feat_nhwc = tran_feat.view(B, N, self.out_channels, H, W).permute(0, 1, 3, 4, 2).contiguous()
         feat_nhwc = feat_nhwc.view(B, N, H, W, self.out_channels)
         pixmask = height_to_mask(height, self.height_range, self.mask_range)
-        if self.collapse_z:       # not used by any config; same concatenation on dim 2 as the reference
+        if return_act:
+            from dhd_b200 import dense as D
+            if self.collapse_z or D.PRECISIONS[self.precision][0] != 1:
+                raise NotImplementedError('return_act=True: bf16 speed mode with collapse_z=False')
+            outs = plan.alloc_outputs('nhwc_bf16', depth.device)           # four (B, Dy, Dx, dz*C) bf16 tensors
+            plan.raw_forward(depth, feat_nhwc, pixmask, outs, 'nhwc_bf16')
+            w_z = torch.cat(outs[1:], dim=-1)                              # low | mid | high slabs stacked on z
+            bev, bev_w_z = D.Act(outs[0], outs[0].shape[-1], 1), D.Act(w_z, w_z.shape[-1], 1)
+        elif self.collapse_z:       # not used by any config; same concatenation on dim 2 as the reference
             outs = plan(depth, feat_nhwc, pixmask, layout='nchw')
             bev, bev_w_z = outs[0], torch.cat(outs[1:], dim=2)
         else:

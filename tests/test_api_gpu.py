@@ -264,3 +264,30 @@ def test_dhd_stereo_forward_train_two_frames(cuda_lib):
     with torch.no_grad():
         occ = model.simple_test(None, [{}] * B, img=img_inputs)
     assert len(occ) == B and occ[0].shape == (200, 200, 16) and occ[0].dtype == np.uint8
+
+
+def test_dhd_stereo_inference_act_path_equals_tensor_path(cuda_lib):
+    """DHD_stereo.simple_test in the bf16 speed mode (the DHD-L wiring of dhd_b200.synth at a reduced image size): the
+    inference fast path -- pool kernel writing bf16 NHWC activations with z collapsed into channels, pre-process nets,
+    frame concatenation, encoders writing channel slices of the SFA input -- against the module-by-module tensor path
+    (fp32 (B, C, Dz, Dy, Dx) tensors, `torch.cat(x.unbind(dim=2), 1)`, DHD_model.py:313-374, 517-541).  Both round the
+    pooled sums and every module output to bf16 at the same points, so the class maps agree."""
+    import projects.mmdet3d_plugin  # noqa: F401
+    from dhd_b200 import synth
+    from dhd_b200.detector_step import DetectorStep
+    cfg = synth.dhd_l_model_cfg('bf16')
+    cfg['img_view_transformer'] = dict(cfg['img_view_transformer'], input_size=(128, 352))
+    step = DetectorStep(cfg, 1, seed=3)
+    step.model.load_state_dict(DO.seeded_state_dict(step.model, 17))
+    img_inputs, _ = step.make_inputs(5)
+    model = step.model
+    assert model.eval()._act_path_ok()
+    fast = step.infer_step(img_inputs)
+    model.act_path = False
+    assert not model._act_path_ok()
+    slow = step.infer_step(img_inputs)
+    model.act_path = True
+    assert len(fast) == len(slow) == 1 and fast[0].shape == (200, 200, 16) and fast[0].dtype == np.uint8
+    agree = float((np.asarray(fast[0]) == np.asarray(slow[0])).mean())
+    assert len(np.unique(np.asarray(slow[0]))) >= 2                       # a non-trivial class map
+    assert agree >= 0.9995, agree
