@@ -104,14 +104,16 @@ class DHD(C.BaseModule):
         return x.view(B, N, x.shape[1], x.shape[2], x.shape[3]), stereo_feat
 
     def prepare_inputs(self, inputs):
-        """bevdet.py:60-78: sensor -> key-ego transforms (fp64 inverse + products, as the reference)."""
+        """bevdet.py:60-78: sensor -> key-ego transforms (fp64 inverse + products, as the reference; `linalg.inv_ex` is
+        `torch.inverse` without the singularity check's device -> host synchronisation: same bits, and the step stays
+        capturable in a CUDA graph)."""
         assert len(inputs) == 7
         B, N = inputs[0].shape[:2]
         imgs, sensor2egos, ego2globals, intrins, post_rots, post_trans, bda = inputs
         sensor2egos = sensor2egos.view(B, N, 4, 4)
         ego2globals = ego2globals.view(B, N, 4, 4)
         keyego2global = ego2globals[:, 0, ...].unsqueeze(1)
-        global2keyego = torch.inverse(keyego2global.double())
+        global2keyego = torch.linalg.inv_ex(keyego2global.double()).inverse
         sensor2keyegos = (global2keyego @ ego2globals.double() @ sensor2egos.double()).float()
         return [imgs, sensor2keyegos, ego2globals, intrins, post_rots, post_trans, bda]
 
@@ -178,18 +180,20 @@ class DHD(C.BaseModule):
         outs = self.occ_head(self.mix(torch.cat(img_feats, dim=1)))
         return self.occ_head.loss(outs, voxel_semantics, mask_camera)
 
-    def simple_test(self, points, img_metas, img=None, rescale=False, **kwargs):
-        """DM:207-226 -> list of (Dx, Dy, Dz) uint8 class maps."""
+    def simple_test(self, points, img_metas, img=None, rescale=False, to_host=True, **kwargs):
+        """DM:207-226 -> list of (Dx, Dy, Dz) uint8 class maps.  to_host=False: the (B, Dx, Dy, Dz) uint8 DEVICE tensor
+        instead (no synchronisation: what a CUDA-graph capture of the step needs, dhd_b200.detector_step)."""
         x_2d, x_3d, _, _, _ = self.extract_feat(points, img_inputs=img, img_metas=img_metas, **kwargs)
-        return self.simple_test_occ([x_2d, x_3d], img_metas)
+        return self.simple_test_occ([x_2d, x_3d], img_metas, to_host=to_host)
 
-    def simple_test_occ(self, img_feats, img_metas=None):
+    def simple_test_occ(self, img_feats, img_metas=None, to_host=True):
         """DM:228-241: cat -> mix -> occ_head -> get_occ.  `img_feats` may also be the logits tensor itself (the
         round-1 calling convention).  The head's fused inference tail produces the class map directly."""
         if isinstance(img_feats, torch.Tensor):
             return self.occ_head.get_occ(img_feats, img_metas)
         fused = self.mix(torch.cat(list(img_feats), dim=1), return_act=True)
-        return self.occ_head.get_occ(self.occ_head.forward_occ(fused), img_metas)
+        occ = self.occ_head.forward_occ(fused)
+        return self.occ_head.get_occ(occ, img_metas) if to_host else occ
 
     def forward_test(self, points=None, img_inputs=None, img_metas=None, **kwargs):
         """bevdet.py:168-204: one test-time augmentation only (aug_test asserts False in the reference too)."""
@@ -273,6 +277,16 @@ class DHD_stereo(DHD):
         """(B, C, Dz, Dy, Dx) -> (B, Dz*C, Dy, Dx), channel = z*C + c (`torch.cat(x.unbind(dim=2), 1)`)."""
         return torch.cat(x.unbind(dim=2), 1)
 
+    def _cv_frustum(self, like):
+        """The stereo frustum template on the features' device / dtype, copied once (the module keeps it as a plain CPU
+        tensor like the reference; a host -> device copy per frame would also break CUDA-graph capture)."""
+        key = (str(like.device), like.dtype)
+        c = self.__dict__.get('_cv_frustum_cache')
+        if c is None or c[0] != key:
+            c = (key, self.img_view_transformer.cv_frustum.to(like))
+            self.__dict__['_cv_frustum_cache'] = c
+        return c[1]
+
     def prepare_bev_feat(self, x, stereo_feat, sensor2keyego, ego2global, intrin, post_rot, post_tran, bda, mlp_input,
                          feat_prev_iv, k2s_sensor, extra_ref_frame=False):
         """DHD_model.py:313-374 from the frame's image features.  x (B, N, C, fH, fW) (None for the extra reference
@@ -282,7 +296,7 @@ class DHD_stereo(DHD):
             return None, None, None, None, stereo_feat
         vt = self.img_view_transformer
         metas = dict(k2s_sensor=k2s_sensor, intrins=intrin, post_rots=post_rot, post_trans=post_tran,
-                     frustum=vt.cv_frustum.to(x), cv_downsample=4, downsample=vt.downsample,
+                     frustum=self._cv_frustum(x), cv_downsample=4, downsample=vt.downsample,
                      grid_config=vt.grid_config, cv_feat_list=[feat_prev_iv, stereo_feat])
         if getattr(self, '_act_path', False):
             # inference fast path: bf16 NHWC activations from the pool kernel to the SFA, no fp32 / NCDHW round trips
@@ -355,17 +369,18 @@ class DHD_stereo(DHD):
         widths = sum(getattr(self, 'img_voxel_encoder%d' % i).n_classes for i in range(3))
         return widths == 256 and getattr(self.mix, 'mix_channels', None) == 512
 
-    def simple_test(self, points, img_metas, img=None, rescale=False, **kwargs):
+    def simple_test(self, points, img_metas, img=None, rescale=False, to_host=True, **kwargs):
         """DM:207-226; in the bf16 speed mode the chain pool -> pre-process nets -> encoders -> SFA -> head runs on bf16 NHWC
         activations end to end (`act_path = False` or DHD_ACT_PATH=0 selects the module-by-module tensor path)."""
         if not self._act_path_ok():
-            return super().simple_test(points, img_metas, img=img, rescale=rescale, **kwargs)
+            return super().simple_test(points, img_metas, img=img, rescale=rescale, to_host=to_host, **kwargs)
         self._act_path = True
         try:
             with torch.no_grad():
                 enc = self.extract_feat(points, img_inputs=img, img_metas=img_metas, **kwargs)[0]
                 fused = self.mix(enc, return_act=True)
-                return self.occ_head.get_occ(self.occ_head.forward_occ(fused), img_metas)
+                occ = self.occ_head.forward_occ(fused)
+                return self.occ_head.get_occ(occ, img_metas) if to_host else occ
         finally:
             self._act_path = False
 
@@ -417,14 +432,14 @@ class DHD_stereo(DHD):
         sensor2egos = sensor2egos.view(B, nf, N, 4, 4)
         ego2globals = ego2globals.view(B, nf, N, 4, 4)
         keyego2global = ego2globals[:, 0, 0, ...].unsqueeze(1).unsqueeze(1)
-        global2keyego = torch.inverse(keyego2global.double())
+        global2keyego = torch.linalg.inv_ex(keyego2global.double()).inverse
         sensor2keyegos = (global2keyego @ ego2globals.double() @ sensor2egos.double()).float()
         curr2adjsensor = None
         if stereo:
             tf = self.temporal_frame
             s_curr, e_curr = sensor2egos[:, :tf].double(), ego2globals[:, :tf].double()
             s_adj, e_adj = sensor2egos[:, 1:tf + 1].double(), ego2globals[:, 1:tf + 1].double()
-            c2a = (torch.inverse(e_adj @ s_adj) @ e_curr @ s_curr).float()
+            c2a = (torch.linalg.inv_ex(e_adj @ s_adj).inverse @ e_curr @ s_curr).float()
             curr2adjsensor = [p.squeeze(1) for p in torch.split(c2a, 1, 1)] + [None] * self.extra_ref_frames
             assert len(curr2adjsensor) == nf
         extra = [sensor2keyegos, ego2globals, intrins.view(B, nf, N, 3, 3), post_rots.view(B, nf, N, 3, 3),

@@ -48,6 +48,19 @@ def main():
         barrier()
         return shard.max_over_ranks([e0.elapsed_time(e1)], device='cuda')[0] / n, n
 
+    def timed_infer(step, img_inputs):
+        """Eager detector inference, then the same step as one CUDA graph (DetectorStep.capture_infer) when it captures."""
+        ms_e, n_e = timed(lambda: step.infer_step(img_inputs), 1.0, warm=2, kmin=3)
+        res = {'eager_ms_per_step': ms_e}
+        if step.capture_infer(img_inputs):
+            import numpy as np
+            same = all(np.array_equal(a, b) for a, b in zip(step.infer_step(img_inputs), step.infer_step_graphed(img_inputs)))
+            ms_g, n_g = timed(lambda: step.infer_step_graphed(), 1.0, warm=2, kmin=3)
+            res.update(ms_per_step=ms_g, timed_passes=n_g, cuda_graph=True, graph_equals_eager=bool(same))
+        else:
+            res.update(ms_per_step=ms_e, timed_passes=n_e, cuda_graph=False, capture_error=step.capture_error[:200])
+        return res
+
     out = []
     if 'dhd_b' in which:
         from dhd_b200.pipeline import HotPathStep, TrainStep
@@ -88,7 +101,7 @@ def main():
         img_inputs, kw = step.make_inputs(300 + rank)
         losses = step.train_step(img_inputs, kw)
         ms_t, n_t = timed(lambda: step.train_step(img_inputs, kw), 2.0, warm=2, kmin=3)
-        ms_i, n_i = timed(lambda: step.infer_step(img_inputs), 1.0, warm=2, kmin=3)
+        inf = timed_infer(step, img_inputs)
         out.append({'config': label + ', 200x200x16 grid, bf16, batch 4 per GPU', 'n_gpus': world, 'unit': 'samples/s',
                     'scaling': 'weak',
                     'train_step': {'value': world * B / (ms_t * 1e-3), 'ms_per_step': ms_t, 'timed_passes': n_t, 'cuda_graph': False,
@@ -97,8 +110,8 @@ def main():
                                            'train() mode: image backbone + neck with batch-statistics BatchNorm (trained, as DHD-S.py '
                                            'does), view transformer, BEV / voxel encoders, SFA, head, four losses, backward through '
                                            'every module, ONE NCCL gradient all-reduce, clip 5, AdamW; eager launches'},
-                    'inference': {'value': world * B / (ms_i * 1e-3), 'ms_per_step': ms_i, 'timed_passes': n_i,
-                                  'what': 'DHD.simple_test: camera images -> list of (200, 200, 16) uint8 class maps (incl. D2H)'}})
+                    'inference': dict(inf, value=world * B / (inf['ms_per_step'] * 1e-3),
+                                      what='DHD.simple_test: camera images -> list of (200, 200, 16) uint8 class maps (incl. D2H)')})
         del step
         torch.cuda.empty_cache()
     if 'dhd_l' in which:
@@ -108,7 +121,7 @@ def main():
         img_inputs, kw = step.make_inputs(200 + rank)
         losses = step.train_step(img_inputs, kw)
         ms_t, n_t = timed(lambda: step.train_step(img_inputs, kw), 2.0, warm=2, kmin=3)
-        ms_i, n_i = timed(lambda: step.infer_step(img_inputs), 1.0, warm=2, kmin=3)
+        inf = timed_infer(step, img_inputs)
         out.append({'config': 'BASELINE configs[4] DHD-L: 6-cam 512x1408 (32x88x512 image features, 128-ch stereo features at 128x352), '
                               'D=88, two temporal frames + stereo reference frame, 200x200x16 grid, bf16, batch 2 per GPU '
                               '(DHD-L.py samples_per_gpu; Swin-B + FPN are outside the hot path: synthetic per-frame features)',
@@ -119,8 +132,9 @@ def main():
                                            'gradients (stereo cost volume, camera-aware DepthNet + HeightNet, fused pool fwd/bwd, '
                                            'pre-process nets, BEV encoder, three UNets, SFA, head, five losses), previous frame under '
                                            'no_grad, backward, ONE NCCL gradient all-reduce, clip 5, AdamW; eager launches'},
-                    'inference': {'value': world * B / (ms_i * 1e-3), 'ms_per_step': ms_i, 'timed_passes': n_i,
-                                  'what': 'DHD_stereo.simple_test: per-frame features -> list of (200, 200, 16) uint8 class maps (incl. D2H)'}})
+                    'inference': dict(inf, value=world * B / (inf['ms_per_step'] * 1e-3),
+                                      what='DHD_stereo.simple_test (bf16 NHWC activation path): per-frame features -> list of '
+                                           '(200, 200, 16) uint8 class maps (incl. D2H)')})
     if rank == 0:
         for o in out:
             print(json.dumps(o), flush=True)
