@@ -182,9 +182,49 @@ class DHD(C.BaseModule):
 
     def simple_test(self, points, img_metas, img=None, rescale=False, to_host=True, **kwargs):
         """DM:207-226 -> list of (Dx, Dy, Dz) uint8 class maps.  to_host=False: the (B, Dx, Dy, Dz) uint8 DEVICE tensor
-        instead (no synchronisation: what a CUDA-graph capture of the step needs, dhd_b200.detector_step)."""
+        instead (no synchronisation: what a CUDA-graph capture of the step needs, dhd_b200.detector_step).
+        In the bf16 speed mode the chain pool -> encoders -> SFA -> head runs on bf16 NHWC activations end to end
+        (`act_path = False` or DHD_ACT_PATH=0 selects the module-by-module tensor path of the reference's code)."""
+        if type(self) is DHD and self._dhd_act_path_ok():
+            with torch.no_grad():
+                occ = self.occ_head.forward_occ(self.mix(self._extract_acts(img), return_act=True))
+            return self.occ_head.get_occ(occ, img_metas) if to_host else occ
         x_2d, x_3d, _, _, _ = self.extract_feat(points, img_inputs=img, img_metas=img_metas, **kwargs)
         return self.simple_test_occ([x_2d, x_3d], img_metas, to_host=to_host)
+
+    def _dhd_act_path_ok(self):
+        import os
+        if os.environ.get('DHD_ACT_PATH', '1') == '0' or not getattr(self, 'act_path', True) or self.training:
+            return False
+        vt = self.img_view_transformer
+        mods = [vt, self.img_bev_encoder_backbone, self.img_bev_encoder_neck, self.mix, self.occ_head] + \
+            [getattr(self, 'img_voxel_encoder%d' % i, None) for i in range(3)]
+        if any(m is None or getattr(m, 'precision', None) != 'bf16' for m in mods) or not getattr(vt, 'collapse_z', False):
+            return False
+        if type(vt).__name__ != 'MGHS' or any(type(getattr(self, 'img_voxel_neck%d' % i, None)).__name__ != 'Identity'
+                                               for i in range(3)):
+            return False
+        widths = sum(getattr(self, 'img_voxel_encoder%d' % i).n_classes for i in range(3))
+        return widths == 256 and getattr(self.mix, 'mix_channels', None) == 512
+
+    def _extract_acts(self, img_inputs):
+        """extract_img_feat (DM:84-114) on activations: -> the SFA's 512-channel bf16 NHWC input, every encoder writing
+        its channel slice in place (the order of DM:103-114's cat: BEV encoder | voxel encoders 0, 1, 2)."""
+        from dhd_b200 import dense as D
+        imgs, sensor2keyegos, ego2globals, intrins, post_rots, post_trans, bda = self.prepare_inputs(list(img_inputs))
+        x, _ = self.image_encoder(imgs)
+        vt = self.img_view_transformer
+        cams = (sensor2keyegos, ego2globals, intrins, post_rots, post_trans, bda)
+        bev, _, _, low, mid, high = vt([x] + list(cams) + [vt.get_mlp_input(*cams)], return_act=True)
+        enc = D.Act.empty(bev.N, bev.H, bev.W, 512, 1, bev.data.device)
+        feats = self.img_bev_encoder_backbone(bev, return_act=True)
+        self.img_bev_encoder_neck(feats, return_act=True, out=enc.slice(0, 256))
+        lo = 256
+        for i, a in enumerate((low, mid, high)):
+            net = getattr(self, 'img_voxel_encoder%d' % i)
+            net(a, return_act=True, out=enc.slice(lo, lo + net.n_classes))
+            lo += net.n_classes
+        return enc
 
     def simple_test_occ(self, img_feats, img_metas=None, to_host=True):
         """DM:228-241: cat -> mix -> occ_head -> get_occ.  `img_feats` may also be the logits tensor itself (the

@@ -208,10 +208,12 @@ class MGHS(EngineOwner, BaseModule):
         self.initial_flag = not self.accelerate
         return plan
 
-    def view_transform(self, input, depth, tran_feat, height, feat_nhwc=None):
+    def view_transform(self, input, depth, tran_feat, height, feat_nhwc=None, return_act=False):
         """depth (B*N, D, fH, fW), tran_feat (B*N, C, fH, fW), height (B*N, H, fH, fW) ->
         (bev, depth, height, low, mid, high) like LH:407-459; the four BEV tensors have the
-        reference's logical shape (B, dz*C, Dy, Dx) [collapse_z] in `out_layout` memory."""
+        reference's logical shape (B, dz*C, Dy, Dx) [collapse_z] in `out_layout` memory.
+        return_act=True (inference, bf16 speed mode, collapse_z=True): the four BEV tensors come back as bf16 NHWC
+        activations (dhd_b200.dense.Act) written by the pool kernel itself."""
         B, N, _, H, W = input[0].shape
         if not depth.is_cuda:
             raise RuntimeError('dhd_b200: expected CUDA tensors (the hot path has no CPU fallback)')
@@ -219,7 +221,14 @@ class MGHS(EngineOwner, BaseModule):
         if feat_nhwc is None:
             feat_nhwc = tran_feat.view(B, N, self.out_channels, H, W).permute(0, 1, 3, 4, 2).contiguous()
         pixmask = height_to_mask(height, self.height_range, self.mask_range)
-        if self.collapse_z:
+        if return_act:
+            from dhd_b200 import dense as D
+            if not self.collapse_z or D.PRECISIONS[self.precision][0] != 1:
+                raise NotImplementedError('return_act=True: bf16 speed mode with collapse_z=True')
+            outs = plan.alloc_outputs('nhwc_bf16', depth.device)
+            plan.raw_forward(depth, feat_nhwc.view(B, N, H, W, self.out_channels), pixmask, outs, 'nhwc_bf16')
+            outs = [D.Act(o, o.shape[-1], 1) for o in outs]
+        elif self.collapse_z:
             outs = plan(depth, feat_nhwc.view(B, N, H, W, self.out_channels), pixmask, layout=self.out_layout)
             if self.out_layout == 'nhwc':
                 outs = [o.permute(0, 3, 1, 2) for o in outs]        # logical NCHW, channels_last memory
@@ -230,9 +239,9 @@ class MGHS(EngineOwner, BaseModule):
         self.create_grid_infos(**self.grid_config)
         return outs[0], depth, height, outs[1], outs[2], outs[3]
 
-    def forward(self, input, stereo_metas=None):
+    def forward(self, input, stereo_metas=None, return_act=False):
         """input = [x (B,N,C,fH,fW), sensor2egos, ego2globals, intrins, post_rots, post_trans, bda,
-        mlp_input] -> (bev, depth, height, low, mid, high), LH:461-490."""
+        mlp_input] -> (bev, depth, height, low, mid, high), LH:461-490 (return_act: see view_transform)."""
         from dhd_b200 import dense as D
         from dhd_b200.modules import DepthHeadEngine
         x = input[0]
@@ -242,6 +251,8 @@ class MGHS(EngineOwner, BaseModule):
             raise RuntimeError('dhd_b200: expected CUDA tensors (the hot path has no CPU fallback)')
         from dhd_b200 import autograd as A
         if A.wants_grad(self, x):
+            if return_act:
+                raise NotImplementedError('return_act=True is the inference hand-off')
             # differentiable form (training): forward with saved activations, backward through the pool backward,
             # depth_net and -- via the height distribution's gradient (get_height_loss) -- HeightNet
             if stereo_metas is not None or self.height_net.stereo:
@@ -259,7 +270,7 @@ class MGHS(EngineOwner, BaseModule):
                                         slot='_depth_engine')
             depth, feat = engine(xa)                                   # softmax-ed depth, NHWC context
             height = self.height_net(xa, mlp_input, stereo_metas, softmax=True)
-            return self.view_transform(input, depth, None, height, feat_nhwc=feat)
+            return self.view_transform(input, depth, None, height, feat_nhwc=feat, return_act=return_act)
 
     # ------------------------------------------------------------------ mlp input (LH:493-526)
     def get_mlp_input(self, sensor2ego, ego2global, intrin, post_rot, post_tran, bda):

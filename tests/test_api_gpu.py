@@ -291,3 +291,30 @@ def test_dhd_stereo_inference_act_path_equals_tensor_path(cuda_lib):
     agree = float((np.asarray(fast[0]) == np.asarray(slow[0])).mean())
     assert len(np.unique(np.asarray(slow[0]))) >= 2                       # a non-trivial class map
     assert agree >= 0.9995, agree
+
+
+def test_dhd_inference_act_path_and_cuda_graph_equal_the_tensor_path(cuda_lib):
+    """DHD.simple_test (DHD-S, bf16 speed mode): (1) the activation fast path (pool kernel -> bf16 NHWC activations ->
+    encoders writing channel slices of the SFA input) against the reference-shaped tensor path of extract_img_feat
+    (DM:84-114); (2) the whole step captured as ONE CUDA graph (DetectorStep.capture_infer: no host synchronisation left
+    in prepare_inputs / the view transformer) replays to exactly the eager result, also for new inputs."""
+    import projects.mmdet3d_plugin  # noqa: F401
+    from dhd_b200 import synth
+    from dhd_b200.detector_step import DetectorStep
+    step = DetectorStep(synth.dhd_s_model_cfg('bf16', images=False), 1, seed=3)
+    step.model.load_state_dict(DO.seeded_state_dict(step.model, 19))
+    a, _ = step.make_inputs(5)
+    b, _ = step.make_inputs(6)
+    model = step.model
+    assert model.eval()._dhd_act_path_ok()
+    fast = step.infer_step(a)
+    model.act_path = False
+    slow = step.infer_step(a)
+    model.act_path = True
+    agree = float((np.asarray(fast[0]) == np.asarray(slow[0])).mean())
+    assert fast[0].shape == (200, 200, 16) and len(np.unique(np.asarray(slow[0]))) >= 2 and agree >= 0.9995, agree
+    assert step.capture_infer(a), getattr(step, 'capture_error', '')
+    assert np.array_equal(step.infer_step_graphed()[0], fast[0])
+    want_b = step.infer_step(b)
+    assert not np.array_equal(want_b[0], fast[0])
+    assert np.array_equal(step.infer_step_graphed(b)[0], want_b[0])
