@@ -17,7 +17,8 @@ so the 1 -> 8 GPU curve measures a step that contains the collective.
 `cpu_baseline` / `--impl reference`: the CPU oracle port of the same training step (the
            reference has no CPU pool kernel; its Python + our C restatement) on the host cores.
 `extras` : inference (image features -> class map; bf16 and fp32 precision modes, e2e),
-           the widened steps with the real encoders, DHD-L, the reference CUDA path.
+           the widened steps with the real encoders, the plugin detector from camera images
+           (forward_train incl. the image backbone / simple_test), DHD-L, the reference CUDA path.
 """
 import argparse
 import json
@@ -330,6 +331,40 @@ def run_ours(args):
             'DHD-S end to end from the 6 x 256x704 camera images (img_backbone ResNet-50 + img_neck CustomFPN of DHD-S.py:44-62 '
             'on the tcgen05 convolution kernel, then the widened hot path with the real BEV / voxel encoders) to the uint8 '
             'class map; e2e = pinned host images in, class map out')
+    if world == 1 and not args.no_encoders and not args.no_train and not quick:
+        # (one GPU only: an extra that fails on one rank must not be able to hang a multi-rank run)
+        # the reference's own entry points on the whole DHD-S detector INCLUDING its image backbone / neck (DHD-S.py:44-62
+        # trains them): DHD.forward_train on camera images -> backward -> all-reduce -> clip -> AdamW, and DHD.simple_test
+        try:
+            from dhd_b200 import synth as _synth
+            from dhd_b200.detector_step import DetectorStep
+            dstep = DetectorStep(_synth.dhd_s_model_cfg(args.precision if args.precision == 'bf16' else 'bf16', images=True), B,
+                                 seed=rank)
+            d_in, d_kw = dstep.make_inputs(300 + rank)
+            for _ in range(2):
+                d_losses = dstep.train_step(d_in, d_kw)
+            ms, n, _, _ = _region(lambda ev: dstep.train_step(d_in, d_kw), 3, 0.5, barrier, st, shard)
+            ms = shard.max_over_ranks([ms], device='cuda')[0]
+            det = {'train_ms_per_step': ms / n, 'train_samples_per_s': world * B * n / (ms * 1e-3), 'train_timed_passes': n,
+                   'trainable_params': dstep.n_params, 'gradient_all_reduce_bytes': dstep.n_params * 4,
+                   'losses': {k: float(v) for k, v in d_losses.items()}, 'train_cuda_graph': False}
+            graphed = dstep.capture_infer(d_in)
+            run_inf = (lambda ev: dstep.infer_step_graphed()) if graphed else (lambda ev: dstep.infer_step(d_in))
+            for _ in range(2):
+                run_inf(None)
+            ms, n, _, _ = _region(run_inf, 5, 0.3, barrier, st, shard)
+            ms = shard.max_over_ranks([ms], device='cuda')[0]
+            det.update(infer_ms_per_step=ms / n, infer_samples_per_s=world * B * n / (ms * 1e-3), infer_cuda_graph=bool(graphed),
+                       what='the plugin DETECTOR driven the way the reference runner drives it, from 6 x 256x704 camera images: '
+                            'DHD.forward_train (DHD_model.py:135-186; ResNet-50 + CustomFPN with batch-statistics BatchNorm and a '
+                            'hand-written backward, view transformer, encoders, SFA, head, four losses) + backward + NCCL gradient '
+                            'all-reduce + clip 5 + AdamW, eager launches through dhd_b200.autograd; and DHD.simple_test (bf16 NHWC '
+                            'activation path, the whole call as one CUDA graph, class maps copied to the host)')
+            extras['detector_api_from_images'] = det
+            del dstep, d_in, d_kw
+        except Exception as e:  # noqa: BLE001 -- an extra must never cost the bench line
+            extras['detector_api_from_images'] = {'error': '%s: %s' % (type(e).__name__, str(e)[:300])}
+        torch.cuda.empty_cache()
     if world == 1 and not args.no_dhdl:
         extras['dhd_l_view_transformer'] = dhdl_extra(args.precision if args.precision in ('bf16', 'fp32') else 'bf16')
     if world == 1 and not quick:

@@ -367,6 +367,20 @@ class DHD_stereo(DHD):
         x_3d = torch.cat([self.voxel_encoder(i, self._collapse_z(s)) for i, s in enumerate(slabs)], dim=1)
         return x_2d, x_3d
 
+    @staticmethod
+    def _frames_to_bev_rows(rows_2d):
+        """Per-frame (B, H, W, C) rows -> the BEV encoder's (B, H, W, F*C) input: `collapse_z(cat(frames, dim=1))` of
+        DM:517-541 for the one-plane tensors, channels-last."""
+        return torch.cat(list(rows_2d), dim=-1).contiguous()
+
+    @staticmethod
+    def _frames_to_slab_rows(rows_3d, C, z0, z1):
+        """Per-frame (B, H, W, nz*C) rows (channel = z*C + c) -> the voxel encoder input of the z slab [z0, z1):
+        `collapse_z(cat(frames, dim=1)[:, :, z0:z1])`, i.e. channel = (z - z0)*(F*C) + f*C + c, channels-last."""
+        B, H, W, ZC = rows_3d[0].shape
+        planes = torch.stack([r.reshape(B, H, W, ZC // C, C) for r in rows_3d], dim=4)       # (B, H, W, z, frame, C)
+        return planes[:, :, :, z0:z1].reshape(B, H, W, -1).contiguous()
+
     def _fuse_frames_acts(self, acts_2d, acts_3d):
         """fuse_frames on bf16 NHWC activations (channel = z*C + c per frame) -> the SFA's 512-channel input, every
         encoder writing its channel slice in place.  Channel orders as the reference's cat / unbind produce them: frames
@@ -377,14 +391,14 @@ class DHD_stereo(DHD):
         B, H, W, dev = a0.N, a0.H, a0.W, a0.data.device
         C = acts_2d[0].C                                                  # channels per z plane
         nz = a0.C // C
-        x2 = torch.cat([rows(a) for a in acts_2d], dim=-1).contiguous()
-        planes = torch.stack([rows(a).reshape(B, H, W, nz, C) for a in acts_3d], dim=4)      # (B, H, W, z, frame, C)
+        x2 = self._frames_to_bev_rows([rows(a) for a in acts_2d])
+        rows_3d = [rows(a) for a in acts_3d]
         enc = D.Act.empty(B, H, W, 512, 1, dev)
         feats = self.img_bev_encoder_backbone(D.Act(x2, x2.shape[-1], 1), return_act=True)
         self.img_bev_encoder_neck(feats, return_act=True, out=enc.slice(0, 256))
         lo = 256
         for i, (z0, z1) in enumerate(((0, 4), (4, 8), (8, nz))):
-            slab = planes[:, :, :, z0:z1].reshape(B, H, W, -1).contiguous()
+            slab = self._frames_to_slab_rows(rows_3d, C, z0, z1)
             net = getattr(self, 'img_voxel_encoder%d' % i)
             net(D.Act(slab, slab.shape[-1], 1), return_act=True, out=enc.slice(lo, lo + net.n_classes))
             lo += net.n_classes
