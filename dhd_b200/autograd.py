@@ -53,7 +53,8 @@ def trainer_of(module, factory, device, batch_bn=None):
             T.set_bn_mode('frozen')
         module.__dict__['_trainer'] = slot = [key, tr, versions]
     elif slot[2] != versions:
-        slot[1].refresh()
+        with T.batched_repack():                     # the bf16 re-pack of all the module's layers in a few launches
+            slot[1].refresh()
         slot[2] = versions
     return slot[1]
 
