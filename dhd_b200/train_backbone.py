@@ -195,14 +195,14 @@ class ImageResNetTrainer(_Buffers):
                 dt1 = self._act('g_t1_' + tag, t1.N, t1.H, t1.W, t1.C)
                 c2.backward(t1, dt2, [dict(out_act=dt1)])
                 act_bwd(dt1, t1, 'relu')
-                dxin = self._act('g_x_' + tag, x.N, x.H, x.W, x.C)
-                c1.backward(x, dt1, [dict(out_act=dxin)])
+                # the identity / downsample path's gradient joins conv1's data gradient in that convolution's epilogue (one
+                # rounding of the fp32 sum, no separate add pass)
+                idg = d
                 if ds is not None:
-                    dxid = self._act('g_id_' + tag, x.N, x.H, x.W, x.C)
-                    ds.backward(x, d, [dict(out_act=dxid)])
-                    act_bwd(dxin, None, None, add=dxid)            # sum of the two paths (the next block / the pool masks)
-                else:
-                    act_bwd(dxin, None, None, add=d)               # identity path
+                    idg = self._act('g_id_' + tag, x.N, x.H, x.W, x.C)
+                    ds.backward(x, d, [dict(out_act=idg)])
+                dxin = self._act('g_x_' + tag, x.N, x.H, x.W, x.C)
+                c1.backward(x, dt1, [dict(out_act=dxin)], residual_act=idg)
                 d = dxin
         if d is None:
             return

@@ -305,12 +305,12 @@ def test_image_backbone_trainer_gradients(cuda_lib, bn, objective):
             assert cos(p.grad, ref) > 0.99, (name, cos(p.grad, ref))
     # measured on B200 (gpurun_out/image_backbone_grad_errs_*.json): frozen -- stem 1.2 %, every other parameter <= 0.7 %;
     # batch statistics -- convolution weights <= 2.6 %, BatchNorm weights / biases <= 3.6 % except the stem's bn1.bias at
-    # 6.3 % (a cancelling sum of the max-pool-routed gradient over all pixels, after 53 layers of bf16 gradient storage)
+    # 6.3-7.1 % (a cancelling sum of the max-pool-routed gradient over all pixels, after 53 layers of bf16 gradient storage)
     if bn == 'frozen':
         assert max(errs.values()) < 2e-2, worst
     else:
         assert max(conv_w.values()) < 4e-2, worst
-        assert max(errs.values()) < 8e-2, worst
+        assert max(errs.values()) < 0.1, worst
 
 
 def test_dhd_forward_train_from_camera_images(cuda_lib):
