@@ -90,6 +90,7 @@ _SIGNATURES = {
     'dhd_launch_count': (ctypes.c_long, []),
     'dhd_maxpool3s2_bwd': (ctypes.c_int, [_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _P]),
     'dhd_bn_apply_res16': (ctypes.c_int, [_P, _I, _I, ctypes.c_long, _I, _P, _P, _I, _P, _I, _I, _P, _I, _I, _P]),
+    'dhd_upsample_bilinear_bwd_gather': (ctypes.c_int, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, _I, _P, _P]),
     'dhd_maxpool2_bwd': (ctypes.c_int, [_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _P]),
     'dhd_upsample_bilinear_bwd': (ctypes.c_int, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     'dhd_maxpool2': (ctypes.c_int, [_P] + [_I] * 7 + [_P, _I, _I, _I, _I, _P]),

@@ -27,6 +27,8 @@ import os as _os
 FUSED_BN_STATS = _os.environ.get('DHD_FUSED_BN_STATS', '1') != '0'
 # the occupancy head's Linear + Softplus + Linear in training: one fused launch (True) or two convolution launches (A/B)
 FUSED_TAIL = _os.environ.get('DHD_TRAIN_FUSED_TAIL', '1') != '0'
+# bilinear up-sampling backward (FPN_LSS): deterministic gather kernel writing bf16 (True) or the atomic scatter into fp32 (A/B)
+UPSAMPLE_BWD_GATHER = _os.environ.get('DHD_UPSAMPLE_BWD_GATHER', '1') != '0'
 # SFA backward: dL/dx collected in bf16 activations (True) or in fp32 tensors (A/B)
 SFA_BF16_DX = _os.environ.get('DHD_SFA_BF16_DX', '1') != '0'
 
@@ -1492,11 +1494,8 @@ class FPNLSSTrainer:
         act_bwd(dw_, w, 'relu')
         dv = self._act('g_v', N, v.H, v.W, v.C)
         self.c3.backward(v, dw_, [dict(out_act=dv)])
-        du32 = self._f32('g_u32', N, u.H, u.W, u.C)
-        _lib.check(lib.dhd_upsample_bilinear_bwd(_p(dv.data), dv.ld, dv.coff, N, u.H, u.W, u.C, v.H, v.W, _p(du32),
-                                                 _stream()), 'upsample_bwd')
         du = self._act('g_u', N, u.H, u.W, u.C)
-        _lib.check(lib.dhd_add_rowvec(_p(du32), None, N, u.H * u.W, u.C, _p(du.data), du.ld, du.coff, _stream()), 'f32->bf16')
+        self._upsample_bwd(dv, u, v.H, v.W, du, 'g_u32')
         act_bwd(du, u, 'relu')
         dt = self._act('g_t', N, t.H, t.W, t.C)
         self.c2.backward(t, du, [dict(out_act=dt)])
@@ -1504,10 +1503,20 @@ class FPNLSSTrainer:
         dcat = self._act('g_cat', N, cat.H, cat.W, cat.C)
         self.c1.backward(cat, dt, [dict(out_act=dcat)])
         d2 = dcat.slice(0, x2.C)                                    # identity "up-sampling": the slice is the gradient
-        d1_32 = self._f32('g_x1_32', N, x1.H, x1.W, x1.C)
         up = dcat.slice(x2.C, x2.C + x1.C)
-        _lib.check(lib.dhd_upsample_bilinear_bwd(_p(up.data), up.ld, up.coff, N, x1.H, x1.W, x1.C, cat.H, cat.W,
-                                                 _p(d1_32), _stream()), 'upsample_bwd')
         d1 = self._act('g_x1', N, x1.H, x1.W, x1.C)
-        _lib.check(lib.dhd_add_rowvec(_p(d1_32), None, N, x1.H * x1.W, x1.C, _p(d1.data), d1.ld, d1.coff, _stream()), 'f32->bf16')
+        self._upsample_bwd(up, x1, cat.H, cat.W, d1, 'g_x1_32')
         return {self.idx[0]: d2, self.idx[1]: d1}
+
+    def _upsample_bwd(self, dy, src, out_H, out_W, dx, scratch):
+        """dx (bf16 Act, the shape of `src`) = backward of the bilinear up-sampling of `src` to out_H x out_W at dy."""
+        lib = _lib.load()
+        N = src.N
+        if UPSAMPLE_BWD_GATHER:
+            _lib.check(lib.dhd_upsample_bilinear_bwd_gather(_p(dy.data), dy.ld, dy.coff, N, src.H, src.W, src.C, out_H, out_W,
+                                                            _p(dx.data), dx.ld, dx.coff, None, _stream()), 'upsample_bwd_gather')
+            return
+        d32 = self._f32(scratch, N, src.H, src.W, src.C)
+        _lib.check(lib.dhd_upsample_bilinear_bwd(_p(dy.data), dy.ld, dy.coff, N, src.H, src.W, src.C, out_H, out_W, _p(d32),
+                                                 _stream()), 'upsample_bwd')
+        _lib.check(lib.dhd_add_rowvec(_p(d32), None, N, src.H * src.W, src.C, _p(dx.data), dx.ld, dx.coff, _stream()), 'f32->bf16')

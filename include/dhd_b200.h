@@ -520,6 +520,10 @@ int dhd_maxpool2_bwd(const void* x, int x_ld, int x_coff, const void* dy, int dy
                      int C, void* dx, int dx_ld, int dx_coff, void* stream);
 int dhd_upsample_bilinear_bwd(const void* dy, int dy_ld, int dy_coff, int N, int H, int W, int C, int out_H, int out_W,
                               float* dx, void* stream);
+/* the same backward in gather form (one thread per input pixel, fixed summation order): deterministic, no atomics, no
+ * zero-fill; dx written once as bf16 rows (dx_b16, dx_ld, dx_coff) and / or fp32 [N*H*W][C] (dx_f32) */
+int dhd_upsample_bilinear_bwd_gather(const void* dy, int dy_ld, int dy_coff, int N, int H, int W, int C, int out_H,
+                                     int out_W, void* dx_b16, int dx_ld, int dx_coff, float* dx_f32, void* stream);
 /* MaxPool2d(kernel 3, stride 2, padding 1) backward (mmdet ResNet.maxpool when the image backbone trains, DHD-S.py:44-55
  * `norm_eval=False, frozen_stages=-1`): x (N, H, W, C) is the pool's bf16 input, dy (N, oH, oW, C) the gradient of its
  * output, dx (N, H, W, C) is written completely.  The gradient of a window goes to its first maximum in scan order

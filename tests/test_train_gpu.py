@@ -628,6 +628,18 @@ def test_encoder_backward_primitives_unit(cuda_lib):
     dxf = torch.empty(1, 5, 7, 64, device='cuda')
     _lib.check(lib.dhd_upsample_bilinear_bwd(p(ga.data), ga.ld, ga.coff, 1, 5, 7, 64, 20, 28, p(dxf), st), 'upsample_bwd')
     assert rel(dxf.permute(0, 3, 1, 2), xr.grad) < 1e-5
+    # ---- the same backward in gather form (deterministic, no atomics): x4, x2, a non-integer ratio and a one-pixel axis
+    for (h, w, oh, ow) in ((5, 7, 20, 28), (25, 25, 50, 50), (6, 9, 13, 20), (1, 4, 3, 9), (3, 1, 7, 1)):
+        x = bf(torch.randn(2, 64, h, w, generator=g))
+        gy = bf(torch.randn(2, 64, oh, ow, generator=g))
+        xr = x.clone().requires_grad_()
+        (F.interpolate(xr, size=(oh, ow), mode='bilinear', align_corners=True) * gy).sum().backward()
+        ga = D.pack_input(gy.cuda(), 1)
+        d16, d32 = D.Act.empty(2, h, w, 64, 1, 'cuda'), torch.empty(2, h, w, 64, device='cuda')
+        _lib.check(lib.dhd_upsample_bilinear_bwd_gather(p(ga.data), ga.ld, ga.coff, 2, h, w, 64, oh, ow, p(d16.data), d16.ld,
+                                                        d16.coff, p(d32), st), 'upsample_bwd_gather')
+        assert rel(d32.permute(0, 3, 1, 2).cpu(), xr.grad) < 1e-5, (h, w, oh, ow)
+        assert torch.equal(d16.float().cpu(), d32.permute(0, 3, 1, 2).cpu().bfloat16().float())
 
 
 @pytest.mark.parametrize('objective', ['random', 'coherent'])
