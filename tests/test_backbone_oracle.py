@@ -84,3 +84,56 @@ def test_plugin_backbone_and_neck_names_and_registry():
                                              'fpn_convs.0.conv.weight', 'fpn_convs.0.conv.bias'}
     with pytest.raises(RuntimeError):
         net.eval()(torch.zeros(1, 3, 64, 64))             # CPU tensors: no fallback
+
+
+def test_oracle_resnet_training_mode_and_gradients_match_torchvision():
+    """The reference of the image-backbone TRAINING parity tests (tests/test_backbone_gpu.py) is torch autograd over
+    `image_resnet_forward` with BN_TRAIN (batch statistics: mmdet's train() with norm_eval=False).  Pinned here: outputs
+    and every parameter gradient equal torchvision's ResNet-50 in train() mode on the same weights and image, and the
+    reference CustomFPN's gradients likewise (when /root/reference is present)."""
+    torchvision = pytest.importorskip('torchvision')
+    net = torchvision.models.resnet50(weights=None)
+    sd0 = MG.backbone_state_dict(net)
+    net.load_state_dict(sd0)
+    net.train()
+    img = DO.seeded_tensor((2, 3, 64, 96), 31)
+    x = net.maxpool(net.relu(net.bn1(net.conv1(img))))
+    c4 = net.layer3(net.layer2(net.layer1(x)))
+    c5 = net.layer4(c4)
+    (0.5 * (c4 * c4).sum() + 0.5 * (c5 * c5).sum()).backward()
+    sd = {k: v.clone().requires_grad_(v.dtype.is_floating_point and 'running' not in k) for k, v in sd0.items()}
+    DO.BN_TRAIN = True
+    try:
+        o4, o5 = DO.image_resnet_forward(sd, img, depth=50, out_indices=(2, 3))
+    finally:
+        DO.BN_TRAIN = False
+    assert torch.allclose(o4, c4, atol=1e-4, rtol=1e-4) and torch.allclose(o5, c5, atol=1e-4, rtol=1e-4)
+    (0.5 * (o4 * o4).sum() + 0.5 * (o5 * o5).sum()).backward()
+    worst = 0.0
+    for name, p in net.named_parameters():
+        if name.startswith('fc.'):
+            continue
+        g = sd[name].grad
+        assert g is not None, name
+        worst = max(worst, float((g - p.grad).norm() / p.grad.norm().clamp_min(1e-12)))
+    assert worst < 1e-3, worst                            # fp32 summation order only
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason='reference tree not present')
+def test_oracle_custom_fpn_gradients_match_the_unmodified_reference():
+    ref = ref_loader.load_reference()
+    neck = ref.CustomFPN(in_channels=[1024, 2048], out_channels=256, num_outs=1, start_level=0, out_ids=[0])
+    sd0 = DO.seeded_state_dict(neck, MG.SEEDS['neck'])
+    neck.load_state_dict(sd0)
+    c4 = DO.seeded_tensor((2, 1024, 6, 10), 5).requires_grad_()
+    c5 = DO.seeded_tensor((2, 2048, 3, 5), 6).requires_grad_()
+    out = neck([c4, c5])[0]
+    (0.5 * (out * out).sum()).backward()
+    sd = {k: v.clone().requires_grad_() for k, v in sd0.items()}
+    a4, a5 = c4.detach().clone().requires_grad_(), c5.detach().clone().requires_grad_()
+    got = DO.custom_fpn_forward(sd, [a4, a5], out_ids=(0,), start_level=0)[0]
+    (0.5 * (got * got).sum()).backward()
+    rel = lambda a, b: float((a - b).norm() / b.norm().clamp_min(1e-12))
+    for name, p in neck.named_parameters():
+        assert rel(sd[name].grad, p.grad) < 1e-4, name
+    assert rel(a4.grad, c4.grad) < 1e-4 and rel(a5.grad, c5.grad) < 1e-4
