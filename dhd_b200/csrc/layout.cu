@@ -605,7 +605,7 @@ maxpool3s2_kernel(const __nv_bfloat16* __restrict__ in, int in_ld, int in_coff, 
 // relu_mask: x is the ReLU output that fed the pool -- the gradient is also multiplied by [x > 0] (the stem's ReLU
 // backward fused into this pass).
 __global__ void __launch_bounds__(256)
-maxpool3s2_bwd_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int x_coff, const __nv_bfloat16* __restrict__ dy,
+maxpool3s2_bwd_ref_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int x_coff, const __nv_bfloat16* __restrict__ dy,
                       int dy_ld, int dy_coff, int N, int H, int W, int C, int oH, int oW, __nv_bfloat16* __restrict__ dx,
                       int dx_ld, int dx_coff, int relu_mask) {
   const int cg = C / 8;
@@ -655,6 +655,62 @@ maxpool3s2_bwd_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int x_coff,
 #pragma unroll
     for (int j = 0; j < 8; ++j)
       if (!(v[j] > 0.f)) r[j] = 0.f;
+  }
+  store_parts8(dx + (((size_t)n * H + yy) * W + xx) * dx_ld + dx_coff + c, r, 1, 0);
+}
+
+// The same result with packed bf16x2 compares and no arg-max bookkeeping (ncu of the kernel above, profiles/
+// r02_maxpool3s2_bwd_full.txt: instruction-bound, 559 M warp instructions, the bf16 -> fp32 unpacking of 36 taps per
+// thread on top): this pixel (tap k of window o) is the window's FIRST maximum iff it is > every earlier tap and >= every
+// later one, so each of the 8 other taps costs one 16-byte load and four `set.{gt,ge}.bf16x2` + AND per 8 channels.
+__global__ void __launch_bounds__(256)
+maxpool3s2_bwd_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int x_coff, const __nv_bfloat16* __restrict__ dy,
+                      int dy_ld, int dy_coff, int N, int H, int W, int C, int oH, int oW, __nv_bfloat16* __restrict__ dx,
+                      int dx_ld, int dx_coff, int relu_mask) {
+  const int cg = C / 8;
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)N * H * W * cg) return;
+  int c, xx, yy;
+  long p = fast_div(i, cg, &c);
+  c *= 8;
+  p = fast_div(p, W, &xx);
+  const int n = (int)fast_div(p, H, &yy);
+  const __nv_bfloat16* img = x + (size_t)n * H * W * x_ld + x_coff + c;
+  const uint4 me4 = __ldg(reinterpret_cast<const uint4*>(img + ((size_t)yy * W + xx) * x_ld));
+  const __nv_bfloat162* me = reinterpret_cast<const __nv_bfloat162*>(&me4);
+  float r[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) r[j] = 0.f;
+  const int oy1 = min((yy + 1) >> 1, oH - 1), ox1 = min((xx + 1) >> 1, oW - 1);
+  for (int oy = yy >> 1; oy <= oy1; ++oy)
+    for (int ox = xx >> 1; ox <= ox1; ++ox) {
+      const int k = (yy - (2 * oy - 1)) * 3 + (xx - (2 * ox - 1));       // this pixel's place in the window's scan
+      unsigned ok[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+#pragma unroll
+      for (int j = 0; j < 9; ++j) {
+        const int iy = 2 * oy - 1 + j / 3, ix = 2 * ox - 1 + j % 3;
+        if (j == k || iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
+        const uint4 q4 = __ldg(reinterpret_cast<const uint4*>(img + ((size_t)iy * W + ix) * x_ld));
+        const __nv_bfloat162* q = reinterpret_cast<const __nv_bfloat162*>(&q4);
+#pragma unroll
+        for (int h = 0; h < 4; ++h) ok[h] &= j < k ? __hgt2_mask(me[h], q[h]) : __hge2_mask(me[h], q[h]);
+      }
+      float g[8];
+      load_parts8(dy + (((size_t)n * oH + oy) * oW + ox) * dy_ld + dy_coff + c, 1, 0, g);
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        if (ok[h] & 0xffffu) r[2 * h] += g[2 * h];
+        if (ok[h] >> 16) r[2 * h + 1] += g[2 * h + 1];
+      }
+    }
+  if (relu_mask) {
+    const __nv_bfloat162 zero = __floats2bfloat162_rn(0.f, 0.f);
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      const unsigned pos = __hgt2_mask(me[h], zero);
+      if (!(pos & 0xffffu)) r[2 * h] = 0.f;
+      if (!(pos >> 16)) r[2 * h + 1] = 0.f;
+    }
   }
   store_parts8(dx + (((size_t)n * H + yy) * W + xx) * dx_ld + dx_coff + c, r, 1, 0);
 }
@@ -1390,7 +1446,11 @@ extern "C" int dhd_maxpool3s2_bwd(const void* x, int x_ld, int x_coff, const voi
               "needs C % 8 == 0 and 16-byte aligned rows");
   const int oH = (H - 1) / 2 + 1, oW = (W - 1) / 2 + 1;
   const long total = (long)N * H * W * (C / 8);
-  maxpool3s2_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+  static const bool ref = [] {                          // DHD_MAXPOOL_BWD=ref: the first (arg-max bookkeeping) kernel (A/B)
+    const char* e = getenv("DHD_MAXPOOL_BWD");
+    return e != nullptr && e[0] == 'r';
+  }();
+  (ref ? maxpool3s2_bwd_ref_kernel : maxpool3s2_bwd_kernel)<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)x, x_ld, x_coff, (const __nv_bfloat16*)dy, dy_ld, dy_coff, N, H, W, C, oH, oW,
       (__nv_bfloat16*)dx, dx_ld, dx_coff, relu_mask);
   DHD_CUDA_LAUNCH_CHECK("maxpool3s2_bwd");
