@@ -519,3 +519,31 @@ def test_stereo_oracle_equals_live_reference_on_random_rigs(seed, bias, C, D):
     assert torch.equal(grid, ref_grid)
     assert torch.allclose(cv, ref_cv, rtol=1e-5, atol=1e-7)
     assert torch.allclose(cv.sum(1), torch.ones_like(cv[:, 0]), atol=1e-5)
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason='reference tree not present')
+def test_synth_dhd_s_model_cfg_is_the_reference_config():
+    """dhd_b200.synth.dhd_s_model_cfg(images=True) -- what bench.py / scripts/bench_configs.py build on the GPU box, where
+    the reference tree is absent -- is `model` of the unchanged projects/configs/DHD/DHD-S.py: every entry of ours equals
+    the reference's (ours adds only the `precision` switch; entries ours leaves out are defaults / train_cfg)."""
+    from dhd_b200 import compat as C
+    from dhd_b200 import synth
+    cfg = C.Config.fromfile(os.path.join(ref_loader.load_reference_configs(), 'DHD-S.py'))
+    ref = cfg.model
+    ref = ref.to_dict() if hasattr(ref, 'to_dict') else dict(ref)
+    ours = synth.dhd_s_model_cfg('bf16', images=True)
+    norm = lambda v: {k: norm(x) for k, x in v.items()} if isinstance(v, dict) else \
+        ([norm(x) for x in v] if isinstance(v, (list, tuple)) else v)
+
+    def check(a, b, path):
+        """every key of ours (a) except `precision` exists in the reference (b) with the same value"""
+        for k, v in a.items():
+            if k == 'precision':
+                continue
+            assert k in b, path + k
+            if isinstance(v, dict):
+                check(v, norm(b[k]), path + k + '.')
+            else:
+                assert norm(v) == norm(b[k]), (path + k, v, b[k])
+    check(norm(ours), norm(ref), 'model.')
+    assert set(k for k in ref if k not in ours) <= {'train_cfg', 'test_cfg', 'pretrained', 'upsample'}
