@@ -547,3 +547,31 @@ def test_synth_dhd_s_model_cfg_is_the_reference_config():
                 assert norm(v) == norm(b[k]), (path + k, v, b[k])
     check(norm(ours), norm(ref), 'model.')
     assert set(k for k in ref if k not in ours) <= {'train_cfg', 'test_cfg', 'pretrained', 'upsample'}
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason='reference tree not present')
+def test_synth_dhd_l_model_cfg_is_the_reference_config():
+    """dhd_b200.synth.dhd_l_model_cfg() (scripts/bench_configs.py dhd_l, BASELINE configs[4]) against `model` of the
+    unchanged projects/configs/DHD/DHD-L.py: every entry of ours equals the reference's; ours leaves out the image
+    backbone / neck (Swin-B + FPN_LSS) and adds the `precision` switch."""
+    from dhd_b200 import compat as C
+    from dhd_b200 import synth
+    cfg = C.Config.fromfile(os.path.join(ref_loader.load_reference_configs(), 'DHD-L.py'))
+    ref = cfg.model
+    ref = ref.to_dict() if hasattr(ref, 'to_dict') else dict(ref)
+    ours = synth.dhd_l_model_cfg('bf16')
+    norm = lambda v: {k: norm(x) for k, x in v.items()} if isinstance(v, dict) else \
+        ([norm(x) for x in v] if isinstance(v, (list, tuple)) else v)
+
+    def check(a, b, path):
+        for k, v in a.items():
+            if k == 'precision':
+                continue
+            assert k in b, path + k
+            if isinstance(v, dict):
+                check(v, norm(b[k]), path + k + '.')
+            else:
+                assert norm(v) == norm(b[k]), (path + k, v, b[k])
+    check(norm(ours), norm(ref), 'model.')
+    assert set(k for k in ref if k not in ours) <= {'img_backbone', 'img_neck', 'train_cfg', 'test_cfg', 'pretrained', 'upsample',
+                                                    'with_prev'}
